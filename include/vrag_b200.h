@@ -1,0 +1,118 @@
+/*
+ * vrag_b200.h — C ABI of libvrag_b200.so: a B200 (sm_100a) GPU-resident corpus store and the
+ * multi-stage retrieval scoring / indexing-time pooling kernels of visual-rag-toolkit.
+ *
+ * The reference (pure Python) has no FFI; its plug-in seam for this path is the duck-typed
+ * `qdrant_client` object handed to the retrievers plus the module-level pooling functions.  Every
+ * entry point below names the reference interface it replaces (paths relative to the reference
+ * repository root).  The Python host layer in visual-rag-toolkit_b200/visual_rag_b200 binds these
+ * with ctypes; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; vrag_last_error() returns a
+ *     thread-local message for the last failure on the calling thread.
+ *   - plain pointers and sizes only.  "host" pointers are ordinary CPU memory borrowed for the
+ *     duration of the call; "dev" pointers are CUDA device pointers on the corpus' device.
+ *   - all device memory behind a vrag_corpus_t is owned by the library.
+ *   - embedding dim is 128 everywhere (visual_rag/indexing/qdrant_indexer.py:133).
+ *   - page ids are int64 "global page ids": shard-local page index + page_base of the shard.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef VRAG_B200_H
+#define VRAG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vrag_corpus vrag_corpus_t;
+
+/* dtype codes for row data handed to the library */
+#define VRAG_F16 0
+#define VRAG_F32 1
+
+/* query flags */
+#define VRAG_Q_NORMALIZE 1u  /* L2-normalise query rows and document rows (cosine); pooling.py:495-503 */
+#define VRAG_Q_POOL 2u       /* mean-pool the query tokens to one row first; two_stage.py:142,148,154 */
+
+const char* vrag_last_error(void);
+int vrag_abi_version(void);
+
+/* ------------------------------------------------------------------ corpus store
+ * Replaces the Qdrant collection with named vectors created by
+ * QdrantIndexer.create_collection (visual_rag/indexing/qdrant_indexer.py:200-239): one named
+ * multi-vector store per name ("initial", "mean_pooling", "experimental_pooling*", "global_pooling"),
+ * fp16 rows resident in HBM, variable rows per page.                                              */
+int vrag_corpus_create(int device, int64_t page_base, vrag_corpus_t** out);
+int vrag_corpus_destroy(vrag_corpus_t* c);
+
+/* Add (or replace) a named store.  rows: [total_rows,128] of `dtype` (fp32 is cast to fp16 exactly like
+ * QdrantIndexer._build_qdrant_points, qdrant_indexer.py:423-441).  Either fixed_rows > 0 (every page has
+ * that many rows) or page_offsets[n_pages+1] (host, int64 row offsets) describes the pages.
+ * rows_on_device != 0: `rows` is a device pointer (copied device-to-device).                      */
+int vrag_store_add(vrag_corpus_t* c, const char* name, const void* rows, int dtype, int rows_on_device,
+                   const int64_t* page_offsets, int64_t n_pages, int64_t fixed_rows);
+
+/* Fill a named store with the seeded synthetic corpus of SURVEY.md 8(d) directly on the device
+ * (gaussian rows, L2-normalised, rounded to fp16).  Row r of the store depends only on (seed, row_seed_base + r). */
+int vrag_store_add_synthetic(vrag_corpus_t* c, const char* name, const int64_t* page_offsets, int64_t n_pages,
+                             int64_t fixed_rows, uint64_t seed, int64_t row_seed_base);
+
+int vrag_store_info(vrag_corpus_t* c, const char* name, int64_t* n_pages, int64_t* total_rows,
+                    int64_t* fixed_rows, int64_t* max_rows);
+/* Copy rows [row0,row0+n_rows) of a store to host as fp16 (qdrant `retrieve(with_vectors=[name])`,
+ * two_stage.py:383-390) */
+int vrag_store_read_rows(vrag_corpus_t* c, const char* name, int64_t row0, int64_t n_rows, void* out_f16_host);
+int vrag_store_page_range(vrag_corpus_t* c, const char* name, int64_t local_page, int64_t* row0, int64_t* n_rows);
+int vrag_store_drop(vrag_corpus_t* c, const char* name);
+
+/* ------------------------------------------------------------------ scoring: one stage
+ * score(page) = sum_q max_t <qhat_q, dhat_t>  — compute_maxsim_score, pooling.py:468-514, and the
+ * pooled-query stage-1 score max_t cos(qbar, d_t) of quick_test.search_two_stage (benchmarks/quick_test.py:182-191)
+ * when VRAG_Q_POOL is set.  Replaces client.query_points(query, using=name, limit=k)
+ * (two_stage.py:349-358, single_stage.py:123-132, three_stage.py:103-157).
+ * cand_ids == NULL: score every page of the store.  Otherwise only the listed global page ids
+ * (HasIdCondition restriction of three_stage.py:75-81 / rerank list of two_stage.py:380-426); ids that
+ * are not in this shard score -inf.  Results are sorted by score descending, ties by lower id.
+ * out_count receives the number of valid results (<= k).                                          */
+int vrag_search(vrag_corpus_t* c, const char* name, const float* query, int n_query_rows, uint32_t flags,
+                const int64_t* cand_ids, int64_t n_cand, int k, float* out_scores, int64_t* out_ids,
+                int* out_count);
+
+/* Score only (no top-k): out_scores[i] for page i of the store (cand_ids == NULL) or candidate i.
+ * Twin of compute_maxsim_batch (pooling.py:517-552).                                              */
+int vrag_score(vrag_corpus_t* c, const char* name, const float* query, int n_query_rows, uint32_t flags,
+               const int64_t* cand_ids, int64_t n_cand, float* out_scores);
+
+/* ------------------------------------------------------------------ scoring: fused multi-stage
+ * n_stages stages executed back to back on the device with ONE host synchronisation: stage s scores
+ * store names[s] with flags[s], restricted to the survivors of stage s-1, and keeps ks[s] pages.
+ *   two-stage  (TwoStageRetriever.search_server_side, two_stage.py:102-191): {pooled store, prefetch_k}, {"initial", top_k}
+ *   three-stage (ThreeStageRetriever.search_server_side, three_stage.py:83-173): {global, stage1_k}, {experimental, stage2_k}, {"initial", top_k}
+ * Outputs are per stage, concatenated: stage s occupies [sum(ks[:s]), sum(ks[:s+1])) of out_scores/out_ids;
+ * out_counts[s] valid entries each.                                                                */
+int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char* const* names, const uint32_t* flags,
+                           const int* ks, const float* query, int n_query_rows, float* out_scores,
+                           int64_t* out_ids, int* out_counts);
+
+/* ------------------------------------------------------------------ device-pointer variants
+ * Same kernels, caller-provided device buffers and stream (cudaStream_t passed as void*): used by the
+ * sharded multi-GPU path, which all-gathers per-shard top-k lists with NCCL between stages.        */
+int vrag_score_dev(vrag_corpus_t* c, const char* name, const float* query_dev, int n_query_rows, uint32_t flags,
+                   const int64_t* cand_ids_dev, int64_t n_cand, float* out_scores_dev, void* stream);
+int vrag_topk_dev(vrag_corpus_t* c, const float* scores_dev, const int64_t* ids_dev, int64_t id_base, int64_t n,
+                  int k, float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+
+/* ------------------------------------------------------------------ measurement helpers */
+/* Device-side time (ms, CUDA events on the library stream) of the most recent vrag_search /
+ * vrag_search_multistage on this corpus: [0] whole call, [1] dominant scan kernel only.            */
+int vrag_last_timing(vrag_corpus_t* c, float* out_ms, int n);
+/* Number of kernels the library has launched on this corpus since creation.                        */
+int64_t vrag_launch_count(vrag_corpus_t* c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRAG_B200_H */

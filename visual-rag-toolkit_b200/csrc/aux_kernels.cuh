@@ -1,0 +1,222 @@
+// Small CUDA-core kernels around the scan: query operand preparation, per-row inverse norms,
+// synthetic corpus generation and exact top-k selection.
+#pragma once
+#include "ptx.cuh"
+
+namespace vrag {
+
+// ------------------------------------------------------------------------------------------------
+// Query preparation.  Mirrors the query side of compute_maxsim_score (pooling.py:495-503):
+//   qhat = q / (||q||_2 + 1e-8) row-wise (skipped when normalize == 0),
+// and the mean-pooled query of the pooled_query_* stage-1 modes (two_stage.py:142,148,154):
+//   qbar = q.mean(axis=0)  (un-normalised mean; cosine normalisation afterwards).
+// Output: the UMMA B-operand image (2*QP rows x 128 fp16, K-major, 128B swizzle): rows [0,QP) = fp16(qhat),
+// rows [QP,2QP) = fp16((qhat - fp16(qhat)) * 2^11); rows >= Q_eff are zero.
+// grid = QP blocks (one per operand row pair), 128 threads (one per dim).
+__global__ void query_prep_kernel(const float* __restrict__ q, int Q, int pool, int normalize, int QP,
+                                  uint8_t* __restrict__ qimg) {
+  const int r = blockIdx.x;
+  const int d = threadIdx.x;
+  const int q_eff = pool ? 1 : Q;
+  __shared__ float wsum[4];
+  float x = 0.0f;
+  if (r < q_eff) {
+    if (pool) {
+      float s = 0.0f;
+      for (int i = 0; i < Q; ++i) s += q[i * 128 + d];  // numpy reduces axis 0 row by row
+      x = s / static_cast<float>(Q);
+    } else {
+      x = q[r * 128 + d];
+    }
+  }
+  float ss = x * x;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  if ((d & 31) == 0) wsum[d >> 5] = ss;
+  __syncthreads();
+  if (normalize) {
+    const float nrm = sqrtf((wsum[0] + wsum[1]) + (wsum[2] + wsum[3]));
+    x = x / (nrm + 1e-8f);
+  }
+  const __half hi = __float2half_rn(x);
+  const __half lo = __float2half_rn((x - __half2float(hi)) * 2048.0f);
+  const uint32_t rows = 2u * QP;
+  *reinterpret_cast<__half*>(qimg + sw128_offset(rows, r, d)) = (r < q_eff) ? hi : __float2half_rn(0.0f);
+  *reinterpret_cast<__half*>(qimg + sw128_offset(rows, QP + r, d)) = (r < q_eff) ? lo : __float2half_rn(0.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// inv_norm[row] = 1 / (||row||_2 + 1e-8) over fp16 rows, fp32 math (doc side of pooling.py:500).
+// 16 lanes per row, 16-byte loads.
+__global__ void inv_norm_kernel(const __half* __restrict__ rows, long long n_rows, float* __restrict__ inv) {
+  const long long gt = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long row = gt >> 4;
+  const int sub = static_cast<int>(gt & 15);
+  float ss = 0.0f;
+  if (row < n_rows) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(rows + row * 128) + sub);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      ss = fmaf(f.x, f.x, ss);
+      ss = fmaf(f.y, f.y, ss);
+    }
+  }
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  if (row < n_rows && sub == 0) inv[row] = 1.0f / (sqrtf(ss) + 1e-8f);
+}
+
+// fp32 -> fp16 conversion of an embedding matrix (the store-dtype cast of qdrant_indexer.py:423-441).
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, long long n, __half* __restrict__ dst) {
+  const long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    *reinterpret_cast<__half2*>(dst + i) = a;
+    *reinterpret_cast<__half2*>(dst + i + 2) = b;
+  } else {
+    for (long long j = i; j < n; ++j) dst[j] = __float2half_rn(src[j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Synthetic corpus: counter-based gaussian rows, L2-normalised in fp32, rounded to fp16 (what a Col*
+// model + fp16 store produces), plus inv_norm of the ROUNDED row (what the oracle will see).
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__global__ void synth_rows_kernel(__half* __restrict__ rows, float* __restrict__ inv, long long row_begin,
+                                  long long n_rows, uint64_t seed, long long row_seed_base) {
+  const long long gt = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long lrow = gt >> 4;
+  const int sub = static_cast<int>(gt & 15);
+  const bool ok = lrow < n_rows;
+  const long long row = row_begin + lrow;
+  float v[8];
+  float ss = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint64_t h = mix64(seed ^ mix64(static_cast<uint64_t>(row_seed_base + row) * 64ull + sub * 4 + j));
+    const float u1 = (static_cast<float>(static_cast<uint32_t>(h >> 40)) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = (static_cast<float>(static_cast<uint32_t>(h) >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float rad = sqrtf(-2.0f * __logf(u1));
+    float s, c;
+    __sincosf(6.283185307f * u2, &s, &c);
+    v[2 * j] = rad * c;
+    v[2 * j + 1] = rad * s;
+    ss += v[2 * j] * v[2 * j] + v[2 * j + 1] * v[2 * j + 1];
+  }
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  const float invn = 1.0f / (sqrtf(ss) + 1e-8f);
+  uint4 out;
+  __half2* h2 = reinterpret_cast<__half2*>(&out);
+  float ss16 = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h2[j] = __floats2half2_rn(v[2 * j] * invn, v[2 * j + 1] * invn);
+    const float2 f = __half22float2(h2[j]);
+    ss16 = fmaf(f.x, f.x, ss16);
+    ss16 = fmaf(f.y, f.y, ss16);
+  }
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) ss16 += __shfl_xor_sync(0xffffffffu, ss16, off);
+  if (ok) {
+    *(reinterpret_cast<uint4*>(rows + row * 128) + sub) = out;
+    if (sub == 0) inv[row] = 1.0f / (sqrtf(ss16) + 1e-8f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact top-k.  Keys are 64-bit: (order-preserving bits of the fp32 score) << 32 | (0xFFFFFFFF - item
+// index), so "largest key first" = "highest score first, ties -> lower item index", which is what
+// Python's stable list.sort(reverse=True) over pages in index order yields (quick_test.py:165,
+// two_stage.py:424).  Each level sorts chunks of kTopkChunk keys in shared memory (bitonic,
+// descending) and keeps the first k of every chunk; the last level writes (score, id) pairs.
+constexpr int kTopkChunk = 8192;
+constexpr int kTopkThreads = 1024;
+constexpr int kTopkMaxK = kTopkChunk / 2;
+
+__device__ __forceinline__ uint32_t score_to_ord(float f) {
+  if (f != f) return 0u;  // NaN sorts last
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_to_score(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+struct TopkArgs {
+  const float* scores;        // level 0 input (nullptr on merge levels)
+  const unsigned long long* keys_in;  // merge-level input
+  long long n;                // number of input elements
+  int k;
+  unsigned long long* keys_out;  // [n_chunks][k] (nullptr on the final level)
+  // final level outputs
+  float* out_scores;          // [k]
+  long long* out_ids;         // [k]
+  int* out_pos;               // [k] item index of each result (optional)
+  int* out_count;             // number of valid results (optional)
+  const long long* ids;       // item index -> id (nullptr: id = id_base + index)
+  long long id_base;
+  long long n_total;          // number of real items (for out_count / padding)
+};
+
+__global__ void __launch_bounds__(kTopkThreads, 1) topk_kernel(const TopkArgs a) {
+  extern __shared__ unsigned long long skeys[];
+  const long long base = static_cast<long long>(blockIdx.x) * kTopkChunk;
+  for (int j = threadIdx.x; j < kTopkChunk; j += kTopkThreads) {
+    const long long i = base + j;
+    unsigned long long key = 0ull;
+    if (i < a.n) {
+      if (a.scores) {
+        key = (static_cast<unsigned long long>(score_to_ord(a.scores[i])) << 32) |
+              static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<uint32_t>(i));
+      } else {
+        key = a.keys_in[i];
+      }
+    }
+    skeys[j] = key;
+  }
+  for (int size = 2; size <= kTopkChunk; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int e = threadIdx.x; e < kTopkChunk / 2; e += kTopkThreads) {
+        const int pos = 2 * e - (e & (stride - 1));
+        const unsigned long long x = skeys[pos], y = skeys[pos + stride];
+        const bool desc = (pos & size) == 0;
+        if ((x < y) == desc) {
+          skeys[pos] = y;
+          skeys[pos + stride] = x;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (a.keys_out) {
+    for (int j = threadIdx.x; j < a.k; j += kTopkThreads) a.keys_out[static_cast<long long>(blockIdx.x) * a.k + j] = skeys[j];
+  } else {
+    const long long nvalid = a.n_total < a.k ? a.n_total : a.k;
+    for (int j = threadIdx.x; j < a.k; j += kTopkThreads) {
+      if (j < nvalid) {
+        const unsigned long long key = skeys[j];
+        const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
+        a.out_scores[j] = ord_to_score(static_cast<uint32_t>(key >> 32));
+        a.out_ids[j] = a.ids ? a.ids[idx] : (a.id_base + idx);
+        if (a.out_pos) a.out_pos[j] = static_cast<int>(idx);
+      } else {
+        a.out_scores[j] = -INFINITY;
+        a.out_ids[j] = -1;
+        if (a.out_pos) a.out_pos[j] = -1;
+      }
+    }
+    if (a.out_count && threadIdx.x == 0) *a.out_count = static_cast<int>(nvalid);
+  }
+}
+
+}  // namespace vrag

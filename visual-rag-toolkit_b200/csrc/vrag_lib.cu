@@ -1,0 +1,708 @@
+// libvrag_b200.so — host side of the C ABI declared in include/vrag_b200.h.
+// Owns the GPU-resident corpus stores and launches the sm_100a kernels. No CPU compute path exists:
+// every scoring call ends in a kernel launch or an error.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vrag_b200.h"
+#include "aux_kernels.cuh"
+#include "maxsim_scan.cuh"
+
+using namespace vrag;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CUDA_OK(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                       __FILE__, __LINE__);                                    \
+  } while (0)
+#define TRY(expr)            \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != 0) return _r;  \
+  } while (0)
+
+extern "C" const char* vrag_last_error(void) { return g_err.c_str(); }
+extern "C" int vrag_abi_version(void) { return 1; }
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// rows: [total_rows][128] fp16, box = {64 cols, box_rows}, 128B swizzle (UMMA K-major SW128 operand layout)
+static int make_rows_map(CUtensorMap* m, void* base, int64_t total_rows, int box_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail("cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t dims[2] = {128, static_cast<cuuint64_t>(total_rows)};
+  cuuint64_t strides[1] = {256};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(rows, box=%d) failed: %d", box_rows, (int)r);
+  return 0;
+}
+static int make_scale_map(CUtensorMap* m, void* base, int64_t total_rows, int box_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail("cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t dims[1] = {static_cast<cuuint64_t>(total_rows)};
+  cuuint64_t strides[1] = {0};
+  cuuint32_t box[1] = {static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[1] = {1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(scale, box=%d) failed: %d", box_rows, (int)r);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ corpus
+struct Store {
+  __half* rows = nullptr;        // [total_rows][128]
+  float* inv = nullptr;          // [total_rows] 1/(||row||+1e-8)
+  long long* offsets = nullptr;  // device [n_pages+1] (nullptr when fixed_rows > 0)
+  std::vector<int64_t> h_offsets;
+  int* tile_page0 = nullptr;     // packed dense variable-length: [n_tiles+1]
+  int64_t n_tiles = 0;
+  int64_t n_pages = 0, total_rows = 0, fixed_rows = 0, max_rows = 0;
+  bool packed = false;
+  CUtensorMap tm128, tm32, ts128, ts32;
+};
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max<size_t>(n, 256);
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct vrag_corpus {
+  int device = 0;
+  int64_t page_base = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  std::map<std::string, Store> stores;
+  DevBuf<float> d_query, d_scores, d_out_scores;
+  DevBuf<uint8_t> d_qimg;
+  DevBuf<unsigned long long> d_keys_a, d_keys_b;
+  DevBuf<long long> d_cand, d_out_ids;
+  DevBuf<int> d_counts;
+  float* h_query = nullptr;       // pinned staging
+  float* h_out_scores = nullptr;
+  long long* h_out_ids = nullptr;
+  int* h_counts = nullptr;
+  size_t h_out_cap = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+  float last_ms[2] = {0, 0};
+  int64_t launches = 0;
+  bool attrs_set = false;
+};
+
+static const int kMaxQueryRows = 1024;  // staging capacity for raw query tokens (pooled queries may be long)
+static const int kMaxStages = 8;
+
+static int set_device(vrag_corpus* c) {
+  CUDA_OK(cudaSetDevice(c->device));
+  return 0;
+}
+
+static void free_store(Store& s) {
+  if (s.rows) cudaFree(s.rows);
+  if (s.inv) cudaFree(s.inv);
+  if (s.offsets) cudaFree(s.offsets);
+  if (s.tile_page0) cudaFree(s.tile_page0);
+  s = Store();
+}
+
+extern "C" int vrag_corpus_create(int device, int64_t page_base, vrag_corpus_t** out) {
+  if (!out) return fail("out is NULL");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail("no CUDA device available (%s): libvrag_b200 has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail("device %d out of range (have %d)", device, ndev);
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+  vrag_corpus* c = new vrag_corpus();
+  c->device = device;
+  c->page_base = page_base;
+  c->num_sms = prop.multiProcessorCount;
+  CUDA_OK(cudaSetDevice(device));
+  CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreate(&c->ev0));
+  CUDA_OK(cudaEventCreate(&c->ev1));
+  CUDA_OK(cudaEventCreate(&c->evk0));
+  CUDA_OK(cudaEventCreate(&c->evk1));
+  CUDA_OK(cudaMallocHost(&c->h_query, kMaxQueryRows * 128 * sizeof(float)));
+  CUDA_OK(cudaMallocHost(&c->h_counts, kMaxStages * sizeof(int)));
+  TRY(c->d_query.ensure(kMaxQueryRows * 128));
+  TRY(c->d_qimg.ensure(256 * 256));
+  TRY(c->d_counts.ensure(kMaxStages));
+  *out = c;
+  return 0;
+}
+
+extern "C" int vrag_corpus_destroy(vrag_corpus_t* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& kv : c->stores) free_store(kv.second);
+  c->d_query.release();
+  c->d_scores.release();
+  c->d_out_scores.release();
+  c->d_qimg.release();
+  c->d_keys_a.release();
+  c->d_keys_b.release();
+  c->d_cand.release();
+  c->d_out_ids.release();
+  c->d_counts.release();
+  if (c->h_query) cudaFreeHost(c->h_query);
+  if (c->h_out_scores) cudaFreeHost(c->h_out_scores);
+  if (c->h_out_ids) cudaFreeHost(c->h_out_ids);
+  if (c->h_counts) cudaFreeHost(c->h_counts);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->evk0);
+  cudaEventDestroy(c->evk1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+static int ensure_host_out(vrag_corpus* c, size_t n) {
+  if (n <= c->h_out_cap) return 0;
+  if (c->h_out_scores) cudaFreeHost(c->h_out_scores);
+  if (c->h_out_ids) cudaFreeHost(c->h_out_ids);
+  c->h_out_cap = 0;
+  size_t want = std::max<size_t>(n, 4096);
+  CUDA_OK(cudaMallocHost(&c->h_out_scores, want * sizeof(float)));
+  CUDA_OK(cudaMallocHost(&c->h_out_ids, want * sizeof(long long)));
+  c->h_out_cap = want;
+  return 0;
+}
+
+// page layout bookkeeping + tensor maps once rows/inv are in place
+static int finish_store(vrag_corpus* c, Store& s, const int64_t* page_offsets, int64_t n_pages, int64_t fixed_rows) {
+  s.n_pages = n_pages;
+  s.fixed_rows = fixed_rows;
+  if (fixed_rows > 0) {
+    s.max_rows = fixed_rows;
+  } else {
+    s.h_offsets.assign(page_offsets, page_offsets + n_pages + 1);
+    int64_t mx = 0;
+    for (int64_t i = 0; i < n_pages; ++i) mx = std::max(mx, page_offsets[i + 1] - page_offsets[i]);
+    s.max_rows = mx;
+    CUDA_OK(cudaMalloc(&s.offsets, (n_pages + 1) * sizeof(long long)));
+    CUDA_OK(cudaMemcpy(s.offsets, page_offsets, (n_pages + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+  }
+  s.packed = s.max_rows <= kTileRows;
+  if (s.packed && fixed_rows == 0 && n_pages > 0) {
+    // greedy packing of consecutive pages into 128-row tiles
+    std::vector<int> t0;
+    int64_t pg = 0;
+    while (pg < n_pages) {
+      t0.push_back(static_cast<int>(pg));
+      int64_t rows = 0;
+      int64_t e = pg;
+      while (e < n_pages && rows + (page_offsets[e + 1] - page_offsets[e]) <= kTileRows && e - pg < kTileRows) {
+        rows += page_offsets[e + 1] - page_offsets[e];
+        ++e;
+      }
+      pg = e;
+    }
+    t0.push_back(static_cast<int>(n_pages));
+    s.n_tiles = static_cast<int64_t>(t0.size()) - 1;
+    CUDA_OK(cudaMalloc(&s.tile_page0, t0.size() * sizeof(int)));
+    CUDA_OK(cudaMemcpy(s.tile_page0, t0.data(), t0.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  if (s.total_rows > 0) {
+    TRY(make_rows_map(&s.tm128, s.rows, s.total_rows, kTileRows));
+    TRY(make_rows_map(&s.tm32, s.rows, s.total_rows, kBoxRowsSmall));
+    TRY(make_scale_map(&s.ts128, s.inv, s.total_rows, kTileRows));
+    TRY(make_scale_map(&s.ts32, s.inv, s.total_rows, kBoxRowsSmall));
+  }
+  return 0;
+}
+
+static int check_layout(const int64_t* page_offsets, int64_t n_pages, int64_t fixed_rows, int64_t* total_rows) {
+  if (n_pages < 0) return fail("n_pages < 0");
+  if (n_pages >= (1ll << 31)) return fail("a shard holds at most 2^31-1 pages");
+  if (fixed_rows > 0) {
+    *total_rows = n_pages * fixed_rows;
+  } else {
+    if (!page_offsets) return fail("page_offsets is NULL and fixed_rows == 0");
+    if (page_offsets[0] != 0) return fail("page_offsets[0] must be 0");
+    for (int64_t i = 0; i < n_pages; ++i)
+      if (page_offsets[i + 1] < page_offsets[i]) return fail("page_offsets must be non-decreasing (page %lld)", (long long)i);
+    *total_rows = page_offsets[n_pages];
+  }
+  if (*total_rows >= (1ll << 31)) return fail("a store holds at most 2^31-1 rows per shard (TMA coordinates are int32)");
+  return 0;
+}
+
+static int alloc_store(vrag_corpus* c, const char* name, int64_t total_rows, Store** out) {
+  if (!name || !*name) return fail("store name is empty");
+  auto it = c->stores.find(name);
+  if (it != c->stores.end()) {
+    free_store(it->second);
+    c->stores.erase(it);
+  }
+  Store s;
+  s.total_rows = total_rows;
+  if (total_rows > 0) {
+    CUDA_OK(cudaMalloc(&s.rows, static_cast<size_t>(total_rows) * 128 * sizeof(__half)));
+    cudaError_t e = cudaMalloc(&s.inv, static_cast<size_t>(total_rows) * sizeof(float));
+    if (e != cudaSuccess) {
+      cudaFree(s.rows);
+      return fail("cudaMalloc(inv) failed: %s", cudaGetErrorString(e));
+    }
+  }
+  c->stores[name] = s;
+  *out = &c->stores[name];
+  return 0;
+}
+
+extern "C" int vrag_store_add(vrag_corpus_t* c, const char* name, const void* rows, int dtype, int rows_on_device,
+                              const int64_t* page_offsets, int64_t n_pages, int64_t fixed_rows) {
+  if (!c) return fail("corpus is NULL");
+  TRY(set_device(c));
+  if (dtype != VRAG_F16 && dtype != VRAG_F32) return fail("unknown dtype %d", dtype);
+  int64_t total_rows = 0;
+  TRY(check_layout(page_offsets, n_pages, fixed_rows, &total_rows));
+  if (total_rows > 0 && !rows) return fail("rows is NULL");
+  Store* s = nullptr;
+  TRY(alloc_store(c, name, total_rows, &s));
+  const size_t n_el = static_cast<size_t>(total_rows) * 128;
+  if (total_rows > 0) {
+    const cudaMemcpyKind kind = rows_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (dtype == VRAG_F16) {
+      CUDA_OK(cudaMemcpy(s->rows, rows, n_el * sizeof(__half), kind));
+    } else {
+      const size_t chunk = size_t(32) << 20;  // elements per staging chunk
+      float* tmp = nullptr;
+      const float* src_base = static_cast<const float*>(rows);
+      if (!rows_on_device) CUDA_OK(cudaMalloc(&tmp, std::min(chunk, n_el) * sizeof(float)));
+      for (size_t o = 0; o < n_el; o += chunk) {
+        const size_t n = std::min(chunk, n_el - o);
+        const float* src = src_base + o;
+        if (!rows_on_device) {
+          CUDA_OK(cudaMemcpy(tmp, src, n * sizeof(float), cudaMemcpyHostToDevice));
+          src = tmp;
+        }
+        f32_to_f16_kernel<<<static_cast<unsigned>((n / 4 + 256) / 256), 256, 0, c->stream>>>(src, n, s->rows + o);
+        c->launches++;
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+      }
+      if (tmp) cudaFree(tmp);
+    }
+    const long long threads = total_rows * 16;
+    inv_norm_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, c->stream>>>(s->rows, total_rows, s->inv);
+    c->launches++;
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+  }
+  return finish_store(c, *s, page_offsets, n_pages, fixed_rows);
+}
+
+extern "C" int vrag_store_add_synthetic(vrag_corpus_t* c, const char* name, const int64_t* page_offsets,
+                                        int64_t n_pages, int64_t fixed_rows, uint64_t seed, int64_t row_seed_base) {
+  if (!c) return fail("corpus is NULL");
+  TRY(set_device(c));
+  int64_t total_rows = 0;
+  TRY(check_layout(page_offsets, n_pages, fixed_rows, &total_rows));
+  Store* s = nullptr;
+  TRY(alloc_store(c, name, total_rows, &s));
+  const int64_t chunk = 1ll << 24;
+  for (int64_t r = 0; r < total_rows; r += chunk) {
+    const int64_t n = std::min(chunk, total_rows - r);
+    synth_rows_kernel<<<static_cast<unsigned>((n * 16 + 255) / 256), 256, 0, c->stream>>>(s->rows, s->inv, r, n, seed,
+                                                                                          row_seed_base);
+    c->launches++;
+  }
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  CUDA_OK(cudaGetLastError());
+  return finish_store(c, *s, page_offsets, n_pages, fixed_rows);
+}
+
+static int find_store(vrag_corpus* c, const char* name, Store** out) {
+  if (!c) return fail("corpus is NULL");
+  if (!name) return fail("store name is NULL");
+  auto it = c->stores.find(name);
+  if (it == c->stores.end()) return fail("unknown vector store '%s'", name);
+  *out = &it->second;
+  return 0;
+}
+
+extern "C" int vrag_store_info(vrag_corpus_t* c, const char* name, int64_t* n_pages, int64_t* total_rows,
+                               int64_t* fixed_rows, int64_t* max_rows) {
+  Store* s;
+  TRY(find_store(c, name, &s));
+  if (n_pages) *n_pages = s->n_pages;
+  if (total_rows) *total_rows = s->total_rows;
+  if (fixed_rows) *fixed_rows = s->fixed_rows;
+  if (max_rows) *max_rows = s->max_rows;
+  return 0;
+}
+
+extern "C" int vrag_store_page_range(vrag_corpus_t* c, const char* name, int64_t local_page, int64_t* row0,
+                                     int64_t* n_rows) {
+  Store* s;
+  TRY(find_store(c, name, &s));
+  if (local_page < 0 || local_page >= s->n_pages) return fail("page %lld out of range", (long long)local_page);
+  if (s->fixed_rows > 0) {
+    *row0 = local_page * s->fixed_rows;
+    *n_rows = s->fixed_rows;
+  } else {
+    *row0 = s->h_offsets[local_page];
+    *n_rows = s->h_offsets[local_page + 1] - s->h_offsets[local_page];
+  }
+  return 0;
+}
+
+extern "C" int vrag_store_read_rows(vrag_corpus_t* c, const char* name, int64_t row0, int64_t n_rows,
+                                    void* out_f16_host) {
+  Store* s;
+  TRY(find_store(c, name, &s));
+  TRY(set_device(c));
+  if (row0 < 0 || n_rows < 0 || row0 + n_rows > s->total_rows) return fail("row range out of bounds");
+  if (n_rows == 0) return 0;
+  CUDA_OK(cudaMemcpy(out_f16_host, s->rows + static_cast<size_t>(row0) * 128, static_cast<size_t>(n_rows) * 256,
+                     cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int vrag_store_drop(vrag_corpus_t* c, const char* name) {
+  Store* s;
+  TRY(find_store(c, name, &s));
+  TRY(set_device(c));
+  free_store(*s);
+  c->stores.erase(name);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ launches
+template <int QP, bool PACKED>
+static int launch_scan_t(vrag_corpus* c, const Store& s, const ScanParams& p, long long n_units, cudaStream_t st) {
+  auto kern = maxsim_scan_kernel<QP, PACKED>;
+  const size_t smem = ScanCfg<QP>::smem_bytes(PACKED);
+  static bool attr_done[8] = {false};  // per device
+  if (!attr_done[c->device & 7]) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_done[c->device & 7] = true;
+  }
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(c->num_sms, n_units));
+  kern<<<grid, kScanThreads, smem, st>>>(s.tm128, s.tm32, s.ts128, s.ts32, p);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Score a store (or a candidate list) into d_scores[n_items]. All pointers are device pointers.
+static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int n_query_rows, uint32_t flags,
+                       const long long* d_cand, int64_t n_cand, float* d_scores, cudaStream_t st, bool time_kernel) {
+  const bool pool = (flags & VRAG_Q_POOL) != 0;
+  const bool normalize = (flags & VRAG_Q_NORMALIZE) != 0;
+  if (n_query_rows < 1) return fail("query has no rows");
+  if (n_query_rows > kMaxQueryRows) return fail("query has %d rows; at most %d supported", n_query_rows, kMaxQueryRows);
+  const int q_eff = pool ? 1 : n_query_rows;
+  if (q_eff > 128) return fail("query has %d token rows; at most 128 supported per call", q_eff);
+  const int QP = q_eff <= 8 ? 8 : q_eff <= 16 ? 16 : q_eff <= 32 ? 32 : q_eff <= 64 ? 64 : 128;
+  const int64_t n_items = d_cand ? n_cand : s.n_pages;
+  if (n_items == 0) return 0;
+  if (s.total_rows == 0) return fail("store is empty");
+
+  query_prep_kernel<<<QP, 128, 0, st>>>(d_query, n_query_rows, pool ? 1 : 0, normalize ? 1 : 0, QP, c->d_qimg.p);
+  c->launches++;
+
+  ScanParams p;
+  memset(&p, 0, sizeof(p));
+  p.offsets = s.offsets;
+  p.fixed_rows = s.fixed_rows;
+  p.n_pages = s.n_pages;
+  p.cand = d_cand;
+  p.cand_base = c->page_base;
+  p.n_items = n_items;
+  p.qimg = c->d_qimg.p;
+  p.scores = d_scores;
+  p.q_valid = q_eff;
+  p.use_scale = normalize ? 1 : 0;
+  long long n_units = n_items;
+  if (s.packed) {
+    if (d_cand) {
+      p.slot_rows = s.max_rows <= 32 ? 32 : (s.max_rows <= 64 ? 64 : 128);
+      const int per_tile = kTileRows / p.slot_rows;
+      p.n_tiles = (n_items + per_tile - 1) / per_tile;
+    } else if (s.fixed_rows > 0) {
+      p.pages_per_tile = static_cast<int>(kTileRows / s.fixed_rows);
+      p.n_tiles = (s.n_pages + p.pages_per_tile - 1) / p.pages_per_tile;
+    } else {
+      p.tile_page0 = s.tile_page0;
+      p.n_tiles = s.n_tiles;
+    }
+    n_units = p.n_tiles;
+  }
+  if (time_kernel) CUDA_OK(cudaEventRecord(c->evk0, st));
+  int r = 0;
+#define VRAG_DISPATCH(QPV)                                                     \
+  case QPV:                                                                    \
+    r = s.packed ? launch_scan_t<QPV, true>(c, s, p, n_units, st)              \
+                 : launch_scan_t<QPV, false>(c, s, p, n_units, st);            \
+    break;
+  switch (QP) {
+    VRAG_DISPATCH(8)
+    VRAG_DISPATCH(16)
+    VRAG_DISPATCH(32)
+    VRAG_DISPATCH(64)
+    VRAG_DISPATCH(128)
+    default:
+      return fail("internal: bad QP %d", QP);
+  }
+#undef VRAG_DISPATCH
+  if (r) return r;
+  if (time_kernel) CUDA_OK(cudaEventRecord(c->evk1, st));
+  return 0;
+}
+
+// Exact top-k of d_scores[n] -> (out_scores[k], out_ids[k]) sorted descending, ties -> lower item index.
+static int launch_topk(vrag_corpus* c, const float* d_scores, const long long* d_ids, int64_t id_base, int64_t n,
+                       int k, float* out_scores, long long* out_ids, int* out_pos, int* out_count, cudaStream_t st) {
+  if (k < 1) return fail("k must be >= 1");
+  if (k > kTopkMaxK) return fail("k=%d exceeds the supported maximum %d", k, kTopkMaxK);
+  if (n >= (1ll << 32) - 1) return fail("too many items for top-k");
+  static bool attr_done[8] = {false};
+  const size_t smem = kTopkChunk * sizeof(unsigned long long);
+  if (!attr_done[c->device & 7]) {
+    CUDA_OK(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_done[c->device & 7] = true;
+  }
+  TopkArgs a;
+  memset(&a, 0, sizeof(a));
+  a.k = k;
+  a.out_scores = out_scores;
+  a.out_ids = out_ids;
+  a.out_pos = out_pos;
+  a.out_count = out_count;
+  a.ids = d_ids;
+  a.id_base = id_base;
+  a.n_total = n;
+  long long m = n;
+  long long nch = std::max<long long>(1, (m + kTopkChunk - 1) / kTopkChunk);
+  if (nch > 1) {
+    TRY(c->d_keys_a.ensure(static_cast<size_t>(nch) * k));
+    TRY(c->d_keys_b.ensure(static_cast<size_t>((nch * k + kTopkChunk - 1) / kTopkChunk) * k + k));
+  }
+  a.scores = d_scores;
+  a.n = m;
+  unsigned long long* bufs[2] = {c->d_keys_a.p, c->d_keys_b.p};
+  int which = 0;
+  while (true) {
+    a.keys_out = (nch > 1) ? bufs[which] : nullptr;
+    topk_kernel<<<static_cast<unsigned>(nch), kTopkThreads, smem, st>>>(a);
+    c->launches++;
+    if (nch == 1) break;
+    a.scores = nullptr;
+    a.keys_in = bufs[which];
+    m = nch * k;
+    a.n = m;
+    nch = (m + kTopkChunk - 1) / kTopkChunk;
+    which ^= 1;
+  }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ host-facing search
+static int stage_query(vrag_corpus* c, const float* query, int n_query_rows) {
+  if (!query) return fail("query is NULL");
+  if (n_query_rows < 1 || n_query_rows > kMaxQueryRows) return fail("query rows %d out of range [1,%d]", n_query_rows, kMaxQueryRows);
+  memcpy(c->h_query, query, static_cast<size_t>(n_query_rows) * 128 * sizeof(float));
+  CUDA_OK(cudaMemcpyAsync(c->d_query.p, c->h_query, static_cast<size_t>(n_query_rows) * 128 * sizeof(float),
+                          cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
+extern "C" int vrag_score(vrag_corpus_t* c, const char* name, const float* query, int n_query_rows, uint32_t flags,
+                          const int64_t* cand_ids, int64_t n_cand, float* out_scores) {
+  Store* s;
+  TRY(find_store(c, name, &s));
+  TRY(set_device(c));
+  const int64_t n_items = cand_ids ? n_cand : s->n_pages;
+  if (n_items == 0) return 0;
+  if (!out_scores) return fail("out_scores is NULL");
+  TRY(stage_query(c, query, n_query_rows));
+  if (cand_ids) {
+    TRY(c->d_cand.ensure(n_cand));
+    CUDA_OK(cudaMemcpyAsync(c->d_cand.p, cand_ids, n_cand * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+  }
+  TRY(c->d_scores.ensure(n_items));
+  CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+  TRY(launch_scan(c, *s, c->d_query.p, n_query_rows, flags, cand_ids ? c->d_cand.p : nullptr, n_cand, c->d_scores.p,
+                  c->stream, true));
+  CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+  CUDA_OK(cudaMemcpyAsync(out_scores, c->d_scores.p, n_items * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1);
+  cudaEventElapsedTime(&c->last_ms[1], c->evk0, c->evk1);
+  return 0;
+}
+
+extern "C" int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char* const* names,
+                                      const uint32_t* flags, const int* ks, const float* query, int n_query_rows,
+                                      float* out_scores, int64_t* out_ids, int* out_counts) {
+  if (!c) return fail("corpus is NULL");
+  if (n_stages < 1 || n_stages > kMaxStages) return fail("n_stages %d out of range [1,%d]", n_stages, kMaxStages);
+  if (!names || !flags || !ks || !out_scores || !out_ids || !out_counts) return fail("NULL argument");
+  TRY(set_device(c));
+  Store* st[kMaxStages];
+  size_t total_k = 0;
+  for (int s = 0; s < n_stages; ++s) {
+    TRY(find_store(c, names[s], &st[s]));
+    if (ks[s] < 1) return fail("stage %d: k must be >= 1", s);
+    if (ks[s] > kTopkMaxK) return fail("stage %d: k=%d exceeds the supported maximum %d", s, ks[s], kTopkMaxK);
+    if (st[s]->n_pages != st[0]->n_pages) return fail("stage %d: store '%s' has a different page count", s, names[s]);
+    total_k += ks[s];
+  }
+  TRY(stage_query(c, query, n_query_rows));
+  TRY(c->d_out_scores.ensure(total_k));
+  TRY(c->d_out_ids.ensure(total_k));
+  TRY(ensure_host_out(c, total_k));
+  TRY(c->d_scores.ensure(std::max<int64_t>(st[0]->n_pages, 1)));
+  CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+  size_t off = 0;
+  int64_t n_prev = st[0]->n_pages;   // survivors entering the stage
+  const long long* d_prev_ids = nullptr;
+  for (int s = 0; s < n_stages; ++s) {
+    const int64_t n_items = n_prev;
+    if (n_items > 0) {
+      // the dominant (timed) kernel is the first-stage scan
+      TRY(launch_scan(c, *st[s], c->d_query.p, n_query_rows, flags[s], d_prev_ids, n_items, c->d_scores.p, c->stream,
+                      s == 0));
+    }
+    TRY(launch_topk(c, c->d_scores.p, d_prev_ids, c->page_base, n_items, ks[s], c->d_out_scores.p + off,
+                    c->d_out_ids.p + off, nullptr, c->d_counts.p + s, c->stream));
+    d_prev_ids = c->d_out_ids.p + off;
+    n_prev = std::min<int64_t>(ks[s], n_items);
+    off += ks[s];
+  }
+  CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->h_out_scores, c->d_out_scores.p, total_k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->h_out_ids, c->d_out_ids.p, total_k * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->h_counts, c->d_counts.p, n_stages * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  memcpy(out_scores, c->h_out_scores, total_k * sizeof(float));
+  memcpy(out_ids, c->h_out_ids, total_k * sizeof(long long));
+  memcpy(out_counts, c->h_counts, n_stages * sizeof(int));
+  cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1);
+  cudaEventElapsedTime(&c->last_ms[1], c->evk0, c->evk1);
+  return 0;
+}
+
+extern "C" int vrag_search(vrag_corpus_t* c, const char* name, const float* query, int n_query_rows, uint32_t flags,
+                           const int64_t* cand_ids, int64_t n_cand, int k, float* out_scores, int64_t* out_ids,
+                           int* out_count) {
+  if (!cand_ids) {
+    const char* names[1] = {name};
+    int cnt = 0;
+    TRY(vrag_search_multistage(c, 1, names, &flags, &k, query, n_query_rows, out_scores, out_ids, &cnt));
+    if (out_count) *out_count = cnt;
+    return 0;
+  }
+  Store* s;
+  TRY(find_store(c, name, &s));
+  TRY(set_device(c));
+  if (k < 1) return fail("k must be >= 1");
+  if (!out_scores || !out_ids) return fail("NULL output");
+  TRY(stage_query(c, query, n_query_rows));
+  TRY(c->d_cand.ensure(std::max<int64_t>(n_cand, 1)));
+  if (n_cand > 0)
+    CUDA_OK(cudaMemcpyAsync(c->d_cand.p, cand_ids, n_cand * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+  TRY(c->d_scores.ensure(std::max<int64_t>(n_cand, 1)));
+  TRY(c->d_out_scores.ensure(k));
+  TRY(c->d_out_ids.ensure(k));
+  TRY(ensure_host_out(c, k));
+  CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+  if (n_cand > 0)
+    TRY(launch_scan(c, *s, c->d_query.p, n_query_rows, flags, c->d_cand.p, n_cand, c->d_scores.p, c->stream, true));
+  TRY(launch_topk(c, c->d_scores.p, c->d_cand.p, 0, n_cand, k, c->d_out_scores.p, c->d_out_ids.p, nullptr,
+                  c->d_counts.p, c->stream));
+  CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->h_out_scores, c->d_out_scores.p, k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->h_out_ids, c->d_out_ids.p, k * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->h_counts, c->d_counts.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  memcpy(out_scores, c->h_out_scores, k * sizeof(float));
+  memcpy(out_ids, c->h_out_ids, k * sizeof(long long));
+  if (out_count) *out_count = c->h_counts[0];
+  cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1);
+  if (n_cand > 0) cudaEventElapsedTime(&c->last_ms[1], c->evk0, c->evk1);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ device-pointer variants
+extern "C" int vrag_score_dev(vrag_corpus_t* c, const char* name, const float* query_dev, int n_query_rows,
+                              uint32_t flags, const int64_t* cand_ids_dev, int64_t n_cand, float* out_scores_dev,
+                              void* stream) {
+  Store* s;
+  TRY(find_store(c, name, &s));
+  TRY(set_device(c));
+  if (!query_dev || !out_scores_dev) return fail("NULL device pointer");
+  return launch_scan(c, *s, query_dev, n_query_rows, flags, reinterpret_cast<const long long*>(cand_ids_dev), n_cand,
+                     out_scores_dev, static_cast<cudaStream_t>(stream), false);
+}
+
+extern "C" int vrag_topk_dev(vrag_corpus_t* c, const float* scores_dev, const int64_t* ids_dev, int64_t id_base,
+                             int64_t n, int k, float* out_scores_dev, int64_t* out_ids_dev, void* stream) {
+  if (!c) return fail("corpus is NULL");
+  TRY(set_device(c));
+  if (!out_scores_dev || !out_ids_dev) return fail("NULL device pointer");
+  return launch_topk(c, scores_dev, reinterpret_cast<const long long*>(ids_dev), id_base, n, k, out_scores_dev,
+                     reinterpret_cast<long long*>(out_ids_dev), nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vrag_last_timing(vrag_corpus_t* c, float* out_ms, int n) {
+  if (!c || !out_ms) return fail("NULL argument");
+  for (int i = 0; i < n && i < 2; ++i) out_ms[i] = c->last_ms[i];
+  return 0;
+}
+extern "C" int64_t vrag_launch_count(vrag_corpus_t* c) { return c ? c->launches : 0; }

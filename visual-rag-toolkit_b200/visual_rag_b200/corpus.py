@@ -1,0 +1,310 @@
+"""GPU-resident corpus store: the B200 stand-in for the Qdrant collection of the reference.
+
+One `GpuCorpus` owns, on one GPU, the named vector stores the reference's collection schema defines
+(visual_rag/indexing/qdrant_indexer.py:200-239): ``initial`` (all page tokens), ``mean_pooling``,
+``experimental_pooling*`` (pooled multi-vectors) and ``global_pooling`` (one row per page) — fp16 rows in
+HBM plus a per-row fp32 inverse norm, pages described by a row-offset array.  All scoring goes through
+libvrag_b200 (hand-written sm_100a kernels); nothing in this module computes scores on the CPU.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+DIM = 128
+
+
+def _as_f32_query(query) -> np.ndarray:
+    """Query -> contiguous fp32 [Q,128] numpy (same conversions as TwoStageRetriever._to_numpy,
+    visual_rag/retrieval/two_stage.py:428-434)."""
+    try:
+        import torch
+
+        if isinstance(query, torch.Tensor):
+            query = query.detach().cpu().float().numpy()
+    except ImportError:  # pragma: no cover
+        pass
+    q = np.array(query, dtype=np.float32)
+    if q.ndim == 1:
+        q = q[None, :]
+    if q.ndim != 2 or q.shape[1] != DIM:
+        raise ValueError(f"query must be [num_tokens, {DIM}], got {q.shape}")
+    return np.ascontiguousarray(q)
+
+
+def query_flags(normalize: bool = True, pool_query: bool = False) -> int:
+    return (N.VRAG_Q_NORMALIZE if normalize else 0) | (N.VRAG_Q_POOL if pool_query else 0)
+
+
+class GpuCorpus:
+    """Handle to one shard of the corpus on one GPU.
+
+    page_base: global id of this shard's first page (global page id = page_base + local index).
+    """
+
+    def __init__(self, device: int = 0, page_base: int = 0):
+        self._lib = N.load()
+        h = C.c_void_p()
+        N.check(self._lib.vrag_corpus_create(int(device), int(page_base), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.page_base = int(page_base)
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.vrag_corpus_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ------------------------------------------------------------------ stores
+    def add_store(
+        self,
+        name: str,
+        rows,
+        page_offsets: Optional[Sequence[int]] = None,
+        fixed_rows: int = 0,
+    ) -> None:
+        """Upload a named store. rows: [total_rows,128] numpy fp16/fp32 (host) or a torch CUDA tensor
+        on this device. fp32 rows are cast to the fp16 store dtype (qdrant_indexer.py:423-441)."""
+        on_device = 0
+        keep = None
+        try:
+            import torch
+
+            if isinstance(rows, torch.Tensor):
+                if rows.is_cuda:
+                    if rows.device.index != self.device:
+                        raise ValueError("rows tensor is on a different device than the corpus")
+                    if rows.dtype not in (torch.float16, torch.float32):
+                        rows = rows.float()
+                    keep = rows.contiguous()
+                    torch.cuda.synchronize(rows.device)
+                    dtype = N.VRAG_F16 if keep.dtype == torch.float16 else N.VRAG_F32
+                    total = keep.shape[0]
+                    ptr = C.c_void_p(keep.data_ptr())
+                    on_device = 1
+                else:
+                    rows = rows.float().numpy() if rows.dtype == torch.bfloat16 else rows.numpy()
+        except ImportError:  # pragma: no cover
+            pass
+        if not on_device:
+            arr = np.asarray(rows)
+            if arr.dtype not in (np.float16, np.float32):
+                arr = arr.astype(np.float32)
+            arr = np.ascontiguousarray(arr.reshape(-1, DIM))
+            keep = arr
+            dtype = N.VRAG_F16 if arr.dtype == np.float16 else N.VRAG_F32
+            total = arr.shape[0]
+            ptr = arr.ctypes.data_as(C.c_void_p)
+        if fixed_rows > 0:
+            if total % fixed_rows:
+                raise ValueError("total rows is not a multiple of fixed_rows")
+            n_pages = total // fixed_rows
+            off_p = None
+        else:
+            off = np.ascontiguousarray(np.asarray(page_offsets, dtype=np.int64))
+            if off.ndim != 1 or off.size < 1:
+                raise ValueError("page_offsets must be a 1-D array of n_pages+1 row offsets")
+            if int(off[-1]) != total:
+                raise ValueError("page_offsets[-1] must equal the number of rows")
+            n_pages = off.size - 1
+            off_p = off.ctypes.data_as(C.POINTER(C.c_int64))
+        N.check(
+            self._lib.vrag_store_add(
+                self._h, name.encode(), ptr, dtype, on_device, off_p, int(n_pages), int(fixed_rows)
+            )
+        )
+        del keep
+
+    def add_synthetic_store(
+        self,
+        name: str,
+        n_pages: int,
+        fixed_rows: int = 0,
+        page_offsets: Optional[Sequence[int]] = None,
+        seed: int = 0,
+        row_seed_base: int = 0,
+    ) -> None:
+        """Generate the seeded synthetic corpus of SURVEY.md §8(d) on the device (unit-norm gaussian
+        rows rounded to fp16)."""
+        off_p = None
+        if fixed_rows <= 0:
+            off = np.ascontiguousarray(np.asarray(page_offsets, dtype=np.int64))
+            n_pages = off.size - 1
+            off_p = off.ctypes.data_as(C.POINTER(C.c_int64))
+        N.check(
+            self._lib.vrag_store_add_synthetic(
+                self._h, name.encode(), off_p, int(n_pages), int(fixed_rows), C.c_uint64(seed), int(row_seed_base)
+            )
+        )
+
+    def drop_store(self, name: str) -> None:
+        N.check(self._lib.vrag_store_drop(self._h, name.encode()))
+
+    def store_info(self, name: str) -> Dict[str, int]:
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        N.check(self._lib.vrag_store_info(self._h, name.encode(), C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"n_pages": a.value, "total_rows": b.value, "fixed_rows": c.value, "max_rows": d.value}
+
+    def has_store(self, name: str) -> bool:
+        a = C.c_int64()
+        return self._lib.vrag_store_info(self._h, name.encode(), C.byref(a), None, None, None) == 0
+
+    def n_pages(self, name: str) -> int:
+        return self.store_info(name)["n_pages"]
+
+    def read_rows(self, name: str, row0: int, n_rows: int) -> np.ndarray:
+        out = np.empty((int(n_rows), DIM), dtype=np.float16)
+        N.check(
+            self._lib.vrag_store_read_rows(self._h, name.encode(), int(row0), int(n_rows), out.ctypes.data_as(C.c_void_p))
+        )
+        return out
+
+    def page_range(self, name: str, local_page: int) -> Tuple[int, int]:
+        r0, n = C.c_int64(), C.c_int64()
+        N.check(self._lib.vrag_store_page_range(self._h, name.encode(), int(local_page), C.byref(r0), C.byref(n)))
+        return r0.value, n.value
+
+    def read_page(self, name: str, local_page: int) -> np.ndarray:
+        """fp16 rows of one page ([rows,128]) — what qdrant `retrieve(with_vectors=[name])` returns
+        (two_stage.py:383-400)."""
+        r0, n = self.page_range(name, local_page)
+        return self.read_rows(name, r0, n)
+
+    # ------------------------------------------------------------------ scoring
+    def score(
+        self,
+        name: str,
+        query,
+        normalize: bool = True,
+        pool_query: bool = False,
+        candidate_ids: Optional[Sequence[int]] = None,
+    ) -> np.ndarray:
+        """MaxSim score of every page (or of the listed global page ids). fp32 [n]."""
+        q = _as_f32_query(query)
+        if candidate_ids is None:
+            n = self.n_pages(name)
+            cand_p, n_cand = None, 0
+        else:
+            cand = np.ascontiguousarray(np.asarray(candidate_ids, dtype=np.int64))
+            n = n_cand = cand.size
+            cand_p = cand.ctypes.data_as(C.POINTER(C.c_int64))
+        out = np.empty((n,), dtype=np.float32)
+        N.check(
+            self._lib.vrag_score(
+                self._h, name.encode(), q.ctypes.data_as(C.POINTER(C.c_float)), q.shape[0],
+                query_flags(normalize, pool_query), cand_p, n_cand, out.ctypes.data_as(C.POINTER(C.c_float)),
+            )
+        )
+        return out
+
+    def search(
+        self,
+        name: str,
+        query,
+        k: int,
+        normalize: bool = True,
+        pool_query: bool = False,
+        candidate_ids: Optional[Sequence[int]] = None,
+    ) -> Tuple[np.ndarray, np.ndarray]:
+        """Top-k pages by MaxSim: (scores fp32 [m], global page ids int64 [m]), m <= k, sorted by score
+        descending, ties by lower id."""
+        q = _as_f32_query(query)
+        k = int(k)
+        if k < 1:
+            return np.empty((0,), np.float32), np.empty((0,), np.int64)
+        if candidate_ids is None:
+            cand_p, n_cand = None, 0
+        else:
+            cand = np.ascontiguousarray(np.asarray(candidate_ids, dtype=np.int64))
+            n_cand = cand.size
+            cand_p = cand.ctypes.data_as(C.POINTER(C.c_int64))
+        scores = np.empty((k,), dtype=np.float32)
+        ids = np.empty((k,), dtype=np.int64)
+        cnt = C.c_int()
+        N.check(
+            self._lib.vrag_search(
+                self._h, name.encode(), q.ctypes.data_as(C.POINTER(C.c_float)), q.shape[0],
+                query_flags(normalize, pool_query), cand_p, n_cand, k,
+                scores.ctypes.data_as(C.POINTER(C.c_float)), ids.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(cnt),
+            )
+        )
+        m = cnt.value
+        return scores[:m], ids[:m]
+
+    def search_multistage(
+        self,
+        stages: Sequence[Tuple[str, bool, int]],
+        query,
+        normalize: bool = True,
+    ) -> List[Tuple[np.ndarray, np.ndarray]]:
+        """Fused multi-stage search: stages = [(store name, pool_query, k), ...]; stage s is restricted to
+        the survivors of stage s-1. One host synchronisation. Returns per-stage (scores, ids)."""
+        q = _as_f32_query(query)
+        ns = len(stages)
+        names = (C.c_char_p * ns)(*[s[0].encode() for s in stages])
+        flags = (C.c_uint32 * ns)(*[query_flags(normalize, bool(s[1])) for s in stages])
+        ks = (C.c_int * ns)(*[int(s[2]) for s in stages])
+        total = int(sum(int(s[2]) for s in stages))
+        scores = np.empty((total,), dtype=np.float32)
+        ids = np.empty((total,), dtype=np.int64)
+        counts = (C.c_int * ns)()
+        N.check(
+            self._lib.vrag_search_multistage(
+                self._h, ns, names, flags, ks, q.ctypes.data_as(C.POINTER(C.c_float)), q.shape[0],
+                scores.ctypes.data_as(C.POINTER(C.c_float)), ids.ctypes.data_as(C.POINTER(C.c_int64)), counts,
+            )
+        )
+        out = []
+        off = 0
+        for s in range(ns):
+            m = counts[s]
+            out.append((scores[off : off + m].copy(), ids[off : off + m].copy()))
+            off += int(stages[s][2])
+        return out
+
+    # ------------------------------------------------------------------ device-pointer variants (multi-GPU path)
+    def score_dev(self, name: str, query_dev_ptr: int, n_query_rows: int, flags: int, cand_dev_ptr: int,
+                  n_cand: int, out_scores_dev_ptr: int, stream: int) -> None:
+        N.check(
+            self._lib.vrag_score_dev(
+                self._h, name.encode(), C.c_void_p(query_dev_ptr), int(n_query_rows), int(flags),
+                C.c_void_p(cand_dev_ptr) if cand_dev_ptr else None, int(n_cand), C.c_void_p(out_scores_dev_ptr),
+                C.c_void_p(stream),
+            )
+        )
+
+    def topk_dev(self, scores_dev_ptr: int, ids_dev_ptr: int, id_base: int, n: int, k: int,
+                 out_scores_dev_ptr: int, out_ids_dev_ptr: int, stream: int) -> None:
+        N.check(
+            self._lib.vrag_topk_dev(
+                self._h, C.c_void_p(scores_dev_ptr), C.c_void_p(ids_dev_ptr) if ids_dev_ptr else None, int(id_base),
+                int(n), int(k), C.c_void_p(out_scores_dev_ptr), C.c_void_p(out_ids_dev_ptr), C.c_void_p(stream),
+            )
+        )
+
+    # ------------------------------------------------------------------ measurement
+    def last_timing_ms(self) -> Tuple[float, float]:
+        buf = (C.c_float * 2)()
+        N.check(self._lib.vrag_last_timing(self._h, buf, 2))
+        return float(buf[0]), float(buf[1])
+
+    def launch_count(self) -> int:
+        return int(self._lib.vrag_launch_count(self._h))
