@@ -29,6 +29,13 @@ constexpr int kTileBytes = kTileRows * kDim * 2;  // 32 KB of fp16 per stage
 constexpr int kHalfBytes = kTileBytes / 2;        // one K-half (64 fp16 = 128 B per row)
 constexpr int kBoxRowsSmall = 32;    // partial tiles are fetched in 32-row boxes
 constexpr int kScanThreads = 192;    // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+// inv_norm rows travel by 1-D TMA whose global start must be 16-byte aligned: fetch from (row & ~3) with a
+// box 4 floats longer and let the epilogue index with the misalignment (row & 3).
+// A tile is split into 128/slot_rows slots (1 slot unless candidates are packed); slot j keeps its scales at
+// sc[j*(slot_rows+32) + (row & 3) + i] so that boxes of different candidates never overlap.
+constexpr int kScaleStride = 256;    // floats per stage (4 slots * (32 + 32))
+constexpr int kScaleBoxBig = kTileRows + 4;
+constexpr int kScaleBoxSmall = kBoxRowsSmall + 4;
 constexpr float kLoScale = 2048.0f;  // lo half of the query is stored scaled by 2^11 (keeps it fp16-normal)
 
 struct ScanParams {
@@ -42,7 +49,7 @@ struct ScanParams {
   float* scores;              // [n_items]; items whose page is not in this shard get -inf
   int q_valid;                // real query rows (<= QP)
   int use_scale;              // 1: multiply by inv_norm rows (normalize=True)
-  int slot_rows;              // PACKED + cand: rows reserved per candidate inside a tile (32/64/128)
+  int slot_rows;              // rows reserved per candidate inside a tile (32/64/128); 128 unless PACKED + cand
   int pages_per_tile;         // PACKED + dense + fixed_rows: floor(128 / fixed_rows)
   const int* tile_page0;      // PACKED + dense + variable rows: [n_tiles+1] first page of each tile
   long long n_tiles;          // PACKED: number of tiles (work units)
@@ -60,11 +67,11 @@ struct ScanCfg {
   static constexpr int stages(bool packed) {
     const int budget = 227 * 1024 - 1024 /*align slack*/ - B_BYTES - MISC_BYTES -
                        (packed ? SC_BUFS * QP * SC_PITCH * 4 : 0);
-    const int s = budget / (kTileBytes + kTileRows * 4);
+    const int s = budget / (kTileBytes + kScaleStride * 4);
     return s > 6 ? 6 : s;
   }
   static constexpr size_t smem_bytes(bool packed) {
-    return 1024 + size_t(stages(packed)) * (kTileBytes + kTileRows * 4) + B_BYTES + MISC_BYTES +
+    return 1024 + size_t(stages(packed)) * (kTileBytes + kScaleStride * 4) + B_BYTES + MISC_BYTES +
            (packed ? SC_BUFS * QP * SC_PITCH * 4 : 0);
   }
 };
@@ -91,26 +98,29 @@ __device__ __forceinline__ long long item_page(const ScanParams& p, long long it
 }
 
 // Fetch `nrows` (1..128) document rows starting at global row `row` into tile rows [dst_row, dst_row+nrows)
-// of stage buffer `a` (+ their inv_norm scales). dst_row is a multiple of 32. Returns bytes issued.
+// of stage buffer `a` (+ their inv_norm scales at sc[(row & 3) ...]). dst_row is a multiple of 32.
+// Returns the bytes the mbarrier must expect.
 __device__ __forceinline__ uint32_t issue_rows(uint8_t* a, float* sc, uint64_t* bar, const CUtensorMap* tm128,
                                                const CUtensorMap* tm32, const CUtensorMap* ts128,
                                                const CUtensorMap* ts32, long long row, int nrows, int dst_row,
                                                bool use_scale) {
+  const int32_t r32 = static_cast<int32_t>(row);
   if (dst_row == 0 && nrows > 96) {
-    tma_load_2d(a, tm128, bar, 0, static_cast<int32_t>(row));
-    tma_load_2d(a + kHalfBytes, tm128, bar, 64, static_cast<int32_t>(row));
-    if (use_scale) tma_load_1d(sc, ts128, bar, static_cast<int32_t>(row));
-    return kTileBytes + (use_scale ? kTileRows * 4 : 0);
+    tma_load_2d(a, tm128, bar, 0, r32);
+    tma_load_2d(a + kHalfBytes, tm128, bar, 64, r32);
+    if (use_scale) tma_load_1d(sc, ts128, bar, r32 & ~3);
+    return kTileBytes + (use_scale ? kScaleBoxBig * 4 : 0);
   }
   const int nb = (nrows + kBoxRowsSmall - 1) / kBoxRowsSmall;
   for (int j = 0; j < nb; ++j) {
-    const int32_t r = static_cast<int32_t>(row) + j * kBoxRowsSmall;
+    const int32_t r = r32 + j * kBoxRowsSmall;
     const int d = dst_row + j * kBoxRowsSmall;
     tma_load_2d(a + d * 128, tm32, bar, 0, r);
     tma_load_2d(a + kHalfBytes + d * 128, tm32, bar, 64, r);
-    if (use_scale) tma_load_1d(sc + d, ts32, bar, r);
+    // consecutive scale boxes of one slot overlap by 4 floats in smem; both write identical values there
+    if (use_scale) tma_load_1d(sc + j * kBoxRowsSmall, ts32, bar, r & ~3);
   }
-  return nb * (kBoxRowsSmall * kDim * 2 + (use_scale ? kBoxRowsSmall * 4 : 0));
+  return nb * (kBoxRowsSmall * kDim * 2 + (use_scale ? kScaleBoxSmall * 4 : 0));
 }
 
 // In-place butterfly max over the 32 lanes of a warp for CNT (power of two <= 32) values per lane.
@@ -157,15 +167,16 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * kTileBytes;
   float* sScale = reinterpret_cast<float*>(sB + Cfg::B_BYTES);
-  float* sSc = sScale + STAGES * kTileRows;                       // PACKED: [SC_BUFS][QP][SC_PITCH]
+  float* sSc = sScale + STAGES * kScaleStride;                       // PACKED: [SC_BUFS][QP][SC_PITCH]
   uint8_t* misc = reinterpret_cast<uint8_t*>(sSc + (PACKED ? Cfg::SC_BUFS * QP * Cfg::SC_PITCH : 0));
   uint64_t* full = reinterpret_cast<uint64_t*>(misc);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + ACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC);
-  float* sRed = reinterpret_cast<float*>(misc + 256);             // LARGE: [2][4][QP]   (<= 4 KB - 256 at QP=64..)
-  int* sSeg = reinterpret_cast<int*>(misc + 256);                 // PACKED: [2][3][128] ints (item, begin, end)
+  int* sMis = reinterpret_cast<int*>(misc + 256);                 // [STAGES][4] scale misalignment per slot
+  float* sRed = reinterpret_cast<float*>(misc + 512);             // LARGE: [2][4][QP]
+  int* sSeg = reinterpret_cast<int*>(misc + 512);                 // PACKED: [2][3][128] ints (item, begin, end)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -214,18 +225,19 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             const int rows = min(kTileRows, nrows - t0);
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* a = sA + stage * kTileBytes;
-            float* sc = sScale + stage * kTileRows;
+            float* sc = sScale + stage * kScaleStride;
             // copies first, then one arrive.expect_tx with the exact byte count: the phase cannot complete
             // before the arrive, and the tx-count may go transiently negative.
             const uint32_t bytes = issue_rows(a, sc, &full[stage], &tm_rows128, &tm_rows32, &tm_scale128,
                                               &tm_scale32, row0 + t0, rows, 0, use_scale);
+            sMis[stage * 4] = static_cast<int>((row0 + t0) & 3);
             mbar_arrive_expect_tx(&full[stage], bytes);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         } else {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* a = sA + stage * kTileBytes;
-          float* sc = sScale + stage * kTileRows;
+          float* sc = sScale + stage * kScaleStride;
           if (p.cand == nullptr) {
             // dense: pages [pg0, pg1) are contiguous rows -> one fetch
             long long pg0, pg1;
@@ -245,6 +257,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             if (rows > 0)
               bytes = issue_rows(a, sc, &full[stage], &tm_rows128, &tm_rows32, &tm_scale128, &tm_scale32, r0, rows,
                                  0, use_scale);
+            sMis[stage * 4] = static_cast<int>(r0 & 3);
             mbar_arrive_expect_tx(&full[stage], bytes);
           } else {
             // candidates: each occupies its own slot of slot_rows rows
@@ -257,9 +270,11 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
               int nr;
               resolve_page(p, item_page(p, i0 + j), r0, nr);
               if (nr > 0)
-                bytes += issue_rows(a, sc, &full[stage], &tm_rows128, &tm_rows32, &tm_scale128, &tm_scale32, r0, nr,
-                                    j * p.slot_rows, use_scale);
+                bytes += issue_rows(a, sc + j * (p.slot_rows + 32), &full[stage], &tm_rows128, &tm_rows32,
+                                    &tm_scale128, &tm_scale32, r0, nr, j * p.slot_rows, use_scale);
+              sMis[stage * 4 + j] = static_cast<int>(r0 & 3);
             }
+            for (int j = cnt; j < 4; ++j) sMis[stage * 4 + j] = 0;   // unused slots: rows are never read back
             mbar_arrive_expect_tx(&full[stage], bytes);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -328,7 +343,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           float scale = 1.0f;
           if (use_scale) {
             mbar_wait(&full[stage], phase);  // acquire the TMA-written scale rows
-            scale = sScale[stage * kTileRows + trow];
+            scale = sScale[stage * kScaleStride + trow + sMis[stage * 4]];
           }
 #pragma unroll
           for (int c = 0; c < QP; c += 8) {
@@ -422,7 +437,9 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         float scale = 1.0f;
         if (use_scale) {
           mbar_wait(&full[stage], phase);
-          scale = sScale[stage * kTileRows + trow];
+          const int slot = trow / p.slot_rows;
+          scale = sScale[stage * kScaleStride + slot * (p.slot_rows + 32) + (trow - slot * p.slot_rows) +
+                         sMis[stage * 4 + slot]];
         }
 #pragma unroll
         for (int c = 0; c < QP; c += 8) {

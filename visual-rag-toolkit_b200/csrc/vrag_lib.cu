@@ -260,8 +260,8 @@ static int finish_store(vrag_corpus* c, Store& s, const int64_t* page_offsets, i
   if (s.total_rows > 0) {
     TRY(make_rows_map(&s.tm128, s.rows, s.total_rows, kTileRows));
     TRY(make_rows_map(&s.tm32, s.rows, s.total_rows, kBoxRowsSmall));
-    TRY(make_scale_map(&s.ts128, s.inv, s.total_rows, kTileRows));
-    TRY(make_scale_map(&s.ts32, s.inv, s.total_rows, kBoxRowsSmall));
+    TRY(make_scale_map(&s.ts128, s.inv, s.total_rows, kScaleBoxBig));
+    TRY(make_scale_map(&s.ts32, s.inv, s.total_rows, kScaleBoxSmall));
   }
   return 0;
 }
@@ -467,6 +467,7 @@ static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int
   p.scores = d_scores;
   p.q_valid = q_eff;
   p.use_scale = normalize ? 1 : 0;
+  p.slot_rows = kTileRows;
   long long n_units = n_items;
   if (s.packed) {
     if (d_cand) {
