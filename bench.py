@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: exhaustive ColBERT MaxSim over a GPU-resident, page-sharded corpus.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                     (the reference's CPU algorithm on the host cores)
+
+Workload (BASELINE.json configs[3] per-GPU shard; weak scaling): every GPU holds
+`--pages-per-gpu` (default 500,000) ColPali-v1.3-shaped pages x 1030 tokens x 128-d fp16
+(131.8 GB/GPU — 4M pages at N=8, i.e. cfg3; 1M pages at N=2, i.e. the cfg1 corpus) generated on the
+device from a counter-based seeded generator. One step = one 20-token query scored against EVERY page
+(exact MaxSim), exact top-10 per shard, NCCL all-gather merge of the per-shard lists.
+  value  : pages/s, corpus and query resident in HBM, CUDA-event timed, max over ranks.
+  e2e    : same metric through the public host API (numpy query in, top-10 (score,id) out) — pinned H2D of the
+           query and D2H of the result inside the timed region, wall-clock, max over ranks.
+  extra  : two-stage (tokens_vs_standard_pooling, prefetch_k=256, top-10) QPS / p50 / p95 through the same API.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "visual-rag-toolkit_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+TOKENS = 1030          # ColPali-v1.3: 1024 visual + 6 instruction tokens
+POOLED_ROWS = 32       # mean_pooling rows per page (colpali_row_mean_pooling)
+Q_TOKENS = 20
+TOP_K = 10
+PREFETCH_K = 256
+SEED = 20260318
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_sample_pages_per_s(docs_f32, query, n_threads_note=True):
+    """The oracle's search_exhaustive (= the reference's client-side CPU path, quick_test.py:158-166) timed on
+    a bounded sample. Returns (pages/s, seconds, blas_threads)."""
+    from oracle import maxsim_oracle as MO
+
+    t0 = time.perf_counter()
+    MO.search_exhaustive(query, docs_f32, TOP_K)
+    dt = time.perf_counter() - t0
+    threads = 1
+    try:
+        from threadpoolctl import threadpool_info
+
+        threads = max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
+    except Exception:
+        pass
+    return len(docs_f32) / dt, dt, threads
+
+
+def host_sample(n_pages, seed):
+    """Seeded ColPali-shaped pages on the host (fp16-representable fp32), for the CPU arms."""
+    rng = np.random.default_rng(seed)
+    docs = []
+    for _ in range(n_pages):
+        x = rng.standard_normal((TOKENS, 128), dtype=np.float32)
+        x /= np.linalg.norm(x, axis=1, keepdims=True)
+        docs.append(x.astype(np.float16).astype(np.float32))
+    return docs
+
+
+def _ref_worker(args):
+    n_pages, seed, qseed, reps = args
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import maxsim_oracle as MO
+
+    docs = host_sample(n_pages, seed)
+    q = np.random.default_rng(qseed).standard_normal((Q_TOKENS, 128)).astype(np.float32)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        MO.search_exhaustive(q, docs, TOP_K)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port of quick_test.search_exhaustive ->
+    compute_maxsim_score) on all host cores: the page sample is split over one process per core, each
+    running the reference's per-page Python loop; a step = one query over the whole sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    workers = max(1, min(cores, 64))
+    pages_per_worker = max(8, args.ref_sample_pages // workers)
+    total_pages = pages_per_worker * workers
+    reps = args.warmup + args.steps
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        res = pool.map(_ref_worker, [(pages_per_worker, SEED + 1000 + w, SEED + 7, reps) for w in range(workers)])
+    # a step finishes when the slowest worker has scored its slice
+    step_times = [max(r[i] for r in res) for i in range(args.warmup, reps)]
+    dt = sum(step_times)
+    value = total_pages * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "exhaustive_maxsim_pages_per_s", "value": value, "unit": "pages/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"exhaustive MaxSim top-{TOP_K}, ColPali-shaped pages x {TOKENS} tok x 128-d, {Q_TOKENS}-token query "
+                               f"(CPU arm: bounded sample of {total_pages} pages per step)",
+                   "pages_per_step": total_pages, "tokens_per_page": TOKENS, "query_tokens": Q_TOKENS, "top_k": TOP_K},
+        "cpu_baseline": {"value": value, "unit": "pages/s", "cores": workers, "kind": "port",
+                         "sample": f"{total_pages} pages/step split over {workers} processes (1 BLAS thread each), "
+                                   "oracle/maxsim_oracle.py::search_exhaustive"},
+        "e2e": {"value": value, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    from visual_rag_b200.corpus import GpuCorpus
+    from visual_rag_b200.distributed import ShardedSearcher
+
+    pages = args.pages_per_gpu
+    corpus = GpuCorpus(local_rank, page_base=rank * pages)
+    t_gen0 = time.perf_counter()
+    corpus.add_synthetic_store("initial", pages, fixed_rows=TOKENS, seed=SEED, row_seed_base=rank * pages * TOKENS)
+    corpus.add_synthetic_store("mean_pooling", pages, fixed_rows=POOLED_ROWS, seed=SEED + 1,
+                               row_seed_base=rank * pages * POOLED_ROWS)
+    gen_s = time.perf_counter() - t_gen0
+    searcher = ShardedSearcher(corpus)
+    rng = np.random.default_rng(SEED + 7)
+    queries = [rng.standard_normal((Q_TOKENS, 128)).astype(np.float32) for _ in range(max(8, args.steps + args.warmup))]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ex_stage = [("initial", False, TOP_K)]
+    ts_stages = [("mean_pooling", False, PREFETCH_K), ("initial", False, TOP_K)]
+
+    # ---------------- correctness spot check against the oracle (rank 0, a few pages read back) ----------------
+    if rank == 0:
+        from oracle import maxsim_oracle as MO
+
+        sc = corpus.score("initial", queries[0], candidate_ids=[corpus.page_base + 3, corpus.page_base + pages - 1])
+        for s, p in zip(sc, (3, pages - 1)):
+            want = MO.maxsim_score(queries[0], corpus.read_page("initial", p).astype(np.float32))
+            assert abs(s - want) <= 1e-3 * abs(want), ("parity spot check failed", s, want)
+
+    # ---------------- device-resident throughput (value) ----------------
+    nq = searcher.upload_query(queries[0])
+    for _ in range(args.warmup):
+        searcher.search_multistage_device(ex_stage, nq)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = corpus.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        searcher.search_multistage_device(ex_stage, nq)
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = corpus.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- dominant kernel alone (roofline numerator), same stream, CUDA events ----------------
+    scores_buf = torch.empty((pages,), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    from visual_rag_b200.corpus import query_flags
+
+    for _ in range(2):
+        corpus.score_dev("initial", searcher._q_dev.data_ptr(), nq, query_flags(True, False), 0, pages, scores_buf.data_ptr(), stream)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        corpus.score_dev("initial", searcher._q_dev.data_ptr(), nq, query_flags(True, False), 0, pages, scores_buf.data_ptr(), stream)
+    k1.record()
+    torch.cuda.synchronize()
+    # each score_dev = query_prep (tiny) + the scan kernel; the prep kernel is ~2 us of the ~20 ms
+    kern_ms = k0.elapsed_time(k1) / args.steps
+
+    # ---------------- end to end through the host API ----------------
+    for i in range(args.warmup):
+        searcher.search("initial", queries[i % len(queries)], TOP_K)
+    barrier()
+    t0 = time.perf_counter()
+    last = None
+    for i in range(args.steps):
+        last = searcher.search("initial", queries[i % len(queries)], TOP_K)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    # ---------------- two-stage latency (extra) ----------------
+    n_lat = args.latency_queries
+    for i in range(5):
+        searcher.search_multistage(ts_stages, queries[i % len(queries)])
+    barrier()
+    lat = []
+    t_all0 = time.perf_counter()
+    for i in range(n_lat):
+        t1 = time.perf_counter()
+        searcher.search_multistage(ts_stages, queries[i % len(queries)])
+        lat.append(1e3 * (time.perf_counter() - t1))
+    ts_wall = time.perf_counter() - t_all0
+    barrier()
+
+    # ---------------- max over ranks ----------------
+    vals = torch.tensor([dev_ms, e2e_s, kern_ms, ts_wall, float(np.percentile(lat, 50)), float(np.percentile(lat, 95))],
+                        dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s, kern_ms, ts_wall, p50, p95 = [float(v) for v in vals.cpu()]
+
+    if rank == 0:
+        total_pages = pages * world
+        peak, peak_src = measured_peaks()
+        bytes_per_page = TOKENS * 128 * 2 + TOKENS * 4          # fp16 tokens + fp32 inv-norm side array
+        achieved = pages * bytes_per_page / (kern_ms * 1e-3) / 1e9
+        # CPU baseline on a bounded sample of the SAME corpus (pages read back from the device)
+        n_cpu = args.cpu_sample_pages
+        docs = [corpus.read_page("initial", p).astype(np.float32) for p in range(n_cpu)]
+        cpu_pps, cpu_s, blas_threads = cpu_sample_pages_per_s(docs, queries[0])
+        gpu_top = corpus.search("initial", queries[0], TOP_K, candidate_ids=list(range(corpus.page_base, corpus.page_base + n_cpu)))
+        from oracle import maxsim_oracle as MO
+
+        cpu_top = MO.search_exhaustive(queries[0], docs, TOP_K)
+        parity_ok = [int(i) for i in gpu_top[1]] == [corpus.page_base + i for i, _ in cpu_top]
+        line = {
+            "metric": "exhaustive_maxsim_pages_per_s",
+            "value": total_pages * args.steps / (dev_ms * 1e-3),
+            "unit": "pages/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands, f32 accumulate (query carried as f16 hi/lo pair)",
+            "data": "synthetic",
+            "config": {
+                "workload": f"exhaustive MaxSim top-{TOP_K} over {total_pages} ColPali-shaped pages "
+                            f"({pages}/GPU x {TOKENS} tok x 128-d fp16 = {pages * TOKENS * 256 / 1e9:.1f} GB/GPU; "
+                            f"BASELINE configs[3] shard), {Q_TOKENS}-token query, NCCL all-gather top-k merge",
+                "pages_per_gpu": pages, "tokens_per_page": TOKENS, "query_tokens": Q_TOKENS, "top_k": TOP_K,
+                "l2": "input (>=26 GB per step) is far larger than the 126 MB L2; no flush needed",
+                "corpus_generation_s": gen_s,
+            },
+            "hbm_gbs_algorithmic": total_pages * bytes_per_page * args.steps / (dev_ms * 1e-3) / 1e9,
+            "e2e": {"value": total_pages * args.steps / e2e_s, "unit": "pages/s",
+                    "h2d_bytes_per_step": Q_TOKENS * 128 * 4, "d2h_bytes_per_step": TOP_K * (4 + 8),
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "vrag::maxsim_scan_kernel<32,false>", "achieved": achieved,
+                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_of_8TBs_nominal": achieved / 8000.0,
+                         "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": pages * bytes_per_page,
+                         "traffic": args.ncu_traffic_bytes},
+            "cpu_baseline": {"value": cpu_pps, "unit": "pages/s", "cores": blas_threads, "kind": "port",
+                             "sample": f"first {n_cpu} pages of the same corpus read back from the device, one query, "
+                                       f"{cpu_s:.1f} s; oracle/maxsim_oracle.py::search_exhaustive (single process, numpy BLAS threads={blas_threads})",
+                             "topk_matches_gpu": bool(parity_ok)},
+            "two_stage": {"mode": "tokens_vs_standard_pooling", "prefetch_k": PREFETCH_K, "top_k": TOP_K,
+                          "qps": n_lat / ts_wall, "p50_ms": p50, "p95_ms": p95, "queries": n_lat,
+                          "pooled_rows_per_page": POOLED_ROWS, "note": "mean_pooling store is synthetic (same shape as row-mean pooling)"},
+            "last_top1": [float(last[0][0]), int(last[1][0])] if last is not None and len(last[0]) else None,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    corpus.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pages-per-gpu", type=int, default=500_000)
+    ap.add_argument("--cpu-sample-pages", type=int, default=3000)
+    ap.add_argument("--ref-sample-pages", type=int, default=4096)
+    ap.add_argument("--latency-queries", type=int, default=200)
+    ap.add_argument("--ncu-traffic-bytes", type=float, default=None,
+                    help="dram bytes per launch of the scan kernel from the committed ncu capture (profiles/)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -91,11 +91,16 @@ int vrag_score(vrag_corpus_t* c, const char* name, const float* query, int n_que
  * store names[s] with flags[s], restricted to the survivors of stage s-1, and keeps ks[s] pages.
  *   two-stage  (TwoStageRetriever.search_server_side, two_stage.py:102-191): {pooled store, prefetch_k}, {"initial", top_k}
  *   three-stage (ThreeStageRetriever.search_server_side, three_stage.py:83-173): {global, stage1_k}, {experimental, stage2_k}, {"initial", top_k}
+ * q_offsets == NULL: every stage uses all n_query_rows rows (VRAG_Q_POOL in flags[s] mean-pools them for
+ * that stage). Otherwise stage s uses query rows [q_offsets[s], q_offsets[s+1]) — e.g. a client that sends the
+ * mean-pooled prefetch vector and the token matrix as two separate queries (two_stage.py:142,159).
+ * cand_ids != NULL restricts stage 0 to the listed global page ids (a payload / HasId filter).
  * Outputs are per stage, concatenated: stage s occupies [sum(ks[:s]), sum(ks[:s+1])) of out_scores/out_ids;
  * out_counts[s] valid entries each.                                                                */
 int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char* const* names, const uint32_t* flags,
-                           const int* ks, const float* query, int n_query_rows, float* out_scores,
-                           int64_t* out_ids, int* out_counts);
+                           const int* ks, const float* query, int n_query_rows, const int* q_offsets,
+                           const int64_t* cand_ids, int64_t n_cand, float* out_scores, int64_t* out_ids,
+                           int* out_counts);
 
 /* ------------------------------------------------------------------ device-pointer variants
  * Same kernels, caller-provided device buffers and stream (cudaStream_t passed as void*): used by the

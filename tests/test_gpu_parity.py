@@ -1,0 +1,315 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the committed reference goldens.
+Run on a B200: python -m pytest tests -m gpu.
+
+Tolerances: the north star allows 1e-3 relative on scores; the kernels carry the fp32 query as an fp16 hi/lo
+pair and accumulate in fp32, so the tests hold them to 2e-5 relative (+1e-6 absolute for near-zero scores).
+Top-k ids must be identical (the seeded cases have no ties inside that tolerance)."""
+import numpy as np
+import pytest
+
+import cases as CS
+from oracle import maxsim_oracle as MO
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 2e-5, 2e-6
+
+
+@pytest.fixture(scope="module")
+def corpus():
+    from visual_rag_b200.corpus import GpuCorpus
+
+    c = GpuCorpus(0)
+    yield c
+    c.close()
+
+
+def rows16(seed, n, scale=True):
+    return CS.unit_rows(seed, n, dtype=np.float16, scale=scale)
+
+
+def close(got, want, rtol=RTOL, atol=ATOL):
+    np.testing.assert_allclose(np.asarray(got, np.float64), np.asarray(want, np.float64), rtol=rtol, atol=atol)
+
+
+# ------------------------------------------------------------------ a1/a2: compute_maxsim_score / batch
+@pytest.mark.parametrize("case", CS.maxsim_cases(), ids=lambda c: c["key"])
+def test_maxsim_golden_cases(corpus, case, maxsim_golden):
+    q = CS.query_rows(case["seed"], case["q"])
+    d = CS.unit_rows(case["seed"] + 1, case["t"], dtype=np.float16, scale=True)
+    corpus.add_store("g", d, fixed_rows=case["t"])
+    want = maxsim_golden[case["key"]]
+    close(corpus.score("g", q)[0], want[0])
+    close(corpus.score("g", q, normalize=False)[0], want[1], rtol=1e-4)
+
+
+def test_bench_corpus_exhaustive_and_two_stage(corpus, maxsim_golden):
+    """a3/a4: quick_test.search_exhaustive / search_two_stage on the seeded in-memory corpus."""
+    q, docs = CS.bench_corpus()
+    rows = np.concatenate(docs).astype(np.float16)
+    corpus.add_store("initial", rows, fixed_rows=docs[0].shape[0])
+    close(corpus.score("initial", q), maxsim_golden["batch_scores"])
+    s, ids = corpus.search("initial", q, 10)
+    assert ids.tolist() == maxsim_golden["exhaustive_ids"].tolist()
+    close(s, maxsim_golden["exhaustive_scores"])
+    pooled = maxsim_golden["batch_pooled"]                      # fp32 tile means produced by the reference
+    corpus.add_store("mean_pooling", pooled.reshape(-1, 128), fixed_rows=pooled.shape[1])
+    (s1, id1), (s2, id2) = corpus.search_multistage([("mean_pooling", True, 30), ("initial", False, 10)], q)
+    assert id2.tolist() == maxsim_golden["two_stage_ids"].tolist()
+    close(s2, maxsim_golden["two_stage_scores"])
+    rank1 = np.array([id1.tolist().index(i) + 1 for i in id2])
+    # the store rounds the reference's fp32 pooled rows to fp16: stage-1 ranks may move by a tie-sized step only
+    assert np.abs(rank1 - maxsim_golden["two_stage_rank1"]).max() <= 2
+
+
+# ------------------------------------------------------------------ shape sweeps vs the oracle
+@pytest.mark.parametrize("q_rows", [1, 8, 20, 33, 100])
+@pytest.mark.parametrize("tokens", [129, 300, 1030])
+def test_large_pages_fixed(corpus, q_rows, tokens):
+    n = 37
+    q = CS.query_rows(100 + q_rows, q_rows)
+    rows = rows16(200 + tokens, n * tokens)
+    corpus.add_store("s", rows, fixed_rows=tokens)
+    want = [MO.maxsim_score(q, rows[i * tokens:(i + 1) * tokens].astype(np.float32)) for i in range(n)]
+    close(corpus.score("s", q), want)
+
+
+@pytest.mark.parametrize("q_rows", [1, 20, 64])
+def test_large_pages_variable_and_candidates(corpus, q_rows):
+    rng = np.random.default_rng(5)
+    lens = rng.integers(1, 700, size=61)
+    lens[3] = 768
+    lens[7] = 128
+    lens[9] = 129
+    off = np.concatenate([[0], np.cumsum(lens)])
+    rows = rows16(300 + q_rows, int(off[-1]))
+    q = CS.query_rows(400 + q_rows, q_rows)
+    corpus.add_store("s", rows, page_offsets=off)
+    want = np.array([MO.maxsim_score(q, rows[off[i]:off[i + 1]].astype(np.float32)) for i in range(len(lens))])
+    close(corpus.score("s", q), want)
+    cand = rng.permutation(len(lens))[:23]
+    close(corpus.score("s", q, candidate_ids=cand), want[cand])
+    want_nn = [MO.maxsim_score(q, rows[off[i]:off[i + 1]].astype(np.float32), normalize=False) for i in range(len(lens))]
+    close(corpus.score("s", q, normalize=False), want_nn, rtol=1e-4)
+
+
+@pytest.mark.parametrize("q_rows", [1, 20, 40])
+@pytest.mark.parametrize("r", [1, 12, 13, 32, 34, 64, 76, 128])
+def test_packed_pages_fixed(corpus, q_rows, r):
+    """Pooled stores: 12/13 rows (ColSmol tiles), 32/34 (ColPali rows / legacy conv), 76 (ColSmol experimental),
+    1 (global_pooling)."""
+    rng = np.random.default_rng(r)
+    n = 1001
+    rows = rows16(500 + r, n * r)
+    q = CS.query_rows(600 + q_rows, q_rows)
+    corpus.add_store("p", rows, fixed_rows=r)
+    want = np.array([MO.maxsim_score(q, rows[i * r:(i + 1) * r].astype(np.float32)) for i in range(n)])
+    close(corpus.score("p", q), want)
+    for ncand in (1, 3, 77):
+        cand = rng.permutation(n)[:ncand]
+        close(corpus.score("p", q, candidate_ids=cand), want[cand])
+    wantp = [MO.pooled_query_score(q, rows[i * r:(i + 1) * r].astype(np.float32)) for i in range(n)]
+    close(corpus.score("p", q, pool_query=True), wantp)
+
+
+def test_packed_pages_variable(corpus):
+    """ColQwen2.5-style pooled store: min(32, H_eff) rows per page."""
+    rng = np.random.default_rng(11)
+    lens = rng.integers(1, 33, size=777)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    rows = rows16(700, int(off[-1]))
+    q = CS.query_rows(701, 20)
+    corpus.add_store("p", rows, page_offsets=off)
+    want = np.array([MO.maxsim_score(q, rows[off[i]:off[i + 1]].astype(np.float32)) for i in range(len(lens))])
+    close(corpus.score("p", q), want)
+    cand = rng.permutation(len(lens))[:50]
+    close(corpus.score("p", q, candidate_ids=cand), want[cand])
+
+
+# ------------------------------------------------------------------ top-k semantics
+def test_topk_order_ties_and_padding(corpus):
+    n, r = 3000, 4
+    rows = rows16(800, n * r)
+    rows[r * 17:r * 18] = rows[r * 5:r * 6]       # page 17 duplicates page 5 -> exact tie
+    rows[r * 2999:r * 3000] = rows[r * 5:r * 6]
+    q = rows[r * 5:r * 6].astype(np.float32)       # makes the tied pages the best ones
+    corpus.add_store("t", rows, fixed_rows=r)
+    sc = corpus.score("t", q)
+    assert sc[5] == sc[17] == sc[2999]
+    for k in (1, 2, 3, 10, 256, 1000, 3000, 4096):
+        s, ids = corpus.search("t", q, k)
+        order = np.lexsort((np.arange(n), -sc))[:k]   # score desc, ties -> lower id (Python's stable sort)
+        assert ids.tolist() == order.tolist()
+        assert np.array_equal(s, sc[order])
+        assert len(ids) == min(k, n)
+    assert corpus.search("t", q, 3)[1].tolist() == [5, 17, 2999]
+
+
+def test_topk_multilevel_large(corpus):
+    n = 300_000
+    corpus.add_synthetic_store("g", n, fixed_rows=1, seed=1)
+    q = CS.query_rows(900, 1)
+    sc = corpus.score("g", q)
+    d = corpus.read_rows("g", 0, n).astype(np.float32)
+    want = (d / (np.linalg.norm(d, axis=1, keepdims=True) + 1e-8)) @ (q[0] / (np.linalg.norm(q[0]) + 1e-8))
+    close(sc, want, rtol=1e-4, atol=1e-5)
+    for k in (10, 1000, 4096):
+        s, ids = corpus.search("g", q, k)
+        order = np.lexsort((np.arange(n), -sc))[:k]
+        assert ids.tolist() == order.tolist() and np.array_equal(s, sc[order])
+
+
+# ------------------------------------------------------------------ edge cases
+def test_edge_cases(corpus):
+    from visual_rag_b200._native import VragError
+
+    rows = rows16(1000, 10 * 40)
+    q = CS.query_rows(1001, 5)
+    corpus.add_store("e", rows, fixed_rows=40)
+    s, ids = corpus.search("e", q, 50)                     # k > n
+    assert len(ids) == 10 and sorted(ids.tolist()) == list(range(10))
+    s, ids = corpus.search("e", q, 5, candidate_ids=[])    # empty candidate list
+    assert len(ids) == 0
+    sc = corpus.score("e", q, candidate_ids=[3, 99, -1, 3])  # ids outside the shard score -inf
+    assert np.isneginf(sc[1]) and np.isneginf(sc[2]) and sc[0] == sc[3]
+    off = np.array([0, 5, 5, 12], dtype=np.int64)          # an empty page
+    corpus.add_store("e2", rows[:12], page_offsets=off)
+    sc = corpus.score("e2", q)
+    assert np.isneginf(sc[1]) and np.isfinite(sc[0]) and np.isfinite(sc[2])
+    with pytest.raises(VragError, match="unknown vector store"):
+        corpus.score("missing", q)
+    with pytest.raises(VragError):
+        corpus.search("e", CS.query_rows(1, 200), 5)       # > 128 query tokens in one call
+    with pytest.raises(ValueError):
+        corpus.score("e", np.zeros((3, 64), np.float32))
+    zero = np.zeros((2 * 8, 128), np.float16)               # all-zero rows: 0/(0+1e-8) = 0, as in numpy
+    corpus.add_store("z", zero, fixed_rows=8)
+    assert corpus.score("z", q).tolist() == [0.0, 0.0]
+
+
+def test_page_base_shard_ids():
+    from visual_rag_b200.corpus import GpuCorpus
+
+    rows = rows16(1100, 20 * 150)
+    q = CS.query_rows(1101, 20)
+    with GpuCorpus(0, page_base=1000) as shard:
+        shard.add_store("initial", rows, fixed_rows=150)
+        s, ids = shard.search("initial", q, 5)
+        assert ids.min() >= 1000 and ids.max() < 1020
+        sc = shard.score("initial", q, candidate_ids=[1003, 3, 1019])
+        assert np.isfinite(sc[0]) and np.isneginf(sc[1]) and np.isfinite(sc[2])
+
+
+# ------------------------------------------------------------------ size-independent properties at scale
+def test_properties_on_large_synthetic_corpus(corpus):
+    n, t = 20_000, 1030
+    corpus.add_synthetic_store("big", n, fixed_rows=t, seed=42)
+    q = CS.query_rows(1200, 20)
+    sc = corpus.score("big", q)
+    assert np.all(np.isfinite(sc)) and sc.shape == (n,)
+    # (1) oracle on a bounded random sample of pages read back from the device
+    rng = np.random.default_rng(0)
+    for p in rng.choice(n, size=12, replace=False):
+        close(sc[p], MO.maxsim_score(q, corpus.read_page("big", int(p)).astype(np.float32)))
+    # (2) gather path == scan path, and candidate order does not matter
+    cand = rng.permutation(n)[:500]
+    g = corpus.score("big", q, candidate_ids=cand)
+    assert np.array_equal(g, sc[cand])
+    # (3) top-k is sorted, consistent with the score array, and idempotent under restriction to itself
+    s, ids = corpus.search("big", q, 100)
+    assert np.all(np.diff(s) <= 0) and np.array_equal(s, sc[ids])
+    s2, ids2 = corpus.search("big", q, 100, candidate_ids=ids)
+    assert np.array_equal(ids2, ids) and np.array_equal(s2, s)
+    # (4) MaxSim is additive over query tokens
+    a, b = corpus.score("big", q[:7]), corpus.score("big", q[7:])
+    close(a + b, sc, rtol=1e-5)
+    # (5) a page scored against its own tokens reaches the self-similarity bound Q (unit rows)
+    own = corpus.read_page("big", 123).astype(np.float32)[:16]
+    close(corpus.score("big", own, candidate_ids=[123])[0], 16.0, rtol=1e-3)
+    corpus.drop_store("big")
+
+
+# ------------------------------------------------------------------ retriever classes on the GPU client
+@pytest.fixture(scope="module")
+def gpu_client(corpus, retrieval_golden):
+    from visual_rag_b200.client import GpuCorpusClient
+
+    q, initial = CS.retrieval_corpus()
+    off_i = np.concatenate([[0], np.cumsum([d.shape[0] for d in initial])])
+    corpus.add_store("initial", np.concatenate(initial).astype(np.float16), page_offsets=off_i)
+    off = retrieval_golden["offsets_pooled"]
+    corpus.add_store("mean_pooling", retrieval_golden["mean_pooling"], page_offsets=off)
+    corpus.add_store("experimental_pooling", retrieval_golden["experimental_pooling"], page_offsets=off)
+    corpus.add_store("global_pooling", retrieval_golden["global_pooling"], fixed_rows=1)
+    n = len(initial)
+    client = GpuCorpusClient(corpus, "c", point_ids=list(range(n)), payloads=[{"page": i, "year": 2000 + i % 3} for i in range(n)])
+    return q, client
+
+
+def _same(got, want, keys):
+    assert [g["id"] for g in got] == [w["id"] for w in want]
+    for k in keys:
+        close([g[k] for g in got], [w[k] for w in want])
+
+
+def test_retrievers_match_reference_goldens(gpu_client, golden_index):
+    from visual_rag_b200.retrieval import (MultiVectorRetriever, SingleStageRetriever, ThreeStageRetriever,
+                                           TwoStageRetriever)
+
+    q, client = gpu_client
+    want = golden_index["retrieval"]
+    two = TwoStageRetriever(client, "c")
+    for mode in ("pooled_query_vs_tiles", "tokens_vs_tiles", "pooled_query_vs_global"):
+        _same(two.search(q, top_k=10, prefetch_k=40, stage1_mode=mode), want[f"two_stage_search::{mode}"],
+              ("score_stage1", "score_stage2", "score_final"))
+    _same(two.search(q, top_k=10, prefetch_k=40, stage1_mode="tokens_vs_tiles", use_reranking=False),
+          want["two_stage_search::norerank"], ("score_stage1", "score_final"))
+    for key, w in want.items():
+        if key.startswith("two_stage_server::"):
+            _same(two.search_server_side(q, top_k=10, prefetch_k=40, stage1_mode=key.split("::")[1]), w, ("score_final",))
+    for use_pooling in (False, True):
+        _same(two.search_single_stage(q, top_k=10, use_pooling=use_pooling), want[f"two_stage_single::{use_pooling}"],
+              ("score_final",))
+    three = ThreeStageRetriever(client, "c")
+    _same(three.search_server_side(query_embedding=q, top_k=10, stage1_k=80, stage2_k=30), want["three_stage"],
+          ("score_stage1", "score_stage2", "score_stage3", "score_final"))
+    single = SingleStageRetriever(client, "c")
+    for strat in ("multi_vector", "tiles_maxsim", "pooled_tile", "pooled_global", "experimental_maxsim", "pooled_experimental"):
+        _same(single.search(q, top_k=10, strategy=strat), want[f"single::{strat}"], ("score",))
+    mv = MultiVectorRetriever("c", qdrant_client=client)
+    _same(mv.search_embedded(query_embedding=q, top_k=10, mode="three_stage", stage1_k=80, stage2_k=30),
+          want["three_stage"], ("score_final",))
+    res = two.search(q, top_k=3, prefetch_k=40, stage1_mode="tokens_vs_tiles", return_embeddings=True)
+    assert res[0]["embedding"].shape[1] == 128 and res[0]["payload"]["page"] == res[0]["id"]
+
+
+def test_payload_and_id_filters(gpu_client):
+    from visual_rag_b200.retrieval import TwoStageRetriever
+    from visual_rag_b200.retrieval.models import Filter, HasIdCondition
+
+    q, client = gpu_client
+    two = TwoStageRetriever(client, "c")
+    f = two.build_filter(year=2001)
+    res = two.search_server_side(q, top_k=10, prefetch_k=40, filter_obj=f, stage1_mode="tokens_vs_standard_pooling")
+    assert len(res) == 10 and all(r["payload"]["year"] == 2001 for r in res)
+    allowed = [4, 9, 77, 120]
+    res = two.search_single_stage(q, top_k=10, filter_obj=Filter(must=[HasIdCondition(has_id=allowed)]))
+    assert sorted(r["id"] for r in res) == allowed
+    got = client.retrieve("c", ids=[9, 4], with_vectors=["initial", "global_pooling"])
+    assert [p.id for p in got] == [9, 4] and len(got[0].vector["global_pooling"]) == 1
+
+
+def test_reference_style_client_calls(gpu_client):
+    """The exact call shapes of the reference retrievers (two_stage.py:349-358, 162-178) against the client."""
+    from visual_rag_b200.retrieval.models import Prefetch, SearchParams
+
+    q, client = gpu_client
+    pts = client.query_points(collection_name="c", query=q.mean(axis=0).tolist(), using="mean_pooling",
+                              query_filter=None, limit=7, with_payload=True, with_vectors=False, timeout=120).points
+    assert len(pts) == 7 and pts[0].score >= pts[-1].score and isinstance(pts[0].score, float)
+    pts2 = client.query_points(collection_name="c", query=q.tolist(), using="initial", limit=5, query_filter=None,
+                               with_payload=True, search_params=SearchParams(exact=True),
+                               prefetch=[Prefetch(query=q.mean(axis=0).tolist(), using="mean_pooling", limit=7)],
+                               timeout=120).points
+    assert len(pts2) == 5 and {p.id for p in pts2} <= {p.id for p in pts}
+    assert client.get_collection("c").points_count == 150

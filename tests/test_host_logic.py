@@ -1,0 +1,170 @@
+"""Host-side logic of the retriever mirrors on CPU: they are driven through the in-memory client double
+(tests/golden/fake_qdrant.py, scoring with the oracle) and must reproduce what the REFERENCE retriever classes
+returned on the same corpus (tests/golden/golden_index.json)."""
+import numpy as np
+import pytest
+
+import cases as CS
+from fake_qdrant import NumpyQdrant
+from oracle import maxsim_oracle as MO
+from visual_rag_b200.retrieval import (MultiVectorRetriever, SingleStageRetriever, ThreeStageRetriever,
+                                       TwoStageRetriever)
+from visual_rag_b200.retrieval._common import resolve_stage1
+
+
+def _split(rows, offsets):
+    return [rows[offsets[i]:offsets[i + 1]].astype(np.float32) for i in range(len(offsets) - 1)]
+
+
+@pytest.fixture(scope="module")
+def setup(retrieval_golden, golden_index):
+    q, initial = CS.retrieval_corpus()
+    off = retrieval_golden["offsets_pooled"]
+    vectors = {
+        "initial": initial,
+        "mean_pooling": _split(retrieval_golden["mean_pooling"], off),
+        "experimental_pooling": _split(retrieval_golden["experimental_pooling"], off),
+        "global_pooling": [g.astype(np.float32) for g in retrieval_golden["global_pooling"]],
+    }
+    return q, NumpyQdrant(vectors, MO.maxsim_score), golden_index["retrieval"]
+
+
+def _ids(res):
+    return [r["id"] for r in res]
+
+
+def test_two_stage_search_matches_reference(setup):
+    q, client, want = setup
+    r = TwoStageRetriever(client, "c")
+    for mode in ("pooled_query_vs_tiles", "tokens_vs_tiles", "pooled_query_vs_global"):
+        got = r.search(q, top_k=10, prefetch_k=40, stage1_mode=mode)
+        w = want[f"two_stage_search::{mode}"]
+        assert _ids(got) == _ids(w)
+        for g, x in zip(got, w):
+            assert g["score_final"] == x["score_final"] and g["score_stage1"] == x["score_stage1"]
+            assert g["score_stage2"] == x["score_stage2"] and "payload" in g
+    got = r.search(q, top_k=10, prefetch_k=40, stage1_mode="tokens_vs_tiles", use_reranking=False)
+    assert _ids(got) == _ids(want["two_stage_search::norerank"])
+    assert all(g["score_final"] == g["score_stage1"] for g in got)
+
+
+def test_two_stage_search_accepts_new_vocabulary(setup):
+    """The reference's search() rejects its own default stage1_mode; the mirror accepts both."""
+    q, client, want = setup
+    r = TwoStageRetriever(client, "c")
+    a = r.search(q, top_k=10, prefetch_k=40)  # default pooled_query_vs_standard_pooling
+    assert _ids(a) == _ids(want["two_stage_search::pooled_query_vs_tiles"])
+    b = r.search(q, top_k=10, prefetch_k=40, stage1_mode="tokens_vs_experimental_pooling")
+    assert len(b) == 10
+    with pytest.raises(ValueError, match="Unknown stage1_mode"):
+        r.search(q, stage1_mode="bogus")
+    with pytest.raises(ValueError, match="Unknown stage1_mode"):
+        r.search_server_side(q, stage1_mode="bogus")
+
+
+def test_two_stage_server_side_matches_reference(setup):
+    q, client, want = setup
+    r = TwoStageRetriever(client, "c")
+    for key, w in want.items():
+        if key.startswith("two_stage_server::"):
+            got = r.search_server_side(q, top_k=10, prefetch_k=40, stage1_mode=key.split("::")[1])
+            assert _ids(got) == _ids(w), key
+            assert [g["score_final"] for g in got] == [x["score_final"] for x in w]
+            assert all(g["score_stage1"] is None and g["score_stage2"] == g["score_final"] for g in got)
+    for use_pooling in (False, True):
+        got = r.search_single_stage(q, top_k=10, use_pooling=use_pooling)
+        assert _ids(got) == _ids(want[f"two_stage_single::{use_pooling}"])
+
+
+def test_default_prefetch_k(setup):
+    q, client, _ = setup
+    r = TwoStageRetriever(client, "c")
+    client.calls.clear()
+    r.search_server_side(q, top_k=3)
+    r.search(q, top_k=20, stage1_mode="tokens_vs_tiles")
+    limits = [c["limit"] for c in client.calls]
+    assert limits[0] == 3          # outer limit; prefetch limit = max(100, 10*top_k) is inside Prefetch
+    assert limits[1] == 200        # stage-1 prefetch of search(): max(100, 10*20)
+
+
+def test_three_stage_matches_reference(setup):
+    q, client, want = setup
+    r = ThreeStageRetriever(client, "c")
+    got = r.search_server_side(query_embedding=q, top_k=10, stage1_k=80, stage2_k=30)
+    w = want["three_stage"]
+    assert _ids(got) == _ids(w)
+    for g, x in zip(got, w):
+        for k in ("score_stage1", "score_stage2", "score_stage3", "score_final"):
+            assert g[k] == x[k]
+    # accepts-and-ignores stage1_mode, None sizes default to 1000/300 (reference raises here)
+    got2 = r.search_server_side(query_embedding=q, top_k=10, stage1_k=None, stage2_k=None, stage1_mode="x")
+    assert len(got2) == 10
+
+
+def test_single_stage_matches_reference(setup):
+    q, client, want = setup
+    r = SingleStageRetriever(client, "c")
+    for strat in ("multi_vector", "tiles_maxsim", "pooled_tile", "pooled_global", "experimental_maxsim",
+                  "pooled_experimental"):
+        got = r.search(q, top_k=10, strategy=strat)
+        w = want[f"single::{strat}"]
+        assert _ids(got) == _ids(w) and [g["score"] for g in got] == [x["score"] for x in w]
+        assert all(g["score"] == g["score_final"] for g in got)
+    with pytest.raises(ValueError, match="Unknown strategy"):
+        r.search(q, strategy="nope")
+
+
+def test_multi_vector_dispatch(setup):
+    q, client, want = setup
+    mv = MultiVectorRetriever("c", qdrant_client=client)
+    assert _ids(mv.search_embedded(query_embedding=q, top_k=10, mode="single_full")) == _ids(want["single::multi_vector"])
+    assert _ids(mv.search_embedded(query_embedding=q, top_k=10, mode="single_tiles")) == _ids(want["single::tiles_maxsim"])
+    assert _ids(mv.search_embedded(query_embedding=q, top_k=10, mode="single_pooled")) == _ids(want["single::pooled_tile"])
+    assert _ids(mv.search_embedded(query_embedding=q, top_k=10, mode="single_global")) == _ids(want["single::pooled_global"])
+    got = mv.search_embedded(query_embedding=q, top_k=10, mode="two_stage", prefetch_k=40,
+                             stage1_mode="tokens_vs_standard_pooling")
+    assert _ids(got) == _ids(want["two_stage_server::tokens_vs_standard_pooling"])
+    got = mv.search_embedded(query_embedding=q, top_k=10, mode="three_stage", stage1_k=80, stage2_k=30)
+    assert _ids(got) == _ids(want["three_stage"])
+    with pytest.raises(ValueError, match="Unknown mode"):
+        mv.search_embedded(query_embedding=q, mode="nope")
+    with pytest.raises(ValueError):
+        MultiVectorRetriever("c")
+    with pytest.raises(ValueError):
+        mv.search("a text query")  # no embedder
+
+
+def test_retry_and_torch_queries(setup):
+    import torch
+
+    q, client, want = setup
+
+    class Flaky:
+        def __init__(self, inner, fails):
+            self.inner, self.fails = inner, fails
+
+        def query_points(self, **kw):
+            if self.fails > 0:
+                self.fails -= 1
+                raise RuntimeError("transient")
+            return self.inner.query_points(**kw)
+
+    r = TwoStageRetriever(Flaky(client, 2), "c", retry_sleep=0.0)
+    got = r.search_server_side(torch.from_numpy(q).to(torch.bfloat16).float(), top_k=10, prefetch_k=40,
+                               stage1_mode="tokens_vs_tiles")
+    assert len(got) == 10
+    r = TwoStageRetriever(Flaky(client, 5), "c", retry_sleep=0.0)
+    with pytest.raises(RuntimeError, match="transient"):
+        r.search_server_side(q)
+
+
+def test_build_filter_and_stage1_table():
+    r = TwoStageRetriever(None, "c")
+    assert r.build_filter() is None
+    f = r.build_filter(year="2020", source=["a", "b"], has_text=True)
+    keys = [c.key for c in f.must]
+    assert keys == ["year", "source", "has_text"]
+    assert f.must[0].match.value == 2020 and f.must[1].match.any == ["a", "b"]
+    assert resolve_stage1("tokens_vs_tiles", "p", "e", "g") == (False, "p")
+    assert resolve_stage1("pooled_query_vs_experimental", "p", "e", "g") == (True, "e")
+    assert resolve_stage1("pooled_query_vs_global", "p", "e", "g") == (True, "g")

@@ -590,6 +590,7 @@ extern "C" int vrag_score(vrag_corpus_t* c, const char* name, const float* query
 
 extern "C" int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char* const* names,
                                       const uint32_t* flags, const int* ks, const float* query, int n_query_rows,
+                                      const int* q_offsets, const int64_t* cand_ids, int64_t n_cand,
                                       float* out_scores, int64_t* out_ids, int* out_counts) {
   if (!c) return fail("corpus is NULL");
   if (n_stages < 1 || n_stages > kMaxStages) return fail("n_stages %d out of range [1,%d]", n_stages, kMaxStages);
@@ -603,22 +604,36 @@ extern "C" int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char
     if (ks[s] > kTopkMaxK) return fail("stage %d: k=%d exceeds the supported maximum %d", s, ks[s], kTopkMaxK);
     if (st[s]->n_pages != st[0]->n_pages) return fail("stage %d: store '%s' has a different page count", s, names[s]);
     total_k += ks[s];
+    if (q_offsets) {
+      if (q_offsets[s] < 0 || q_offsets[s + 1] <= q_offsets[s] || q_offsets[s + 1] > n_query_rows)
+        return fail("stage %d: bad query row range [%d,%d)", s, q_offsets[s], q_offsets[s + 1]);
+    }
   }
+  if (cand_ids && n_cand < 0) return fail("n_cand < 0");
   TRY(stage_query(c, query, n_query_rows));
   TRY(c->d_out_scores.ensure(total_k));
   TRY(c->d_out_ids.ensure(total_k));
   TRY(ensure_host_out(c, total_k));
-  TRY(c->d_scores.ensure(std::max<int64_t>(st[0]->n_pages, 1)));
+  const int64_t n_first = cand_ids ? n_cand : st[0]->n_pages;
+  TRY(c->d_scores.ensure(std::max<int64_t>(n_first, 1)));
+  if (cand_ids) {
+    TRY(c->d_cand.ensure(std::max<int64_t>(n_cand, 1)));
+    if (n_cand > 0)
+      CUDA_OK(cudaMemcpyAsync(c->d_cand.p, cand_ids, n_cand * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+  }
   CUDA_OK(cudaEventRecord(c->ev0, c->stream));
   size_t off = 0;
-  int64_t n_prev = st[0]->n_pages;   // survivors entering the stage
-  const long long* d_prev_ids = nullptr;
+  int64_t n_prev = n_first;   // survivors entering the stage
+  const long long* d_prev_ids = cand_ids ? c->d_cand.p : nullptr;
+  bool timed = false;
   for (int s = 0; s < n_stages; ++s) {
     const int64_t n_items = n_prev;
+    const float* dq = c->d_query.p + (q_offsets ? static_cast<size_t>(q_offsets[s]) * 128 : 0);
+    const int qrows = q_offsets ? (q_offsets[s + 1] - q_offsets[s]) : n_query_rows;
     if (n_items > 0) {
-      // the dominant (timed) kernel is the first-stage scan
-      TRY(launch_scan(c, *st[s], c->d_query.p, n_query_rows, flags[s], d_prev_ids, n_items, c->d_scores.p, c->stream,
-                      s == 0));
+      // the dominant (timed) kernel is the first scan
+      TRY(launch_scan(c, *st[s], dq, qrows, flags[s], d_prev_ids, n_items, c->d_scores.p, c->stream, !timed));
+      timed = true;
     }
     TRY(launch_topk(c, c->d_scores.p, d_prev_ids, c->page_base, n_items, ks[s], c->d_out_scores.p + off,
                     c->d_out_ids.p + off, nullptr, c->d_counts.p + s, c->stream));
@@ -635,48 +650,18 @@ extern "C" int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char
   memcpy(out_ids, c->h_out_ids, total_k * sizeof(long long));
   memcpy(out_counts, c->h_counts, n_stages * sizeof(int));
   cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1);
-  cudaEventElapsedTime(&c->last_ms[1], c->evk0, c->evk1);
+  if (timed) cudaEventElapsedTime(&c->last_ms[1], c->evk0, c->evk1);
   return 0;
 }
 
 extern "C" int vrag_search(vrag_corpus_t* c, const char* name, const float* query, int n_query_rows, uint32_t flags,
                            const int64_t* cand_ids, int64_t n_cand, int k, float* out_scores, int64_t* out_ids,
                            int* out_count) {
-  if (!cand_ids) {
-    const char* names[1] = {name};
-    int cnt = 0;
-    TRY(vrag_search_multistage(c, 1, names, &flags, &k, query, n_query_rows, out_scores, out_ids, &cnt));
-    if (out_count) *out_count = cnt;
-    return 0;
-  }
-  Store* s;
-  TRY(find_store(c, name, &s));
-  TRY(set_device(c));
-  if (k < 1) return fail("k must be >= 1");
-  if (!out_scores || !out_ids) return fail("NULL output");
-  TRY(stage_query(c, query, n_query_rows));
-  TRY(c->d_cand.ensure(std::max<int64_t>(n_cand, 1)));
-  if (n_cand > 0)
-    CUDA_OK(cudaMemcpyAsync(c->d_cand.p, cand_ids, n_cand * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
-  TRY(c->d_scores.ensure(std::max<int64_t>(n_cand, 1)));
-  TRY(c->d_out_scores.ensure(k));
-  TRY(c->d_out_ids.ensure(k));
-  TRY(ensure_host_out(c, k));
-  CUDA_OK(cudaEventRecord(c->ev0, c->stream));
-  if (n_cand > 0)
-    TRY(launch_scan(c, *s, c->d_query.p, n_query_rows, flags, c->d_cand.p, n_cand, c->d_scores.p, c->stream, true));
-  TRY(launch_topk(c, c->d_scores.p, c->d_cand.p, 0, n_cand, k, c->d_out_scores.p, c->d_out_ids.p, nullptr,
-                  c->d_counts.p, c->stream));
-  CUDA_OK(cudaEventRecord(c->ev1, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->h_out_scores, c->d_out_scores.p, k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->h_out_ids, c->d_out_ids.p, k * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->h_counts, c->d_counts.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_OK(cudaStreamSynchronize(c->stream));
-  memcpy(out_scores, c->h_out_scores, k * sizeof(float));
-  memcpy(out_ids, c->h_out_ids, k * sizeof(long long));
-  if (out_count) *out_count = c->h_counts[0];
-  cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1);
-  if (n_cand > 0) cudaEventElapsedTime(&c->last_ms[1], c->evk0, c->evk1);
+  const char* names[1] = {name};
+  int cnt = 0;
+  TRY(vrag_search_multistage(c, 1, names, &flags, &k, query, n_query_rows, nullptr, cand_ids, n_cand, out_scores,
+                             out_ids, &cnt));
+  if (out_count) *out_count = cnt;
   return 0;
 }
 

@@ -1,0 +1,214 @@
+"""`GpuCorpusClient`: the duck-typed `qdrant_client` of the reference retrievers, backed by a GpuCorpus.
+
+The reference retrievers only ever call `query_points`, `retrieve` and `get_collection` on their client
+(two_stage.py:162-178,307-316,349-358,384-390; three_stage.py:103-157;
+single_stage.py:123-132).  This class implements exactly those with Qdrant's COSINE + MAX_SIM semantics
+(qdrant_indexer.py:200-239) computed by the sm_100a kernels, so the reference's own retriever classes — and
+the mirrors in visual_rag_b200.retrieval — run unchanged on top of the GPU store.
+"""
+
+from __future__ import annotations
+
+from typing import Any, Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from .corpus import GpuCorpus
+
+
+class ScoredPoint:
+    __slots__ = ("id", "score", "payload", "vector", "version")
+
+    def __init__(self, id, score=None, payload=None, vector=None):
+        self.id = id
+        self.score = score
+        self.payload = payload
+        self.vector = vector
+        self.version = 0
+
+    def __repr__(self):  # pragma: no cover
+        return f"ScoredPoint(id={self.id!r}, score={self.score!r})"
+
+
+class QueryResponse:
+    __slots__ = ("points",)
+
+    def __init__(self, points):
+        self.points = points
+
+
+class _VectorInfo:
+    def __init__(self, multivector: bool):
+        self.multivector_config = object() if multivector else None
+        self.size = 128
+
+
+class _CollectionInfo:
+    def __init__(self, vectors: Dict[str, _VectorInfo], points_count: int):
+        params = type("Params", (), {"vectors": vectors})()
+        self.config = type("Config", (), {"params": params})()
+        self.points_count = points_count
+
+
+def _match(cond, payload: dict) -> bool:
+    """FieldCondition(key, match=MatchValue(value)|MatchAny(any)) on a payload dict (two_stage.py:449-480)."""
+    val = payload.get(getattr(cond, "key", None)) if payload else None
+    m = getattr(cond, "match", None)
+    if m is None:
+        return True
+    if hasattr(m, "any") and getattr(m, "any") is not None:
+        return val in list(m.any)
+    if hasattr(m, "value"):
+        return val == m.value
+    return True
+
+
+class GpuCorpusClient:
+    """In-process, GPU-resident replacement of QdrantClient for the retrieval path.
+
+    point_ids: external id of page i (any hashable: int or UUID string as produced by
+    QdrantIndexer.generate_point_id, qdrant_indexer.py:602-613). Defaults to the global page index.
+    """
+
+    def __init__(self, corpus: GpuCorpus, collection_name: str = "gpu", point_ids: Optional[Sequence[Any]] = None,
+                 payloads: Optional[Sequence[Optional[dict]]] = None):
+        self.corpus = corpus
+        self.collection_name = collection_name
+        self._ids: Optional[List[Any]] = list(point_ids) if point_ids is not None else None
+        self._index: Optional[Dict[Any, int]] = (
+            {pid: i for i, pid in enumerate(self._ids)} if self._ids is not None else None
+        )
+        self._payloads = list(payloads) if payloads is not None else None
+
+    # ------------------------------------------------------------------ id mapping
+    def set_points(self, point_ids: Sequence[Any], payloads: Optional[Sequence[Optional[dict]]] = None) -> None:
+        self._ids = list(point_ids)
+        self._index = {pid: i for i, pid in enumerate(self._ids)}
+        self._payloads = list(payloads) if payloads is not None else None
+
+    def _pid(self, page: int):
+        local = page - self.corpus.page_base
+        return self._ids[local] if self._ids is not None else page
+
+    def _page(self, pid) -> int:
+        if self._index is not None:
+            i = self._index.get(pid)
+            if i is None and not isinstance(pid, str):
+                i = self._index.get(str(pid))
+            return -1 if i is None else i + self.corpus.page_base
+        try:
+            return int(pid)
+        except (TypeError, ValueError):
+            return -1
+
+    def _payload(self, page: int):
+        if self._payloads is None:
+            return {}
+        return self._payloads[page - self.corpus.page_base]
+
+    # ------------------------------------------------------------------ filters
+    def _candidates(self, query_filter, n_pages: int) -> Optional[np.ndarray]:
+        """Filter -> sorted global page ids, or None for 'all pages'. HasIdCondition is the candidate
+        restriction of three_stage.py:75-81; FieldConditions (build_filter, two_stage.py:436-480) are
+        evaluated on the host payloads."""
+        if query_filter is None:
+            return None
+        allowed: Optional[set] = None
+        field_conds = []
+
+        def walk(f):
+            nonlocal allowed
+            for cond in (getattr(f, "must", None) or []):
+                if hasattr(cond, "has_id"):
+                    s = {self._page(p) for p in cond.has_id}
+                    s.discard(-1)
+                    allowed = s if allowed is None else (allowed & s)
+                elif hasattr(cond, "must") or hasattr(cond, "should") or hasattr(cond, "must_not"):
+                    walk(cond)
+                elif hasattr(cond, "key"):
+                    field_conds.append(cond)
+
+        walk(query_filter)
+        if allowed is None and not field_conds:
+            return None
+        base = self.corpus.page_base
+        pages: Iterable[int] = sorted(allowed) if allowed is not None else range(base, base + n_pages)
+        if field_conds:
+            pages = [p for p in pages if all(_match(c, self._payload(p)) for c in field_conds)]
+        return np.asarray(list(pages), dtype=np.int64)
+
+    # ------------------------------------------------------------------ the three client methods
+    @staticmethod
+    def _as_query(query) -> np.ndarray:
+        q = np.asarray(query, dtype=np.float32)
+        return q[None, :] if q.ndim == 1 else q
+
+    def query_points(self, collection_name=None, query=None, using=None, limit=10, query_filter=None,
+                     with_payload=True, with_vectors=False, search_params=None, prefetch=None, timeout=None,
+                     **_ignored) -> QueryResponse:
+        if using is None:
+            raise ValueError("`using` (named vector) is required")
+        limit = int(limit)
+        n_pages = self.corpus.n_pages(using)
+        cand = self._candidates(query_filter, n_pages)
+        q = self._as_query(query)
+        if prefetch:
+            # Qdrant prefetch= (two_stage.py:170-176): stage-1 query and rerank query travel separately;
+            # both stages run back to back on the device with a single host synchronisation.
+            pf = prefetch[0] if isinstance(prefetch, (list, tuple)) else prefetch
+            stages = self.corpus.search_multistage(
+                [(pf.using, False, int(pf.limit)), (using, False, limit)], None,
+                stage_queries=[self._as_query(pf.query), q], candidate_ids=cand)
+            scores, ids = stages[-1]
+        else:
+            scores, ids = self.corpus.search(using, q, limit, candidate_ids=cand)
+        keep = np.isfinite(scores)
+        points = [
+            ScoredPoint(self._pid(int(i)), float(s), self._payload(int(i)) if with_payload else None)
+            for s, i in zip(scores[keep], ids[keep])
+        ]
+        if with_vectors:
+            names = [using] if with_vectors is True else list(with_vectors)
+            for p in points:
+                page = self._page(p.id) - self.corpus.page_base
+                p.vector = {nm: self.corpus.read_page(nm, page).astype(np.float32).tolist() for nm in names}
+        return QueryResponse(points)
+
+    def query_three_stage(self, *, stage1_query, stage2_query, stage3_query, stage1_using, stage2_using,
+                          stage3_using, stage1_k: int, stage2_k: int, top_k: int, query_filter=None):
+        """The three ID-restricted scans of ThreeStageRetriever.search_server_side (three_stage.py:102-159)
+        fused on the device: returns the three point lists (stage 3 with payloads)."""
+        cand = self._candidates(query_filter, self.corpus.n_pages(stage1_using))
+        stages = self.corpus.search_multistage(
+            [(stage1_using, False, int(stage1_k)), (stage2_using, False, int(stage2_k)), (stage3_using, False, int(top_k))],
+            None, stage_queries=[self._as_query(stage1_query), self._as_query(stage2_query), self._as_query(stage3_query)],
+            candidate_ids=cand)
+        out = []
+        for si, (scores, ids) in enumerate(stages):
+            keep = np.isfinite(scores)
+            out.append([ScoredPoint(self._pid(int(i)), float(s), self._payload(int(i)) if si == 2 else None)
+                        for s, i in zip(scores[keep], ids[keep])])
+        return out
+
+    def retrieve(self, collection_name=None, ids=(), with_payload=False, with_vectors=None, timeout=None, **_ignored):
+        out = []
+        names = [] if not with_vectors else (list(with_vectors) if not isinstance(with_vectors, bool) else [])
+        for pid in ids:
+            page = self._page(pid)
+            if page < 0:
+                continue
+            local = page - self.corpus.page_base
+            vec = {nm: self.corpus.read_page(nm, local).astype(np.float32).tolist() for nm in names
+                   if self.corpus.has_store(nm)}
+            out.append(ScoredPoint(pid, None, self._payload(page) if with_payload else None, vec or None))
+        return out
+
+    def get_collection(self, collection_name=None):
+        vectors = {}
+        count = 0
+        for nm in ("initial", "mean_pooling", "experimental_pooling", "global_pooling"):
+            if self.corpus.has_store(nm):
+                info = self.corpus.store_info(nm)
+                vectors[nm] = _VectorInfo(multivector=(nm != "global_pooling"))
+                count = info["n_pages"]
+        return _CollectionInfo(vectors, count)

@@ -228,7 +228,7 @@ class GpuCorpus:
         descending, ties by lower id."""
         q = _as_f32_query(query)
         k = int(k)
-        if k < 1:
+        if k < 1 or (candidate_ids is not None and len(candidate_ids) == 0):
             return np.empty((0,), np.float32), np.empty((0,), np.int64)
         if candidate_ids is None:
             cand_p, n_cand = None, 0
@@ -254,11 +254,32 @@ class GpuCorpus:
         stages: Sequence[Tuple[str, bool, int]],
         query,
         normalize: bool = True,
+        stage_queries: Optional[Sequence] = None,
+        candidate_ids: Optional[Sequence[int]] = None,
     ) -> List[Tuple[np.ndarray, np.ndarray]]:
         """Fused multi-stage search: stages = [(store name, pool_query, k), ...]; stage s is restricted to
-        the survivors of stage s-1. One host synchronisation. Returns per-stage (scores, ids)."""
-        q = _as_f32_query(query)
+        the survivors of stage s-1 (stage 0 to `candidate_ids` if given). One host synchronisation.
+        stage_queries: optional per-stage query matrices (else every stage uses `query`).
+        Returns per-stage (scores, ids)."""
         ns = len(stages)
+        if stage_queries is not None:
+            qs = [_as_f32_query(x) for x in stage_queries]
+            if len(qs) != ns:
+                raise ValueError("stage_queries must have one entry per stage")
+            q = np.ascontiguousarray(np.concatenate(qs, axis=0))
+            offs = np.concatenate([[0], np.cumsum([x.shape[0] for x in qs])]).astype(np.int32)
+            off_p = offs.ctypes.data_as(C.POINTER(C.c_int))
+        else:
+            q = _as_f32_query(query)
+            off_p = None
+        if candidate_ids is None:
+            cand_p, n_cand = None, 0
+        elif len(candidate_ids) == 0:
+            return [(np.empty((0,), np.float32), np.empty((0,), np.int64)) for _ in stages]
+        else:
+            cand = np.ascontiguousarray(np.asarray(candidate_ids, dtype=np.int64))
+            n_cand = cand.size
+            cand_p = cand.ctypes.data_as(C.POINTER(C.c_int64))
         names = (C.c_char_p * ns)(*[s[0].encode() for s in stages])
         flags = (C.c_uint32 * ns)(*[query_flags(normalize, bool(s[1])) for s in stages])
         ks = (C.c_int * ns)(*[int(s[2]) for s in stages])
@@ -268,7 +289,8 @@ class GpuCorpus:
         counts = (C.c_int * ns)()
         N.check(
             self._lib.vrag_search_multistage(
-                self._h, ns, names, flags, ks, q.ctypes.data_as(C.POINTER(C.c_float)), q.shape[0],
+                self._h, ns, names, flags, ks, q.ctypes.data_as(C.POINTER(C.c_float)), q.shape[0], off_p,
+                cand_p, n_cand,
                 scores.ctypes.data_as(C.POINTER(C.c_float)), ids.ctypes.data_as(C.POINTER(C.c_int64)), counts,
             )
         )

@@ -1,0 +1,124 @@
+"""Page-sharded multi-GPU search (one process per GPU, torch.distributed / NCCL over NVLink).
+
+Every rank owns a contiguous page range of every named store and scans only its shard.
+The only exchange on the path is the top-k merge: each rank contributes its local top-k (fp32 score, int64
+global page id) to ONE all-gather per stage, after which every rank runs the same deterministic merge
+(score descending, ties -> lower id) with the library's top-k kernel. Multi-stage search keeps the
+reference semantics "global top-prefetch_k, then rerank": the merged stage-s list is the candidate list of
+stage s+1 on every rank, and a rank scores only the candidates it owns (the others come back as -inf).
+No data-path collective touches the corpus itself.
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .corpus import GpuCorpus, _as_f32_query, query_flags
+
+
+def shard_page_range(n_pages_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous page range [begin, end) owned by `rank`: rank r owns
+    [r*N/P, (r+1)*N/P) with integer floors, so ranges are disjoint, ordered by rank and cover [0, N)."""
+    return (n_pages_total * rank) // world, (n_pages_total * (rank + 1)) // world
+
+
+class ShardedSearcher:
+    """`corpus` is a GpuCorpus (device pointers + CUDA stream). Anything exposing the same
+    score_dev / topk_dev / n_pages / page_base / device surface works; device=None means host tensors
+    (used by the gloo tests of the exchange logic)."""
+
+    def __init__(self, corpus: GpuCorpus, group=None, max_query_rows: int = 128):
+        self.corpus = corpus
+        self.group = group
+        self.dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.rank = self.dist.get_rank(group) if self.dist else 0
+        self.on_gpu = corpus.device is not None
+        self.device = torch.device("cuda", corpus.device) if self.on_gpu else torch.device("cpu")
+        self._q_dev = torch.empty((max_query_rows, 128), dtype=torch.float32, device=self.device)
+        self._q_pin = torch.empty((max_query_rows, 128), dtype=torch.float32)
+        if self.on_gpu:
+            self._q_pin = self._q_pin.pin_memory()
+        self._scores: Optional[torch.Tensor] = None
+        self._bufs = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _buf(self, key: str, n: int, dtype) -> torch.Tensor:
+        t = self._bufs.get(key)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty((max(n, 1),), dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t[:n]
+
+    def _score_buf(self, n: int) -> torch.Tensor:
+        if self._scores is None or self._scores.numel() < n:
+            self._scores = torch.empty((max(n, 1),), dtype=torch.float32, device=self.device)
+        return self._scores[:n]
+
+    def upload_query(self, query) -> int:
+        """Host query -> device (pinned staging, async H2D on the current stream). Returns the row count."""
+        q = _as_f32_query(query)
+        n = q.shape[0]
+        self._q_pin[:n].copy_(torch.from_numpy(q))
+        self._q_dev[:n].copy_(self._q_pin[:n], non_blocking=True)
+        return n
+
+    def _stage(self, name: str, n_q: int, flags: int, cand: Optional[torch.Tensor], k: int,
+               tag: str) -> Tuple[torch.Tensor, torch.Tensor]:
+        """One stage on the device: local scan -> local top-k -> all-gather -> merged global top-k.
+        Returns (scores[k], global ids[k]) identical on every rank; invalid slots are (-inf, -1)."""
+        c = self.corpus
+        stream = torch.cuda.current_stream(self.device).cuda_stream if self.on_gpu else 0
+        n_items = int(cand.numel()) if cand is not None else c.n_pages(name)
+        scores = self._score_buf(n_items)
+        if n_items > 0:
+            c.score_dev(name, self._q_dev.data_ptr(), n_q, flags, cand.data_ptr() if cand is not None else 0,
+                        n_items, scores.data_ptr(), stream)
+        ls = self._buf(tag + "_ls", k, torch.float32)
+        li = self._buf(tag + "_li", k, torch.int64)
+        c.topk_dev(scores.data_ptr(), cand.data_ptr() if cand is not None else 0, c.page_base, n_items, k,
+                   ls.data_ptr(), li.data_ptr(), stream)
+        if self.world == 1:
+            return ls, li
+        gs = self._buf(tag + "_gs", k * self.world, torch.float32)
+        gi = self._buf(tag + "_gi", k * self.world, torch.int64)
+        self.dist.all_gather_into_tensor(gs, ls, group=self.group)
+        self.dist.all_gather_into_tensor(gi, li, group=self.group)
+        ms = self._buf(tag + "_ms", k, torch.float32)
+        mi = self._buf(tag + "_mi", k, torch.int64)
+        # merge: keys are (score, position in the gathered list); rank-major gather order + per-rank id order
+        # make "lower position" == "lower global id" among equal scores of different ranks only if shards are
+        # id-ordered by rank, which contiguous page ranges guarantee.
+        c.topk_dev(gs.data_ptr(), gi.data_ptr(), 0, k * self.world, k, ms.data_ptr(), mi.data_ptr(), stream)
+        return ms, mi
+
+    # ------------------------------------------------------------------ public API
+    def search_multistage_device(self, stages: Sequence[Tuple[str, bool, int]], n_q: int,
+                                 normalize: bool = True) -> List[Tuple[torch.Tensor, torch.Tensor]]:
+        """All stages on the device, no host synchronisation. The query must already be uploaded."""
+        out = []
+        cand = None
+        for s, (name, pool, k) in enumerate(stages):
+            sc, ids = self._stage(name, n_q, query_flags(normalize, pool), cand, int(k), f"s{s}")
+            out.append((sc, ids))
+            cand = ids
+        return out
+
+    def search_multistage(self, stages: Sequence[Tuple[str, bool, int]], query,
+                          normalize: bool = True) -> List[Tuple[np.ndarray, np.ndarray]]:
+        """Host-facing: uploads the query, runs the stages, reads back every stage's merged list."""
+        n_q = self.upload_query(query)
+        dev = self.search_multistage_device(stages, n_q, normalize)
+        res = []
+        for sc, ids in dev:
+            s = sc.cpu().numpy()
+            i = ids.cpu().numpy()
+            keep = (i >= 0) & np.isfinite(s)
+            res.append((s[keep], i[keep]))
+        return res
+
+    def search(self, name: str, query, k: int, normalize: bool = True, pool_query: bool = False):
+        return self.search_multistage([(name, pool_query, k)], query, normalize)[0]
