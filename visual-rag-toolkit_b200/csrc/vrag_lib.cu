@@ -235,7 +235,8 @@ static int finish_store(vrag_corpus* c, Store& s, const int64_t* page_offsets, i
     for (int64_t i = 0; i < n_pages; ++i) mx = std::max(mx, page_offsets[i + 1] - page_offsets[i]);
     s.max_rows = mx;
     CUDA_OK(cudaMalloc(&s.offsets, (n_pages + 1) * sizeof(long long)));
-    CUDA_OK(cudaMemcpy(s.offsets, page_offsets, (n_pages + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpyAsync(s.offsets, page_offsets, (n_pages + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
   }
   s.packed = s.max_rows <= kTileRows;
   if (s.packed && fixed_rows == 0 && n_pages > 0) {
@@ -255,7 +256,8 @@ static int finish_store(vrag_corpus* c, Store& s, const int64_t* page_offsets, i
     t0.push_back(static_cast<int>(n_pages));
     s.n_tiles = static_cast<int64_t>(t0.size()) - 1;
     CUDA_OK(cudaMalloc(&s.tile_page0, t0.size() * sizeof(int)));
-    CUDA_OK(cudaMemcpy(s.tile_page0, t0.data(), t0.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpyAsync(s.tile_page0, t0.data(), t0.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
   }
   if (s.total_rows > 0) {
     TRY(make_rows_map(&s.tm128, s.rows, s.total_rows, kTileRows));
@@ -318,7 +320,9 @@ extern "C" int vrag_store_add(vrag_corpus_t* c, const char* name, const void* ro
   if (total_rows > 0) {
     const cudaMemcpyKind kind = rows_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (dtype == VRAG_F16) {
-      CUDA_OK(cudaMemcpy(s->rows, rows, n_el * sizeof(__half), kind));
+      // all copies go through the library stream: the kernels below run on it (a non-blocking stream does not
+      // order against the legacy default stream a plain cudaMemcpy uses)
+      CUDA_OK(cudaMemcpyAsync(s->rows, rows, n_el * sizeof(__half), kind, c->stream));
     } else {
       const size_t chunk = size_t(32) << 20;  // elements per staging chunk
       float* tmp = nullptr;
@@ -328,7 +332,7 @@ extern "C" int vrag_store_add(vrag_corpus_t* c, const char* name, const void* ro
         const size_t n = std::min(chunk, n_el - o);
         const float* src = src_base + o;
         if (!rows_on_device) {
-          CUDA_OK(cudaMemcpy(tmp, src, n * sizeof(float), cudaMemcpyHostToDevice));
+          CUDA_OK(cudaMemcpyAsync(tmp, src, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
           src = tmp;
         }
         f32_to_f16_kernel<<<static_cast<unsigned>((n / 4 + 256) / 256), 256, 0, c->stream>>>(src, n, s->rows + o);
@@ -407,8 +411,9 @@ extern "C" int vrag_store_read_rows(vrag_corpus_t* c, const char* name, int64_t 
   TRY(set_device(c));
   if (row0 < 0 || n_rows < 0 || row0 + n_rows > s->total_rows) return fail("row range out of bounds");
   if (n_rows == 0) return 0;
-  CUDA_OK(cudaMemcpy(out_f16_host, s->rows + static_cast<size_t>(row0) * 128, static_cast<size_t>(n_rows) * 256,
-                     cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpyAsync(out_f16_host, s->rows + static_cast<size_t>(row0) * 128, static_cast<size_t>(n_rows) * 256,
+                          cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
