@@ -110,6 +110,51 @@ int vrag_score_dev(vrag_corpus_t* c, const char* name, const float* query_dev, i
 int vrag_topk_dev(vrag_corpus_t* c, const float* scores_dev, const int64_t* ids_dev, int64_t id_base, int64_t n,
                   int k, float* out_scores_dev, int64_t* out_ids_dev, void* stream);
 
+/* ------------------------------------------------------------------ indexing-time pooling
+ * The pooling arithmetic of visual_rag/embedding/pooling.py as CUDA kernels. One spec = one pooling
+ * function call; `kind` selects it:                                                               */
+#define VRAG_POOL_TILE_MEAN 0             /* tile_level_mean_pooling, pooling.py:35-98 (patches_per_tile) */
+#define VRAG_POOL_ADAPTIVE_ROWS 2         /* colpali_row_mean_pooling / adaptive_row_mean_pooling_from_grid,
+                                             pooling.py:101-185 (grid_h, grid_w, target_rows, clamp_to_h) */
+#define VRAG_POOL_COLSMOL_EXPERIMENTAL 3  /* colsmol_experimental_pooling, pooling.py:188-232 (num_tiles, patches_per_tile) */
+#define VRAG_POOL_LEGACY_CONV 4           /* colpali_experimental_pooling_from_rows, pooling.py:235-286 (window) */
+#define VRAG_POOL_SMOOTH 5                /* weighted_row_smoothing_same_length, pooling.py:289-375 (window, weights) */
+#define VRAG_POOL_TILE_4N 6               /* colsmol_tile_4n_pooling_from_tiles, pooling.py:378-436 (n_rows, n_cols, ...) */
+#define VRAG_POOL_GLOBAL_MEAN 7           /* global_mean_pooling, pooling.py:439-465; global_pool_from_mean_pool, visual_embedder.py:837-840 */
+#define VRAG_POOL_SEQ_CHUNKS 8            /* last-resort sequence chunk pooling, visual_embedder.py:824-835 (target_rows) */
+
+typedef struct vrag_pool_spec {
+  int kind;
+  int patches_per_tile;
+  int grid_h, grid_w;     /* ADAPTIVE_ROWS: fixed grid (ignored when a per-page grid array is given) */
+  int target_rows;        /* ADAPTIVE_ROWS / SEQ_CHUNKS; <= 0: all grid rows */
+  int clamp_to_h;         /* ADAPTIVE_ROWS: rows = min(target_rows, grid_h) — the ColQwen2.5 cap, visual_embedder.py:791-793 */
+  int num_tiles;          /* COLSMOL_EXPERIMENTAL: requested num_tiles (<= 0: ceil(T / patches_per_tile)) */
+  int window;             /* LEGACY_CONV / SMOOTH */
+  int n_weights;          /* SMOOTH: window normalised fp32 taps (pooling.py:329-355) */
+  float weights[16];
+  int n_rows, n_cols, has_global, include_self; /* TILE_4N */
+  int via_f16;            /* GLOBAL_MEAN: round the fp32 mean to fp16 first (numpy's fp16 mean, pooling.py:463) */
+} vrag_pool_spec_t;
+
+/* Rows this spec produces for a page of in_rows rows (host arithmetic only; validates the arguments with the
+ * reference's error conditions, pooling.py:118,158,168,205-216,262-268,317-321,405-410).            */
+int vrag_pool_out_rows(const vrag_pool_spec_t* spec, int64_t in_rows, int64_t* out_rows);
+
+/* One pooling call on one page: in [in_rows,128] (host, VRAG_F16/VRAG_F32) -> out (host, VRAG_F16/VRAG_F32).
+ * The drop-in for calling a pooling.py function on one numpy array.                                 */
+int vrag_pool_page(int device, const vrag_pool_spec_t* spec, const void* in, int in_dtype, int64_t in_rows,
+                   void* out, int out_dtype, int64_t out_capacity_rows, int64_t* out_rows);
+
+/* Bulk pooling on the device: derive n_specs named stores from store `src` without leaving HBM (the
+ * per-page orchestration of ProcessingPipeline._process_single_page, pipeline.py:400-507, and
+ * scripts/qdrant_recompute_colqwen_pooling_from_initial.py:292-327, for a whole collection).
+ * Token-level kinds read `src` once each; SMOOTH / TILE_4N / LEGACY_CONV / GLOBAL_MEAN specs are all
+ * produced in ONE pass over `src`. grid_hw: optional host [n_pages][2] per-page (grid_h, grid_w) /
+ * (n_rows, n_cols). Outputs are rounded to the fp16 store dtype (qdrant_indexer.py:423-441).        */
+int vrag_store_pool(vrag_corpus_t* c, const char* src, int n_specs, const vrag_pool_spec_t* specs,
+                    const char* const* dst_names, const int32_t* grid_hw);
+
 /* ------------------------------------------------------------------ measurement helpers */
 /* Device-side time (ms, CUDA events on the library stream) of the most recent vrag_search /
  * vrag_search_multistage on this corpus: [0] whole call, [1] dominant scan kernel only.            */

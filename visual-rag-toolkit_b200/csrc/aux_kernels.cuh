@@ -136,11 +136,17 @@ __global__ void synth_rows_kernel(__half* __restrict__ rows, float* __restrict__
 // Exact top-k.  Keys are 64-bit: (order-preserving bits of the fp32 score) << 32 | (0xFFFFFFFF - item
 // index), so "largest key first" = "highest score first, ties -> lower item index", which is what
 // Python's stable list.sort(reverse=True) over pages in index order yields (quick_test.py:165,
-// two_stage.py:424).  Each level sorts chunks of kTopkChunk keys in shared memory (bitonic,
-// descending) and keeps the first k of every chunk; the last level writes (score, id) pairs.
-constexpr int kTopkChunk = 8192;
-constexpr int kTopkThreads = 1024;
-constexpr int kTopkMaxK = kTopkChunk / 2;
+// two_stage.py:424).
+//
+// One level = one kernel: every block takes a chunk of CHUNK keys into shared memory and leaves the chunk's
+// K2 = pow2ceil(k) largest keys sorted descending at the front:
+//   1. bitonic-sort runs of K2 keys, even runs descending / odd runs ascending;
+//   2. repeat: element-wise max of each (descending, ascending) run pair = the pair's K2 largest keys as a
+//      bitonic sequence; drop the other half; bitonic-merge the surviving runs (alternating directions again).
+// Shared-memory traffic, which bounds this kernel, shrinks geometrically after step 1, and step 1 is
+// O(log^2 K2) instead of O(log^2 CHUNK) stages.  Levels repeat until one chunk is left; that last level
+// writes (score, id) pairs.
+constexpr int kTopkMaxK = 4096;
 
 __device__ __forceinline__ uint32_t score_to_ord(float f) {
   if (f != f) return 0u;  // NaN sorts last
@@ -156,6 +162,7 @@ struct TopkArgs {
   const unsigned long long* keys_in;  // merge-level input
   long long n;                // number of input elements
   int k;
+  int k2;                     // pow2ceil(k), <= CHUNK
   unsigned long long* keys_out;  // [n_chunks][k] (nullptr on the final level)
   // final level outputs
   float* out_scores;          // [k]
@@ -167,10 +174,12 @@ struct TopkArgs {
   long long n_total;          // number of real items (for out_count / padding)
 };
 
-__global__ void __launch_bounds__(kTopkThreads, 1) topk_kernel(const TopkArgs a) {
+template <int CHUNK, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) topk_kernel(const TopkArgs a) {
   extern __shared__ unsigned long long skeys[];
-  const long long base = static_cast<long long>(blockIdx.x) * kTopkChunk;
-  for (int j = threadIdx.x; j < kTopkChunk; j += kTopkThreads) {
+  constexpr int PER = CHUNK / 2 / THREADS;   // compare-exchanges per thread per full-width stage
+  const long long base = static_cast<long long>(blockIdx.x) * CHUNK;
+  for (int j = threadIdx.x; j < CHUNK; j += THREADS) {
     const long long i = base + j;
     unsigned long long key = 0ull;
     if (i < a.n) {
@@ -183,10 +192,14 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_kernel(const TopkArgs a)
     }
     skeys[j] = key;
   }
-  for (int size = 2; size <= kTopkChunk; size <<= 1) {
+  const int K2 = a.k2;
+  // 1. sorted runs of K2, run r descending iff r is even
+  for (int size = 2; size <= K2; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       __syncthreads();
-      for (int e = threadIdx.x; e < kTopkChunk / 2; e += kTopkThreads) {
+#pragma unroll
+      for (int t = 0; t < PER; ++t) {
+        const int e = threadIdx.x + t * THREADS;
         const int pos = 2 * e - (e & (stride - 1));
         const unsigned long long x = skeys[pos], y = skeys[pos + stride];
         const bool desc = (pos & size) == 0;
@@ -197,12 +210,50 @@ __global__ void __launch_bounds__(kTopkThreads, 1) topk_kernel(const TopkArgs a)
       }
     }
   }
+  // 2. merge-and-prune rounds
+  for (int live = CHUNK; live > K2; live >>= 1) {
+    __syncthreads();
+    unsigned long long keep[PER];
+    const int half = live >> 1;
+#pragma unroll
+    for (int t = 0; t < PER; ++t) {
+      const int e = threadIdx.x + t * THREADS;
+      keep[t] = 0ull;
+      if (e < half) {
+        const int j = e / K2, i = e - j * K2;
+        const unsigned long long x = skeys[(2 * j) * K2 + i], y = skeys[(2 * j + 1) * K2 + i];
+        keep[t] = x > y ? x : y;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < PER; ++t) {
+      const int e = threadIdx.x + t * THREADS;
+      if (e < half) skeys[e] = keep[t];
+    }
+    for (int stride = K2 >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < PER; ++t) {
+        const int e = threadIdx.x + t * THREADS;
+        if (e < (half >> 1)) {
+          const int pos = 2 * e - (e & (stride - 1));
+          const unsigned long long x = skeys[pos], y = skeys[pos + stride];
+          const bool desc = ((pos / K2) & 1) == 0;
+          if ((x < y) == desc) {
+            skeys[pos] = y;
+            skeys[pos + stride] = x;
+          }
+        }
+      }
+    }
+  }
   __syncthreads();
   if (a.keys_out) {
-    for (int j = threadIdx.x; j < a.k; j += kTopkThreads) a.keys_out[static_cast<long long>(blockIdx.x) * a.k + j] = skeys[j];
+    for (int j = threadIdx.x; j < a.k; j += THREADS) a.keys_out[static_cast<long long>(blockIdx.x) * a.k + j] = skeys[j];
   } else {
     const long long nvalid = a.n_total < a.k ? a.n_total : a.k;
-    for (int j = threadIdx.x; j < a.k; j += kTopkThreads) {
+    for (int j = threadIdx.x; j < a.k; j += THREADS) {
       if (j < nvalid) {
         const unsigned long long key = skeys[j];
         const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);

@@ -12,6 +12,7 @@
 #include "../../include/vrag_b200.h"
 #include "aux_kernels.cuh"
 #include "maxsim_scan.cuh"
+#include "pooling_kernels.cuh"
 
 using namespace vrag;
 
@@ -511,17 +512,27 @@ static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int
 }
 
 // Exact top-k of d_scores[n] -> (out_scores[k], out_ids[k]) sorted descending, ties -> lower item index.
+template <int CHUNK, int THREADS>
+static int launch_topk_level(vrag_corpus* c, const TopkArgs& a, long long n_chunks, cudaStream_t st) {
+  auto kern = topk_kernel<CHUNK, THREADS>;
+  const size_t smem = CHUNK * sizeof(unsigned long long);
+  static bool attr_done[8] = {false};
+  if (!attr_done[c->device & 7]) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_done[c->device & 7] = true;
+  }
+  kern<<<static_cast<unsigned>(n_chunks), THREADS, smem, st>>>(a);
+  c->launches++;
+  return 0;
+}
+
 static int launch_topk(vrag_corpus* c, const float* d_scores, const long long* d_ids, int64_t id_base, int64_t n,
                        int k, float* out_scores, long long* out_ids, int* out_pos, int* out_count, cudaStream_t st) {
   if (k < 1) return fail("k must be >= 1");
   if (k > kTopkMaxK) return fail("k=%d exceeds the supported maximum %d", k, kTopkMaxK);
   if (n >= (1ll << 32) - 1) return fail("too many items for top-k");
-  static bool attr_done[8] = {false};
-  const size_t smem = kTopkChunk * sizeof(unsigned long long);
-  if (!attr_done[c->device & 7]) {
-    CUDA_OK(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_done[c->device & 7] = true;
-  }
+  int k2 = 1;
+  while (k2 < k) k2 <<= 1;
   TopkArgs a;
   memset(&a, 0, sizeof(a));
   a.k = k;
@@ -532,26 +543,34 @@ static int launch_topk(vrag_corpus* c, const float* d_scores, const long long* d
   a.ids = d_ids;
   a.id_base = id_base;
   a.n_total = n;
-  long long m = n;
-  long long nch = std::max<long long>(1, (m + kTopkChunk - 1) / kTopkChunk);
-  if (nch > 1) {
-    TRY(c->d_keys_a.ensure(static_cast<size_t>(nch) * k));
-    TRY(c->d_keys_b.ensure(static_cast<size_t>((nch * k + kTopkChunk - 1) / kTopkChunk) * k + k));
-  }
   a.scores = d_scores;
-  a.n = m;
+  long long m = n;
+  // chunk policy: k <= 1024 -> 2048-key chunks (many blocks, cheap sorts), last level 1024 or 2048;
+  //               larger k  -> 8192-key chunks.
+  const bool big_k = k > 1024;
+  {
+    const long long ch0 = big_k ? 8192 : 2048;
+    const long long nch0 = std::max<long long>(1, (m + ch0 - 1) / ch0);
+    if (nch0 > 1) {
+      TRY(c->d_keys_a.ensure(static_cast<size_t>(nch0) * k));
+      TRY(c->d_keys_b.ensure(static_cast<size_t>((nch0 * k + ch0 - 1) / ch0) * k + k));
+    }
+  }
   unsigned long long* bufs[2] = {c->d_keys_a.p, c->d_keys_b.p};
   int which = 0;
   while (true) {
+    const int chunk = big_k ? 8192 : (m <= 1024 ? 1024 : 2048);
+    const long long nch = std::max<long long>(1, (m + chunk - 1) / chunk);
+    a.n = m;
+    a.k2 = std::min(k2, chunk);
     a.keys_out = (nch > 1) ? bufs[which] : nullptr;
-    topk_kernel<<<static_cast<unsigned>(nch), kTopkThreads, smem, st>>>(a);
-    c->launches++;
+    if (chunk == 8192) TRY((launch_topk_level<8192, 1024>(c, a, nch, st)));
+    else if (chunk == 2048) TRY((launch_topk_level<2048, 1024>(c, a, nch, st)));
+    else TRY((launch_topk_level<1024, 512>(c, a, nch, st)));
     if (nch == 1) break;
     a.scores = nullptr;
     a.keys_in = bufs[which];
     m = nch * k;
-    a.n = m;
-    nch = (m + kTopkChunk - 1) / kTopkChunk;
     which ^= 1;
   }
   CUDA_OK(cudaGetLastError());
@@ -689,6 +708,313 @@ extern "C" int vrag_topk_dev(vrag_corpus_t* c, const float* scores_dev, const in
   if (!out_scores_dev || !out_ids_dev) return fail("NULL device pointer");
   return launch_topk(c, scores_dev, reinterpret_cast<const long long*>(ids_dev), id_base, n, k, out_scores_dev,
                      reinterpret_cast<long long*>(out_ids_dev), nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+
+// ------------------------------------------------------------------------------------------------ pooling
+static int ceil_div_i64(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
+
+// Output rows + argument validation for one spec on a page of t rows (grid overrides for per-page grids).
+static int pool_out_rows(const vrag_pool_spec_t& s, int64_t t, int gh, int gw, int64_t* out) {
+  switch (s.kind) {
+    case VRAG_POOL_TILE_MEAN:
+      if (s.patches_per_tile <= 0) return fail("patches_per_tile must be > 0");
+      *out = ceil_div_i64(t, s.patches_per_tile);
+      return 0;
+    case VRAG_POOL_ADAPTIVE_ROWS: {
+      if (gh <= 0 || gw <= 0) return fail("grid_h and grid_w must be > 0");
+      if (static_cast<int64_t>(gh) * gw != t)
+        return fail("Expected %lld visual tokens for grid_h x grid_w=%dx%d, got %lld", (long long)gh * gw, gh, gw, (long long)t);
+      if (gh > 256) return fail("grid_h=%d exceeds the supported maximum 256", gh);
+      int r = s.target_rows > 0 ? s.target_rows : gh;
+      if (s.clamp_to_h && r > gh) r = gh;
+      *out = r;
+      return 0;
+    }
+    case VRAG_POOL_SEQ_CHUNKS:
+      if (s.target_rows <= 0) return fail("target_rows must be > 0");
+      if (t < 1) return fail("embedding must be non-empty");
+      *out = s.target_rows;
+      return 0;
+    case VRAG_POOL_COLSMOL_EXPERIMENTAL: {
+      if (s.patches_per_tile <= 0) return fail("patches_per_tile must be > 0");
+      int64_t nt = s.num_tiles > 0 ? s.num_tiles : ceil_div_i64(t, s.patches_per_tile);
+      if ((nt - 1) * s.patches_per_tile >= t) nt = ceil_div_i64(t, s.patches_per_tile);
+      if (nt <= 0) return fail("Not enough tokens for num_tiles=%d, patches_per_tile=%d: got %lld", s.num_tiles, s.patches_per_tile, (long long)t);
+      const int64_t last = (nt - 1) * s.patches_per_tile;
+      *out = (nt - 1) + std::min<int64_t>(s.patches_per_tile, t - last);
+      return 0;
+    }
+    case VRAG_POOL_LEGACY_CONV:
+      if (t < 1) return fail("row_vectors must be non-empty");
+      if (s.window < 1) return fail("window_size must be >= 1");
+      if (s.window % 2 == 0) return fail("window_size must be odd");
+      if (s.window == 1 || t == 1) *out = t;
+      else if (s.window == 3 && t == 2) *out = 3;
+      else *out = t + 2 * (s.window / 2);
+      return 0;
+    case VRAG_POOL_SMOOTH:
+      if (t < 1) return fail("row_vectors must be non-empty");
+      if (s.window < 1) return fail("window_size must be >= 1");
+      if (s.window > kPoolMaxWeights) return fail("window_size %d exceeds the supported maximum %d", s.window, kPoolMaxWeights);
+      if (s.window > 1 && s.n_weights != s.window) return fail("SMOOTH needs window weights");
+      *out = t;
+      return 0;
+    case VRAG_POOL_TILE_4N: {
+      if (gh <= 0 || gw <= 0) return fail("n_rows and n_cols must be > 0");
+      const int64_t g = static_cast<int64_t>(gh) * gw;
+      if (t < g) return fail("Expected at least %lld tile vectors for n_rows x n_cols=%dx%d, got %lld", (long long)g, gh, gw, (long long)t);
+      if (!s.include_self && g == 1) return fail("need at least one array to stack");
+      *out = g + ((s.has_global && t > g) ? 1 : 0);
+      return 0;
+    }
+    case VRAG_POOL_GLOBAL_MEAN:
+      *out = 1;
+      return 0;
+    default:
+      return fail("unknown pooling kind %d", s.kind);
+  }
+}
+
+static bool pool_is_row_level(int kind) {
+  return kind == VRAG_POOL_SMOOTH || kind == VRAG_POOL_TILE_4N;
+}
+static void pool_grid_of(const vrag_pool_spec_t& s, const int32_t* grid_hw, int64_t page, int* gh, int* gw) {
+  if (s.kind == VRAG_POOL_TILE_4N) {
+    *gh = s.n_rows;
+    *gw = s.n_cols;
+  } else {
+    *gh = s.grid_h;
+    *gw = s.grid_w;
+  }
+  if (grid_hw) {
+    *gh = grid_hw[2 * page];
+    *gw = grid_hw[2 * page + 1];
+  }
+}
+
+extern "C" int vrag_pool_out_rows(const vrag_pool_spec_t* spec, int64_t in_rows, int64_t* out_rows) {
+  if (!spec || !out_rows) return fail("NULL argument");
+  int gh, gw;
+  pool_grid_of(*spec, nullptr, 0, &gh, &gw);
+  return pool_out_rows(*spec, in_rows, gh, gw, out_rows);
+}
+
+static PoolSpecDev to_dev_spec(const vrag_pool_spec_t& s) {
+  PoolSpecDev d;
+  memset(&d, 0, sizeof(d));
+  d.kind = s.kind;
+  d.ppt = s.patches_per_tile;
+  d.grid_h = s.grid_h;
+  d.grid_w = s.grid_w;
+  d.target_rows = s.target_rows;
+  d.clamp_to_h = s.clamp_to_h;
+  d.num_tiles = s.num_tiles;
+  d.window = s.window;
+  d.n_weights = s.n_weights;
+  for (int i = 0; i < kPoolMaxWeights; ++i) d.weights[i] = s.weights[i];
+  d.n_rows = s.n_rows;
+  d.n_cols = s.n_cols;
+  d.has_global = s.has_global;
+  d.include_self = s.include_self;
+  d.via_f16 = s.via_f16;
+  return d;
+}
+
+// Launch the right kernel(s) for `specs` over `in`; every dev spec already has its output pointers set.
+static int launch_pool(const PoolInput& in, int n, const vrag_pool_spec_t* specs, PoolSpecDev* dev, int max_in_rows,
+                       int max_grid_h, int num_sms, cudaStream_t st, int64_t* launches) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_OK(cudaFuncSetAttribute(pool_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 512));
+    CUDA_OK(cudaFuncSetAttribute(pool_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 512));
+    attr_done = true;
+  }
+  if (in.n_pages == 0) return 0;
+  PoolRowsArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.in = in;
+  for (int i = 0; i < n; ++i) {
+    if (pool_is_row_level(specs[i].kind)) {
+      if (ra.n_specs >= kPoolMaxSpecs) return fail("too many row-level pooling specs");
+      ra.specs[ra.n_specs++] = dev[i];
+    }
+  }
+  // LEGACY_CONV / GLOBAL_MEAN ride along with the row-level pass when the input pages are small enough
+  const bool small_pages = max_in_rows <= 256;
+  for (int i = 0; i < n; ++i) {
+    const int k = specs[i].kind;
+    if (pool_is_row_level(k)) continue;
+    if (ra.n_specs > 0 && small_pages && (k == VRAG_POOL_LEGACY_CONV || k == VRAG_POOL_GLOBAL_MEAN) &&
+        ra.n_specs < kPoolMaxSpecs) {
+      ra.specs[ra.n_specs++] = dev[i];
+      continue;
+    }
+    const size_t smem = (k == VRAG_POOL_ADAPTIVE_ROWS) ? static_cast<size_t>(std::max(max_grid_h, 1)) * 512 : 0;
+    const unsigned grid = static_cast<unsigned>(std::min<long long>(in.n_pages, static_cast<long long>(num_sms) * 8));
+    pool_tokens_kernel<<<grid, 256, smem, st>>>(in, dev[i]);
+    if (launches) ++*launches;
+  }
+  if (ra.n_specs > 0) {
+    if (max_in_rows > 256) return fail("SMOOTH / TILE_4N need pages of at most 256 rows (got %d)", max_in_rows);
+    const size_t smem = static_cast<size_t>(std::max(max_in_rows, 1)) * 512;
+    const unsigned grid = static_cast<unsigned>(std::min<long long>(in.n_pages, static_cast<long long>(num_sms) * 8));
+    pool_rows_kernel<<<grid, 128, smem, st>>>(ra);
+    if (launches) ++*launches;
+  }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vrag_pool_page(int device, const vrag_pool_spec_t* spec, const void* in, int in_dtype, int64_t in_rows,
+                              void* out, int out_dtype, int64_t out_capacity_rows, int64_t* out_rows) {
+  if (!spec || !out_rows) return fail("NULL argument");
+  if ((in_dtype != VRAG_F16 && in_dtype != VRAG_F32) || (out_dtype != VRAG_F16 && out_dtype != VRAG_F32))
+    return fail("unknown dtype");
+  if (in_rows < 0) return fail("in_rows < 0");
+  int gh, gw;
+  pool_grid_of(*spec, nullptr, 0, &gh, &gw);
+  int64_t n_out = 0;
+  TRY(pool_out_rows(*spec, in_rows, gh, gw, &n_out));
+  *out_rows = n_out;
+  if (n_out > out_capacity_rows) return fail("output buffer too small: need %lld rows", (long long)n_out);
+  if (n_out == 0) return 0;
+  if (!in && in_rows > 0) return fail("in is NULL");
+  if (!out) return fail("out is NULL");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device available: libvrag_b200 has no CPU fallback");
+  CUDA_OK(cudaSetDevice(device));
+  const size_t in_b = static_cast<size_t>(in_rows) * 128 * (in_dtype == VRAG_F32 ? 4 : 2);
+  const size_t out_b = static_cast<size_t>(n_out) * 128 * (out_dtype == VRAG_F32 ? 4 : 2);
+  void *d_in = nullptr, *d_out = nullptr;
+  cudaStream_t st;
+  CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  int rc = 0;
+  do {
+    if (cudaMalloc(&d_in, std::max<size_t>(in_b, 256)) != cudaSuccess || cudaMalloc(&d_out, out_b) != cudaSuccess) {
+      rc = fail("cudaMalloc failed in vrag_pool_page");
+      break;
+    }
+    if (in_b && cudaMemcpyAsync(d_in, in, in_b, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = fail("H2D copy failed"); break; }
+    PoolInput pin;
+    memset(&pin, 0, sizeof(pin));
+    pin.in = d_in;
+    pin.in_f32 = in_dtype == VRAG_F32;
+    pin.in_fixed = std::max<int64_t>(in_rows, 1);
+    pin.n_pages = 1;
+    PoolSpecDev dev = to_dev_spec(*spec);
+    dev.out = d_out;
+    dev.out_f32 = out_dtype == VRAG_F32;
+    dev.out_fixed = n_out;
+    long long* d_off = nullptr;
+    if (in_rows == 0) {   // empty page (GLOBAL_MEAN of an empty mean-pool): describe it with offsets {0,0}
+      long long h_off[2] = {0, 0};
+      if (cudaMalloc(&d_off, sizeof(h_off)) != cudaSuccess) { rc = fail("cudaMalloc failed"); break; }
+      cudaMemcpyAsync(d_off, h_off, sizeof(h_off), cudaMemcpyHostToDevice, st);
+      pin.in_off = d_off;
+      pin.in_fixed = 0;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    rc = launch_pool(pin, 1, spec, &dev, static_cast<int>(in_rows), gh, prop.multiProcessorCount, st, nullptr);
+    if (rc == 0 && cudaMemcpyAsync(out, d_out, out_b, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = fail("D2H copy failed");
+    if (rc == 0) {
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) rc = fail("pooling kernel failed: %s", cudaGetErrorString(e));
+    }
+    if (d_off) cudaFree(d_off);
+  } while (0);
+  if (d_in) cudaFree(d_in);
+  if (d_out) cudaFree(d_out);
+  cudaStreamDestroy(st);
+  return rc;
+}
+
+extern "C" int vrag_store_pool(vrag_corpus_t* c, const char* src, int n_specs, const vrag_pool_spec_t* specs,
+                               const char* const* dst_names, const int32_t* grid_hw) {
+  Store* sp;
+  TRY(find_store(c, src, &sp));
+  TRY(set_device(c));
+  if (n_specs < 1 || n_specs > kPoolMaxSpecs) return fail("n_specs %d out of range [1,%d]", n_specs, kPoolMaxSpecs);
+  if (!specs || !dst_names) return fail("NULL argument");
+  const int64_t n_pages = sp->n_pages;
+  // 1. shapes
+  std::vector<std::vector<int64_t>> offs(n_specs);
+  std::vector<int64_t> fixed(n_specs, 0);
+  int max_gh = 0;
+  for (int i = 0; i < n_specs; ++i) {
+    if (!dst_names[i] || !*dst_names[i]) return fail("dst name %d is empty", i);
+    if (std::string(dst_names[i]) == src) return fail("dst store must differ from src");
+    offs[i].resize(n_pages + 1);
+    offs[i][0] = 0;
+    bool all_same = true;
+    for (int64_t p = 0; p < n_pages; ++p) {
+      const int64_t t = sp->fixed_rows > 0 ? sp->fixed_rows : (sp->h_offsets[p + 1] - sp->h_offsets[p]);
+      int gh, gw;
+      pool_grid_of(specs[i], grid_hw, p, &gh, &gw);
+      int64_t r = 0;
+      TRY(pool_out_rows(specs[i], t, gh, gw, &r));
+      if (specs[i].kind == VRAG_POOL_ADAPTIVE_ROWS) max_gh = std::max(max_gh, gh);
+      offs[i][p + 1] = offs[i][p] + r;
+      if (p > 0 && r != offs[i][1]) all_same = false;
+    }
+    if (all_same && n_pages > 0 && offs[i][1] > 0) fixed[i] = offs[i][1];
+  }
+  // 2. allocate destination stores, device offsets, per-page grids
+  int* d_grid = nullptr;
+  if (grid_hw && n_pages > 0) {
+    CUDA_OK(cudaMalloc(&d_grid, n_pages * 2 * sizeof(int)));
+    CUDA_OK(cudaMemcpyAsync(d_grid, grid_hw, n_pages * 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  }
+  std::vector<PoolSpecDev> dev(n_specs);
+  std::vector<Store*> dst(n_specs);
+  std::vector<long long*> d_offs(n_specs, nullptr);
+  // NOTE: alloc_store may rehash the map; std::map keeps element addresses stable, and `sp` stays valid.
+  for (int i = 0; i < n_specs; ++i) {
+    TRY(alloc_store(c, dst_names[i], offs[i][n_pages], &dst[i]));
+    dev[i] = to_dev_spec(specs[i]);
+    dev[i].out = dst[i]->rows;
+    dev[i].out_f32 = 0;
+    dev[i].out_fixed = fixed[i];
+    if (fixed[i] == 0 && n_pages > 0) {
+      CUDA_OK(cudaMalloc(&d_offs[i], (n_pages + 1) * sizeof(long long)));
+      CUDA_OK(cudaMemcpyAsync(d_offs[i], offs[i].data(), (n_pages + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+      dev[i].out_off = d_offs[i];
+    }
+  }
+  TRY(find_store(c, src, &sp));
+  PoolInput pin;
+  memset(&pin, 0, sizeof(pin));
+  pin.in = sp->rows;
+  pin.in_f32 = 0;
+  pin.in_off = sp->offsets;
+  pin.in_fixed = sp->fixed_rows;
+  pin.n_pages = n_pages;
+  pin.grid_hw = d_grid;
+  CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+  int rc = launch_pool(pin, n_specs, specs, dev.data(), static_cast<int>(sp->max_rows), max_gh, c->num_sms, c->stream,
+                       &c->launches);
+  CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+  if (rc == 0) {
+    for (int i = 0; i < n_specs; ++i) {
+      const int64_t tr = offs[i][n_pages];
+      if (tr > 0) {
+        inv_norm_kernel<<<static_cast<unsigned>((tr * 16 + 255) / 256), 256, 0, c->stream>>>(dst[i]->rows, tr, dst[i]->inv);
+        c->launches++;
+      }
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  for (auto p : d_offs) if (p) cudaFree(p);
+  if (d_grid) cudaFree(d_grid);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail("pooling kernels failed: %s", cudaGetErrorString(e));
+  cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1);
+  c->last_ms[1] = c->last_ms[0];
+  for (int i = 0; i < n_specs; ++i)
+    TRY(finish_store(c, *dst[i], fixed[i] > 0 ? nullptr : offs[i].data(), n_pages, fixed[i]));
+  return 0;
 }
 
 extern "C" int vrag_last_timing(vrag_corpus_t* c, float* out_ms, int n) {

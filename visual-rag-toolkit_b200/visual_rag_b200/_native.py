@@ -30,6 +30,28 @@ POOL_TILE_4N = 6
 POOL_GLOBAL_MEAN = 7
 POOL_SEQ_CHUNKS = 8
 
+class PoolSpec(C.Structure):
+    """vrag_pool_spec_t (include/vrag_b200.h)."""
+
+    _fields_ = [
+        ("kind", C.c_int),
+        ("patches_per_tile", C.c_int),
+        ("grid_h", C.c_int),
+        ("grid_w", C.c_int),
+        ("target_rows", C.c_int),
+        ("clamp_to_h", C.c_int),
+        ("num_tiles", C.c_int),
+        ("window", C.c_int),
+        ("n_weights", C.c_int),
+        ("weights", C.c_float * 16),
+        ("n_rows", C.c_int),
+        ("n_cols", C.c_int),
+        ("has_global", C.c_int),
+        ("include_self", C.c_int),
+        ("via_f16", C.c_int),
+    ]
+
+
 _i64p = C.POINTER(C.c_int64)
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int)
@@ -52,6 +74,9 @@ SIGNATURES = {
     "vrag_search_multistage": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _u32p, _i32p, _f32p, C.c_int, _i32p, _i64p, C.c_int64, _f32p, _i64p, _i32p]),
     "vrag_score_dev": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "vrag_topk_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vrag_pool_out_rows": (C.c_int, [C.POINTER(PoolSpec), C.c_int64, _i64p]),
+    "vrag_pool_page": (C.c_int, [C.c_int, C.POINTER(PoolSpec), C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64, _i64p]),
+    "vrag_store_pool": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(PoolSpec), C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]),
     "vrag_last_timing": (C.c_int, [C.c_void_p, _f32p, C.c_int]),
     "vrag_launch_count": (C.c_int64, [C.c_void_p]),
 }

@@ -188,6 +188,23 @@ class GpuCorpus:
         r0, n = self.page_range(name, local_page)
         return self.read_rows(name, r0, n)
 
+    # ------------------------------------------------------------------ bulk pooling on the device
+    def pool_store(self, src: str, specs: Sequence, dst_names: Sequence[str], grid_hw=None) -> float:
+        """Derive pooled stores from `src` without leaving HBM (pipeline.py:400-507 for a whole collection).
+        specs: sequence of _native.PoolSpec (see visual_rag_b200.embedding.pooling.spec_*). grid_hw: optional
+        [n_pages,2] int32 per-page (grid_h, grid_w) / (n_rows, n_cols). Returns the device time in ms."""
+        n = len(specs)
+        arr = (N.PoolSpec * n)(*specs)
+        names = (C.c_char_p * n)(*[d.encode() for d in dst_names])
+        g = None
+        if grid_hw is not None:
+            gh = np.ascontiguousarray(np.asarray(grid_hw, dtype=np.int32).reshape(-1, 2))
+            if gh.shape[0] != self.n_pages(src):
+                raise ValueError("grid_hw must have one (h, w) pair per page")
+            g = gh.ctypes.data_as(C.POINTER(C.c_int32))
+        N.check(self._lib.vrag_store_pool(self._h, src.encode(), n, arr, names, g))
+        return self.last_timing_ms()[0]
+
     # ------------------------------------------------------------------ scoring
     def score(
         self,
