@@ -313,3 +313,22 @@ def test_reference_style_client_calls(gpu_client):
                                timeout=120).points
     assert len(pts2) == 5 and {p.id for p in pts2} <= {p.id for p in pts}
     assert client.get_collection("c").points_count == 150
+
+
+def test_sharded_searcher_single_rank_matches_corpus_api(corpus):
+    """The multi-GPU code path (device-pointer API + merge) at world size 1 equals the host API."""
+    from visual_rag_b200.distributed import ShardedSearcher
+
+    n = 4000
+    corpus.add_synthetic_store("initial", n, fixed_rows=300, seed=5)
+    corpus.add_synthetic_store("mean_pooling", n, fixed_rows=32, seed=6)
+    q = CS.query_rows(1300, 20)
+    s = ShardedSearcher(corpus)
+    stages = [("mean_pooling", False, 256), ("initial", False, 10)]
+    a = s.search_multistage(stages, q)
+    b = corpus.search_multistage(stages, q)
+    for (sa, ia), (sb, ib) in zip(a, b):
+        assert ia.tolist() == ib.tolist() and np.array_equal(sa, sb)
+    sa, ia = s.search("initial", q, 7)
+    sb, ib = corpus.search("initial", q, 7)
+    assert ia.tolist() == ib.tolist() and np.array_equal(sa, sb)
