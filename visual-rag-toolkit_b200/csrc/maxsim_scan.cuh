@@ -28,7 +28,7 @@ constexpr int kTileRows = 128;       // UMMA M
 constexpr int kTileBytes = kTileRows * kDim * 2;  // 32 KB of fp16 per stage
 constexpr int kHalfBytes = kTileBytes / 2;        // one K-half (64 fp16 = 128 B per row)
 constexpr int kBoxRowsSmall = 32;    // partial tiles are fetched in 32-row boxes
-constexpr int kScanThreads = 192;    // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+// threads: warp0 TMA, warp1 MMA, then 4 epilogue warps per epilogue group (ScanCfg::threads)
 // inv_norm rows travel by 1-D TMA whose global start must be 16-byte aligned: fetch from (row & ~3) with a
 // box 4 floats longer and let the epilogue index with the misalignment (row & 3).
 // A tile is split into 128/slot_rows slots (1 slot unless candidates are packed); slot j keeps its scales at
@@ -52,6 +52,11 @@ struct ScanParams {
   int slot_rows;              // rows reserved per candidate inside a tile (32/64/128); 128 unless PACKED + cand
   int pages_per_tile;         // PACKED + dense + fixed_rows: floor(128 / fixed_rows)
   const int* tile_page0;      // PACKED + dense + variable rows: [n_tiles+1] first page of each tile
+  const long long* tile_row0; // PACKED + dense + variable rows: [n_tiles+1] first row of each tile
+  int slot_mode;              // PACKED: 1 -> every item is fetched separately into its own slot of slot_rows tile rows
+  int hi_only;                // 1: contract only the fp16 hi half of the query (N = QP); QP >= 16
+  int shfl_rows;              // PACKED: > 0 -> every page sits in its own power-of-two slot of shfl_rows (<= 32) tile
+                              //   rows, so the per-page max is a segmented warp butterfly (no smem round trip)
   long long n_tiles;          // PACKED: number of tiles (work units)
 };
 
@@ -61,18 +66,21 @@ struct ScanCfg {
   static constexpr int ACC = (N <= 128) ? 4 : 2;           // TMEM accumulator stages
   static constexpr int TMEM_COLS = (ACC * N < 32) ? 32 : ACC * N;
   static constexpr int B_BYTES = N * kDim * 2;
-  static constexpr int SC_PITCH = kTileRows + 1;           // PACKED: transposed score buffer pitch
-  static constexpr int SC_BUFS = (QP <= 32) ? 2 : 1;       // PACKED: score buffers (1 => extra barrier per tile)
+  static constexpr int SC_PITCH = kTileRows + 4;           // PACKED: transposed score buffer pitch (16 B aligned rows)
+  // PACKED: two epilogue groups of 4 warps alternate tiles (the per-tile epilogue is a dependent chain on one
+  // warp per SM sub-partition; a second group per sub-partition hides its latency). One score buffer per group.
+  static constexpr int EPI_GROUPS_PACKED = (QP <= 64) ? 2 : 1;
   static constexpr int MISC_BYTES = 8192;                  // barriers, reduce scratch, segment tables
+  static constexpr int epi_groups(bool packed) { return packed ? EPI_GROUPS_PACKED : 1; }
+  static constexpr int threads(bool packed) { return 64 + 128 * epi_groups(packed); }
+  static constexpr int sc_bytes(bool packed) { return packed ? EPI_GROUPS_PACKED * QP * SC_PITCH * 4 : 0; }
   static constexpr int stages(bool packed) {
-    const int budget = 227 * 1024 - 1024 /*align slack*/ - B_BYTES - MISC_BYTES -
-                       (packed ? SC_BUFS * QP * SC_PITCH * 4 : 0);
+    const int budget = 227 * 1024 - 1024 /*align slack*/ - B_BYTES - MISC_BYTES - sc_bytes(packed);
     const int s = budget / (kTileBytes + kScaleStride * 4);
     return s > 6 ? 6 : s;
   }
   static constexpr size_t smem_bytes(bool packed) {
-    return 1024 + size_t(stages(packed)) * (kTileBytes + kScaleStride * 4) + B_BYTES + MISC_BYTES +
-           (packed ? SC_BUFS * QP * SC_PITCH * 4 : 0);
+    return 1024 + size_t(stages(packed)) * (kTileBytes + kScaleStride * 4) + B_BYTES + MISC_BYTES + sc_bytes(packed);
   }
 };
 
@@ -95,6 +103,78 @@ __device__ __forceinline__ bool resolve_page(const ScanParams& p, long long page
 }
 __device__ __forceinline__ long long item_page(const ScanParams& p, long long item) {
   return p.cand ? (__ldg(p.cand + item) - p.cand_base) : item;
+}
+
+// Row ranges one PACKED tile fetches: dense layouts -> one contiguous range; slot mode -> up to 4 items.
+struct PackedTileMeta {
+  long long r0[4];
+  int nr[4];
+  int cnt;
+};
+__device__ __forceinline__ void packed_tile_meta(const ScanParams& p, long long u, PackedTileMeta& m) {
+  if (!p.slot_mode) {
+    m.cnt = 1;
+    if (p.fixed_rows > 0) {
+      const long long pg0 = u * p.pages_per_tile;
+      const long long pg1 = min(pg0 + p.pages_per_tile, p.n_pages);
+      m.r0[0] = pg0 * p.fixed_rows;
+      m.nr[0] = static_cast<int>((pg1 - pg0) * p.fixed_rows);
+    } else {
+      const long long a = __ldg(p.tile_row0 + u), b = __ldg(p.tile_row0 + u + 1);
+      m.r0[0] = a;
+      m.nr[0] = static_cast<int>(b - a);
+    }
+  } else {
+    const int per_tile = kTileRows / p.slot_rows;
+    const long long i0 = u * per_tile;
+    m.cnt = static_cast<int>(min(static_cast<long long>(per_tile), p.n_items - i0));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      m.r0[j] = 0;
+      m.nr[j] = 0;
+      if (j < m.cnt) resolve_page(p, item_page(p, i0 + j), m.r0[j], m.nr[j]);
+    }
+  }
+}
+
+// General PACKED path: entry `et` of tile u's segment table (item, first tile row, end tile row) and the table size.
+__device__ __forceinline__ void packed_segment(const ScanParams& p, long long u, int et, int& nseg, int& item, int& rb,
+                                               int& re) {
+  item = rb = re = 0;
+  if (!p.slot_mode) {
+    long long pg0, pg1;
+    if (p.fixed_rows > 0) {
+      pg0 = u * p.pages_per_tile;
+      pg1 = min(pg0 + p.pages_per_tile, p.n_pages);
+    } else {
+      pg0 = __ldg(p.tile_page0 + u);
+      pg1 = __ldg(p.tile_page0 + u + 1);
+    }
+    nseg = static_cast<int>(pg1 - pg0);
+    if (et < nseg) {
+      long long rbase, r0;
+      int tmp, nr;
+      if (p.fixed_rows > 0) rbase = pg0 * p.fixed_rows;
+      else rbase = __ldg(p.tile_row0 + u);
+      (void)tmp;
+      resolve_page(p, pg0 + et, r0, nr);
+      item = static_cast<int>(pg0 + et);   // dense: item == page (n_items == n_pages < 2^31 per shard)
+      rb = static_cast<int>(r0 - rbase);
+      re = rb + nr;
+    }
+  } else {
+    const int per_tile = kTileRows / p.slot_rows;
+    const long long i0 = u * per_tile;
+    nseg = static_cast<int>(min(static_cast<long long>(per_tile), p.n_items - i0));
+    if (et < nseg) {
+      long long r0;
+      int nr;
+      resolve_page(p, item_page(p, i0 + et), r0, nr);
+      item = static_cast<int>(i0 + et);
+      rb = et * p.slot_rows;
+      re = rb + nr;   // nr == 0 -> empty segment -> -inf
+    }
+  }
 }
 
 // Fetch `nrows` (1..128) document rows starting at global row `row` into tile rows [dst_row, dst_row+nrows)
@@ -149,8 +229,45 @@ __device__ __forceinline__ void warp_transpose_max(float* v, int lane) {
   }
 }
 
+// PACKED fast path: the SR (power of two <= 32) lanes of a slot hold QP values each (one tile row per lane).
+// Segmented transpose-max over the slot's lanes, then sum over q. Returns the slot's score in all of its lanes.
+template <int QP, int SR>
+__device__ __forceinline__ float slot_maxsim(float* v, int lane, int q_valid) {
+  int cnt = QP;
+#pragma unroll
+  for (int off = SR / 2; off >= 1; off >>= 1) {
+    if (cnt > 1) {
+      const int half = cnt >> 1;
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j < half) {
+          const float keep = upper ? v[j + half] : v[j];
+          const float send = upper ? v[j] : v[j + half];
+          v[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
+        }
+      }
+      cnt = half;
+    } else {
+      v[0] = fmaxf(v[0], __shfl_xor_sync(0xffffffffu, v[0], off));
+    }
+  }
+  constexpr int CF = QP >= SR ? QP / SR : 1;    // q values left per lane
+  constexpr int DUP = QP >= SR ? 1 : SR / QP;   // lanes holding the same q
+  const int b = lane & (SR - 1);
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < CF; ++i) {
+    const int q = (b / DUP) * CF + i;
+    if (q < q_valid && (b % DUP) == 0) sum += v[i];
+  }
+#pragma unroll
+  for (int off = SR / 2; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  return sum;
+}
+
 template <int QP, bool PACKED>
-__global__ void __launch_bounds__(kScanThreads, 1)
+__global__ void __launch_bounds__(ScanCfg<QP>::threads(PACKED), 1)
 maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_constant__ CUtensorMap tm_rows32,
                    const __grid_constant__ CUtensorMap tm_scale128, const __grid_constant__ CUtensorMap tm_scale32,
                    const ScanParams p) {
@@ -158,6 +275,8 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   constexpr int N = Cfg::N;
   constexpr int ACC = Cfg::ACC;
   constexpr int STAGES = Cfg::stages(PACKED);
+  constexpr int NTHREADS = Cfg::threads(PACKED);
+  constexpr int EPI_GROUPS = Cfg::epi_groups(PACKED);
   constexpr int QG = (QP + 31) / 32;           // 32-wide query groups
   constexpr int QW = QP < 32 ? QP : 32;        // queries per group
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
@@ -167,8 +286,8 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * kTileBytes;
   float* sScale = reinterpret_cast<float*>(sB + Cfg::B_BYTES);
-  float* sSc = sScale + STAGES * kScaleStride;                       // PACKED: [SC_BUFS][QP][SC_PITCH]
-  uint8_t* misc = reinterpret_cast<uint8_t*>(sSc + (PACKED ? Cfg::SC_BUFS * QP * Cfg::SC_PITCH : 0));
+  float* sSc = sScale + STAGES * kScaleStride;                       // PACKED: [EPI_GROUPS][QP][SC_PITCH]
+  uint8_t* misc = reinterpret_cast<uint8_t*>(sSc) + Cfg::sc_bytes(PACKED);
   uint64_t* full = reinterpret_cast<uint64_t*>(misc);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
@@ -176,7 +295,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC);
   int* sMis = reinterpret_cast<int*>(misc + 256);                 // [STAGES][4] scale misalignment per slot
   float* sRed = reinterpret_cast<float*>(misc + 512);             // LARGE: [2][4][QP]
-  int* sSeg = reinterpret_cast<int*>(misc + 512);                 // PACKED: [2][3][128] ints (item, begin, end)
+  int* sSeg = reinterpret_cast<int*>(misc + 512);                 // PACKED: [EPI_GROUPS][3][128] ints (item, begin, end)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -201,7 +320,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   {  // query operand image: global -> smem (already in the swizzled UMMA layout)
     const uint4* src = reinterpret_cast<const uint4*>(p.qimg);
     uint4* dst = reinterpret_cast<uint4*>(sB);
-    for (int i = threadIdx.x; i < Cfg::B_BYTES / 16; i += kScanThreads) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < Cfg::B_BYTES / 16; i += NTHREADS) dst[i] = __ldg(src + i);
     fence_proxy_async_smem();
   }
   tc_fence_before_sync();
@@ -216,6 +335,8 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
     // ===================================================================== TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      PackedTileMeta cur, nxt;
+      cur.cnt = nxt.cnt = 0;
       for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
         if constexpr (!PACKED) {
           long long row0;
@@ -235,48 +356,34 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         } else {
+          // tile metadata (row ranges) is loaded one tile ahead so the dependent global loads (candidate id ->
+          // page offsets) overlap the previous tile instead of stalling the TMA issue
+          if (u == static_cast<long long>(blockIdx.x)) packed_tile_meta(p, u, cur);
+          const long long un = u + gridDim.x;
+          if (un < n_units) packed_tile_meta(p, un, nxt);
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* a = sA + stage * kTileBytes;
           float* sc = sScale + stage * kScaleStride;
-          if (p.cand == nullptr) {
-            // dense: pages [pg0, pg1) are contiguous rows -> one fetch
-            long long pg0, pg1;
-            if (p.fixed_rows > 0) {
-              pg0 = u * p.pages_per_tile;
-              pg1 = min(pg0 + p.pages_per_tile, p.n_pages);
-            } else {
-              pg0 = __ldg(p.tile_page0 + u);
-              pg1 = __ldg(p.tile_page0 + u + 1);
-            }
-            long long r0, r1;
-            int tmp;
-            resolve_page(p, pg0, r0, tmp);
-            resolve_page(p, pg1 - 1, r1, tmp);
-            const int rows = static_cast<int>(r1 + tmp - r0);
-            uint32_t bytes = 0;
-            if (rows > 0)
-              bytes = issue_rows(a, sc, &full[stage], &tm_rows128, &tm_rows32, &tm_scale128, &tm_scale32, r0, rows,
-                                 0, use_scale);
-            sMis[stage * 4] = static_cast<int>(r0 & 3);
-            mbar_arrive_expect_tx(&full[stage], bytes);
+          uint32_t bytes = 0;
+          if (!p.slot_mode) {
+            // dense: the tile's pages are contiguous rows -> one fetch
+            if (cur.nr[0] > 0)
+              bytes = issue_rows(a, sc, &full[stage], &tm_rows128, &tm_rows32, &tm_scale128, &tm_scale32, cur.r0[0],
+                                 cur.nr[0], 0, use_scale);
+            sMis[stage * 4] = static_cast<int>(cur.r0[0] & 3);
           } else {
-            // candidates: each occupies its own slot of slot_rows rows
-            const int per_tile = kTileRows / p.slot_rows;
-            const long long i0 = u * per_tile;
-            const int cnt = static_cast<int>(min(static_cast<long long>(per_tile), p.n_items - i0));
-            uint32_t bytes = 0;
-            for (int j = 0; j < cnt; ++j) {
-              long long r0;
-              int nr;
-              resolve_page(p, item_page(p, i0 + j), r0, nr);
-              if (nr > 0)
+            // slot mode (candidate lists): each item occupies its own slot
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j < cur.cnt && cur.nr[j] > 0)
                 bytes += issue_rows(a, sc + j * (p.slot_rows + 32), &full[stage], &tm_rows128, &tm_rows32,
-                                    &tm_scale128, &tm_scale32, r0, nr, j * p.slot_rows, use_scale);
-              sMis[stage * 4 + j] = static_cast<int>(r0 & 3);
+                                    &tm_scale128, &tm_scale32, cur.r0[j], cur.nr[j], j * p.slot_rows, use_scale);
+              // low 2 bits: scale misalignment; rest: rows of the slot (0 for unused slots)
+              sMis[stage * 4 + j] = (j < cur.cnt) ? (static_cast<int>(cur.r0[j] & 3) | (cur.nr[j] << 2)) : 0;
             }
-            for (int j = cnt; j < 4; ++j) sMis[stage * 4 + j] = 0;   // unused slots: rows are never read back
-            mbar_arrive_expect_tx(&full[stage], bytes);
           }
+          mbar_arrive_expect_tx(&full[stage], bytes);
+          cur = nxt;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -284,7 +391,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (one thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(kTileRows, N);
+      const uint32_t idesc = umma_idesc_f16(kTileRows, p.hi_only ? QP : N);
       const uint32_t b_addr = smem_u32(sB);
       uint32_t stage = 0, phase = 0, acc = 0, accphase = 0;
       for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -318,17 +425,18 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
       }
     }
   } else {
-    // ===================================================================== epilogue (4 warps = 128 TMEM lanes)
-    const int ew = warp - 2;                 // 0..3
+    // ===================================================================== epilogue (4 warps = 128 TMEM lanes per group)
+    const int grp = (warp - 2) >> 2;         // epilogue group (PACKED: groups alternate tiles)
+    const int ew = (warp - 2) & 3;           // warp within the group
     const int lg = warp & 3;                 // TMEM lane group this warp may access
     const int trow = lg * 32 + lane;         // tile row (= TMEM lane) owned by this thread
-    const int et = ew * 32 + lane;           // 0..127 epilogue thread id
+    const int et = ew * 32 + lane;           // 0..127 thread id within the group
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
-    uint32_t stage = 0, phase = 0, acc = 0, accphase = 0, par = 0;
     constexpr float kInvLo = 1.0f / kLoScale;
 
-    for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
-      if constexpr (!PACKED) {
+    if constexpr (!PACKED) {
+      uint32_t stage = 0, phase = 0, acc = 0, accphase = 0, par = 0;
+      for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
         long long row0;
         int nrows;
         const bool ok = resolve_page(p, item_page(p, u), row0, nrows);
@@ -343,13 +451,18 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           float scale = 1.0f;
           if (use_scale) {
             mbar_wait(&full[stage], phase);  // acquire the TMA-written scale rows
-            scale = sScale[stage * kScaleStride + trow + sMis[stage * 4]];
+            scale = sScale[stage * kScaleStride + trow + (sMis[stage * 4] & 3)];
           }
 #pragma unroll
           for (int c = 0; c < QP; c += 8) {
             uint32_t hi[8], lo[8];
             tmem_ld_x8(ta + c, hi);
-            tmem_ld_x8(ta + QP + c, lo);
+            if (!p.hi_only) {
+              tmem_ld_x8(ta + QP + c, lo);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) lo[j] = 0u;
+            }
             tmem_ld_wait();
             if (trow < valid) {
 #pragma unroll
@@ -392,54 +505,103 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           if (lane == 0) p.scores[u] = (ok && nrows > 0) ? sum : -INFINITY;
         }
         par ^= 1;
-      } else {
-        // ---------------- PACKED: several pages per tile
-        // 1. segment table of this tile (item, first tile row, end tile row) -> smem (double buffered)
-        int* seg = sSeg + par * 3 * kTileRows;
-        int nseg;
-        if (p.cand == nullptr) {
-          long long pg0, pg1;
-          if (p.fixed_rows > 0) {
-            pg0 = u * p.pages_per_tile;
-            pg1 = min(pg0 + p.pages_per_tile, p.n_pages);
-          } else {
-            pg0 = __ldg(p.tile_page0 + u);
-            pg1 = __ldg(p.tile_page0 + u + 1);
+      }
+    } else {
+      // ---------------- PACKED: several pages per tile; group `grp` handles tiles grp, grp+EPI_GROUPS, ...
+      int* seg = sSeg + grp * 3 * kTileRows;
+      float* sc = sSc + grp * QP * Cfg::SC_PITCH;
+      const uint32_t bar_id = 1 + grp;
+      long long seq = grp;
+      int seg_n = 0, seg_item = 0, seg_rb = 0, seg_re = 0;   // general path: this thread's entry of the tile's segment table
+      bool seg_ready = false;
+      for (long long u = blockIdx.x + static_cast<long long>(grp) * gridDim.x; u < n_units;
+           u += static_cast<long long>(EPI_GROUPS) * gridDim.x, seq += EPI_GROUPS) {
+        const uint32_t stage = static_cast<uint32_t>(seq % STAGES), phase = static_cast<uint32_t>((seq / STAGES) & 1);
+        const uint32_t acc = static_cast<uint32_t>(seq % ACC), accphase = static_cast<uint32_t>((seq / ACC) & 1);
+        const uint32_t ta = lane_addr + acc * N;
+        bool fast = false;
+        if constexpr (QP <= 32) fast = p.shfl_rows > 0;
+        if (fast) {
+          if constexpr (QP <= 32) {
+            // fast path: page j of the tile owns tile rows [j*SR, j*SR + nr)
+            const int SR = p.shfl_rows;
+            const int slot = trow / SR, rin = trow - slot * SR;
+            const long long item = u * (kTileRows / SR) + slot;
+            int nr = 0;
+            bool item_ok;
+            if (!p.slot_mode) {
+              item_ok = item < p.n_pages;
+              nr = item_ok ? SR : 0;
+            } else {
+              item_ok = item < p.n_items;
+            }
+            mbar_wait(&tfull[acc], accphase);
+            tc_fence_after_sync();
+            mbar_wait(&full[stage], phase);   // acquire the producer's per-slot metadata and the scale rows
+            if (p.slot_mode) nr = item_ok ? (sMis[stage * 4 + slot] >> 2) : 0;   // slot == 32-row slot here (SR == 32)
+            float scale = 1.0f;
+            if (use_scale) {
+              const int sslot = trow / p.slot_rows;
+              scale = sScale[stage * kScaleStride + sslot * (p.slot_rows + 32) + (trow - sslot * p.slot_rows) +
+                             (sMis[stage * 4 + sslot] & 3)];
+            }
+            float v[QP];
+            const bool live = rin < nr;
+#pragma unroll
+            for (int c = 0; c < QP; c += 8) {
+              uint32_t hi[8], lo[8];
+              tmem_ld_x8(ta + c, hi);
+              tmem_ld_x8(ta + QP + c, lo);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                v[c + j] = live ? fmaf(__uint_as_float(lo[j]), kInvLo, __uint_as_float(hi[j])) * scale : -INFINITY;
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&tempty[acc]);
+              mbar_arrive(&empty[stage]);
+            }
+            float sum;
+            switch (SR) {
+              case 32: sum = slot_maxsim<QP, 32>(v, lane, p.q_valid); break;
+              case 16: sum = slot_maxsim<QP, 16>(v, lane, p.q_valid); break;
+              case 8: sum = slot_maxsim<QP, 8>(v, lane, p.q_valid); break;
+              case 4: sum = slot_maxsim<QP, 4>(v, lane, p.q_valid); break;
+              case 2: sum = slot_maxsim<QP, 2>(v, lane, p.q_valid); break;
+              default: sum = slot_maxsim<QP, 1>(v, lane, p.q_valid); break;
+            }
+            if (rin == 0 && item_ok) p.scores[item] = nr > 0 ? sum : -INFINITY;
           }
-          nseg = static_cast<int>(pg1 - pg0);
-          if (et < nseg) {
-            long long rbase, r0;
-            int tmp, nr;
-            resolve_page(p, pg0, rbase, tmp);
-            resolve_page(p, pg0 + et, r0, nr);
-            seg[et] = static_cast<int>(pg0 + et);   // dense: item == page (n_items == n_pages < 2^31 per shard)
-            seg[kTileRows + et] = static_cast<int>(r0 - rbase);
-            seg[2 * kTileRows + et] = static_cast<int>(r0 - rbase) + nr;
-          }
-        } else {
-          const int per_tile = kTileRows / p.slot_rows;
-          const long long i0 = u * per_tile;
-          nseg = static_cast<int>(min(static_cast<long long>(per_tile), p.n_items - i0));
-          if (et < nseg) {
-            long long r0;
-            int nr;
-            resolve_page(p, item_page(p, i0 + et), r0, nr);
-            seg[et] = static_cast<int>(i0 + et);
-            seg[kTileRows + et] = et * p.slot_rows;
-            seg[2 * kTileRows + et] = et * p.slot_rows + nr;   // nr == 0 -> empty segment -> -inf
-          }
+          continue;
+        }
+        // general path
+        // 1. segment table of this tile (item, first tile row, end tile row) -> smem. The table of the group's NEXT
+        //    tile is loaded into registers now (tile -> page -> offsets is a chain of dependent global loads).
+        if (!seg_ready) {
+          packed_segment(p, u, et, seg_n, seg_item, seg_rb, seg_re);
+          seg_ready = true;
+        }
+        const int nseg = seg_n;
+        if (et < nseg) {
+          seg[et] = seg_item;
+          seg[kTileRows + et] = seg_rb;
+          seg[2 * kTileRows + et] = seg_re;
+        }
+        {
+          const long long un = u + static_cast<long long>(EPI_GROUPS) * gridDim.x;
+          if (un < n_units) packed_segment(p, un, et, seg_n, seg_item, seg_rb, seg_re);
         }
         // 2. scaled scores of my row -> transposed smem buffer sc[q][row]
-        float* sc = sSc + (Cfg::SC_BUFS == 2 ? par : 0) * QP * Cfg::SC_PITCH;
         mbar_wait(&tfull[acc], accphase);
         tc_fence_after_sync();
-        const uint32_t ta = lane_addr + acc * N;
         float scale = 1.0f;
         if (use_scale) {
           mbar_wait(&full[stage], phase);
           const int slot = trow / p.slot_rows;
           scale = sScale[stage * kScaleStride + slot * (p.slot_rows + 32) + (trow - slot * p.slot_rows) +
-                         sMis[stage * 4 + slot]];
+                         (sMis[stage * 4 + slot] & 3)];
         }
 #pragma unroll
         for (int c = 0; c < QP; c += 8) {
@@ -458,35 +620,42 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           mbar_arrive(&tempty[acc]);
           mbar_arrive(&empty[stage]);
         }
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        if (++acc == ACC) { acc = 0; accphase ^= 1; }
-        named_bar_sync(1, 128);
-        // 3. segmented max: a group of QW lanes handles one segment; lane -> q (+32 per extra group)
+        named_bar_sync(bar_id, 128);
+        // 3. segmented max: a group of QW lanes handles one segment; lane -> q (+32 per extra query group);
+        //    rows are read 4 at a time (16-byte aligned, conflict-free at pitch 132)
         constexpr int SEGS_PER_WARP = 32 / QW;
         const int sub = lane / QW, ql = lane % QW;
         for (int s0 = ew * SEGS_PER_WARP; s0 < nseg; s0 += 4 * SEGS_PER_WARP) {
-          const int s = s0 + sub;
+          const int sg = s0 + sub;
           float sum = 0.0f;
           int item = -1;
           bool nonempty = false;
-          if (s < nseg) {
-            item = seg[s];
-            const int rb = seg[kTileRows + s], re = seg[2 * kTileRows + s];
+          if (sg < nseg) {
+            item = seg[sg];
+            const int rb = seg[kTileRows + sg], re = seg[2 * kTileRows + sg];
             nonempty = re > rb;
 #pragma unroll
             for (int g = 0; g < QG; ++g) {
               const int q = g * 32 + ql;
-              float m = -INFINITY;
-              for (int r = rb; r < re; ++r) m = fmaxf(m, sc[q * Cfg::SC_PITCH + r]);
-              if (q < p.q_valid) sum += m;
+              const float* row = sc + q * Cfg::SC_PITCH;
+              float m0 = -INFINITY, m1 = -INFINITY;
+              for (int r4 = rb & ~3; r4 < re; r4 += 4) {
+                const float4 x = *reinterpret_cast<const float4*>(row + r4);
+                const float a0 = (r4 >= rb) ? x.x : -INFINITY;
+                const float a1 = (r4 + 1 >= rb && r4 + 1 < re) ? x.y : -INFINITY;
+                const float a2 = (r4 + 2 >= rb && r4 + 2 < re) ? x.z : -INFINITY;
+                const float a3 = (r4 + 3 < re) ? x.w : -INFINITY;
+                m0 = fmaxf(m0, fmaxf(a0, a1));
+                m1 = fmaxf(m1, fmaxf(a2, a3));
+              }
+              if (q < p.q_valid) sum += fmaxf(m0, m1);
             }
           }
 #pragma unroll
           for (int off = QW / 2; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-          if (s < nseg && ql == 0) p.scores[item] = nonempty ? sum : -INFINITY;
+          if (sg < nseg && ql == 0) p.scores[item] = nonempty ? sum : -INFINITY;
         }
-        if constexpr (Cfg::SC_BUFS == 1) named_bar_sync(1, 128);  // single score buffer: drain before reuse
-        par ^= 1;
+        named_bar_sync(bar_id, 128);   // the group's buffers are reused by its next tile
       }
     }
   }

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -90,6 +91,7 @@ struct Store {
   long long* offsets = nullptr;  // device [n_pages+1] (nullptr when fixed_rows > 0)
   std::vector<int64_t> h_offsets;
   int* tile_page0 = nullptr;     // packed dense variable-length: [n_tiles+1]
+  long long* tile_row0 = nullptr;  // first row of each tile [n_tiles+1]
   int64_t n_tiles = 0;
   int64_t n_pages = 0, total_rows = 0, fixed_rows = 0, max_rows = 0;
   bool packed = false;
@@ -153,6 +155,7 @@ static void free_store(Store& s) {
   if (s.inv) cudaFree(s.inv);
   if (s.offsets) cudaFree(s.offsets);
   if (s.tile_page0) cudaFree(s.tile_page0);
+  if (s.tile_row0) cudaFree(s.tile_row0);
   s = Store();
 }
 
@@ -258,6 +261,10 @@ static int finish_store(vrag_corpus* c, Store& s, const int64_t* page_offsets, i
     s.n_tiles = static_cast<int64_t>(t0.size()) - 1;
     CUDA_OK(cudaMalloc(&s.tile_page0, t0.size() * sizeof(int)));
     CUDA_OK(cudaMemcpyAsync(s.tile_page0, t0.data(), t0.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    std::vector<long long> tr(t0.size());
+    for (size_t i = 0; i < t0.size(); ++i) tr[i] = page_offsets[t0[i]];
+    CUDA_OK(cudaMalloc(&s.tile_row0, tr.size() * sizeof(long long)));
+    CUDA_OK(cudaMemcpyAsync(s.tile_row0, tr.data(), tr.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
   }
   if (s.total_rows > 0) {
@@ -438,7 +445,7 @@ static int launch_scan_t(vrag_corpus* c, const Store& s, const ScanParams& p, lo
     attr_done[c->device & 7] = true;
   }
   const unsigned grid = static_cast<unsigned>(std::min<long long>(c->num_sms, n_units));
-  kern<<<grid, kScanThreads, smem, st>>>(s.tm128, s.tm32, s.ts128, s.ts32, p);
+  kern<<<grid, ScanCfg<QP>::threads(PACKED), smem, st>>>(s.tm128, s.tm32, s.ts128, s.ts32, p);
   c->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -474,17 +481,28 @@ static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int
   p.q_valid = q_eff;
   p.use_scale = normalize ? 1 : 0;
   p.slot_rows = kTileRows;
+  {  // experiment knob: VRAG_QUERY_SPLIT=0 drops the lo half of the query (fp16-only query, LARGE pages only)
+    const char* e = getenv("VRAG_QUERY_SPLIT");
+    p.hi_only = (e && e[0] == '0' && QP >= 16 && !s.packed) ? 1 : 0;
+  }
   long long n_units = n_items;
   if (s.packed) {
+    const bool small_rows = s.max_rows <= 32;
     if (d_cand) {
-      p.slot_rows = s.max_rows <= 32 ? 32 : (s.max_rows <= 64 ? 64 : 128);
+      // slot mode (candidate lists): one slot per page -> segmented-butterfly epilogue when slots are 32 rows
+      p.slot_mode = 1;
+      p.slot_rows = small_rows ? 32 : (s.max_rows <= 64 ? 64 : 128);
       const int per_tile = kTileRows / p.slot_rows;
       p.n_tiles = (n_items + per_tile - 1) / per_tile;
+      if (p.slot_rows == 32 && QP <= 32) p.shfl_rows = 32;
     } else if (s.fixed_rows > 0) {
       p.pages_per_tile = static_cast<int>(kTileRows / s.fixed_rows);
       p.n_tiles = (s.n_pages + p.pages_per_tile - 1) / p.pages_per_tile;
+      const bool pow2 = (s.fixed_rows & (s.fixed_rows - 1)) == 0;
+      if (pow2 && s.fixed_rows <= 32 && QP <= 32) p.shfl_rows = static_cast<int>(s.fixed_rows);
     } else {
       p.tile_page0 = s.tile_page0;
+      p.tile_row0 = s.tile_row0;
       p.n_tiles = s.n_tiles;
     }
     n_units = p.n_tiles;
