@@ -50,6 +50,11 @@ struct PoolSpecDev {
   int out_f32;
   const long long* out_off;   // [n_pages+1] device, or nullptr when out_fixed > 0
   long long out_fixed;
+  // TILE_MEAN only: optional fused colsmol_experimental_pooling output (same tile means for the first tiles,
+  // then the raw rows of the last tile), so the tokens are read once for both stores
+  void* out2;
+  const long long* out2_off;
+  long long out2_fixed;
 };
 
 struct PoolInput {
@@ -87,16 +92,44 @@ __device__ __forceinline__ float4 f4_div(float4 a, float d) {
   return make_float4(__fdiv_rn(a.x, d), __fdiv_rn(a.y, d), __fdiv_rn(a.z, d), __fdiv_rn(a.w, d));
 }
 
-// mean of global rows [lo, hi) of `base`, accumulated row after row (8 loads in flight)
+// mean of global rows [lo, hi) of `base`, accumulated row after row. 16 row loads are kept in flight per warp
+// (4 KB): with ~40 resident warps per SM that is what it takes to cover HBM latency at full bandwidth.
+struct PoolRaw {
+  uint4 w;   // fp32: one float4; fp16: .x/.y hold 4 halves
+};
+__device__ __forceinline__ PoolRaw pool_load_raw(const void* base, int f32, long long row, int lane) {
+  PoolRaw r;
+  if (f32) {
+    r.w = __ldg(reinterpret_cast<const uint4*>(static_cast<const float*>(base) + row * 128) + lane);
+  } else {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(base) + row * 128) + lane);
+    r.w = make_uint4(v.x, v.y, 0u, 0u);
+  }
+  return r;
+}
+__device__ __forceinline__ float4 pool_raw_to_f4(const PoolRaw& r, int f32) {
+  if (f32) return make_float4(__uint_as_float(r.w.x), __uint_as_float(r.w.y), __uint_as_float(r.w.z), __uint_as_float(r.w.w));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.w.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.w.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
 __device__ __forceinline__ float4 range_mean_global(const void* base, int f32, long long lo, long long hi, int lane) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   long long r = lo;
-  for (; r + 8 <= hi; r += 8) {
-    float4 v[8];
+  for (; r + 16 <= hi; r += 16) {
+    PoolRaw v[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = pool_load4(base, f32, r + j, lane);
+    for (int j = 0; j < 16; ++j) v[j] = pool_load_raw(base, f32, r + j, lane);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc = f4_add(acc, v[j]);
+    for (int j = 0; j < 16; ++j) acc = f4_add(acc, pool_raw_to_f4(v[j], f32));
+  }
+  if (r + 8 <= hi) {
+    PoolRaw v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = pool_load_raw(base, f32, r + j, lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = f4_add(acc, pool_raw_to_f4(v[j], f32));
+    r += 8;
   }
   for (; r < hi; ++r) acc = f4_add(acc, pool_load4(base, f32, r, lane));
   return f4_div(acc, static_cast<float>(hi - lo));
@@ -225,6 +258,22 @@ __global__ void __launch_bounds__(256) pool_tokens_kernel(const PoolInput in, co
         v = range_mean_global(in.in, in.in_f32, r0 + lo, r0 + hi, lane);
       }
       pool_store4(s.out, s.out_f32, o0 + o, lane, v, s.via_f16);
+      if (s.kind == kPoolTileMean && s.out2 && o < n_out - 1) {
+        long long e0;
+        int e_n;
+        pool_page_rows(s.out2_off, s.out2_fixed, page, e0, e_n);
+        pool_store4(s.out2, s.out_f32, e0 + o, lane, v, 0);
+      }
+    }
+    if (s.kind == kPoolTileMean && s.out2 && n_out > 0) {
+      // raw rows of the last tile (pooling.py:221-232); n_out == ceil(t / ppt) == num_tiles here
+      long long e0;
+      int e_n;
+      pool_page_rows(s.out2_off, s.out2_fixed, page, e0, e_n);
+      const int head = n_out - 1;
+      for (int o = head + warp; o < e_n; o += kWarps)
+        pool_store4(s.out2, s.out_f32, e0 + o, lane,
+                    pool_load4(in.in, in.in_f32, r0 + static_cast<long long>(head) * s.ppt + (o - head), lane), 0);
     }
   }
 }

@@ -860,9 +860,24 @@ static int launch_pool(const PoolInput& in, int n, const vrag_pool_spec_t* specs
   }
   // LEGACY_CONV / GLOBAL_MEAN ride along with the row-level pass when the input pages are small enough
   const bool small_pages = max_in_rows <= 256;
+  // TILE_MEAN + COLSMOL_EXPERIMENTAL (default num_tiles, same patches_per_tile) share one pass over the tokens
+  int fused_exp = -1;
+  for (int i = 0; i < n && fused_exp < 0; ++i) {
+    if (specs[i].kind != VRAG_POOL_TILE_MEAN) continue;
+    for (int j = 0; j < n; ++j) {
+      if (specs[j].kind == VRAG_POOL_COLSMOL_EXPERIMENTAL && specs[j].num_tiles <= 0 &&
+          specs[j].patches_per_tile == specs[i].patches_per_tile && dev[j].out_f32 == dev[i].out_f32) {
+        dev[i].out2 = dev[j].out;
+        dev[i].out2_off = dev[j].out_off;
+        dev[i].out2_fixed = dev[j].out_fixed;
+        fused_exp = j;
+        break;
+      }
+    }
+  }
   for (int i = 0; i < n; ++i) {
     const int k = specs[i].kind;
-    if (pool_is_row_level(k)) continue;
+    if (pool_is_row_level(k) || i == fused_exp) continue;
     if (ra.n_specs > 0 && small_pages && (k == VRAG_POOL_LEGACY_CONV || k == VRAG_POOL_GLOBAL_MEAN) &&
         ra.n_specs < kPoolMaxSpecs) {
       ra.specs[ra.n_specs++] = dev[i];
@@ -876,7 +891,9 @@ static int launch_pool(const PoolInput& in, int n, const vrag_pool_spec_t* specs
   if (ra.n_specs > 0) {
     if (max_in_rows > 256) return fail("SMOOTH / TILE_4N need pages of at most 256 rows (got %d)", max_in_rows);
     const size_t smem = static_cast<size_t>(std::max(max_in_rows, 1)) * 512;
-    const unsigned grid = static_cast<unsigned>(std::min<long long>(in.n_pages, static_cast<long long>(num_sms) * 8));
+    // small pages: latency-bound per block (load -> sync -> compute), so keep every SM full of blocks
+    const int per_sm = std::max(1, std::min(16, static_cast<int>((200 * 1024) / std::max<size_t>(smem, 1))));
+    const unsigned grid = static_cast<unsigned>(std::min<long long>(in.n_pages, static_cast<long long>(num_sms) * per_sm));
     pool_rows_kernel<<<grid, 128, smem, st>>>(ra);
     if (launches) ++*launches;
   }
