@@ -159,6 +159,27 @@ def test_topk_multilevel_large(corpus):
         assert ids.tolist() == order.tolist() and np.array_equal(s, sc[order])
 
 
+def test_topk_radix_select_with_massive_ties(corpus):
+    """n > 4096 goes through the radix select; duplicated pages give hundreds of exact ties at the threshold,
+    which must be resolved by lower page id (Python's stable sort)."""
+    base = rows16(950, 50, scale=False)
+    rng = np.random.default_rng(1)
+    pick = rng.integers(0, 50, size=20000)
+    corpus.add_store("dup", base[pick], fixed_rows=1)
+    q = CS.query_rows(951, 3)
+    sc = corpus.score("dup", q)
+    assert len(np.unique(sc)) <= 50
+    for k in (1, 10, 256, 1000, 4096):
+        s, ids = corpus.search("dup", q, k)
+        order = np.lexsort((np.arange(len(sc)), -sc))[:k]
+        assert ids.tolist() == order.tolist()
+        assert np.array_equal(s, sc[order])
+    allsame = np.repeat(base[:1], 9000, axis=0)
+    corpus.add_store("same", allsame, fixed_rows=1)
+    s, ids = corpus.search("same", q, 300)
+    assert ids.tolist() == list(range(300))
+
+
 # ------------------------------------------------------------------ edge cases
 def test_edge_cases(corpus):
     from visual_rag_b200._native import VragError

@@ -172,22 +172,31 @@ struct TopkArgs {
   const long long* ids;       // item index -> id (nullptr: id = id_base + index)
   long long id_base;
   long long n_total;          // number of real items (for out_count / padding)
+  // batch (blockIdx.y = query): element strides between consecutive queries (0 when unbatched)
+  long long in_stride;        // scores / keys_in
+  long long keys_out_stride;
+  long long out_stride;       // out_scores / out_ids / out_pos
+  long long ids_stride;
+  const int* n_dyn;           // optional per-query element count (device); overrides n / n_total
 };
 
 template <int CHUNK, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) topk_kernel(const TopkArgs a) {
   extern __shared__ unsigned long long skeys[];
   constexpr int PER = CHUNK / 2 / THREADS;   // compare-exchanges per thread per full-width stage
+  const long long b = blockIdx.y;
+  const long long n_in = a.n_dyn ? a.n_dyn[b] : a.n;
+  const long long n_real = a.n_dyn ? a.n_dyn[b] : a.n_total;
   const long long base = static_cast<long long>(blockIdx.x) * CHUNK;
   for (int j = threadIdx.x; j < CHUNK; j += THREADS) {
     const long long i = base + j;
     unsigned long long key = 0ull;
-    if (i < a.n) {
+    if (i < n_in) {
       if (a.scores) {
-        key = (static_cast<unsigned long long>(score_to_ord(a.scores[i])) << 32) |
+        key = (static_cast<unsigned long long>(score_to_ord(a.scores[b * a.in_stride + i])) << 32) |
               static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<uint32_t>(i));
       } else {
-        key = a.keys_in[i];
+        key = a.keys_in[b * a.in_stride + i];
       }
     }
     skeys[j] = key;
@@ -250,23 +259,189 @@ __global__ void __launch_bounds__(THREADS, 1) topk_kernel(const TopkArgs a) {
   }
   __syncthreads();
   if (a.keys_out) {
-    for (int j = threadIdx.x; j < a.k; j += THREADS) a.keys_out[static_cast<long long>(blockIdx.x) * a.k + j] = skeys[j];
+    for (int j = threadIdx.x; j < a.k; j += THREADS)
+      a.keys_out[b * a.keys_out_stride + static_cast<long long>(blockIdx.x) * a.k + j] = skeys[j];
   } else {
-    const long long nvalid = a.n_total < a.k ? a.n_total : a.k;
+    const long long nvalid = n_real < a.k ? n_real : a.k;
+    const long long ob = b * a.out_stride;
     for (int j = threadIdx.x; j < a.k; j += THREADS) {
       if (j < nvalid) {
         const unsigned long long key = skeys[j];
         const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
-        a.out_scores[j] = ord_to_score(static_cast<uint32_t>(key >> 32));
-        a.out_ids[j] = a.ids ? a.ids[idx] : (a.id_base + idx);
-        if (a.out_pos) a.out_pos[j] = static_cast<int>(idx);
+        a.out_scores[ob + j] = ord_to_score(static_cast<uint32_t>(key >> 32));
+        a.out_ids[ob + j] = a.ids ? a.ids[b * a.ids_stride + idx] : (a.id_base + idx);
+        if (a.out_pos) a.out_pos[ob + j] = static_cast<int>(idx);
       } else {
-        a.out_scores[j] = -INFINITY;
-        a.out_ids[j] = -1;
-        if (a.out_pos) a.out_pos[j] = -1;
+        a.out_scores[ob + j] = -INFINITY;
+        a.out_ids[ob + j] = -1;
+        if (a.out_pos) a.out_pos[ob + j] = -1;
       }
     }
-    if (a.out_count && threadIdx.x == 0) *a.out_count = static_cast<int>(nvalid);
+    if (a.out_count && threadIdx.x == 0) a.out_count[b] = static_cast<int>(nvalid);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Radix select for large inputs (n > 4096): find the k-th largest 32-bit score key T with three histogram passes
+// (11 + 11 + 10 bits), gather the keys > T and the needed keys == T (lowest indices first), then sort only those k
+// keys with topk_kernel. Cost is ~3 reads of the score array regardless of k. blockIdx.y = query of a batch.
+constexpr int kSelBins = 2048;
+constexpr int kSelItemsPerBlock = 4096;
+struct SelState {
+  unsigned int prefix;     // selected high bits of T so far
+  int k_rem;               // how many of the k still have to come from the current prefix bucket
+  int count_gt;            // items known to be > T
+  int eq_count;            // items == T (after the last pass)
+  int counter;             // compaction cursor
+  int pad[3];
+};
+struct SelArgs {
+  const float* scores;     // [batch][n]
+  long long n;
+  int k;
+  SelState* state;         // [batch]
+  unsigned int* hist;      // [batch][3][kSelBins]
+  unsigned long long* keys_out;   // [batch][k]
+};
+
+__device__ __forceinline__ int sel_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
+__device__ __forceinline__ unsigned int sel_mask_above(int pass) {   // bits already fixed before this pass
+  return pass == 0 ? 0u : (pass == 1 ? 0xFFE00000u : 0xFFFFFC00u);
+}
+
+__global__ void __launch_bounds__(256) sel_hist_kernel(const SelArgs a, int pass) {
+  __shared__ unsigned int h[kSelBins];
+  const long long b = blockIdx.y;
+  for (int i = threadIdx.x; i < kSelBins; i += 256) h[i] = 0;
+  __syncthreads();
+  const unsigned int prefix = a.state[b].prefix, above = sel_mask_above(pass);
+  const int shift = sel_shift(pass);
+  const unsigned int bin_mask = pass == 2 ? 1023u : 2047u;
+  const float* sc = a.scores + b * a.n;
+  const long long base = static_cast<long long>(blockIdx.x) * kSelItemsPerBlock;
+  const int lane = threadIdx.x & 31;
+#pragma unroll 4
+  for (int j = 0; j < kSelItemsPerBlock / 256; ++j) {
+    const long long i = base + j * 256 + threadIdx.x;
+    int bin = -1;
+    if (i < a.n) {
+      const unsigned int key = score_to_ord(sc[i]);
+      if ((key & above) == (prefix & above)) bin = static_cast<int>((key >> shift) & bin_mask);
+    }
+    // warp-aggregated shared atomics: scores cluster in a few bins
+    const unsigned int peers = __match_any_sync(0xffffffffu, bin);
+    if (bin >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(&h[bin], __popc(peers));
+  }
+  __syncthreads();
+  unsigned int* gh = a.hist + (b * 3 + pass) * kSelBins;
+  for (int i = threadIdx.x; i < kSelBins; i += 256)
+    if (h[i]) atomicAdd(&gh[i], h[i]);
+}
+
+// one block per query: pick the bucket that contains the k_rem-th largest key of the current prefix bucket
+__global__ void __launch_bounds__(256) sel_scan_kernel(const SelArgs a, int pass) {
+  __shared__ unsigned int part[256];
+  const long long b = blockIdx.x;
+  const unsigned int* gh = a.hist + (b * 3 + pass) * kSelBins;
+  SelState* st = a.state + b;
+  const int k_rem = st->k_rem;
+  // thread t owns bins [8t, 8t+8); suffix sums from the top
+  unsigned int mine[8], s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { mine[j] = gh[threadIdx.x * 8 + j]; s += mine[j]; }
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 1; off < 256; off <<= 1) {   // inclusive suffix scan
+    const unsigned int add = (threadIdx.x + off < 256) ? part[threadIdx.x + off] : 0u;
+    __syncthreads();
+    part[threadIdx.x] += add;
+    __syncthreads();
+  }
+  const unsigned int incl = part[threadIdx.x];            // items in bins >= 8t
+  const unsigned int excl = incl - s;                     // items in bins >= 8t+8
+  if (excl < static_cast<unsigned int>(k_rem) && incl >= static_cast<unsigned int>(k_rem)) {
+    unsigned int above = excl;
+    for (int j = 7; j >= 0; --j) {
+      if (above + mine[j] >= static_cast<unsigned int>(k_rem)) {
+        st->prefix |= static_cast<unsigned int>(threadIdx.x * 8 + j) << sel_shift(pass);
+        st->k_rem = k_rem - static_cast<int>(above);
+        st->count_gt += static_cast<int>(above);
+        st->eq_count = static_cast<int>(mine[j]);
+        break;
+      }
+      above += mine[j];
+    }
+  }
+}
+
+// gather keys > T (any order) and, when every key == T is needed, those too
+__global__ void __launch_bounds__(256) sel_compact_kernel(const SelArgs a) {
+  const long long b = blockIdx.y;
+  SelState* st = a.state + b;
+  const unsigned int T = st->prefix;
+  const bool take_eq = st->eq_count == st->k_rem;
+  const float* sc = a.scores + b * a.n;
+  unsigned long long* out = a.keys_out + b * a.k;
+  const long long base = static_cast<long long>(blockIdx.x) * kSelItemsPerBlock;
+  for (int j = 0; j < kSelItemsPerBlock / 256; ++j) {
+    const long long i = base + j * 256 + threadIdx.x;
+    if (i < a.n) {
+      const unsigned int key = score_to_ord(sc[i]);
+      if (key > T || (take_eq && key == T)) {
+        const int pos = atomicAdd(&st->counter, 1);
+        out[pos] = (static_cast<unsigned long long>(key) << 32) |
+                   static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<uint32_t>(i));
+      }
+    }
+  }
+}
+
+// ties at T beyond what is needed: take the k_rem lowest indices (index order scan, one block per query)
+__global__ void __launch_bounds__(1024) sel_ties_kernel(const SelArgs a) {
+  const long long b = blockIdx.x;
+  SelState* st = a.state + b;
+  if (st->eq_count == st->k_rem) return;
+  __shared__ int wsum[32];
+  __shared__ int running;
+  const unsigned int T = st->prefix;
+  const int need = st->k_rem, start = st->count_gt;
+  const float* sc = a.scores + b * a.n;
+  unsigned long long* out = a.keys_out + b * a.k;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long base = 0; base < a.n; base += 1024) {
+    const long long i = base + threadIdx.x;
+    const bool hit = i < a.n && score_to_ord(sc[i]) == T;
+    const unsigned int bal = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    int before = running;
+    for (int w = 0; w < warp; ++w) before += wsum[w];
+    const int pos = before + __popc(bal & ((1u << lane) - 1u));
+    if (hit && pos < need)
+      out[start + pos] = (static_cast<unsigned long long>(T) << 32) |
+                         static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<uint32_t>(i));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += wsum[w];
+      running += tot;
+    }
+    __syncthreads();
+    if (running >= need) break;
+  }
+}
+
+__global__ void sel_init_kernel(SelState* st, int k, int batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < batch) {
+    st[b].prefix = 0u;
+    st[b].k_rem = k;
+    st[b].count_gt = 0;
+    st[b].eq_count = 0;
+    st[b].counter = 0;
   }
 }
 

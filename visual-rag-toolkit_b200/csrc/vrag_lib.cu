@@ -129,6 +129,8 @@ struct vrag_corpus {
   DevBuf<float> d_query, d_scores, d_out_scores;
   DevBuf<uint8_t> d_qimg;
   DevBuf<unsigned long long> d_keys_a, d_keys_b;
+  DevBuf<uint8_t> d_sel_state;
+  DevBuf<unsigned int> d_sel_hist;
   DevBuf<long long> d_cand, d_out_ids;
   DevBuf<int> d_counts;
   float* h_query = nullptr;       // pinned staging
@@ -199,6 +201,8 @@ extern "C" int vrag_corpus_destroy(vrag_corpus_t* c) {
   c->d_qimg.release();
   c->d_keys_a.release();
   c->d_keys_b.release();
+  c->d_sel_state.release();
+  c->d_sel_hist.release();
   c->d_cand.release();
   c->d_out_ids.release();
   c->d_counts.release();
@@ -529,9 +533,10 @@ static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int
   return 0;
 }
 
-// Exact top-k of d_scores[n] -> (out_scores[k], out_ids[k]) sorted descending, ties -> lower item index.
+// Exact top-k of d_scores[batch][n] -> (out_scores[batch][k], out_ids[batch][k]) sorted descending, ties -> lower
+// item index. n <= 4096: one shared-memory sort; larger: radix select of the k best keys, then sort those.
 template <int CHUNK, int THREADS>
-static int launch_topk_level(vrag_corpus* c, const TopkArgs& a, long long n_chunks, cudaStream_t st) {
+static int launch_topk_sort(vrag_corpus* c, const TopkArgs& a, int batch, cudaStream_t st) {
   auto kern = topk_kernel<CHUNK, THREADS>;
   const size_t smem = CHUNK * sizeof(unsigned long long);
   static bool attr_done[8] = {false};
@@ -539,16 +544,18 @@ static int launch_topk_level(vrag_corpus* c, const TopkArgs& a, long long n_chun
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_done[c->device & 7] = true;
   }
-  kern<<<static_cast<unsigned>(n_chunks), THREADS, smem, st>>>(a);
+  kern<<<dim3(1, static_cast<unsigned>(batch)), THREADS, smem, st>>>(a);
   c->launches++;
   return 0;
 }
 
 static int launch_topk(vrag_corpus* c, const float* d_scores, const long long* d_ids, int64_t id_base, int64_t n,
-                       int k, float* out_scores, long long* out_ids, int* out_pos, int* out_count, cudaStream_t st) {
+                       int k, float* out_scores, long long* out_ids, int* out_pos, int* out_count, cudaStream_t st,
+                       int batch = 1, long long ids_stride = 0) {
   if (k < 1) return fail("k must be >= 1");
   if (k > kTopkMaxK) return fail("k=%d exceeds the supported maximum %d", k, kTopkMaxK);
   if (n >= (1ll << 32) - 1) return fail("too many items for top-k");
+  if (batch < 1) return fail("batch must be >= 1");
   int k2 = 1;
   while (k2 < k) k2 <<= 1;
   TopkArgs a;
@@ -561,36 +568,46 @@ static int launch_topk(vrag_corpus* c, const float* d_scores, const long long* d
   a.ids = d_ids;
   a.id_base = id_base;
   a.n_total = n;
-  a.scores = d_scores;
-  long long m = n;
-  // chunk policy: k <= 1024 -> 2048-key chunks (many blocks, cheap sorts), last level 1024 or 2048;
-  //               larger k  -> 8192-key chunks.
-  const bool big_k = k > 1024;
-  {
-    const long long ch0 = big_k ? 8192 : 2048;
-    const long long nch0 = std::max<long long>(1, (m + ch0 - 1) / ch0);
-    if (nch0 > 1) {
-      TRY(c->d_keys_a.ensure(static_cast<size_t>(nch0) * k));
-      TRY(c->d_keys_b.ensure(static_cast<size_t>((nch0 * k + ch0 - 1) / ch0) * k + k));
+  a.out_stride = k;
+  a.ids_stride = ids_stride;
+  long long m = n;   // elements the final sort sees
+  if (n > 4096) {
+    // ---- radix select: leaves exactly k keys per query in d_keys_a
+    TRY(c->d_sel_state.ensure(static_cast<size_t>(batch) * sizeof(SelState)));
+    TRY(c->d_sel_hist.ensure(static_cast<size_t>(batch) * 3 * kSelBins));
+    TRY(c->d_keys_a.ensure(static_cast<size_t>(batch) * k));
+    SelArgs sa;
+    sa.scores = d_scores;
+    sa.n = n;
+    sa.k = k;
+    sa.state = reinterpret_cast<SelState*>(c->d_sel_state.p);
+    sa.hist = c->d_sel_hist.p;
+    sa.keys_out = c->d_keys_a.p;
+    CUDA_OK(cudaMemsetAsync(sa.hist, 0, static_cast<size_t>(batch) * 3 * kSelBins * sizeof(unsigned int), st));
+    sel_init_kernel<<<(batch + 127) / 128, 128, 0, st>>>(sa.state, k, batch);
+    const dim3 grid(static_cast<unsigned>((n + kSelItemsPerBlock - 1) / kSelItemsPerBlock), static_cast<unsigned>(batch));
+    for (int pass = 0; pass < 3; ++pass) {
+      sel_hist_kernel<<<grid, 256, 0, st>>>(sa, pass);
+      sel_scan_kernel<<<batch, 256, 0, st>>>(sa, pass);
     }
-  }
-  unsigned long long* bufs[2] = {c->d_keys_a.p, c->d_keys_b.p};
-  int which = 0;
-  while (true) {
-    const int chunk = big_k ? 8192 : (m <= 1024 ? 1024 : 2048);
-    const long long nch = std::max<long long>(1, (m + chunk - 1) / chunk);
-    a.n = m;
-    a.k2 = std::min(k2, chunk);
-    a.keys_out = (nch > 1) ? bufs[which] : nullptr;
-    if (chunk == 8192) TRY((launch_topk_level<8192, 1024>(c, a, nch, st)));
-    else if (chunk == 2048) TRY((launch_topk_level<2048, 1024>(c, a, nch, st)));
-    else TRY((launch_topk_level<1024, 512>(c, a, nch, st)));
-    if (nch == 1) break;
+    sel_compact_kernel<<<grid, 256, 0, st>>>(sa);
+    sel_ties_kernel<<<batch, 1024, 0, st>>>(sa);
+    c->launches += 9;
     a.scores = nullptr;
-    a.keys_in = bufs[which];
-    m = nch * k;
-    which ^= 1;
+    a.keys_in = c->d_keys_a.p;
+    a.in_stride = k;
+    m = k;
+  } else {
+    a.scores = d_scores;
+    a.in_stride = n;
   }
+  a.n = m;
+  const int chunk = m <= 1024 ? 1024 : (m <= 2048 ? 2048 : 8192);
+  a.k2 = std::min(k2, chunk);
+  a.keys_out = nullptr;
+  if (chunk == 8192) TRY((launch_topk_sort<8192, 1024>(c, a, batch, st)));
+  else if (chunk == 2048) TRY((launch_topk_sort<2048, 1024>(c, a, batch, st)));
+  else TRY((launch_topk_sort<1024, 512>(c, a, batch, st)));
   CUDA_OK(cudaGetLastError());
   return 0;
 }
