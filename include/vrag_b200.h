@@ -102,6 +102,19 @@ int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char* const* na
                            const int64_t* cand_ids, int64_t n_cand, float* out_scores, int64_t* out_ids,
                            int* out_counts);
 
+/* ------------------------------------------------------------------ scoring: batched queries
+ * n_queries independent multi-stage searches in one call and one host synchronisation (the evaluation loop of
+ * benchmarks/vidore_beir_qdrant/run_qdrant_beir.py:378-402 issues them one by one; BASELINE configs[2] batches 256).
+ * Stages, names, flags and ks as in vrag_search_multistage. query_rows: all query matrices concatenated, [rows,128] fp32.
+ * per_stage_queries == 0: q_offsets[n_queries+1], query b = rows [q_offsets[b], q_offsets[b+1]) for every stage.
+ * per_stage_queries != 0: q_offsets[n_queries*n_stages+1], (query b, stage s) = rows [q_offsets[b*n_stages+s], q_offsets[b*n_stages+s+1]).
+ * Outputs are stage-major: stage s occupies [n_queries*sum(ks[:s]), +n_queries*ks[s]) of out_scores/out_ids as
+ * [n_queries][ks[s]]; out_counts[s*n_queries + b] entries of row b are valid (the rest are (-inf, -1)).
+ * Stage >= 1 of ALL queries runs as one kernel launch (each query on its own candidate list).        */
+int vrag_search_multistage_batch(vrag_corpus_t* c, int n_stages, const char* const* names, const uint32_t* flags,
+                                 const int* ks, int n_queries, const float* query_rows, const int* q_offsets,
+                                 int per_stage_queries, float* out_scores, int64_t* out_ids, int* out_counts);
+
 /* ------------------------------------------------------------------ device-pointer variants
  * Same kernels, caller-provided device buffers and stream (cudaStream_t passed as void*): used by the
  * sharded multi-GPU path, which all-gathers per-shard top-k lists with NCCL between stages.        */

@@ -1,0 +1,52 @@
+"""Profiling driver (run under ncu on the GPU box): launches ONE kernel family repeatedly so that
+`ncu -k regex:<name> -s <skip> -c 1` captures a steady-state launch.
+  python scripts/prof_driver.py large|packed|global|rerank|pool_tokens|pool_rows [n_pages]
+"""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "visual-rag-toolkit_b200"))
+from visual_rag_b200.corpus import GpuCorpus
+from visual_rag_b200.embedding import pooling as GP
+
+what = sys.argv[1]
+rng = np.random.default_rng(0)
+q20 = rng.standard_normal((20, 128)).astype(np.float32)
+c = GpuCorpus(0)
+reps = 4
+if what == "large":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 100_000
+    c.add_synthetic_store("initial", n, fixed_rows=1030, seed=1)
+    for _ in range(reps):
+        c.search("initial", q20, 10)
+    print("large", n, c.last_timing_ms())
+elif what == "packed":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+    c.add_synthetic_store("mean_pooling", n, fixed_rows=32, seed=2)
+    for _ in range(reps):
+        c.search("mean_pooling", q20, 256)
+    print("packed", n, c.last_timing_ms())
+elif what == "global":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 4_000_000
+    c.add_synthetic_store("global_pooling", n, fixed_rows=1, seed=3)
+    for _ in range(reps):
+        c.search("global_pooling", q20, 1000, pool_query=True)
+    print("global", n, c.last_timing_ms())
+elif what == "rerank":
+    c.add_synthetic_store("initial", 100_000, fixed_rows=1030, seed=1)
+    cand = rng.permutation(100_000)[:256]
+    for _ in range(reps):
+        c.search("initial", q20, 10, candidate_ids=cand)
+    print("rerank", c.last_timing_ms())
+elif what == "pool_tokens":
+    c.add_synthetic_store("vis", 200_000, fixed_rows=1024, seed=6)
+    for _ in range(reps):
+        ms = c.pool_store("vis", [GP.spec_adaptive_rows(32, 32, 32)], ["mean_pooling"])
+    print("pool_tokens", ms)
+elif what == "pool_rows":
+    c.add_synthetic_store("mean_pooling", 1_000_000, fixed_rows=32, seed=6)
+    for _ in range(reps):
+        ms = c.pool_store("mean_pooling", [GP.spec_legacy_conv(3), GP.spec_smooth(3, "gaussian"), GP.spec_smooth(3, "triangular"),
+                                           GP.spec_global_mean(True)], ["e1", "e2", "e3", "g"])
+    print("pool_rows", ms)
+c.close()

@@ -353,3 +353,79 @@ def test_sharded_searcher_single_rank_matches_corpus_api(corpus):
     sa, ia = s.search("initial", q, 7)
     sb, ib = corpus.search("initial", q, 7)
     assert ia.tolist() == ib.tolist() and np.array_equal(sa, sb)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# batched queries (BASELINE configs[2]): one native call, stage >= 1 of all queries in one launch
+def _ragged_store(rng, n_pages, lo, hi):
+    lens = rng.integers(lo, hi + 1, size=n_pages)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    rows = rng.standard_normal((int(off[-1]), 128)).astype(np.float16)
+    return rows, off, [rows[off[i]:off[i + 1]].astype(np.float32) for i in range(n_pages)]
+
+
+def _same_ranking(ids, scores, want, rtol=RTOL, atol=ATOL):
+    """ids identical to the oracle's, except swaps among oracle scores closer than the score tolerance."""
+    want_ids = [i for i, _ in want]
+    want_sc = np.asarray([x for _, x in want], np.float64)
+    np.testing.assert_allclose(np.asarray(scores, np.float64), want_sc, rtol=rtol, atol=atol)
+    got_ids = list(ids)
+    if got_ids == want_ids:
+        return
+    by_id = dict(want)
+    for j, (g, w) in enumerate(zip(got_ids, want_ids)):
+        if g != w:
+            assert g in by_id, f"position {j}: id {g} is not in the oracle list"
+            assert abs(by_id[g] - by_id[w]) <= 2 * (atol + rtol * abs(by_id[w])), f"position {j}: {g} vs {w} is not a near-tie"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_queries", [1, 7, 40])
+def test_batched_three_stage_matches_oracle_and_single_query_path(corpus, n_queries):
+    rng = np.random.default_rng(100 + n_queries)
+    n = 700
+    init_rows, init_off, init_docs = _ragged_store(rng, n, 150, 400)
+    exp_rows, exp_off, exp_docs = _ragged_store(rng, n, 16, 32)
+    glob = rng.standard_normal((n, 128)).astype(np.float16)
+    glob_docs = [glob[i:i + 1].astype(np.float32) for i in range(n)]
+    corpus.add_store("b_initial", init_rows, page_offsets=init_off)
+    corpus.add_store("b_exp", exp_rows, page_offsets=exp_off)
+    corpus.add_store("b_glob", glob, fixed_rows=1)
+    queries = [rng.standard_normal((int(rng.integers(10, 31)), 128)).astype(np.float32) for _ in range(n_queries)]
+    stages = [("b_glob", True, 200), ("b_exp", False, 60), ("b_initial", False, 10)]
+    got = corpus.search_multistage_batch(stages, queries)
+    assert len(got) == n_queries
+    for q, res in zip(queries, got):
+        want = MO.multistage(q, [(glob_docs, True, 200), (exp_docs, False, 60), (init_docs, False, 10)])
+        single = corpus.search_multistage(stages, q)
+        for s in range(3):
+            sc, ids = res[s]
+            _same_ranking(ids.tolist(), sc, want[s])
+            assert ids.tolist() == single[s][1].tolist()
+            np.testing.assert_array_equal(sc, single[s][0])      # same kernels arithmetic -> bit-identical
+    for nm in ("b_initial", "b_exp", "b_glob"):
+        corpus.drop_store(nm)
+
+
+@pytest.mark.gpu
+def test_batched_two_stage_per_stage_queries_and_k_larger_than_corpus(corpus):
+    rng = np.random.default_rng(77)
+    n = 90
+    init = rng.standard_normal((n * 300, 128)).astype(np.float16)
+    pooled = rng.standard_normal((n * 32, 128)).astype(np.float16)
+    corpus.add_store("b2_initial", init, fixed_rows=300)
+    corpus.add_store("b2_pooled", pooled, fixed_rows=32)
+    init_docs = [init[i * 300:(i + 1) * 300].astype(np.float32) for i in range(n)]
+    pooled_docs = [pooled[i * 32:(i + 1) * 32].astype(np.float32) for i in range(n)]
+    queries = [rng.standard_normal((int(rng.integers(5, 40)), 128)).astype(np.float32) for _ in range(9)]
+    # the client sends the mean-pooled prefetch vector and the token matrix separately (two_stage.py:142,159)
+    sq = [[q.mean(axis=0, keepdims=True), q] for q in queries]
+    stages = [("b2_pooled", False, 128), ("b2_initial", False, 10)]      # prefetch_k > n pages
+    got = corpus.search_multistage_batch(stages, None, stage_queries=sq)
+    for q, res in zip(queries, got):
+        want = MO.multistage(q, [(pooled_docs, True, 128), (init_docs, False, 10)])
+        assert len(res[0][1]) == n
+        for s in range(2):
+            _same_ranking(res[s][1].tolist(), res[s][0], want[s])
+    corpus.drop_store("b2_initial")
+    corpus.drop_store("b2_pooled")

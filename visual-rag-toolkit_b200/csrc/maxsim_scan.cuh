@@ -57,7 +57,13 @@ struct ScanParams {
   int hi_only;                // 1: contract only the fp16 hi half of the query (N = QP); QP >= 16
   int shfl_rows;              // PACKED: > 0 -> every page sits in its own power-of-two slot of shfl_rows (<= 32) tile
                               //   rows, so the per-page max is a segmented warp butterfly (no smem round trip)
-  long long n_tiles;          // PACKED: number of tiles (work units)
+  long long n_tiles;          // PACKED: number of tiles (work units) per group
+  // ---- query groups (batched candidate lists; BSW kernels). Group g = query g with its own operand image
+  // qimg + g*qimg_stride, its own candidate list cand[g*n_items + i] and its own scores[g*n_items + i];
+  // n_items / n_tiles above are PER GROUP. n_groups == 1: the single-query layout.
+  int n_groups;
+  long long qimg_stride;      // bytes between consecutive groups' operand images
+  const int* q_valid_arr;     // [n_groups] real query rows of each group (nullptr: q_valid for all)
 };
 
 template <int QP>
@@ -74,13 +80,15 @@ struct ScanCfg {
   static constexpr int epi_groups(bool packed) { return packed ? EPI_GROUPS_PACKED : 1; }
   static constexpr int threads(bool packed) { return 64 + 128 * epi_groups(packed); }
   static constexpr int sc_bytes(bool packed) { return packed ? EPI_GROUPS_PACKED * QP * SC_PITCH * 4 : 0; }
-  static constexpr int stages(bool packed) {
-    const int budget = 227 * 1024 - 1024 /*align slack*/ - B_BYTES - MISC_BYTES - sc_bytes(packed);
+  // bsw: the query operand is double-buffered so that a CTA can switch between query groups mid-kernel
+  static constexpr int stages(bool packed, bool bsw = false) {
+    const int budget = 227 * 1024 - 1024 /*align slack*/ - (bsw ? 2 : 1) * B_BYTES - MISC_BYTES - sc_bytes(packed);
     const int s = budget / (kTileBytes + kScaleStride * 4);
     return s > 6 ? 6 : s;
   }
-  static constexpr size_t smem_bytes(bool packed) {
-    return 1024 + size_t(stages(packed)) * (kTileBytes + kScaleStride * 4) + B_BYTES + MISC_BYTES + sc_bytes(packed);
+  static constexpr size_t smem_bytes(bool packed, bool bsw = false) {
+    return 1024 + size_t(stages(packed, bsw)) * (kTileBytes + kScaleStride * 4) + (bsw ? 2 : 1) * B_BYTES + MISC_BYTES +
+           sc_bytes(packed);
   }
 };
 
@@ -101,8 +109,37 @@ __device__ __forceinline__ bool resolve_page(const ScanParams& p, long long page
   }
   return true;
 }
-__device__ __forceinline__ long long item_page(const ScanParams& p, long long item) {
-  return p.cand ? (__ldg(p.cand + item) - p.cand_base) : item;
+__device__ __forceinline__ long long item_page(const ScanParams& p, long long item, int g = 0) {
+  return p.cand ? (__ldg(p.cand + g * p.n_items + item) - p.cand_base) : item;
+}
+
+// Work units of one CTA. One group: units blockIdx.x, +gridDim.x, ... (neighbouring CTAs stream neighbouring
+// tiles). Several groups: a contiguous range of the (group-major) unit space, so that a CTA changes its query
+// operand only a few times. Unit U -> (group U / units_per_group, local unit U % units_per_group).
+struct UnitRange {
+  long long first, step, count, per_group;
+  __device__ __forceinline__ void decode(long long i, int& g, long long& u) const {
+    const long long U = first + i * step;
+    if (per_group == 0) { g = 0; u = U; }
+    else { g = static_cast<int>(U / per_group); u = U - g * per_group; }
+  }
+};
+__device__ __forceinline__ UnitRange unit_range(const ScanParams& p, long long units_per_group) {
+  UnitRange r;
+  if (p.n_groups <= 1) {
+    r.first = blockIdx.x;
+    r.step = gridDim.x;
+    r.count = units_per_group > r.first ? (units_per_group - r.first + r.step - 1) / r.step : 0;
+    r.per_group = 0;
+  } else {
+    const long long total = units_per_group * p.n_groups;
+    const long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
+    r.first = lo;
+    r.step = 1;
+    r.count = hi - lo;
+    r.per_group = units_per_group;
+  }
+  return r;
 }
 
 // Row ranges one PACKED tile fetches: dense layouts -> one contiguous range; slot mode -> up to 4 items.
@@ -111,7 +148,7 @@ struct PackedTileMeta {
   int nr[4];
   int cnt;
 };
-__device__ __forceinline__ void packed_tile_meta(const ScanParams& p, long long u, PackedTileMeta& m) {
+__device__ __forceinline__ void packed_tile_meta(const ScanParams& p, int g, long long u, PackedTileMeta& m) {
   if (!p.slot_mode) {
     m.cnt = 1;
     if (p.fixed_rows > 0) {
@@ -132,14 +169,14 @@ __device__ __forceinline__ void packed_tile_meta(const ScanParams& p, long long 
     for (int j = 0; j < 4; ++j) {
       m.r0[j] = 0;
       m.nr[j] = 0;
-      if (j < m.cnt) resolve_page(p, item_page(p, i0 + j), m.r0[j], m.nr[j]);
+      if (j < m.cnt) resolve_page(p, item_page(p, i0 + j, g), m.r0[j], m.nr[j]);
     }
   }
 }
 
 // General PACKED path: entry `et` of tile u's segment table (item, first tile row, end tile row) and the table size.
-__device__ __forceinline__ void packed_segment(const ScanParams& p, long long u, int et, int& nseg, int& item, int& rb,
-                                               int& re) {
+__device__ __forceinline__ void packed_segment(const ScanParams& p, int g, long long u, int et, int& nseg, int& item,
+                                               int& rb, int& re) {
   item = rb = re = 0;
   if (!p.slot_mode) {
     long long pg0, pg1;
@@ -169,7 +206,7 @@ __device__ __forceinline__ void packed_segment(const ScanParams& p, long long u,
     if (et < nseg) {
       long long r0;
       int nr;
-      resolve_page(p, item_page(p, i0 + et), r0, nr);
+      resolve_page(p, item_page(p, i0 + et, g), r0, nr);
       item = static_cast<int>(i0 + et);
       rb = et * p.slot_rows;
       re = rb + nr;   // nr == 0 -> empty segment -> -inf
@@ -266,7 +303,7 @@ __device__ __forceinline__ float slot_maxsim(float* v, int lane, int q_valid) {
   return sum;
 }
 
-template <int QP, bool PACKED>
+template <int QP, bool PACKED, bool BSW>
 __global__ void __launch_bounds__(ScanCfg<QP>::threads(PACKED), 1)
 maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_constant__ CUtensorMap tm_rows32,
                    const __grid_constant__ CUtensorMap tm_scale128, const __grid_constant__ CUtensorMap tm_scale32,
@@ -274,7 +311,8 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   using Cfg = ScanCfg<QP>;
   constexpr int N = Cfg::N;
   constexpr int ACC = Cfg::ACC;
-  constexpr int STAGES = Cfg::stages(PACKED);
+  constexpr int STAGES = Cfg::stages(PACKED, BSW);
+  constexpr int NB = BSW ? 2 : 1;              // query operand buffers
   constexpr int NTHREADS = Cfg::threads(PACKED);
   constexpr int EPI_GROUPS = Cfg::epi_groups(PACKED);
   constexpr int QG = (QP + 31) / 32;           // 32-wide query groups
@@ -285,14 +323,16 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * kTileBytes;
-  float* sScale = reinterpret_cast<float*>(sB + Cfg::B_BYTES);
+  float* sScale = reinterpret_cast<float*>(sB + NB * Cfg::B_BYTES);
   float* sSc = sScale + STAGES * kScaleStride;                       // PACKED: [EPI_GROUPS][QP][SC_PITCH]
   uint8_t* misc = reinterpret_cast<uint8_t*>(sSc) + Cfg::sc_bytes(PACKED);
   uint64_t* full = reinterpret_cast<uint64_t*>(misc);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + ACC;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC);
+  uint64_t* bfull = tempty + ACC;            // BSW: operand buffer filled (bulk copy) / drained (MMAs retired)
+  uint64_t* bempty = bfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty + 2);
   int* sMis = reinterpret_cast<int*>(misc + 256);                 // [STAGES][4] scale misalignment per slot
   float* sRed = reinterpret_cast<float*>(misc + 512);             // LARGE: [2][4][QP]
   int* sSeg = reinterpret_cast<int*>(misc + 512);                 // PACKED: [EPI_GROUPS][3][128] ints (item, begin, end)
@@ -314,10 +354,14 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], 4);
     }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bfull[b], 1);
+      mbar_init(&bempty[b], 1);
+    }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-  {  // query operand image: global -> smem (already in the swizzled UMMA layout)
+  if constexpr (!BSW) {  // query operand image: global -> smem (already in the swizzled UMMA layout)
     const uint4* src = reinterpret_cast<const uint4*>(p.qimg);
     uint4* dst = reinterpret_cast<uint4*>(sB);
     for (int i = threadIdx.x; i < Cfg::B_BYTES / 16; i += NTHREADS) dst[i] = __ldg(src + i);
@@ -328,8 +372,8 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  // Work units of this CTA: u = blockIdx.x, blockIdx.x + gridDim.x, ...
-  const long long n_units = PACKED ? p.n_tiles : p.n_items;
+  // Work units of this CTA (LARGE: items, PACKED: tiles)
+  const UnitRange ur = unit_range(p, PACKED ? p.n_tiles : p.n_items);
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -337,11 +381,25 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
       uint32_t stage = 0, phase = 0;
       PackedTileMeta cur, nxt;
       cur.cnt = nxt.cnt = 0;
-      for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+      int cur_g = -1, n_sw = -1;
+      for (long long i = 0; i < ur.count; ++i) {
+        int g;
+        long long u;
+        ur.decode(i, g, u);
+        if constexpr (BSW) {
+          if (g != cur_g) {   // next query group: fill the other operand buffer once its previous MMAs retired
+            ++n_sw;
+            const int slot = n_sw & 1;
+            if (n_sw >= 2) mbar_wait(&bempty[slot], ((n_sw >> 1) - 1) & 1);
+            bulk_load(sB + slot * Cfg::B_BYTES, p.qimg + g * p.qimg_stride, Cfg::B_BYTES, &bfull[slot]);
+            mbar_arrive_expect_tx(&bfull[slot], Cfg::B_BYTES);
+            cur_g = g;
+          }
+        }
         if constexpr (!PACKED) {
           long long row0;
           int nrows;
-          resolve_page(p, item_page(p, u), row0, nrows);
+          resolve_page(p, item_page(p, u, g), row0, nrows);
           for (int t0 = 0; t0 < nrows; t0 += kTileRows) {
             const int rows = min(kTileRows, nrows - t0);
             mbar_wait(&empty[stage], phase ^ 1);
@@ -358,9 +416,13 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         } else {
           // tile metadata (row ranges) is loaded one tile ahead so the dependent global loads (candidate id ->
           // page offsets) overlap the previous tile instead of stalling the TMA issue
-          if (u == static_cast<long long>(blockIdx.x)) packed_tile_meta(p, u, cur);
-          const long long un = u + gridDim.x;
-          if (un < n_units) packed_tile_meta(p, un, nxt);
+          if (i == 0) packed_tile_meta(p, g, u, cur);
+          if (i + 1 < ur.count) {
+            int gn;
+            long long un;
+            ur.decode(i + 1, gn, un);
+            packed_tile_meta(p, gn, un, nxt);
+          }
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* a = sA + stage * kTileBytes;
           float* sc = sScale + stage * kScaleStride;
@@ -392,14 +454,28 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
     // ===================================================================== MMA issuer (one thread)
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(kTileRows, p.hi_only ? QP : N);
-      const uint32_t b_addr = smem_u32(sB);
+      uint32_t b_addr = smem_u32(sB);
       uint32_t stage = 0, phase = 0, acc = 0, accphase = 0;
-      for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+      int cur_g = -1, n_sw = -1;
+      for (long long i = 0; i < ur.count; ++i) {
+        int g;
+        long long u;
+        ur.decode(i, g, u);
+        if constexpr (BSW) {
+          if (g != cur_g) {
+            if (n_sw >= 0) umma_commit(&bempty[n_sw & 1]);   // previous group's operand buffer is free once its MMAs retire
+            ++n_sw;
+            mbar_wait(&bfull[n_sw & 1], (n_sw >> 1) & 1);
+            tc_fence_after_sync();
+            b_addr = smem_u32(sB + (n_sw & 1) * Cfg::B_BYTES);
+            cur_g = g;
+          }
+        }
         int ntiles = 1;
         if constexpr (!PACKED) {
           long long row0;
           int nrows;
-          resolve_page(p, item_page(p, u), row0, nrows);
+          resolve_page(p, item_page(p, u, g), row0, nrows);
           ntiles = (nrows + kTileRows - 1) / kTileRows;
         }
         for (int t = 0; t < ntiles; ++t) {
@@ -436,10 +512,14 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
 
     if constexpr (!PACKED) {
       uint32_t stage = 0, phase = 0, acc = 0, accphase = 0, par = 0;
-      for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+      for (long long i = 0; i < ur.count; ++i) {
+        int g;
+        long long u;
+        ur.decode(i, g, u);
+        const int q_valid = p.q_valid_arr ? __ldg(p.q_valid_arr + g) : p.q_valid;
         long long row0;
         int nrows;
-        const bool ok = resolve_page(p, item_page(p, u), row0, nrows);
+        const bool ok = resolve_page(p, item_page(p, u, g), row0, nrows);
         float run[QP];
 #pragma unroll
         for (int q = 0; q < QP; ++q) run[q] = -INFINITY;
@@ -497,12 +577,12 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             const int q = g * 32 + lane;
             if (q < QP) {
               const float m = fmaxf(fmaxf(red[q], red[QP + q]), fmaxf(red[2 * QP + q], red[3 * QP + q]));
-              if (q < p.q_valid) sum += m;
+              if (q < q_valid) sum += m;
             }
           }
 #pragma unroll
           for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-          if (lane == 0) p.scores[u] = (ok && nrows > 0) ? sum : -INFINITY;
+          if (lane == 0) p.scores[g * p.n_items + u] = (ok && nrows > 0) ? sum : -INFINITY;
         }
         par ^= 1;
       }
@@ -511,11 +591,14 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
       int* seg = sSeg + grp * 3 * kTileRows;
       float* sc = sSc + grp * QP * Cfg::SC_PITCH;
       const uint32_t bar_id = 1 + grp;
-      long long seq = grp;
       int seg_n = 0, seg_item = 0, seg_rb = 0, seg_re = 0;   // general path: this thread's entry of the tile's segment table
       bool seg_ready = false;
-      for (long long u = blockIdx.x + static_cast<long long>(grp) * gridDim.x; u < n_units;
-           u += static_cast<long long>(EPI_GROUPS) * gridDim.x, seq += EPI_GROUPS) {
+      for (long long seq = grp; seq < ur.count; seq += EPI_GROUPS) {
+        int g;
+        long long u;
+        ur.decode(seq, g, u);
+        const int q_valid = p.q_valid_arr ? __ldg(p.q_valid_arr + g) : p.q_valid;
+        float* const scores_g = p.scores + g * p.n_items;
         const uint32_t stage = static_cast<uint32_t>(seq % STAGES), phase = static_cast<uint32_t>((seq / STAGES) & 1);
         const uint32_t acc = static_cast<uint32_t>(seq % ACC), accphase = static_cast<uint32_t>((seq / ACC) & 1);
         const uint32_t ta = lane_addr + acc * N;
@@ -565,14 +648,14 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             }
             float sum;
             switch (SR) {
-              case 32: sum = slot_maxsim<QP, 32>(v, lane, p.q_valid); break;
-              case 16: sum = slot_maxsim<QP, 16>(v, lane, p.q_valid); break;
-              case 8: sum = slot_maxsim<QP, 8>(v, lane, p.q_valid); break;
-              case 4: sum = slot_maxsim<QP, 4>(v, lane, p.q_valid); break;
-              case 2: sum = slot_maxsim<QP, 2>(v, lane, p.q_valid); break;
-              default: sum = slot_maxsim<QP, 1>(v, lane, p.q_valid); break;
+              case 32: sum = slot_maxsim<QP, 32>(v, lane, q_valid); break;
+              case 16: sum = slot_maxsim<QP, 16>(v, lane, q_valid); break;
+              case 8: sum = slot_maxsim<QP, 8>(v, lane, q_valid); break;
+              case 4: sum = slot_maxsim<QP, 4>(v, lane, q_valid); break;
+              case 2: sum = slot_maxsim<QP, 2>(v, lane, q_valid); break;
+              default: sum = slot_maxsim<QP, 1>(v, lane, q_valid); break;
             }
-            if (rin == 0 && item_ok) p.scores[item] = nr > 0 ? sum : -INFINITY;
+            if (rin == 0 && item_ok) scores_g[item] = nr > 0 ? sum : -INFINITY;
           }
           continue;
         }
@@ -580,7 +663,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         // 1. segment table of this tile (item, first tile row, end tile row) -> smem. The table of the group's NEXT
         //    tile is loaded into registers now (tile -> page -> offsets is a chain of dependent global loads).
         if (!seg_ready) {
-          packed_segment(p, u, et, seg_n, seg_item, seg_rb, seg_re);
+          packed_segment(p, g, u, et, seg_n, seg_item, seg_rb, seg_re);
           seg_ready = true;
         }
         const int nseg = seg_n;
@@ -590,8 +673,12 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           seg[2 * kTileRows + et] = seg_re;
         }
         {
-          const long long un = u + static_cast<long long>(EPI_GROUPS) * gridDim.x;
-          if (un < n_units) packed_segment(p, un, et, seg_n, seg_item, seg_rb, seg_re);
+          if (seq + EPI_GROUPS < ur.count) {
+            int gn;
+            long long un;
+            ur.decode(seq + EPI_GROUPS, gn, un);
+            packed_segment(p, gn, un, et, seg_n, seg_item, seg_rb, seg_re);
+          }
         }
         // 2. scaled scores of my row -> transposed smem buffer sc[q][row]
         mbar_wait(&tfull[acc], accphase);
@@ -648,12 +735,12 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
                 m0 = fmaxf(m0, fmaxf(a0, a1));
                 m1 = fmaxf(m1, fmaxf(a2, a3));
               }
-              if (q < p.q_valid) sum += fmaxf(m0, m1);
+              if (q < q_valid) sum += fmaxf(m0, m1);
             }
           }
 #pragma unroll
           for (int off = QW / 2; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-          if (sg < nseg && ql == 0) p.scores[item] = nonempty ? sum : -INFINITY;
+          if (sg < nseg && ql == 0) scores_g[item] = nonempty ? sum : -INFINITY;
         }
         named_bar_sync(bar_id, 128);   // the group's buffers are reused by its next tile
       }

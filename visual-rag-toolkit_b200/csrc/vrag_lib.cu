@@ -133,6 +133,11 @@ struct vrag_corpus {
   DevBuf<unsigned int> d_sel_hist;
   DevBuf<long long> d_cand, d_out_ids;
   DevBuf<int> d_counts;
+  DevBuf<uint8_t> d_qimg_batch;   // batched search: one operand image per query
+  DevBuf<int> d_qmeta;            // batched search: [n_stages][2][nq] query row ranges + [nq] effective rows
+  int* h_qmeta = nullptr;         // pinned staging of d_qmeta
+  size_t h_qmeta_cap = 0;
+  size_t h_query_cap = 0;         // rows
   float* h_query = nullptr;       // pinned staging
   float* h_out_scores = nullptr;
   long long* h_out_ids = nullptr;
@@ -182,6 +187,7 @@ extern "C" int vrag_corpus_create(int device, int64_t page_base, vrag_corpus_t**
   CUDA_OK(cudaEventCreate(&c->evk0));
   CUDA_OK(cudaEventCreate(&c->evk1));
   CUDA_OK(cudaMallocHost(&c->h_query, kMaxQueryRows * 128 * sizeof(float)));
+  c->h_query_cap = kMaxQueryRows;
   CUDA_OK(cudaMallocHost(&c->h_counts, kMaxStages * sizeof(int)));
   TRY(c->d_query.ensure(kMaxQueryRows * 128));
   TRY(c->d_qimg.ensure(256 * 256));
@@ -206,6 +212,9 @@ extern "C" int vrag_corpus_destroy(vrag_corpus_t* c) {
   c->d_cand.release();
   c->d_out_ids.release();
   c->d_counts.release();
+  c->d_qimg_batch.release();
+  c->d_qmeta.release();
+  if (c->h_qmeta) cudaFreeHost(c->h_qmeta);
   if (c->h_query) cudaFreeHost(c->h_query);
   if (c->h_out_scores) cudaFreeHost(c->h_out_scores);
   if (c->h_out_ids) cudaFreeHost(c->h_out_ids);
@@ -439,10 +448,10 @@ extern "C" int vrag_store_drop(vrag_corpus_t* c, const char* name) {
 }
 
 // ------------------------------------------------------------------------------------------------ launches
-template <int QP, bool PACKED>
+template <int QP, bool PACKED, bool BSW = false>
 static int launch_scan_t(vrag_corpus* c, const Store& s, const ScanParams& p, long long n_units, cudaStream_t st) {
-  auto kern = maxsim_scan_kernel<QP, PACKED>;
-  const size_t smem = ScanCfg<QP>::smem_bytes(PACKED);
+  auto kern = maxsim_scan_kernel<QP, PACKED, BSW>;
+  const size_t smem = ScanCfg<QP>::smem_bytes(PACKED, BSW);
   static bool attr_done[8] = {false};  // per device
   if (!attr_done[c->device & 7]) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -455,24 +464,10 @@ static int launch_scan_t(vrag_corpus* c, const Store& s, const ScanParams& p, lo
   return 0;
 }
 
-// Score a store (or a candidate list) into d_scores[n_items]. All pointers are device pointers.
-static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int n_query_rows, uint32_t flags,
-                       const long long* d_cand, int64_t n_cand, float* d_scores, cudaStream_t st, bool time_kernel) {
-  const bool pool = (flags & VRAG_Q_POOL) != 0;
-  const bool normalize = (flags & VRAG_Q_NORMALIZE) != 0;
-  if (n_query_rows < 1) return fail("query has no rows");
-  if (n_query_rows > kMaxQueryRows) return fail("query has %d rows; at most %d supported", n_query_rows, kMaxQueryRows);
-  const int q_eff = pool ? 1 : n_query_rows;
-  if (q_eff > 128) return fail("query has %d token rows; at most 128 supported per call", q_eff);
-  const int QP = q_eff <= 8 ? 8 : q_eff <= 16 ? 16 : q_eff <= 32 ? 32 : q_eff <= 64 ? 64 : 128;
-  const int64_t n_items = d_cand ? n_cand : s.n_pages;
-  if (n_items == 0) return 0;
-  if (s.total_rows == 0) return fail("store is empty");
-
-  query_prep_kernel<<<QP, 128, 0, st>>>(d_query, n_query_rows, pool ? 1 : 0, normalize ? 1 : 0, QP, c->d_qimg.p);
-  c->launches++;
-
-  ScanParams p;
+// Work layout of one scan over store `s`: every page (d_cand == nullptr) or n_items candidate ids (per query group).
+static void fill_scan_params(vrag_corpus* c, const Store& s, const long long* d_cand, int64_t n_items, int QP,
+                             bool normalize, float* d_scores, ScanParams* out, long long* n_units_out) {
+  ScanParams& p = *out;
   memset(&p, 0, sizeof(p));
   p.offsets = s.offsets;
   p.fixed_rows = s.fixed_rows;
@@ -480,15 +475,10 @@ static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int
   p.cand = d_cand;
   p.cand_base = c->page_base;
   p.n_items = n_items;
-  p.qimg = c->d_qimg.p;
   p.scores = d_scores;
-  p.q_valid = q_eff;
   p.use_scale = normalize ? 1 : 0;
   p.slot_rows = kTileRows;
-  {  // experiment knob: VRAG_QUERY_SPLIT=0 drops the lo half of the query (fp16-only query, LARGE pages only)
-    const char* e = getenv("VRAG_QUERY_SPLIT");
-    p.hi_only = (e && e[0] == '0' && QP >= 16 && !s.packed) ? 1 : 0;
-  }
+  p.n_groups = 1;
   long long n_units = n_items;
   if (s.packed) {
     const bool small_rows = s.max_rows <= 32;
@@ -511,6 +501,35 @@ static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int
     }
     n_units = p.n_tiles;
   }
+  *n_units_out = n_units;
+}
+
+// Score a store (or a candidate list) into d_scores[n_items]. All pointers are device pointers.
+static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int n_query_rows, uint32_t flags,
+                       const long long* d_cand, int64_t n_cand, float* d_scores, cudaStream_t st, bool time_kernel) {
+  const bool pool = (flags & VRAG_Q_POOL) != 0;
+  const bool normalize = (flags & VRAG_Q_NORMALIZE) != 0;
+  if (n_query_rows < 1) return fail("query has no rows");
+  if (n_query_rows > kMaxQueryRows) return fail("query has %d rows; at most %d supported", n_query_rows, kMaxQueryRows);
+  const int q_eff = pool ? 1 : n_query_rows;
+  if (q_eff > 128) return fail("query has %d token rows; at most 128 supported per call", q_eff);
+  const int QP = q_eff <= 8 ? 8 : q_eff <= 16 ? 16 : q_eff <= 32 ? 32 : q_eff <= 64 ? 64 : 128;
+  const int64_t n_items = d_cand ? n_cand : s.n_pages;
+  if (n_items == 0) return 0;
+  if (s.total_rows == 0) return fail("store is empty");
+
+  query_prep_kernel<<<QP, 128, 0, st>>>(d_query, n_query_rows, pool ? 1 : 0, normalize ? 1 : 0, QP, c->d_qimg.p);
+  c->launches++;
+
+  ScanParams p;
+  long long n_units = 0;
+  fill_scan_params(c, s, d_cand, n_items, QP, normalize, d_scores, &p, &n_units);
+  p.qimg = c->d_qimg.p;
+  p.q_valid = q_eff;
+  {  // experiment knob: VRAG_QUERY_SPLIT=0 drops the lo half of the query (fp16-only query, LARGE pages only)
+    const char* e = getenv("VRAG_QUERY_SPLIT");
+    p.hi_only = (e && e[0] == '0' && QP >= 16 && !s.packed) ? 1 : 0;
+  }
   if (time_kernel) CUDA_OK(cudaEventRecord(c->evk0, st));
   int r = 0;
 #define VRAG_DISPATCH(QPV)                                                     \
@@ -531,6 +550,40 @@ static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int
   if (r) return r;
   if (time_kernel) CUDA_OK(cudaEventRecord(c->evk1, st));
   return 0;
+}
+
+
+// Batched candidate scan: query b (operand image b of d_qimg_batch) scores its own candidate list
+// d_cand[b*n_items + i] into d_scores[b*n_items + i], all queries in ONE launch (the CTAs switch operands).
+// Returns 2 (no error set) when the shape is not covered by the batched kernels; the caller then runs the
+// queries one launch each.
+static int launch_scan_batch(vrag_corpus* c, const Store& s, const float* d_queries, const int* d_qbegin,
+                             const int* d_qend, int* d_qvalid, int nq, int max_q_eff, uint32_t flags,
+                             const long long* d_cand, int64_t n_items, float* d_scores, cudaStream_t st) {
+  const bool pool = (flags & VRAG_Q_POOL) != 0;
+  const bool normalize = (flags & VRAG_Q_NORMALIZE) != 0;
+  const int q_eff = pool ? 1 : max_q_eff;
+  if (q_eff > 64 || !d_cand) return 2;
+  if (n_items == 0 || nq == 0) return 0;
+  if (s.total_rows == 0) return fail("store is empty");
+  const int QP = q_eff <= 32 ? 32 : 64;
+  const size_t img = static_cast<size_t>(2 * QP) * 256;
+  TRY(c->d_qimg_batch.ensure(img * nq));
+  query_prep_batch_kernel<<<dim3(QP, nq), 128, 0, st>>>(d_queries, d_qbegin, d_qend, pool ? 1 : 0, normalize ? 1 : 0, QP,
+                                                        c->d_qimg_batch.p, static_cast<long long>(img), d_qvalid);
+  c->launches++;
+  ScanParams p;
+  long long upg = 0;
+  fill_scan_params(c, s, d_cand, n_items, QP, normalize, d_scores, &p, &upg);
+  p.qimg = c->d_qimg_batch.p;
+  p.qimg_stride = static_cast<long long>(img);
+  p.q_valid_arr = d_qvalid;
+  p.n_groups = nq;
+  const long long n_units = upg * nq;
+  int r;
+  if (QP == 32) r = s.packed ? launch_scan_t<32, true, true>(c, s, p, n_units, st) : launch_scan_t<32, false, true>(c, s, p, n_units, st);
+  else r = s.packed ? launch_scan_t<64, true, true>(c, s, p, n_units, st) : launch_scan_t<64, false, true>(c, s, p, n_units, st);
+  return r;
 }
 
 // Exact top-k of d_scores[batch][n] -> (out_scores[batch][k], out_ids[batch][k]) sorted descending, ties -> lower
@@ -721,6 +774,137 @@ extern "C" int vrag_search(vrag_corpus_t* c, const char* name, const float* quer
   TRY(vrag_search_multistage(c, 1, names, &flags, &k, query, n_query_rows, nullptr, cand_ids, n_cand, out_scores,
                              out_ids, &cnt));
   if (out_count) *out_count = cnt;
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------ batched queries
+static int ensure_host_query(vrag_corpus* c, size_t rows) {
+  if (rows <= c->h_query_cap) return 0;
+  if (c->h_query) cudaFreeHost(c->h_query);
+  c->h_query = nullptr;
+  c->h_query_cap = 0;
+  CUDA_OK(cudaMallocHost(&c->h_query, rows * 128 * sizeof(float)));
+  c->h_query_cap = rows;
+  return 0;
+}
+
+extern "C" int vrag_search_multistage_batch(vrag_corpus_t* c, int n_stages, const char* const* names,
+                                            const uint32_t* flags, const int* ks, int n_queries, const float* query_rows,
+                                            const int* q_offsets, int per_stage_queries, float* out_scores,
+                                            int64_t* out_ids, int* out_counts) {
+  if (!c) return fail("corpus is NULL");
+  if (n_stages < 1 || n_stages > kMaxStages) return fail("n_stages %d out of range [1,%d]", n_stages, kMaxStages);
+  if (!names || !flags || !ks || !out_scores || !out_ids || !out_counts || !query_rows || !q_offsets) return fail("NULL argument");
+  if (n_queries < 0) return fail("n_queries < 0");
+  if (n_queries == 0) return 0;
+  TRY(set_device(c));
+  Store* st[kMaxStages];
+  size_t total_k = 0;
+  for (int s = 0; s < n_stages; ++s) {
+    TRY(find_store(c, names[s], &st[s]));
+    if (ks[s] < 1) return fail("stage %d: k must be >= 1", s);
+    if (ks[s] > kTopkMaxK) return fail("stage %d: k=%d exceeds the supported maximum %d", s, ks[s], kTopkMaxK);
+    if (st[s]->n_pages != st[0]->n_pages) return fail("stage %d: store '%s' has a different page count", s, names[s]);
+    total_k += ks[s];
+  }
+  const int nq = n_queries;
+  const int qs = per_stage_queries ? n_stages : 1;
+  const int total_rows = q_offsets[static_cast<size_t>(nq) * qs];
+  // per (stage, query) row range + the largest effective row count per stage
+  std::vector<int> max_rows(n_stages, 0);
+  for (int b = 0; b < nq; ++b)
+    for (int s = 0; s < n_stages; ++s) {
+      const int i = b * qs + (per_stage_queries ? s : 0);
+      const int r0 = q_offsets[i], r1 = q_offsets[i + 1];
+      if (r0 < 0 || r1 <= r0 || r1 > total_rows) return fail("query %d stage %d: bad row range [%d,%d)", b, s, r0, r1);
+      if (r1 - r0 > kMaxQueryRows) return fail("query %d has %d rows; at most %d supported", b, r1 - r0, kMaxQueryRows);
+      max_rows[s] = std::max(max_rows[s], r1 - r0);
+    }
+  for (int s = 0; s < n_stages; ++s)
+    if (!(flags[s] & VRAG_Q_POOL) && max_rows[s] > 128) return fail("query has %d token rows; at most 128 supported per call", max_rows[s]);
+  // ---- stage queries and metadata to the device
+  TRY(ensure_host_query(c, total_rows));
+  TRY(c->d_query.ensure(static_cast<size_t>(total_rows) * 128));
+  memcpy(c->h_query, query_rows, static_cast<size_t>(total_rows) * 128 * sizeof(float));
+  CUDA_OK(cudaMemcpyAsync(c->d_query.p, c->h_query, static_cast<size_t>(total_rows) * 128 * sizeof(float),
+                          cudaMemcpyHostToDevice, c->stream));
+  const size_t meta_n = static_cast<size_t>(n_stages) * 2 * nq + nq;   // [s][begin|end][b], then q_valid scratch [b]
+  if (meta_n > c->h_qmeta_cap) {
+    if (c->h_qmeta) cudaFreeHost(c->h_qmeta);
+    c->h_qmeta = nullptr;
+    c->h_qmeta_cap = 0;
+    CUDA_OK(cudaMallocHost(&c->h_qmeta, meta_n * sizeof(int)));
+    c->h_qmeta_cap = meta_n;
+  }
+  TRY(c->d_qmeta.ensure(meta_n));
+  for (int s = 0; s < n_stages; ++s)
+    for (int b = 0; b < nq; ++b) {
+      const int i = b * qs + (per_stage_queries ? s : 0);
+      c->h_qmeta[(static_cast<size_t>(s) * 2 + 0) * nq + b] = q_offsets[i];
+      c->h_qmeta[(static_cast<size_t>(s) * 2 + 1) * nq + b] = q_offsets[i + 1];
+    }
+  CUDA_OK(cudaMemcpyAsync(c->d_qmeta.p, c->h_qmeta, (meta_n - nq) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  int* d_qvalid = c->d_qmeta.p + static_cast<size_t>(n_stages) * 2 * nq;
+  // ---- outputs, stage-major: stage s occupies [nq*sum(ks[:s]), +nq*ks[s]) as [nq][ks[s]]
+  const size_t out_n = total_k * nq;
+  TRY(c->d_out_scores.ensure(out_n));
+  TRY(c->d_out_ids.ensure(out_n));
+  TRY(ensure_host_out(c, out_n));
+  const int64_t n_pages = st[0]->n_pages;
+  // stage-0 score matrix [chunk][n_pages] is bounded to ~1 GiB: queries are processed in chunks
+  const int64_t max_scores = int64_t(1) << 28;
+  const int qchunk = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nq, max_scores / std::max<int64_t>(n_pages, 1))));
+  int64_t need = static_cast<int64_t>(qchunk) * std::max<int64_t>(n_pages, 1);
+  for (int s = 0; s + 1 < n_stages; ++s) need = std::max<int64_t>(need, static_cast<int64_t>(qchunk) * ks[s]);
+  TRY(c->d_scores.ensure(need));
+  CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+  bool timed = false;
+  for (int b0 = 0; b0 < nq; b0 += qchunk) {
+    const int qc = std::min(qchunk, nq - b0);
+    size_t off = 0;
+    int64_t n_prev = n_pages;
+    const long long* d_prev_ids = nullptr;
+    for (int s = 0; s < n_stages; ++s) {
+      const int* d_qb = c->d_qmeta.p + (static_cast<size_t>(s) * 2 + 0) * nq + b0;
+      const int* d_qe = c->d_qmeta.p + (static_cast<size_t>(s) * 2 + 1) * nq + b0;
+      const int64_t n_items = (s == 0) ? n_pages : ks[s - 1];   // candidate lists keep the full stride; missing ids are -1
+      if (n_prev > 0) {
+        int r = 2;
+        if (s > 0) {
+          if (!timed) CUDA_OK(cudaEventRecord(c->evk0, c->stream));
+          r = launch_scan_batch(c, *st[s], c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows[s], flags[s], d_prev_ids,
+                                n_items, c->d_scores.p, c->stream);
+          if (r == 1) return r;
+          if (!timed && r == 0) { CUDA_OK(cudaEventRecord(c->evk1, c->stream)); timed = true; }
+        }
+        if (r == 2) {   // one launch per query (dense stage 0, or shapes the batched kernels do not cover)
+          for (int b = 0; b < qc; ++b) {
+            const int i = (b0 + b) * qs + (per_stage_queries ? s : 0);
+            TRY(launch_scan(c, *st[s], c->d_query.p + static_cast<size_t>(q_offsets[i]) * 128, q_offsets[i + 1] - q_offsets[i],
+                            flags[s], d_prev_ids ? d_prev_ids + static_cast<size_t>(b) * n_items : nullptr, n_items,
+                            c->d_scores.p + static_cast<size_t>(b) * n_items, c->stream, false));
+          }
+        }
+      }
+      float* o_sc = c->d_out_scores.p + off * nq + static_cast<size_t>(b0) * ks[s];
+      long long* o_id = c->d_out_ids.p + off * nq + static_cast<size_t>(b0) * ks[s];
+      TRY(launch_topk(c, c->d_scores.p, d_prev_ids, c->page_base, n_prev > 0 ? n_items : 0, ks[s], o_sc, o_id, nullptr,
+                      nullptr, c->stream, qc, d_prev_ids ? n_items : 0));
+      d_prev_ids = o_id;
+      n_prev = std::min<int64_t>(ks[s], n_prev);
+      for (int b = 0; b < qc; ++b) out_counts[static_cast<size_t>(s) * nq + b0 + b] = static_cast<int>(n_prev);
+      off += ks[s];
+    }
+  }
+  CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->h_out_scores, c->d_out_scores.p, out_n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->h_out_ids, c->d_out_ids.p, out_n * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  memcpy(out_scores, c->h_out_scores, out_n * sizeof(float));
+  memcpy(out_ids, c->h_out_ids, out_n * sizeof(long long));
+  cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1);
+  if (timed) cudaEventElapsedTime(&c->last_ms[1], c->evk0, c->evk1);
   return 0;
 }
 

@@ -319,6 +319,61 @@ class GpuCorpus:
             off += int(stages[s][2])
         return out
 
+    def search_multistage_batch(
+        self,
+        stages: Sequence[Tuple[str, bool, int]],
+        queries: Sequence,
+        normalize: bool = True,
+        stage_queries: Optional[Sequence[Sequence]] = None,
+    ) -> List[List[Tuple[np.ndarray, np.ndarray]]]:
+        """`search_multistage` for a batch of independent queries in ONE native call / host synchronisation
+        (BASELINE configs[2]: 256 queries). queries: sequence of [Q_b,128] matrices (ragged). stage_queries:
+        optional, per query a sequence of one matrix per stage (e.g. the mean-pooled prefetch vector and the
+        token matrix, two_stage.py:142,159). Returns, per query, the per-stage (scores, ids) lists."""
+        ns = len(stages)
+        if stage_queries is not None:
+            mats = []
+            for sq in stage_queries:
+                if len(sq) != ns:
+                    raise ValueError("stage_queries must have one entry per stage for every query")
+                mats.extend(_as_f32_query(x) for x in sq)
+            nq = len(stage_queries)
+            per_stage = 1
+        else:
+            mats = [_as_f32_query(x) for x in queries]
+            nq = len(mats)
+            per_stage = 0
+        if nq == 0:
+            return []
+        rows = np.ascontiguousarray(np.concatenate(mats, axis=0))
+        offs = np.ascontiguousarray(np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])]).astype(np.int32))
+        names = (C.c_char_p * ns)(*[s[0].encode() for s in stages])
+        flags = (C.c_uint32 * ns)(*[query_flags(normalize, bool(s[1])) for s in stages])
+        ks = [int(s[2]) for s in stages]
+        ks_c = (C.c_int * ns)(*ks)
+        total = int(sum(ks)) * nq
+        scores = np.empty((total,), dtype=np.float32)
+        ids = np.empty((total,), dtype=np.int64)
+        counts = np.zeros((ns * nq,), dtype=np.int32)
+        N.check(
+            self._lib.vrag_search_multistage_batch(
+                self._h, ns, names, flags, ks_c, nq, rows.ctypes.data_as(C.POINTER(C.c_float)),
+                offs.ctypes.data_as(C.POINTER(C.c_int)), per_stage,
+                scores.ctypes.data_as(C.POINTER(C.c_float)), ids.ctypes.data_as(C.POINTER(C.c_int64)),
+                counts.ctypes.data_as(C.POINTER(C.c_int)),
+            )
+        )
+        out: List[List[Tuple[np.ndarray, np.ndarray]]] = [[] for _ in range(nq)]
+        off = 0
+        for s in range(ns):
+            sc = scores[off : off + nq * ks[s]].reshape(nq, ks[s])
+            ii = ids[off : off + nq * ks[s]].reshape(nq, ks[s])
+            for b in range(nq):
+                m = int(counts[s * nq + b])
+                out[b].append((sc[b, :m].copy(), ii[b, :m].copy()))
+            off += nq * ks[s]
+        return out
+
     # ------------------------------------------------------------------ device-pointer variants (multi-GPU path)
     def score_dev(self, name: str, query_dev_ptr: int, n_query_rows: int, flags: int, cand_dev_ptr: int,
                   n_cand: int, out_scores_dev_ptr: int, stream: int) -> None:
