@@ -87,6 +87,53 @@ __global__ void query_prep_batch_kernel(const float* __restrict__ q, const int* 
   if (r == 0 && d == 0) q_valid_out[b] = q_eff;
 }
 
+// Dense batched scans: G = QP/QS queries share one operand image (blockIdx.y = image); image row r holds row
+// r % QS of query (image*G + r / QS), hi half at row r and lo half at row QP + r; absent rows/queries are zero.
+__global__ void query_prep_group_kernel(const float* __restrict__ q, const int* __restrict__ q_begin,
+                                        const int* __restrict__ q_end, int nq, int pool, int normalize, int QP, int QS,
+                                        uint8_t* __restrict__ qimg, long long qimg_stride,
+                                        int* __restrict__ q_valid_out) {
+  const int r = blockIdx.x;
+  const int d = threadIdx.x;
+  const int b = blockIdx.y * (QP / QS) + r / QS;
+  const int t = r % QS;
+  __shared__ float wsum[4];
+  float x = 0.0f;
+  int q_eff = 0;
+  if (b < nq) {
+    const int r0 = q_begin[b];
+    const int Q = q_end[b] - r0;
+    q_eff = pool ? 1 : Q;
+    const float* qb = q + static_cast<long long>(r0) * 128;
+    if (t < q_eff) {
+      if (pool) {
+        float s = 0.0f;
+        for (int i = 0; i < Q; ++i) s += qb[i * 128 + d];
+        x = s / static_cast<float>(Q);
+      } else {
+        x = qb[t * 128 + d];
+      }
+    }
+    if (t == 0 && d == 0) q_valid_out[b] = q_eff;
+  }
+  float ss = x * x;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  if ((d & 31) == 0) wsum[d >> 5] = ss;
+  __syncthreads();
+  if (normalize) {
+    const float nrm = sqrtf((wsum[0] + wsum[1]) + (wsum[2] + wsum[3]));
+    x = x / (nrm + 1e-8f);
+  }
+  const bool live = b < nq && t < q_eff;
+  const __half hi = __float2half_rn(x);
+  const __half lo = __float2half_rn((x - __half2float(hi)) * 2048.0f);
+  const uint32_t rows = 2u * QP;
+  uint8_t* img = qimg + blockIdx.y * qimg_stride;
+  *reinterpret_cast<__half*>(img + sw128_offset(rows, r, d)) = live ? hi : __float2half_rn(0.0f);
+  *reinterpret_cast<__half*>(img + sw128_offset(rows, QP + r, d)) = live ? lo : __float2half_rn(0.0f);
+}
+
 // ------------------------------------------------------------------------------------------------
 // inv_norm[row] = 1 / (||row||_2 + 1e-8) over fp16 rows, fp32 math (doc side of pooling.py:500).
 // 16 lanes per row, 16-byte loads.

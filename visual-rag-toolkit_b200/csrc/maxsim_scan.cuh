@@ -64,6 +64,11 @@ struct ScanParams {
   int n_groups;
   long long qimg_stride;      // bytes between consecutive groups' operand images
   const int* q_valid_arr;     // [n_groups] real query rows of each group (nullptr: q_valid for all)
+  // ---- sub-queries (dense batched scans; kernels with QS < QP). One operand image holds QP/QS queries of QS
+  // columns each (query j = columns [j*QS, (j+1)*QS) of the hi and of the lo half). Query j of the launch writes
+  // scores[j*score_stride + item]; q_valid_arr[j] = its real rows; only the first n_sub queries exist.
+  long long score_stride;
+  int n_sub;
 };
 
 template <int QP>
@@ -269,7 +274,7 @@ __device__ __forceinline__ void warp_transpose_max(float* v, int lane) {
 // PACKED fast path: the SR (power of two <= 32) lanes of a slot hold QP values each (one tile row per lane).
 // Segmented transpose-max over the slot's lanes, then sum over q. Returns the slot's score in all of its lanes.
 template <int QP, int SR>
-__device__ __forceinline__ float slot_maxsim(float* v, int lane, int q_valid) {
+__device__ __forceinline__ void slot_colmax(float* v, int lane) {
   int cnt = QP;
 #pragma unroll
   for (int off = SR / 2; off >= 1; off >>= 1) {
@@ -289,6 +294,10 @@ __device__ __forceinline__ float slot_maxsim(float* v, int lane, int q_valid) {
       v[0] = fmaxf(v[0], __shfl_xor_sync(0xffffffffu, v[0], off));
     }
   }
+}
+template <int QP, int SR>
+__device__ __forceinline__ float slot_maxsim(float* v, int lane, int q_valid) {
+  slot_colmax<QP, SR>(v, lane);
   constexpr int CF = QP >= SR ? QP / SR : 1;    // q values left per lane
   constexpr int DUP = QP >= SR ? 1 : SR / QP;   // lanes holding the same q
   const int b = lane & (SR - 1);
@@ -303,7 +312,9 @@ __device__ __forceinline__ float slot_maxsim(float* v, int lane, int q_valid) {
   return sum;
 }
 
-template <int QP, bool PACKED, bool BSW>
+// QS: columns per query inside the operand image. QS == QP: one query per image (single-query scans and BSW
+// candidate scans). QS < QP (dense batched scans): QP/QS queries share every document tile.
+template <int QP, int QS, bool PACKED, bool BSW>
 __global__ void __launch_bounds__(ScanCfg<QP>::threads(PACKED), 1)
 maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_constant__ CUtensorMap tm_rows32,
                    const __grid_constant__ CUtensorMap tm_scale128, const __grid_constant__ CUtensorMap tm_scale32,
@@ -318,6 +329,8 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   constexpr int QG = (QP + 31) / 32;           // 32-wide query groups
   constexpr int QW = QP < 32 ? QP : 32;        // queries per group
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
+  static_assert(QS == QP || ((QS == 1 || QS == 32) && QP == 128 && !BSW), "sub-query layouts: 128x1 or 4x32 columns");
+  constexpr bool MULTI = QS < QP;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -570,7 +583,21 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           if ((lane & (rep - 1)) == 0) red[ew * QP + g * 32 + (lane / rep)] = run[g * 32];
         }
         named_bar_sync(1, 128);
-        if (ew == 0) {
+        if constexpr (MULTI) {
+          // warp ew owns the 32 columns [ew*32, ew*32+32): one query of 32 columns (QS == 32) or 32 pooled queries
+          const int q = ew * 32 + lane;
+          const float m = fmaxf(fmaxf(red[q], red[QP + q]), fmaxf(red[2 * QP + q], red[3 * QP + q]));
+          const float dead = (ok && nrows > 0) ? 0.0f : -INFINITY;
+          if constexpr (QS == 32) {
+            const int qv = ew < p.n_sub ? __ldg(p.q_valid_arr + ew) : 0;
+            float sum = lane < qv ? m : 0.0f;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            if (lane == 0 && ew < p.n_sub) p.scores[ew * p.score_stride + u] = sum + dead;
+          } else {
+            if (q < p.n_sub) p.scores[q * p.score_stride + u] = m + dead;
+          }
+        } else if (ew == 0) {
           float sum = 0.0f;
 #pragma unroll
           for (int g = 0; g < QG; ++g) {
@@ -603,9 +630,75 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         const uint32_t acc = static_cast<uint32_t>(seq % ACC), accphase = static_cast<uint32_t>((seq / ACC) & 1);
         const uint32_t ta = lane_addr + acc * N;
         bool fast = false;
-        if constexpr (QP <= 32) fast = p.shfl_rows > 0;
+        if constexpr (QP <= 32 || MULTI) fast = p.shfl_rows > 0;
         if (fast) {
-          if constexpr (QP <= 32) {
+          if constexpr (MULTI) {
+            // dense batched: page j of the tile owns tile rows [j*SR, j*SR + SR); 32-column chunks of the accumulator
+            const int SR = p.shfl_rows;
+            const int slot = trow / SR, rin = trow - slot * SR;
+            const long long item = u * (kTileRows / SR) + slot;
+            const bool item_ok = item < p.n_pages;
+            mbar_wait(&tfull[acc], accphase);
+            tc_fence_after_sync();
+            float scale = 1.0f;
+            if (use_scale) {
+              mbar_wait(&full[stage], phase);
+              scale = sScale[stage * kScaleStride + trow + (sMis[stage * 4] & 3)];
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < QP; c0 += 32) {
+              float v[32];
+#pragma unroll
+              for (int c = 0; c < 32; c += 8) {
+                uint32_t hi[8], lo[8];
+                tmem_ld_x8(ta + c0 + c, hi);
+                tmem_ld_x8(ta + QP + c0 + c, lo);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  v[c + j] = item_ok ? fmaf(__uint_as_float(lo[j]), kInvLo, __uint_as_float(hi[j])) * scale : -INFINITY;
+              }
+              if (c0 + 32 >= QP) {   // last chunk read: release the accumulator and the scale rows
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) {
+                  mbar_arrive(&tempty[acc]);
+                  mbar_arrive(&empty[stage]);
+                }
+              }
+              if constexpr (QS == 32) {
+                const int j = c0 >> 5;
+                const int qv = j < p.n_sub ? __ldg(p.q_valid_arr + j) : 0;
+                float sum;
+                switch (SR) {
+                  case 32: sum = slot_maxsim<32, 32>(v, lane, qv); break;
+                  case 16: sum = slot_maxsim<32, 16>(v, lane, qv); break;
+                  case 8: sum = slot_maxsim<32, 8>(v, lane, qv); break;
+                  case 4: sum = slot_maxsim<32, 4>(v, lane, qv); break;
+                  case 2: sum = slot_maxsim<32, 2>(v, lane, qv); break;
+                  default: sum = slot_maxsim<32, 1>(v, lane, qv); break;
+                }
+                if (rin == 0 && item_ok && j < p.n_sub) p.scores[j * p.score_stride + item] = sum;
+              } else {
+                // pooled queries: every column is a query. After the segmented butterfly lane b of a slot holds the
+                // column maxima of columns (b*32/SR) .. +32/SR.
+                switch (SR) {
+                  case 32: slot_colmax<32, 32>(v, lane); break;
+                  case 16: slot_colmax<32, 16>(v, lane); break;
+                  case 8: slot_colmax<32, 8>(v, lane); break;
+                  case 4: slot_colmax<32, 4>(v, lane); break;
+                  case 2: slot_colmax<32, 2>(v, lane); break;
+                  default: break;
+                }
+                const int cf = 32 / SR;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const int q = c0 + rin * cf + i;
+                  if (i < cf && item_ok && q < p.n_sub) p.scores[q * p.score_stride + item] = v[i];
+                }
+              }
+            }
+          } else if constexpr (QP <= 32) {
             // fast path: page j of the tile owns tile rows [j*SR, j*SR + nr)
             const int SR = p.shfl_rows;
             const int slot = trow / SR, rin = trow - slot * SR;
@@ -735,9 +828,24 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
                 m0 = fmaxf(m0, fmaxf(a0, a1));
                 m1 = fmaxf(m1, fmaxf(a2, a3));
               }
-              if (q < q_valid) sum += fmaxf(m0, m1);
+              if constexpr (MULTI) {
+                // sg is warp-uniform here (QW == 32): every 32-column group is one query (QS == 32) or 32 pooled queries
+                const float m = fmaxf(m0, m1);
+                if constexpr (QS == 32) {
+                  const int qv = g < p.n_sub ? __ldg(p.q_valid_arr + g) : 0;
+                  float sg_sum = ql < qv ? m : 0.0f;
+#pragma unroll
+                  for (int off = 16; off >= 1; off >>= 1) sg_sum += __shfl_xor_sync(0xffffffffu, sg_sum, off);
+                  if (ql == 0 && g < p.n_sub) p.scores[g * p.score_stride + item] = nonempty ? sg_sum : -INFINITY;
+                } else {
+                  if (q < p.n_sub) p.scores[q * p.score_stride + item] = nonempty ? m : -INFINITY;
+                }
+              } else {
+                if (q < q_valid) sum += fmaxf(m0, m1);
+              }
             }
           }
+          if constexpr (MULTI) continue;
 #pragma unroll
           for (int off = QW / 2; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
           if (sg < nseg && ql == 0) scores_g[item] = nonempty ? sum : -INFINITY;

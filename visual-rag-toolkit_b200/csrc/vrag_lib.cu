@@ -448,9 +448,9 @@ extern "C" int vrag_store_drop(vrag_corpus_t* c, const char* name) {
 }
 
 // ------------------------------------------------------------------------------------------------ launches
-template <int QP, bool PACKED, bool BSW = false>
+template <int QP, bool PACKED, bool BSW = false, int QS = QP>
 static int launch_scan_t(vrag_corpus* c, const Store& s, const ScanParams& p, long long n_units, cudaStream_t st) {
-  auto kern = maxsim_scan_kernel<QP, PACKED, BSW>;
+  auto kern = maxsim_scan_kernel<QP, QS, PACKED, BSW>;
   const size_t smem = ScanCfg<QP>::smem_bytes(PACKED, BSW);
   static bool attr_done[8] = {false};  // per device
   if (!attr_done[c->device & 7]) {
@@ -466,7 +466,8 @@ static int launch_scan_t(vrag_corpus* c, const Store& s, const ScanParams& p, lo
 
 // Work layout of one scan over store `s`: every page (d_cand == nullptr) or n_items candidate ids (per query group).
 static void fill_scan_params(vrag_corpus* c, const Store& s, const long long* d_cand, int64_t n_items, int QP,
-                             bool normalize, float* d_scores, ScanParams* out, long long* n_units_out) {
+                             bool normalize, float* d_scores, ScanParams* out, long long* n_units_out,
+                             bool multi = false) {
   ScanParams& p = *out;
   memset(&p, 0, sizeof(p));
   p.offsets = s.offsets;
@@ -493,7 +494,7 @@ static void fill_scan_params(vrag_corpus* c, const Store& s, const long long* d_
       p.pages_per_tile = static_cast<int>(kTileRows / s.fixed_rows);
       p.n_tiles = (s.n_pages + p.pages_per_tile - 1) / p.pages_per_tile;
       const bool pow2 = (s.fixed_rows & (s.fixed_rows - 1)) == 0;
-      if (pow2 && s.fixed_rows <= 32 && QP <= 32) p.shfl_rows = static_cast<int>(s.fixed_rows);
+      if (pow2 && s.fixed_rows <= 32 && (QP <= 32 || multi)) p.shfl_rows = static_cast<int>(s.fixed_rows);
     } else {
       p.tile_page0 = s.tile_page0;
       p.tile_row0 = s.tile_row0;
@@ -584,6 +585,47 @@ static int launch_scan_batch(vrag_corpus* c, const Store& s, const float* d_quer
   if (QP == 32) r = s.packed ? launch_scan_t<32, true, true>(c, s, p, n_units, st) : launch_scan_t<32, false, true>(c, s, p, n_units, st);
   else r = s.packed ? launch_scan_t<64, true, true>(c, s, p, n_units, st) : launch_scan_t<64, false, true>(c, s, p, n_units, st);
   return r;
+}
+
+// Dense batched scan: every query scores every page of the store; G = 128/QS queries share each document tile
+// (QS = 1: pooled / single-row queries, 128 per launch; QS = 32: up to 32 token rows, 4 per launch).
+// d_scores is [nq][n_pages]. Returns 2 when the shape is not covered (caller falls back to one launch per query).
+static int launch_scan_dense_batch(vrag_corpus* c, const Store& s, const float* d_queries, const int* d_qbegin,
+                                   const int* d_qend, int* d_qvalid, int nq, int max_q_eff, uint32_t flags,
+                                   float* d_scores, cudaStream_t st, bool time_kernel) {
+  const bool pool = (flags & VRAG_Q_POOL) != 0;
+  const bool normalize = (flags & VRAG_Q_NORMALIZE) != 0;
+  const int q_eff = pool ? 1 : max_q_eff;
+  if (q_eff > 32 || nq < 2) return 2;
+  if (s.n_pages == 0) return 0;
+  if (s.total_rows == 0) return fail("store is empty");
+  const int QP = 128;
+  const int QS = q_eff == 1 ? 1 : 32;
+  const int G = QP / QS;
+  const int n_img = (nq + G - 1) / G;
+  const size_t img = static_cast<size_t>(2 * QP) * 256;
+  TRY(c->d_qimg_batch.ensure(img * n_img));
+  query_prep_group_kernel<<<dim3(QP, n_img), 128, 0, st>>>(d_queries, d_qbegin, d_qend, nq, pool ? 1 : 0, normalize ? 1 : 0,
+                                                           QP, QS, c->d_qimg_batch.p, static_cast<long long>(img), d_qvalid);
+  c->launches++;
+  if (time_kernel) CUDA_OK(cudaEventRecord(c->evk0, st));
+  for (int g = 0; g < n_img; ++g) {
+    ScanParams p;
+    long long n_units = 0;
+    fill_scan_params(c, s, nullptr, s.n_pages, QP, normalize, d_scores + static_cast<size_t>(g) * G * s.n_pages, &p, &n_units,
+                     true);
+    p.qimg = c->d_qimg_batch.p + img * g;
+    p.q_valid = QS;
+    p.q_valid_arr = d_qvalid + g * G;
+    p.score_stride = s.n_pages;
+    p.n_sub = std::min(G, nq - g * G);
+    int r;
+    if (QS == 1) r = s.packed ? launch_scan_t<128, true, false, 1>(c, s, p, n_units, st) : launch_scan_t<128, false, false, 1>(c, s, p, n_units, st);
+    else r = s.packed ? launch_scan_t<128, true, false, 32>(c, s, p, n_units, st) : launch_scan_t<128, false, false, 32>(c, s, p, n_units, st);
+    if (r) return r;
+  }
+  if (time_kernel) CUDA_OK(cudaEventRecord(c->evk1, st));
+  return 0;
 }
 
 // Exact top-k of d_scores[batch][n] -> (out_scores[batch][k], out_ids[batch][k]) sorted descending, ties -> lower
@@ -871,7 +913,12 @@ extern "C" int vrag_search_multistage_batch(vrag_corpus_t* c, int n_stages, cons
       const int64_t n_items = (s == 0) ? n_pages : ks[s - 1];   // candidate lists keep the full stride; missing ids are -1
       if (n_prev > 0) {
         int r = 2;
-        if (s > 0) {
+        if (s == 0) {
+          r = launch_scan_dense_batch(c, *st[s], c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows[s], flags[s],
+                                      c->d_scores.p, c->stream, !timed);
+          if (r == 1) return r;
+          if (r == 0) timed = true;
+        } else {
           if (!timed) CUDA_OK(cudaEventRecord(c->evk0, c->stream));
           r = launch_scan_batch(c, *st[s], c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows[s], flags[s], d_prev_ids,
                                 n_items, c->d_scores.p, c->stream);
