@@ -458,3 +458,31 @@ def test_dense_batched_scan_equals_single_query_scan(corpus, layout, pool):
             want = MO.multistage(q, [(docs, pool, n)])[0]
             _same_ranking(ids.tolist(), sc, want)
     corpus.drop_store("db")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout,pool,k", [("fixed1", True, 1000), ("fixed32", False, 256), ("fixed32", True, 300),
+                                           ("fixed300", False, 500)])
+def test_fused_topk_prefilter_is_exact(corpus, layout, pool, k, monkeypatch):
+    """Large dense batched stage: the sample-threshold prefilter (scores never written to HBM) must return exactly
+    the lists of the unfiltered path (VRAG_PREFILTER=0), which the tests above pin to the oracle."""
+    rng = np.random.default_rng(5)
+    r = int(layout[5:])
+    n = 300_000 if r <= 32 else 270_000
+    corpus.add_synthetic_store("pf", n, fixed_rows=r, seed=11)
+    queries = [rng.standard_normal((int(rng.integers(8, 33)), 128)).astype(np.float32) for _ in range(9)]
+    stages = [("pf", pool, k)]
+    got = corpus.search_multistage_batch(stages, queries)
+    monkeypatch.setenv("VRAG_PREFILTER", "0")
+    want = corpus.search_multistage_batch(stages, queries)
+    monkeypatch.delenv("VRAG_PREFILTER")
+    for g, w in zip(got, want):
+        assert len(g[0][1]) == k
+        assert g[0][1].tolist() == w[0][1].tolist()
+        np.testing.assert_array_equal(g[0][0], w[0][0])
+    # spot check against the oracle on the best page of the first query
+    best = int(got[0][0][1][0])
+    page = corpus.read_page("pf", best).astype(np.float32)
+    q = queries[0].mean(axis=0, keepdims=True) if pool else queries[0]
+    assert abs(MO.maxsim_score(q, page) - float(got[0][0][0][0])) <= RTOL * abs(float(got[0][0][0][0])) + ATOL
+    corpus.drop_store("pf")

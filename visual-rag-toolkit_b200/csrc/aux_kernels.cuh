@@ -523,6 +523,27 @@ __global__ void __launch_bounds__(1024) sel_ties_kernel(const SelArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused top-k prefilter helpers (dense batched scans). thr[b] = the m-th best score of query b's sample.
+__global__ void prefilter_thr_kernel(const float* __restrict__ sample_top, int m, int batch, float* __restrict__ thr,
+                                     int* __restrict__ cnt) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < batch) {
+    thr[b] = sample_top[static_cast<long long>(b) * m + (m - 1)];
+    cnt[b] = 0;
+  }
+}
+// The candidate list of query b is usable iff it holds at least `need` and at most `cap` entries; otherwise the
+// estimate failed and the host reruns the batch with the exact (unfiltered) path. Counts are clamped to cap.
+__global__ void prefilter_check_kernel(int* __restrict__ cnt, int batch, int need, int cap, int* __restrict__ flag) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < batch) {
+    const int c = cnt[b];
+    if (c < need || c > cap) atomicOr(flag, 1);
+    if (c > cap) cnt[b] = cap;
+  }
+}
+
 __global__ void sel_init_kernel(SelState* st, int k, int batch) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < batch) {

@@ -69,7 +69,24 @@ struct ScanParams {
   // scores[j*score_stride + item]; q_valid_arr[j] = its real rows; only the first n_sub queries exist.
   long long score_stride;
   int n_sub;
+  // ---- dense scans only: sampling and fused top-k prefilter
+  int tile_stride;            // >= 1. > 1: only every tile_stride-th unit (LARGE: page, PACKED fixed rows: tile) is
+                              //   scored and scores are written compactly (sample pass of the threshold estimate)
+  const float* f_thr;         // != nullptr (QS < QP kernels): instead of writing the score matrix, append
+  int* f_cnt;                 //   (score, page) keys of scores > f_thr[j] to f_keys[j*f_cap + atomicAdd(f_cnt[j])]
+  unsigned long long* f_keys; //   key = order-preserving score bits << 32 | ~page index (same as the top-k kernels)
+  int f_cap;
 };
+
+__device__ __forceinline__ unsigned long long score_key(float f, uint32_t idx) {
+  uint32_t o;
+  if (f != f) o = 0u;
+  else {
+    const uint32_t u = __float_as_uint(f);
+    o = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  }
+  return (static_cast<unsigned long long>(o) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - idx);
+}
 
 template <int QP>
 struct ScanCfg {
@@ -115,7 +132,7 @@ __device__ __forceinline__ bool resolve_page(const ScanParams& p, long long page
   return true;
 }
 __device__ __forceinline__ long long item_page(const ScanParams& p, long long item, int g = 0) {
-  return p.cand ? (__ldg(p.cand + g * p.n_items + item) - p.cand_base) : item;
+  return p.cand ? (__ldg(p.cand + g * p.n_items + item) - p.cand_base) : item * p.tile_stride;
 }
 
 // Work units of one CTA. One group: units blockIdx.x, +gridDim.x, ... (neighbouring CTAs stream neighbouring
@@ -157,7 +174,7 @@ __device__ __forceinline__ void packed_tile_meta(const ScanParams& p, int g, lon
   if (!p.slot_mode) {
     m.cnt = 1;
     if (p.fixed_rows > 0) {
-      const long long pg0 = u * p.pages_per_tile;
+      const long long pg0 = u * p.tile_stride * p.pages_per_tile;
       const long long pg1 = min(pg0 + p.pages_per_tile, p.n_pages);
       m.r0[0] = pg0 * p.fixed_rows;
       m.nr[0] = static_cast<int>((pg1 - pg0) * p.fixed_rows);
@@ -349,6 +366,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   int* sMis = reinterpret_cast<int*>(misc + 256);                 // [STAGES][4] scale misalignment per slot
   float* sRed = reinterpret_cast<float*>(misc + 512);             // LARGE: [2][4][QP]
   int* sSeg = reinterpret_cast<int*>(misc + 512);                 // PACKED: [EPI_GROUPS][3][128] ints (item, begin, end)
+  float* sThr = reinterpret_cast<float*>(misc + 7168);            // QS < QP: [128] prefilter thresholds
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -380,39 +398,127 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
     for (int i = threadIdx.x; i < Cfg::B_BYTES / 16; i += NTHREADS) dst[i] = __ldg(src + i);
     fence_proxy_async_smem();
   }
+  if constexpr (QS < QP) {
+    if (p.f_thr && threadIdx.x < 128) sThr[threadIdx.x] = static_cast<int>(threadIdx.x) < p.n_sub ? __ldg(p.f_thr + threadIdx.x) : INFINITY;
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // QS < QP kernels: deliver the score of (query j of the launch, page): into the score matrix at column `col`, or,
+  // with the prefilter on, into query j's candidate list when it beats the query's threshold.
+  auto emit = [&](int j, long long col, long long page, float val) {
+    if (p.f_thr) {
+      if (val > sThr[j]) {
+        const int pos = atomicAdd(p.f_cnt + j, 1);
+        if (pos < p.f_cap) p.f_keys[static_cast<long long>(j) * p.f_cap + pos] = score_key(val, static_cast<uint32_t>(page));
+      }
+    } else {
+      p.scores[j * p.score_stride + col] = val;
+    }
+  };
 
   // Work units of this CTA (LARGE: items, PACKED: tiles)
   const UnitRange ur = unit_range(p, PACKED ? p.n_tiles : p.n_items);
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+    uint32_t stage = 0, phase = 0;
+    int cur_g = -1, n_sw = -1;
+    // BSW: entering query group g -> fill the other operand buffer once its previous MMAs retired (lane 0 only)
+    auto switch_group = [&](int g) {
+      if constexpr (BSW) {
+        if (g != cur_g) {
+          ++n_sw;
+          const int slot = n_sw & 1;
+          if (n_sw >= 2) mbar_wait(&bempty[slot], ((n_sw >> 1) - 1) & 1);
+          bulk_load(sB + slot * Cfg::B_BYTES, p.qimg + g * p.qimg_stride, Cfg::B_BYTES, &bfull[slot]);
+          mbar_arrive_expect_tx(&bfull[slot], Cfg::B_BYTES);
+          cur_g = g;
+        }
+      }
+    };
+    bool slot_path = false;
+    if constexpr (PACKED) slot_path = p.slot_mode != 0;
+    if (slot_path) {
+      if constexpr (PACKED) {
+        // Slot mode (gathered pages, one slot per item): item -> candidate id -> page offsets is a chain of dependent
+        // global loads (~2 us). The whole warp resolves 32 items at a time (lane l: item l of the batch), one batch
+        // ahead of the tiles being issued, so the chain is off the TMA issue path.
+        const int per_tile = kTileRows / p.slot_rows;          // 4, 2 or 1 items per tile
+        const int tiles_per_batch = 32 / per_tile;
+        auto resolve_batch = [&](long long i0, long long& r0, int& nr) {
+          const long long i = i0 + lane / per_tile;
+          r0 = 0;
+          nr = 0;
+          if (i < ur.count) {
+            int g;
+            long long u;
+            ur.decode(i, g, u);
+            const long long it = u * per_tile + (lane % per_tile);
+            if (it < p.n_items) resolve_page(p, item_page(p, it, g), r0, nr);
+          }
+        };
+        long long cur_r0, nxt_r0;
+        int cur_nr, nxt_nr;
+        resolve_batch(0, cur_r0, cur_nr);
+        for (long long i0 = 0; i0 < ur.count; i0 += tiles_per_batch) {
+          resolve_batch(i0 + tiles_per_batch, nxt_r0, nxt_nr);
+          for (int t = 0; t < tiles_per_batch; ++t) {
+            if (i0 + t >= ur.count) break;   // warp-uniform
+            long long r0j[4];
+            int nrj[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int src = (t * per_tile + j) & 31;
+              r0j[j] = __shfl_sync(0xffffffffu, cur_r0, src);
+              nrj[j] = __shfl_sync(0xffffffffu, cur_nr, src);
+              if (j >= per_tile) nrj[j] = 0, r0j[j] = 0;
+            }
+            if (lane == 0) {
+              int g;
+              long long u;
+              ur.decode(i0 + t, g, u);
+              switch_group(g);
+              mbar_wait(&empty[stage], phase ^ 1);
+              uint8_t* a = sA + stage * kTileBytes;
+              float* sc = sScale + stage * kScaleStride;
+              uint32_t bytes = 0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (nrj[j] > 0)
+                  bytes += issue_rows(a, sc + j * (p.slot_rows + 32), &full[stage], &tm_rows128, &tm_rows32, &tm_scale128,
+                                      &tm_scale32, r0j[j], nrj[j], j * p.slot_rows, use_scale);
+                // low 2 bits: scale misalignment; rest: rows of the slot (0 for unused / empty slots)
+                sMis[stage * 4 + j] = static_cast<int>(r0j[j] & 3) | (nrj[j] << 2);
+              }
+              mbar_arrive_expect_tx(&full[stage], bytes);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          cur_r0 = nxt_r0;
+          cur_nr = nxt_nr;
+        }
+      }
+    } else if (lane == 0) {
       PackedTileMeta cur, nxt;
       cur.cnt = nxt.cnt = 0;
-      int cur_g = -1, n_sw = -1;
+      long long row0 = 0, row0_n = 0;
+      int nrows = 0, nrows_n = 0;
       for (long long i = 0; i < ur.count; ++i) {
         int g;
         long long u;
         ur.decode(i, g, u);
-        if constexpr (BSW) {
-          if (g != cur_g) {   // next query group: fill the other operand buffer once its previous MMAs retired
-            ++n_sw;
-            const int slot = n_sw & 1;
-            if (n_sw >= 2) mbar_wait(&bempty[slot], ((n_sw >> 1) - 1) & 1);
-            bulk_load(sB + slot * Cfg::B_BYTES, p.qimg + g * p.qimg_stride, Cfg::B_BYTES, &bfull[slot]);
-            mbar_arrive_expect_tx(&bfull[slot], Cfg::B_BYTES);
-            cur_g = g;
-          }
-        }
+        switch_group(g);
         if constexpr (!PACKED) {
-          long long row0;
-          int nrows;
-          resolve_page(p, item_page(p, u, g), row0, nrows);
+          // the next item's row range is resolved before this item's tiles are issued (dependent global loads)
+          if (i == 0) resolve_page(p, item_page(p, u, g), row0, nrows);
+          if (i + 1 < ur.count) {
+            int gn;
+            long long un;
+            ur.decode(i + 1, gn, un);
+            resolve_page(p, item_page(p, un, gn), row0_n, nrows_n);
+          }
           for (int t0 = 0; t0 < nrows; t0 += kTileRows) {
             const int rows = min(kTileRows, nrows - t0);
             mbar_wait(&empty[stage], phase ^ 1);
@@ -426,9 +532,10 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             mbar_arrive_expect_tx(&full[stage], bytes);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+          row0 = row0_n;
+          nrows = nrows_n;
         } else {
-          // tile metadata (row ranges) is loaded one tile ahead so the dependent global loads (candidate id ->
-          // page offsets) overlap the previous tile instead of stalling the TMA issue
+          // dense: the tile's pages are contiguous rows -> one fetch; the row range is loaded one tile ahead
           if (i == 0) packed_tile_meta(p, g, u, cur);
           if (i + 1 < ur.count) {
             int gn;
@@ -440,23 +547,10 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           uint8_t* a = sA + stage * kTileBytes;
           float* sc = sScale + stage * kScaleStride;
           uint32_t bytes = 0;
-          if (!p.slot_mode) {
-            // dense: the tile's pages are contiguous rows -> one fetch
-            if (cur.nr[0] > 0)
-              bytes = issue_rows(a, sc, &full[stage], &tm_rows128, &tm_rows32, &tm_scale128, &tm_scale32, cur.r0[0],
-                                 cur.nr[0], 0, use_scale);
-            sMis[stage * 4] = static_cast<int>(cur.r0[0] & 3);
-          } else {
-            // slot mode (candidate lists): each item occupies its own slot
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (j < cur.cnt && cur.nr[j] > 0)
-                bytes += issue_rows(a, sc + j * (p.slot_rows + 32), &full[stage], &tm_rows128, &tm_rows32,
-                                    &tm_scale128, &tm_scale32, cur.r0[j], cur.nr[j], j * p.slot_rows, use_scale);
-              // low 2 bits: scale misalignment; rest: rows of the slot (0 for unused slots)
-              sMis[stage * 4 + j] = (j < cur.cnt) ? (static_cast<int>(cur.r0[j] & 3) | (cur.nr[j] << 2)) : 0;
-            }
-          }
+          if (cur.nr[0] > 0)
+            bytes = issue_rows(a, sc, &full[stage], &tm_rows128, &tm_rows32, &tm_scale128, &tm_scale32, cur.r0[0],
+                               cur.nr[0], 0, use_scale);
+          sMis[stage * 4] = static_cast<int>(cur.r0[0] & 3);
           mbar_arrive_expect_tx(&full[stage], bytes);
           cur = nxt;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -593,9 +687,9 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             float sum = lane < qv ? m : 0.0f;
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-            if (lane == 0 && ew < p.n_sub) p.scores[ew * p.score_stride + u] = sum + dead;
+            if (lane == 0 && ew < p.n_sub) emit(ew, u, u * p.tile_stride, sum + dead);
           } else {
-            if (q < p.n_sub) p.scores[q * p.score_stride + u] = m + dead;
+            if (q < p.n_sub) emit(q, u, u * p.tile_stride, m + dead);
           }
         } else if (ew == 0) {
           float sum = 0.0f;
@@ -636,15 +730,27 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             // dense batched: page j of the tile owns tile rows [j*SR, j*SR + SR); 32-column chunks of the accumulator
             const int SR = p.shfl_rows;
             const int slot = trow / SR, rin = trow - slot * SR;
-            const long long item = u * (kTileRows / SR) + slot;
-            const bool item_ok = item < p.n_pages;
+            const long long item = u * (kTileRows / SR) + slot;                   // score column (compact when sampling)
+            const long long page = u * p.tile_stride * (kTileRows / SR) + slot;   // page (slot mode: item) scored
+            int nr = 0;
+            bool item_ok;
+            if (!p.slot_mode) {
+              item_ok = page < p.n_pages;
+              nr = item_ok ? SR : 0;
+            } else {
+              item_ok = item < p.n_items;
+            }
             mbar_wait(&tfull[acc], accphase);
             tc_fence_after_sync();
+            mbar_wait(&full[stage], phase);   // acquire the producer's per-slot metadata and the scale rows
+            if (p.slot_mode) nr = item_ok ? (sMis[stage * 4 + slot] >> 2) : 0;   // slot == 32-row slot here (SR == 32)
             float scale = 1.0f;
             if (use_scale) {
-              mbar_wait(&full[stage], phase);
-              scale = sScale[stage * kScaleStride + trow + (sMis[stage * 4] & 3)];
+              const int sslot = trow / p.slot_rows;
+              scale = sScale[stage * kScaleStride + sslot * (p.slot_rows + 32) + (trow - sslot * p.slot_rows) +
+                             (sMis[stage * 4 + sslot] & 3)];
             }
+            const bool live = rin < nr;
 #pragma unroll 1
             for (int c0 = 0; c0 < QP; c0 += 32) {
               float v[32];
@@ -656,7 +762,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                  v[c + j] = item_ok ? fmaf(__uint_as_float(lo[j]), kInvLo, __uint_as_float(hi[j])) * scale : -INFINITY;
+                  v[c + j] = live ? fmaf(__uint_as_float(lo[j]), kInvLo, __uint_as_float(hi[j])) * scale : -INFINITY;
               }
               if (c0 + 32 >= QP) {   // last chunk read: release the accumulator and the scale rows
                 tc_fence_before_sync();
@@ -678,7 +784,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
                   case 2: sum = slot_maxsim<32, 2>(v, lane, qv); break;
                   default: sum = slot_maxsim<32, 1>(v, lane, qv); break;
                 }
-                if (rin == 0 && item_ok && j < p.n_sub) p.scores[j * p.score_stride + item] = sum;
+                if (rin == 0 && item_ok && j < p.n_sub) emit(j, item, page, sum);
               } else {
                 // pooled queries: every column is a query. After the segmented butterfly lane b of a slot holds the
                 // column maxima of columns (b*32/SR) .. +32/SR.
@@ -694,7 +800,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                   const int q = c0 + rin * cf + i;
-                  if (i < cf && item_ok && q < p.n_sub) p.scores[q * p.score_stride + item] = v[i];
+                  if (i < cf && item_ok && q < p.n_sub) emit(q, item, page, v[i]);
                 }
               }
             }
@@ -836,9 +942,9 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
                   float sg_sum = ql < qv ? m : 0.0f;
 #pragma unroll
                   for (int off = 16; off >= 1; off >>= 1) sg_sum += __shfl_xor_sync(0xffffffffu, sg_sum, off);
-                  if (ql == 0 && g < p.n_sub) p.scores[g * p.score_stride + item] = nonempty ? sg_sum : -INFINITY;
+                  if (ql == 0 && g < p.n_sub) emit(g, item, item, nonempty ? sg_sum : -INFINITY);
                 } else {
-                  if (q < p.n_sub) p.scores[q * p.score_stride + item] = nonempty ? m : -INFINITY;
+                  if (q < p.n_sub) emit(q, item, item, nonempty ? m : -INFINITY);
                 }
               } else {
                 if (q < q_valid) sum += fmaxf(m0, m1);

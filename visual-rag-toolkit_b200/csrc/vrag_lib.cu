@@ -135,6 +135,12 @@ struct vrag_corpus {
   DevBuf<int> d_counts;
   DevBuf<uint8_t> d_qimg_batch;   // batched search: one operand image per query
   DevBuf<int> d_qmeta;            // batched search: [n_stages][2][nq] query row ranges + [nq] effective rows
+  DevBuf<float> d_fthr, d_ftop;   // prefilter: thresholds [nq], sample top-m scores [nq][m]
+  DevBuf<long long> d_ftop_ids;
+  DevBuf<int> d_fcnt;             // prefilter: candidate counts [nq] + flag [1]
+  DevBuf<unsigned long long> d_fkeys;   // prefilter: candidate keys [nq][cap]
+  int* h_flag = nullptr;          // pinned
+  int64_t prefilter_runs = 0, prefilter_fallbacks = 0;
   int* h_qmeta = nullptr;         // pinned staging of d_qmeta
   size_t h_qmeta_cap = 0;
   size_t h_query_cap = 0;         // rows
@@ -189,6 +195,8 @@ extern "C" int vrag_corpus_create(int device, int64_t page_base, vrag_corpus_t**
   CUDA_OK(cudaMallocHost(&c->h_query, kMaxQueryRows * 128 * sizeof(float)));
   c->h_query_cap = kMaxQueryRows;
   CUDA_OK(cudaMallocHost(&c->h_counts, kMaxStages * sizeof(int)));
+  CUDA_OK(cudaMallocHost(&c->h_flag, sizeof(int)));
+  *c->h_flag = 0;
   TRY(c->d_query.ensure(kMaxQueryRows * 128));
   TRY(c->d_qimg.ensure(256 * 256));
   TRY(c->d_counts.ensure(kMaxStages));
@@ -214,6 +222,12 @@ extern "C" int vrag_corpus_destroy(vrag_corpus_t* c) {
   c->d_counts.release();
   c->d_qimg_batch.release();
   c->d_qmeta.release();
+  c->d_fthr.release();
+  c->d_ftop.release();
+  c->d_ftop_ids.release();
+  c->d_fcnt.release();
+  c->d_fkeys.release();
+  if (c->h_flag) cudaFreeHost(c->h_flag);
   if (c->h_qmeta) cudaFreeHost(c->h_qmeta);
   if (c->h_query) cudaFreeHost(c->h_query);
   if (c->h_out_scores) cudaFreeHost(c->h_out_scores);
@@ -480,6 +494,7 @@ static void fill_scan_params(vrag_corpus* c, const Store& s, const long long* d_
   p.use_scale = normalize ? 1 : 0;
   p.slot_rows = kTileRows;
   p.n_groups = 1;
+  p.tile_stride = 1;
   long long n_units = n_items;
   if (s.packed) {
     const bool small_rows = s.max_rows <= 32;
@@ -495,6 +510,13 @@ static void fill_scan_params(vrag_corpus* c, const Store& s, const long long* d_
       p.n_tiles = (s.n_pages + p.pages_per_tile - 1) / p.pages_per_tile;
       const bool pow2 = (s.fixed_rows & (s.fixed_rows - 1)) == 0;
       if (pow2 && s.fixed_rows <= 32 && (QP <= 32 || multi)) p.shfl_rows = static_cast<int>(s.fixed_rows);
+    } else if (small_rows && (QP <= 32 || multi) && s.total_rows * 2 >= s.n_pages * 32) {
+      // variable pages of <= 32 rows, reasonably full: fetch every page into its own 32-row slot (the over-read of
+      // the next page's first rows hits L2) so that the segmented-butterfly epilogue applies
+      p.slot_mode = 1;
+      p.slot_rows = 32;
+      p.n_tiles = (n_items + 3) / 4;
+      p.shfl_rows = 32;
     } else {
       p.tile_page0 = s.tile_page0;
       p.tile_row0 = s.tile_row0;
@@ -590,13 +612,26 @@ static int launch_scan_batch(vrag_corpus* c, const Store& s, const float* d_quer
 // Dense batched scan: every query scores every page of the store; G = 128/QS queries share each document tile
 // (QS = 1: pooled / single-row queries, 128 per launch; QS = 32: up to 32 token rows, 4 per launch).
 // d_scores is [nq][n_pages]. Returns 2 when the shape is not covered (caller falls back to one launch per query).
+struct DenseOpts {
+  int tile_stride = 1;            // > 1: sample pass, scores written compactly as [nq][n_sample]
+  int64_t n_sample = 0;           // pages scored by the sample pass
+  const float* thr = nullptr;     // prefilter pass: per-query thresholds / counters / key lists
+  int* cnt = nullptr;
+  unsigned long long* keys = nullptr;
+  int cap = 0;
+  bool skip_prep = false;         // operand images are already in d_qimg_batch (second pass of the same queries)
+};
+static bool dense_batch_covers(int nq, int max_q_eff, uint32_t flags) {
+  const int q_eff = (flags & VRAG_Q_POOL) ? 1 : max_q_eff;
+  return q_eff <= 32 && nq >= 2;
+}
 static int launch_scan_dense_batch(vrag_corpus* c, const Store& s, const float* d_queries, const int* d_qbegin,
                                    const int* d_qend, int* d_qvalid, int nq, int max_q_eff, uint32_t flags,
-                                   float* d_scores, cudaStream_t st, bool time_kernel) {
+                                   float* d_scores, cudaStream_t st, bool time_kernel, const DenseOpts& o = DenseOpts()) {
   const bool pool = (flags & VRAG_Q_POOL) != 0;
   const bool normalize = (flags & VRAG_Q_NORMALIZE) != 0;
   const int q_eff = pool ? 1 : max_q_eff;
-  if (q_eff > 32 || nq < 2) return 2;
+  if (q_eff > 32 || nq < 1) return 2;
   if (s.n_pages == 0) return 0;
   if (s.total_rows == 0) return fail("store is empty");
   const int QP = 128;
@@ -604,21 +639,41 @@ static int launch_scan_dense_batch(vrag_corpus* c, const Store& s, const float* 
   const int G = QP / QS;
   const int n_img = (nq + G - 1) / G;
   const size_t img = static_cast<size_t>(2 * QP) * 256;
-  TRY(c->d_qimg_batch.ensure(img * n_img));
-  query_prep_group_kernel<<<dim3(QP, n_img), 128, 0, st>>>(d_queries, d_qbegin, d_qend, nq, pool ? 1 : 0, normalize ? 1 : 0,
-                                                           QP, QS, c->d_qimg_batch.p, static_cast<long long>(img), d_qvalid);
-  c->launches++;
+  if (!o.skip_prep) {
+    TRY(c->d_qimg_batch.ensure(img * n_img));
+    query_prep_group_kernel<<<dim3(QP, n_img), 128, 0, st>>>(d_queries, d_qbegin, d_qend, nq, pool ? 1 : 0, normalize ? 1 : 0,
+                                                             QP, QS, c->d_qimg_batch.p, static_cast<long long>(img), d_qvalid);
+    c->launches++;
+  }
   if (time_kernel) CUDA_OK(cudaEventRecord(c->evk0, st));
+  const int64_t stride_cols = o.tile_stride > 1 ? o.n_sample : s.n_pages;
   for (int g = 0; g < n_img; ++g) {
     ScanParams p;
     long long n_units = 0;
-    fill_scan_params(c, s, nullptr, s.n_pages, QP, normalize, d_scores + static_cast<size_t>(g) * G * s.n_pages, &p, &n_units,
-                     true);
+    fill_scan_params(c, s, nullptr, s.n_pages, QP, normalize, d_scores ? d_scores + static_cast<size_t>(g) * G * stride_cols : nullptr,
+                     &p, &n_units, true);
     p.qimg = c->d_qimg_batch.p + img * g;
     p.q_valid = QS;
     p.q_valid_arr = d_qvalid + g * G;
-    p.score_stride = s.n_pages;
+    p.score_stride = stride_cols;
     p.n_sub = std::min(G, nq - g * G);
+    if (o.tile_stride > 1) {   // sample pass: every tile_stride-th page (LARGE) / full tile (PACKED fixed rows)
+      p.tile_stride = o.tile_stride;
+      if (s.packed) {
+        const int64_t full_tiles = s.n_pages / p.pages_per_tile;
+        p.n_tiles = (full_tiles + o.tile_stride - 1) / o.tile_stride;
+        n_units = p.n_tiles;
+      } else {
+        p.n_items = (s.n_pages + o.tile_stride - 1) / o.tile_stride;
+        n_units = p.n_items;
+      }
+    }
+    if (o.thr) {
+      p.f_thr = o.thr + g * G;
+      p.f_cnt = o.cnt + g * G;
+      p.f_keys = o.keys + static_cast<size_t>(g) * G * o.cap;
+      p.f_cap = o.cap;
+    }
     int r;
     if (QS == 1) r = s.packed ? launch_scan_t<128, true, false, 1>(c, s, p, n_units, st) : launch_scan_t<128, false, false, 1>(c, s, p, n_units, st);
     else r = s.packed ? launch_scan_t<128, true, false, 32>(c, s, p, n_units, st) : launch_scan_t<128, false, false, 32>(c, s, p, n_units, st);
@@ -820,6 +875,75 @@ extern "C" int vrag_search(vrag_corpus_t* c, const char* name, const float* quer
 }
 
 
+// Sorted top-k of per-query key lists keys[batch][cap] holding n_dyn[b] valid keys each (cap <= 8192).
+static int launch_topk_keys(vrag_corpus* c, const unsigned long long* keys, const int* n_dyn, int cap, int k,
+                            int64_t id_base, float* out_scores, long long* out_ids, cudaStream_t st, int batch) {
+  int k2 = 1;
+  while (k2 < k) k2 <<= 1;
+  TopkArgs a;
+  memset(&a, 0, sizeof(a));
+  a.k = k;
+  a.keys_in = keys;
+  a.in_stride = cap;
+  a.n = cap;
+  a.n_total = cap;
+  a.n_dyn = n_dyn;
+  a.out_scores = out_scores;
+  a.out_ids = out_ids;
+  a.id_base = id_base;
+  a.out_stride = k;
+  const int chunk = cap <= 1024 ? 1024 : (cap <= 2048 ? 2048 : 8192);
+  a.k2 = std::min(k2, chunk);
+  if (chunk == 8192) TRY((launch_topk_sort<8192, 1024>(c, a, batch, st)));
+  else if (chunk == 2048) TRY((launch_topk_sort<2048, 1024>(c, a, batch, st)));
+  else TRY((launch_topk_sort<1024, 512>(c, a, batch, st)));
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Fused top-k prefilter plan for a dense batched stage (top-k of n_pages scores per query, k << n_pages):
+//   1. score a strided sample of S pages, take each query's m-th best sample score as its threshold;
+//   2. scan the whole store, keeping only (score, page) pairs above the threshold (expected ~m*n/S >= k of them);
+//   3. sort the survivors. Exact whenever every query keeps between k and cap candidates (checked on the device;
+//      otherwise the caller reruns the batch without the filter).
+// The n x nq score matrix is never written. m solves m - 5 sqrt(m) >= k*S/n (5-sigma margin on the count).
+struct PrefilterPlan {
+  bool on = false;
+  int tile_stride = 1;
+  int64_t n_sample = 0;
+  int m = 0;
+  int cap = 8192;
+};
+static PrefilterPlan plan_prefilter(const Store& s, int k, int nq, int max_q_eff, uint32_t flags) {
+  PrefilterPlan pl;
+  const char* e = getenv("VRAG_PREFILTER");
+  if (e && e[0] == '0') return pl;
+  const int64_t n = s.n_pages;
+  if (n < (1 << 18) || !dense_batch_covers(nq, max_q_eff, flags)) return pl;
+  int64_t unit_pages = 1, n_units = n;   // sampling granularity
+  if (s.packed) {
+    const bool pow2 = s.fixed_rows > 0 && (s.fixed_rows & (s.fixed_rows - 1)) == 0 && s.fixed_rows <= 32;
+    if (!pow2) return pl;
+    unit_pages = kTileRows / s.fixed_rows;
+    n_units = n / unit_pages;
+  }
+  const int64_t want = std::max<int64_t>(65536, (32 * n + k - 1) / k);   // sample size: >= 32 expected hits above the k-th score
+  if (want * 4 > n) return pl;
+  const int64_t stride = n_units / ((want + unit_pages - 1) / unit_pages);
+  if (stride < 2) return pl;
+  const int64_t sampled_units = (n_units + stride - 1) / stride;
+  pl.n_sample = sampled_units * unit_pages;
+  const double ratio = static_cast<double>(n) / pl.n_sample;
+  const double target = k / ratio;
+  int m = static_cast<int>(target) + 1;
+  while (m - 5.0 * sqrt(static_cast<double>(m)) < target) ++m;
+  if (m > kTopkMaxK || m * ratio * (1.0 + 5.0 / sqrt(static_cast<double>(m))) > pl.cap) return pl;
+  pl.m = m;
+  pl.tile_stride = static_cast<int>(stride);
+  pl.on = true;
+  return pl;
+}
+
 // ------------------------------------------------------------------------------------------------ batched queries
 static int ensure_host_query(vrag_corpus* c, size_t rows) {
   if (rows <= c->h_query_cap) return 0;
@@ -831,10 +955,10 @@ static int ensure_host_query(vrag_corpus* c, size_t rows) {
   return 0;
 }
 
-extern "C" int vrag_search_multistage_batch(vrag_corpus_t* c, int n_stages, const char* const* names,
-                                            const uint32_t* flags, const int* ks, int n_queries, const float* query_rows,
-                                            const int* q_offsets, int per_stage_queries, float* out_scores,
-                                            int64_t* out_ids, int* out_counts) {
+static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const char* const* names,
+                                        const uint32_t* flags, const int* ks, int n_queries, const float* query_rows,
+                                        const int* q_offsets, int per_stage_queries, float* out_scores,
+                                        int64_t* out_ids, int* out_counts, bool no_prefilter) {
   if (!c) return fail("corpus is NULL");
   if (n_stages < 1 || n_stages > kMaxStages) return fail("n_stages %d out of range [1,%d]", n_stages, kMaxStages);
   if (!names || !flags || !ks || !out_scores || !out_ids || !out_counts || !query_rows || !q_offsets) return fail("NULL argument");
@@ -900,6 +1024,18 @@ extern "C" int vrag_search_multistage_batch(vrag_corpus_t* c, int n_stages, cons
   int64_t need = static_cast<int64_t>(qchunk) * std::max<int64_t>(n_pages, 1);
   for (int s = 0; s + 1 < n_stages; ++s) need = std::max<int64_t>(need, static_cast<int64_t>(qchunk) * ks[s]);
   TRY(c->d_scores.ensure(need));
+  const char* pf_env = getenv("VRAG_PREFILTER");
+  PrefilterPlan plan;
+  if (!(no_prefilter || (pf_env && pf_env[0] == '0'))) plan = plan_prefilter(*st[0], ks[0], qchunk, max_rows[0], flags[0]);
+  if (plan.on) {
+    TRY(c->d_fthr.ensure(qchunk));
+    TRY(c->d_ftop.ensure(static_cast<size_t>(qchunk) * plan.m));
+    TRY(c->d_ftop_ids.ensure(static_cast<size_t>(qchunk) * plan.m));
+    TRY(c->d_fcnt.ensure(nq + 1));
+    TRY(c->d_fkeys.ensure(static_cast<size_t>(qchunk) * plan.cap));
+    CUDA_OK(cudaMemsetAsync(c->d_fcnt.p + nq, 0, sizeof(int), c->stream));
+    c->prefilter_runs++;
+  }
   CUDA_OK(cudaEventRecord(c->ev0, c->stream));
   bool timed = false;
   for (int b0 = 0; b0 < nq; b0 += qchunk) {
@@ -913,7 +1049,38 @@ extern "C" int vrag_search_multistage_batch(vrag_corpus_t* c, int n_stages, cons
       const int64_t n_items = (s == 0) ? n_pages : ks[s - 1];   // candidate lists keep the full stride; missing ids are -1
       if (n_prev > 0) {
         int r = 2;
-        if (s == 0) {
+        if (s == 0 && plan.on) {
+          // fused top-k prefilter: sample -> thresholds -> filtered scan -> sort the survivors
+          DenseOpts o;
+          o.tile_stride = plan.tile_stride;
+          o.n_sample = plan.n_sample;
+          TRY(launch_scan_dense_batch(c, *st[0], c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows[0], flags[0],
+                                      c->d_scores.p, c->stream, false, o));
+          TRY(launch_topk(c, c->d_scores.p, nullptr, 0, plan.n_sample, plan.m, c->d_ftop.p, c->d_ftop_ids.p, nullptr, nullptr,
+                          c->stream, qc));
+          prefilter_thr_kernel<<<(qc + 127) / 128, 128, 0, c->stream>>>(c->d_ftop.p, plan.m, qc, c->d_fthr.p, c->d_fcnt.p);
+          DenseOpts f;
+          f.thr = c->d_fthr.p;
+          f.cnt = c->d_fcnt.p;
+          f.keys = c->d_fkeys.p;
+          f.cap = plan.cap;
+          f.skip_prep = true;
+          TRY(launch_scan_dense_batch(c, *st[0], c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows[0], flags[0], nullptr,
+                                      c->stream, !timed, f));
+          timed = true;
+          prefilter_check_kernel<<<(qc + 127) / 128, 128, 0, c->stream>>>(c->d_fcnt.p, qc, static_cast<int>(std::min<int64_t>(ks[0], n_pages)),
+                                                                          plan.cap, c->d_fcnt.p + nq);
+          c->launches += 2;
+          float* o_sc0 = c->d_out_scores.p + static_cast<size_t>(b0) * ks[0];
+          long long* o_id0 = c->d_out_ids.p + static_cast<size_t>(b0) * ks[0];
+          TRY(launch_topk_keys(c, c->d_fkeys.p, c->d_fcnt.p, plan.cap, ks[0], c->page_base, o_sc0, o_id0, c->stream, qc));
+          d_prev_ids = o_id0;
+          n_prev = std::min<int64_t>(ks[0], n_prev);
+          for (int b = 0; b < qc; ++b) out_counts[b0 + b] = static_cast<int>(n_prev);
+          off += ks[0];
+          continue;
+        }
+        if (s == 0 && dense_batch_covers(qc, max_rows[s], flags[s])) {
           r = launch_scan_dense_batch(c, *st[s], c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows[s], flags[s],
                                       c->d_scores.p, c->stream, !timed);
           if (r == 1) return r;
@@ -947,12 +1114,28 @@ extern "C" int vrag_search_multistage_batch(vrag_corpus_t* c, int n_stages, cons
   CUDA_OK(cudaEventRecord(c->ev1, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->h_out_scores, c->d_out_scores.p, out_n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->h_out_ids, c->d_out_ids.p, out_n * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  if (plan.on) CUDA_OK(cudaMemcpyAsync(c->h_flag, c->d_fcnt.p + nq, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (plan.on && *c->h_flag) {
+    // a threshold estimate kept too few / too many candidates for some query: redo the batch with the exact path
+    *c->h_flag = 0;
+    c->prefilter_fallbacks++;
+    return search_multistage_batch_impl(c, n_stages, names, flags, ks, n_queries, query_rows, q_offsets, per_stage_queries,
+                                        out_scores, out_ids, out_counts, true);
+  }
   memcpy(out_scores, c->h_out_scores, out_n * sizeof(float));
   memcpy(out_ids, c->h_out_ids, out_n * sizeof(long long));
   cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1);
   if (timed) cudaEventElapsedTime(&c->last_ms[1], c->evk0, c->evk1);
   return 0;
+}
+
+extern "C" int vrag_search_multistage_batch(vrag_corpus_t* c, int n_stages, const char* const* names,
+                                            const uint32_t* flags, const int* ks, int n_queries, const float* query_rows,
+                                            const int* q_offsets, int per_stage_queries, float* out_scores,
+                                            int64_t* out_ids, int* out_counts) {
+  return search_multistage_batch_impl(c, n_stages, names, flags, ks, n_queries, query_rows, q_offsets, per_stage_queries,
+                                      out_scores, out_ids, out_counts, false);
 }
 
 // ------------------------------------------------------------------------------------------------ device-pointer variants
