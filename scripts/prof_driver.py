@@ -32,6 +32,27 @@ elif what == "global":
     for _ in range(reps):
         c.search("global_pooling", q20, 1000, pool_query=True)
     print("global", n, c.last_timing_ms())
+elif what == "global_batch":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+    c.add_synthetic_store("global_pooling", n, fixed_rows=1, seed=3)
+    qs = [rng.standard_normal((int(rng.integers(10, 31)), 128)).astype(np.float32) for _ in range(128)]
+    for _ in range(reps):
+        c.search_multistage_batch([("global_pooling", True, 1000)], qs)
+    print("global_batch", n, c.last_timing_ms())
+elif what == "large_batch":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 100_000
+    c.add_synthetic_store("initial", n, fixed_rows=1030, seed=1)
+    qs = [rng.standard_normal((20, 128)).astype(np.float32) for _ in range(4)]
+    for _ in range(reps):
+        c.search_multistage_batch([("initial", False, 10)], qs)
+    print("large_batch", n, c.last_timing_ms())
+elif what == "packed_batch":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 500_000
+    c.add_synthetic_store("mean_pooling", n, fixed_rows=32, seed=2)
+    qs = [rng.standard_normal((20, 128)).astype(np.float32) for _ in range(4)]
+    for _ in range(reps):
+        c.search_multistage_batch([("mean_pooling", False, 256)], qs)
+    print("packed_batch", n, c.last_timing_ms())
 elif what == "rerank":
     c.add_synthetic_store("initial", 100_000, fixed_rows=1030, seed=1)
     cand = rng.permutation(100_000)[:256]

@@ -99,18 +99,21 @@ struct ScanCfg {
   // warp per SM sub-partition; a second group per sub-partition hides its latency). One score buffer per group.
   static constexpr int EPI_GROUPS_PACKED = (QP <= 64) ? 2 : 1;
   static constexpr int MISC_BYTES = 8192;                  // barriers, reduce scratch, segment tables
-  static constexpr int epi_groups(bool packed) { return packed ? EPI_GROUPS_PACKED : 1; }
-  static constexpr int threads(bool packed) { return 64 + 128 * epi_groups(packed); }
-  static constexpr int sc_bytes(bool packed) { return packed ? EPI_GROUPS_PACKED * QP * SC_PITCH * 4 : 0; }
+  // multi (sub-query kernels, QP == 128): four epilogue groups, each owning 32 accumulator columns
+  static constexpr int epi_groups(bool packed, bool multi = false) { return multi ? 4 : (packed ? EPI_GROUPS_PACKED : 1); }
+  static constexpr int threads(bool packed, bool multi = false) { return 64 + 128 * epi_groups(packed, multi); }
+  static constexpr int sc_bytes(bool packed, bool multi = false) {
+    return packed ? (multi ? 4 * 32 : EPI_GROUPS_PACKED * QP) * SC_PITCH * 4 : 0;
+  }
   // bsw: the query operand is double-buffered so that a CTA can switch between query groups mid-kernel
-  static constexpr int stages(bool packed, bool bsw = false) {
-    const int budget = 227 * 1024 - 1024 /*align slack*/ - (bsw ? 2 : 1) * B_BYTES - MISC_BYTES - sc_bytes(packed);
+  static constexpr int stages(bool packed, bool bsw = false, bool multi = false) {
+    const int budget = 227 * 1024 - 1024 /*align slack*/ - (bsw ? 2 : 1) * B_BYTES - MISC_BYTES - sc_bytes(packed, multi);
     const int s = budget / (kTileBytes + kScaleStride * 4);
     return s > 6 ? 6 : s;
   }
-  static constexpr size_t smem_bytes(bool packed, bool bsw = false) {
-    return 1024 + size_t(stages(packed, bsw)) * (kTileBytes + kScaleStride * 4) + (bsw ? 2 : 1) * B_BYTES + MISC_BYTES +
-           sc_bytes(packed);
+  static constexpr size_t smem_bytes(bool packed, bool bsw = false, bool multi = false) {
+    return 1024 + size_t(stages(packed, bsw, multi)) * (kTileBytes + kScaleStride * 4) + (bsw ? 2 : 1) * B_BYTES +
+           MISC_BYTES + sc_bytes(packed, multi);
   }
 };
 
@@ -332,22 +335,24 @@ __device__ __forceinline__ float slot_maxsim(float* v, int lane, int q_valid) {
 // QS: columns per query inside the operand image. QS == QP: one query per image (single-query scans and BSW
 // candidate scans). QS < QP (dense batched scans): QP/QS queries share every document tile.
 template <int QP, int QS, bool PACKED, bool BSW>
-__global__ void __launch_bounds__(ScanCfg<QP>::threads(PACKED), 1)
+__global__ void __launch_bounds__(ScanCfg<QP>::threads(PACKED, QS < QP), 1)
 maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_constant__ CUtensorMap tm_rows32,
                    const __grid_constant__ CUtensorMap tm_scale128, const __grid_constant__ CUtensorMap tm_scale32,
                    const ScanParams p) {
   using Cfg = ScanCfg<QP>;
   constexpr int N = Cfg::N;
   constexpr int ACC = Cfg::ACC;
-  constexpr int STAGES = Cfg::stages(PACKED, BSW);
+  constexpr bool MULTI = QS < QP;
+  constexpr int STAGES = Cfg::stages(PACKED, BSW, MULTI);
   constexpr int NB = BSW ? 2 : 1;              // query operand buffers
-  constexpr int NTHREADS = Cfg::threads(PACKED);
-  constexpr int EPI_GROUPS = Cfg::epi_groups(PACKED);
-  constexpr int QG = (QP + 31) / 32;           // 32-wide query groups
-  constexpr int QW = QP < 32 ? QP : 32;        // queries per group
+  constexpr int NTHREADS = Cfg::threads(PACKED, MULTI);
+  constexpr int EPI_GROUPS = Cfg::epi_groups(PACKED, MULTI);
+  constexpr int QE = MULTI ? 32 : QP;          // accumulator columns one epilogue group handles
+  constexpr int QG = (QE + 31) / 32;           // 32-wide column groups per epilogue group
+  constexpr int QW = QE < 32 ? QE : 32;        // columns per 32-wide group
+  constexpr int EPI_ARRIVALS = MULTI ? 16 : 4; // epilogue warps that consume every tile
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
   static_assert(QS == QP || ((QS == 1 || QS == 32) && QP == 128 && !BSW), "sub-query layouts: 128x1 or 4x32 columns");
-  constexpr bool MULTI = QS < QP;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -355,7 +360,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   uint8_t* sB = sA + STAGES * kTileBytes;
   float* sScale = reinterpret_cast<float*>(sB + NB * Cfg::B_BYTES);
   float* sSc = sScale + STAGES * kScaleStride;                       // PACKED: [EPI_GROUPS][QP][SC_PITCH]
-  uint8_t* misc = reinterpret_cast<uint8_t*>(sSc) + Cfg::sc_bytes(PACKED);
+  uint8_t* misc = reinterpret_cast<uint8_t*>(sSc) + Cfg::sc_bytes(PACKED, MULTI);
   uint64_t* full = reinterpret_cast<uint64_t*>(misc);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
@@ -379,11 +384,11 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
     tma_prefetch_desc(&tm_scale32);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1 + 4);   // tcgen05.commit + one arrive per epilogue warp (scale rows consumed)
+      mbar_init(&empty[s], 1 + EPI_ARRIVALS);   // tcgen05.commit + one arrive per consuming epilogue warp (scale rows)
     }
     for (int a = 0; a < ACC; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], EPI_ARRIVALS);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bfull[b], 1);
@@ -609,13 +614,21 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
     }
   } else {
     // ===================================================================== epilogue (4 warps = 128 TMEM lanes per group)
-    const int grp = (warp - 2) >> 2;         // epilogue group (PACKED: groups alternate tiles)
+    // Single-query kernels: one group (LARGE) or two groups alternating tiles (PACKED). Sub-query kernels
+    // (QS < QP): four groups, group k owns accumulator columns [32k, 32k+32) of EVERY tile — one 32-column query
+    // (QS == 32) or 32 single-column queries (QS == 1) — so that each SM sub-partition has four warps to hide the
+    // TMEM-load / shuffle latency chains behind each other.
+    const int grp = (warp - 2) >> 2;         // epilogue group
     const int ew = (warp - 2) & 3;           // warp within the group
     const int lg = warp & 3;                 // TMEM lane group this warp may access
     const int trow = lg * 32 + lane;         // tile row (= TMEM lane) owned by this thread
     const int et = ew * 32 + lane;           // 0..127 thread id within the group
+    const int col0 = MULTI ? grp * 32 : 0;   // first accumulator column of this group
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
+    const uint32_t bar_id = 1 + grp;
     constexpr float kInvLo = 1.0f / kLoScale;
+    const int seq0 = MULTI ? 0 : grp, seq_step = MULTI ? 1 : EPI_GROUPS;
+    (void)seq0; (void)seq_step; (void)et;
 
     if constexpr (!PACKED) {
       uint32_t stage = 0, phase = 0, acc = 0, accphase = 0, par = 0;
@@ -623,37 +636,43 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         int g;
         long long u;
         ur.decode(i, g, u);
-        const int q_valid = p.q_valid_arr ? __ldg(p.q_valid_arr + g) : p.q_valid;
+        int q_valid;
+        if constexpr (MULTI) q_valid = (QS == 32 && grp < p.n_sub) ? __ldg(p.q_valid_arr + grp) : 0;
+        else q_valid = p.q_valid_arr ? __ldg(p.q_valid_arr + g) : p.q_valid;
         long long row0;
         int nrows;
         const bool ok = resolve_page(p, item_page(p, u, g), row0, nrows);
-        float run[QP];
+        float run[QE];
 #pragma unroll
-        for (int q = 0; q < QP; ++q) run[q] = -INFINITY;
+        for (int q = 0; q < QE; ++q) run[q] = -INFINITY;
         for (int t0 = 0; t0 < nrows; t0 += kTileRows) {
           const int valid = min(kTileRows, nrows - t0);
           mbar_wait(&tfull[acc], accphase);
           tc_fence_after_sync();
-          const uint32_t ta = lane_addr + acc * N;
+          const uint32_t ta = lane_addr + acc * N + col0;
           float scale = 1.0f;
           if (use_scale) {
             mbar_wait(&full[stage], phase);  // acquire the TMA-written scale rows
             scale = sScale[stage * kScaleStride + trow + (sMis[stage * 4] & 3)];
           }
+          // 16 columns (hi and lo) per TMEM round trip; 8 when the group has only 8 columns
+          constexpr int LW = QE >= 16 ? 16 : 8;
 #pragma unroll
-          for (int c = 0; c < QP; c += 8) {
-            uint32_t hi[8], lo[8];
-            tmem_ld_x8(ta + c, hi);
+          for (int c = 0; c < QE; c += LW) {
+            uint32_t hi[LW], lo[LW];
+            if constexpr (LW == 16) tmem_ld_x16(ta + c, hi);
+            else tmem_ld_x8(ta + c, hi);
             if (!p.hi_only) {
-              tmem_ld_x8(ta + QP + c, lo);
+              if constexpr (LW == 16) tmem_ld_x16(ta + QP + c, lo);
+              else tmem_ld_x8(ta + QP + c, lo);
             } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) lo[j] = 0u;
+              for (int j = 0; j < LW; ++j) lo[j] = 0u;
             }
             tmem_ld_wait();
             if (trow < valid) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < LW; ++j) {
                 const float s = fmaf(__uint_as_float(lo[j]), kInvLo, __uint_as_float(hi[j])) * scale;
                 run[c + j] = fmaxf(run[c + j], s);
               }
@@ -668,70 +687,70 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           if (++acc == ACC) { acc = 0; accphase ^= 1; }
         }
-        // page done: max across the 128 rows owned by the epilogue threads, then sum over q
-        float* red = sRed + par * 4 * QP;
+        // page done: max across the 128 rows owned by the group's threads, then sum over q
+        float* red = sRed + par * 4 * QP + col0;
 #pragma unroll
-        for (int g = 0; g < QG; ++g) {
-          warp_transpose_max<QW>(run + g * 32, lane);
+        for (int gq = 0; gq < QG; ++gq) {
+          warp_transpose_max<QW>(run + gq * 32, lane);
           constexpr int rep = 32 / QW;  // lanes holding the same q
-          if ((lane & (rep - 1)) == 0) red[ew * QP + g * 32 + (lane / rep)] = run[g * 32];
+          if ((lane & (rep - 1)) == 0) red[ew * QP + gq * 32 + (lane / rep)] = run[gq * 32];
         }
-        named_bar_sync(1, 128);
-        if constexpr (MULTI) {
-          // warp ew owns the 32 columns [ew*32, ew*32+32): one query of 32 columns (QS == 32) or 32 pooled queries
-          const int q = ew * 32 + lane;
-          const float m = fmaxf(fmaxf(red[q], red[QP + q]), fmaxf(red[2 * QP + q], red[3 * QP + q]));
-          const float dead = (ok && nrows > 0) ? 0.0f : -INFINITY;
-          if constexpr (QS == 32) {
-            const int qv = ew < p.n_sub ? __ldg(p.q_valid_arr + ew) : 0;
-            float sum = lane < qv ? m : 0.0f;
+        named_bar_sync(bar_id, 128);
+        if (ew == 0) {
+          if constexpr (MULTI) {
+            const float m = fmaxf(fmaxf(red[lane], red[QP + lane]), fmaxf(red[2 * QP + lane], red[3 * QP + lane]));
+            const float dead = (ok && nrows > 0) ? 0.0f : -INFINITY;
+            if constexpr (QS == 32) {
+              float sum = lane < q_valid ? m : 0.0f;
+#pragma unroll
+              for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+              if (lane == 0 && grp < p.n_sub) emit(grp, u, u * p.tile_stride, sum + dead);
+            } else {
+              if (col0 + lane < p.n_sub) emit(col0 + lane, u, u * p.tile_stride, m + dead);
+            }
+          } else {
+            float sum = 0.0f;
+#pragma unroll
+            for (int gq = 0; gq < QG; ++gq) {
+              const int q = gq * 32 + lane;
+              if (q < QP) {
+                const float m = fmaxf(fmaxf(red[q], red[QP + q]), fmaxf(red[2 * QP + q], red[3 * QP + q]));
+                if (q < q_valid) sum += m;
+              }
+            }
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-            if (lane == 0 && ew < p.n_sub) emit(ew, u, u * p.tile_stride, sum + dead);
-          } else {
-            if (q < p.n_sub) emit(q, u, u * p.tile_stride, m + dead);
+            if (lane == 0) p.scores[g * p.n_items + u] = (ok && nrows > 0) ? sum : -INFINITY;
           }
-        } else if (ew == 0) {
-          float sum = 0.0f;
-#pragma unroll
-          for (int g = 0; g < QG; ++g) {
-            const int q = g * 32 + lane;
-            if (q < QP) {
-              const float m = fmaxf(fmaxf(red[q], red[QP + q]), fmaxf(red[2 * QP + q], red[3 * QP + q]));
-              if (q < q_valid) sum += m;
-            }
-          }
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-          if (lane == 0) p.scores[g * p.n_items + u] = (ok && nrows > 0) ? sum : -INFINITY;
         }
         par ^= 1;
       }
     } else {
-      // ---------------- PACKED: several pages per tile; group `grp` handles tiles grp, grp+EPI_GROUPS, ...
+      // ---------------- PACKED: several pages per tile
       int* seg = sSeg + grp * 3 * kTileRows;
-      float* sc = sSc + grp * QP * Cfg::SC_PITCH;
-      const uint32_t bar_id = 1 + grp;
+      float* sc = sSc + grp * QE * Cfg::SC_PITCH;
       int seg_n = 0, seg_item = 0, seg_rb = 0, seg_re = 0;   // general path: this thread's entry of the tile's segment table
       bool seg_ready = false;
-      for (long long seq = grp; seq < ur.count; seq += EPI_GROUPS) {
+      for (long long seq = seq0; seq < ur.count; seq += seq_step) {
         int g;
         long long u;
         ur.decode(seq, g, u);
-        const int q_valid = p.q_valid_arr ? __ldg(p.q_valid_arr + g) : p.q_valid;
+        int q_valid;
+        if constexpr (MULTI) q_valid = (QS == 32 && grp < p.n_sub) ? __ldg(p.q_valid_arr + grp) : 0;
+        else q_valid = p.q_valid_arr ? __ldg(p.q_valid_arr + g) : p.q_valid;
         float* const scores_g = p.scores + g * p.n_items;
         const uint32_t stage = static_cast<uint32_t>(seq % STAGES), phase = static_cast<uint32_t>((seq / STAGES) & 1);
         const uint32_t acc = static_cast<uint32_t>(seq % ACC), accphase = static_cast<uint32_t>((seq / ACC) & 1);
-        const uint32_t ta = lane_addr + acc * N;
+        const uint32_t ta = lane_addr + acc * N + col0;
         bool fast = false;
-        if constexpr (QP <= 32 || MULTI) fast = p.shfl_rows > 0;
+        if constexpr (QE <= 32) fast = p.shfl_rows > 0;
         if (fast) {
-          if constexpr (MULTI) {
-            // dense batched: page j of the tile owns tile rows [j*SR, j*SR + SR); 32-column chunks of the accumulator
+          if constexpr (QE <= 32) {
+            // fast path: page j of the tile owns tile rows [j*SR, j*SR + nr)
             const int SR = p.shfl_rows;
             const int slot = trow / SR, rin = trow - slot * SR;
             const long long item = u * (kTileRows / SR) + slot;                   // score column (compact when sampling)
-            const long long page = u * p.tile_stride * (kTileRows / SR) + slot;   // page (slot mode: item) scored
+            const long long page = u * p.tile_stride * (kTileRows / SR) + slot;   // dense: the page scored
             int nr = 0;
             bool item_ok;
             if (!p.slot_mode) {
@@ -750,93 +769,22 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
               scale = sScale[stage * kScaleStride + sslot * (p.slot_rows + 32) + (trow - sslot * p.slot_rows) +
                              (sMis[stage * 4 + sslot] & 3)];
             }
+            float v[QE];
             const bool live = rin < nr;
-#pragma unroll 1
-            for (int c0 = 0; c0 < QP; c0 += 32) {
-              float v[32];
+            constexpr int LW = QE >= 16 ? 16 : 8;
 #pragma unroll
-              for (int c = 0; c < 32; c += 8) {
-                uint32_t hi[8], lo[8];
-                tmem_ld_x8(ta + c0 + c, hi);
-                tmem_ld_x8(ta + QP + c0 + c, lo);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  v[c + j] = live ? fmaf(__uint_as_float(lo[j]), kInvLo, __uint_as_float(hi[j])) * scale : -INFINITY;
-              }
-              if (c0 + 32 >= QP) {   // last chunk read: release the accumulator and the scale rows
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) {
-                  mbar_arrive(&tempty[acc]);
-                  mbar_arrive(&empty[stage]);
-                }
-              }
-              if constexpr (QS == 32) {
-                const int j = c0 >> 5;
-                const int qv = j < p.n_sub ? __ldg(p.q_valid_arr + j) : 0;
-                float sum;
-                switch (SR) {
-                  case 32: sum = slot_maxsim<32, 32>(v, lane, qv); break;
-                  case 16: sum = slot_maxsim<32, 16>(v, lane, qv); break;
-                  case 8: sum = slot_maxsim<32, 8>(v, lane, qv); break;
-                  case 4: sum = slot_maxsim<32, 4>(v, lane, qv); break;
-                  case 2: sum = slot_maxsim<32, 2>(v, lane, qv); break;
-                  default: sum = slot_maxsim<32, 1>(v, lane, qv); break;
-                }
-                if (rin == 0 && item_ok && j < p.n_sub) emit(j, item, page, sum);
+            for (int c = 0; c < QE; c += LW) {
+              uint32_t hi[LW], lo[LW];
+              if constexpr (LW == 16) {
+                tmem_ld_x16(ta + c, hi);
+                tmem_ld_x16(ta + QP + c, lo);
               } else {
-                // pooled queries: every column is a query. After the segmented butterfly lane b of a slot holds the
-                // column maxima of columns (b*32/SR) .. +32/SR.
-                switch (SR) {
-                  case 32: slot_colmax<32, 32>(v, lane); break;
-                  case 16: slot_colmax<32, 16>(v, lane); break;
-                  case 8: slot_colmax<32, 8>(v, lane); break;
-                  case 4: slot_colmax<32, 4>(v, lane); break;
-                  case 2: slot_colmax<32, 2>(v, lane); break;
-                  default: break;
-                }
-                const int cf = 32 / SR;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  const int q = c0 + rin * cf + i;
-                  if (i < cf && item_ok && q < p.n_sub) emit(q, item, page, v[i]);
-                }
+                tmem_ld_x8(ta + c, hi);
+                tmem_ld_x8(ta + QP + c, lo);
               }
-            }
-          } else if constexpr (QP <= 32) {
-            // fast path: page j of the tile owns tile rows [j*SR, j*SR + nr)
-            const int SR = p.shfl_rows;
-            const int slot = trow / SR, rin = trow - slot * SR;
-            const long long item = u * (kTileRows / SR) + slot;
-            int nr = 0;
-            bool item_ok;
-            if (!p.slot_mode) {
-              item_ok = item < p.n_pages;
-              nr = item_ok ? SR : 0;
-            } else {
-              item_ok = item < p.n_items;
-            }
-            mbar_wait(&tfull[acc], accphase);
-            tc_fence_after_sync();
-            mbar_wait(&full[stage], phase);   // acquire the producer's per-slot metadata and the scale rows
-            if (p.slot_mode) nr = item_ok ? (sMis[stage * 4 + slot] >> 2) : 0;   // slot == 32-row slot here (SR == 32)
-            float scale = 1.0f;
-            if (use_scale) {
-              const int sslot = trow / p.slot_rows;
-              scale = sScale[stage * kScaleStride + sslot * (p.slot_rows + 32) + (trow - sslot * p.slot_rows) +
-                             (sMis[stage * 4 + sslot] & 3)];
-            }
-            float v[QP];
-            const bool live = rin < nr;
-#pragma unroll
-            for (int c = 0; c < QP; c += 8) {
-              uint32_t hi[8], lo[8];
-              tmem_ld_x8(ta + c, hi);
-              tmem_ld_x8(ta + QP + c, lo);
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
+              for (int j = 0; j < LW; ++j)
                 v[c + j] = live ? fmaf(__uint_as_float(lo[j]), kInvLo, __uint_as_float(hi[j])) * scale : -INFINITY;
             }
             tc_fence_before_sync();
@@ -845,16 +793,52 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
               mbar_arrive(&tempty[acc]);
               mbar_arrive(&empty[stage]);
             }
-            float sum;
-            switch (SR) {
-              case 32: sum = slot_maxsim<QP, 32>(v, lane, q_valid); break;
-              case 16: sum = slot_maxsim<QP, 16>(v, lane, q_valid); break;
-              case 8: sum = slot_maxsim<QP, 8>(v, lane, q_valid); break;
-              case 4: sum = slot_maxsim<QP, 4>(v, lane, q_valid); break;
-              case 2: sum = slot_maxsim<QP, 2>(v, lane, q_valid); break;
-              default: sum = slot_maxsim<QP, 1>(v, lane, q_valid); break;
+            if constexpr (MULTI && QS == 1) {
+              // 32 single-column queries: after the segmented butterfly lane rin of a slot holds the column maxima
+              // of columns col0 + rin*cf .. +cf (cf = 32 / SR)
+              switch (SR) {
+                case 32: slot_colmax<32, 32>(v, lane); break;
+                case 16: slot_colmax<32, 16>(v, lane); break;
+                case 8: slot_colmax<32, 8>(v, lane); break;
+                case 4: slot_colmax<32, 4>(v, lane); break;
+                case 2: slot_colmax<32, 2>(v, lane); break;
+                default: break;
+              }
+              const int cf = 32 / SR;
+              const int qb = col0 + rin * cf;
+              if (p.f_thr) {
+                // prefilter: one compare per score; the (rare) survivors are appended to their query's candidate list
+                unsigned pass = 0u;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < cf && v[i] > sThr[qb + i]) pass |= 1u << i;   // sThr is +inf for absent queries
+                if (!item_ok) pass = 0u;
+                if (pass) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    if ((pass >> i) & 1u) emit(qb + i, item, page, v[i]);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < cf && item_ok && qb + i < p.n_sub) p.scores[(qb + i) * p.score_stride + item] = v[i];
+              }
+            } else {
+              float sum;
+              switch (SR) {
+                case 32: sum = slot_maxsim<QE, 32>(v, lane, q_valid); break;
+                case 16: sum = slot_maxsim<QE, 16>(v, lane, q_valid); break;
+                case 8: sum = slot_maxsim<QE, 8>(v, lane, q_valid); break;
+                case 4: sum = slot_maxsim<QE, 4>(v, lane, q_valid); break;
+                case 2: sum = slot_maxsim<QE, 2>(v, lane, q_valid); break;
+                default: sum = slot_maxsim<QE, 1>(v, lane, q_valid); break;
+              }
+              if constexpr (MULTI) {
+                if (rin == 0 && item_ok && grp < p.n_sub) emit(grp, item, page, nr > 0 ? sum : -INFINITY);
+              } else {
+                if (rin == 0 && item_ok) scores_g[item] = nr > 0 ? sum : -INFINITY;
+              }
             }
-            if (rin == 0 && item_ok) scores_g[item] = nr > 0 ? sum : -INFINITY;
           }
           continue;
         }
@@ -871,13 +855,11 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           seg[kTileRows + et] = seg_rb;
           seg[2 * kTileRows + et] = seg_re;
         }
-        {
-          if (seq + EPI_GROUPS < ur.count) {
-            int gn;
-            long long un;
-            ur.decode(seq + EPI_GROUPS, gn, un);
-            packed_segment(p, gn, un, et, seg_n, seg_item, seg_rb, seg_re);
-          }
+        if (seq + seq_step < ur.count) {
+          int gn;
+          long long un;
+          ur.decode(seq + seq_step, gn, un);
+          packed_segment(p, gn, un, et, seg_n, seg_item, seg_rb, seg_re);
         }
         // 2. scaled scores of my row -> transposed smem buffer sc[q][row]
         mbar_wait(&tfull[acc], accphase);
@@ -890,7 +872,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
                          (sMis[stage * 4 + slot] & 3)];
         }
 #pragma unroll
-        for (int c = 0; c < QP; c += 8) {
+        for (int c = 0; c < QE; c += 8) {
           uint32_t hi[8], lo[8];
           tmem_ld_x8(ta + c, hi);
           tmem_ld_x8(ta + QP + c, lo);
@@ -921,8 +903,8 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             const int rb = seg[kTileRows + sg], re = seg[2 * kTileRows + sg];
             nonempty = re > rb;
 #pragma unroll
-            for (int g = 0; g < QG; ++g) {
-              const int q = g * 32 + ql;
+            for (int gq = 0; gq < QG; ++gq) {
+              const int q = gq * 32 + ql;
               const float* row = sc + q * Cfg::SC_PITCH;
               float m0 = -INFINITY, m1 = -INFINITY;
               for (int r4 = rb & ~3; r4 < re; r4 += 4) {
@@ -934,27 +916,22 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
                 m0 = fmaxf(m0, fmaxf(a0, a1));
                 m1 = fmaxf(m1, fmaxf(a2, a3));
               }
-              if constexpr (MULTI) {
-                // sg is warp-uniform here (QW == 32): every 32-column group is one query (QS == 32) or 32 pooled queries
-                const float m = fmaxf(m0, m1);
-                if constexpr (QS == 32) {
-                  const int qv = g < p.n_sub ? __ldg(p.q_valid_arr + g) : 0;
-                  float sg_sum = ql < qv ? m : 0.0f;
-#pragma unroll
-                  for (int off = 16; off >= 1; off >>= 1) sg_sum += __shfl_xor_sync(0xffffffffu, sg_sum, off);
-                  if (ql == 0 && g < p.n_sub) emit(g, item, item, nonempty ? sg_sum : -INFINITY);
-                } else {
-                  if (q < p.n_sub) emit(q, item, item, nonempty ? m : -INFINITY);
-                }
+              if constexpr (MULTI && QS == 1) {
+                // QW == 32: sg is warp-uniform; every column is a query
+                if (col0 + q < p.n_sub) emit(col0 + q, item, item, nonempty ? fmaxf(m0, m1) : -INFINITY);
               } else {
                 if (q < q_valid) sum += fmaxf(m0, m1);
               }
             }
           }
-          if constexpr (MULTI) continue;
+          if constexpr (MULTI && QS == 1) continue;
 #pragma unroll
           for (int off = QW / 2; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-          if (sg < nseg && ql == 0) scores_g[item] = nonempty ? sum : -INFINITY;
+          if constexpr (MULTI) {
+            if (sg < nseg && ql == 0 && grp < p.n_sub) emit(grp, item, item, nonempty ? sum : -INFINITY);
+          } else {
+            if (sg < nseg && ql == 0) scores_g[item] = nonempty ? sum : -INFINITY;
+          }
         }
         named_bar_sync(bar_id, 128);   // the group's buffers are reused by its next tile
       }

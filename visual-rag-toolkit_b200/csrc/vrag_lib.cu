@@ -465,14 +465,14 @@ extern "C" int vrag_store_drop(vrag_corpus_t* c, const char* name) {
 template <int QP, bool PACKED, bool BSW = false, int QS = QP>
 static int launch_scan_t(vrag_corpus* c, const Store& s, const ScanParams& p, long long n_units, cudaStream_t st) {
   auto kern = maxsim_scan_kernel<QP, QS, PACKED, BSW>;
-  const size_t smem = ScanCfg<QP>::smem_bytes(PACKED, BSW);
+  const size_t smem = ScanCfg<QP>::smem_bytes(PACKED, BSW, QS < QP);
   static bool attr_done[8] = {false};  // per device
   if (!attr_done[c->device & 7]) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_done[c->device & 7] = true;
   }
   const unsigned grid = static_cast<unsigned>(std::min<long long>(c->num_sms, n_units));
-  kern<<<grid, ScanCfg<QP>::threads(PACKED), smem, st>>>(s.tm128, s.tm32, s.ts128, s.ts32, p);
+  kern<<<grid, ScanCfg<QP>::threads(PACKED, QS < QP), smem, st>>>(s.tm128, s.tm32, s.ts128, s.ts32, p);
   c->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;

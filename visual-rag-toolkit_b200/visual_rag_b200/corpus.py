@@ -370,7 +370,7 @@ class GpuCorpus:
             ii = ids[off : off + nq * ks[s]].reshape(nq, ks[s])
             for b in range(nq):
                 m = int(counts[s * nq + b])
-                out[b].append((sc[b, :m].copy(), ii[b, :m].copy()))
+                out[b].append((sc[b, :m], ii[b, :m]))   # views into this call's own result arrays
             off += nq * ks[s]
         return out
 
