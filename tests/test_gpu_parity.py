@@ -304,6 +304,32 @@ def test_retrievers_match_reference_goldens(gpu_client, golden_index):
     assert res[0]["embedding"].shape[1] == 128 and res[0]["payload"]["page"] == res[0]["id"]
 
 
+def test_retriever_batch_methods_equal_per_query_calls(gpu_client):
+    """search_server_side_batch (one native call) == the per-query retrievers pinned to the reference goldens."""
+    from visual_rag_b200.retrieval import MultiVectorRetriever, ThreeStageRetriever, TwoStageRetriever
+
+    q, client = gpu_client
+    rng = np.random.default_rng(9)
+    queries = [q] + [rng.standard_normal((int(rng.integers(8, 30)), 128)).astype(np.float32) for _ in range(6)]
+    three = ThreeStageRetriever(client, "c")
+    got = three.search_server_side_batch(query_embeddings=queries, top_k=10, stage1_k=80, stage2_k=30)
+    for qq, g in zip(queries, got):
+        _same(g, three.search_server_side(query_embedding=qq, top_k=10, stage1_k=80, stage2_k=30),
+              ("score_stage1", "score_stage2", "score_stage3", "score_final"))
+    two = TwoStageRetriever(client, "c")
+    for mode in ("pooled_query_vs_standard_pooling", "tokens_vs_standard_pooling", "pooled_query_vs_global",
+                 "tokens_vs_experimental_pooling"):
+        got = two.search_server_side_batch(queries, top_k=10, prefetch_k=40, stage1_mode=mode)
+        for qq, g in zip(queries, got):
+            _same(g, two.search_server_side(qq, top_k=10, prefetch_k=40, stage1_mode=mode), ("score_final",))
+    mv = MultiVectorRetriever("c", qdrant_client=client)
+    got = mv.search_embedded_batch(query_embeddings=queries[:2], top_k=5, mode="single_full")
+    assert [r["id"] for r in got[0]] == [r["id"] for r in mv.search_embedded(query_embedding=queries[0], top_k=5)]
+    f = two.build_filter(year=2001)   # filters fall back to the per-query path
+    got = two.search_server_side_batch(queries[:2], top_k=5, prefetch_k=40, filter_obj=f)
+    assert all(r["payload"]["year"] == 2001 for r in got[0]) and len(got) == 2
+
+
 def test_payload_and_id_filters(gpu_client):
     from visual_rag_b200.retrieval import TwoStageRetriever
     from visual_rag_b200.retrieval.models import Filter, HasIdCondition

@@ -190,6 +190,30 @@ class GpuCorpusClient:
                         for s, i in zip(scores[keep], ids[keep])])
         return out
 
+    def query_multistage_batch(self, *, usings: Sequence[str], limits: Sequence[int],
+                               stage_queries: Sequence[Sequence[Any]], with_payload: bool = True):
+        """A batch of independent multi-stage searches in ONE native call (BASELINE configs[2]: 256 queries):
+        stage s scans named vector usings[s] with that query's stage-s matrix, restricted to the survivors of
+        stage s-1, and keeps limits[s] points. stage_queries[b][s] is what the reference would send as `query=`
+        of stage s for query b (the mean-pooled vector or the token matrix, two_stage.py:142-159,
+        three_stage.py:96-100). Returns per query the per-stage point lists (payloads on the last stage only)."""
+        ns = len(usings)
+        if len(limits) != ns:
+            raise ValueError("usings and limits must have the same length")
+        sq = [[self._as_query(x) for x in per_query] for per_query in stage_queries]
+        res = self.corpus.search_multistage_batch([(usings[s], False, int(limits[s])) for s in range(ns)], None,
+                                                  stage_queries=sq)
+        out = []
+        for per_query in res:
+            stages = []
+            for si, (scores, ids) in enumerate(per_query):
+                keep = np.isfinite(scores)
+                last = si == ns - 1
+                stages.append([ScoredPoint(self._pid(int(i)), float(s), self._payload(int(i)) if (last and with_payload) else None)
+                               for s, i in zip(scores[keep], ids[keep])])
+            out.append(stages)
+        return out
+
     def retrieve(self, collection_name=None, ids=(), with_payload=False, with_vectors=None, timeout=None, **_ignored):
         out = []
         names = [] if not with_vectors else (list(with_vectors) if not isinstance(with_vectors, bool) else [])

@@ -92,3 +92,19 @@ class MultiVectorRetriever:
                                                         stage1_k=stage1_k, stage2_k=stage2_k, filter_obj=filter_obj,
                                                         stage1_mode=stage1_mode)
         raise ValueError(f"Unknown mode: {mode}")
+
+    def search_embedded_batch(self, *, query_embeddings, top_k: int = 10, mode: str = "two_stage",
+                              prefetch_k: Optional[int] = None, stage1_mode: str = "pooled_query_vs_standard_pooling",
+                              stage1_k: Optional[int] = None, stage2_k: Optional[int] = None,
+                              filter_obj=None) -> List[List[Dict[str, Any]]]:
+        """search_embedded for a batch of queries; two_stage / three_stage run as one native call on the GPU
+        backend, every other mode is the per-query loop."""
+        if mode == "two_stage":
+            return self._two_stage.search_server_side_batch(query_embeddings, top_k=top_k, prefetch_k=prefetch_k,
+                                                            filter_obj=filter_obj, stage1_mode=stage1_mode)
+        if mode == "three_stage":
+            return self._three_stage.search_server_side_batch(query_embeddings=query_embeddings, top_k=top_k,
+                                                              stage1_k=stage1_k, stage2_k=stage2_k, filter_obj=filter_obj)
+        return [self.search_embedded(query_embedding=q, top_k=top_k, mode=mode, prefetch_k=prefetch_k,
+                                     stage1_mode=stage1_mode, stage1_k=stage1_k, stage2_k=stage2_k,
+                                     filter_obj=filter_obj) for q in query_embeddings]

@@ -110,3 +110,44 @@ class ThreeStageRetriever:
                 "payload": p.payload,
             })
         return out
+
+    def search_server_side_batch(
+        self,
+        *,
+        query_embeddings,
+        top_k: int = 100,
+        stage1_k: Optional[int] = 1000,
+        stage2_k: Optional[int] = 300,
+        filter_obj=None,
+    ) -> List[List[Dict[str, Any]]]:
+        """`search_server_side` for a batch of queries (BASELINE configs[2]). On a GpuCorpusClient all queries run
+        in one native call — the global stage as a dense batched scan with the fused top-k prefilter, the two
+        ID-restricted stages as one launch each; with a filter (or any other client) it is the per-query loop the
+        reference's evaluation runs (run_qdrant_beir.py:378-402). Same result dicts as search_server_side."""
+        batch = getattr(self.client, "query_multistage_batch", None)
+        if batch is None or filter_obj is not None:
+            return [self.search_server_side(query_embedding=q, top_k=top_k, stage1_k=stage1_k, stage2_k=stage2_k,
+                                            filter_obj=filter_obj) for q in query_embeddings]
+        stage1_k = 1000 if stage1_k is None else int(stage1_k)
+        stage2_k = 300 if stage2_k is None else int(stage2_k)
+        qs = [self._to_numpy(q) for q in query_embeddings]
+        sq = [[q.mean(axis=0, keepdims=True), q, q] for q in qs]
+        res = self._retry_call(lambda: batch(
+            usings=[self.global_vector_name, self.experimental_vector_name, self.full_vector_name],
+            limits=[stage1_k, stage2_k, int(top_k)], stage_queries=sq))
+        out = []
+        for s1, s2, s3 in res:
+            if not s1 or not s2:
+                out.append([])
+                continue
+            s1_score = {str(p.id): float(p.score) for p in s1}
+            s2_score = {str(p.id): float(p.score) for p in s2}
+            out.append([{
+                "id": p.id,
+                "score_stage1": s1_score.get(str(p.id)),
+                "score_stage2": s2_score.get(str(p.id)),
+                "score_stage3": float(p.score),
+                "score_final": float(p.score),
+                "payload": p.payload,
+            } for p in s3])
+        return out

@@ -91,6 +91,31 @@ class TwoStageRetriever:
             for r in results
         ]
 
+    def search_server_side_batch(
+        self,
+        query_embeddings,
+        top_k: int = 10,
+        prefetch_k: Optional[int] = None,
+        filter_obj=None,
+        stage1_mode: str = "pooled_query_vs_standard_pooling",
+    ) -> List[List[Dict[str, Any]]]:
+        """`search_server_side` for a batch of queries: one native call on a GpuCorpusClient (stage 1 as a dense
+        batched scan, the rerank of all queries as one launch); otherwise the per-query loop."""
+        batch = getattr(self.client, "query_multistage_batch", None)
+        if batch is None or filter_obj is not None:
+            return [self.search_server_side(q, top_k=top_k, prefetch_k=prefetch_k, filter_obj=filter_obj,
+                                            stage1_mode=stage1_mode) for q in query_embeddings]
+        if prefetch_k is None:
+            prefetch_k = max(100, top_k * 10)
+        pool, prefetch_using = resolve_stage1(stage1_mode, self.pooled_vector_name, self.experimental_vector_name,
+                                              self.global_vector_name)
+        qs = [self._to_numpy(q) for q in query_embeddings]
+        sq = [[q.mean(axis=0, keepdims=True) if pool else q, q] for q in qs]
+        res = self._retry_call(lambda: batch(usings=[prefetch_using, self.full_vector_name],
+                                             limits=[int(prefetch_k), int(top_k)], stage_queries=sq))
+        return [[{"id": r.id, "score_stage1": None, "score_stage2": r.score, "score_final": r.score, "payload": r.payload}
+                 for r in stages[-1]] for stages in res]
+
     # ------------------------------------------------------------------ client-side flow
     def search(
         self,
