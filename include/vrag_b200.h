@@ -148,6 +148,10 @@ typedef struct vrag_pool_spec {
   float weights[16];
   int n_rows, n_cols, has_global, include_self; /* TILE_4N */
   int via_f16;            /* GLOBAL_MEAN: round the fp32 mean to fp16 first (numpy's fp16 mean, pooling.py:463) */
+  int input_spec;         /* vrag_store_pool only. 0: pool the source store. k > 0: pool the OUTPUT of spec k-1 of the same
+                             call (a token-level spec): the pipeline's "experimental / global pooling of the mean-pooled
+                             rows" (pipeline.py:452-507), computed inside that spec's pass from shared memory — the pooled
+                             rows are used as stored (rounded to the store dtype), never re-read from HBM.            */
 } vrag_pool_spec_t;
 
 /* Rows this spec produces for a page of in_rows rows (host arithmetic only; validates the arguments with the
@@ -163,7 +167,7 @@ int vrag_pool_page(int device, const vrag_pool_spec_t* spec, const void* in, int
  * per-page orchestration of ProcessingPipeline._process_single_page, pipeline.py:400-507, and
  * scripts/qdrant_recompute_colqwen_pooling_from_initial.py:292-327, for a whole collection).
  * Token-level kinds read `src` once each; SMOOTH / TILE_4N / LEGACY_CONV / GLOBAL_MEAN specs are all
- * produced in ONE pass over `src`. grid_hw: optional host [n_pages][2] per-page (grid_h, grid_w) /
+ * produced in ONE pass over `src`, or — chained with input_spec — inside the pass of the token-level spec they derive from. grid_hw: optional host [n_pages][2] per-page (grid_h, grid_w) /
  * (n_rows, n_cols). Outputs are rounded to the fp16 store dtype (qdrant_indexer.py:423-441).        */
 int vrag_store_pool(vrag_corpus_t* c, const char* src, int n_specs, const vrag_pool_spec_t* specs,
                     const char* const* dst_names, const int32_t* grid_hw);

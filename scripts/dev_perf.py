@@ -59,6 +59,10 @@ b1 = 200_000 * (1024 * 256 + 32 * 256) / 1e9
 b2 = 200_000 * (32 + 34 + 32 + 32 + 1) * 256 / 1e9
 print(f"pooling ColPali: tokens->32 rows {ms1:.3f} ms ({b1/ms1*1e3:.0f} GB/s, {b1/ms1*1e3/PEAK:.1%}); derived x4 {ms2:.3f} ms ({b2/ms2*1e3:.0f} GB/s); "
       f"{200_000/(ms1+ms2)*1e3/1e6:.2f} M pages/s", flush=True)
+for _ in range(3):
+    ms3 = c.pool_store("vis", [GP.spec_adaptive_rows(32, 32, 32)] + [GP.derived_from(x, 0) for x in (GP.spec_legacy_conv(3), GP.spec_smooth(3, "gaussian"),
+                       GP.spec_smooth(3, "triangular"), GP.spec_global_mean(True))], ["mean_pooling", "e1", "e2", "e3", "g"])
+print(f"pooling ColPali FUSED single pass: {ms3:.3f} ms ({(b1+b2)/ms3*1e3:.0f} GB/s algorithmic, {(b1+b2)/ms3*1e3/PEAK:.1%}); {200_000/ms3*1e3/1e6:.2f} M pages/s", flush=True)
 c.add_synthetic_store("smol", 200_000, fixed_rows=832, seed=7)
 for _ in range(3):
     ms1 = c.pool_store("smol", [GP.spec_tile_mean(64)], ["mean_pooling"])
@@ -66,3 +70,10 @@ for _ in range(3):
     ms2 = c.pool_store("mean_pooling", [GP.spec_tile_4n(4, 3), GP.spec_global_mean(True)], ["e2d", "g"])
 print(f"pooling ColSmol: tile mean {ms1:.3f} ms ({200_000*(832*256+13*256)/1e9/ms1*1e3:.0f} GB/s); experimental {ms1b:.3f} ms; 4n+global {ms2:.3f} ms; "
       f"{200_000/(ms1+ms1b+ms2)*1e3/1e6:.2f} M pages/s", flush=True)
+
+g = np.tile(np.array([[4, 3]], dtype=np.int32), (200_000, 1))
+for _ in range(3):
+    ms4 = c.pool_store("smol", [GP.spec_tile_mean(64), GP.spec_colsmol_experimental(0, 64), GP.derived_from(GP.spec_tile_4n(0, 0), 0),
+                                GP.derived_from(GP.spec_global_mean(True), 0)], ["mean_pooling", "exp", "e2d", "g"], grid_hw=g)
+bs = 200_000 * (832 * 256 + (13 + 76 + 13 + 1) * 256) / 1e9
+print(f"pooling ColSmol FUSED single pass: {ms4:.3f} ms ({bs/ms4*1e3:.0f} GB/s algorithmic, {bs/ms4*1e3/PEAK:.1%}); {200_000/ms4*1e3/1e6:.2f} M pages/s", flush=True)

@@ -182,3 +182,61 @@ def test_store_pool_colsmol_and_colqwen():
         _check_store(c, "experimental_pooling", [PO.weighted_row_smoothing_same_length(m, window_size=3, kernel="gaussian") for m in mp])
         _check_store(c, "experimental_pooling_triangular", [PO.weighted_row_smoothing_same_length(m, window_size=3, kernel="triangular") for m in mp])
         _check_store(c, "global_pooling", [PO.global_pool_from_mean_pool(m, np.float16) for m in mp])
+
+
+def _stores_equal(c, a, b):
+    ia, ib = c.store_info(a), c.store_info(b)
+    assert ia["n_pages"] == ib["n_pages"] and ia["total_rows"] == ib["total_rows"]
+    ra, rb = c.read_rows(a, 0, ia["total_rows"]), c.read_rows(b, 0, ib["total_rows"])
+    assert np.array_equal(ra.view(np.uint16), rb.view(np.uint16)), (a, b)
+    for p in (0, ia["n_pages"] - 1):
+        assert c.page_range(a, p) == c.page_range(b, p)
+
+
+def test_store_pool_chained_specs_single_pass():
+    """input_spec chaining: the derived stores computed inside the token pass (pooled rows kept in shared memory)
+    are bit-identical to deriving them from the stored pooled rows in a second call (checked against the oracle
+    above), for the ColPali, ColSmol and ColQwen2.5 pipelines."""
+    from visual_rag_b200.corpus import GpuCorpus
+    from visual_rag_b200.embedding import pooling as GP
+
+    rng = np.random.default_rng(4)
+    with GpuCorpus(0) as c:
+        # ColPali
+        c.add_store("initial", CS.unit_rows(81, 60 * 1024, dtype=np.float16), fixed_rows=1024)
+        c.pool_store("initial", [GP.spec_adaptive_rows(32, 32, 32)], ["mp"])
+        two = [GP.spec_legacy_conv(3), GP.spec_smooth(3, "gaussian"), GP.spec_smooth(3, "triangular"), GP.spec_global_mean(True)]
+        c.pool_store("mp", two, ["e", "eg", "et", "g"])
+        one = [GP.spec_adaptive_rows(32, 32, 32)] + [GP.derived_from(s, 0) for s in
+                                                     (GP.spec_legacy_conv(3), GP.spec_smooth(3, "gaussian"),
+                                                      GP.spec_smooth(3, "triangular"), GP.spec_global_mean(True))]
+        c.pool_store("initial", one, ["mp1", "e1", "eg1", "et1", "g1"])
+        for a, b in (("mp", "mp1"), ("e", "e1"), ("eg", "eg1"), ("et", "et1"), ("g", "g1")):
+            _stores_equal(c, a, b)
+        # ColSmol (variable tile counts, per-page tile grids)
+        lens = np.array([832, 768, 800, 832, 64, 130, 832])
+        offs = np.concatenate([[0], np.cumsum(lens)])
+        grids = np.array([[4, 3], [3, 4], [4, 3], [4, 3], [1, 1], [1, 2], [2, 6]], dtype=np.int32)
+        c.add_store("initial", CS.unit_rows(82, int(offs[-1]), dtype=np.float16), page_offsets=offs)
+        c.pool_store("initial", [GP.spec_tile_mean(64), GP.spec_colsmol_experimental(0, 64)], ["mp", "e"])
+        c.pool_store("mp", [GP.spec_tile_4n(0, 0, True, True), GP.spec_global_mean(True)], ["e2d", "g"], grid_hw=grids)
+        c.pool_store("initial", [GP.spec_tile_mean(64), GP.spec_colsmol_experimental(0, 64),
+                                 GP.derived_from(GP.spec_tile_4n(0, 0, True, True), 0), GP.derived_from(GP.spec_global_mean(True), 0)],
+                     ["mp1", "e1", "e2d1", "g1"], grid_hw=grids)
+        for a, b in (("mp", "mp1"), ("e", "e1"), ("e2d", "e2d1"), ("g", "g1")):
+            _stores_equal(c, a, b)
+        # ColQwen2.5 (dynamic grids, cap 32)
+        gh = rng.integers(16, 48, size=31)
+        gw = rng.integers(8, 33, size=31)
+        offs = np.concatenate([[0], np.cumsum(gh * gw)])
+        ghw = np.stack([gh, gw], axis=1)
+        c.add_store("initial", CS.unit_rows(83, int(offs[-1]), dtype=np.float16), page_offsets=offs)
+        c.pool_store("initial", [GP.spec_adaptive_rows(0, 0, 32, clamp_to_h=True)], ["mp"], grid_hw=ghw)
+        c.pool_store("mp", [GP.spec_smooth(3, "gaussian"), GP.spec_smooth(3, "triangular"), GP.spec_global_mean(True)], ["e", "et", "g"])
+        c.pool_store("initial", [GP.spec_adaptive_rows(0, 0, 32, clamp_to_h=True), GP.derived_from(GP.spec_smooth(3, "gaussian"), 0),
+                                 GP.derived_from(GP.spec_smooth(3, "triangular"), 0), GP.derived_from(GP.spec_global_mean(True), 0)],
+                     ["mp1", "e1", "et1", "g1"], grid_hw=ghw)
+        for a, b in (("mp", "mp1"), ("e", "e1"), ("et", "et1"), ("g", "g1")):
+            _stores_equal(c, a, b)
+        with pytest.raises(Exception):
+            c.pool_store("initial", [GP.derived_from(GP.spec_smooth(3, "gaussian"), 0)], ["x"])

@@ -161,12 +161,119 @@ __device__ __forceinline__ void pool_page_rows(const long long* off, long long f
   }
 }
 
+// ------------------------------------------------------------------------------------------------ row-level
+struct PoolRowsArgs {
+  PoolInput in;
+  int n_specs;
+  PoolSpecDev specs[kPoolMaxSpecs];
+};
+
+// Output row `o` of a row-level spec over the n rows of one page staged in smem as fp32 (nr x nc: TILE_4N grid).
+__device__ __forceinline__ float4 pool_row_level(const PoolSpecDev& s, const float* rows, int n, int o, int lane, int nr,
+                                                 int nc) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s.kind == kPoolSmooth) {
+    if (s.window == 1 || n == 1) {
+      v = reinterpret_cast<const float4*>(rows + o * 128)[lane];
+    } else {
+      // pooling.py:358-374: taps i-left+t, products rounded to fp32, summed in tap order; weight mass in fp64
+      const int left = s.window / 2;
+      double mass = 0.0;
+      for (int t = 0; t < s.window; ++t) {
+        const int j = o - left + t;
+        if (j < 0 || j >= n) continue;
+        const float w = s.weights[t];
+        const float4 x = reinterpret_cast<const float4*>(rows + j * 128)[lane];
+        v = f4_add(v, make_float4(__fmul_rn(w, x.x), __fmul_rn(w, x.y), __fmul_rn(w, x.z), __fmul_rn(w, x.w)));
+        mass += static_cast<double>(w);
+      }
+      // interior rows: the taps sum to exactly 1.0f and x / 1 == x, so the (slow, IEEE) division is skipped
+      const float fm = static_cast<float>(mass);
+      if (mass > 0.0) { if (fm != 1.0f) v = f4_div(v, fm); }
+      else v = reinterpret_cast<const float4*>(rows + o * 128)[lane];
+    }
+  } else if (s.kind == kPoolTile4n) {
+    const int g = nr * nc;
+    if (o >= g) {
+      v = reinterpret_cast<const float4*>(rows + g * 128)[lane];   // global tile copied through
+    } else {
+      const int r = o / nc, c = o - r * nc;
+      int cnt = 0;
+      if (s.include_self) { v = f4_add(v, reinterpret_cast<const float4*>(rows + o * 128)[lane]); ++cnt; }
+      if (r > 0) { v = f4_add(v, reinterpret_cast<const float4*>(rows + (o - nc) * 128)[lane]); ++cnt; }
+      if (r + 1 < nr) { v = f4_add(v, reinterpret_cast<const float4*>(rows + (o + nc) * 128)[lane]); ++cnt; }
+      if (c > 0) { v = f4_add(v, reinterpret_cast<const float4*>(rows + (o - 1) * 128)[lane]); ++cnt; }
+      if (c + 1 < nc) { v = f4_add(v, reinterpret_cast<const float4*>(rows + (o + 1) * 128)[lane]); ++cnt; }
+      v = f4_div(v, static_cast<float>(cnt));
+    }
+  } else if (s.kind == kPoolLegacyConv) {
+    const int r = s.window / 2;
+    int lo, hi;
+    if (s.window == 1 || n == 1) { lo = o; hi = o + 1; }
+    else if (s.window == 3 && n == 2) { lo = (o == 2) ? 1 : 0; hi = (o == 0) ? 1 : 2; }
+    else { lo = max(0, o - 2 * r); hi = min(n - 1, o) + 1; }
+    v = (hi - lo == 1) ? reinterpret_cast<const float4*>(rows + lo * 128)[lane] : range_mean_smem(rows, lo, hi, lane);
+  } else if (s.kind == kPoolGlobalMean) {
+    if (n > 0) v = range_mean_smem(rows, 0, n, lane);   // empty page -> zeros (visual_embedder.py:838-839)
+  }
+  return v;
+}
+
+// All row-level specs of `a` for one page whose n rows are staged in `rows` (smem, fp32). kWarps warps cooperate.
+template <int kWarps>
+__device__ __forceinline__ void pool_derive_page(const PoolRowsArgs& a, const float* rows, int n, long long page, int warp,
+                                                 int lane) {
+  for (int si = 0; si < a.n_specs; ++si) {
+    const PoolSpecDev& s = a.specs[si];
+    long long o0;
+    int n_out;
+    pool_page_rows(s.out_off, s.out_fixed, page, o0, n_out);
+    int nr = s.n_rows, nc = s.n_cols;
+    if (s.kind == kPoolTile4n && a.in.grid_hw) {
+      nr = a.in.grid_hw[2 * page];
+      nc = a.in.grid_hw[2 * page + 1];
+    }
+    for (int o = warp; o < n_out; o += kWarps)
+      pool_store4(s.out, s.out_f32, o0 + o, lane, pool_row_level(s, rows, n, o, lane, nr, nc), s.via_f16);
+  }
+}
+
+// block = 128 threads (4 warps); one page per block iteration; dynamic smem = max_rows*128 floats.
+__global__ void __launch_bounds__(128) pool_rows_kernel(const PoolRowsArgs a) {
+  extern __shared__ float pool_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kWarps = 4;
+  for (long long page = blockIdx.x; page < a.in.n_pages; page += gridDim.x) {
+    long long r0;
+    int n;
+    pool_page_rows(a.in.in_off, a.in.in_fixed, page, r0, n);
+    for (int r = warp; r < n; r += kWarps)
+      reinterpret_cast<float4*>(pool_smem + r * 128)[lane] = pool_load4(a.in.in, a.in.in_f32, r0 + r, lane);
+    __syncthreads();
+    pool_derive_page<kWarps>(a, pool_smem, n, page, warp, lane);
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ token-level
 // block = 256 threads (8 warps); one page per block iteration; dynamic smem = grid_h_max*128 floats (ADAPTIVE).
-__global__ void __launch_bounds__(256) pool_tokens_kernel(const PoolInput in, const PoolSpecDev s) {
+// `d`: row-level specs DERIVED from this spec's output (d.n_specs may be 0): the page's pooled rows, rounded to the
+// store dtype exactly as a reader of the stored rows would see them (the reference's dtype chain), are
+// kept in smem (at float offset d_off) and the derived stores are written in the same pass — the pooled store is
+// never re-read from HBM.
+template <bool DERIVE>
+__global__ void __launch_bounds__(256, 3) pool_tokens_kernel(const PoolInput in, const PoolSpecDev s, const PoolRowsArgs d,
+                                                             const int d_off) {
   extern __shared__ float pool_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kWarps = 8;
+  float* drows = pool_smem + d_off;
+  auto keep = [&](int o, float4 v) {   // stage output row o for the derived specs, as stored
+    if constexpr (DERIVE) {
+      if (!s.out_f32 || s.via_f16) v = make_float4(pool_round_f16(v.x), pool_round_f16(v.y), pool_round_f16(v.z), pool_round_f16(v.w));
+      reinterpret_cast<float4*>(drows + o * 128)[lane] = v;
+    }
+  };
   for (long long page = blockIdx.x; page < in.n_pages; page += gridDim.x) {
     long long r0, o0;
     int t, n_out;
@@ -198,8 +305,13 @@ __global__ void __launch_bounds__(256) pool_tokens_kernel(const PoolInput in, co
           v = range_mean_smem(pool_smem, lo, hi, lane);
         }
         pool_store4(s.out, s.out_f32, o0 + o, lane, v, 0);
+        keep(o, v);
       }
       __syncthreads();
+      if constexpr (DERIVE) {
+        pool_derive_page<kWarps>(d, drows, n_out, page, warp, lane);
+        __syncthreads();
+      }
       continue;
     }
     for (int o = warp; o < n_out; o += kWarps) {
@@ -258,6 +370,7 @@ __global__ void __launch_bounds__(256) pool_tokens_kernel(const PoolInput in, co
         v = range_mean_global(in.in, in.in_f32, r0 + lo, r0 + hi, lane);
       }
       pool_store4(s.out, s.out_f32, o0 + o, lane, v, s.via_f16);
+      keep(o, v);
       if (s.kind == kPoolTileMean && s.out2 && o < n_out - 1) {
         long long e0;
         int e_n;
@@ -275,87 +388,11 @@ __global__ void __launch_bounds__(256) pool_tokens_kernel(const PoolInput in, co
         pool_store4(s.out2, s.out_f32, e0 + o, lane,
                     pool_load4(in.in, in.in_f32, r0 + static_cast<long long>(head) * s.ppt + (o - head), lane), 0);
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ row-level
-struct PoolRowsArgs {
-  PoolInput in;
-  int n_specs;
-  PoolSpecDev specs[kPoolMaxSpecs];
-};
-
-// block = 128 threads (4 warps); one page per block iteration; dynamic smem = max_rows*128 floats.
-__global__ void __launch_bounds__(128) pool_rows_kernel(const PoolRowsArgs a) {
-  extern __shared__ float pool_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kWarps = 4;
-  for (long long page = blockIdx.x; page < a.in.n_pages; page += gridDim.x) {
-    long long r0;
-    int n;
-    pool_page_rows(a.in.in_off, a.in.in_fixed, page, r0, n);
-    for (int r = warp; r < n; r += kWarps)
-      reinterpret_cast<float4*>(pool_smem + r * 128)[lane] = pool_load4(a.in.in, a.in.in_f32, r0 + r, lane);
-    __syncthreads();
-    for (int si = 0; si < a.n_specs; ++si) {
-      const PoolSpecDev& s = a.specs[si];
-      long long o0;
-      int n_out;
-      pool_page_rows(s.out_off, s.out_fixed, page, o0, n_out);
-      for (int o = warp; o < n_out; o += kWarps) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s.kind == kPoolSmooth) {
-          if (s.window == 1 || n == 1) {
-            v = reinterpret_cast<const float4*>(pool_smem + o * 128)[lane];
-          } else {
-            // pooling.py:358-374: taps i-left+t, products rounded to fp32, summed in tap order; weight mass in fp64
-            const int left = s.window / 2;
-            double mass = 0.0;
-            for (int t = 0; t < s.window; ++t) {
-              const int j = o - left + t;
-              if (j < 0 || j >= n) continue;
-              const float w = s.weights[t];
-              const float4 x = reinterpret_cast<const float4*>(pool_smem + j * 128)[lane];
-              v = f4_add(v, make_float4(__fmul_rn(w, x.x), __fmul_rn(w, x.y), __fmul_rn(w, x.z), __fmul_rn(w, x.w)));
-              mass += static_cast<double>(w);
-            }
-            if (mass > 0.0) v = f4_div(v, static_cast<float>(mass));
-            else v = reinterpret_cast<const float4*>(pool_smem + o * 128)[lane];
-          }
-        } else if (s.kind == kPoolTile4n) {
-          int nr = s.n_rows, nc = s.n_cols;
-          if (a.in.grid_hw) {
-            nr = a.in.grid_hw[2 * page];
-            nc = a.in.grid_hw[2 * page + 1];
-          }
-          const int g = nr * nc;
-          if (o >= g) {
-            v = reinterpret_cast<const float4*>(pool_smem + g * 128)[lane];   // global tile copied through
-          } else {
-            const int r = o / nc, c = o - r * nc;
-            int cnt = 0;
-            if (s.include_self) { v = f4_add(v, reinterpret_cast<const float4*>(pool_smem + o * 128)[lane]); ++cnt; }
-            if (r > 0) { v = f4_add(v, reinterpret_cast<const float4*>(pool_smem + (o - nc) * 128)[lane]); ++cnt; }
-            if (r + 1 < nr) { v = f4_add(v, reinterpret_cast<const float4*>(pool_smem + (o + nc) * 128)[lane]); ++cnt; }
-            if (c > 0) { v = f4_add(v, reinterpret_cast<const float4*>(pool_smem + (o - 1) * 128)[lane]); ++cnt; }
-            if (c + 1 < nc) { v = f4_add(v, reinterpret_cast<const float4*>(pool_smem + (o + 1) * 128)[lane]); ++cnt; }
-            v = f4_div(v, static_cast<float>(cnt));
-          }
-        } else if (s.kind == kPoolLegacyConv) {
-          const int r = s.window / 2;
-          int lo, hi;
-          if (s.window == 1 || n == 1) { lo = o; hi = o + 1; }
-          else if (s.window == 3 && n == 2) { lo = (o == 2) ? 1 : 0; hi = (o == 0) ? 1 : 2; }
-          else { lo = max(0, o - 2 * r); hi = min(n - 1, o) + 1; }
-          v = (hi - lo == 1) ? reinterpret_cast<const float4*>(pool_smem + lo * 128)[lane]
-                             : range_mean_smem(pool_smem, lo, hi, lane);
-        } else if (s.kind == kPoolGlobalMean) {
-          if (n > 0) v = range_mean_smem(pool_smem, 0, n, lane);   // empty page -> zeros (visual_embedder.py:838-839)
-        }
-        pool_store4(s.out, s.out_f32, o0 + o, lane, v, s.via_f16);
-      }
+    if constexpr (DERIVE) {
+      __syncthreads();
+      pool_derive_page<kWarps>(d, drows, n_out, page, warp, lane);
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 

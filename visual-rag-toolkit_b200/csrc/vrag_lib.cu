@@ -1271,11 +1271,15 @@ static PoolSpecDev to_dev_spec(const vrag_pool_spec_t& s) {
 }
 
 // Launch the right kernel(s) for `specs` over `in`; every dev spec already has its output pointers set.
+// Specs with input_spec == k > 0 are DERIVED from the output of spec k-1 (a token-level spec of the same call) and
+// are computed inside that spec's pass from the pooled rows held in shared memory. max_out[i]: largest row count
+// spec i produces for any page (shared-memory sizing).
 static int launch_pool(const PoolInput& in, int n, const vrag_pool_spec_t* specs, PoolSpecDev* dev, int max_in_rows,
-                       int max_grid_h, int num_sms, cudaStream_t st, int64_t* launches) {
+                       int max_grid_h, const int* max_out, int num_sms, cudaStream_t st, int64_t* launches) {
   static bool attr_done = false;
   if (!attr_done) {
-    CUDA_OK(cudaFuncSetAttribute(pool_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 512));
+    CUDA_OK(cudaFuncSetAttribute(pool_tokens_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 384 * 512));
+    CUDA_OK(cudaFuncSetAttribute(pool_tokens_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 384 * 512));
     CUDA_OK(cudaFuncSetAttribute(pool_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 512));
     attr_done = true;
   }
@@ -1284,7 +1288,7 @@ static int launch_pool(const PoolInput& in, int n, const vrag_pool_spec_t* specs
   memset(&ra, 0, sizeof(ra));
   ra.in = in;
   for (int i = 0; i < n; ++i) {
-    if (pool_is_row_level(specs[i].kind)) {
+    if (specs[i].input_spec == 0 && pool_is_row_level(specs[i].kind)) {
       if (ra.n_specs >= kPoolMaxSpecs) return fail("too many row-level pooling specs");
       ra.specs[ra.n_specs++] = dev[i];
     }
@@ -1294,9 +1298,9 @@ static int launch_pool(const PoolInput& in, int n, const vrag_pool_spec_t* specs
   // TILE_MEAN + COLSMOL_EXPERIMENTAL (default num_tiles, same patches_per_tile) share one pass over the tokens
   int fused_exp = -1;
   for (int i = 0; i < n && fused_exp < 0; ++i) {
-    if (specs[i].kind != VRAG_POOL_TILE_MEAN) continue;
+    if (specs[i].kind != VRAG_POOL_TILE_MEAN || specs[i].input_spec != 0) continue;
     for (int j = 0; j < n; ++j) {
-      if (specs[j].kind == VRAG_POOL_COLSMOL_EXPERIMENTAL && specs[j].num_tiles <= 0 &&
+      if (specs[j].kind == VRAG_POOL_COLSMOL_EXPERIMENTAL && specs[j].input_spec == 0 && specs[j].num_tiles <= 0 &&
           specs[j].patches_per_tile == specs[i].patches_per_tile && dev[j].out_f32 == dev[i].out_f32) {
         dev[i].out2 = dev[j].out;
         dev[i].out2_off = dev[j].out_off;
@@ -1308,15 +1312,25 @@ static int launch_pool(const PoolInput& in, int n, const vrag_pool_spec_t* specs
   }
   for (int i = 0; i < n; ++i) {
     const int k = specs[i].kind;
-    if (pool_is_row_level(k) || i == fused_exp) continue;
+    if (specs[i].input_spec != 0 || pool_is_row_level(k) || i == fused_exp) continue;
     if (ra.n_specs > 0 && small_pages && (k == VRAG_POOL_LEGACY_CONV || k == VRAG_POOL_GLOBAL_MEAN) &&
         ra.n_specs < kPoolMaxSpecs) {
       ra.specs[ra.n_specs++] = dev[i];
       continue;
     }
-    const size_t smem = (k == VRAG_POOL_ADAPTIVE_ROWS) ? static_cast<size_t>(std::max(max_grid_h, 1)) * 512 : 0;
+    // specs derived from this one
+    PoolRowsArgs d;
+    memset(&d, 0, sizeof(d));
+    d.in = in;
+    for (int j = 0; j < n; ++j)
+      if (specs[j].input_spec == i + 1) d.specs[d.n_specs++] = dev[j];
+    const int grid_rows = (k == VRAG_POOL_ADAPTIVE_ROWS) ? std::max(max_grid_h, 1) : 0;
+    const int keep_rows = d.n_specs > 0 ? std::max(max_out[i], 1) : 0;
+    if (grid_rows + keep_rows > 384) return fail("pooling: %d staged rows per page exceed shared memory", grid_rows + keep_rows);
+    const size_t smem = static_cast<size_t>(grid_rows + keep_rows) * 512;
     const unsigned grid = static_cast<unsigned>(std::min<long long>(in.n_pages, static_cast<long long>(num_sms) * 8));
-    pool_tokens_kernel<<<grid, 256, smem, st>>>(in, dev[i]);
+    if (d.n_specs > 0) pool_tokens_kernel<true><<<grid, 256, smem, st>>>(in, dev[i], d, grid_rows * 128);
+    else pool_tokens_kernel<false><<<grid, 256, smem, st>>>(in, dev[i], d, grid_rows * 128);
     if (launches) ++*launches;
   }
   if (ra.n_specs > 0) {
@@ -1335,6 +1349,7 @@ static int launch_pool(const PoolInput& in, int n, const vrag_pool_spec_t* specs
 extern "C" int vrag_pool_page(int device, const vrag_pool_spec_t* spec, const void* in, int in_dtype, int64_t in_rows,
                               void* out, int out_dtype, int64_t out_capacity_rows, int64_t* out_rows) {
   if (!spec || !out_rows) return fail("NULL argument");
+  if (spec->input_spec != 0) return fail("input_spec must be 0 for a single pooling call");
   if ((in_dtype != VRAG_F16 && in_dtype != VRAG_F32) || (out_dtype != VRAG_F16 && out_dtype != VRAG_F32))
     return fail("unknown dtype");
   if (in_rows < 0) return fail("in_rows < 0");
@@ -1383,7 +1398,8 @@ extern "C" int vrag_pool_page(int device, const vrag_pool_spec_t* spec, const vo
     }
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
-    rc = launch_pool(pin, 1, spec, &dev, static_cast<int>(in_rows), gh, prop.multiProcessorCount, st, nullptr);
+    const int mo = static_cast<int>(n_out);
+    rc = launch_pool(pin, 1, spec, &dev, static_cast<int>(in_rows), gh, &mo, prop.multiProcessorCount, st, nullptr);
     if (rc == 0 && cudaMemcpyAsync(out, d_out, out_b, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = fail("D2H copy failed");
     if (rc == 0) {
       cudaError_t e = cudaStreamSynchronize(st);
@@ -1408,21 +1424,34 @@ extern "C" int vrag_store_pool(vrag_corpus_t* c, const char* src, int n_specs, c
   // 1. shapes
   std::vector<std::vector<int64_t>> offs(n_specs);
   std::vector<int64_t> fixed(n_specs, 0);
+  std::vector<int> max_out(n_specs, 0);
   int max_gh = 0;
   for (int i = 0; i < n_specs; ++i) {
     if (!dst_names[i] || !*dst_names[i]) return fail("dst name %d is empty", i);
     if (std::string(dst_names[i]) == src) return fail("dst store must differ from src");
+    const int par = specs[i].input_spec - 1;   // -1: the source store
+    if (par >= i) return fail("spec %d: input_spec must name an earlier spec", i);
+    if (par >= 0) {
+      const int pk = specs[par].kind;
+      if (specs[par].input_spec != 0 || pool_is_row_level(pk))
+        return fail("spec %d: derived specs must hang off a token-level spec of the source store", i);
+      const int k = specs[i].kind;
+      if (!(pool_is_row_level(k) || k == VRAG_POOL_LEGACY_CONV || k == VRAG_POOL_GLOBAL_MEAN))
+        return fail("spec %d: kind %d cannot be derived from pooled rows", i, k);
+    }
     offs[i].resize(n_pages + 1);
     offs[i][0] = 0;
     bool all_same = true;
     for (int64_t p = 0; p < n_pages; ++p) {
-      const int64_t t = sp->fixed_rows > 0 ? sp->fixed_rows : (sp->h_offsets[p + 1] - sp->h_offsets[p]);
+      const int64_t t = par >= 0 ? (offs[par][p + 1] - offs[par][p])
+                                 : (sp->fixed_rows > 0 ? sp->fixed_rows : (sp->h_offsets[p + 1] - sp->h_offsets[p]));
       int gh, gw;
       pool_grid_of(specs[i], grid_hw, p, &gh, &gw);
       int64_t r = 0;
       TRY(pool_out_rows(specs[i], t, gh, gw, &r));
       if (specs[i].kind == VRAG_POOL_ADAPTIVE_ROWS) max_gh = std::max(max_gh, gh);
       offs[i][p + 1] = offs[i][p] + r;
+      max_out[i] = std::max<int>(max_out[i], static_cast<int>(r));
       if (p > 0 && r != offs[i][1]) all_same = false;
     }
     if (all_same && n_pages > 0 && offs[i][1] > 0) fixed[i] = offs[i][1];
@@ -1459,8 +1488,8 @@ extern "C" int vrag_store_pool(vrag_corpus_t* c, const char* src, int n_specs, c
   pin.n_pages = n_pages;
   pin.grid_hw = d_grid;
   CUDA_OK(cudaEventRecord(c->ev0, c->stream));
-  int rc = launch_pool(pin, n_specs, specs, dev.data(), static_cast<int>(sp->max_rows), max_gh, c->num_sms, c->stream,
-                       &c->launches);
+  int rc = launch_pool(pin, n_specs, specs, dev.data(), static_cast<int>(sp->max_rows), max_gh, max_out.data(), c->num_sms,
+                       c->stream, &c->launches);
   CUDA_OK(cudaEventRecord(c->ev1, c->stream));
   if (rc == 0) {
     for (int i = 0; i < n_specs; ++i) {

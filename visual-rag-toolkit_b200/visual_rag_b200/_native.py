@@ -49,6 +49,7 @@ class PoolSpec(C.Structure):
         ("has_global", C.c_int),
         ("include_self", C.c_int),
         ("via_f16", C.c_int),
+        ("input_spec", C.c_int),
     ]
 
 

@@ -156,6 +156,13 @@ def spec_seq_chunks(target_rows: int) -> N.PoolSpec:
     return N.PoolSpec(kind=N.POOL_SEQ_CHUNKS, target_rows=int(target_rows))
 
 
+def derived_from(spec: N.PoolSpec, index: int) -> N.PoolSpec:
+    """Chain `spec` to the OUTPUT of spec number `index` of the same GpuCorpus.pool_store call (the pipeline's
+    experimental / global pooling of the mean-pooled rows, pipeline.py:452-507): computed in that spec's pass."""
+    spec.input_spec = int(index) + 1
+    return spec
+
+
 # ------------------------------------------------------------------------------------------------ p1 .. p8
 def tile_level_mean_pooling(embedding, num_tiles: int, patches_per_tile: int = 64, output_dtype=None) -> np.ndarray:
     """pooling.py:35-98. `num_tiles` only matters when it matches T / patches_per_tile (otherwise it is
