@@ -105,14 +105,20 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_sample_pages_per_s(docs_f32, query, n_threads_note=True):
+def cpu_sample_pages_per_s(docs_f32, queries, min_seconds=10.0, max_passes=200):
     """The oracle's search_exhaustive (= the reference's client-side CPU path, quick_test.py:158-166) timed on
-    a bounded sample. Returns (pages/s, seconds, blas_threads)."""
+    a bounded sample: one query after the other over the sampled pages until `min_seconds` of CPU work are done.
+    Returns (pages/s, seconds, blas_threads, passes)."""
     from oracle import maxsim_oracle as MO
 
     t0 = time.perf_counter()
-    MO.search_exhaustive(query, docs_f32, TOP_K)
-    dt = time.perf_counter() - t0
+    passes = 0
+    while True:
+        MO.search_exhaustive(queries[passes % len(queries)], docs_f32, TOP_K)
+        passes += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds or passes >= max_passes:
+            break
     threads = 1
     try:
         from threadpoolctl import threadpool_info
@@ -120,7 +126,7 @@ def cpu_sample_pages_per_s(docs_f32, query, n_threads_note=True):
         threads = max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
     except Exception:
         pass
-    return len(docs_f32) / dt, dt, threads
+    return passes * len(docs_f32) / dt, dt, threads, passes
 
 
 def host_sample(n_pages, seed):
@@ -281,6 +287,16 @@ def run_ours(args):
     torch.cuda.synchronize()
     # each score_dev = query_prep (tiny) + the scan kernel; the prep kernel is ~2 us of the ~20 ms
     kern_ms = k0.elapsed_time(k1) / args.steps
+    # same launch with the opt-in fp16 query operand (VRAG_Q_FP16): half the tensor work, scores within ~1e-4 relative
+    fl16 = query_flags(True, False, True)
+    corpus.score_dev("initial", searcher._q_dev.data_ptr(), nq, fl16, 0, pages, scores_buf.data_ptr(), stream)
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(args.steps):
+        corpus.score_dev("initial", searcher._q_dev.data_ptr(), nq, fl16, 0, pages, scores_buf.data_ptr(), stream)
+    k1.record()
+    torch.cuda.synchronize()
+    kern16_ms = k0.elapsed_time(k1) / args.steps
 
     # ---------------- end to end through the host API ----------------
     for i in range(args.warmup):
@@ -323,7 +339,7 @@ def run_ours(args):
         # CPU baseline on a bounded sample of the SAME corpus (pages read back from the device)
         n_cpu = args.cpu_sample_pages
         docs = [corpus.read_page("initial", p).astype(np.float32) for p in range(n_cpu)]
-        cpu_pps, cpu_s, blas_threads = cpu_sample_pages_per_s(docs, queries[0])
+        cpu_pps, cpu_s, blas_threads, cpu_passes = cpu_sample_pages_per_s(docs, queries, args.cpu_seconds)
         gpu_top = corpus.search("initial", queries[0], TOP_K, candidate_ids=list(range(corpus.page_base, corpus.page_base + n_cpu)))
         from oracle import maxsim_oracle as MO
 
@@ -357,12 +373,16 @@ def run_ours(args):
                          "frac_of_8TBs_nominal": achieved / 8000.0,
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": pages * bytes_per_page,
                          "traffic": (args.ncu_traffic_ratio * pages * bytes_per_page) if args.ncu_traffic_ratio else None,
-                         "traffic_source": "dram__bytes_read+write per launch / algorithmic bytes = 1.0026 in the ncu --set full "
-                                           "capture at 100k pages per launch (profiles/r1_scan_kernel_ncu_summary.md), scaled to this launch"},
+                         "traffic_source": "dram__bytes_read+write per launch / algorithmic bytes = 1.0014 in the ncu --set full "
+                                           "capture at 100k pages per launch (profiles/r1b_kernels_ncu_summary.md, column `large`), scaled to this launch"},
             "cpu_baseline": {"value": cpu_pps, "unit": "pages/s", "cores": blas_threads, "kind": "port",
-                             "sample": f"first {n_cpu} pages of the same corpus read back from the device, one query, "
-                                       f"{cpu_s:.1f} s; oracle/maxsim_oracle.py::search_exhaustive (single process, numpy BLAS threads={blas_threads})",
+                             "sample": f"first {n_cpu} pages of the same corpus read back from the device, {cpu_passes} queries one after "
+                                       f"the other ({cpu_passes * n_cpu} page scorings, {cpu_s:.1f} s); oracle/maxsim_oracle.py::search_exhaustive "
+                                       f"(single process, numpy BLAS threads={blas_threads})",
                              "topk_matches_gpu": bool(parity_ok)},
+            "fp16_query_variant": {"flag": "VRAG_Q_FP16 (opt-in; default is the fp32-exact hi/lo query)", "kernel_ms": kern16_ms,
+                                   "hbm_gbs": pages * bytes_per_page / (kern16_ms * 1e-3) / 1e9,
+                                   "frac": pages * bytes_per_page / (kern16_ms * 1e-3) / 1e9 / peak},
             "two_stage": {"mode": "tokens_vs_standard_pooling", "prefetch_k": PREFETCH_K, "top_k": TOP_K,
                           "qps": n_lat / ts_wall, "p50_ms": p50, "p95_ms": p95, "queries": n_lat,
                           "pooled_rows_per_page": POOLED_ROWS,
@@ -372,11 +392,97 @@ def run_ours(args):
                         "hbm_gbs": pages * (TOKENS * 256 + POOLED_ROWS * 256) / (pool_ms * 1e-3) / 1e9},
             "last_top1": [float(last[0][0]), int(last[1][0])] if last is not None and len(last[0]) else None,
         }
+        if world == 1 and args.extras:
+            try:
+                line.update(run_extras(corpus, args, peak, kern_ms))
+            except Exception as e:  # extras must never cost the headline line
+                line["extras_error"] = repr(e)
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
     corpus.close()
     return 0
+
+
+def run_extras(corpus, args, peak, kern_ms):
+    """N=1 only, after the headline measurements: the other BASELINE configs on the same GPU.
+      three_stage_batched : cfg2 — ColQwen2.5-shaped variable pages, 256 queries, global -> experimental -> MaxSim.
+      exhaustive_batched  : 4 queries share every document tile (tensor-pipe-heavier variant of the headline scan).
+      pooling_cfg4        : cfg4 — all pooled stores of a ColPali / ColSmol collection derived in one pass."""
+    from visual_rag_b200.embedding import pooling as GP
+
+    out = {}
+    rng = np.random.default_rng(SEED + 99)
+    # ---- batched exhaustive on the headline corpus
+    q4 = [rng.standard_normal((Q_TOKENS, 128)).astype(np.float32) for _ in range(4)]
+    for _ in range(2):
+        corpus.search_multistage_batch([("initial", False, TOP_K)], q4)
+    corpus.search_multistage_batch([("initial", False, TOP_K)], q4)
+    ms = corpus.last_timing_ms()[0]
+    pages = corpus.n_pages("initial")
+    out["exhaustive_batched"] = {"queries_per_pass": 4, "ms_per_pass": ms, "page_scorings_per_s": 4 * pages / (ms * 1e-3),
+                                 "speedup_vs_single_query": 4 * kern_ms / ms}
+    for nm in ("initial", "mean_pooling"):
+        corpus.drop_store(nm)
+    # ---- cfg2
+    n = args.cfg2_pages
+    h = rng.integers(16, 33, size=n)
+    w = np.minimum(rng.integers(16, 33, size=n), 768 // h)
+    off = np.concatenate([[0], np.cumsum(h * w)]).astype(np.int64)
+    offp = np.concatenate([[0], np.cumsum(np.minimum(h, 32))]).astype(np.int64)
+    corpus.add_synthetic_store("initial", 0, page_offsets=off, seed=SEED + 1)
+    corpus.add_synthetic_store("experimental_pooling", 0, page_offsets=offp, seed=SEED + 2)
+    corpus.add_synthetic_store("global_pooling", n, fixed_rows=1, seed=SEED + 3)
+    nq = 256
+    queries = [rng.standard_normal((int(rng.integers(10, 31)), 128)).astype(np.float32) for _ in range(nq)]
+    stages = [("global_pooling", True, 1000), ("experimental_pooling", False, 300), ("initial", False, 100)]
+    for _ in range(2):
+        corpus.search_multistage_batch(stages, queries)
+    walls = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        res = corpus.search_multistage_batch(stages, queries)
+        walls.append(time.perf_counter() - t0)
+    dev_ms = corpus.last_timing_ms()[0]
+    t0 = time.perf_counter()
+    for q in queries[:32]:
+        single = corpus.search_multistage(stages, q)
+    seq_ms = 1e3 * (time.perf_counter() - t0) / 32
+    same = bool(np.array_equal(single[2][1], res[31][2][1]))
+    out["three_stage_batched"] = {
+        "workload": f"cfg2: {n} ColQwen2.5-shaped pages (H,W in [16,32], T=H*W<=768, {int(off[-1])} tokens = {off[-1] * 256 / 1e9:.1f} GB), "
+                    f"pooled rows min(H,32), global 1 row; {nq} queries with 10..30 tokens; stage1_k=1000, stage2_k=300, top_k=100",
+        "batch_wall_ms": 1e3 * float(np.median(walls)), "batch_device_ms": dev_ms, "qps": nq / float(np.median(walls)),
+        "ms_per_query_batched": 1e3 * float(np.median(walls)) / nq, "ms_per_query_sequential_api": seq_ms,
+        "last_query_matches_single_query_path": same}
+    for nm in ("initial", "experimental_pooling", "global_pooling"):
+        corpus.drop_store(nm)
+    # ---- cfg4
+    npg = args.cfg4_pages
+    corpus.add_synthetic_store("vis", npg, fixed_rows=1024, seed=SEED + 4)
+    specs = [GP.spec_adaptive_rows(32, 32, 32)] + [GP.derived_from(x, 0) for x in (
+        GP.spec_legacy_conv(3), GP.spec_smooth(3, "gaussian"), GP.spec_smooth(3, "triangular"), GP.spec_global_mean(True))]
+    names = ["mean_pooling", "experimental_pooling", "experimental_pooling_gaussian", "experimental_pooling_triangular", "global_pooling"]
+    for _ in range(3):
+        ms = corpus.pool_store("vis", specs, names)
+    b = npg * (1024 * 256 + (32 + 34 + 32 + 32 + 1) * 256)
+    out["pooling_cfg4"] = {"colpali": {"pages": npg, "ms": ms, "pages_per_s": npg / (ms * 1e-3), "hbm_gbs_algorithmic": b / (ms * 1e-3) / 1e9,
+                                       "frac_of_peak": b / (ms * 1e-3) / 1e9 / peak,
+                                       "stores": "row-mean 32 + legacy k=3 (34) + gaussian (32) + triangular (32) + global (1), one pass"}}
+    for nm in names + ["vis"]:
+        corpus.drop_store(nm)
+    corpus.add_synthetic_store("smol", npg, fixed_rows=832, seed=SEED + 5)
+    g = np.tile(np.array([[4, 3]], dtype=np.int32), (npg, 1))
+    specs = [GP.spec_tile_mean(64), GP.spec_colsmol_experimental(0, 64), GP.derived_from(GP.spec_tile_4n(0, 0), 0),
+             GP.derived_from(GP.spec_global_mean(True), 0)]
+    names = ["mean_pooling", "experimental_pooling", "experimental_pooling_2d", "global_pooling"]
+    for _ in range(3):
+        ms = corpus.pool_store("smol", specs, names, grid_hw=g)
+    b = npg * (832 * 256 + (13 + 76 + 13 + 1) * 256)
+    out["pooling_cfg4"]["colsmol"] = {"pages": npg, "ms": ms, "pages_per_s": npg / (ms * 1e-3),
+                                      "hbm_gbs_algorithmic": b / (ms * 1e-3) / 1e9, "frac_of_peak": b / (ms * 1e-3) / 1e9 / peak,
+                                      "stores": "tile mean 13 + experimental 76 + 4-neighbour 13 + global 1, one pass"}
+    return out
 
 
 def main():
@@ -387,9 +493,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pages-per-gpu", type=int, default=500_000)
     ap.add_argument("--cpu-sample-pages", type=int, default=3000)
-    ap.add_argument("--ref-sample-pages", type=int, default=4096)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work of the cpu_baseline leg")
+    ap.add_argument("--extras", type=int, default=1, help="0: skip the cfg2 / cfg4 / batched extra sections")
+    ap.add_argument("--ref-sample-pages", type=int, default=16384)
     ap.add_argument("--latency-queries", type=int, default=200)
-    ap.add_argument("--ncu-traffic-ratio", type=float, default=1.0026,
+    ap.add_argument("--cfg2-pages", type=int, default=1_000_000)
+    ap.add_argument("--cfg4-pages", type=int, default=400_000)
+    ap.add_argument("--ncu-traffic-ratio", type=float, default=1.0014,
                     help="DRAM bytes / algorithmic bytes of the scan kernel in the committed ncu capture (profiles/)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -36,6 +36,9 @@ typedef struct vrag_corpus vrag_corpus_t;
 /* query flags */
 #define VRAG_Q_NORMALIZE 1u  /* L2-normalise query rows and document rows (cosine); pooling.py:495-503 */
 #define VRAG_Q_POOL 2u       /* mean-pool the query tokens to one row first; two_stage.py:142,148,154 */
+#define VRAG_Q_FP16 4u       /* opt-in: contract the query as plain fp16 instead of the exact fp16 hi/lo pair (scores then carry
+                                the fp16 rounding of the query, ~1e-4 relative, still inside the 1e-3 parity gate); halves the
+                                tensor work of scans over stores with > 128 rows per page. Default (flag clear): fp32-exact query. */
 
 const char* vrag_last_error(void);
 int vrag_abi_version(void);
@@ -54,6 +57,12 @@ int vrag_corpus_destroy(vrag_corpus_t* c);
  * rows_on_device != 0: `rows` is a device pointer (copied device-to-device).                      */
 int vrag_store_add(vrag_corpus_t* c, const char* name, const void* rows, int dtype, int rows_on_device,
                    const int64_t* page_offsets, int64_t n_pages, int64_t fixed_rows);
+
+/* Append pages behind the existing pages of a named store (the store is created on first use). This is the ingest path
+ * of QdrantIndexer.upload_batch (visual_rag/indexing/qdrant_indexer.py:341-507): one call per uploaded batch and named
+ * vector; page index = upload order. Same arguments as vrag_store_add (page_offsets are relative to this batch).  */
+int vrag_store_append(vrag_corpus_t* c, const char* name, const void* rows, int dtype, int rows_on_device,
+                      const int64_t* page_offsets, int64_t n_pages, int64_t fixed_rows);
 
 /* Fill a named store with the seeded synthetic corpus of SURVEY.md 8(d) directly on the device
  * (gaussian rows, L2-normalised, rounded to fp16).  Row r of the store depends only on (seed, row_seed_base + r). */

@@ -512,3 +512,80 @@ def test_fused_topk_prefilter_is_exact(corpus, layout, pool, k, monkeypatch):
     q = queries[0].mean(axis=0, keepdims=True) if pool else queries[0]
     assert abs(MO.maxsim_score(q, page) - float(got[0][0][0][0])) <= RTOL * abs(float(got[0][0][0][0])) + ATOL
     corpus.drop_store("pf")
+
+
+@pytest.mark.gpu
+def test_fp16_query_flag_is_inside_the_parity_gate(corpus):
+    """VRAG_Q_FP16 (opt-in): scores carry the fp16 rounding of the query — well inside the 1e-3 gate — and the exact
+    default is unchanged."""
+    from visual_rag_b200 import _native as N
+    import ctypes as C
+
+    rng = np.random.default_rng(12)
+    n, t = 64, 700
+    rows = rows16(31, n * t)
+    corpus.add_store("fq", rows, fixed_rows=t)
+    q = rng.standard_normal((20, 128)).astype(np.float32)
+    exact = corpus.score("fq", q)
+    out = np.empty((n,), np.float32)
+    N.check(corpus._lib.vrag_score(corpus._h, b"fq", q.ctypes.data_as(C.POINTER(C.c_float)), 20,
+                                   N.VRAG_Q_NORMALIZE | N.VRAG_Q_FP16, None, 0, out.ctypes.data_as(C.POINTER(C.c_float))))
+    want = np.array(MO.maxsim_batch(q, [rows[i * t:(i + 1) * t].astype(np.float32) for i in range(n)]))
+    np.testing.assert_allclose(exact, want, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(out, want, rtol=5e-4)
+    assert np.abs(out - want).max() > 0          # it really is the reduced-precision path
+    corpus.drop_store("fq")
+
+
+@pytest.mark.gpu
+def test_indexer_upload_batches_equals_bulk_store():
+    """GpuIndexer.upload_batch (append path, qdrant_indexer.py:341-507) in several batches == one bulk add_store:
+    same search results, fp32 -> fp16 store cast, global = mean(tile_pooled) fallback, ids/payloads served."""
+    from visual_rag_b200.client import GpuCorpusClient
+    from visual_rag_b200.corpus import GpuCorpus
+    from visual_rag_b200.indexing import GpuIndexer
+    from visual_rag_b200.retrieval import ThreeStageRetriever, TwoStageRetriever
+
+    rng = np.random.default_rng(21)
+    n = 57
+    pts = []
+    for i in range(n):
+        t = int(rng.integers(140, 420))
+        r = int(rng.integers(10, 33))
+        vis = rng.standard_normal((t, 128)).astype(np.float32)
+        tile = rng.standard_normal((r, 128)).astype(np.float32)
+        p = {"id": GpuIndexer.generate_point_id("doc.pdf", i), "visual_embedding": vis, "tile_pooled_embedding": tile,
+             "experimental_pooled_embedding": {"experimental_pooling": rng.standard_normal((r, 128)).astype(np.float32)},
+             "metadata": {"filename": "doc.pdf", "page_number": i, "year": 2020 + i % 2}}
+        if i % 3:
+            p["global_pooled_embedding"] = rng.standard_normal((128,)).astype(np.float32)
+        pts.append(p)
+    with GpuCorpus(0) as c1, GpuCorpus(0) as c2:
+        idx = GpuIndexer(c1, "c")
+        assert idx.create_collection(force_recreate=True)
+        up = 0
+        for lo, hi in ((0, 1), (1, 20), (20, 21), (21, 57)):
+            up += idx.upload_batch(pts[lo:hi])
+        assert up == n and idx.check_exists(pts[5]["id"]) and not idx.check_exists("nope")
+        with pytest.raises(ValueError):
+            idx.upload_batch(pts[:1])
+        # bulk twin
+        def cat(key, f=lambda p: p):
+            mats = [np.asarray(f(p), np.float32).reshape(-1, 128) for p in pts]
+            return np.concatenate(mats).astype(np.float16), np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])])
+        for name, f in (("initial", lambda p: p["visual_embedding"]), ("mean_pooling", lambda p: p["tile_pooled_embedding"]),
+                        ("experimental_pooling", lambda p: p["experimental_pooled_embedding"]["experimental_pooling"]),
+                        ("global_pooling", lambda p: p.get("global_pooled_embedding", p["tile_pooled_embedding"].mean(axis=0)))):
+            rows, off = cat(name, f)
+            c2.add_store(name, rows, page_offsets=off)
+            assert np.array_equal(c1.read_rows(name, 0, rows.shape[0]).view(np.uint16), rows.view(np.uint16))
+        client2 = GpuCorpusClient(c2, "c", point_ids=[p["id"] for p in pts], payloads=[p["metadata"] for p in pts])
+        q = rng.standard_normal((17, 128)).astype(np.float32)
+        a = TwoStageRetriever(idx.client, "c").search_server_side(q, top_k=5, prefetch_k=20, stage1_mode="tokens_vs_standard_pooling")
+        b = TwoStageRetriever(client2, "c").search_server_side(q, top_k=5, prefetch_k=20, stage1_mode="tokens_vs_standard_pooling")
+        assert [r["id"] for r in a] == [r["id"] for r in b] and [r["score_final"] for r in a] == [r["score_final"] for r in b]
+        assert a[0]["payload"]["filename"] == "doc.pdf"
+        a3 = ThreeStageRetriever(idx.client, "c").search_server_side(query_embedding=q, top_k=5, stage1_k=30, stage2_k=12)
+        b3 = ThreeStageRetriever(client2, "c").search_server_side(query_embedding=q, top_k=5, stage1_k=30, stage2_k=12)
+        assert [r["id"] for r in a3] == [r["id"] for r in b3]
+        assert idx.get_existing_ids("doc.pdf") == {p["id"] for p in pts}

@@ -94,6 +94,8 @@ struct Store {
   long long* tile_row0 = nullptr;  // first row of each tile [n_tiles+1]
   int64_t n_tiles = 0;
   int64_t n_pages = 0, total_rows = 0, fixed_rows = 0, max_rows = 0;
+  int64_t cap_rows = 0;          // allocated rows (>= total_rows; vrag_store_append grows geometrically)
+  bool dirty = false;            // appended to since the page tables / tensor maps were last built
   bool packed = false;
   CUtensorMap tm128, tm32, ts128, ts32;
 };
@@ -256,12 +258,20 @@ static int ensure_host_out(vrag_corpus* c, size_t n) {
 
 // page layout bookkeeping + tensor maps once rows/inv are in place
 static int finish_store(vrag_corpus* c, Store& s, const int64_t* page_offsets, int64_t n_pages, int64_t fixed_rows) {
+  if (s.offsets) cudaFree(s.offsets);
+  if (s.tile_page0) cudaFree(s.tile_page0);
+  if (s.tile_row0) cudaFree(s.tile_row0);
+  s.offsets = nullptr;
+  s.tile_page0 = nullptr;
+  s.tile_row0 = nullptr;
+  s.n_tiles = 0;
+  s.dirty = false;
   s.n_pages = n_pages;
   s.fixed_rows = fixed_rows;
   if (fixed_rows > 0) {
     s.max_rows = fixed_rows;
   } else {
-    s.h_offsets.assign(page_offsets, page_offsets + n_pages + 1);
+    if (page_offsets != s.h_offsets.data()) s.h_offsets.assign(page_offsets, page_offsets + n_pages + 1);
     int64_t mx = 0;
     for (int64_t i = 0; i < n_pages; ++i) mx = std::max(mx, page_offsets[i + 1] - page_offsets[i]);
     s.max_rows = mx;
@@ -328,6 +338,7 @@ static int alloc_store(vrag_corpus* c, const char* name, int64_t total_rows, Sto
   }
   Store s;
   s.total_rows = total_rows;
+  s.cap_rows = total_rows;
   if (total_rows > 0) {
     CUDA_OK(cudaMalloc(&s.rows, static_cast<size_t>(total_rows) * 128 * sizeof(__half)));
     cudaError_t e = cudaMalloc(&s.inv, static_cast<size_t>(total_rows) * sizeof(float));
@@ -341,6 +352,41 @@ static int alloc_store(vrag_corpus* c, const char* name, int64_t total_rows, Sto
   return 0;
 }
 
+// rows (host or device, fp16 or fp32) -> fp16 rows at dst + their inverse norms. fp32 is cast exactly like
+// QdrantIndexer._build_qdrant_points (qdrant_indexer.py:423-441).
+static int upload_rows(vrag_corpus* c, __half* dst, float* dst_inv, const void* rows, int dtype, int rows_on_device,
+                       int64_t n_rows) {
+  const size_t n_el = static_cast<size_t>(n_rows) * 128;
+  const cudaMemcpyKind kind = rows_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (dtype == VRAG_F16) {
+    // all copies go through the library stream: the kernels below run on it (a non-blocking stream does not
+    // order against the legacy default stream a plain cudaMemcpy uses)
+    CUDA_OK(cudaMemcpyAsync(dst, rows, n_el * sizeof(__half), kind, c->stream));
+  } else {
+    const size_t chunk = size_t(32) << 20;  // elements per staging chunk
+    float* tmp = nullptr;
+    const float* src_base = static_cast<const float*>(rows);
+    if (!rows_on_device) CUDA_OK(cudaMalloc(&tmp, std::min(chunk, n_el) * sizeof(float)));
+    for (size_t o = 0; o < n_el; o += chunk) {
+      const size_t n = std::min(chunk, n_el - o);
+      const float* src = src_base + o;
+      if (!rows_on_device) {
+        CUDA_OK(cudaMemcpyAsync(tmp, src, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        src = tmp;
+      }
+      f32_to_f16_kernel<<<static_cast<unsigned>((n / 4 + 256) / 256), 256, 0, c->stream>>>(src, n, dst + o);
+      c->launches++;
+      CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+    if (tmp) cudaFree(tmp);
+  }
+  const long long threads = n_rows * 16;
+  inv_norm_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, c->stream>>>(dst, n_rows, dst_inv);
+  c->launches++;
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 extern "C" int vrag_store_add(vrag_corpus_t* c, const char* name, const void* rows, int dtype, int rows_on_device,
                               const int64_t* page_offsets, int64_t n_pages, int64_t fixed_rows) {
   if (!c) return fail("corpus is NULL");
@@ -351,37 +397,73 @@ extern "C" int vrag_store_add(vrag_corpus_t* c, const char* name, const void* ro
   if (total_rows > 0 && !rows) return fail("rows is NULL");
   Store* s = nullptr;
   TRY(alloc_store(c, name, total_rows, &s));
-  const size_t n_el = static_cast<size_t>(total_rows) * 128;
-  if (total_rows > 0) {
-    const cudaMemcpyKind kind = rows_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (dtype == VRAG_F16) {
-      // all copies go through the library stream: the kernels below run on it (a non-blocking stream does not
-      // order against the legacy default stream a plain cudaMemcpy uses)
-      CUDA_OK(cudaMemcpyAsync(s->rows, rows, n_el * sizeof(__half), kind, c->stream));
-    } else {
-      const size_t chunk = size_t(32) << 20;  // elements per staging chunk
-      float* tmp = nullptr;
-      const float* src_base = static_cast<const float*>(rows);
-      if (!rows_on_device) CUDA_OK(cudaMalloc(&tmp, std::min(chunk, n_el) * sizeof(float)));
-      for (size_t o = 0; o < n_el; o += chunk) {
-        const size_t n = std::min(chunk, n_el - o);
-        const float* src = src_base + o;
-        if (!rows_on_device) {
-          CUDA_OK(cudaMemcpyAsync(tmp, src, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-          src = tmp;
-        }
-        f32_to_f16_kernel<<<static_cast<unsigned>((n / 4 + 256) / 256), 256, 0, c->stream>>>(src, n, s->rows + o);
-        c->launches++;
-        CUDA_OK(cudaStreamSynchronize(c->stream));
-      }
-      if (tmp) cudaFree(tmp);
-    }
-    const long long threads = total_rows * 16;
-    inv_norm_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, c->stream>>>(s->rows, total_rows, s->inv);
-    c->launches++;
-    CUDA_OK(cudaStreamSynchronize(c->stream));
-  }
+  if (total_rows > 0) TRY(upload_rows(c, s->rows, s->inv, rows, dtype, rows_on_device, total_rows));
   return finish_store(c, *s, page_offsets, n_pages, fixed_rows);
+}
+
+// Append pages to a named store (created on first use): the ingest path of QdrantIndexer.upload_batch
+// (qdrant_indexer.py:341-507) — every batch of points adds its pages behind the existing ones; page index = upload
+// order. Device buffers grow geometrically; page tables and tensor maps are rebuilt lazily on the next use.
+extern "C" int vrag_store_append(vrag_corpus_t* c, const char* name, const void* rows, int dtype, int rows_on_device,
+                                 const int64_t* page_offsets, int64_t n_pages, int64_t fixed_rows) {
+  if (!c) return fail("corpus is NULL");
+  if (!name || !*name) return fail("store name is empty");
+  auto it = c->stores.find(name);
+  if (it == c->stores.end()) return vrag_store_add(c, name, rows, dtype, rows_on_device, page_offsets, n_pages, fixed_rows);
+  TRY(set_device(c));
+  if (dtype != VRAG_F16 && dtype != VRAG_F32) return fail("unknown dtype %d", dtype);
+  int64_t new_rows = 0;
+  TRY(check_layout(page_offsets, n_pages, fixed_rows, &new_rows));
+  if (n_pages == 0) return 0;
+  if (new_rows > 0 && !rows) return fail("rows is NULL");
+  Store& s = it->second;
+  const int64_t total = s.total_rows + new_rows;
+  if (total >= (1ll << 31)) return fail("a store holds at most 2^31-1 rows per shard (TMA coordinates are int32)");
+  if (s.n_pages + n_pages >= (1ll << 31)) return fail("a shard holds at most 2^31-1 pages");
+  // ---- page layout: stay fixed-rows only if every new page has the same row count
+  bool stay_fixed = s.fixed_rows > 0;
+  if (stay_fixed) {
+    if (fixed_rows > 0) stay_fixed = fixed_rows == s.fixed_rows;
+    else
+      for (int64_t i = 0; i < n_pages && stay_fixed; ++i) stay_fixed = (page_offsets[i + 1] - page_offsets[i]) == s.fixed_rows;
+  }
+  if (!stay_fixed) {
+    if (s.fixed_rows > 0 || s.h_offsets.empty()) {   // materialise the offsets of the existing pages
+      s.h_offsets.resize(s.n_pages + 1);
+      for (int64_t i = 0; i <= s.n_pages; ++i) s.h_offsets[i] = i * s.fixed_rows;
+    }
+    for (int64_t i = 0; i < n_pages; ++i) {
+      const int64_t r = fixed_rows > 0 ? fixed_rows : (page_offsets[i + 1] - page_offsets[i]);
+      s.h_offsets.push_back(s.h_offsets.back() + r);
+    }
+    s.fixed_rows = 0;
+  }
+  // ---- grow
+  if (total > s.cap_rows) {
+    const int64_t cap = std::min<int64_t>((1ll << 31) - 1, std::max<int64_t>(total, s.cap_rows + s.cap_rows / 2 + 1024));
+    __half* nr = nullptr;
+    float* ni = nullptr;
+    CUDA_OK(cudaMalloc(&nr, static_cast<size_t>(cap) * 128 * sizeof(__half)));
+    if (cudaMalloc(&ni, static_cast<size_t>(cap) * sizeof(float)) != cudaSuccess) {
+      cudaFree(nr);
+      return fail("cudaMalloc(inv) failed while growing store '%s'", name);
+    }
+    if (s.total_rows > 0) {
+      CUDA_OK(cudaMemcpyAsync(nr, s.rows, static_cast<size_t>(s.total_rows) * 256, cudaMemcpyDeviceToDevice, c->stream));
+      CUDA_OK(cudaMemcpyAsync(ni, s.inv, static_cast<size_t>(s.total_rows) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+      CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+    if (s.rows) cudaFree(s.rows);
+    if (s.inv) cudaFree(s.inv);
+    s.rows = nr;
+    s.inv = ni;
+    s.cap_rows = cap;
+  }
+  if (new_rows > 0) TRY(upload_rows(c, s.rows + static_cast<size_t>(s.total_rows) * 128, s.inv + s.total_rows, rows, dtype, rows_on_device, new_rows));
+  s.total_rows = total;
+  s.n_pages += n_pages;
+  s.dirty = true;
+  return 0;
 }
 
 extern "C" int vrag_store_add_synthetic(vrag_corpus_t* c, const char* name, const int64_t* page_offsets,
@@ -410,6 +492,11 @@ static int find_store(vrag_corpus* c, const char* name, Store** out) {
   auto it = c->stores.find(name);
   if (it == c->stores.end()) return fail("unknown vector store '%s'", name);
   *out = &it->second;
+  if (it->second.dirty) {   // appended to: rebuild page tables, tile packing and tensor maps once, on first use
+    Store& s = it->second;
+    TRY(set_device(c));
+    TRY(finish_store(c, s, s.fixed_rows > 0 ? nullptr : s.h_offsets.data(), s.n_pages, s.fixed_rows));
+  }
   return 0;
 }
 
@@ -549,9 +636,10 @@ static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int
   fill_scan_params(c, s, d_cand, n_items, QP, normalize, d_scores, &p, &n_units);
   p.qimg = c->d_qimg.p;
   p.q_valid = q_eff;
-  {  // experiment knob: VRAG_QUERY_SPLIT=0 drops the lo half of the query (fp16-only query, LARGE pages only)
+  {  // VRAG_Q_FP16 (or the experiment knob VRAG_QUERY_SPLIT=0): contract only the fp16 hi half of the query
+    // (half the tensor work; LARGE pages only — that is where the scan is power/bandwidth bound)
     const char* e = getenv("VRAG_QUERY_SPLIT");
-    p.hi_only = (e && e[0] == '0' && QP >= 16 && !s.packed) ? 1 : 0;
+    p.hi_only = (((flags & VRAG_Q_FP16) != 0 || (e && e[0] == '0')) && QP >= 16 && !s.packed) ? 1 : 0;
   }
   if (time_kernel) CUDA_OK(cudaEventRecord(c->evk0, st));
   int r = 0;

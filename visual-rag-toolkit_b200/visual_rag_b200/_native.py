@@ -18,6 +18,7 @@ VRAG_F16 = 0
 VRAG_F32 = 1
 VRAG_Q_NORMALIZE = 1
 VRAG_Q_POOL = 2
+VRAG_Q_FP16 = 4
 
 # pooling kinds (mirrors include/vrag_b200.h)
 POOL_TILE_MEAN = 0
@@ -65,6 +66,7 @@ SIGNATURES = {
     "vrag_corpus_create": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
     "vrag_corpus_destroy": (C.c_int, [C.c_void_p]),
     "vrag_store_add": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, _i64p, C.c_int64, C.c_int64]),
+    "vrag_store_append": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, _i64p, C.c_int64, C.c_int64]),
     "vrag_store_add_synthetic": (C.c_int, [C.c_void_p, C.c_char_p, _i64p, C.c_int64, C.c_int64, C.c_uint64, C.c_int64]),
     "vrag_store_info": (C.c_int, [C.c_void_p, C.c_char_p, _i64p, _i64p, _i64p, _i64p]),
     "vrag_store_read_rows": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64, C.c_void_p]),

@@ -37,8 +37,10 @@ def _as_f32_query(query) -> np.ndarray:
     return np.ascontiguousarray(q)
 
 
-def query_flags(normalize: bool = True, pool_query: bool = False) -> int:
-    return (N.VRAG_Q_NORMALIZE if normalize else 0) | (N.VRAG_Q_POOL if pool_query else 0)
+def query_flags(normalize: bool = True, pool_query: bool = False, fp16_query: bool = False) -> int:
+    """fp16_query: opt-in reduced-precision query operand (VRAG_Q_FP16, include/vrag_b200.h); default exact."""
+    return ((N.VRAG_Q_NORMALIZE if normalize else 0) | (N.VRAG_Q_POOL if pool_query else 0)
+            | (N.VRAG_Q_FP16 if fp16_query else 0))
 
 
 class GpuCorpus:
@@ -132,6 +134,26 @@ class GpuCorpus:
             )
         )
         del keep
+
+    def append_store(self, name: str, rows, page_offsets: Optional[Sequence[int]] = None, fixed_rows: int = 0) -> None:
+        """Append pages behind the existing pages of `name` (created on first use) — the per-batch ingest of
+        QdrantIndexer.upload_batch (qdrant_indexer.py:341-507). rows: host numpy fp16/fp32 [total_rows,128]."""
+        arr = np.asarray(rows)
+        if arr.dtype not in (np.float16, np.float32):
+            arr = arr.astype(np.float32)
+        arr = np.ascontiguousarray(arr.reshape(-1, DIM))
+        dtype = N.VRAG_F16 if arr.dtype == np.float16 else N.VRAG_F32
+        if fixed_rows > 0:
+            if arr.shape[0] % fixed_rows:
+                raise ValueError("total rows is not a multiple of fixed_rows")
+            n_pages, off_p = arr.shape[0] // fixed_rows, None
+        else:
+            off = np.ascontiguousarray(np.asarray(page_offsets, dtype=np.int64))
+            if off.ndim != 1 or off.size < 1 or int(off[-1]) != arr.shape[0]:
+                raise ValueError("page_offsets must be n_pages+1 row offsets ending at the number of rows")
+            n_pages, off_p = off.size - 1, off.ctypes.data_as(C.POINTER(C.c_int64))
+        N.check(self._lib.vrag_store_append(self._h, name.encode(), arr.ctypes.data_as(C.c_void_p), dtype, 0, off_p,
+                                            int(n_pages), int(fixed_rows)))
 
     def add_synthetic_store(
         self,

@@ -1,0 +1,133 @@
+"""`GpuIndexer`: the ingest side of the GPU-resident corpus — mirror of the parts of
+visual_rag/indexing/qdrant_indexer.py::QdrantIndexer that the processing pipeline drives
+(`create_collection` 154-267, `upload_batch` 341-507, `check_exists` 509-520, `generate_point_id` 602-613).
+
+`ProcessingPipeline` (pipeline.py:620-629) hands `upload_batch` point dicts with `id`, `visual_embedding`,
+`tile_pooled_embedding`, `experimental_pooled_embedding` (array or {name: array}), `global_pooled_embedding`
+(optional) and `metadata`; this class appends them to the named stores of a GpuCorpus with the same store-dtype
+cast (every array -> fp32 -> fp16, 423-441) and the same fallback global = mean(tile_pooled) (417-421), and
+registers id / payload with the GpuCorpusClient so the retrievers can serve the pages immediately.
+"""
+
+from __future__ import annotations
+
+import hashlib
+import logging
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .client import GpuCorpusClient
+from .corpus import GpuCorpus
+
+logger = logging.getLogger(__name__)
+
+
+class GpuIndexer:
+    def __init__(self, corpus: GpuCorpus, collection_name: str = "gpu", client: Optional[GpuCorpusClient] = None,
+                 vector_datatype: str = "float16"):
+        if vector_datatype not in ("float16", "float32"):
+            raise ValueError("vector_datatype must be 'float16' or 'float32'")   # qdrant_indexer.py:137-138
+        # the HBM store dtype is always fp16 (tcgen05 has no fp32 operand path); fp32 collections are rounded on ingest
+        self.vector_datatype = vector_datatype
+        self.corpus = corpus
+        self.collection_name = collection_name
+        self.client = client if client is not None else GpuCorpusClient(corpus, collection_name, point_ids=[], payloads=[])
+        if self.client._ids is None:
+            self.client.set_points([], [])
+        self._extra_names: List[str] = []
+
+    # ------------------------------------------------------------------ collection
+    def collection_exists(self) -> bool:
+        return self.corpus.has_store("initial")
+
+    def create_collection(self, force_recreate: bool = False, enable_quantization: bool = False,
+                          indexing_threshold: int = 20000, full_scan_threshold: int = 0,
+                          experimental_vector_names: Optional[Sequence[str]] = None) -> bool:
+        """qdrant_indexer.py:154-267: named vectors initial / mean_pooling / experimental_pooling[...] /
+        global_pooling. Stores are created lazily by the first upload; force_recreate drops existing ones."""
+        names = ["initial", "mean_pooling", "experimental_pooling", "global_pooling"] + [str(n) for n in (experimental_vector_names or [])]
+        self._extra_names = [str(n) for n in (experimental_vector_names or [])]
+        if self.collection_exists():
+            if not force_recreate:
+                return False
+            for nm in names:
+                if self.corpus.has_store(nm):
+                    self.corpus.drop_store(nm)
+            self.client.set_points([], [])
+        return True
+
+    @staticmethod
+    def generate_point_id(filename: str, page_number: int) -> str:
+        """qdrant_indexer.py:602-613."""
+        content = f"{filename}:page:{page_number}"
+        hash_obj = hashlib.sha256(content.encode())
+        hex_str = hash_obj.hexdigest()[:32]
+        return f"{hex_str[:8]}-{hex_str[8:12]}-{hex_str[12:16]}-{hex_str[16:20]}-{hex_str[20:32]}"
+
+    def check_exists(self, chunk_id: str) -> bool:
+        return self.client._page(chunk_id) >= 0
+
+    def get_existing_ids(self, filename: Optional[str] = None) -> set:
+        ids = self.client._ids or []
+        if filename is None:
+            return set(ids)
+        pl = self.client._payloads or []
+        return {i for i, p in zip(ids, pl) if p and p.get("filename") == filename}
+
+    # ------------------------------------------------------------------ upload
+    @staticmethod
+    def _rows(val) -> np.ndarray:
+        a = np.array(val, dtype=np.float32)          # every array goes through fp32 first (qdrant_indexer.py:423-441)
+        return a.reshape(-1, a.shape[-1]) if a.ndim != 2 else a
+
+    def upload_batch(self, points: List[Dict[str, Any]], max_retries: int = 3, delay_between_batches: float = 0.0,
+                     wait: bool = True, stop_event=None) -> int:
+        """qdrant_indexer.py:341-507. Returns the number of uploaded points. Points whose id already exists are
+        rejected with ValueError (an upsert would need an in-place page replacement, which the append-only shard
+        layout does not offer; use create_collection(force_recreate=True) to rebuild)."""
+        if not points:
+            return 0
+        if stop_event is not None and getattr(stop_event, "is_set", lambda: False)():
+            return 0
+        stores: Dict[str, List[np.ndarray]] = {}
+        ids, payloads = [], []
+        seen = set()
+        for p in points:
+            if self.check_exists(p["id"]) or p["id"] in seen:
+                raise ValueError(f"point id {p['id']!r} is already in the collection")
+            seen.add(p["id"])
+            tile = self._rows(p["tile_pooled_embedding"])
+            glob = p.get("global_pooled_embedding")
+            if glob is None:
+                glob = tile.mean(axis=0)                                    # 417-421
+            glob = np.array(glob, dtype=np.float32).reshape(1, -1)
+            per_point = {"initial": self._rows(p["visual_embedding"]), "mean_pooling": tile, "global_pooling": glob}
+            exp = p.get("experimental_pooled_embedding")
+            if isinstance(exp, dict):
+                for k, v in exp.items():
+                    if v is not None:
+                        per_point[str(k)] = self._rows(v)
+            elif exp is not None:
+                per_point["experimental_pooling"] = self._rows(exp)
+            for k, v in per_point.items():
+                stores.setdefault(k, []).append(v)
+            ids.append(p["id"])
+            payloads.append(p.get("metadata"))
+        n = len(points)
+        n_before = len(self.client._ids)
+        for name, mats in stores.items():
+            if len(mats) != n:
+                raise ValueError(f"named vector '{name}' is missing from some points of the batch")
+            if self.corpus.has_store(name):
+                have = self.corpus.n_pages(name)
+            else:
+                have = 0
+            if have != n_before:
+                raise ValueError(f"named vector '{name}' holds {have} pages but the collection has {n_before} points")
+        for name, mats in stores.items():
+            off = np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])]).astype(np.int64)
+            rows = np.concatenate(mats, axis=0).astype(np.float16)           # store dtype cast
+            self.corpus.append_store(name, rows, page_offsets=off)
+        self.client.set_points(list(self.client._ids) + ids, list(self.client._payloads or []) + payloads)
+        return n
