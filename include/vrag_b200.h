@@ -124,6 +124,13 @@ int vrag_search_multistage_batch(vrag_corpus_t* c, int n_stages, const char* con
                                  const int* ks, int n_queries, const float* query_rows, const int* q_offsets,
                                  int per_stage_queries, float* out_scores, int64_t* out_ids, int* out_counts);
 
+/* ------------------------------------------------------------------ saliency
+ * Per-token relevance of one page for a query: out_scores[t] = max_q <qhat_q, dhat_t>, the `patch_scores` of
+ * generate_saliency_map (visual_rag/visualization/saliency.py:69-79) — the column-max twin of MaxSim, computed for the
+ * pages a search returned. out_rows receives the page's token count (<= capacity).                               */
+int vrag_saliency(vrag_corpus_t* c, const char* name, const float* query, int n_query_rows, int64_t page_id,
+                  float* out_scores, int64_t capacity, int64_t* out_rows);
+
 /* ------------------------------------------------------------------ device-pointer variants
  * Same kernels, caller-provided device buffers and stream (cudaStream_t passed as void*): used by the
  * sharded multi-GPU path, which all-gathers per-shard top-k lists with NCCL between stages.        */
@@ -157,6 +164,10 @@ typedef struct vrag_pool_spec {
   float weights[16];
   int n_rows, n_cols, has_global, include_self; /* TILE_4N */
   int via_f16;            /* GLOBAL_MEAN: round the fp32 mean to fp16 first (numpy's fp16 mean, pooling.py:463) */
+  int derive_from_f32;    /* on a spec that others derive from (input_spec): hand them its fp32 rows BEFORE the store-dtype
+                             rounding — the arithmetic of scripts/qdrant_recompute_colqwen_pooling_from_initial.py:292-327,
+                             which pools and smooths in fp32 and lets the collection round on write. Default 0: derived specs
+                             see the rows as stored (the pipeline's dtype chain, visual_embedder.py:776-799).            */
   int input_spec;         /* vrag_store_pool only. 0: pool the source store. k > 0: pool the OUTPUT of spec k-1 of the same
                              call (a token-level spec): the pipeline's "experimental / global pooling of the mean-pooled
                              rows" (pipeline.py:452-507), computed inside that spec's pass from shared memory — the pooled

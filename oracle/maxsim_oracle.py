@@ -141,3 +141,11 @@ def merge_shard_topk(lists: Sequence[Sequence[Tuple[int, float]]], k: int) -> Li
     flat = [x for lst in lists for x in lst]
     flat.sort(key=lambda t: (-t[1], t[0]))
     return flat[:k]
+
+
+def saliency_patch_scores(query: np.ndarray, doc: np.ndarray) -> np.ndarray:
+    """patch_scores of generate_saliency_map, visual_rag/visualization/saliency.py:69-79: max over query tokens of
+    the cosine with each document token."""
+    q = l2_normalize_rows(np.asarray(query, dtype=np.float32))
+    d = l2_normalize_rows(np.asarray(doc, dtype=np.float32))
+    return np.dot(q, d.T).max(axis=0)

@@ -429,3 +429,54 @@ def pool_page(model_name: str, visual_embedding, token_info: Optional[Dict[str, 
                 pass
     out["global_pooling"] = global_pool_from_mean_pool(mean_pool, output_dtype)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Bulk re-pooling from the stored `initial` vectors.
+def infer_grid(num_tokens: int, *, width: Optional[int] = None, height: Optional[int] = None):
+    """(grid_h, grid_w) with grid_h*grid_w == num_tokens whose aspect ratio w/h is closest (log distance) to
+    width/height — scripts/qdrant_recompute_colqwen_pooling_from_initial.py:64-105. Ties keep the first pair in
+    the enumeration order h = 1..isqrt(n), orientation (h, w) before (w, h)."""
+    import math
+
+    n = int(num_tokens)
+    if n <= 0:
+        raise ValueError("num_tokens must be > 0")
+    aspect = float(width) / float(height) if (width and height and int(width) > 0 and int(height) > 0) else 1.0
+    best, best_score = None, float("inf")
+    for h in range(1, int(math.isqrt(n)) + 1):
+        if n % h:
+            continue
+        w = n // h
+        for hh, ww in ((h, w), (w, h)):
+            score = abs(math.log(max(float(ww) / float(hh), 1e-9) / max(aspect, 1e-9)))
+            if score < best_score:
+                best_score, best = score, (int(hh), int(ww))
+    return best
+
+
+def payload_size(payload: Optional[Dict[str, Any]]):
+    """Image size the script reads from a point's payload (lines 274-290): resized, else cropped, else original."""
+    payload = payload or {}
+    w = payload.get("resized_width") or payload.get("cropped_width") or payload.get("original_width")
+    h = payload.get("resized_height") or payload.get("cropped_height") or payload.get("original_height")
+    try:
+        return (int(w) if w is not None else None), (int(h) if h is not None else None)
+    except Exception:
+        return None, None
+
+
+def repool_from_initial(emb: np.ndarray, payload: Optional[Dict[str, Any]] = None, max_mean_pool_vectors: int = 32):
+    """Per-point arithmetic of the script (lines 292-327), everything in fp32: adaptive row-mean pooling on the
+    inferred grid (cap min(max_mean_pool_vectors, grid_h)), gaussian / triangular k=3 smoothing of the UNROUNDED
+    fp32 rows, global = mean of those rows. Returns {name: fp32 array}; `experimental_pooling` is the gaussian."""
+    emb = np.asarray(emb, dtype=np.float32)
+    w, h = payload_size(payload)
+    gh, gw = infer_grid(emb.shape[0], width=w, height=h)
+    cap = int(max_mean_pool_vectors)
+    mp = adaptive_row_mean_pooling_from_grid(emb, grid_h=gh, grid_w=gw, target_rows=(gh if cap <= 0 else min(cap, gh)),
+                                             output_dtype=np.float32)
+    g = weighted_row_smoothing_same_length(mp, window_size=3, kernel="gaussian", output_dtype=np.float32)
+    t = weighted_row_smoothing_same_length(mp, window_size=3, kernel="triangular", output_dtype=np.float32)
+    return {"mean_pooling": mp, "global_pooling": mp.mean(axis=0).astype(np.float32), "experimental_pooling": g,
+            "experimental_pooling_gaussian": g, "experimental_pooling_triangular": t}

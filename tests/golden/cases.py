@@ -124,3 +124,31 @@ def retrieval_corpus(seed: int = 9000, n: int = 150):
     initial = [unit_rows(seed + 1 + i, int(lens[i]), scale=True) for i in range(n)]
     q = query_rows(seed + 100000, 20)
     return q, initial
+
+
+# ------------------------------------------------------------------ bulk re-pooling
+def infer_grid_cases():
+    """(num_tokens, width, height) triples for _infer_grid: primes, squares, ColQwen-like grids, missing sizes."""
+    out = []
+    for n in (1, 2, 7, 12, 64, 97, 256, 300, 391, 512, 640, 729, 736, 748, 750, 768, 1024):
+        for w, h in ((None, None), (1240, 1754), (1754, 1240), (800, 800), (3000, 500), (0, 100), (1, 5000)):
+            out.append((n, w, h))
+    return out
+
+
+def repool_cases():
+    rng = np.random.default_rng(4242)
+    out = []
+    for i in range(14):
+        gh, gw = int(rng.integers(8, 40)), int(rng.integers(6, 33))
+        while gh * gw > 1100:
+            gh -= 1
+        w, h = (gw * 28 + int(rng.integers(0, 20)), gh * 28 + int(rng.integers(0, 20))) if i % 4 else (None, None)
+        out.append({"key": f"repool{i}", "seed": 9000 + i, "n": gh * gw, "w": w, "h": h, "cap": 32 if i % 3 else 0})
+    return out
+
+
+def saliency_cases():
+    return [{"key": f"sal{i}", "seed": 9100 + i, "qseed": 9200 + i, "n": n, "q": q, "token_info": ti}
+            for i, (n, q, ti) in enumerate([(832, 20, {"n_rows": 4, "n_cols": 3}), (1030, 13, None), (300, 1, None),
+                                            (768, 32, {"n_rows": 3, "n_cols": 4}), (70, 25, {"n_rows": 1, "n_cols": 1})])]

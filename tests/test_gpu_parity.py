@@ -589,3 +589,46 @@ def test_indexer_upload_batches_equals_bulk_store():
         b3 = ThreeStageRetriever(client2, "c").search_server_side(query_embedding=q, top_k=5, stage1_k=30, stage2_k=12)
         assert [r["id"] for r in a3] == [r["id"] for r in b3]
         assert idx.get_existing_ids("doc.pdf") == {p["id"] for p in pts}
+
+
+@pytest.mark.gpu
+def test_saliency_kernel_matches_reference_goldens(corpus):
+    """vrag_saliency (column-max twin of MaxSim) vs patch_scores produced by the reference's generate_saliency_map."""
+    import os
+
+    from visual_rag_b200.visualization import saliency_scores
+
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "repool_golden.npz"))
+    cs = CS.saliency_cases()
+    mats = [CS.unit_rows(c["seed"], c["n"], dtype=np.float16) for c in cs]
+    off = np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])])
+    corpus.add_store("sal", np.concatenate(mats), page_offsets=off)
+    for p, c in enumerate(cs):
+        q = CS.query_rows(c["qseed"], c["q"])
+        res = saliency_scores(corpus, q, p, token_info=c["token_info"], vector_name="sal")
+        want = gold[c["key"] + "::patch_scores"]
+        np.testing.assert_allclose(res["patch_scores"], want, rtol=1e-5, atol=2e-6)
+        assert res["patch_scores_norm"].min() >= 0.0 and res["patch_scores_norm"].max() <= 1.0
+        if c["token_info"] and c["n"] >= c["token_info"]["n_rows"] * c["token_info"]["n_cols"] * 64:
+            assert res["tile_scores"].shape == (c["token_info"]["n_rows"], c["token_info"]["n_cols"])
+        # consistency with MaxSim: sum_q max_t >= max_t max_q ... and the best patch score is the best single cosine
+        assert abs(res["patch_scores"].max() - MO.saliency_patch_scores(q, mats[p].astype(np.float32)).max()) < 1e-5
+    with pytest.raises(Exception):
+        corpus.saliency("sal", CS.query_rows(1, 5), 99)
+    corpus.drop_store("sal")
+
+
+@pytest.mark.gpu
+def test_payload_filter_cache_and_vectorised_conditions(gpu_client):
+    from visual_rag_b200.retrieval import TwoStageRetriever
+
+    q, client = gpu_client
+    two = TwoStageRetriever(client, "c")
+    f = two.build_filter(year=[2000, 2002])
+    n_cached = len(client._filter_cache)
+    r1 = two.search_single_stage(q, top_k=20, filter_obj=f)
+    r2 = two.search_single_stage(q, top_k=20, filter_obj=two.build_filter(year=[2002, 2000]))   # same filter, cached
+    assert [r["id"] for r in r1] == [r["id"] for r in r2] and all(r["payload"]["year"] in (2000, 2002) for r in r1)
+    assert len(client._filter_cache) == n_cached + 1
+    none = two.search_single_stage(q, top_k=5, filter_obj=two.build_filter(year=1900))
+    assert none == []

@@ -240,3 +240,33 @@ def test_store_pool_chained_specs_single_pass():
             _stores_equal(c, a, b)
         with pytest.raises(Exception):
             c.pool_store("initial", [GP.derived_from(GP.spec_smooth(3, "gaussian"), 0)], ["x"])
+
+
+def test_bulk_repool_from_initial_matches_reference_script():
+    """recompute_pooling_from_initial (one device pass) vs the reference script's per-point arithmetic (goldens made by
+    running its functions), rounded to the fp16 store dtype."""
+    import json
+    import os
+
+    from visual_rag_b200.corpus import GpuCorpus
+    from visual_rag_b200.embedding.repool import recompute_pooling_from_initial
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gold = np.load(os.path.join(here, "repool_golden.npz"))
+    for cap in (32, 0):
+        cases = [c for c in CS.repool_cases() if c["cap"] == cap]
+        mats = [CS.unit_rows(c["seed"], c["n"], dtype=np.float16) for c in cases]
+        payloads = [({"resized_width": c["w"], "resized_height": c["h"]} if c["w"] else {}) for c in cases]
+        off = np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])])
+        with GpuCorpus(0) as c:
+            c.add_store("initial", np.concatenate(mats), page_offsets=off)
+            info = recompute_pooling_from_initial(c, payloads, max_mean_pool_vectors=cap)
+            assert info["pages"] == len(cases)
+            for nm, gk in (("mean_pooling", "mean_pooling"), ("experimental_pooling", "experimental_pooling_gaussian"),
+                           ("experimental_pooling_gaussian", "experimental_pooling_gaussian"),
+                           ("experimental_pooling_triangular", "experimental_pooling_triangular"), ("global_pooling", "global_pooling")):
+                for p, cs in enumerate(cases):
+                    want = gold[f"{cs['key']}::{gk}"]
+                    if want.ndim == 1:
+                        want = want[None, :]
+                    assert_pooled(c.read_page(nm, p), want.astype(np.float16), f"{cs['key']}::{nm}")

@@ -168,3 +168,20 @@ def test_build_filter_and_stage1_table():
     assert resolve_stage1("tokens_vs_tiles", "p", "e", "g") == (False, "p")
     assert resolve_stage1("pooled_query_vs_experimental", "p", "e", "g") == (True, "e")
     assert resolve_stage1("pooled_query_vs_global", "p", "e", "g") == (True, "g")
+
+
+def test_infer_grid_mirror_matches_reference_goldens():
+    """visual_rag_b200.embedding.repool.infer_grid (host logic) against outputs of the reference script's _infer_grid."""
+    import json
+    import os
+
+    import cases as CS
+    from visual_rag_b200.embedding.repool import infer_grid
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    idx = json.load(open(os.path.join(here, "repool_index.json")))
+    for (n, w, h), want in zip(CS.infer_grid_cases(), idx["infer_grid"]):
+        assert list(infer_grid(n, width=w, height=h)) == want
+    import pytest
+    with pytest.raises(ValueError):
+        infer_grid(0, width=1, height=1)

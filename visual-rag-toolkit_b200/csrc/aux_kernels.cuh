@@ -524,6 +524,43 @@ __global__ void __launch_bounds__(1024) sel_ties_kernel(const SelArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Per-token saliency of one page (visual_rag/visualization/saliency.py:69-79):
+//   patch_scores[t] = max_q <q_q / (||q_q|| + 1e-8), d_t / (||d_t|| + 1e-8)>
+// the column-max twin of MaxSim's row-max. One warp per document token (a lane owns 4 dims), the normalised query
+// lives in shared memory as fp32; 8 warps per block. Only the top-k returned pages are ever scored, so this is a
+// CUDA-core kernel (~2.6 MFLOP per page).
+__global__ void __launch_bounds__(256) saliency_kernel(const __half* __restrict__ rows, const float* __restrict__ inv,
+                                                       long long row0, int n_rows, const float* __restrict__ q, int Q,
+                                                       float* __restrict__ out) {
+  extern __shared__ float sq[];   // [Q][128] normalised query
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < Q; r += 8) {
+    const float4 x = reinterpret_cast<const float4*>(q + r * 128)[lane];
+    float ss = x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    const float s = 1.0f / (sqrtf(ss) + 1e-8f);
+    reinterpret_cast<float4*>(sq + r * 128)[lane] = make_float4(x.x * s, x.y * s, x.z * s, x.w * s);
+  }
+  __syncthreads();
+  for (int t = blockIdx.x * 8 + warp; t < n_rows; t += gridDim.x * 8) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(rows + (row0 + t) * 128) + lane);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    const float dn = __ldg(inv + row0 + t);
+    float best = -INFINITY;
+    for (int r = 0; r < Q; ++r) {
+      const float4 x = reinterpret_cast<const float4*>(sq + r * 128)[lane];
+      float d = a.x * x.x + a.y * x.y + b.x * x.z + b.y * x.w;
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+      best = fmaxf(best, d * dn);
+    }
+    if (lane == 0) out[t] = best;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fused top-k prefilter helpers (dense batched scans). thr[b] = the m-th best score of query b's sample.
 __global__ void prefilter_thr_kernel(const float* __restrict__ sample_top, int m, int batch, float* __restrict__ thr,
                                      int* __restrict__ cnt) {

@@ -45,6 +45,7 @@ struct PoolSpecDev {
   float weights[kPoolMaxWeights];
   int n_rows, n_cols, has_global, include_self;
   int via_f16;
+  int keep_f32;     // derived specs read this spec's fp32 rows before the store-dtype rounding
   // output
   void* out;
   int out_f32;
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(256, 3) pool_tokens_kernel(const PoolInput in,
   float* drows = pool_smem + d_off;
   auto keep = [&](int o, float4 v) {   // stage output row o for the derived specs, as stored
     if constexpr (DERIVE) {
-      if (!s.out_f32 || s.via_f16) v = make_float4(pool_round_f16(v.x), pool_round_f16(v.y), pool_round_f16(v.z), pool_round_f16(v.w));
+      if ((!s.out_f32 || s.via_f16) && !s.keep_f32) v = make_float4(pool_round_f16(v.x), pool_round_f16(v.y), pool_round_f16(v.z), pool_round_f16(v.w));
       reinterpret_cast<float4*>(drows + o * 128)[lane] = v;
     }
   };

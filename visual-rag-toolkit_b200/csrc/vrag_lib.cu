@@ -1226,6 +1226,39 @@ extern "C" int vrag_search_multistage_batch(vrag_corpus_t* c, int n_stages, cons
                                       out_scores, out_ids, out_counts, false);
 }
 
+// ------------------------------------------------------------------------------------------------ saliency
+extern "C" int vrag_saliency(vrag_corpus_t* c, const char* name, const float* query, int n_query_rows, int64_t page_id,
+                             float* out_scores, int64_t capacity, int64_t* out_rows) {
+  Store* s;
+  TRY(find_store(c, name, &s));
+  TRY(set_device(c));
+  if (!out_rows) return fail("out_rows is NULL");
+  const int64_t local = page_id - c->page_base;
+  if (local < 0 || local >= s->n_pages) return fail("page id %lld is not in this shard", (long long)page_id);
+  if (n_query_rows < 1 || n_query_rows > 96) return fail("query rows %d out of range [1,96]", n_query_rows);
+  const int64_t r0 = s->fixed_rows > 0 ? local * s->fixed_rows : s->h_offsets[local];
+  const int64_t n = s->fixed_rows > 0 ? s->fixed_rows : (s->h_offsets[local + 1] - s->h_offsets[local]);
+  *out_rows = n;
+  if (n > capacity) return fail("output buffer too small: need %lld scores", (long long)n);
+  if (n == 0) return 0;
+  if (!out_scores) return fail("out_scores is NULL");
+  TRY(stage_query(c, query, n_query_rows));
+  TRY(c->d_scores.ensure(n));
+  const size_t smem = static_cast<size_t>(n_query_rows) * 512;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_OK(cudaFuncSetAttribute(saliency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 512));
+    attr_done = true;
+  }
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>((n + 7) / 8, c->num_sms * 4));
+  saliency_kernel<<<grid, 256, smem, c->stream>>>(s->rows, s->inv, r0, static_cast<int>(n), c->d_query.p, n_query_rows, c->d_scores.p);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(out_scores, c->d_scores.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ device-pointer variants
 extern "C" int vrag_score_dev(vrag_corpus_t* c, const char* name, const float* query_dev, int n_query_rows,
                               uint32_t flags, const int64_t* cand_ids_dev, int64_t n_cand, float* out_scores_dev,
@@ -1355,6 +1388,7 @@ static PoolSpecDev to_dev_spec(const vrag_pool_spec_t& s) {
   d.has_global = s.has_global;
   d.include_self = s.include_self;
   d.via_f16 = s.via_f16;
+  d.keep_f32 = s.derive_from_f32;
   return d;
 }
 

@@ -50,6 +50,7 @@ class PoolSpec(C.Structure):
         ("has_global", C.c_int),
         ("include_self", C.c_int),
         ("via_f16", C.c_int),
+        ("derive_from_f32", C.c_int),
         ("input_spec", C.c_int),
     ]
 
@@ -76,6 +77,7 @@ SIGNATURES = {
     "vrag_score": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int, C.c_uint32, _i64p, C.c_int64, _f32p]),
     "vrag_search_multistage": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _u32p, _i32p, _f32p, C.c_int, _i32p, _i64p, C.c_int64, _f32p, _i64p, _i32p]),
     "vrag_search_multistage_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _u32p, _i32p, C.c_int, _f32p, _i32p, C.c_int, _f32p, _i64p, _i32p]),
+    "vrag_saliency": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int, C.c_int64, _f32p, C.c_int64, _i64p]),
     "vrag_score_dev": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "vrag_topk_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vrag_pool_out_rows": (C.c_int, [C.POINTER(PoolSpec), C.c_int64, _i64p]),

@@ -396,6 +396,17 @@ class GpuCorpus:
             off += nq * ks[s]
         return out
 
+    def saliency(self, name: str, query, page_id: int) -> np.ndarray:
+        """patch_scores of generate_saliency_map (visualization/saliency.py:69-79) for one page (global page id):
+        fp32 [tokens], max over query tokens of the cosine with each document token."""
+        q = _as_f32_query(query)
+        r0, n = self.page_range(name, int(page_id) - self.page_base)
+        out = np.empty((max(n, 1),), dtype=np.float32)
+        got = C.c_int64()
+        N.check(self._lib.vrag_saliency(self._h, name.encode(), q.ctypes.data_as(C.POINTER(C.c_float)), q.shape[0],
+                                        int(page_id), out.ctypes.data_as(C.POINTER(C.c_float)), out.shape[0], C.byref(got)))
+        return out[: got.value]
+
     # ------------------------------------------------------------------ device-pointer variants (multi-GPU path)
     def score_dev(self, name: str, query_dev_ptr: int, n_query_rows: int, flags: int, cand_dev_ptr: int,
                   n_cand: int, out_scores_dev_ptr: int, stream: int) -> None:
