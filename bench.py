@@ -368,7 +368,7 @@ def run_ours(args):
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "vrag::maxsim_scan_kernel<32,false>", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "vrag::maxsim_scan_kernel<QP=24 (MMA N=48), LARGE>", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "frac_of_8TBs_nominal": achieved / 8000.0,
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": pages * bytes_per_page,

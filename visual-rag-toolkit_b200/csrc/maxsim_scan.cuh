@@ -92,7 +92,8 @@ template <int QP>
 struct ScanCfg {
   static constexpr int N = 2 * QP;                         // UMMA N (hi | lo)
   static constexpr int ACC = (N <= 128) ? 4 : 2;           // TMEM accumulator stages
-  static constexpr int TMEM_COLS = (ACC * N < 32) ? 32 : ACC * N;
+  static constexpr int tmem_pow2(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+  static constexpr int TMEM_COLS = tmem_pow2(ACC * N);     // allocations are powers of two >= 32 columns
   static constexpr int B_BYTES = N * kDim * 2;
   static constexpr int SC_PITCH = kTileRows + 4;           // PACKED: transposed score buffer pitch (16 B aligned rows)
   // PACKED: two epilogue groups of 4 warps alternate tiles (the per-tile epilogue is a dependent chain on one
@@ -348,8 +349,11 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   constexpr int NTHREADS = Cfg::threads(PACKED, MULTI);
   constexpr int EPI_GROUPS = Cfg::epi_groups(PACKED, MULTI);
   constexpr int QE = MULTI ? 32 : QP;          // accumulator columns one epilogue group handles
-  constexpr int QG = (QE + 31) / 32;           // 32-wide column groups per epilogue group
-  constexpr int QW = QE < 32 ? QE : 32;        // columns per 32-wide group
+  constexpr int QR = QE <= 8 ? 8 : QE <= 16 ? 16 : QE <= 32 ? 32 : QE;   // QE padded to a power of two (reductions)
+  constexpr int QG = (QR + 31) / 32;           // 32-wide column groups per epilogue group
+  constexpr int QW = QR < 32 ? QR : 32;        // columns per 32-wide group
+  constexpr int RS = MULTI ? QP : QR;          // LARGE: row stride of the cross-warp reduce scratch
+  static_assert(QE == QR || !PACKED, "non-power-of-two query widths are only built for LARGE pages");
   constexpr int EPI_ARRIVALS = MULTI ? 16 : 4; // epilogue warps that consume every tile
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
   static_assert(QS == QP || ((QS == 1 || QS == 32) && QP == 128 && !BSW), "sub-query layouts: 128x1 or 4x32 columns");
@@ -565,7 +569,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (one thread)
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(kTileRows, p.hi_only ? QP : N);
+      const uint32_t idesc = umma_idesc_f16(kTileRows, p.hi_only ? ((QP + 15) / 16) * 16 : N);
       uint32_t b_addr = smem_u32(sB);
       uint32_t stage = 0, phase = 0, acc = 0, accphase = 0;
       int cur_g = -1, n_sw = -1;
@@ -642,9 +646,9 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         long long row0;
         int nrows;
         const bool ok = resolve_page(p, item_page(p, u, g), row0, nrows);
-        float run[QE];
+        float run[QR];
 #pragma unroll
-        for (int q = 0; q < QE; ++q) run[q] = -INFINITY;
+        for (int q = 0; q < QR; ++q) run[q] = -INFINITY;
         for (int t0 = 0; t0 < nrows; t0 += kTileRows) {
           const int valid = min(kTileRows, nrows - t0);
           mbar_wait(&tfull[acc], accphase);
@@ -655,8 +659,8 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             mbar_wait(&full[stage], phase);  // acquire the TMA-written scale rows
             scale = sScale[stage * kScaleStride + trow + (sMis[stage * 4] & 3)];
           }
-          // 16 columns (hi and lo) per TMEM round trip; 8 when the group has only 8 columns
-          constexpr int LW = QE >= 16 ? 16 : 8;
+          // 16 columns (hi and lo) per TMEM round trip; 8 when the group's width is not a multiple of 16
+          constexpr int LW = (QE % 16 == 0) ? 16 : 8;
 #pragma unroll
           for (int c = 0; c < QE; c += LW) {
             uint32_t hi[LW], lo[LW];
@@ -688,17 +692,17 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           if (++acc == ACC) { acc = 0; accphase ^= 1; }
         }
         // page done: max across the 128 rows owned by the group's threads, then sum over q
-        float* red = sRed + par * 4 * QP + col0;
+        float* red = sRed + par * 4 * RS + col0;
 #pragma unroll
         for (int gq = 0; gq < QG; ++gq) {
           warp_transpose_max<QW>(run + gq * 32, lane);
           constexpr int rep = 32 / QW;  // lanes holding the same q
-          if ((lane & (rep - 1)) == 0) red[ew * QP + gq * 32 + (lane / rep)] = run[gq * 32];
+          if ((lane & (rep - 1)) == 0) red[ew * RS + gq * 32 + (lane / rep)] = run[gq * 32];
         }
         named_bar_sync(bar_id, 128);
         if (ew == 0) {
           if constexpr (MULTI) {
-            const float m = fmaxf(fmaxf(red[lane], red[QP + lane]), fmaxf(red[2 * QP + lane], red[3 * QP + lane]));
+            const float m = fmaxf(fmaxf(red[lane], red[RS + lane]), fmaxf(red[2 * RS + lane], red[3 * RS + lane]));
             const float dead = (ok && nrows > 0) ? 0.0f : -INFINITY;
             if constexpr (QS == 32) {
               float sum = lane < q_valid ? m : 0.0f;
@@ -713,8 +717,8 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
 #pragma unroll
             for (int gq = 0; gq < QG; ++gq) {
               const int q = gq * 32 + lane;
-              if (q < QP) {
-                const float m = fmaxf(fmaxf(red[q], red[QP + q]), fmaxf(red[2 * QP + q], red[3 * QP + q]));
+              if (q < QR) {
+                const float m = fmaxf(fmaxf(red[q], red[RS + q]), fmaxf(red[2 * RS + q], red[3 * RS + q]));
                 if (q < q_valid) sum += m;
               }
             }

@@ -623,7 +623,9 @@ static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int
   if (n_query_rows > kMaxQueryRows) return fail("query has %d rows; at most %d supported", n_query_rows, kMaxQueryRows);
   const int q_eff = pool ? 1 : n_query_rows;
   if (q_eff > 128) return fail("query has %d token rows; at most 128 supported per call", q_eff);
-  const int QP = q_eff <= 8 ? 8 : q_eff <= 16 ? 16 : q_eff <= 32 ? 32 : q_eff <= 64 ? 64 : 128;
+  // operand width: the next power of two, except 17..24 token queries over LARGE pages, which get a 24-row operand
+  // (MMA N = 48 instead of 64: a quarter less tensor work and TMEM traffic where the scan is power-limited)
+  const int QP = q_eff <= 8 ? 8 : q_eff <= 16 ? 16 : (q_eff <= 24 && !s.packed) ? 24 : q_eff <= 32 ? 32 : q_eff <= 64 ? 64 : 128;
   const int64_t n_items = d_cand ? n_cand : s.n_pages;
   if (n_items == 0) return 0;
   if (s.total_rows == 0) return fail("store is empty");
@@ -651,6 +653,9 @@ static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int
   switch (QP) {
     VRAG_DISPATCH(8)
     VRAG_DISPATCH(16)
+    case 24:
+      r = launch_scan_t<24, false>(c, s, p, n_units, st);
+      break;
     VRAG_DISPATCH(32)
     VRAG_DISPATCH(64)
     VRAG_DISPATCH(128)
