@@ -64,6 +64,13 @@ elif what == "pool_tokens":
     for _ in range(reps):
         ms = c.pool_store("vis", [GP.spec_adaptive_rows(32, 32, 32)], ["mean_pooling"])
     print("pool_tokens", ms)
+elif what == "pool_fused":
+    c.add_synthetic_store("vis", 200_000, fixed_rows=1024, seed=6)
+    specs = [GP.spec_adaptive_rows(32, 32, 32)] + [GP.derived_from(x, 0) for x in (GP.spec_legacy_conv(3), GP.spec_smooth(3, "gaussian"),
+             GP.spec_smooth(3, "triangular"), GP.spec_global_mean(True))]
+    for _ in range(reps):
+        ms = c.pool_store("vis", specs, ["mean_pooling", "e1", "e2", "e3", "g"])
+    print("pool_fused", ms)
 elif what == "pool_rows":
     c.add_synthetic_store("mean_pooling", 1_000_000, fixed_rows=32, seed=6)
     for _ in range(reps):
