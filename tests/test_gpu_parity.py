@@ -632,3 +632,22 @@ def test_payload_filter_cache_and_vectorised_conditions(gpu_client):
     assert len(client._filter_cache) == n_cached + 1
     none = two.search_single_stage(q, top_k=5, filter_obj=two.build_filter(year=1900))
     assert none == []
+
+
+@pytest.mark.gpu
+def test_cfg0_full_size_colsmol_top10_matches_reference_cpu_path(corpus):
+    """BASELINE configs[0] at full size: 10,000 ColSmol-shaped pages x 768 tokens (1.97 GB fp16), 20-token queries,
+    exact MaxSim top-10 vs the reference's client-side CPU path (oracle search_exhaustive on the same bits)."""
+    n, t = 10_000, 768
+    corpus.add_synthetic_store("cfg0", n, fixed_rows=t, seed=2024)
+    rows = corpus.read_rows("cfg0", 0, n * t).astype(np.float32)
+    docs = [rows[i * t:(i + 1) * t] for i in range(n)]
+    rng = np.random.default_rng(2024)
+    queries = [rng.standard_normal((20, 128)).astype(np.float32) for _ in range(6)]
+    got = corpus.search_multistage_batch([("cfg0", False, 10)], queries)
+    for q, g in zip(queries, got):
+        want = MO.search_exhaustive(q, docs, 10)
+        _same_ranking(g[0][1].tolist(), g[0][0], want)
+        s1, i1 = corpus.search("cfg0", q, 10)
+        assert i1.tolist() == g[0][1].tolist()
+    corpus.drop_store("cfg0")

@@ -570,6 +570,74 @@ __global__ void prefilter_thr_kernel(const float* __restrict__ sample_top, int m
     cnt[b] = 0;
   }
 }
+// Threshold straight from the sample, one block per query: linear 2048-bin histogram of the query's sample scores
+// between their min and max, then the lower edge of the bin in which the count from the top reaches m. The
+// threshold only has to let roughly m sample scores through (the survivor count of the full scan is verified
+// afterwards), so no exact selection is needed: two passes over an L2-resident 256 KB row.
+__global__ void __launch_bounds__(1024) prefilter_sample_thr_kernel(const float* __restrict__ sample, long long n_sample,
+                                                                    int m, float* __restrict__ thr, int* __restrict__ cnt) {
+  __shared__ unsigned int hist[2048];
+  __shared__ float red_lo[32], red_hi[32];
+  __shared__ float s_lo, s_w;
+  __shared__ int s_bin;
+  const long long b = blockIdx.x;
+  const float* sc = sample + b * n_sample;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float lo = INFINITY, hi = -INFINITY;
+  for (long long i = threadIdx.x; i < n_sample; i += 1024) {
+    const float x = sc[i];
+    if (x > -INFINITY && x < INFINITY) { lo = fminf(lo, x); hi = fmaxf(hi, x); }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+  }
+  if (lane == 0) { red_lo[warp] = lo; red_hi[warp] = hi; }
+  for (int i = threadIdx.x; i < 2048; i += 1024) hist[i] = 0u;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < 32; ++w) { lo = fminf(lo, red_lo[w]); hi = fmaxf(hi, red_hi[w]); }
+    s_lo = lo;
+    s_w = (hi > lo) ? (hi - lo) / 2048.0f : 0.0f;
+    s_bin = -1;
+  }
+  __syncthreads();
+  const float base = s_lo, w = s_w;
+  if (w > 0.0f) {
+    const float inv_w = 1.0f / w;
+    for (long long i = threadIdx.x; i < n_sample; i += 1024) {
+      const float x = sc[i];
+      if (x > -INFINITY && x < INFINITY) atomicAdd(&hist[min(2047, max(0, static_cast<int>((x - base) * inv_w)))], 1u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {   // warp 0: count from the top, 64 bins per lane
+    unsigned int mine = 0;
+    for (int j = 0; j < 64; ++j) mine += hist[2047 - (lane * 64 + j)];
+    unsigned int incl = mine;   // inclusive prefix over lanes (lane 0 = top bins)
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned int v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    const unsigned int excl = incl - mine;
+    if (excl < static_cast<unsigned int>(m) && incl >= static_cast<unsigned int>(m)) {
+      unsigned int acc = excl;
+      for (int j = 0; j < 64; ++j) {
+        acc += hist[2047 - (lane * 64 + j)];
+        if (acc >= static_cast<unsigned int>(m)) { s_bin = 2047 - (lane * 64 + j); break; }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // fewer than m finite sample scores (or a degenerate range): let everything through; the survivor check decides
+    thr[b] = (s_bin >= 0 && w > 0.0f) ? (base + static_cast<float>(s_bin) * w) : -INFINITY;
+    cnt[b] = 0;
+  }
+}
+
 // The candidate list of query b is usable iff it holds at least `need` and at most `cap` entries; otherwise the
 // estimate failed and the host reruns the batch with the exact (unfiltered) path. Counts are clamped to cap.
 __global__ void prefilter_check_kernel(int* __restrict__ cnt, int batch, int need, int cap, int* __restrict__ flag) {

@@ -1122,8 +1122,6 @@ static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const ch
   if (!(no_prefilter || (pf_env && pf_env[0] == '0'))) plan = plan_prefilter(*st[0], ks[0], qchunk, max_rows[0], flags[0]);
   if (plan.on) {
     TRY(c->d_fthr.ensure(qchunk));
-    TRY(c->d_ftop.ensure(static_cast<size_t>(qchunk) * plan.m));
-    TRY(c->d_ftop_ids.ensure(static_cast<size_t>(qchunk) * plan.m));
     TRY(c->d_fcnt.ensure(nq + 1));
     TRY(c->d_fkeys.ensure(static_cast<size_t>(qchunk) * plan.cap));
     CUDA_OK(cudaMemsetAsync(c->d_fcnt.p + nq, 0, sizeof(int), c->stream));
@@ -1149,9 +1147,7 @@ static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const ch
           o.n_sample = plan.n_sample;
           TRY(launch_scan_dense_batch(c, *st[0], c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows[0], flags[0],
                                       c->d_scores.p, c->stream, false, o));
-          TRY(launch_topk(c, c->d_scores.p, nullptr, 0, plan.n_sample, plan.m, c->d_ftop.p, c->d_ftop_ids.p, nullptr, nullptr,
-                          c->stream, qc));
-          prefilter_thr_kernel<<<(qc + 127) / 128, 128, 0, c->stream>>>(c->d_ftop.p, plan.m, qc, c->d_fthr.p, c->d_fcnt.p);
+          prefilter_sample_thr_kernel<<<qc, 1024, 0, c->stream>>>(c->d_scores.p, plan.n_sample, plan.m, c->d_fthr.p, c->d_fcnt.p);
           DenseOpts f;
           f.thr = c->d_fthr.p;
           f.cnt = c->d_fcnt.p;

@@ -347,11 +347,14 @@ class GpuCorpus:
         queries: Sequence,
         normalize: bool = True,
         stage_queries: Optional[Sequence[Sequence]] = None,
-    ) -> List[List[Tuple[np.ndarray, np.ndarray]]]:
+        as_arrays: bool = False,
+    ):
         """`search_multistage` for a batch of independent queries in ONE native call / host synchronisation
         (BASELINE configs[2]: 256 queries). queries: sequence of [Q_b,128] matrices (ragged). stage_queries:
         optional, per query a sequence of one matrix per stage (e.g. the mean-pooled prefetch vector and the
-        token matrix, two_stage.py:142,159). Returns, per query, the per-stage (scores, ids) lists."""
+        token matrix, two_stage.py:142,159). Returns, per query, the per-stage (scores, ids) lists; with
+        as_arrays=True instead one (scores [nq,k_s], ids [nq,k_s], counts [nq]) triple per stage (no per-query
+        Python work: rows are valid up to their count, the rest is (-inf, -1))."""
         ns = len(stages)
         if stage_queries is not None:
             mats = []
@@ -385,6 +388,13 @@ class GpuCorpus:
                 counts.ctypes.data_as(C.POINTER(C.c_int)),
             )
         )
+        if as_arrays:
+            res, off = [], 0
+            for s in range(ns):
+                res.append((scores[off : off + nq * ks[s]].reshape(nq, ks[s]), ids[off : off + nq * ks[s]].reshape(nq, ks[s]),
+                            counts[s * nq : (s + 1) * nq]))
+                off += nq * ks[s]
+            return res
         out: List[List[Tuple[np.ndarray, np.ndarray]]] = [[] for _ in range(nq)]
         off = 0
         for s in range(ns):
