@@ -376,6 +376,13 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   float* sRed = reinterpret_cast<float*>(misc + 512);             // LARGE: [2][4][QP]
   int* sSeg = reinterpret_cast<int*>(misc + 512);                 // PACKED: [EPI_GROUPS][3][128] ints (item, begin, end)
   float* sThr = reinterpret_cast<float*>(misc + 7168);            // QS < QP: [128] prefilter thresholds
+  int* sStageCnt = reinterpret_cast<int*>(misc + 7680);           // QS < QP: [128] survivors staged by this CTA per query
+  // Prefilter survivors of the slot/shuffle epilogue are staged per CTA in the (otherwise unused) transpose buffer and
+  // flushed with one global atomicAdd per (CTA, query): thousands of same-address atomics from all SMs serialise in L2.
+  constexpr int kStageKeys = 8192;                                // 64 KB of keys, split evenly between the launch's queries
+  unsigned long long* sStage = reinterpret_cast<unsigned long long*>(sSc);
+  const bool stage_on = PACKED && MULTI && p.f_thr != nullptr && p.shfl_rows > 0;
+  const int stage_cap = kStageKeys / (QP / QS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -409,6 +416,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   }
   if constexpr (QS < QP) {
     if (p.f_thr && threadIdx.x < 128) sThr[threadIdx.x] = static_cast<int>(threadIdx.x) < p.n_sub ? __ldg(p.f_thr + threadIdx.x) : INFINITY;
+    if (threadIdx.x < 128) sStageCnt[threadIdx.x] = 0;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -419,8 +427,16 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   auto emit = [&](int j, long long col, long long page, float val) {
     if (p.f_thr) {
       if (val > sThr[j]) {
+        const unsigned long long key = score_key(val, static_cast<uint32_t>(page));
+        if (stage_on) {
+          const int slot = atomicAdd(&sStageCnt[j], 1);
+          if (slot < stage_cap) {
+            sStage[j * stage_cap + slot] = key;
+            return;
+          }
+        }
         const int pos = atomicAdd(p.f_cnt + j, 1);
-        if (pos < p.f_cap) p.f_keys[static_cast<long long>(j) * p.f_cap + pos] = score_key(val, static_cast<uint32_t>(page));
+        if (pos < p.f_cap) p.f_keys[static_cast<long long>(j) * p.f_cap + pos] = key;
       }
     } else {
       p.scores[j * p.score_stride + col] = val;
@@ -475,34 +491,34 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           resolve_batch(i0 + tiles_per_batch, nxt_r0, nxt_nr);
           for (int t = 0; t < tiles_per_batch; ++t) {
             if (i0 + t >= ur.count) break;   // warp-uniform
-            long long r0j[4];
-            int nrj[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int src = (t * per_tile + j) & 31;
-              r0j[j] = __shfl_sync(0xffffffffu, cur_r0, src);
-              nrj[j] = __shfl_sync(0xffffffffu, cur_nr, src);
-              if (j >= per_tile) nrj[j] = 0, r0j[j] = 0;
-            }
+            // lane j (< per_tile) owns item j of this tile and issues its TMA boxes itself: the copies of the (up to 4)
+            // items are issued in parallel instead of one thread serialising 12 bulk-tensor instructions per tile
+            const int src = (t * per_tile + lane) & 31;
+            long long my_r0 = __shfl_sync(0xffffffffu, cur_r0, src);
+            int my_nr = __shfl_sync(0xffffffffu, cur_nr, src);
+            if (lane >= per_tile) my_nr = 0, my_r0 = 0;
             if (lane == 0) {
               int g;
               long long u;
               ur.decode(i0 + t, g, u);
               switch_group(g);
               mbar_wait(&empty[stage], phase ^ 1);
+            }
+            __syncwarp();
+            uint32_t bytes = 0;
+            if (lane < 4) {
               uint8_t* a = sA + stage * kTileBytes;
               float* sc = sScale + stage * kScaleStride;
-              uint32_t bytes = 0;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (nrj[j] > 0)
-                  bytes += issue_rows(a, sc + j * (p.slot_rows + 32), &full[stage], &tm_rows128, &tm_rows32, &tm_scale128,
-                                      &tm_scale32, r0j[j], nrj[j], j * p.slot_rows, use_scale);
-                // low 2 bits: scale misalignment; rest: rows of the slot (0 for unused / empty slots)
-                sMis[stage * 4 + j] = static_cast<int>(r0j[j] & 3) | (nrj[j] << 2);
-              }
-              mbar_arrive_expect_tx(&full[stage], bytes);
+              if (my_nr > 0)
+                bytes = issue_rows(a, sc + lane * (p.slot_rows + 32), &full[stage], &tm_rows128, &tm_rows32, &tm_scale128,
+                                   &tm_scale32, my_r0, my_nr, lane * p.slot_rows, use_scale);
+              // low 2 bits: scale misalignment; rest: rows of the slot (0 for unused / empty slots)
+              sMis[stage * 4 + lane] = static_cast<int>(my_r0 & 3) | (my_nr << 2);
             }
+            bytes += __shfl_xor_sync(0xffffffffu, bytes, 1);
+            bytes += __shfl_xor_sync(0xffffffffu, bytes, 2);
+            __syncwarp();   // the other lanes' sMis stores are ordered before lane 0's (releasing) arrive
+            if (lane == 0) mbar_arrive_expect_tx(&full[stage], bytes);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           cur_r0 = nxt_r0;
@@ -636,13 +652,17 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
 
     if constexpr (!PACKED) {
       uint32_t stage = 0, phase = 0, acc = 0, accphase = 0, par = 0;
+      int q_valid = 0, qv_g = -1;
       for (long long i = 0; i < ur.count; ++i) {
         int g;
         long long u;
         ur.decode(i, g, u);
-        int q_valid;
-        if constexpr (MULTI) q_valid = (QS == 32 && grp < p.n_sub) ? __ldg(p.q_valid_arr + grp) : 0;
-        else q_valid = p.q_valid_arr ? __ldg(p.q_valid_arr + g) : p.q_valid;
+        // per-group query width: a global load, so it is refreshed only when the group changes (never on the tile path)
+        if (g != qv_g) {
+          if constexpr (MULTI) q_valid = (QS == 32 && grp < p.n_sub) ? __ldg(p.q_valid_arr + grp) : 0;
+          else q_valid = p.q_valid_arr ? __ldg(p.q_valid_arr + g) : p.q_valid;
+          qv_g = g;
+        }
         long long row0;
         int nrows;
         const bool ok = resolve_page(p, item_page(p, u, g), row0, nrows);
@@ -735,13 +755,17 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
       float* sc = sSc + grp * QE * Cfg::SC_PITCH;
       int seg_n = 0, seg_item = 0, seg_rb = 0, seg_re = 0;   // general path: this thread's entry of the tile's segment table
       bool seg_ready = false;
+      int q_valid = 0, qv_g = -1;
       for (long long seq = seq0; seq < ur.count; seq += seq_step) {
         int g;
         long long u;
         ur.decode(seq, g, u);
-        int q_valid;
-        if constexpr (MULTI) q_valid = (QS == 32 && grp < p.n_sub) ? __ldg(p.q_valid_arr + grp) : 0;
-        else q_valid = p.q_valid_arr ? __ldg(p.q_valid_arr + g) : p.q_valid;
+        // per-group query width: a global load, so it is refreshed only when the group changes (never on the tile path)
+        if (g != qv_g) {
+          if constexpr (MULTI) q_valid = (QS == 32 && grp < p.n_sub) ? __ldg(p.q_valid_arr + grp) : 0;
+          else q_valid = p.q_valid_arr ? __ldg(p.q_valid_arr + g) : p.q_valid;
+          qv_g = g;
+        }
         float* const scores_g = p.scores + g * p.n_items;
         const uint32_t stage = static_cast<uint32_t>(seq % STAGES), phase = static_cast<uint32_t>((seq / STAGES) & 1);
         const uint32_t acc = static_cast<uint32_t>(seq % ACC), accphase = static_cast<uint32_t>((seq / ACC) & 1);
@@ -944,6 +968,18 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
 
   tc_fence_before_sync();
   __syncthreads();
+  if constexpr (QS < QP) {
+    if (stage_on) {   // flush this CTA's staged survivors: one range reservation per query
+      for (int j = warp; j < p.n_sub; j += NTHREADS / 32) {
+        const int n = min(sStageCnt[j], stage_cap);
+        int base = 0;
+        if (lane == 0 && n > 0) base = atomicAdd(p.f_cnt + j, n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < n; i += 32)
+          if (base + i < p.f_cap) p.f_keys[static_cast<long long>(j) * p.f_cap + base + i] = sStage[j * stage_cap + i];
+      }
+    }
+  }
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
