@@ -669,6 +669,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         float run[QR];
 #pragma unroll
         for (int q = 0; q < QR; ++q) run[q] = -INFINITY;
+        const int ncol = !MULTI ? QE : (QS == 32 ? ((q_valid + 7) & ~7) : ((min(32, max(0, p.n_sub - col0)) + 7) & ~7));
         for (int t0 = 0; t0 < nrows; t0 += kTileRows) {
           const int valid = min(kTileRows, nrows - t0);
           mbar_wait(&tfull[acc], accphase);
@@ -679,10 +680,13 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             mbar_wait(&full[stage], phase);  // acquire the TMA-written scale rows
             scale = sScale[stage * kScaleStride + trow + (sMis[stage * 4] & 3)];
           }
-          // 16 columns (hi and lo) per TMEM round trip; 8 when the group's width is not a multiple of 16
-          constexpr int LW = (QE % 16 == 0) ? 16 : 8;
+          // 16 columns (hi and lo) per TMEM round trip; 8 when the group's width is not a multiple of 16. Sub-query
+          // kernels are bound by the TMEM read port (64 B/clk: a 128x256 fp32 accumulator takes 2048 clk to drain), so
+          // they read only the columns that hold real query rows (ncol, a multiple of 8).
+          constexpr int LW = (QE % 16 == 0 && !MULTI) ? 16 : 8;
 #pragma unroll
           for (int c = 0; c < QE; c += LW) {
+            if (MULTI && c >= ncol) break;
             uint32_t hi[LW], lo[LW];
             if constexpr (LW == 16) tmem_ld_x16(ta + c, hi);
             else tmem_ld_x8(ta + c, hi);
@@ -799,9 +803,15 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             }
             float v[QE];
             const bool live = rin < nr;
-            constexpr int LW = QE >= 16 ? 16 : 8;
+            constexpr int LW = (QE >= 16 && !MULTI) ? 16 : 8;
+            const int ncol = !MULTI ? QE : (QS == 32 ? ((q_valid + 7) & ~7) : ((min(32, max(0, p.n_sub - col0)) + 7) & ~7));
 #pragma unroll
             for (int c = 0; c < QE; c += LW) {
+              if (MULTI && c >= ncol) {   // columns without query rows are not read from TMEM (see the LARGE path)
+#pragma unroll
+                for (int j = 0; j < LW; ++j) v[c + j] = -INFINITY;
+                continue;
+              }
               uint32_t hi[LW], lo[LW];
               if constexpr (LW == 16) {
                 tmem_ld_x16(ta + c, hi);

@@ -750,6 +750,10 @@ static int launch_scan_dense_batch(vrag_corpus* c, const Store& s, const float* 
     p.q_valid_arr = d_qvalid + g * G;
     p.score_stride = stride_cols;
     p.n_sub = std::min(G, nq - g * G);
+    {
+      const char* e = getenv("VRAG_QUERY_SPLIT");
+      p.hi_only = (((flags & VRAG_Q_FP16) != 0 || (e && e[0] == '0')) && !s.packed) ? 1 : 0;
+    }
     if (o.tile_stride > 1) {   // sample pass: every tile_stride-th page (LARGE) / full tile (PACKED fixed rows)
       p.tile_stride = o.tile_stride;
       if (s.packed) {
