@@ -373,8 +373,8 @@ def run_ours(args):
                          "frac_of_8TBs_nominal": achieved / 8000.0,
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": pages * bytes_per_page,
                          "traffic": (args.ncu_traffic_ratio * pages * bytes_per_page) if args.ncu_traffic_ratio else None,
-                         "traffic_source": "dram__bytes_read+write per launch / algorithmic bytes = 1.0014 in the ncu --set full "
-                                           "capture at 100k pages per launch (profiles/r1b_kernels_ncu_summary.md, column `large`), scaled to this launch"},
+                         "traffic_source": "dram__bytes_read+write per launch / algorithmic bytes = 1.0079 in the ncu --set full "
+                                           "capture at 100k pages per launch (profiles/r1c_kernels_ncu_summary.md, column `large`), scaled to this launch"},
             "cpu_baseline": {"value": cpu_pps, "unit": "pages/s", "cores": blas_threads, "kind": "port",
                              "sample": f"first {n_cpu} pages of the same corpus read back from the device, {cpu_passes} queries one after "
                                        f"the other ({cpu_passes * n_cpu} page scorings, {cpu_s:.1f} s); oracle/maxsim_oracle.py::search_exhaustive "
@@ -444,6 +444,14 @@ def run_extras(corpus, args, peak, kern_ms):
         arr = corpus.search_multistage_batch(stages, queries, as_arrays=True)
         walls.append(time.perf_counter() - t0)
     dev_ms = corpus.last_timing_ms()[0]
+    from visual_rag_b200.corpus import pack_queries
+
+    packed = pack_queries(queries)
+    walls_packed = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        arr = corpus.search_multistage_batch(stages, packed, as_arrays=True)
+        walls_packed.append(time.perf_counter() - t0)
     res = corpus.search_multistage_batch(stages, queries)
     t0 = time.perf_counter()
     for q in queries[:32]:
@@ -454,6 +462,7 @@ def run_extras(corpus, args, peak, kern_ms):
         "workload": f"cfg2: {n} ColQwen2.5-shaped pages (H,W in [16,32], T=H*W<=768, {int(off[-1])} tokens = {off[-1] * 256 / 1e9:.1f} GB), "
                     f"pooled rows min(H,32), global 1 row; {nq} queries with 10..30 tokens; stage1_k=1000, stage2_k=300, top_k=100",
         "batch_wall_ms": 1e3 * float(np.median(walls)), "batch_device_ms": dev_ms, "qps": nq / float(np.median(walls)),
+        "batch_wall_ms_prepacked_queries": 1e3 * float(np.median(walls_packed)), "qps_prepacked_queries": nq / float(np.median(walls_packed)),
         "ms_per_query_batched": 1e3 * float(np.median(walls)) / nq, "ms_per_query_sequential_api": seq_ms,
         "last_query_matches_single_query_path": same}
     for nm in ("initial", "experimental_pooling", "global_pooling"):
@@ -500,7 +509,7 @@ def main():
     ap.add_argument("--latency-queries", type=int, default=200)
     ap.add_argument("--cfg2-pages", type=int, default=1_000_000)
     ap.add_argument("--cfg4-pages", type=int, default=400_000)
-    ap.add_argument("--ncu-traffic-ratio", type=float, default=1.0014,
+    ap.add_argument("--ncu-traffic-ratio", type=float, default=1.0079,
                     help="DRAM bytes / algorithmic bytes of the scan kernel in the committed ncu capture (profiles/)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -651,3 +651,19 @@ def test_cfg0_full_size_colsmol_top10_matches_reference_cpu_path(corpus):
         s1, i1 = corpus.search("cfg0", q, 10)
         assert i1.tolist() == g[0][1].tolist()
     corpus.drop_store("cfg0")
+
+
+@pytest.mark.gpu
+def test_packed_queries_and_array_results(corpus):
+    from visual_rag_b200.corpus import pack_queries
+
+    rng = np.random.default_rng(31)
+    rows = rows16(32, 50 * 200)
+    corpus.add_store("pq", rows, fixed_rows=200)
+    qs = [rng.standard_normal((int(rng.integers(3, 28)), 128)).astype(np.float32) for _ in range(12)]
+    a = corpus.search_multistage_batch([("pq", False, 7)], qs)
+    (sc, ids, cnt), = corpus.search_multistage_batch([("pq", False, 7)], pack_queries(qs), as_arrays=True)
+    assert sc.shape == (12, 7) and ids.shape == (12, 7) and cnt.tolist() == [7] * 12
+    for b in range(12):
+        assert ids[b].tolist() == a[b][0][1].tolist() and np.array_equal(sc[b], a[b][0][0])
+    corpus.drop_store("pq")

@@ -37,6 +37,33 @@ def _as_f32_query(query) -> np.ndarray:
     return np.ascontiguousarray(q)
 
 
+class PackedQueries:
+    """A batch of query matrices packed once into the layout the native batch call consumes: all rows
+    concatenated ([R,128] fp32, C-contiguous) + row offsets ([n+1] int32). Build it with `pack_queries` when the same
+    batch is searched repeatedly or the embedder already emits one padded tensor — the per-call Python work of
+    converting and concatenating hundreds of small arrays is otherwise a third of a batched search's wall time."""
+
+    __slots__ = ("rows", "offsets")
+
+    def __init__(self, rows: np.ndarray, offsets: np.ndarray):
+        self.rows = np.ascontiguousarray(rows, dtype=np.float32)
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        if self.rows.ndim != 2 or self.rows.shape[1] != DIM:
+            raise ValueError(f"rows must be [total_rows, {DIM}]")
+        if self.offsets.ndim != 1 or self.offsets.size < 1 or int(self.offsets[-1]) != self.rows.shape[0] or int(self.offsets[0]) != 0:
+            raise ValueError("offsets must be n+1 non-decreasing row offsets from 0 to total_rows")
+
+    def __len__(self) -> int:
+        return self.offsets.size - 1
+
+
+def pack_queries(queries: Sequence) -> PackedQueries:
+    mats = [_as_f32_query(x) for x in queries]
+    if not mats:
+        return PackedQueries(np.zeros((0, DIM), np.float32), np.zeros((1,), np.int32))
+    return PackedQueries(np.concatenate(mats, axis=0), np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])]))
+
+
 def query_flags(normalize: bool = True, pool_query: bool = False, fp16_query: bool = False) -> int:
     """fp16_query: opt-in reduced-precision query operand (VRAG_Q_FP16, include/vrag_b200.h); default exact."""
     return ((N.VRAG_Q_NORMALIZE if normalize else 0) | (N.VRAG_Q_POOL if pool_query else 0)
@@ -364,14 +391,21 @@ class GpuCorpus:
                 mats.extend(_as_f32_query(x) for x in sq)
             nq = len(stage_queries)
             per_stage = 1
+        elif isinstance(queries, PackedQueries):
+            mats = None
+            nq = len(queries)
+            per_stage = 0
         else:
             mats = [_as_f32_query(x) for x in queries]
             nq = len(mats)
             per_stage = 0
         if nq == 0:
             return []
-        rows = np.ascontiguousarray(np.concatenate(mats, axis=0))
-        offs = np.ascontiguousarray(np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])]).astype(np.int32))
+        if mats is None:
+            rows, offs = queries.rows, queries.offsets
+        else:
+            rows = np.ascontiguousarray(np.concatenate(mats, axis=0))
+            offs = np.ascontiguousarray(np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])]).astype(np.int32))
         names = (C.c_char_p * ns)(*[s[0].encode() for s in stages])
         flags = (C.c_uint32 * ns)(*[query_flags(normalize, bool(s[1])) for s in stages])
         ks = [int(s[2]) for s in stages]
