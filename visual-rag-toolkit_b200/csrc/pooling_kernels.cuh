@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(128) pool_rows_kernel(const PoolRowsArgs a) {
 // kept in smem (at float offset d_off) and the derived stores are written in the same pass — the pooled store is
 // never re-read from HBM.
 template <bool DERIVE>
-__global__ void __launch_bounds__(256, 3) pool_tokens_kernel(const PoolInput in, const PoolSpecDev s, const PoolRowsArgs d,
+__global__ void __launch_bounds__(256, 4) pool_tokens_kernel(const PoolInput in, const PoolSpecDev s, const PoolRowsArgs d,
                                                              const int d_off) {
   extern __shared__ float pool_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
