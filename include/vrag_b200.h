@@ -124,6 +124,22 @@ int vrag_search_multistage_batch(vrag_corpus_t* c, int n_stages, const char* con
                                  const int* ks, int n_queries, const float* query_rows, const int* q_offsets,
                                  int per_stage_queries, float* out_scores, int64_t* out_ids, int* out_counts);
 
+/* Device-level form of the batched search for the sharded multi-GPU path (the caller all-gathers the per-shard lists with
+ * NCCL between the stages): upload the batch once, then per stage score it on this shard — cand_ids_dev == NULL: every
+ * page, with the fused top-k prefilter when allow_prefilter != 0; else per-query candidate lists [n_queries][n_cand] of
+ * global page ids (ids of other shards score -inf) — and write the LOCAL top-k as [n_queries][k] device arrays; with
+ * k == 0 a candidate stage writes its raw [n_queries][n_cand] scores instead (max-all-reduced across shards by the caller,
+ * so that the final top-k breaks ties by candidate order exactly like a single shard).
+ * vrag_batch_prefilter_failed reports (after synchronising `stream`) whether a prefiltered stage must be repeated with
+ * allow_prefilter = 0; vrag_topk_batch_dev merges gathered [n_queries][n] lists (ties -> lower position).          */
+int vrag_batch_upload(vrag_corpus_t* c, int n_stages, int n_queries, const float* query_rows, const int* q_offsets,
+                      int per_stage_queries);
+int vrag_batch_stage_dev(vrag_corpus_t* c, int stage, const char* name, uint32_t flags, int k, const int64_t* cand_ids_dev,
+                         int64_t n_cand, int allow_prefilter, float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+int vrag_batch_prefilter_failed(vrag_corpus_t* c, void* stream, int* failed);
+int vrag_topk_batch_dev(vrag_corpus_t* c, const float* scores_dev, const int64_t* ids_dev, int64_t n, int k, int n_queries,
+                        float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+
 /* ------------------------------------------------------------------ saliency
  * Per-token relevance of one page for a query: out_scores[t] = max_q <qhat_q, dhat_t>, the `patch_scores` of
  * generate_saliency_map (visual_rag/visualization/saliency.py:69-79) — the column-max twin of MaxSim, computed for the

@@ -73,6 +73,47 @@ class OracleShard:
         oi[:len(order)] = torch.from_numpy(ids[order].copy())
 
 
+    # ---- batched surface (device-level batched stages)
+    def batch_upload(self, n_stages, packed, per_stage=False):
+        self._batch = [packed.rows[packed.offsets[b]:packed.offsets[b + 1]] for b in range(len(packed))]
+
+    def batch_stage_dev(self, stage, name, flags, k, cand_ptr, n_cand, allow_prefilter, out_s_ptr, out_i_ptr, stream):
+        nq = len(self._batch)
+        store = self.stores[name]
+        pool = bool(flags & 2)
+        cand = self._view(cand_ptr, nq * n_cand, torch.int64).numpy().reshape(nq, n_cand) if cand_ptr else None
+        if k == 0:   # raw candidate scores
+            raw = self._view(out_s_ptr, nq * n_cand, torch.float32).view(nq, n_cand)
+            for b, q in enumerate(self._batch):
+                qq = q.mean(axis=0, keepdims=True) if pool else q
+                for j, i in enumerate(cand[b] - self.page_base):
+                    raw[b, j] = self.MO.maxsim_score(qq, store[i]) if 0 <= i < len(store) else float("-inf")
+            return
+        os_, oi = self._view(out_s_ptr, nq * k, torch.float32).view(nq, k), self._view(out_i_ptr, nq * k, torch.int64).view(nq, k)
+        for b, q in enumerate(self._batch):
+            qq = q.mean(axis=0, keepdims=True) if pool else q
+            ids = (cand[b] - self.page_base) if cand is not None else np.arange(len(store))
+            sc = np.array([self.MO.maxsim_score(qq, store[i]) if 0 <= i < len(store) else float("-inf") for i in ids], np.float32)
+            gid = cand[b] if cand is not None else np.arange(len(store)) + self.page_base
+            order = np.lexsort((np.arange(len(sc)), -sc))[:k]
+            os_[b] = float("-inf")
+            oi[b] = -1
+            os_[b, :len(order)] = torch.from_numpy(sc[order].copy())
+            oi[b, :len(order)] = torch.from_numpy(np.asarray(gid)[order].copy())
+
+    def batch_prefilter_failed(self, stream):
+        return False
+
+    def topk_batch_dev(self, scores_ptr, ids_ptr, n, k, nq, out_s_ptr, out_i_ptr, stream):
+        sc = self._view(scores_ptr, nq * n, torch.float32).numpy().reshape(nq, n)
+        ids = self._view(ids_ptr, nq * n, torch.int64).numpy().reshape(nq, n)
+        os_, oi = self._view(out_s_ptr, nq * k, torch.float32).view(nq, k), self._view(out_i_ptr, nq * k, torch.int64).view(nq, k)
+        for b in range(nq):
+            order = np.lexsort((np.arange(n), -sc[b]))[:k]
+            os_[b] = torch.from_numpy(sc[b][order].copy())
+            oi[b] = torch.from_numpy(ids[b][order].copy())
+
+
 def _worker(rank, world, port, ret):
     _paths()
     import cases as CS
@@ -126,6 +167,16 @@ def _worker(rank, world, port, ret):
         # k larger than the whole corpus
         sc, ids = s.search("initial", q, 100)
         assert len(ids) == n and sorted(ids.tolist()) == list(range(n))
+        # batched three-stage: one all-gather per stage for the whole batch
+        qs = [CS.query_rows(40 + j, 5 + 3 * j) for j in range(4)]
+        stages = [("global_pooling", True, 50), ("mean_pooling", False, 45), ("initial", False, 7)]
+        got = s.search_multistage_batch(stages, qs)
+        for j, qq in enumerate(qs):
+            ref = MO.multistage(qq, [(glob, True, 50), (pooled, False, 45), (initial, False, 7)])
+            for (gsc, gid), r in zip(got, ref):
+                keep = gid[j] >= 0
+                assert gid[j][keep].tolist() == [i for i, _ in r]
+                np.testing.assert_allclose(gsc[j][keep], [x for _, x in r], rtol=1e-6)
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()

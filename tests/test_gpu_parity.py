@@ -667,3 +667,25 @@ def test_packed_queries_and_array_results(corpus):
     for b in range(12):
         assert ids[b].tolist() == a[b][0][1].tolist() and np.array_equal(sc[b], a[b][0][0])
     corpus.drop_store("pq")
+
+
+@pytest.mark.gpu
+def test_sharded_batched_search_single_rank_equals_corpus_batch(corpus):
+    """ShardedSearcher.search_multistage_batch (device-level batched stages + merge) at world size 1 == the host batch API,
+    including a prefiltered dense stage."""
+    from visual_rag_b200.distributed import ShardedSearcher
+
+    rng = np.random.default_rng(55)
+    n = 270_000
+    corpus.add_synthetic_store("sb_glob", n, fixed_rows=1, seed=5)
+    lens = rng.integers(8, 33, size=n)
+    corpus.add_synthetic_store("sb_exp", 0, page_offsets=np.concatenate([[0], np.cumsum(lens)]), seed=6)
+    corpus.add_synthetic_store("sb_init", n, fixed_rows=130, seed=7)
+    qs = [rng.standard_normal((int(rng.integers(6, 30)), 128)).astype(np.float32) for _ in range(10)]
+    stages = [("sb_glob", True, 500), ("sb_exp", False, 100), ("sb_init", False, 10)]
+    want = corpus.search_multistage_batch(stages, qs, as_arrays=True)
+    got = ShardedSearcher(corpus).search_multistage_batch(stages, qs)
+    for (ws, wi, _), (gs, gi) in zip(want, got):
+        assert np.array_equal(wi, gi) and np.array_equal(ws, gs)
+    for nm in ("sb_glob", "sb_exp", "sb_init"):
+        corpus.drop_store(nm)

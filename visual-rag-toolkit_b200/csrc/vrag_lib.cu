@@ -122,8 +122,16 @@ struct DevBuf {
   }
 };
 
+struct BatchCtx {   // the batch of queries last uploaded to the device
+  bool valid = false;
+  int nq = 0, n_stages = 0, qs = 1;
+  bool per_stage = false;
+  std::vector<int> max_rows;   // largest query row count per stage
+};
+
 struct vrag_corpus {
   int device = 0;
+  BatchCtx batch;
   int64_t page_base = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
@@ -1052,40 +1060,28 @@ static int ensure_host_query(vrag_corpus* c, size_t rows) {
   return 0;
 }
 
-static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const char* const* names,
-                                        const uint32_t* flags, const int* ks, int n_queries, const float* query_rows,
-                                        const int* q_offsets, int per_stage_queries, float* out_scores,
-                                        int64_t* out_ids, int* out_counts, bool no_prefilter) {
-  if (!c) return fail("corpus is NULL");
-  if (n_stages < 1 || n_stages > kMaxStages) return fail("n_stages %d out of range [1,%d]", n_stages, kMaxStages);
-  if (!names || !flags || !ks || !out_scores || !out_ids || !out_counts || !query_rows || !q_offsets) return fail("NULL argument");
-  if (n_queries < 0) return fail("n_queries < 0");
-  if (n_queries == 0) return 0;
-  TRY(set_device(c));
-  Store* st[kMaxStages];
-  size_t total_k = 0;
-  for (int s = 0; s < n_stages; ++s) {
-    TRY(find_store(c, names[s], &st[s]));
-    if (ks[s] < 1) return fail("stage %d: k must be >= 1", s);
-    if (ks[s] > kTopkMaxK) return fail("stage %d: k=%d exceeds the supported maximum %d", s, ks[s], kTopkMaxK);
-    if (st[s]->n_pages != st[0]->n_pages) return fail("stage %d: store '%s' has a different page count", s, names[s]);
-    total_k += ks[s];
-  }
+// ---- an uploaded batch of queries (vrag_search_multistage_batch and the device-level stage API share it)
+static int batch_upload(vrag_corpus* c, int n_stages, const uint32_t* flags, int n_queries, const float* query_rows,
+                        const int* q_offsets, int per_stage_queries) {
+  BatchCtx& bc = c->batch;
+  bc.valid = false;
   const int nq = n_queries;
   const int qs = per_stage_queries ? n_stages : 1;
   const int total_rows = q_offsets[static_cast<size_t>(nq) * qs];
   // per (stage, query) row range + the largest effective row count per stage
-  std::vector<int> max_rows(n_stages, 0);
+  bc.max_rows.assign(n_stages, 0);
   for (int b = 0; b < nq; ++b)
     for (int s = 0; s < n_stages; ++s) {
       const int i = b * qs + (per_stage_queries ? s : 0);
       const int r0 = q_offsets[i], r1 = q_offsets[i + 1];
       if (r0 < 0 || r1 <= r0 || r1 > total_rows) return fail("query %d stage %d: bad row range [%d,%d)", b, s, r0, r1);
       if (r1 - r0 > kMaxQueryRows) return fail("query %d has %d rows; at most %d supported", b, r1 - r0, kMaxQueryRows);
-      max_rows[s] = std::max(max_rows[s], r1 - r0);
+      bc.max_rows[s] = std::max(bc.max_rows[s], r1 - r0);
     }
-  for (int s = 0; s < n_stages; ++s)
-    if (!(flags[s] & VRAG_Q_POOL) && max_rows[s] > 128) return fail("query has %d token rows; at most 128 supported per call", max_rows[s]);
+  if (flags)
+    for (int s = 0; s < n_stages; ++s)
+      if (!(flags[s] & VRAG_Q_POOL) && bc.max_rows[s] > 128)
+        return fail("query has %d token rows; at most 128 supported per call", bc.max_rows[s]);
   // ---- stage queries and metadata to the device
   TRY(ensure_host_query(c, total_rows));
   TRY(c->d_query.ensure(static_cast<size_t>(total_rows) * 128));
@@ -1108,28 +1104,136 @@ static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const ch
       c->h_qmeta[(static_cast<size_t>(s) * 2 + 1) * nq + b] = q_offsets[i + 1];
     }
   CUDA_OK(cudaMemcpyAsync(c->d_qmeta.p, c->h_qmeta, (meta_n - nq) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  int* d_qvalid = c->d_qmeta.p + static_cast<size_t>(n_stages) * 2 * nq;
+  TRY(c->d_fcnt.ensure(nq + 1));
+  CUDA_OK(cudaMemsetAsync(c->d_fcnt.p + nq, 0, sizeof(int), c->stream));
+  bc.nq = nq;
+  bc.n_stages = n_stages;
+  bc.qs = qs;
+  bc.per_stage = per_stage_queries != 0;
+  bc.valid = true;
+  return 0;
+}
+
+// One stage of the uploaded batch for queries [b0, b0+qc): scan (dense / candidate lists) + local top-k into
+// o_sc / o_id ([qc][k]). d_prev_ids: nullptr (every page) or [qc][n_items] global candidate ids.
+static int batch_stage_chunk(vrag_corpus* c, int s, Store& store, uint32_t flags, int k, const long long* d_prev_ids,
+                             int64_t n_items, bool have_items, int b0, int qc, float* o_sc, long long* o_id, cudaStream_t stm,
+                             const PrefilterPlan& plan, bool* timed, float* raw_out = nullptr) {
+  // raw_out != nullptr (candidate stages only): write the [qc][n_items] score matrix there and skip the top-k
+  BatchCtx& bc = c->batch;
+  float* const d_sc = raw_out ? raw_out : c->d_scores.p;
+  const int nq = bc.nq;
+  const int* d_qb = c->d_qmeta.p + (static_cast<size_t>(s) * 2 + 0) * nq + b0;
+  const int* d_qe = c->d_qmeta.p + (static_cast<size_t>(s) * 2 + 1) * nq + b0;
+  int* d_qvalid = c->d_qmeta.p + static_cast<size_t>(bc.n_stages) * 2 * nq;
+  const int max_rows = bc.max_rows[s];
+  if (have_items) {
+    int r = 2;
+    if (!d_prev_ids && plan.on) {
+      // fused top-k prefilter: sample -> thresholds -> filtered scan -> sort the survivors
+      DenseOpts o;
+      o.tile_stride = plan.tile_stride;
+      o.n_sample = plan.n_sample;
+      TRY(launch_scan_dense_batch(c, store, c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows, flags, c->d_scores.p, stm,
+                                  false, o));
+      prefilter_sample_thr_kernel<<<qc, 1024, 0, stm>>>(c->d_scores.p, plan.n_sample, plan.m, c->d_fthr.p, c->d_fcnt.p);
+      DenseOpts f;
+      f.thr = c->d_fthr.p;
+      f.cnt = c->d_fcnt.p;
+      f.keys = c->d_fkeys.p;
+      f.cap = plan.cap;
+      f.skip_prep = true;
+      TRY(launch_scan_dense_batch(c, store, c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows, flags, nullptr, stm,
+                                  timed && !*timed, f));
+      if (timed) *timed = true;
+      prefilter_check_kernel<<<(qc + 127) / 128, 128, 0, stm>>>(c->d_fcnt.p, qc, static_cast<int>(std::min<int64_t>(k, store.n_pages)),
+                                                                plan.cap, c->d_fcnt.p + nq);
+      c->launches += 2;
+      TRY(launch_topk_keys(c, c->d_fkeys.p, c->d_fcnt.p, plan.cap, k, c->page_base, o_sc, o_id, stm, qc));
+      return 0;
+    }
+    if (!d_prev_ids && dense_batch_covers(qc, max_rows, flags)) {
+      r = launch_scan_dense_batch(c, store, c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows, flags, c->d_scores.p, stm,
+                                  timed && !*timed);
+      if (r == 1) return r;
+      if (r == 0 && timed) *timed = true;
+    } else if (d_prev_ids) {
+      const bool t = timed && !*timed;
+      if (t) CUDA_OK(cudaEventRecord(c->evk0, stm));
+      r = launch_scan_batch(c, store, c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows, flags, d_prev_ids, n_items,
+                            d_sc, stm);
+      if (r == 1) return r;
+      if (t && r == 0) { CUDA_OK(cudaEventRecord(c->evk1, stm)); *timed = true; }
+    }
+    if (r == 2) {   // one launch per query (shapes the batched kernels do not cover)
+      for (int b = 0; b < qc; ++b) {
+        const int q0 = c->h_qmeta[(static_cast<size_t>(s) * 2 + 0) * nq + b0 + b];
+        const int q1 = c->h_qmeta[(static_cast<size_t>(s) * 2 + 1) * nq + b0 + b];
+        TRY(launch_scan(c, store, c->d_query.p + static_cast<size_t>(q0) * 128, q1 - q0, flags,
+                        d_prev_ids ? d_prev_ids + static_cast<size_t>(b) * n_items : nullptr, n_items,
+                        d_sc + static_cast<size_t>(b) * n_items, stm, false));
+      }
+    }
+  }
+  if (raw_out) return 0;
+  return launch_topk(c, c->d_scores.p, d_prev_ids, c->page_base, have_items ? n_items : 0, k, o_sc, o_id, nullptr, nullptr, stm,
+                     qc, d_prev_ids ? n_items : 0);
+}
+
+// chunk size (queries) that bounds the stage-0 score matrix [chunk][n_pages] to ~1 GiB, and the scratch it needs
+static int batch_prepare_stage(vrag_corpus* c, Store& store, int k, int64_t n_items, bool dense, bool allow_prefilter,
+                               uint32_t flags, int s, PrefilterPlan* plan, int* qchunk_out) {
+  BatchCtx& bc = c->batch;
+  const int64_t max_scores = int64_t(1) << 28;
+  const int64_t per_query = std::max<int64_t>(dense ? store.n_pages : n_items, 1);
+  const int qchunk = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(bc.nq, max_scores / per_query)));
+  TRY(c->d_scores.ensure(static_cast<int64_t>(qchunk) * per_query));
+  *plan = PrefilterPlan();
+  const char* pf_env = getenv("VRAG_PREFILTER");
+  if (dense && allow_prefilter && !(pf_env && pf_env[0] == '0')) *plan = plan_prefilter(store, k, qchunk, bc.max_rows[s], flags);
+  if (plan->on) {
+    TRY(c->d_fthr.ensure(qchunk));
+    TRY(c->d_fkeys.ensure(static_cast<size_t>(qchunk) * plan->cap));
+    c->prefilter_runs++;
+  }
+  *qchunk_out = qchunk;
+  return 0;
+}
+
+static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const char* const* names,
+                                        const uint32_t* flags, const int* ks, int n_queries, const float* query_rows,
+                                        const int* q_offsets, int per_stage_queries, float* out_scores,
+                                        int64_t* out_ids, int* out_counts, bool no_prefilter) {
+  if (!c) return fail("corpus is NULL");
+  if (n_stages < 1 || n_stages > kMaxStages) return fail("n_stages %d out of range [1,%d]", n_stages, kMaxStages);
+  if (!names || !flags || !ks || !out_scores || !out_ids || !out_counts || !query_rows || !q_offsets) return fail("NULL argument");
+  if (n_queries < 0) return fail("n_queries < 0");
+  if (n_queries == 0) return 0;
+  TRY(set_device(c));
+  Store* st[kMaxStages];
+  size_t total_k = 0;
+  for (int s = 0; s < n_stages; ++s) {
+    TRY(find_store(c, names[s], &st[s]));
+    if (ks[s] < 1) return fail("stage %d: k must be >= 1", s);
+    if (ks[s] > kTopkMaxK) return fail("stage %d: k=%d exceeds the supported maximum %d", s, ks[s], kTopkMaxK);
+    if (st[s]->n_pages != st[0]->n_pages) return fail("stage %d: store '%s' has a different page count", s, names[s]);
+    total_k += ks[s];
+  }
+  const int nq = n_queries;
+  TRY(batch_upload(c, n_stages, flags, nq, query_rows, q_offsets, per_stage_queries));
   // ---- outputs, stage-major: stage s occupies [nq*sum(ks[:s]), +nq*ks[s]) as [nq][ks[s]]
   const size_t out_n = total_k * nq;
   TRY(c->d_out_scores.ensure(out_n));
   TRY(c->d_out_ids.ensure(out_n));
   TRY(ensure_host_out(c, out_n));
   const int64_t n_pages = st[0]->n_pages;
-  // stage-0 score matrix [chunk][n_pages] is bounded to ~1 GiB: queries are processed in chunks
-  const int64_t max_scores = int64_t(1) << 28;
-  const int qchunk = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nq, max_scores / std::max<int64_t>(n_pages, 1))));
-  int64_t need = static_cast<int64_t>(qchunk) * std::max<int64_t>(n_pages, 1);
-  for (int s = 0; s + 1 < n_stages; ++s) need = std::max<int64_t>(need, static_cast<int64_t>(qchunk) * ks[s]);
-  TRY(c->d_scores.ensure(need));
-  const char* pf_env = getenv("VRAG_PREFILTER");
   PrefilterPlan plan;
-  if (!(no_prefilter || (pf_env && pf_env[0] == '0'))) plan = plan_prefilter(*st[0], ks[0], qchunk, max_rows[0], flags[0]);
-  if (plan.on) {
-    TRY(c->d_fthr.ensure(qchunk));
-    TRY(c->d_fcnt.ensure(nq + 1));
-    TRY(c->d_fkeys.ensure(static_cast<size_t>(qchunk) * plan.cap));
-    CUDA_OK(cudaMemsetAsync(c->d_fcnt.p + nq, 0, sizeof(int), c->stream));
-    c->prefilter_runs++;
+  int qchunk = 1;
+  TRY(batch_prepare_stage(c, *st[0], ks[0], 0, true, !no_prefilter, flags[0], 0, &plan, &qchunk));
+  {
+    int64_t need = static_cast<int64_t>(qchunk) * std::max<int64_t>(n_pages, 1);
+    for (int s = 0; s + 1 < n_stages; ++s) need = std::max<int64_t>(need, static_cast<int64_t>(qchunk) * ks[s]);
+    TRY(c->d_scores.ensure(need));
   }
   CUDA_OK(cudaEventRecord(c->ev0, c->stream));
   bool timed = false;
@@ -1139,65 +1243,11 @@ static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const ch
     int64_t n_prev = n_pages;
     const long long* d_prev_ids = nullptr;
     for (int s = 0; s < n_stages; ++s) {
-      const int* d_qb = c->d_qmeta.p + (static_cast<size_t>(s) * 2 + 0) * nq + b0;
-      const int* d_qe = c->d_qmeta.p + (static_cast<size_t>(s) * 2 + 1) * nq + b0;
       const int64_t n_items = (s == 0) ? n_pages : ks[s - 1];   // candidate lists keep the full stride; missing ids are -1
-      if (n_prev > 0) {
-        int r = 2;
-        if (s == 0 && plan.on) {
-          // fused top-k prefilter: sample -> thresholds -> filtered scan -> sort the survivors
-          DenseOpts o;
-          o.tile_stride = plan.tile_stride;
-          o.n_sample = plan.n_sample;
-          TRY(launch_scan_dense_batch(c, *st[0], c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows[0], flags[0],
-                                      c->d_scores.p, c->stream, false, o));
-          prefilter_sample_thr_kernel<<<qc, 1024, 0, c->stream>>>(c->d_scores.p, plan.n_sample, plan.m, c->d_fthr.p, c->d_fcnt.p);
-          DenseOpts f;
-          f.thr = c->d_fthr.p;
-          f.cnt = c->d_fcnt.p;
-          f.keys = c->d_fkeys.p;
-          f.cap = plan.cap;
-          f.skip_prep = true;
-          TRY(launch_scan_dense_batch(c, *st[0], c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows[0], flags[0], nullptr,
-                                      c->stream, !timed, f));
-          timed = true;
-          prefilter_check_kernel<<<(qc + 127) / 128, 128, 0, c->stream>>>(c->d_fcnt.p, qc, static_cast<int>(std::min<int64_t>(ks[0], n_pages)),
-                                                                          plan.cap, c->d_fcnt.p + nq);
-          c->launches += 2;
-          float* o_sc0 = c->d_out_scores.p + static_cast<size_t>(b0) * ks[0];
-          long long* o_id0 = c->d_out_ids.p + static_cast<size_t>(b0) * ks[0];
-          TRY(launch_topk_keys(c, c->d_fkeys.p, c->d_fcnt.p, plan.cap, ks[0], c->page_base, o_sc0, o_id0, c->stream, qc));
-          d_prev_ids = o_id0;
-          n_prev = std::min<int64_t>(ks[0], n_prev);
-          for (int b = 0; b < qc; ++b) out_counts[b0 + b] = static_cast<int>(n_prev);
-          off += ks[0];
-          continue;
-        }
-        if (s == 0 && dense_batch_covers(qc, max_rows[s], flags[s])) {
-          r = launch_scan_dense_batch(c, *st[s], c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows[s], flags[s],
-                                      c->d_scores.p, c->stream, !timed);
-          if (r == 1) return r;
-          if (r == 0) timed = true;
-        } else {
-          if (!timed) CUDA_OK(cudaEventRecord(c->evk0, c->stream));
-          r = launch_scan_batch(c, *st[s], c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows[s], flags[s], d_prev_ids,
-                                n_items, c->d_scores.p, c->stream);
-          if (r == 1) return r;
-          if (!timed && r == 0) { CUDA_OK(cudaEventRecord(c->evk1, c->stream)); timed = true; }
-        }
-        if (r == 2) {   // one launch per query (dense stage 0, or shapes the batched kernels do not cover)
-          for (int b = 0; b < qc; ++b) {
-            const int i = (b0 + b) * qs + (per_stage_queries ? s : 0);
-            TRY(launch_scan(c, *st[s], c->d_query.p + static_cast<size_t>(q_offsets[i]) * 128, q_offsets[i + 1] - q_offsets[i],
-                            flags[s], d_prev_ids ? d_prev_ids + static_cast<size_t>(b) * n_items : nullptr, n_items,
-                            c->d_scores.p + static_cast<size_t>(b) * n_items, c->stream, false));
-          }
-        }
-      }
       float* o_sc = c->d_out_scores.p + off * nq + static_cast<size_t>(b0) * ks[s];
       long long* o_id = c->d_out_ids.p + off * nq + static_cast<size_t>(b0) * ks[s];
-      TRY(launch_topk(c, c->d_scores.p, d_prev_ids, c->page_base, n_prev > 0 ? n_items : 0, ks[s], o_sc, o_id, nullptr,
-                      nullptr, c->stream, qc, d_prev_ids ? n_items : 0));
+      TRY(batch_stage_chunk(c, s, *st[s], flags[s], ks[s], d_prev_ids, n_items, n_prev > 0, b0, qc, o_sc, o_id, c->stream,
+                            s == 0 ? plan : PrefilterPlan(), &timed));
       d_prev_ids = o_id;
       n_prev = std::min<int64_t>(ks[s], n_prev);
       for (int b = 0; b < qc; ++b) out_counts[static_cast<size_t>(s) * nq + b0 + b] = static_cast<int>(n_prev);
@@ -1221,6 +1271,76 @@ static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const ch
   cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1);
   if (timed) cudaEventElapsedTime(&c->last_ms[1], c->evk0, c->evk1);
   return 0;
+}
+
+// ---- device-level batched stage API (sharded multi-GPU search: NCCL all-gathers run between the stages)
+extern "C" int vrag_batch_upload(vrag_corpus_t* c, int n_stages, int n_queries, const float* query_rows, const int* q_offsets,
+                                 int per_stage_queries) {
+  if (!c) return fail("corpus is NULL");
+  if (n_stages < 1 || n_stages > kMaxStages) return fail("n_stages %d out of range [1,%d]", n_stages, kMaxStages);
+  if (n_queries < 1 || !query_rows || !q_offsets) return fail("bad batch arguments");
+  TRY(set_device(c));
+  TRY(batch_upload(c, n_stages, nullptr, n_queries, query_rows, q_offsets, per_stage_queries));
+  CUDA_OK(cudaStreamSynchronize(c->stream));   // later stages may run on the caller's stream
+  return 0;
+}
+
+extern "C" int vrag_batch_stage_dev(vrag_corpus_t* c, int stage, const char* name, uint32_t flags, int k,
+                                    const int64_t* cand_ids_dev, int64_t n_cand, int allow_prefilter, float* out_scores_dev,
+                                    int64_t* out_ids_dev, void* stream) {
+  Store* st;
+  TRY(find_store(c, name, &st));
+  TRY(set_device(c));
+  BatchCtx& bc = c->batch;
+  if (!bc.valid) return fail("no uploaded batch: call vrag_batch_upload first");
+  if (stage < 0 || stage >= bc.n_stages) return fail("stage %d out of range", stage);
+  const bool raw = k == 0;   // candidate stage, scores only: [n_queries][n_cand] into out_scores_dev
+  if (raw && !cand_ids_dev) return fail("k == 0 (raw scores) needs candidate lists");
+  if (!raw && (k < 1 || k > kTopkMaxK)) return fail("k=%d out of range [1,%d]", k, kTopkMaxK);
+  if (!out_scores_dev || (!raw && !out_ids_dev)) return fail("NULL device pointer");
+  if (!(flags & VRAG_Q_POOL) && bc.max_rows[stage] > 128) return fail("query has %d token rows; at most 128 supported per call", bc.max_rows[stage]);
+  cudaStream_t stm = static_cast<cudaStream_t>(stream);
+  const bool dense = cand_ids_dev == nullptr;
+  PrefilterPlan plan;
+  int qchunk = 1;
+  TRY(batch_prepare_stage(c, *st, k, n_cand, dense, allow_prefilter != 0, flags, stage, &plan, &qchunk));
+  const int64_t n_items = dense ? st->n_pages : n_cand;
+  for (int b0 = 0; b0 < bc.nq; b0 += qchunk) {
+    const int qc = std::min(qchunk, bc.nq - b0);
+    TRY(batch_stage_chunk(c, stage, *st, flags, k, dense ? nullptr : reinterpret_cast<const long long*>(cand_ids_dev) + static_cast<size_t>(b0) * n_cand,
+                          n_items, n_items > 0, b0, qc, out_scores_dev + static_cast<size_t>(b0) * k,
+                          reinterpret_cast<long long*>(out_ids_dev) + static_cast<size_t>(b0) * k, stm, plan, nullptr,
+                          raw ? out_scores_dev + static_cast<size_t>(b0) * n_cand : nullptr));
+  }
+  return 0;
+}
+
+// 1 if a prefiltered stage since the last upload kept too few / too many candidates for some query (the caller then
+// repeats the stages with allow_prefilter = 0). Synchronises `stream`.
+extern "C" int vrag_batch_prefilter_failed(vrag_corpus_t* c, void* stream, int* failed) {
+  if (!c || !failed) return fail("NULL argument");
+  TRY(set_device(c));
+  if (!c->batch.valid) return fail("no uploaded batch");
+  cudaStream_t stm = static_cast<cudaStream_t>(stream);
+  CUDA_OK(cudaMemcpyAsync(c->h_flag, c->d_fcnt.p + c->batch.nq, sizeof(int), cudaMemcpyDeviceToHost, stm));
+  CUDA_OK(cudaStreamSynchronize(stm));
+  *failed = *c->h_flag ? 1 : 0;
+  if (*c->h_flag) {
+    *c->h_flag = 0;
+    c->prefilter_fallbacks++;
+    CUDA_OK(cudaMemsetAsync(c->d_fcnt.p + c->batch.nq, 0, sizeof(int), stm));
+  }
+  return 0;
+}
+
+// Batched exact top-k merge: scores/ids [nq][n] (device) -> [nq][k], ties -> lower position.
+extern "C" int vrag_topk_batch_dev(vrag_corpus_t* c, const float* scores_dev, const int64_t* ids_dev, int64_t n, int k, int nq,
+                                   float* out_scores_dev, int64_t* out_ids_dev, void* stream) {
+  if (!c) return fail("corpus is NULL");
+  TRY(set_device(c));
+  if (!scores_dev || !ids_dev || !out_scores_dev || !out_ids_dev) return fail("NULL device pointer");
+  return launch_topk(c, scores_dev, reinterpret_cast<const long long*>(ids_dev), 0, n, k, out_scores_dev,
+                     reinterpret_cast<long long*>(out_ids_dev), nullptr, nullptr, static_cast<cudaStream_t>(stream), nq, n);
 }
 
 extern "C" int vrag_search_multistage_batch(vrag_corpus_t* c, int n_stages, const char* const* names,

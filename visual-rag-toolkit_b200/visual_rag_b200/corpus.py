@@ -471,6 +471,30 @@ class GpuCorpus:
             )
         )
 
+    # ------------------------------------------------------------------ device-level batched stages (sharded batched search)
+    def batch_upload(self, n_stages: int, packed: "PackedQueries", per_stage: bool = False) -> None:
+        N.check(self._lib.vrag_batch_upload(self._h, int(n_stages), len(packed) // (n_stages if per_stage else 1),
+                                            packed.rows.ctypes.data_as(C.POINTER(C.c_float)),
+                                            packed.offsets.ctypes.data_as(C.POINTER(C.c_int)), 1 if per_stage else 0))
+
+    def batch_stage_dev(self, stage: int, name: str, flags: int, k: int, cand_dev_ptr: int, n_cand: int,
+                        allow_prefilter: bool, out_scores_dev_ptr: int, out_ids_dev_ptr: int, stream: int) -> None:
+        N.check(self._lib.vrag_batch_stage_dev(self._h, int(stage), name.encode(), int(flags), int(k),
+                                               C.c_void_p(cand_dev_ptr) if cand_dev_ptr else None, int(n_cand),
+                                               1 if allow_prefilter else 0, C.c_void_p(out_scores_dev_ptr),
+                                               C.c_void_p(out_ids_dev_ptr) if out_ids_dev_ptr else None, C.c_void_p(stream)))
+
+    def batch_prefilter_failed(self, stream: int) -> bool:
+        f = C.c_int()
+        N.check(self._lib.vrag_batch_prefilter_failed(self._h, C.c_void_p(stream), C.byref(f)))
+        return bool(f.value)
+
+    def topk_batch_dev(self, scores_dev_ptr: int, ids_dev_ptr: int, n: int, k: int, nq: int, out_scores_dev_ptr: int,
+                       out_ids_dev_ptr: int, stream: int) -> None:
+        N.check(self._lib.vrag_topk_batch_dev(self._h, C.c_void_p(scores_dev_ptr), C.c_void_p(ids_dev_ptr), int(n), int(k),
+                                              int(nq), C.c_void_p(out_scores_dev_ptr), C.c_void_p(out_ids_dev_ptr),
+                                              C.c_void_p(stream)))
+
     # ------------------------------------------------------------------ measurement
     def last_timing_ms(self) -> Tuple[float, float]:
         buf = (C.c_float * 2)()

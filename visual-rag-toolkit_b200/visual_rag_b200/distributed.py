@@ -16,7 +16,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from .corpus import GpuCorpus, _as_f32_query, query_flags
+from .corpus import GpuCorpus, PackedQueries, _as_f32_query, pack_queries, query_flags
 
 
 def shard_page_range(n_pages_total: int, rank: int, world: int) -> Tuple[int, int]:
@@ -77,6 +77,14 @@ class ShardedSearcher:
         if n_items > 0:
             c.score_dev(name, self._q_dev.data_ptr(), n_q, flags, cand.data_ptr() if cand is not None else 0,
                         n_items, scores.data_ptr(), stream)
+        if cand is not None and self.world > 1:
+            # candidate stage: every candidate is owned by exactly one shard (-inf elsewhere) -> one max-all-reduce of
+            # the score vector, then the same top-k on every rank: ties keep candidate order, exactly like one shard
+            self.dist.all_reduce(scores, op=self.dist.ReduceOp.MAX, group=self.group)
+            ms = self._buf(tag + "_ms", k, torch.float32)
+            mi = self._buf(tag + "_mi", k, torch.int64)
+            c.topk_dev(scores.data_ptr(), cand.data_ptr(), 0, n_items, k, ms.data_ptr(), mi.data_ptr(), stream)
+            return ms, mi
         ls = self._buf(tag + "_ls", k, torch.float32)
         li = self._buf(tag + "_li", k, torch.int64)
         c.topk_dev(scores.data_ptr(), cand.data_ptr() if cand is not None else 0, c.page_base, n_items, k,
@@ -122,3 +130,67 @@ class ShardedSearcher:
 
     def search(self, name: str, query, k: int, normalize: bool = True, pool_query: bool = False):
         return self.search_multistage([(name, pool_query, k)], query, normalize)[0]
+
+    # ------------------------------------------------------------------ batched queries
+    def search_multistage_batch(self, stages: Sequence[Tuple[str, bool, int]], queries, normalize: bool = True):
+        """A batch of independent multi-stage searches over the sharded corpus (BASELINE configs[2] on several GPUs):
+        every rank uploads the same queries, scores each stage on its shard for ALL queries in one or two launches
+        (dense stage 0 with the fused top-k prefilter, candidate stages with the operand-switching kernel), and the
+        per-shard lists of the whole batch travel in ONE all-gather per stage ([n_queries, k] scores + ids) before the
+        batched deterministic merge. Returns per stage (scores [nq,k], ids [nq,k]) numpy arrays, identical on every
+        rank; invalid slots are (-inf, -1)."""
+        packed = queries if isinstance(queries, PackedQueries) else pack_queries(queries)
+        nq = len(packed)
+        if nq == 0:
+            return [(np.empty((0, int(k)), np.float32), np.empty((0, int(k)), np.int64)) for _, _, k in stages]
+        c = self.corpus
+        c.batch_upload(len(stages), packed)
+        stream = torch.cuda.current_stream(self.device).cuda_stream if self.on_gpu else 0
+        for allow_prefilter in (True, False):
+            dev = []
+            cand = None
+            for s, (name, pool, k) in enumerate(stages):
+                k = int(k)
+                ls = self._buf(f"b{s}_ls", nq * k, torch.float32)
+                li = self._buf(f"b{s}_li", nq * k, torch.int64)
+                if cand is not None and self.world > 1:
+                    # candidate stage across shards: raw scores of every candidate (-inf where another shard owns the
+                    # page), ONE max-all-reduce for the whole batch, then the batched top-k in candidate order
+                    n_cand = int(cand.numel() // nq)
+                    raw = self._buf(f"b{s}_raw", nq * n_cand, torch.float32)
+                    c.batch_stage_dev(s, name, query_flags(normalize, pool), 0, cand.data_ptr(), n_cand, False,
+                                      raw.data_ptr(), 0, stream)
+                    self.dist.all_reduce(raw, op=self.dist.ReduceOp.MAX, group=self.group)
+                    c.topk_batch_dev(raw.data_ptr(), cand.data_ptr(), n_cand, k, nq, ls.data_ptr(), li.data_ptr(), stream)
+                    dev.append((ls, li, k))
+                    cand = li
+                    continue
+                c.batch_stage_dev(s, name, query_flags(normalize, pool), k, cand.data_ptr() if cand is not None else 0,
+                                  int(cand.numel() // nq) if cand is not None else 0, allow_prefilter, ls.data_ptr(),
+                                  li.data_ptr(), stream)
+                if self.world == 1:
+                    ms, mi = ls, li
+                else:
+                    gs = self._buf(f"b{s}_gs", nq * k * self.world, torch.float32)
+                    gi = self._buf(f"b{s}_gi", nq * k * self.world, torch.int64)
+                    self.dist.all_gather_into_tensor(gs, ls, group=self.group)
+                    self.dist.all_gather_into_tensor(gi, li, group=self.group)
+                    # [world][nq][k] -> [nq][world*k]: rank-major inside every query row, so that "lower position" is
+                    # "lower global id" among equal scores of different shards (contiguous page ranges per rank)
+                    ps = self._buf(f"b{s}_ps", nq * k * self.world, torch.float32)
+                    pi = self._buf(f"b{s}_pi", nq * k * self.world, torch.int64)
+                    ps.view(nq, self.world, k).copy_(gs.view(self.world, nq, k).permute(1, 0, 2))
+                    pi.view(nq, self.world, k).copy_(gi.view(self.world, nq, k).permute(1, 0, 2))
+                    ms = self._buf(f"b{s}_ms", nq * k, torch.float32)
+                    mi = self._buf(f"b{s}_mi", nq * k, torch.int64)
+                    c.topk_batch_dev(ps.data_ptr(), pi.data_ptr(), k * self.world, k, nq, ms.data_ptr(), mi.data_ptr(), stream)
+                dev.append((ms, mi, k))
+                cand = mi
+            failed = c.batch_prefilter_failed(stream) if allow_prefilter else False
+            if self.world > 1 and allow_prefilter:
+                flag = torch.tensor([1 if failed else 0], dtype=torch.int32, device=self.device)
+                self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX, group=self.group)
+                failed = bool(flag.item())
+            if not failed:
+                break
+        return [(ms.view(nq, k).cpu().numpy(), mi.view(nq, k).cpu().numpy()) for ms, mi, k in dev]
