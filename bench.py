@@ -452,6 +452,20 @@ def run_extras(corpus, args, peak, kern_ms):
         t0 = time.perf_counter()
         arr = corpus.search_multistage_batch(stages, packed, as_arrays=True)
         walls_packed.append(time.perf_counter() - t0)
+    walls_final = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        fin = corpus.search_multistage_batch(stages, packed, final_only=True)
+        walls_final.append(time.perf_counter() - t0)
+    # the reference-facing call: ThreeStageRetriever.search_server_side_batch -> list of result dicts per query
+    from visual_rag_b200.client import GpuCorpusClient
+    from visual_rag_b200.retrieval import ThreeStageRetriever
+
+    retr = ThreeStageRetriever(GpuCorpusClient(corpus, "bench"), "bench")
+    retr.search_server_side_batch(query_embeddings=queries, top_k=100, stage1_k=1000, stage2_k=300)
+    t0 = time.perf_counter()
+    hits = retr.search_server_side_batch(query_embeddings=queries, top_k=100, stage1_k=1000, stage2_k=300)
+    retr_wall = time.perf_counter() - t0
     res = corpus.search_multistage_batch(stages, queries)
     t0 = time.perf_counter()
     for q in queries[:32]:
@@ -463,6 +477,9 @@ def run_extras(corpus, args, peak, kern_ms):
                     f"pooled rows min(H,32), global 1 row; {nq} queries with 10..30 tokens; stage1_k=1000, stage2_k=300, top_k=100",
         "batch_wall_ms": 1e3 * float(np.median(walls)), "batch_device_ms": dev_ms, "qps": nq / float(np.median(walls)),
         "batch_wall_ms_prepacked_queries": 1e3 * float(np.median(walls_packed)), "qps_prepacked_queries": nq / float(np.median(walls_packed)),
+        "batch_wall_ms_final_only": 1e3 * float(np.median(walls_final)), "qps_final_only": nq / float(np.median(walls_final)),
+        "retriever_batch_wall_ms": 1e3 * retr_wall, "retriever_batch_qps": nq / retr_wall,
+        "retriever_results_match": bool([h["id"] for h in hits[31]] == [int(i) for i in res[31][2][1]] if True else False),
         "ms_per_query_batched": 1e3 * float(np.median(walls)) / nq, "ms_per_query_sequential_api": seq_ms,
         "last_query_matches_single_query_path": same}
     for nm in ("initial", "experimental_pooling", "global_pooling"):

@@ -124,6 +124,15 @@ int vrag_search_multistage_batch(vrag_corpus_t* c, int n_stages, const char* con
                                  const int* ks, int n_queries, const float* query_rows, const int* q_offsets,
                                  int per_stage_queries, float* out_scores, int64_t* out_ids, int* out_counts);
 
+/* Same search, compact results: only the LAST stage's lists travel to the host (out_scores / out_ids [n_queries][ks[last]],
+ * out_counts [n_queries]) plus, for every final result, the score its page had in each earlier stage
+ * (out_stage_scores [n_queries][ks[last]][n_stages-1], NaN if absent) — exactly what the result dictionaries of
+ * ThreeStageRetriever.search_server_side carry (score_stage1 / score_stage2 / score_stage3, three_stage.py:160-173).   */
+int vrag_search_multistage_batch_final(vrag_corpus_t* c, int n_stages, const char* const* names, const uint32_t* flags,
+                                       const int* ks, int n_queries, const float* query_rows, const int* q_offsets,
+                                       int per_stage_queries, float* out_scores, int64_t* out_ids, float* out_stage_scores,
+                                       int* out_counts);
+
 /* Device-level form of the batched search for the sharded multi-GPU path (the caller all-gathers the per-shard lists with
  * NCCL between the stages): upload the batch once, then per stage score it on this shard — cand_ids_dev == NULL: every
  * page, with the fused top-k prefilter when allow_prefilter != 0; else per-query candidate lists [n_queries][n_cand] of

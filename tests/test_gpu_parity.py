@@ -689,3 +689,28 @@ def test_sharded_batched_search_single_rank_equals_corpus_batch(corpus):
         assert np.array_equal(wi, gi) and np.array_equal(ws, gs)
     for nm in ("sb_glob", "sb_exp", "sb_init"):
         corpus.drop_store(nm)
+
+
+@pytest.mark.gpu
+def test_final_only_batch_results(corpus):
+    """final_only: last-stage lists + the earlier-stage scores of the final pages == the full per-stage lists."""
+    rng = np.random.default_rng(71)
+    n = 500
+    g = rng.standard_normal((n, 128)).astype(np.float16)
+    e = rng.standard_normal((n * 16, 128)).astype(np.float16)
+    i = rng.standard_normal((n * 150, 128)).astype(np.float16)
+    corpus.add_store("fo_g", g, fixed_rows=1)
+    corpus.add_store("fo_e", e, fixed_rows=16)
+    corpus.add_store("fo_i", i, fixed_rows=150)
+    qs = [rng.standard_normal((int(rng.integers(4, 30)), 128)).astype(np.float32) for _ in range(9)]
+    stages = [("fo_g", True, 120), ("fo_e", False, 40), ("fo_i", False, 7)]
+    full = corpus.search_multistage_batch(stages, qs)
+    sc, ids, st, cnt = corpus.search_multistage_batch(stages, qs, final_only=True)
+    assert sc.shape == (9, 7) and st.shape == (9, 7, 2) and cnt.tolist() == [7] * 9
+    for b in range(9):
+        assert ids[b].tolist() == full[b][2][1].tolist() and np.array_equal(sc[b], full[b][2][0])
+        for s in range(2):
+            lut = dict(zip(full[b][s][1].tolist(), full[b][s][0].tolist()))
+            assert [lut[p] for p in ids[b].tolist()] == st[b, :, s].tolist()
+    for nm in ("fo_g", "fo_e", "fo_i"):
+        corpus.drop_store(nm)

@@ -649,6 +649,34 @@ __global__ void prefilter_check_kernel(int* __restrict__ cnt, int batch, int nee
   }
 }
 
+// For every final result (query q, rank j) look its page id up in an earlier stage's list and fetch the score it had
+// there (NaN if absent): the score_stage1 / score_stage2 fields of ThreeStageRetriever's result dicts
+// (three_stage.py:160-173) without shipping the whole stage lists to the host. One warp per (q, j).
+__global__ void __launch_bounds__(256) gather_stage_scores_kernel(const long long* __restrict__ final_ids, int k_final, int nq,
+                                                                  const long long* __restrict__ stage_ids,
+                                                                  const float* __restrict__ stage_scores, int k_stage,
+                                                                  float* __restrict__ out, int out_stride, int out_col) {
+  const long long w = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= static_cast<long long>(nq) * k_final) return;
+  const int q = static_cast<int>(w / k_final);
+  const long long id = final_ids[w];
+  float found = __int_as_float(0x7fc00000);
+  if (id >= 0) {
+    const long long* ids = stage_ids + static_cast<long long>(q) * k_stage;
+    for (int i0 = 0; i0 < k_stage; i0 += 32) {
+      const int i = i0 + lane;
+      const bool hit = i < k_stage && ids[i] == id;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) {
+        found = stage_scores[static_cast<long long>(q) * k_stage + i0 + (__ffs(m) - 1)];
+        break;
+      }
+    }
+  }
+  if (lane == 0) out[w * out_stride + out_col] = found;
+}
+
 __global__ void sel_init_kernel(SelState* st, int k, int batch) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < batch) {

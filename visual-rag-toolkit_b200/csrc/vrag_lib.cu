@@ -147,6 +147,7 @@ struct vrag_corpus {
   DevBuf<int> d_qmeta;            // batched search: [n_stages][2][nq] query row ranges + [nq] effective rows
   DevBuf<float> d_fthr, d_ftop;   // prefilter: thresholds [nq], sample top-m scores [nq][m]
   DevBuf<long long> d_ftop_ids;
+  DevBuf<float> d_stage_sc;       // final-only batch results: earlier-stage scores of the final ids
   DevBuf<int> d_fcnt;             // prefilter: candidate counts [nq] + flag [1]
   DevBuf<unsigned long long> d_fkeys;   // prefilter: candidate keys [nq][cap]
   int* h_flag = nullptr;          // pinned
@@ -236,6 +237,7 @@ extern "C" int vrag_corpus_destroy(vrag_corpus_t* c) {
   c->d_ftop.release();
   c->d_ftop_ids.release();
   c->d_fcnt.release();
+  c->d_stage_sc.release();
   c->d_fkeys.release();
   if (c->h_flag) cudaFreeHost(c->h_flag);
   if (c->h_qmeta) cudaFreeHost(c->h_qmeta);
@@ -1203,10 +1205,14 @@ static int batch_prepare_stage(vrag_corpus* c, Store& store, int k, int64_t n_it
 static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const char* const* names,
                                         const uint32_t* flags, const int* ks, int n_queries, const float* query_rows,
                                         const int* q_offsets, int per_stage_queries, float* out_scores,
-                                        int64_t* out_ids, int* out_counts, bool no_prefilter) {
+                                        int64_t* out_ids, int* out_counts, bool no_prefilter,
+                                        float* out_stage_scores = nullptr, bool final_only = false) {
+  // final_only: only the last stage's lists ([nq][k_last]) travel to the host, plus for every final result its score in
+  // each earlier stage (out_stage_scores [nq][k_last][n_stages-1], NaN if absent); out_counts is [nq].
   if (!c) return fail("corpus is NULL");
   if (n_stages < 1 || n_stages > kMaxStages) return fail("n_stages %d out of range [1,%d]", n_stages, kMaxStages);
   if (!names || !flags || !ks || !out_scores || !out_ids || !out_counts || !query_rows || !q_offsets) return fail("NULL argument");
+  if (final_only && n_stages > 1 && !out_stage_scores) return fail("out_stage_scores is NULL");
   if (n_queries < 0) return fail("n_queries < 0");
   if (n_queries == 0) return 0;
   TRY(set_device(c));
@@ -1225,7 +1231,10 @@ static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const ch
   const size_t out_n = total_k * nq;
   TRY(c->d_out_scores.ensure(out_n));
   TRY(c->d_out_ids.ensure(out_n));
-  TRY(ensure_host_out(c, out_n));
+  const int k_last = ks[n_stages - 1];
+  const size_t stage_sc_n = static_cast<size_t>(nq) * k_last * std::max(n_stages - 1, 1);
+  TRY(ensure_host_out(c, std::max(out_n, stage_sc_n)));
+  if (final_only) TRY(c->d_stage_sc.ensure(stage_sc_n));
   const int64_t n_pages = st[0]->n_pages;
   PrefilterPlan plan;
   int qchunk = 1;
@@ -1250,13 +1259,34 @@ static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const ch
                             s == 0 ? plan : PrefilterPlan(), &timed));
       d_prev_ids = o_id;
       n_prev = std::min<int64_t>(ks[s], n_prev);
-      for (int b = 0; b < qc; ++b) out_counts[static_cast<size_t>(s) * nq + b0 + b] = static_cast<int>(n_prev);
+      if (!final_only) for (int b = 0; b < qc; ++b) out_counts[static_cast<size_t>(s) * nq + b0 + b] = static_cast<int>(n_prev);
+      else if (s == n_stages - 1) for (int b = 0; b < qc; ++b) out_counts[b0 + b] = static_cast<int>(n_prev);
+      off += ks[s];
+    }
+  }
+  const size_t off_last = (total_k - k_last) * nq;   // the last stage's [nq][k_last] block
+  if (final_only) {
+    size_t off = 0;
+    for (int s = 0; s + 1 < n_stages; ++s) {
+      const long long warps = static_cast<long long>(nq) * k_last;
+      gather_stage_scores_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, c->stream>>>(
+          c->d_out_ids.p + off_last, k_last, nq, c->d_out_ids.p + off * nq, c->d_out_scores.p + off * nq, ks[s], c->d_stage_sc.p,
+          n_stages - 1, s);
+      c->launches++;
       off += ks[s];
     }
   }
   CUDA_OK(cudaEventRecord(c->ev1, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->h_out_scores, c->d_out_scores.p, out_n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->h_out_ids, c->d_out_ids.p, out_n * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  if (final_only) {
+    const size_t fn = static_cast<size_t>(nq) * k_last;
+    CUDA_OK(cudaMemcpyAsync(c->h_out_ids, c->d_out_ids.p + off_last, fn * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(out_scores, c->d_out_scores.p + off_last, fn * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (n_stages > 1)
+      CUDA_OK(cudaMemcpyAsync(c->h_out_scores, c->d_stage_sc.p, stage_sc_n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    CUDA_OK(cudaMemcpyAsync(c->h_out_scores, c->d_out_scores.p, out_n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->h_out_ids, c->d_out_ids.p, out_n * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  }
   if (plan.on) CUDA_OK(cudaMemcpyAsync(c->h_flag, c->d_fcnt.p + nq, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
   if (plan.on && *c->h_flag) {
@@ -1264,13 +1294,27 @@ static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const ch
     *c->h_flag = 0;
     c->prefilter_fallbacks++;
     return search_multistage_batch_impl(c, n_stages, names, flags, ks, n_queries, query_rows, q_offsets, per_stage_queries,
-                                        out_scores, out_ids, out_counts, true);
+                                        out_scores, out_ids, out_counts, true, out_stage_scores, final_only);
   }
-  memcpy(out_scores, c->h_out_scores, out_n * sizeof(float));
-  memcpy(out_ids, c->h_out_ids, out_n * sizeof(long long));
+  if (final_only) {
+    memcpy(out_ids, c->h_out_ids, static_cast<size_t>(nq) * k_last * sizeof(long long));
+    if (n_stages > 1) memcpy(out_stage_scores, c->h_out_scores, stage_sc_n * sizeof(float));
+  } else {
+    memcpy(out_scores, c->h_out_scores, out_n * sizeof(float));
+    memcpy(out_ids, c->h_out_ids, out_n * sizeof(long long));
+  }
   cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1);
   if (timed) cudaEventElapsedTime(&c->last_ms[1], c->evk0, c->evk1);
   return 0;
+}
+
+extern "C" int vrag_search_multistage_batch_final(vrag_corpus_t* c, int n_stages, const char* const* names,
+                                                  const uint32_t* flags, const int* ks, int n_queries,
+                                                  const float* query_rows, const int* q_offsets, int per_stage_queries,
+                                                  float* out_scores, int64_t* out_ids, float* out_stage_scores,
+                                                  int* out_counts) {
+  return search_multistage_batch_impl(c, n_stages, names, flags, ks, n_queries, query_rows, q_offsets, per_stage_queries,
+                                      out_scores, out_ids, out_counts, false, out_stage_scores, true);
 }
 
 // ---- device-level batched stage API (sharded multi-GPU search: NCCL all-gathers run between the stages)

@@ -277,6 +277,31 @@ class GpuCorpusClient:
             out.append(stages)
         return out
 
+    def query_multistage_batch_final(self, *, usings: Sequence[str], limits: Sequence[int],
+                                     stage_queries: Sequence[Sequence[Any]], with_payload: bool = True):
+        """`query_multistage_batch` with compact results: per query a list of (ScoredPoint of the LAST stage, [score of
+        that page in stage 0, stage 1, ...]) — the long intermediate lists stay on the device."""
+        ns = len(usings)
+        sq = [[self._as_query(x) for x in per_query] for per_query in stage_queries]
+        sc, ids, st, cnt = self.corpus.search_multistage_batch(
+            [(usings[s], False, int(limits[s])) for s in range(ns)], None, stage_queries=sq, final_only=True)
+        # plain Python lists once (numpy scalar access per element would dominate the whole call)
+        sc_l, ids_l, st_l, cnt_l = sc.tolist(), ids.tolist(), st.tolist(), cnt.tolist()
+        inf = float("inf")
+        out = []
+        for b in range(len(sc_l)):
+            row = []
+            srow, irow, trow = sc_l[b], ids_l[b], st_l[b]
+            for j in range(cnt_l[b]):
+                s = srow[j]
+                if s != s or s == inf or s == -inf:
+                    continue
+                page = irow[j]
+                row.append((ScoredPoint(self._pid(page), s, self._payload(page) if with_payload else None),
+                            [None if x != x else x for x in trow[j]]))
+            out.append(row)
+        return out
+
     def retrieve(self, collection_name=None, ids=(), with_payload=False, with_vectors=None, timeout=None, **_ignored):
         out = []
         names = [] if not with_vectors else (list(with_vectors) if not isinstance(with_vectors, bool) else [])

@@ -375,13 +375,17 @@ class GpuCorpus:
         normalize: bool = True,
         stage_queries: Optional[Sequence[Sequence]] = None,
         as_arrays: bool = False,
+        final_only: bool = False,
     ):
         """`search_multistage` for a batch of independent queries in ONE native call / host synchronisation
         (BASELINE configs[2]: 256 queries). queries: sequence of [Q_b,128] matrices (ragged). stage_queries:
         optional, per query a sequence of one matrix per stage (e.g. the mean-pooled prefetch vector and the
         token matrix, two_stage.py:142,159). Returns, per query, the per-stage (scores, ids) lists; with
         as_arrays=True instead one (scores [nq,k_s], ids [nq,k_s], counts [nq]) triple per stage (no per-query
-        Python work: rows are valid up to their count, the rest is (-inf, -1))."""
+        Python work: rows are valid up to their count, the rest is (-inf, -1)). final_only=True returns just
+        (scores [nq,k_last], ids [nq,k_last], stage_scores [nq,k_last,n_stages-1], counts [nq]): the last stage's lists and,
+        for every final result, the score its page had in each earlier stage (NaN if absent) — what the retrievers' result
+        dictionaries carry — so the long intermediate lists never leave the device."""
         ns = len(stages)
         if stage_queries is not None:
             mats = []
@@ -410,6 +414,21 @@ class GpuCorpus:
         flags = (C.c_uint32 * ns)(*[query_flags(normalize, bool(s[1])) for s in stages])
         ks = [int(s[2]) for s in stages]
         ks_c = (C.c_int * ns)(*ks)
+        if final_only:
+            kl = ks[-1]
+            f_sc = np.empty((nq, kl), dtype=np.float32)
+            f_id = np.empty((nq, kl), dtype=np.int64)
+            f_st = np.empty((nq, kl, max(ns - 1, 1)), dtype=np.float32)
+            f_cnt = np.zeros((nq,), dtype=np.int32)
+            N.check(
+                self._lib.vrag_search_multistage_batch_final(
+                    self._h, ns, names, flags, ks_c, nq, rows.ctypes.data_as(C.POINTER(C.c_float)),
+                    offs.ctypes.data_as(C.POINTER(C.c_int)), per_stage,
+                    f_sc.ctypes.data_as(C.POINTER(C.c_float)), f_id.ctypes.data_as(C.POINTER(C.c_int64)),
+                    f_st.ctypes.data_as(C.POINTER(C.c_float)), f_cnt.ctypes.data_as(C.POINTER(C.c_int)),
+                )
+            )
+            return f_sc, f_id, f_st[:, :, : ns - 1], f_cnt
         total = int(sum(ks)) * nq
         scores = np.empty((total,), dtype=np.float32)
         ids = np.empty((total,), dtype=np.int64)

@@ -124,7 +124,7 @@ class ThreeStageRetriever:
         in one native call — the global stage as a dense batched scan with the fused top-k prefilter, the two
         ID-restricted stages as one launch each; with a filter (or any other client) it is the per-query loop the
         reference's evaluation runs (run_qdrant_beir.py:378-402). Same result dicts as search_server_side."""
-        batch = getattr(self.client, "query_multistage_batch", None)
+        batch = getattr(self.client, "query_multistage_batch_final", None)
         if batch is None or filter_obj is not None:
             return [self.search_server_side(query_embedding=q, top_k=top_k, stage1_k=stage1_k, stage2_k=stage2_k,
                                             filter_obj=filter_obj) for q in query_embeddings]
@@ -135,19 +135,12 @@ class ThreeStageRetriever:
         res = self._retry_call(lambda: batch(
             usings=[self.global_vector_name, self.experimental_vector_name, self.full_vector_name],
             limits=[stage1_k, stage2_k, int(top_k)], stage_queries=sq))
-        out = []
-        for s1, s2, s3 in res:
-            if not s1 or not s2:
-                out.append([])
-                continue
-            s1_score = {str(p.id): float(p.score) for p in s1}
-            s2_score = {str(p.id): float(p.score) for p in s2}
-            out.append([{
-                "id": p.id,
-                "score_stage1": s1_score.get(str(p.id)),
-                "score_stage2": s2_score.get(str(p.id)),
-                "score_stage3": float(p.score),
-                "score_final": float(p.score),
-                "payload": p.payload,
-            } for p in s3])
-        return out
+        # compact results: the final points plus their stage-1 / stage-2 scores (looked up on the device)
+        return [[{
+            "id": p.id,
+            "score_stage1": st[0],
+            "score_stage2": st[1],
+            "score_stage3": float(p.score),
+            "score_final": float(p.score),
+            "payload": p.payload,
+        } for p, st in per_query] for per_query in res]

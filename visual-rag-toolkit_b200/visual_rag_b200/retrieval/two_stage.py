@@ -101,7 +101,7 @@ class TwoStageRetriever:
     ) -> List[List[Dict[str, Any]]]:
         """`search_server_side` for a batch of queries: one native call on a GpuCorpusClient (stage 1 as a dense
         batched scan, the rerank of all queries as one launch); otherwise the per-query loop."""
-        batch = getattr(self.client, "query_multistage_batch", None)
+        batch = getattr(self.client, "query_multistage_batch_final", None)
         if batch is None or filter_obj is not None:
             return [self.search_server_side(q, top_k=top_k, prefetch_k=prefetch_k, filter_obj=filter_obj,
                                             stage1_mode=stage1_mode) for q in query_embeddings]
@@ -114,7 +114,7 @@ class TwoStageRetriever:
         res = self._retry_call(lambda: batch(usings=[prefetch_using, self.full_vector_name],
                                              limits=[int(prefetch_k), int(top_k)], stage_queries=sq))
         return [[{"id": r.id, "score_stage1": None, "score_stage2": r.score, "score_final": r.score, "payload": r.payload}
-                 for r in stages[-1]] for stages in res]
+                 for r, _ in per_query] for per_query in res]
 
     # ------------------------------------------------------------------ client-side flow
     def search(
