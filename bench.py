@@ -374,8 +374,8 @@ def run_ours(args):
                          "frac_of_8TBs_nominal": achieved / 8000.0,
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": pages * bytes_per_page,
                          "traffic": (args.ncu_traffic_ratio * pages * bytes_per_page) if args.ncu_traffic_ratio else None,
-                         "traffic_source": "dram__bytes_read+write per launch / algorithmic bytes = 1.0079 in the ncu --set full "
-                                           "capture at 100k pages per launch (profiles/r1c_kernels_ncu_summary.md, column `large`), scaled to this launch"},
+                         "traffic_source": "dram__bytes_read+write per launch / algorithmic bytes = 1.0021 in the ncu --set full "
+                                           "capture at 100k pages per launch (profiles/r1d_kernels_ncu_summary.md, column `large`), scaled to this launch"},
             "cpu_baseline": {"value": cpu_pps, "unit": "pages/s", "cores": blas_threads, "kind": "port",
                              "sample": f"first {n_cpu} pages of the same corpus read back from the device, {cpu_passes} queries one after "
                                        f"the other ({cpu_passes * n_cpu} page scorings, {cpu_s:.1f} s); oracle/maxsim_oracle.py::search_exhaustive "
@@ -528,7 +528,7 @@ def main():
     ap.add_argument("--latency-queries", type=int, default=200)
     ap.add_argument("--cfg2-pages", type=int, default=1_000_000)
     ap.add_argument("--cfg4-pages", type=int, default=400_000)
-    ap.add_argument("--ncu-traffic-ratio", type=float, default=1.0079,
+    ap.add_argument("--ncu-traffic-ratio", type=float, default=1.0021,
                     help="DRAM bytes / algorithmic bytes of the scan kernel in the committed ncu capture (profiles/)")
     args = ap.parse_args()
     if args.warmup < 3:
