@@ -53,6 +53,12 @@ elif what == "packed_batch":
     for _ in range(reps):
         c.search_multistage_batch([("mean_pooling", False, 256)], qs)
     print("packed_batch", n, c.last_timing_ms())
+elif what == "colsmol13":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 2_000_000
+    c.add_synthetic_store("mean_pooling", n, fixed_rows=13, seed=2)
+    for _ in range(reps):
+        c.search("mean_pooling", q20, 256)
+    print("colsmol13", n, c.last_timing_ms())
 elif what == "rerank":
     c.add_synthetic_store("initial", 100_000, fixed_rows=1030, seed=1)
     cand = rng.permutation(100_000)[:256]

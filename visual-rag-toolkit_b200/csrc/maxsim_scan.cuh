@@ -57,6 +57,10 @@ struct ScanParams {
   int hi_only;                // 1: contract only the fp16 hi half of the query (N = QP); QP >= 16
   int shfl_rows;              // PACKED: > 0 -> every page sits in its own power-of-two slot of shfl_rows (<= 32) tile
                               //   rows, so the per-page max is a segmented warp butterfly (no smem round trip)
+  int pad_rows;               // PACKED + dense + fixed_rows not a power of two (<= 32): > 0 -> pages are fetched through a
+                              //   3-D tensor map {128 cols, fixed_rows, n_pages} with a {64, shfl_rows, 128/shfl_rows} box: rows
+                              //   fixed_rows..shfl_rows-1 of every page are out of bounds, so TMA zero-fills them and every
+                              //   page lands in its own power-of-two slot of the tile (value = fixed_rows)
   long long n_tiles;          // PACKED: number of tiles (work units) per group
   // ---- query groups (batched candidate lists; BSW kernels). Group g = query g with its own operand image
   // qimg + g*qimg_stride, its own candidate list cand[g*n_items + i] and its own scores[g*n_items + i];
@@ -572,7 +576,17 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           uint8_t* a = sA + stage * kTileBytes;
           float* sc = sScale + stage * kScaleStride;
           uint32_t bytes = 0;
-          if (cur.nr[0] > 0)
+          if (p.pad_rows > 0) {
+            // padded slots: the first map is the store's 3-D {cols, rows-in-page, pages} view; one box per K-half
+            const int32_t pg0 = static_cast<int32_t>(cur.r0[0] / p.pad_rows);
+            tma_load_3d(a, &tm_rows128, &full[stage], 0, 0, pg0);
+            tma_load_3d(a + kHalfBytes, &tm_rows128, &full[stage], 64, 0, pg0);
+            bytes = kTileBytes;   // out-of-bounds rows / pages are zero-filled and counted
+            if (use_scale) {
+              tma_load_1d(sc, &tm_scale128, &full[stage], static_cast<int32_t>(cur.r0[0]) & ~3);
+              bytes += kScaleBoxBig * 4;
+            }
+          } else if (cur.nr[0] > 0)
             bytes = issue_rows(a, sc, &full[stage], &tm_rows128, &tm_rows32, &tm_scale128, &tm_scale32, cur.r0[0],
                                cur.nr[0], 0, use_scale);
           sMis[stage * 4] = static_cast<int>(cur.r0[0] & 3);
@@ -787,7 +801,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             bool item_ok;
             if (!p.slot_mode) {
               item_ok = page < p.n_pages;
-              nr = item_ok ? SR : 0;
+              nr = item_ok ? (p.pad_rows > 0 ? p.pad_rows : SR) : 0;
             } else {
               item_ok = item < p.n_items;
             }
@@ -797,9 +811,14 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             if (p.slot_mode) nr = item_ok ? (sMis[stage * 4 + slot] >> 2) : 0;   // slot == 32-row slot here (SR == 32)
             float scale = 1.0f;
             if (use_scale) {
-              const int sslot = trow / p.slot_rows;
-              scale = sScale[stage * kScaleStride + sslot * (p.slot_rows + 32) + (trow - sslot * p.slot_rows) +
-                             (sMis[stage * 4 + sslot] & 3)];
+              if (p.pad_rows > 0) {
+                // padded slots: the scale rows are the tile's real rows back to back (slot j starts at j * fixed_rows)
+                scale = rin < nr ? sScale[stage * kScaleStride + slot * p.pad_rows + rin + (sMis[stage * 4] & 3)] : 0.0f;
+              } else {
+                const int sslot = trow / p.slot_rows;
+                scale = sScale[stage * kScaleStride + sslot * (p.slot_rows + 32) + (trow - sslot * p.slot_rows) +
+                               (sMis[stage * 4 + sslot] & 3)];
+              }
             }
             float v[QE];
             const bool live = rin < nr;

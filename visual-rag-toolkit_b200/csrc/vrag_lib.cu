@@ -71,6 +71,20 @@ static int make_rows_map(CUtensorMap* m, void* base, int64_t total_rows, int box
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(rows, box=%d) failed: %d", box_rows, (int)r);
   return 0;
 }
+// 3-D view {128 cols, rows_per_page, n_pages} of a fixed-rows store; box {64, slot_rows, 128/slot_rows}: the rows of a
+// page beyond rows_per_page are out of bounds and arrive as zeros, so every page fills a power-of-two slot of the tile.
+static int make_padded_map(CUtensorMap* m, void* base, int64_t n_pages, int rows_per_page, int slot_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail("cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t dims[3] = {128, static_cast<cuuint64_t>(rows_per_page), static_cast<cuuint64_t>(n_pages)};
+  cuuint64_t strides[2] = {256, static_cast<cuuint64_t>(rows_per_page) * 256};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(slot_rows), static_cast<cuuint32_t>(kTileRows / slot_rows)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(padded, rows=%d slot=%d) failed: %d", rows_per_page, slot_rows, (int)r);
+  return 0;
+}
 static int make_scale_map(CUtensorMap* m, void* base, int64_t total_rows, int box_rows) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail("cuTensorMapEncodeTiled not available (no CUDA driver?)");
@@ -98,6 +112,8 @@ struct Store {
   bool dirty = false;            // appended to since the page tables / tensor maps were last built
   bool packed = false;
   CUtensorMap tm128, tm32, ts128, ts32;
+  CUtensorMap tm3d;              // fixed_rows <= 32, not a power of two: {128, fixed_rows, n_pages} view with a padded box
+  int pad_slot = 0;              // its slot height (next power of two), 0 when the view does not exist
 };
 
 template <typename T>
@@ -313,6 +329,13 @@ static int finish_store(vrag_corpus* c, Store& s, const int64_t* page_offsets, i
     CUDA_OK(cudaMalloc(&s.tile_row0, tr.size() * sizeof(long long)));
     CUDA_OK(cudaMemcpyAsync(s.tile_row0, tr.data(), tr.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
+  }
+  s.pad_slot = 0;
+  if (s.total_rows > 0 && fixed_rows > 0 && fixed_rows <= 32 && (fixed_rows & (fixed_rows - 1)) != 0) {
+    int slot = 4;
+    while (slot < fixed_rows) slot <<= 1;
+    TRY(make_padded_map(&s.tm3d, s.rows, n_pages, static_cast<int>(fixed_rows), slot));
+    s.pad_slot = slot;
   }
   if (s.total_rows > 0) {
     TRY(make_rows_map(&s.tm128, s.rows, s.total_rows, kTileRows));
@@ -569,7 +592,7 @@ static int launch_scan_t(vrag_corpus* c, const Store& s, const ScanParams& p, lo
     attr_done[c->device & 7] = true;
   }
   const unsigned grid = static_cast<unsigned>(std::min<long long>(c->num_sms, n_units));
-  kern<<<grid, ScanCfg<QP>::threads(PACKED, QS < QP), smem, st>>>(s.tm128, s.tm32, s.ts128, s.ts32, p);
+  kern<<<grid, ScanCfg<QP>::threads(PACKED, QS < QP), smem, st>>>(p.pad_rows > 0 ? s.tm3d : s.tm128, s.tm32, s.ts128, s.ts32, p);
   c->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -602,6 +625,12 @@ static void fill_scan_params(vrag_corpus* c, const Store& s, const long long* d_
       const int per_tile = kTileRows / p.slot_rows;
       p.n_tiles = (n_items + per_tile - 1) / per_tile;
       if (p.slot_rows == 32 && QP <= 32) p.shfl_rows = 32;
+    } else if (s.fixed_rows > 0 && s.pad_slot > 0 && (QP <= 32 || multi) && !getenv("VRAG_NO_PAD")) {
+      // odd page sizes (ColSmol's 12/13 tiles, 3, 5, ...): TMA pads every page to a power-of-two slot for free
+      p.pad_rows = static_cast<int>(s.fixed_rows);
+      p.shfl_rows = s.pad_slot;
+      p.pages_per_tile = kTileRows / s.pad_slot;
+      p.n_tiles = (s.n_pages + p.pages_per_tile - 1) / p.pages_per_tile;
     } else if (s.fixed_rows > 0) {
       p.pages_per_tile = static_cast<int>(kTileRows / s.fixed_rows);
       p.n_tiles = (s.n_pages + p.pages_per_tile - 1) / p.pages_per_tile;
