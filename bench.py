@@ -324,6 +324,24 @@ def run_ours(args):
     ts_wall = time.perf_counter() - t_all0
     barrier()
 
+    # the same two-stage search through the reference-facing class (TwoStageRetriever.search_server_side on the
+    # GpuCorpusClient: result dicts with payloads), single shard only — the sharded path has no per-shard client
+    retr_lat = None
+    if world == 1:
+        from visual_rag_b200.client import GpuCorpusClient
+        from visual_rag_b200.retrieval import TwoStageRetriever
+
+        retr = TwoStageRetriever(GpuCorpusClient(corpus, "bench"), "bench")
+        for i in range(5):
+            retr.search_server_side(queries[i % len(queries)], top_k=TOP_K, prefetch_k=PREFETCH_K, stage1_mode="tokens_vs_standard_pooling")
+        retr_lat = []
+        for i in range(n_lat):
+            t1 = time.perf_counter()
+            hits = retr.search_server_side(queries[i % len(queries)], top_k=TOP_K, prefetch_k=PREFETCH_K,
+                                           stage1_mode="tokens_vs_standard_pooling")
+            retr_lat.append(1e3 * (time.perf_counter() - t1))
+        assert len(hits) == TOP_K
+
     # ---------------- max over ranks ----------------
     vals = torch.tensor([dev_ms, e2e_s, kern_ms, ts_wall, float(np.percentile(lat, 50)), float(np.percentile(lat, 95))],
                         dtype=torch.float64, device="cuda")
@@ -388,6 +406,10 @@ def run_ours(args):
             "two_stage": {"mode": "tokens_vs_standard_pooling", "prefetch_k": PREFETCH_K, "top_k": TOP_K,
                           "qps": n_lat / ts_wall, "p50_ms": p50, "p95_ms": p95, "queries": n_lat,
                           "pooled_rows_per_page": POOLED_ROWS,
+                          "retriever_p50_ms": float(np.percentile(retr_lat, 50)) if retr_lat else None,
+                          "retriever_p95_ms": float(np.percentile(retr_lat, 95)) if retr_lat else None,
+                          "retriever_call": "TwoStageRetriever.search_server_side(q, top_k=10, prefetch_k=256, "
+                                            "stage1_mode='tokens_vs_standard_pooling') -> result dicts (N=1 only)",
                           "note": "mean_pooling derived on the device from `initial` (sequence-chunk mean pooling, 32 rows/page)"},
             "pooling": {"kind": "seq_chunks 1030 -> 32 rows/page (visual_embedder.py:824-835), fp16 in / fp16 out",
                         "pages_per_s_per_gpu": pages / (pool_ms * 1e-3), "ms": pool_ms,

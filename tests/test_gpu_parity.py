@@ -200,7 +200,7 @@ def test_edge_cases(corpus):
     with pytest.raises(VragError, match="unknown vector store"):
         corpus.score("missing", q)
     with pytest.raises(VragError):
-        corpus.search("e", CS.query_rows(1, 200), 5)       # > 128 query tokens in one call
+        corpus.search("e", CS.query_rows(1, 1025), 5)      # more query rows than the staging buffers hold (1024)
     with pytest.raises(ValueError):
         corpus.score("e", np.zeros((3, 64), np.float32))
     zero = np.zeros((2 * 8, 128), np.float16)               # all-zero rows: 0/(0+1e-8) = 0, as in numpy
@@ -713,4 +713,60 @@ def test_final_only_batch_results(corpus):
             lut = dict(zip(full[b][s][1].tolist(), full[b][s][0].tolist()))
             assert [lut[p] for p in ids[b].tolist()] == st[b, :, s].tolist()
     for nm in ("fo_g", "fo_e", "fo_i"):
+        corpus.drop_store(nm)
+
+
+# ------------------------------------------------------------------ maximum sizes: queries longer than one operand image
+@pytest.mark.gpu
+@pytest.mark.parametrize("q_rows", [129, 200, 300, 1024])
+def test_long_queries_are_scored_in_row_chunks(corpus, q_rows):
+    """The reference accepts any number of query tokens (pooling.py:468-514); more than 128 rows are scored as balanced
+    row chunks whose partial page scores add up — LARGE, PACKED and candidate-list scans, search and multistage."""
+    rng = np.random.default_rng(q_rows)
+    q = CS.query_rows(7000 + q_rows, q_rows)
+    lens = rng.integers(1, 400, size=41)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    rows = rows16(7100 + q_rows, int(off[-1]))
+    docs = [rows[off[i]:off[i + 1]].astype(np.float32) for i in range(len(lens))]
+    corpus.add_store("lq", rows, page_offsets=off)
+    want = np.array([MO.maxsim_score(q, d) for d in docs])
+    close(corpus.score("lq", q), want)
+    cand = rng.permutation(len(lens))[:17]
+    close(corpus.score("lq", q, candidate_ids=cand), want[cand])
+    pooled = rows16(7200 + q_rows, len(lens) * 32)
+    pdocs = [pooled[i * 32:(i + 1) * 32].astype(np.float32) for i in range(len(lens))]
+    corpus.add_store("lqp", pooled, fixed_rows=32)
+    close(corpus.score("lqp", q), [MO.maxsim_score(q, d) for d in pdocs])
+    got = corpus.search_multistage([("lqp", False, 20), ("lq", False, 5)], q)
+    ref = MO.multistage(q, [(pdocs, False, 20), (docs, False, 5)])
+    assert got[1][1].tolist() == [i for i, _ in ref[1]]
+    close(got[1][0], [s for _, s in ref[1]])
+    # pooled query of a long token matrix: one row after the mean, no chunking involved
+    ref1 = MO.multistage(q, [(pdocs, True, 9)])
+    s, ids = corpus.search("lqp", q, 9, pool_query=True)
+    assert ids.tolist() == [i for i, _ in ref1[0]]
+    for nm in ("lq", "lqp"):
+        corpus.drop_store(nm)
+
+
+@pytest.mark.gpu
+def test_long_queries_in_batches_and_saliency(corpus):
+    rng = np.random.default_rng(77)
+    n, t, r = 50, 150, 16
+    rows = rows16(7300, n * t)
+    pooled = rows16(7301, n * r)
+    docs = [rows[i * t:(i + 1) * t].astype(np.float32) for i in range(n)]
+    pdocs = [pooled[i * r:(i + 1) * r].astype(np.float32) for i in range(n)]
+    corpus.add_store("bq", rows, fixed_rows=t)
+    corpus.add_store("bqp", pooled, fixed_rows=r)
+    qs = [CS.query_rows(7400 + i, m) for i, m in enumerate((20, 260, 129, 7))]   # a batch mixing short and long queries
+    stages = [("bqp", False, 12), ("bq", False, 4)]
+    got = corpus.search_multistage_batch(stages, qs)
+    for q, g in zip(qs, got):
+        ref = MO.multistage(q, [(pdocs, False, 12), (docs, False, 4)])
+        assert g[1][1].tolist() == [i for i, _ in ref[1]]
+        close(g[1][0], [s for _, s in ref[1]])
+    q = qs[1]
+    close(corpus.saliency("bq", q, 3), MO.saliency_patch_scores(q, docs[3]), rtol=1e-5, atol=2e-6)
+    for nm in ("bq", "bqp"):
         corpus.drop_store(nm)

@@ -185,3 +185,59 @@ def test_infer_grid_mirror_matches_reference_goldens():
     import pytest
     with pytest.raises(ValueError):
         infer_grid(0, width=1, height=1)
+
+
+class _ArrayCorpus:
+    """Stand-in for GpuCorpus.search_multistage_batch(final_only=True): hands back prepared arrays and records the call."""
+
+    page_base = 100
+
+    def __init__(self, sc, ids, st, cnt):
+        self.arrays = (sc, ids, st, cnt)
+        self.calls = []
+
+    def search_multistage_batch(self, stages, queries, normalize=True, stage_queries=None, as_arrays=False, final_only=False):
+        self.calls.append((list(stages), queries, stage_queries, final_only))
+        return self.arrays
+
+
+def test_batched_retriever_results_from_columnar_client_lists():
+    """Host logic of the batched retriever calls: short rows, -inf padding, NaN stage scores -> None, external ids,
+    payload lookup, and the stage layout handed to the corpus (stage 1 pooled on the device, three_stage.py:96)."""
+    from visual_rag_b200.client import GpuCorpusClient
+
+    inf = np.float32(np.inf)
+    sc = np.array([[3.0, 2.0, 1.0], [5.0, -inf, -inf]], dtype=np.float32)
+    ids = np.array([[102, 100, 101], [101, -1, -1]], dtype=np.int64)
+    st = np.array([[[0.3, 0.6], [0.2, np.nan], [0.1, 0.4]], [[0.9, 0.8], [np.nan, np.nan], [np.nan, np.nan]]], dtype=np.float32)
+    cnt = np.array([3, 1], dtype=np.int32)
+    corpus = _ArrayCorpus(sc, ids, st, cnt)
+    client = GpuCorpusClient(corpus, "c", point_ids=["a", "b", "c"], payloads=[{"n": 0}, {"n": 1}, {"n": 2}])
+    three = ThreeStageRetriever(client, "c")
+    qs = [np.ones((4, 128), np.float32), np.ones((7, 128), np.float32)]
+    res = three.search_server_side_batch(query_embeddings=qs, top_k=3, stage1_k=50, stage2_k=20)
+    stages, queries, stage_queries, final_only = corpus.calls[-1]
+    assert stages == [("global_pooling", True, 50), ("experimental_pooling", False, 20), ("initial", False, 3)]
+    assert final_only and stage_queries is None and len(queries) == 2
+    assert [r["id"] for r in res[0]] == ["c", "a", "b"] and [r["id"] for r in res[1]] == ["b"]
+    assert res[0][1]["score_stage2"] is None and res[0][1]["score_stage1"] == pytest.approx(0.2)
+    assert res[0][0] == {"id": "c", "score_stage1": pytest.approx(0.3), "score_stage2": pytest.approx(0.6),
+                         "score_stage3": 3.0, "score_final": 3.0, "payload": {"n": 2}}
+    assert res[1][0]["payload"] == {"n": 1} and res[1][0]["score_final"] == 5.0
+
+    two = TwoStageRetriever(client, "c")
+    res2 = two.search_server_side_batch(qs, top_k=3, prefetch_k=40, stage1_mode="pooled_query_vs_global")
+    stages, _, _, _ = corpus.calls[-1]
+    assert stages == [("global_pooling", True, 40), ("initial", False, 3)]
+    assert res2[0][2] == {"id": "b", "score_stage1": None, "score_stage2": 1.0, "score_final": 1.0, "payload": {"n": 1}}
+    stages = two.search_server_side_batch(qs, top_k=3, stage1_mode="tokens_vs_tiles") and corpus.calls[-1][0]
+    assert stages == [("mean_pooling", False, 100), ("initial", False, 3)]
+
+    # default ids / no payloads, explicit per-stage query matrices
+    plain = GpuCorpusClient(corpus, "c")
+    cols = plain.query_multistage_batch_final(usings=["mean_pooling", "initial"], limits=[40, 3],
+                                              stage_queries=[[q.mean(axis=0), q] for q in qs], with_payload=False)
+    assert cols[0][0] == [102, 100, 101] and cols[0][3] == [None, None, None] and cols[1][1] == [5.0]
+    assert corpus.calls[-1][2] is not None and corpus.calls[-1][2][0][0].shape == (1, 128)
+    with pytest.raises(ValueError):
+        plain.query_multistage_batch_final(usings=["initial"], limits=[3])

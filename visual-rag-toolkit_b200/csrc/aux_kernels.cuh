@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(1024) sel_ties_kernel(const SelArgs a) {
 // CUDA-core kernel (~2.6 MFLOP per page).
 __global__ void __launch_bounds__(256) saliency_kernel(const __half* __restrict__ rows, const float* __restrict__ inv,
                                                        long long row0, int n_rows, const float* __restrict__ q, int Q,
-                                                       float* __restrict__ out) {
+                                                       float* __restrict__ out, int combine) {
   extern __shared__ float sq[];   // [Q][128] normalised query
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int r = warp; r < Q; r += 8) {
@@ -556,8 +556,15 @@ __global__ void __launch_bounds__(256) saliency_kernel(const __half* __restrict_
       for (int off = 16; off >= 1; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
       best = fmaxf(best, d * dn);
     }
-    if (lane == 0) out[t] = best;
+    if (lane == 0) out[t] = combine ? fmaxf(out[t], best) : best;   // combine: a later chunk of a long query
   }
+}
+
+// acc[i] += part[i]: MaxSim is a sum over query tokens, so a query longer than one operand image (128 rows) is scored
+// in row chunks whose partial page scores add up (-inf = "page not in this shard" stays -inf).
+__global__ void add_scores_kernel(float* __restrict__ acc, const float* __restrict__ part, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) acc[i] = __fadd_rn(acc[i], part[i]);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -153,6 +153,7 @@ struct vrag_corpus {
   cudaStream_t stream = nullptr;
   std::map<std::string, Store> stores;
   DevBuf<float> d_query, d_scores, d_out_scores;
+  DevBuf<float> d_scores_part;    // partial page scores of the later row chunks of a > 128-token query
   DevBuf<uint8_t> d_qimg;
   DevBuf<unsigned long long> d_keys_a, d_keys_b;
   DevBuf<uint8_t> d_sel_state;
@@ -182,6 +183,7 @@ struct vrag_corpus {
   bool attrs_set = false;
 };
 
+static const int kOperandRows = 128;    // query rows of one MMA operand image; longer token queries are scored in chunks
 static const int kMaxQueryRows = 1024;  // staging capacity for raw query tokens (pooled queries may be long)
 static const int kMaxStages = 8;
 
@@ -239,6 +241,7 @@ extern "C" int vrag_corpus_destroy(vrag_corpus_t* c) {
   c->d_query.release();
   c->d_scores.release();
   c->d_out_scores.release();
+  c->d_scores_part.release();
   c->d_qimg.release();
   c->d_keys_a.release();
   c->d_keys_b.release();
@@ -661,7 +664,27 @@ static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int
   if (n_query_rows < 1) return fail("query has no rows");
   if (n_query_rows > kMaxQueryRows) return fail("query has %d rows; at most %d supported", n_query_rows, kMaxQueryRows);
   const int q_eff = pool ? 1 : n_query_rows;
-  if (q_eff > 128) return fail("query has %d token rows; at most 128 supported per call", q_eff);
+  if (q_eff > kOperandRows) {
+    // longer than one operand image: score balanced row chunks and add the partial page scores (the sum over query
+    // tokens of compute_maxsim_score, pooling.py:509-512, split over chunks)
+    const int64_t n = d_cand ? n_cand : s.n_pages;
+    if (n == 0) return 0;
+    TRY(c->d_scores_part.ensure(n));
+    const int n_chunks = (q_eff + kOperandRows - 1) / kOperandRows;
+    int r0 = 0;
+    for (int i = 0; i < n_chunks; ++i) {
+      const int rows = (q_eff - r0 + (n_chunks - i) - 1) / (n_chunks - i);
+      float* dst = i == 0 ? d_scores : c->d_scores_part.p;
+      TRY(launch_scan(c, s, d_query + static_cast<size_t>(r0) * 128, rows, flags, d_cand, n_cand, dst, st, time_kernel && i == 0));
+      if (i > 0) {
+        add_scores_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(d_scores, c->d_scores_part.p, n);
+        c->launches++;
+      }
+      r0 += rows;
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   // operand width: the next power of two, except 17..24 token queries over LARGE pages, which get a 24-row operand
   // (MMA N = 48 instead of 64: a quarter less tensor work and TMEM traffic where the scan is power-limited)
   const int QP = q_eff <= 8 ? 8 : q_eff <= 16 ? 16 : (q_eff <= 24 && !s.packed) ? 24 : q_eff <= 32 ? 32 : q_eff <= 64 ? 64 : 128;
@@ -1109,10 +1132,6 @@ static int batch_upload(vrag_corpus* c, int n_stages, const uint32_t* flags, int
       if (r1 - r0 > kMaxQueryRows) return fail("query %d has %d rows; at most %d supported", b, r1 - r0, kMaxQueryRows);
       bc.max_rows[s] = std::max(bc.max_rows[s], r1 - r0);
     }
-  if (flags)
-    for (int s = 0; s < n_stages; ++s)
-      if (!(flags[s] & VRAG_Q_POOL) && bc.max_rows[s] > 128)
-        return fail("query has %d token rows; at most 128 supported per call", bc.max_rows[s]);
   // ---- stage queries and metadata to the device
   TRY(ensure_host_query(c, total_rows));
   TRY(c->d_query.ensure(static_cast<size_t>(total_rows) * 128));
@@ -1371,7 +1390,6 @@ extern "C" int vrag_batch_stage_dev(vrag_corpus_t* c, int stage, const char* nam
   if (raw && !cand_ids_dev) return fail("k == 0 (raw scores) needs candidate lists");
   if (!raw && (k < 1 || k > kTopkMaxK)) return fail("k=%d out of range [1,%d]", k, kTopkMaxK);
   if (!out_scores_dev || (!raw && !out_ids_dev)) return fail("NULL device pointer");
-  if (!(flags & VRAG_Q_POOL) && bc.max_rows[stage] > 128) return fail("query has %d token rows; at most 128 supported per call", bc.max_rows[stage]);
   cudaStream_t stm = static_cast<cudaStream_t>(stream);
   const bool dense = cand_ids_dev == nullptr;
   PrefilterPlan plan;
@@ -1433,7 +1451,7 @@ extern "C" int vrag_saliency(vrag_corpus_t* c, const char* name, const float* qu
   if (!out_rows) return fail("out_rows is NULL");
   const int64_t local = page_id - c->page_base;
   if (local < 0 || local >= s->n_pages) return fail("page id %lld is not in this shard", (long long)page_id);
-  if (n_query_rows < 1 || n_query_rows > 96) return fail("query rows %d out of range [1,96]", n_query_rows);
+  if (n_query_rows < 1 || n_query_rows > kMaxQueryRows) return fail("query rows %d out of range [1,%d]", n_query_rows, kMaxQueryRows);
   const int64_t r0 = s->fixed_rows > 0 ? local * s->fixed_rows : s->h_offsets[local];
   const int64_t n = s->fixed_rows > 0 ? s->fixed_rows : (s->h_offsets[local + 1] - s->h_offsets[local]);
   *out_rows = n;
@@ -1442,15 +1460,19 @@ extern "C" int vrag_saliency(vrag_corpus_t* c, const char* name, const float* qu
   if (!out_scores) return fail("out_scores is NULL");
   TRY(stage_query(c, query, n_query_rows));
   TRY(c->d_scores.ensure(n));
-  const size_t smem = static_cast<size_t>(n_query_rows) * 512;
+  const int kSalRows = 96;   // query rows held in shared memory per launch; longer queries max-combine over chunks
   static bool attr_done = false;
   if (!attr_done) {
-    CUDA_OK(cudaFuncSetAttribute(saliency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 512));
+    CUDA_OK(cudaFuncSetAttribute(saliency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSalRows * 512));
     attr_done = true;
   }
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>((n + 7) / 8, c->num_sms * 4));
-  saliency_kernel<<<grid, 256, smem, c->stream>>>(s->rows, s->inv, r0, static_cast<int>(n), c->d_query.p, n_query_rows, c->d_scores.p);
-  c->launches++;
+  for (int q0 = 0; q0 < n_query_rows; q0 += kSalRows) {
+    const int rows = std::min(kSalRows, n_query_rows - q0);
+    saliency_kernel<<<grid, 256, static_cast<size_t>(rows) * 512, c->stream>>>(
+        s->rows, s->inv, r0, static_cast<int>(n), c->d_query.p + static_cast<size_t>(q0) * 128, rows, c->d_scores.p, q0 > 0 ? 1 : 0);
+    c->launches++;
+  }
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpyAsync(out_scores, c->d_scores.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));

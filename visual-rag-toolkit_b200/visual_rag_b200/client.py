@@ -70,6 +70,8 @@ class GpuCorpusClient:
     QdrantIndexer.generate_point_id, qdrant_indexer.py:602-613). Defaults to the global page index.
     """
 
+    accepts_numpy = True   # queries may arrive as fp32 numpy arrays (no list round trip), see retrieval/_common.py::wire
+
     def __init__(self, corpus: GpuCorpus, collection_name: str = "gpu", point_ids: Optional[Sequence[Any]] = None,
                  payloads: Optional[Sequence[Optional[dict]]] = None):
         self.corpus = corpus
@@ -278,28 +280,63 @@ class GpuCorpusClient:
         return out
 
     def query_multistage_batch_final(self, *, usings: Sequence[str], limits: Sequence[int],
-                                     stage_queries: Sequence[Sequence[Any]], with_payload: bool = True):
-        """`query_multistage_batch` with compact results: per query a list of (ScoredPoint of the LAST stage, [score of
-        that page in stage 0, stage 1, ...]) — the long intermediate lists stay on the device."""
+                                     stage_queries: Optional[Sequence[Sequence[Any]]] = None,
+                                     queries: Optional[Sequence[Any]] = None,
+                                     pool_flags: Optional[Sequence[bool]] = None, with_payload: bool = True):
+        """`query_multistage_batch` with compact, columnar results: per query four parallel lists
+        `(ids, scores, stage_scores, payloads)` for the points of the LAST stage — `stage_scores[s][j]` is the score
+        point j had in stage s < last (None where absent). The long intermediate lists stay on the device and
+        no per-point Python object is built here (a retriever turns the columns into its result dicts with one zip).
+        Either `stage_queries[b][s]` (what the reference would send as `query=` of stage s for query b) or
+        `queries[b]` (the token matrix) plus `pool_flags[s]` (stage s scans with the mean-pooled query,
+        two_stage.py:142 / three_stage.py:96, pooled on the device) describes the batch."""
         ns = len(usings)
-        sq = [[self._as_query(x) for x in per_query] for per_query in stage_queries]
-        sc, ids, st, cnt = self.corpus.search_multistage_batch(
-            [(usings[s], False, int(limits[s])) for s in range(ns)], None, stage_queries=sq, final_only=True)
-        # plain Python lists once (numpy scalar access per element would dominate the whole call)
-        sc_l, ids_l, st_l, cnt_l = sc.tolist(), ids.tolist(), st.tolist(), cnt.tolist()
-        inf = float("inf")
+        if len(limits) != ns:
+            raise ValueError("usings and limits must have the same length")
+        if stage_queries is not None:
+            sq = [[self._as_query(x) for x in per_query] for per_query in stage_queries]
+            sc, ids, st, cnt = self.corpus.search_multistage_batch(
+                [(usings[s], False, int(limits[s])) for s in range(ns)], None, stage_queries=sq, final_only=True)
+        else:
+            if queries is None:
+                raise ValueError("either stage_queries or queries is required")
+            pf = [False] * ns if pool_flags is None else [bool(x) for x in pool_flags]
+            if len(pf) != ns:
+                raise ValueError("pool_flags must have one entry per stage")
+            sc, ids, st, cnt = self.corpus.search_multistage_batch(
+                [(usings[s], pf[s], int(limits[s])) for s in range(ns)], queries, final_only=True)
+        nq, kl = sc.shape
+        valid = np.isfinite(sc) & (np.arange(kl, dtype=np.int64)[None, :] < np.asarray(cnt, dtype=np.int64)[:, None])
+        row_full = valid.all(axis=1).tolist()
+        # plain Python lists once (numpy scalar access per element would dominate the whole call); stage scores as one
+        # column per stage
+        st_cols = []
+        for s_i in range(ns - 1):
+            col = st[:, :, s_i]
+            if np.isnan(col).any():
+                col_o = col.astype(object)
+                col_o[np.isnan(col)] = None
+                st_cols.append(col_o.tolist())
+            else:
+                st_cols.append(col.tolist())
+        sc_l, ids_l = sc.tolist(), ids.tolist()
+        base, ext, pls = self.corpus.page_base, self._ids, self._payloads
         out = []
-        for b in range(len(sc_l)):
-            row = []
-            srow, irow, trow = sc_l[b], ids_l[b], st_l[b]
-            for j in range(cnt_l[b]):
-                s = srow[j]
-                if s != s or s == inf or s == -inf:
-                    continue
-                page = irow[j]
-                row.append((ScoredPoint(self._pid(page), s, self._payload(page) if with_payload else None),
-                            [None if x != x else x for x in trow[j]]))
-            out.append(row)
+        for b in range(nq):
+            pages, scores, stages = ids_l[b], sc_l[b], [col[b] for col in st_cols]
+            if not row_full[b]:
+                keep = np.nonzero(valid[b])[0].tolist()
+                pages = [pages[j] for j in keep]
+                scores = [scores[j] for j in keep]
+                stages = [[col[j] for j in keep] for col in stages]
+            pids = pages if ext is None else [ext[p - base] for p in pages]
+            if not with_payload:
+                payloads = [None] * len(pages)
+            elif pls is None:
+                payloads = [{} for _ in pages]
+            else:
+                payloads = [pls[p - base] for p in pages]
+            out.append((pids, scores, stages, payloads))
         return out
 
     def retrieve(self, collection_name=None, ids=(), with_payload=False, with_vectors=None, timeout=None, **_ignored):

@@ -22,13 +22,17 @@ DIM = 128
 def _as_f32_query(query) -> np.ndarray:
     """Query -> contiguous fp32 [Q,128] numpy (same conversions as TwoStageRetriever._to_numpy,
     visual_rag/retrieval/two_stage.py:428-434)."""
-    try:
-        import torch
+    if isinstance(query, np.ndarray):
+        if query.dtype == np.float32 and query.ndim == 2 and query.shape[1] == DIM and query.flags.c_contiguous:
+            return query    # already in the native layout: borrowed for the duration of the call, never written
+    elif not isinstance(query, (list, tuple)):
+        try:
+            import torch
 
-        if isinstance(query, torch.Tensor):
-            query = query.detach().cpu().float().numpy()
-    except ImportError:  # pragma: no cover
-        pass
+            if isinstance(query, torch.Tensor):
+                query = query.detach().cpu().float().numpy()
+        except ImportError:  # pragma: no cover
+            pass
     q = np.array(query, dtype=np.float32)
     if q.ndim == 1:
         q = q[None, :]

@@ -62,6 +62,9 @@ class ShardedSearcher:
         """Host query -> device (pinned staging, async H2D on the current stream). Returns the row count."""
         q = _as_f32_query(query)
         n = q.shape[0]
+        if n > self._q_pin.shape[0]:   # long queries (> 128 tokens are scored in row chunks by the library)
+            self._q_dev = torch.empty((n, 128), dtype=torch.float32, device=self.device)
+            self._q_pin = torch.empty((n, 128), dtype=torch.float32, pin_memory=self._q_pin.is_pinned())
         self._q_pin[:n].copy_(torch.from_numpy(q))
         self._q_dev[:n].copy_(self._q_pin[:n], non_blocking=True)
         return n

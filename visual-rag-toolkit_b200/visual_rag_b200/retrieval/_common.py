@@ -2,6 +2,8 @@
 
 from __future__ import annotations
 
+import contextlib
+import gc
 import time
 from typing import Tuple
 
@@ -26,6 +28,27 @@ def to_numpy(embedding) -> np.ndarray:
     except ImportError:  # pragma: no cover
         pass
     return np.array(embedding, dtype=np.float32)
+
+
+@contextlib.contextmanager
+def no_gc():
+    """Pause the cyclic garbage collector while a batch of result dictionaries is built: tens of thousands of new
+    (acyclic) containers otherwise trigger full collections that walk every object of the process — measured 40 ms of
+    a 57 ms batched three-stage call (256 queries x 100 results) against 3.3 ms on the device."""
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
+
+
+def wire(client, array: np.ndarray):
+    """A query as it travels to the client: the reference serialises to nested lists for Qdrant's JSON/gRPC wire
+    (two_stage.py:142-159); an in-process client that declares `accepts_numpy` gets the fp32 array itself (a
+    20 x 128 `.tolist()` + re-parse costs ~0.1 ms per call, a tenth of a two-stage search on the GPU store)."""
+    return array if getattr(client, "accepts_numpy", False) else array.tolist()
 
 
 def resolve_stage1(stage1_mode: str, pooled_name: str, experimental_name: str, global_name: str) -> Tuple[bool, str]:

@@ -8,7 +8,7 @@ from typing import Any, Dict, List
 
 import numpy as np
 
-from ._common import to_numpy
+from ._common import to_numpy, wire
 
 logger = logging.getLogger(__name__)
 
@@ -49,7 +49,7 @@ class SingleStageRetriever:
         if strategy not in table:
             raise ValueError(f"Unknown strategy: {strategy}")
         vector_name, pool = table[strategy]
-        query_vector = query_np.mean(axis=0).tolist() if pool else query_np.tolist()
+        query_vector = wire(self.client, query_np.mean(axis=0)) if pool else wire(self.client, query_np)
         results = self.client.query_points(
             collection_name=self.collection_name, query=query_vector, using=vector_name, query_filter=filter_obj,
             limit=top_k, with_payload=True, with_vectors=False, timeout=self.request_timeout,

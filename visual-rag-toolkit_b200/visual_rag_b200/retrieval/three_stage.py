@@ -9,7 +9,7 @@ from typing import Any, Dict, List, Optional
 import numpy as np
 
 from . import models as m
-from ._common import retry_call, to_numpy
+from ._common import no_gc, retry_call, to_numpy, wire
 
 logger = logging.getLogger(__name__)
 
@@ -64,8 +64,8 @@ class ThreeStageRetriever:
         stage1_k = 1000 if stage1_k is None else int(stage1_k)
         stage2_k = 300 if stage2_k is None else int(stage2_k)
         query_np = self._to_numpy(query_embedding)
-        stage1_query = query_np.mean(axis=0).tolist()
-        tokens = query_np.tolist()
+        stage1_query = wire(self.client, query_np.mean(axis=0))
+        tokens = wire(self.client, query_np)
 
         fused = getattr(self.client, "query_three_stage", None)
         if fused is not None:
@@ -131,16 +131,19 @@ class ThreeStageRetriever:
         stage1_k = 1000 if stage1_k is None else int(stage1_k)
         stage2_k = 300 if stage2_k is None else int(stage2_k)
         qs = [self._to_numpy(q) for q in query_embeddings]
-        sq = [[q.mean(axis=0, keepdims=True), q, q] for q in qs]
-        res = self._retry_call(lambda: batch(
-            usings=[self.global_vector_name, self.experimental_vector_name, self.full_vector_name],
-            limits=[stage1_k, stage2_k, int(top_k)], stage_queries=sq))
-        # compact results: the final points plus their stage-1 / stage-2 scores (looked up on the device)
-        return [[{
-            "id": p.id,
-            "score_stage1": st[0],
-            "score_stage2": st[1],
-            "score_stage3": float(p.score),
-            "score_final": float(p.score),
-            "payload": p.payload,
-        } for p, st in per_query] for per_query in res]
+        # stage 1 scans with the mean-pooled query (three_stage.py:96), pooled on the device from the same token rows
+        with no_gc():
+            res = self._retry_call(lambda: batch(
+                usings=[self.global_vector_name, self.experimental_vector_name, self.full_vector_name],
+                limits=[stage1_k, stage2_k, int(top_k)], queries=qs, pool_flags=[True, False, False]))
+        # compact columnar results: the final points plus their stage-1 / stage-2 scores (looked up on the device)
+        with no_gc():
+            return [[{
+                "id": pid,
+                "score_stage1": s1,
+                "score_stage2": s2,
+                "score_stage3": score,
+                "score_final": score,
+                "payload": payload,
+            } for pid, score, s1, s2, payload in zip(ids, scores, stage_scores[0], stage_scores[1], payloads)]
+                for ids, scores, stage_scores, payloads in res]

@@ -15,7 +15,7 @@ from typing import Any, Dict, List, Optional, Union
 import numpy as np
 
 from . import models as qdrant_models
-from ._common import resolve_stage1, retry_call, to_numpy
+from ._common import no_gc, resolve_stage1, retry_call, to_numpy, wire
 from .models import FieldCondition, Filter, HasIdCondition, MatchAny, MatchValue
 
 logger = logging.getLogger(__name__)
@@ -53,7 +53,7 @@ class TwoStageRetriever:
     def _stage1_query(self, query_np: np.ndarray, stage1_mode: str):
         pool, name = resolve_stage1(stage1_mode, self.pooled_vector_name, self.experimental_vector_name,
                                     self.global_vector_name)
-        vec = query_np.mean(axis=0).tolist() if pool else query_np.tolist()   # two_stage.py:142-155
+        vec = wire(self.client, query_np.mean(axis=0)) if pool else wire(self.client, query_np)   # two_stage.py:142-155
         return vec, name
 
     # ------------------------------------------------------------------ server-side (fused on the GPU)
@@ -70,7 +70,7 @@ class TwoStageRetriever:
         if prefetch_k is None:
             prefetch_k = max(100, top_k * 10)
         prefetch_query, prefetch_using = self._stage1_query(query_np, stage1_mode)
-        rerank_query = query_np.tolist()
+        rerank_query = wire(self.client, query_np)
 
         def _do_query():
             return self.client.query_points(
@@ -110,11 +110,11 @@ class TwoStageRetriever:
         pool, prefetch_using = resolve_stage1(stage1_mode, self.pooled_vector_name, self.experimental_vector_name,
                                               self.global_vector_name)
         qs = [self._to_numpy(q) for q in query_embeddings]
-        sq = [[q.mean(axis=0, keepdims=True) if pool else q, q] for q in qs]
-        res = self._retry_call(lambda: batch(usings=[prefetch_using, self.full_vector_name],
-                                             limits=[int(prefetch_k), int(top_k)], stage_queries=sq))
-        return [[{"id": r.id, "score_stage1": None, "score_stage2": r.score, "score_final": r.score, "payload": r.payload}
-                 for r, _ in per_query] for per_query in res]
+        with no_gc():
+            res = self._retry_call(lambda: batch(usings=[prefetch_using, self.full_vector_name],
+                                                 limits=[int(prefetch_k), int(top_k)], queries=qs, pool_flags=[pool, False]))
+            return [[{"id": pid, "score_stage1": None, "score_stage2": score, "score_final": score, "payload": payload}
+                     for pid, score, payload in zip(per_query[0], per_query[1], per_query[3])] for per_query in res]
 
     # ------------------------------------------------------------------ client-side flow
     def search(
@@ -152,10 +152,10 @@ class TwoStageRetriever:
         query_np = self._to_numpy(query_embedding)
         if use_pooling:
             vector_name = self.pooled_vector_name
-            query_vector = query_np.mean(axis=0).tolist()
+            query_vector = wire(self.client, query_np.mean(axis=0))
         else:
             vector_name = self.full_vector_name
-            query_vector = query_np.tolist()
+            query_vector = wire(self.client, query_np)
         results = self.client.query_points(
             collection_name=self.collection_name, query=query_vector, using=vector_name, query_filter=filter_obj,
             limit=top_k, with_payload=True, with_vectors=False, timeout=120,
@@ -187,7 +187,7 @@ class TwoStageRetriever:
 
         def _do_rerank():
             return self.client.query_points(
-                collection_name=self.collection_name, query=query_np.tolist(), using=self.full_vector_name,
+                collection_name=self.collection_name, query=wire(self.client, query_np), using=self.full_vector_name,
                 query_filter=Filter(must=[HasIdCondition(has_id=candidate_ids)]), limit=len(candidate_ids),
                 with_payload=False, with_vectors=False, search_params=qdrant_models.SearchParams(exact=True),
                 timeout=self.request_timeout,
