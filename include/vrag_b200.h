@@ -64,6 +64,14 @@ int vrag_store_add(vrag_corpus_t* c, const char* name, const void* rows, int dty
 int vrag_store_append(vrag_corpus_t* c, const char* name, const void* rows, int dtype, int rows_on_device,
                       const int64_t* page_offsets, int64_t n_pages, int64_t fixed_rows);
 
+/* Overwrite existing pages in place — the "upsert of a point that already exists" half of QdrantIndexer.upload_batch
+ * (client.upsert, visual_rag/indexing/qdrant_indexer.py:459-507; ids are deterministic, 602-613, so re-indexing a document
+ * re-sends the same ids). local_pages[n_pages]: shard-local page indices; rows / page_offsets describe the new pages
+ * back to back as in vrag_store_append. Every new page must have exactly the row count of the page it replaces (the shard
+ * layout is dense; a page whose shape changed needs a rebuilt store) — otherwise nothing is written and the call fails. */
+int vrag_store_replace_pages(vrag_corpus_t* c, const char* name, const int64_t* local_pages, int64_t n_pages,
+                             const void* rows, int dtype, int rows_on_device, const int64_t* page_offsets, int64_t fixed_rows);
+
 /* Fill a named store with the seeded synthetic corpus of SURVEY.md 8(d) directly on the device
  * (gaussian rows, L2-normalised, rounded to fp16).  Row r of the store depends only on (seed, row_seed_base + r). */
 int vrag_store_add_synthetic(vrag_corpus_t* c, const char* name, const int64_t* page_offsets, int64_t n_pages,

@@ -567,8 +567,7 @@ def test_indexer_upload_batches_equals_bulk_store():
         for lo, hi in ((0, 1), (1, 20), (20, 21), (21, 57)):
             up += idx.upload_batch(pts[lo:hi])
         assert up == n and idx.check_exists(pts[5]["id"]) and not idx.check_exists("nope")
-        with pytest.raises(ValueError):
-            idx.upload_batch(pts[:1])
+        assert idx.upload_batch(pts[:1]) == 1     # re-sending an existing id is an (idempotent) in-place upsert
         # bulk twin
         def cat(key, f=lambda p: p):
             mats = [np.asarray(f(p), np.float32).reshape(-1, 128) for p in pts]
@@ -770,3 +769,70 @@ def test_long_queries_in_batches_and_saliency(corpus):
     close(corpus.saliency("bq", q, 3), MO.saliency_patch_scores(q, docs[3]), rtol=1e-5, atol=2e-6)
     for nm in ("bq", "bqp"):
         corpus.drop_store(nm)
+
+
+@pytest.mark.gpu
+def test_indexer_upsert_replaces_pages_in_place():
+    """client.upsert semantics of QdrantIndexer.upload_batch (qdrant_indexer.py:459-507): a batch mixing ids that exist
+    (same shapes, new vectors and payload) with new ids == a bulk store of the final state; a point whose shape changed is
+    refused before anything is written."""
+    from visual_rag_b200.client import GpuCorpusClient
+    from visual_rag_b200.corpus import GpuCorpus
+    from visual_rag_b200.indexing import GpuIndexer
+    from visual_rag_b200.retrieval import TwoStageRetriever
+
+    rng = np.random.default_rng(33)
+
+    def point(i, t, r, ver):
+        g = np.random.default_rng(1000 * ver + i)
+        return {"id": GpuIndexer.generate_point_id("d.pdf", i), "visual_embedding": g.standard_normal((t, 128)).astype(np.float32),
+                "tile_pooled_embedding": g.standard_normal((r, 128)).astype(np.float32),
+                "experimental_pooled_embedding": g.standard_normal((r + 2, 128)).astype(np.float32),
+                "metadata": {"filename": "d.pdf", "page_number": i, "version": ver}}
+
+    shapes = [(int(rng.integers(130, 300)), int(rng.integers(8, 33))) for _ in range(30)]
+    v1 = [point(i, *shapes[i], 1) for i in range(20)]
+    with GpuCorpus(0) as c1, GpuCorpus(0) as c2:
+        idx = GpuIndexer(c1, "c")
+        idx.create_collection(force_recreate=True)
+        assert idx.upload_batch(v1) == 20
+        q = rng.standard_normal((21, 128)).astype(np.float32)
+        two = TwoStageRetriever(idx.client, "c")
+        two.search_server_side(q, top_k=5, prefetch_k=12)          # builds page tables / tensor maps before the upsert
+        changed = [3, 0, 19, 7]
+        batch = [point(i, *shapes[i], 2) for i in changed] + [point(i, *shapes[i], 2) for i in range(20, 30)]
+        batch.insert(2, point(7, *shapes[7], 3))                   # duplicate id inside the batch: the last occurrence wins
+        assert idx.upload_batch(batch) == len(batch)
+        final = {p["id"]: p for p in v1}
+        order = [p["id"] for p in v1]
+        for p in batch:
+            if p["id"] not in final:
+                order.append(p["id"])
+            final[p["id"]] = p
+        assert final[GpuIndexer.generate_point_id("d.pdf", 7)]["metadata"]["version"] == 2
+        pts = [final[i] for i in order]
+        for name, f in (("initial", lambda p: p["visual_embedding"]), ("mean_pooling", lambda p: p["tile_pooled_embedding"]),
+                        ("experimental_pooling", lambda p: p["experimental_pooled_embedding"]),
+                        ("global_pooling", lambda p: p["tile_pooled_embedding"].mean(axis=0))):
+            mats = [np.asarray(f(p), np.float32).reshape(-1, 128) for p in pts]
+            rows = np.concatenate(mats).astype(np.float16)
+            c2.add_store(name, rows, page_offsets=np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])]))
+            assert np.array_equal(c1.read_rows(name, 0, rows.shape[0]).view(np.uint16), rows.view(np.uint16)), name
+        client2 = GpuCorpusClient(c2, "c", point_ids=order, payloads=[p["metadata"] for p in pts])
+        for mode in ("tokens_vs_standard_pooling", "pooled_query_vs_global", "tokens_vs_experimental_pooling"):
+            a = two.search_server_side(q, top_k=8, prefetch_k=15, stage1_mode=mode)
+            b = TwoStageRetriever(client2, "c").search_server_side(q, top_k=8, prefetch_k=15, stage1_mode=mode)
+            assert [(r["id"], r["score_final"], r["payload"]) for r in a] == [(r["id"], r["score_final"], r["payload"]) for r in b]
+        assert {r["payload"]["version"] for r in two.search_server_side(q, top_k=30, prefetch_k=30)} == {1, 2}
+        # a point whose token count changed cannot be replaced in place: refused, collection untouched
+        before = c1.read_rows("initial", 0, 50).copy()
+        bad = [point(31, 150, 9, 4), point(3, shapes[3][0] + 1, shapes[3][1], 4)]
+        with pytest.raises(ValueError, match="equal shapes"):
+            idx.upload_batch(bad)
+        assert not idx.check_exists(bad[0]["id"]) and c1.n_pages("initial") == 30
+        assert np.array_equal(c1.read_rows("initial", 0, 50), before)
+        from visual_rag_b200._native import VragError
+        with pytest.raises(VragError, match="equal shapes"):
+            c1.replace_pages("initial", [0], np.zeros((3, 128), np.float16), [0, 3])
+        with pytest.raises(VragError, match="out of range"):
+            c1.replace_pages("initial", [99], np.zeros((3, 128), np.float16), [0, 3])

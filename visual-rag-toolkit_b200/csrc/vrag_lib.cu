@@ -502,6 +502,44 @@ extern "C" int vrag_store_append(vrag_corpus_t* c, const char* name, const void*
   return 0;
 }
 
+extern "C" int vrag_store_replace_pages(vrag_corpus_t* c, const char* name, const int64_t* local_pages, int64_t n_pages,
+                                        const void* rows, int dtype, int rows_on_device, const int64_t* page_offsets,
+                                        int64_t fixed_rows) {
+  if (!c) return fail("corpus is NULL");
+  if (!name || !*name) return fail("store name is empty");
+  auto it = c->stores.find(name);
+  if (it == c->stores.end()) return fail("unknown vector store '%s'", name);
+  TRY(set_device(c));
+  if (dtype != VRAG_F16 && dtype != VRAG_F32) return fail("unknown dtype %d", dtype);
+  int64_t new_rows = 0;
+  TRY(check_layout(page_offsets, n_pages, fixed_rows, &new_rows));
+  if (n_pages == 0) return 0;
+  if (!local_pages) return fail("local_pages is NULL");
+  if (new_rows > 0 && !rows) return fail("rows is NULL");
+  Store& s = it->second;
+  // validate everything first: either all pages are replaced or none
+  for (int64_t i = 0; i < n_pages; ++i) {
+    const int64_t pg = local_pages[i];
+    if (pg < 0 || pg >= s.n_pages) return fail("page %lld out of range (store '%s' has %lld pages)", (long long)pg, name, (long long)s.n_pages);
+    const int64_t have = s.fixed_rows > 0 ? s.fixed_rows : (s.h_offsets[pg + 1] - s.h_offsets[pg]);
+    const int64_t got = fixed_rows > 0 ? fixed_rows : (page_offsets[i + 1] - page_offsets[i]);
+    if (have != got)
+      return fail("page %lld of store '%s' has %lld rows, its replacement has %lld: in-place replacement needs equal shapes",
+                  (long long)pg, name, (long long)have, (long long)got);
+  }
+  const size_t el = dtype == VRAG_F16 ? sizeof(__half) : sizeof(float);
+  for (int64_t i = 0; i < n_pages; ++i) {
+    const int64_t pg = local_pages[i];
+    const int64_t r0 = s.fixed_rows > 0 ? pg * s.fixed_rows : s.h_offsets[pg];
+    const int64_t src0 = fixed_rows > 0 ? i * fixed_rows : page_offsets[i];
+    const int64_t nr = fixed_rows > 0 ? fixed_rows : (page_offsets[i + 1] - page_offsets[i]);
+    if (nr == 0) continue;
+    TRY(upload_rows(c, s.rows + static_cast<size_t>(r0) * 128, s.inv + r0,
+                    static_cast<const char*>(rows) + static_cast<size_t>(src0) * 128 * el, dtype, rows_on_device, nr));
+  }
+  return 0;   // row counts are unchanged: page tables, tile packing and tensor maps stay valid
+}
+
 extern "C" int vrag_store_add_synthetic(vrag_corpus_t* c, const char* name, const int64_t* page_offsets,
                                         int64_t n_pages, int64_t fixed_rows, uint64_t seed, int64_t row_seed_base) {
   if (!c) return fail("corpus is NULL");

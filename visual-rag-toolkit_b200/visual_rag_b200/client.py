@@ -92,6 +92,31 @@ class GpuCorpusClient:
         self._columns = {}
         self._filter_cache = {}
 
+    def append_points(self, point_ids: Sequence[Any], payloads: Optional[Sequence[Optional[dict]]] = None) -> None:
+        """Register the pages a batch upload appended (incremental: O(batch), not O(collection))."""
+        if self._ids is None:
+            self._ids, self._index = [], {}
+        if self._payloads is None:
+            self._payloads = [None] * len(self._ids)
+        n0 = len(self._ids)
+        self._ids.extend(point_ids)
+        for i, pid in enumerate(point_ids):
+            self._index[pid] = n0 + i
+        self._payloads.extend(payloads if payloads is not None else [None] * len(point_ids))
+        self._columns = {}
+        self._filter_cache = {}
+
+    def set_payload(self, point_id, payload: Optional[dict]) -> None:
+        """Replace the payload of an existing point (upsert of an id that is already in the collection)."""
+        page = self._page(point_id)
+        if page < 0:
+            raise KeyError(point_id)
+        if self._payloads is None:
+            self._payloads = [None] * len(self._ids)
+        self._payloads[page - self.corpus.page_base] = payload
+        self._columns = {}
+        self._filter_cache = {}
+
     def _pid(self, page: int):
         local = page - self.corpus.page_base
         return self._ids[local] if self._ids is not None else page

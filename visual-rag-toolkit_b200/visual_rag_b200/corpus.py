@@ -186,6 +186,23 @@ class GpuCorpus:
         N.check(self._lib.vrag_store_append(self._h, name.encode(), arr.ctypes.data_as(C.c_void_p), dtype, 0, off_p,
                                             int(n_pages), int(fixed_rows)))
 
+    def replace_pages(self, name: str, local_pages: Sequence[int], rows, page_offsets: Sequence[int]) -> None:
+        """Overwrite existing pages of `name` in place (the upsert of points that already exist,
+        qdrant_indexer.py:459-507). Every replacement must have the row count of the page it replaces; otherwise the
+        library refuses and nothing is written."""
+        arr = np.asarray(rows)
+        if arr.dtype not in (np.float16, np.float32):
+            arr = arr.astype(np.float32)
+        arr = np.ascontiguousarray(arr.reshape(-1, DIM))
+        dtype = N.VRAG_F16 if arr.dtype == np.float16 else N.VRAG_F32
+        pages = np.ascontiguousarray(np.asarray(local_pages, dtype=np.int64))
+        off = np.ascontiguousarray(np.asarray(page_offsets, dtype=np.int64))
+        if off.ndim != 1 or off.size != pages.size + 1 or int(off[-1]) != arr.shape[0]:
+            raise ValueError("page_offsets must be len(local_pages)+1 row offsets ending at the number of rows")
+        N.check(self._lib.vrag_store_replace_pages(self._h, name.encode(), pages.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                   int(pages.size), arr.ctypes.data_as(C.c_void_p), dtype, 0,
+                                                   off.ctypes.data_as(C.POINTER(C.c_int64)), 0))
+
     def add_synthetic_store(
         self,
         name: str,

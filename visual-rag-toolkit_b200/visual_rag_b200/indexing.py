@@ -6,7 +6,8 @@ visual_rag/indexing/qdrant_indexer.py::QdrantIndexer that the processing pipelin
 `tile_pooled_embedding`, `experimental_pooled_embedding` (array or {name: array}), `global_pooled_embedding`
 (optional) and `metadata`; this class appends them to the named stores of a GpuCorpus with the same store-dtype
 cast (every array -> fp32 -> fp16, 423-441) and the same fallback global = mean(tile_pooled) (417-421), and
-registers id / payload with the GpuCorpusClient so the retrievers can serve the pages immediately.
+registers id / payload with the GpuCorpusClient so the retrievers can serve the pages immediately. Ids that already
+exist are overwritten in place (upsert), as long as the point keeps its shape.
 """
 
 from __future__ import annotations
@@ -83,20 +84,19 @@ class GpuIndexer:
 
     def upload_batch(self, points: List[Dict[str, Any]], max_retries: int = 3, delay_between_batches: float = 0.0,
                      wait: bool = True, stop_event=None) -> int:
-        """qdrant_indexer.py:341-507. Returns the number of uploaded points. Points whose id already exists are
-        rejected with ValueError (an upsert would need an in-place page replacement, which the append-only shard
-        layout does not offer; use create_collection(force_recreate=True) to rebuild)."""
+        """qdrant_indexer.py:341-507 (client.upsert semantics). Returns the number of uploaded points. New ids are
+        appended behind the existing pages; an id that is already in the collection is overwritten IN PLACE (vectors of
+        every named store + payload), which needs every vector of the point to keep its row count — the dense shard
+        layout cannot grow a page in the middle, so a point whose shape changed raises ValueError (nothing is written;
+        rebuild with create_collection(force_recreate=True)). Within one batch the last occurrence of an id wins."""
         if not points:
             return 0
         if stop_event is not None and getattr(stop_event, "is_set", lambda: False)():
             return 0
-        stores: Dict[str, List[np.ndarray]] = {}
-        ids, payloads = [], []
-        seen = set()
+        # ---- every point -> its named vectors (fp32 first, 423-441); the last occurrence of an id wins
+        per_id: Dict[Any, Dict[str, np.ndarray]] = {}
+        payload_of: Dict[Any, Any] = {}
         for p in points:
-            if self.check_exists(p["id"]) or p["id"] in seen:
-                raise ValueError(f"point id {p['id']!r} is already in the collection")
-            seen.add(p["id"])
             tile = self._rows(p["tile_pooled_embedding"])
             glob = p.get("global_pooled_embedding")
             if glob is None:
@@ -110,24 +110,43 @@ class GpuIndexer:
                         per_point[str(k)] = self._rows(v)
             elif exp is not None:
                 per_point["experimental_pooling"] = self._rows(exp)
-            for k, v in per_point.items():
-                stores.setdefault(k, []).append(v)
-            ids.append(p["id"])
-            payloads.append(p.get("metadata"))
-        n = len(points)
+            per_id.pop(p["id"], None)            # re-insert so that dict order = order of the last occurrences
+            per_id[p["id"]] = per_point
+            payload_of[p["id"]] = p.get("metadata")
+        new_ids = [i for i in per_id if not self.check_exists(i)]
+        old_ids = [i for i in per_id if self.check_exists(i)]
         n_before = len(self.client._ids)
-        for name, mats in stores.items():
-            if len(mats) != n:
+        names = sorted({k for v in per_id.values() for k in v})
+        # ---- validate before anything is written
+        for name in names:
+            missing = [i for i in per_id if name not in per_id[i]]
+            if missing:
                 raise ValueError(f"named vector '{name}' is missing from some points of the batch")
-            if self.corpus.has_store(name):
-                have = self.corpus.n_pages(name)
-            else:
-                have = 0
+            have = self.corpus.n_pages(name) if self.corpus.has_store(name) else 0
             if have != n_before:
                 raise ValueError(f"named vector '{name}' holds {have} pages but the collection has {n_before} points")
-        for name, mats in stores.items():
-            off = np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])]).astype(np.int64)
-            rows = np.concatenate(mats, axis=0).astype(np.float16)           # store dtype cast
-            self.corpus.append_store(name, rows, page_offsets=off)
-        self.client.set_points(list(self.client._ids) + ids, list(self.client._payloads or []) + payloads)
-        return n
+        base = self.corpus.page_base
+        old_pages = [self.client._page(i) - base for i in old_ids]
+        for name in names:
+            for i, pg in zip(old_ids, old_pages):
+                have_rows = self.corpus.page_range(name, pg)[1]
+                got_rows = per_id[i][name].shape[0]
+                if have_rows != got_rows:
+                    raise ValueError(f"point id {i!r}: named vector '{name}' has {have_rows} rows in the collection, the "
+                                     f"upserted point has {got_rows}; in-place replacement needs equal shapes")
+        # ---- write: replacements in place, new points appended
+        for name in names:
+            if old_ids:
+                mats = [per_id[i][name] for i in old_ids]
+                off = np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])]).astype(np.int64)
+                self.corpus.replace_pages(name, old_pages, np.concatenate(mats, axis=0).astype(np.float16), off)
+            if new_ids:
+                mats = [per_id[i][name] for i in new_ids]
+                off = np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])]).astype(np.int64)
+                rows = np.concatenate(mats, axis=0).astype(np.float16)           # store dtype cast
+                self.corpus.append_store(name, rows, page_offsets=off)
+        for i in old_ids:
+            self.client.set_payload(i, payload_of[i])
+        if new_ids:
+            self.client.append_points(new_ids, [payload_of[i] for i in new_ids])
+        return len(points)
