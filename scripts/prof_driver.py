@@ -59,6 +59,21 @@ elif what == "colsmol13":
     for _ in range(reps):
         c.search("mean_pooling", q20, 256)
     print("colsmol13", n, c.last_timing_ms())
+elif what == "cfg2":
+    # BASELINE configs[2]: the batched three-stage search (launch list: which kernels make up the 3.2 ms)
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+    h = rng.integers(16, 33, size=n)
+    w = np.minimum(rng.integers(16, 33, size=n), 768 // h)
+    off = np.concatenate([[0], np.cumsum(h * w)]).astype(np.int64)
+    offp = np.concatenate([[0], np.cumsum(np.minimum(h, 32))]).astype(np.int64)
+    c.add_synthetic_store("initial", 0, page_offsets=off, seed=1)
+    c.add_synthetic_store("experimental_pooling", 0, page_offsets=offp, seed=2)
+    c.add_synthetic_store("global_pooling", n, fixed_rows=1, seed=3)
+    qs = [rng.standard_normal((int(rng.integers(10, 31)), 128)).astype(np.float32) for _ in range(256)]
+    stages = [("global_pooling", True, 1000), ("experimental_pooling", False, 300), ("initial", False, 100)]
+    for _ in range(3):
+        c.search_multistage_batch(stages, qs, final_only=True)
+    print("cfg2", n, c.last_timing_ms())
 elif what == "rerank":
     c.add_synthetic_store("initial", 100_000, fixed_rows=1030, seed=1)
     cand = rng.permutation(100_000)[:256]

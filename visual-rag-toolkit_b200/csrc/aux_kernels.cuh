@@ -291,6 +291,14 @@ __global__ void __launch_bounds__(THREADS, 1) topk_kernel(const TopkArgs a) {
     skeys[j] = key;
   }
   const int K2 = a.k2;
+  // Only the first `eff` slots can hold real keys (the rest is zero padding, the smallest key): the sort network is
+  // sized for eff = the smallest power-of-two multiple of K2 that covers this block's keys, not for CHUNK — a
+  // prefiltered candidate list of ~2k keys in an 8192-key buffer sorts 4x less.
+  int eff = CHUNK;
+  {
+    const long long here = n_in - base;   // keys of this block
+    while ((eff >> 1) >= K2 && (eff >> 1) >= here) eff >>= 1;
+  }
   // 1. sorted runs of K2, run r descending iff r is even
   for (int size = 2; size <= K2; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -298,6 +306,7 @@ __global__ void __launch_bounds__(THREADS, 1) topk_kernel(const TopkArgs a) {
 #pragma unroll
       for (int t = 0; t < PER; ++t) {
         const int e = threadIdx.x + t * THREADS;
+        if (2 * e >= eff) break;
         const int pos = 2 * e - (e & (stride - 1));
         const unsigned long long x = skeys[pos], y = skeys[pos + stride];
         const bool desc = (pos & size) == 0;
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(THREADS, 1) topk_kernel(const TopkArgs a) {
     }
   }
   // 2. merge-and-prune rounds
-  for (int live = CHUNK; live > K2; live >>= 1) {
+  for (int live = eff; live > K2; live >>= 1) {
     __syncthreads();
     unsigned long long keep[PER];
     const int half = live >> 1;

@@ -774,6 +774,9 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
       int seg_n = 0, seg_item = 0, seg_rb = 0, seg_re = 0;   // general path: this thread's entry of the tile's segment table
       bool seg_ready = false;
       int q_valid = 0, qv_g = -1;
+      const bool row_fast = MULTI && QS == 1 && p.f_thr != nullptr && p.shfl_rows == 1 && !p.slot_mode && p.pad_rows == 0 &&
+                            p.tile_stride == 1 && p.fixed_rows == 1;
+      (void)row_fast;
       for (long long seq = seq0; seq < ur.count; seq += seq_step) {
         int g;
         long long u;
@@ -788,6 +791,61 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         const uint32_t stage = static_cast<uint32_t>(seq % STAGES), phase = static_cast<uint32_t>((seq / STAGES) & 1);
         const uint32_t acc = static_cast<uint32_t>(seq % ACC), accphase = static_cast<uint32_t>((seq / ACC) & 1);
         const uint32_t ta = lane_addr + acc * N + col0;
+        if constexpr (MULTI && QS == 1) {
+          // ---- one page per tile row (global_pooling) under the top-k prefilter: the dense stage-1 scan of a batch of
+          // pooled queries. Every thread owns one page and 32 queries; the kernel is bound by the epilogue's instruction
+          // stream (4 warps per scheduler, ~1000 instructions per warp and tile on the generic path), so this path is
+          // written for the minimum: two x16 TMEM round trips, FFMA+FMUL+FSETP+LOP per score, one warp-wide OR of the
+          // hit masks, and the (rare: ~2 per warp and tile) survivors appended from a warp-uniform loop.
+          if (row_fast) {
+            const long long page = u * kTileRows + trow;
+            mbar_wait(&tfull[acc], accphase);
+            tc_fence_after_sync();
+            float scale = 1.0f;
+            if (use_scale) {
+              mbar_wait(&full[stage], phase);
+              scale = sScale[stage * kScaleStride + trow + (sMis[stage * 4] & 3)];
+            }
+            float v[32];
+            uint32_t pass = 0u;
+            const float4* thr4 = reinterpret_cast<const float4*>(sThr + col0);   // +inf for absent queries
+#pragma unroll
+            for (int c = 0; c < 32; c += 16) {
+              uint32_t hi[16], lo[16];
+              tmem_ld_x16(ta + c, hi);
+              tmem_ld_x16(ta + QP + c, lo);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 t = thr4[c / 4 + j4];
+                const float tt[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  const int j = j4 * 4 + jj;
+                  v[c + j] = fmaf(__uint_as_float(lo[j]), kInvLo, __uint_as_float(hi[j])) * scale;
+                  if (v[c + j] > tt[jj]) pass |= 1u << (c + j);
+                }
+              }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&tempty[acc]);
+              mbar_arrive(&empty[stage]);
+            }
+            if (page >= p.n_pages) pass = 0u;
+            unsigned any = __reduce_or_sync(0xffffffffu, pass);
+            while (any) {   // warp-uniform
+              const int i = __ffs(any) - 1;
+              any &= any - 1;
+              float val = v[0];
+#pragma unroll
+              for (int j = 1; j < 32; ++j) val = (i == j) ? v[j] : val;
+              if ((pass >> i) & 1u) emit(col0 + i, page, page, val);
+            }
+            continue;
+          }
+        }
         bool fast = false;
         if constexpr (QE <= 32) fast = p.shfl_rows > 0;
         if (fast) {
@@ -824,6 +882,10 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             const bool live = rin < nr;
             constexpr int LW = (QE >= 16 && !MULTI) ? 16 : 8;
             const int ncol = !MULTI ? QE : (QS == 32 ? ((q_valid + 7) & ~7) : ((min(32, max(0, p.n_sub - col0)) + 7) & ~7));
+            // one page per tile row (SR == 1, e.g. global_pooling) in a single-column-query kernel: every use of v[] below
+            // is guarded by item_ok or by a compare against +inf thresholds, so the per-element "row is live" select is
+            // dropped (the dense batched global stage is bound by epilogue instruction issue, not by HBM)
+            const bool row_pages = MULTI && QS == 1 && SR == 1;
 #pragma unroll
             for (int c = 0; c < QE; c += LW) {
               if (MULTI && c >= ncol) {   // columns without query rows are not read from TMEM (see the LARGE path)
@@ -840,9 +902,14 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
                 tmem_ld_x8(ta + QP + c, lo);
               }
               tmem_ld_wait();
+              if (row_pages) {
 #pragma unroll
-              for (int j = 0; j < LW; ++j)
-                v[c + j] = live ? fmaf(__uint_as_float(lo[j]), kInvLo, __uint_as_float(hi[j])) * scale : -INFINITY;
+                for (int j = 0; j < LW; ++j) v[c + j] = fmaf(__uint_as_float(lo[j]), kInvLo, __uint_as_float(hi[j])) * scale;
+              } else {
+#pragma unroll
+                for (int j = 0; j < LW; ++j)
+                  v[c + j] = live ? fmaf(__uint_as_float(lo[j]), kInvLo, __uint_as_float(hi[j])) * scale : -INFINITY;
+              }
             }
             tc_fence_before_sync();
             __syncwarp();
@@ -864,16 +931,32 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
               const int cf = 32 / SR;
               const int qb = col0 + rin * cf;
               if (p.f_thr) {
-                // prefilter: one compare per score; the (rare) survivors are appended to their query's candidate list
-                unsigned pass = 0u;
+                // prefilter: one compare + one warp vote per score column; survivors are rare (~2 per warp and tile), so
+                // the append path runs under a warp-uniform branch (sThr is +inf for absent queries)
+                if (SR == 1) {
+                  const float4* thr4 = reinterpret_cast<const float4*>(sThr + col0);   // all lanes: queries col0..col0+31
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (i < cf && v[i] > sThr[qb + i]) pass |= 1u << i;   // sThr is +inf for absent queries
-                if (!item_ok) pass = 0u;
-                if (pass) {
+                  for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 t = thr4[i4];
+                    const float tt[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-                  for (int i = 0; i < 32; ++i)
-                    if ((pass >> i) & 1u) emit(qb + i, item, page, v[i]);
+                    for (int j = 0; j < 4; ++j) {
+                      const bool hit = v[i4 * 4 + j] > tt[j] && item_ok;
+                      if (__any_sync(0xffffffffu, hit)) {
+                        if (hit) emit(col0 + i4 * 4 + j, item, page, v[i4 * 4 + j]);
+                      }
+                    }
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    if (i < cf) {   // warp-uniform
+                      const bool hit = v[i] > sThr[qb + i] && item_ok;
+                      if (__any_sync(0xffffffffu, hit)) {
+                        if (hit) emit(qb + i, item, page, v[i]);
+                      }
+                    }
+                  }
                 }
               } else {
 #pragma unroll
