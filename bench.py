@@ -160,6 +160,17 @@ def _ref_worker(args):
     return times
 
 
+def workload_config(pages, world):
+    """`config` of the JSON line — the same dict on both arms (the reference arm adds what it sampled)."""
+    total_pages = pages * world
+    return {
+        "workload": f"exhaustive MaxSim top-{TOP_K} over {total_pages} ColPali-shaped pages "
+                    f"({pages}/GPU x {TOKENS} tok x 128-d fp16 = {pages * TOKENS * 256 / 1e9:.1f} GB/GPU; "
+                    f"BASELINE configs[3] shard), {Q_TOKENS}-token query, NCCL all-gather top-k merge",
+        "pages_per_gpu": pages, "tokens_per_page": TOKENS, "query_tokens": Q_TOKENS, "top_k": TOP_K,
+    }
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port of quick_test.search_exhaustive ->
     compute_maxsim_score) on all host cores: the page sample is split over one process per core, each
@@ -185,9 +196,10 @@ def run_reference(args):
         "impl": "reference", "metric": "exhaustive_maxsim_pages_per_s", "value": value, "unit": "pages/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"exhaustive MaxSim top-{TOP_K}, ColPali-shaped pages x {TOKENS} tok x 128-d, {Q_TOKENS}-token query "
-                               f"(CPU arm: bounded sample of {total_pages} pages per step)",
-                   "pages_per_step": total_pages, "tokens_per_page": TOKENS, "query_tokens": Q_TOKENS, "top_k": TOP_K},
+        "config": dict(workload_config(args.pages_per_gpu, max(1, args.gpus)),
+                       reference_sample=f"each step scores a bounded sample of {total_pages} pages of this workload on the host cores; "
+                                        "pages/s is the rate over the sample",
+                       pages_per_step=total_pages),
         "cpu_baseline": {"value": value, "unit": "pages/s", "cores": workers, "kind": "port",
                          "sample": f"{total_pages} pages/step split over {workers} processes (1 BLAS thread each), "
                                    "oracle/maxsim_oracle.py::search_exhaustive"},
@@ -371,16 +383,12 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 operands, f32 accumulate (query carried as f16 hi/lo pair)",
+            "dtype": "f16",
+            "dtype_detail": "fp16 tensor-core operands, fp32 accumulate; the fp32 query is carried as an fp16 hi/lo pair (fp32-exact)",
             "data": "synthetic",
-            "config": {
-                "workload": f"exhaustive MaxSim top-{TOP_K} over {total_pages} ColPali-shaped pages "
-                            f"({pages}/GPU x {TOKENS} tok x 128-d fp16 = {pages * TOKENS * 256 / 1e9:.1f} GB/GPU; "
-                            f"BASELINE configs[3] shard), {Q_TOKENS}-token query, NCCL all-gather top-k merge",
-                "pages_per_gpu": pages, "tokens_per_page": TOKENS, "query_tokens": Q_TOKENS, "top_k": TOP_K,
-                "l2": "input (>=26 GB per step) is far larger than the 126 MB L2; no flush needed",
-                "corpus_generation_s": gen_s,
-            },
+            "config": dict(workload_config(pages, world),
+                           l2="input (>=26 GB per step) is far larger than the 126 MB L2; no flush needed",
+                           corpus_generation_s=gen_s),
             "hbm_gbs_algorithmic": total_pages * bytes_per_page * args.steps / (dev_ms * 1e-3) / 1e9,
             "e2e": {"value": total_pages * args.steps / e2e_s, "unit": "pages/s",
                     "h2d_bytes_per_step": Q_TOKENS * 128 * 4, "d2h_bytes_per_step": TOP_K * (4 + 8),
@@ -392,8 +400,9 @@ def run_ours(args):
                          "frac_of_8TBs_nominal": achieved / 8000.0,
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": pages * bytes_per_page,
                          "traffic": (args.ncu_traffic_ratio * pages * bytes_per_page) if args.ncu_traffic_ratio else None,
-                         "traffic_source": "dram__bytes_read+write per launch / algorithmic bytes = 1.0021 in the ncu --set full "
-                                           "capture at 100k pages per launch (profiles/r1d_kernels_ncu_summary.md, column `large`), scaled to this launch"},
+                         "traffic_source": "dram__bytes_read+write per launch / algorithmic bytes = 1.0104 in the ncu --set full capture of "
+                                           "this same launch shape, 500k pages (profiles/r1e_kernels_ncu_summary.md, column `large_500k`: "
+                                           "135.285 GB read + 9.7 MB written vs 133.9 GB algorithmic); scaled by pages for other sizes"},
             "cpu_baseline": {"value": cpu_pps, "unit": "pages/s", "cores": blas_threads, "kind": "port",
                              "sample": f"first {n_cpu} pages of the same corpus read back from the device, {cpu_passes} queries one after "
                                        f"the other ({cpu_passes * n_cpu} page scorings, {cpu_s:.1f} s); oracle/maxsim_oracle.py::search_exhaustive "
@@ -550,7 +559,7 @@ def main():
     ap.add_argument("--latency-queries", type=int, default=200)
     ap.add_argument("--cfg2-pages", type=int, default=1_000_000)
     ap.add_argument("--cfg4-pages", type=int, default=400_000)
-    ap.add_argument("--ncu-traffic-ratio", type=float, default=1.0021,
+    ap.add_argument("--ncu-traffic-ratio", type=float, default=1.0104,
                     help="DRAM bytes / algorithmic bytes of the scan kernel in the committed ncu capture (profiles/)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -10,6 +10,9 @@ from visual_rag_b200.corpus import GpuCorpus
 from visual_rag_b200.embedding import pooling as GP
 
 what = sys.argv[1]
+if ":" in what:      # "large:500000" == "large 500000" (one token, for scripts/gpu_profile.sh)
+    what, _n = what.split(":", 1)
+    sys.argv[1:2] = [what, _n]
 rng = np.random.default_rng(0)
 q20 = rng.standard_normal((20, 128)).astype(np.float32)
 c = GpuCorpus(0)

@@ -43,6 +43,28 @@ static int fail(const char* fmt, ...) {
 extern "C" const char* vrag_last_error(void) { return g_err.c_str(); }
 extern "C" int vrag_abi_version(void) { return 1; }
 
+// Function attributes (opt-in dynamic shared memory) are per device: every launch site keeps one flag per device of
+// the process. Returns true the first time a site is reached on the current device.
+struct PerDeviceOnce {
+  bool done[64] = {false};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+// Experiment / fallback knobs read from the environment once per process.
+static bool env_flag_is(const char* name, char value) {
+  const char* e = getenv(name);
+  return e && e[0] == value;
+}
+static bool knob_no_pad() { static const bool v = getenv("VRAG_NO_PAD") != nullptr; return v; }
+static bool knob_hi_only() { static const bool v = env_flag_is("VRAG_QUERY_SPLIT", '0'); return v; }
+static bool knob_no_prefilter() { return env_flag_is("VRAG_PREFILTER", '0'); }   // per batch call: tests toggle it at run time
+
 // ------------------------------------------------------------------------------------------------ tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -406,13 +428,20 @@ static int upload_rows(vrag_corpus* c, __half* dst, float* dst_inv, const void* 
     for (size_t o = 0; o < n_el; o += chunk) {
       const size_t n = std::min(chunk, n_el - o);
       const float* src = src_base + o;
+      cudaError_t e = cudaSuccess;
       if (!rows_on_device) {
-        CUDA_OK(cudaMemcpyAsync(tmp, src, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        e = cudaMemcpyAsync(tmp, src, n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
         src = tmp;
       }
-      f32_to_f16_kernel<<<static_cast<unsigned>((n / 4 + 256) / 256), 256, 0, c->stream>>>(src, n, dst + o);
-      c->launches++;
-      CUDA_OK(cudaStreamSynchronize(c->stream));
+      if (e == cudaSuccess) {
+        f32_to_f16_kernel<<<static_cast<unsigned>((n / 4 + 256) / 256), 256, 0, c->stream>>>(src, n, dst + o);
+        c->launches++;
+        e = cudaStreamSynchronize(c->stream);
+      }
+      if (e != cudaSuccess) {
+        if (tmp) cudaFree(tmp);
+        return fail("fp32 -> fp16 store cast failed: %s", cudaGetErrorString(e));
+      }
     }
     if (tmp) cudaFree(tmp);
   }
@@ -627,11 +656,8 @@ template <int QP, bool PACKED, bool BSW = false, int QS = QP>
 static int launch_scan_t(vrag_corpus* c, const Store& s, const ScanParams& p, long long n_units, cudaStream_t st) {
   auto kern = maxsim_scan_kernel<QP, QS, PACKED, BSW>;
   const size_t smem = ScanCfg<QP>::smem_bytes(PACKED, BSW, QS < QP);
-  static bool attr_done[8] = {false};  // per device
-  if (!attr_done[c->device & 7]) {
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_done[c->device & 7] = true;
-  }
+  static PerDeviceOnce once;
+  if (once.first()) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const unsigned grid = static_cast<unsigned>(std::min<long long>(c->num_sms, n_units));
   kern<<<grid, ScanCfg<QP>::threads(PACKED, QS < QP), smem, st>>>(p.pad_rows > 0 ? s.tm3d : s.tm128, s.tm32, s.ts128, s.ts32, p);
   c->launches++;
@@ -666,7 +692,7 @@ static void fill_scan_params(vrag_corpus* c, const Store& s, const long long* d_
       const int per_tile = kTileRows / p.slot_rows;
       p.n_tiles = (n_items + per_tile - 1) / per_tile;
       if (p.slot_rows == 32 && QP <= 32) p.shfl_rows = 32;
-    } else if (s.fixed_rows > 0 && s.pad_slot > 0 && (QP <= 32 || multi) && !getenv("VRAG_NO_PAD")) {
+    } else if (s.fixed_rows > 0 && s.pad_slot > 0 && (QP <= 32 || multi) && !knob_no_pad()) {
       // odd page sizes (ColSmol's 12/13 tiles, 3, 5, ...): TMA pads every page to a power-of-two slot for free
       p.pad_rows = static_cast<int>(s.fixed_rows);
       p.shfl_rows = s.pad_slot;
@@ -740,8 +766,7 @@ static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int
   p.q_valid = q_eff;
   {  // VRAG_Q_FP16 (or the experiment knob VRAG_QUERY_SPLIT=0): contract only the fp16 hi half of the query
     // (half the tensor work; LARGE pages only — that is where the scan is power/bandwidth bound)
-    const char* e = getenv("VRAG_QUERY_SPLIT");
-    p.hi_only = (((flags & VRAG_Q_FP16) != 0 || (e && e[0] == '0')) && QP >= 16 && !s.packed) ? 1 : 0;
+    p.hi_only = (((flags & VRAG_Q_FP16) != 0 || knob_hi_only()) && QP >= 16 && !s.packed) ? 1 : 0;
   }
   if (time_kernel) CUDA_OK(cudaEventRecord(c->evk0, st));
   int r = 0;
@@ -851,8 +876,7 @@ static int launch_scan_dense_batch(vrag_corpus* c, const Store& s, const float* 
     p.score_stride = stride_cols;
     p.n_sub = std::min(G, nq - g * G);
     {
-      const char* e = getenv("VRAG_QUERY_SPLIT");
-      p.hi_only = (((flags & VRAG_Q_FP16) != 0 || (e && e[0] == '0')) && !s.packed) ? 1 : 0;
+      p.hi_only = (((flags & VRAG_Q_FP16) != 0 || knob_hi_only()) && !s.packed) ? 1 : 0;
     }
     if (o.tile_stride > 1) {   // sample pass: every tile_stride-th page (LARGE) / full tile (PACKED fixed rows)
       p.tile_stride = o.tile_stride;
@@ -886,11 +910,8 @@ template <int CHUNK, int THREADS>
 static int launch_topk_sort(vrag_corpus* c, const TopkArgs& a, int batch, cudaStream_t st) {
   auto kern = topk_kernel<CHUNK, THREADS>;
   const size_t smem = CHUNK * sizeof(unsigned long long);
-  static bool attr_done[8] = {false};
-  if (!attr_done[c->device & 7]) {
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_done[c->device & 7] = true;
-  }
+  static PerDeviceOnce once;
+  if (once.first()) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kern<<<dim3(1, static_cast<unsigned>(batch)), THREADS, smem, st>>>(a);
   c->launches++;
   return 0;
@@ -1113,8 +1134,7 @@ struct PrefilterPlan {
 };
 static PrefilterPlan plan_prefilter(const Store& s, int k, int nq, int max_q_eff, uint32_t flags) {
   PrefilterPlan pl;
-  const char* e = getenv("VRAG_PREFILTER");
-  if (e && e[0] == '0') return pl;
+  if (knob_no_prefilter()) return pl;
   const int64_t n = s.n_pages;
   if (n < (1 << 18) || !dense_batch_covers(nq, max_q_eff, flags)) return pl;
   int64_t unit_pages = 1, n_units = n;   // sampling granularity
@@ -1277,8 +1297,7 @@ static int batch_prepare_stage(vrag_corpus* c, Store& store, int k, int64_t n_it
   const int qchunk = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(bc.nq, max_scores / per_query)));
   TRY(c->d_scores.ensure(static_cast<int64_t>(qchunk) * per_query));
   *plan = PrefilterPlan();
-  const char* pf_env = getenv("VRAG_PREFILTER");
-  if (dense && allow_prefilter && !(pf_env && pf_env[0] == '0')) *plan = plan_prefilter(store, k, qchunk, bc.max_rows[s], flags);
+  if (dense && allow_prefilter && !knob_no_prefilter()) *plan = plan_prefilter(store, k, qchunk, bc.max_rows[s], flags);
   if (plan->on) {
     TRY(c->d_fthr.ensure(qchunk));
     TRY(c->d_fkeys.ensure(static_cast<size_t>(qchunk) * plan->cap));
@@ -1499,11 +1518,8 @@ extern "C" int vrag_saliency(vrag_corpus_t* c, const char* name, const float* qu
   TRY(stage_query(c, query, n_query_rows));
   TRY(c->d_scores.ensure(n));
   const int kSalRows = 96;   // query rows held in shared memory per launch; longer queries max-combine over chunks
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_OK(cudaFuncSetAttribute(saliency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSalRows * 512));
-    attr_done = true;
-  }
+  static PerDeviceOnce once;
+  if (once.first()) CUDA_OK(cudaFuncSetAttribute(saliency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSalRows * 512));
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>((n + 7) / 8, c->num_sms * 4));
   for (int q0 = 0; q0 < n_query_rows; q0 += kSalRows) {
     const int rows = std::min(kSalRows, n_query_rows - q0);
@@ -1656,12 +1672,11 @@ static PoolSpecDev to_dev_spec(const vrag_pool_spec_t& s) {
 // spec i produces for any page (shared-memory sizing).
 static int launch_pool(const PoolInput& in, int n, const vrag_pool_spec_t* specs, PoolSpecDev* dev, int max_in_rows,
                        int max_grid_h, const int* max_out, int num_sms, cudaStream_t st, int64_t* launches) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     CUDA_OK(cudaFuncSetAttribute(pool_tokens_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 384 * 512));
     CUDA_OK(cudaFuncSetAttribute(pool_tokens_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 384 * 512));
     CUDA_OK(cudaFuncSetAttribute(pool_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 512));
-    attr_done = true;
   }
   if (in.n_pages == 0) return 0;
   PoolRowsArgs ra;
