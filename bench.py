@@ -457,6 +457,8 @@ def run_extras(corpus, args, peak, kern_ms):
                                  "speedup_vs_single_query": 4 * kern_ms / ms}
     for nm in ("initial", "mean_pooling"):
         corpus.drop_store(nm)
+    # ---- cfg0: the reference's own CPU-runnable case, in full on both sides (ColSmol-shaped, exact top-10)
+    out["cfg0_colsmol"] = run_cfg0(corpus, args, rng)
     # ---- cfg2
     n = args.cfg2_pages
     h = rng.integers(16, 33, size=n)
@@ -545,6 +547,68 @@ def run_extras(corpus, args, peak, kern_ms):
     return out
 
 
+def run_cfg0(corpus, args, rng):
+    """BASELINE configs[0]: 10k pages x 768 tokens x 128-d fp16, 20-token queries, exact MaxSim top-10 — GPU through the
+    host API against the oracle port of benchmarks/quick_test.py::search_exhaustive / search_two_stage on the SAME pages
+    (read back from the device), a few queries on the CPU side (1.7 s each), 100 on the GPU side."""
+    from oracle import maxsim_oracle as MO
+    from visual_rag_b200.embedding import pooling as GP
+
+    n0, t0 = args.cfg0_pages, 768
+    corpus.add_synthetic_store("initial", n0, fixed_rows=t0, seed=SEED + 10)
+    corpus.pool_store("initial", [GP.spec_tile_mean(64)], ["mean_pooling"])      # 12 tile means per page
+    qs = [rng.standard_normal((Q_TOKENS, 128)).astype(np.float32) for _ in range(100)]
+    ts = [("mean_pooling", True, 256), ("initial", False, TOP_K)]                 # pooled_query_vs_tiles -> MaxSim rerank
+    for q in qs[:5]:
+        corpus.search("initial", q, TOP_K)
+        corpus.search_multistage(ts, q)
+    lat_ex, lat_ts = [], []
+    for q in qs:
+        t1 = time.perf_counter()
+        ex = corpus.search("initial", q, TOP_K)
+        lat_ex.append(1e3 * (time.perf_counter() - t1))
+    dev_ms = corpus.last_timing_ms()[1]
+    for q in qs:
+        t1 = time.perf_counter()
+        corpus.search_multistage(ts, q)
+        lat_ts.append(1e3 * (time.perf_counter() - t1))
+    # CPU side on the same bits
+    raw = corpus.read_rows("initial", 0, n0 * t0).astype(np.float32)
+    docs = [raw[i * t0:(i + 1) * t0] for i in range(n0)]
+    praw = corpus.read_rows("mean_pooling", 0, n0 * 12).astype(np.float32)
+    pooled = [praw[i * 12:(i + 1) * 12] for i in range(n0)]
+    n_cpu = max(1, args.cfg0_cpu_queries)
+    same_ex = same_ts = True
+    t1 = time.perf_counter()
+    cpu_ex = [MO.search_exhaustive(q, docs, TOP_K) for q in qs[:n_cpu]]
+    cpu_ex_s = (time.perf_counter() - t1) / n_cpu
+    t1 = time.perf_counter()
+    cpu_ts = [MO.search_two_stage_pooled(q, docs, pooled, 256, TOP_K) for q in qs[:n_cpu]]
+    cpu_ts_s = (time.perf_counter() - t1) / n_cpu
+    max_rel = 0.0
+    for q, ce, ct in zip(qs, cpu_ex, cpu_ts):
+        s, ids = corpus.search("initial", q, TOP_K)
+        same_ex &= [int(i) for i in ids] == [i for i, _ in ce]
+        max_rel = max(max_rel, max(abs(float(a) - b) / abs(b) for a, (_, b) in zip(s, ce)))
+        g = corpus.search_multistage(ts, q)
+        same_ts &= [int(i) for i in g[1][1]] == [i for i, _, _ in ct]
+    for nm in ("initial", "mean_pooling"):
+        corpus.drop_store(nm)
+    bytes_pp = t0 * 256 + t0 * 4
+    return {
+        "workload": f"cfg0: {n0} ColSmol-shaped pages x {t0} tok x 128-d fp16 ({n0 * t0 * 256 / 1e9:.2f} GB), {Q_TOKENS}-token queries, exact top-{TOP_K}",
+        "gpu_exhaustive_p50_ms": float(np.percentile(lat_ex, 50)), "gpu_exhaustive_qps": 1e3 / float(np.mean(lat_ex)),
+        "gpu_exhaustive_pages_per_s": n0 * 1e3 / float(np.mean(lat_ex)), "gpu_scan_kernel_ms": dev_ms,
+        "gpu_scan_hbm_gbs": n0 * bytes_pp / (dev_ms * 1e-3) / 1e9,
+        "gpu_two_stage_p50_ms": float(np.percentile(lat_ts, 50)), "gpu_two_stage_qps": 1e3 / float(np.mean(lat_ts)),
+        "cpu_exhaustive_s_per_query": cpu_ex_s, "cpu_exhaustive_pages_per_s": n0 / cpu_ex_s,
+        "cpu_two_stage_s_per_query": cpu_ts_s, "cpu_queries": n_cpu,
+        "cpu_kind": "port (oracle/maxsim_oracle.py::search_exhaustive / search_two_stage_pooled = benchmarks/quick_test.py:158-206), single process",
+        "top10_ids_identical_exhaustive": bool(same_ex), "top10_ids_identical_two_stage": bool(same_ts),
+        "max_rel_score_diff": max_rel,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -557,6 +621,8 @@ def main():
     ap.add_argument("--extras", type=int, default=1, help="0: skip the cfg2 / cfg4 / batched extra sections")
     ap.add_argument("--ref-sample-pages", type=int, default=16384)
     ap.add_argument("--latency-queries", type=int, default=200)
+    ap.add_argument("--cfg0-pages", type=int, default=10_000)
+    ap.add_argument("--cfg0-cpu-queries", type=int, default=2)
     ap.add_argument("--cfg2-pages", type=int, default=1_000_000)
     ap.add_argument("--cfg4-pages", type=int, default=400_000)
     ap.add_argument("--ncu-traffic-ratio", type=float, default=1.0104,

@@ -836,3 +836,58 @@ def test_indexer_upsert_replaces_pages_in_place():
             c1.replace_pages("initial", [0], np.zeros((3, 128), np.float16), [0, 3])
         with pytest.raises(VragError, match="out of range"):
             c1.replace_pages("initial", [99], np.zeros((3, 128), np.float16), [0, 3])
+
+
+@pytest.mark.gpu
+def test_indexer_upload_from_threads_and_shared_handle():
+    """The reference ingests with uploader threads (run_qdrant_beir.py:720-768) while queries may run: upload_batch calls
+    from several threads and searches on the same handle serialise; every id ends up on the page that holds its vectors."""
+    import threading
+
+    from visual_rag_b200.corpus import GpuCorpus
+    from visual_rag_b200.indexing import GpuIndexer
+    from visual_rag_b200.retrieval import TwoStageRetriever
+
+    def point(i):
+        g = np.random.default_rng(500 + i)
+        t, r = 130 + (i % 7) * 10, 8 + i % 5
+        return {"id": f"p{i}", "visual_embedding": g.standard_normal((t, 128)).astype(np.float32),
+                "tile_pooled_embedding": g.standard_normal((r, 128)).astype(np.float32),
+                "experimental_pooled_embedding": g.standard_normal((r, 128)).astype(np.float32), "metadata": {"i": i}}
+
+    pts = [point(i) for i in range(96)]
+    with GpuCorpus(0) as c:
+        idx = GpuIndexer(c, "c")
+        idx.create_collection(force_recreate=True)
+        idx.upload_batch(pts[:8])
+        errors = []
+        q = np.random.default_rng(1).standard_normal((15, 128)).astype(np.float32)
+
+        def uploader(lo, hi):
+            try:
+                for a in range(lo, hi, 4):
+                    idx.upload_batch(pts[a:a + 4])
+            except Exception as e:   # noqa: BLE001
+                errors.append(e)
+
+        def searcher():
+            try:
+                two = TwoStageRetriever(idx.client, "c")
+                for _ in range(30):
+                    res = two.search_single_stage(q, top_k=3)
+                    assert len(res) == 3
+            except Exception as e:   # noqa: BLE001
+                errors.append(e)
+
+        threads = [threading.Thread(target=uploader, args=(8 + 22 * k, 8 + 22 * (k + 1))) for k in range(4)] + [threading.Thread(target=searcher)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors
+        assert c.n_pages("initial") == 96 and idx.get_existing_ids() == {p["id"] for p in pts}
+        for p in pts[::5]:
+            got = idx.client.retrieve("c", ids=[p["id"]], with_payload=True, with_vectors=["initial", "mean_pooling"])[0]
+            assert got.payload == p["metadata"]
+            assert np.array_equal(np.asarray(got.vector["initial"], np.float32), p["visual_embedding"].astype(np.float16).astype(np.float32))
+            assert np.array_equal(np.asarray(got.vector["mean_pooling"], np.float32), p["tile_pooled_embedding"].astype(np.float16).astype(np.float32))

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -34,6 +35,9 @@ static int fail(const char* fmt, ...) {
     if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
                                        __FILE__, __LINE__);                                    \
   } while (0)
+#define VRAG_LOCK(c)                             \
+  if (!(c)) return fail("corpus is NULL");       \
+  std::lock_guard<std::recursive_mutex> _vrag_lock((c)->mu)
 #define TRY(expr)            \
   do {                       \
     int _r = (expr);         \
@@ -168,6 +172,10 @@ struct BatchCtx {   // the batch of queries last uploaded to the device
 };
 
 struct vrag_corpus {
+  // One handle = one stream + one set of scratch buffers: entry points serialise on this lock, so a handle may be shared
+  // by threads (the reference's ingest runs uploader threads, run_qdrant_beir.py:720-768; ctypes releases the GIL).
+  // Recursive: vrag_search / vrag_store_append call other entry points.
+  std::recursive_mutex mu;
   int device = 0;
   BatchCtx batch;
   int64_t page_base = 0;
@@ -454,6 +462,7 @@ static int upload_rows(vrag_corpus* c, __half* dst, float* dst_inv, const void* 
 
 extern "C" int vrag_store_add(vrag_corpus_t* c, const char* name, const void* rows, int dtype, int rows_on_device,
                               const int64_t* page_offsets, int64_t n_pages, int64_t fixed_rows) {
+  VRAG_LOCK(c);
   if (!c) return fail("corpus is NULL");
   TRY(set_device(c));
   if (dtype != VRAG_F16 && dtype != VRAG_F32) return fail("unknown dtype %d", dtype);
@@ -471,6 +480,7 @@ extern "C" int vrag_store_add(vrag_corpus_t* c, const char* name, const void* ro
 // order. Device buffers grow geometrically; page tables and tensor maps are rebuilt lazily on the next use.
 extern "C" int vrag_store_append(vrag_corpus_t* c, const char* name, const void* rows, int dtype, int rows_on_device,
                                  const int64_t* page_offsets, int64_t n_pages, int64_t fixed_rows) {
+  VRAG_LOCK(c);
   if (!c) return fail("corpus is NULL");
   if (!name || !*name) return fail("store name is empty");
   auto it = c->stores.find(name);
@@ -534,6 +544,7 @@ extern "C" int vrag_store_append(vrag_corpus_t* c, const char* name, const void*
 extern "C" int vrag_store_replace_pages(vrag_corpus_t* c, const char* name, const int64_t* local_pages, int64_t n_pages,
                                         const void* rows, int dtype, int rows_on_device, const int64_t* page_offsets,
                                         int64_t fixed_rows) {
+  VRAG_LOCK(c);
   if (!c) return fail("corpus is NULL");
   if (!name || !*name) return fail("store name is empty");
   auto it = c->stores.find(name);
@@ -571,6 +582,7 @@ extern "C" int vrag_store_replace_pages(vrag_corpus_t* c, const char* name, cons
 
 extern "C" int vrag_store_add_synthetic(vrag_corpus_t* c, const char* name, const int64_t* page_offsets,
                                         int64_t n_pages, int64_t fixed_rows, uint64_t seed, int64_t row_seed_base) {
+  VRAG_LOCK(c);
   if (!c) return fail("corpus is NULL");
   TRY(set_device(c));
   int64_t total_rows = 0;
@@ -605,6 +617,7 @@ static int find_store(vrag_corpus* c, const char* name, Store** out) {
 
 extern "C" int vrag_store_info(vrag_corpus_t* c, const char* name, int64_t* n_pages, int64_t* total_rows,
                                int64_t* fixed_rows, int64_t* max_rows) {
+  VRAG_LOCK(c);
   Store* s;
   TRY(find_store(c, name, &s));
   if (n_pages) *n_pages = s->n_pages;
@@ -616,6 +629,7 @@ extern "C" int vrag_store_info(vrag_corpus_t* c, const char* name, int64_t* n_pa
 
 extern "C" int vrag_store_page_range(vrag_corpus_t* c, const char* name, int64_t local_page, int64_t* row0,
                                      int64_t* n_rows) {
+  VRAG_LOCK(c);
   Store* s;
   TRY(find_store(c, name, &s));
   if (local_page < 0 || local_page >= s->n_pages) return fail("page %lld out of range", (long long)local_page);
@@ -631,6 +645,7 @@ extern "C" int vrag_store_page_range(vrag_corpus_t* c, const char* name, int64_t
 
 extern "C" int vrag_store_read_rows(vrag_corpus_t* c, const char* name, int64_t row0, int64_t n_rows,
                                     void* out_f16_host) {
+  VRAG_LOCK(c);
   Store* s;
   TRY(find_store(c, name, &s));
   TRY(set_device(c));
@@ -643,6 +658,7 @@ extern "C" int vrag_store_read_rows(vrag_corpus_t* c, const char* name, int64_t 
 }
 
 extern "C" int vrag_store_drop(vrag_corpus_t* c, const char* name) {
+  VRAG_LOCK(c);
   Store* s;
   TRY(find_store(c, name, &s));
   TRY(set_device(c));
@@ -992,6 +1008,7 @@ static int stage_query(vrag_corpus* c, const float* query, int n_query_rows) {
 
 extern "C" int vrag_score(vrag_corpus_t* c, const char* name, const float* query, int n_query_rows, uint32_t flags,
                           const int64_t* cand_ids, int64_t n_cand, float* out_scores) {
+  VRAG_LOCK(c);
   Store* s;
   TRY(find_store(c, name, &s));
   TRY(set_device(c));
@@ -1019,6 +1036,7 @@ extern "C" int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char
                                       const uint32_t* flags, const int* ks, const float* query, int n_query_rows,
                                       const int* q_offsets, const int64_t* cand_ids, int64_t n_cand,
                                       float* out_scores, int64_t* out_ids, int* out_counts) {
+  VRAG_LOCK(c);
   if (!c) return fail("corpus is NULL");
   if (n_stages < 1 || n_stages > kMaxStages) return fail("n_stages %d out of range [1,%d]", n_stages, kMaxStages);
   if (!names || !flags || !ks || !out_scores || !out_ids || !out_counts) return fail("NULL argument");
@@ -1084,6 +1102,7 @@ extern "C" int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char
 extern "C" int vrag_search(vrag_corpus_t* c, const char* name, const float* query, int n_query_rows, uint32_t flags,
                            const int64_t* cand_ids, int64_t n_cand, int k, float* out_scores, int64_t* out_ids,
                            int* out_count) {
+  VRAG_LOCK(c);
   const char* names[1] = {name};
   int cnt = 0;
   TRY(vrag_search_multistage(c, 1, names, &flags, &k, query, n_query_rows, nullptr, cand_ids, n_cand, out_scores,
@@ -1418,6 +1437,7 @@ extern "C" int vrag_search_multistage_batch_final(vrag_corpus_t* c, int n_stages
                                                   const float* query_rows, const int* q_offsets, int per_stage_queries,
                                                   float* out_scores, int64_t* out_ids, float* out_stage_scores,
                                                   int* out_counts) {
+  VRAG_LOCK(c);
   return search_multistage_batch_impl(c, n_stages, names, flags, ks, n_queries, query_rows, q_offsets, per_stage_queries,
                                       out_scores, out_ids, out_counts, false, out_stage_scores, true);
 }
@@ -1425,6 +1445,7 @@ extern "C" int vrag_search_multistage_batch_final(vrag_corpus_t* c, int n_stages
 // ---- device-level batched stage API (sharded multi-GPU search: NCCL all-gathers run between the stages)
 extern "C" int vrag_batch_upload(vrag_corpus_t* c, int n_stages, int n_queries, const float* query_rows, const int* q_offsets,
                                  int per_stage_queries) {
+  VRAG_LOCK(c);
   if (!c) return fail("corpus is NULL");
   if (n_stages < 1 || n_stages > kMaxStages) return fail("n_stages %d out of range [1,%d]", n_stages, kMaxStages);
   if (n_queries < 1 || !query_rows || !q_offsets) return fail("bad batch arguments");
@@ -1437,6 +1458,7 @@ extern "C" int vrag_batch_upload(vrag_corpus_t* c, int n_stages, int n_queries, 
 extern "C" int vrag_batch_stage_dev(vrag_corpus_t* c, int stage, const char* name, uint32_t flags, int k,
                                     const int64_t* cand_ids_dev, int64_t n_cand, int allow_prefilter, float* out_scores_dev,
                                     int64_t* out_ids_dev, void* stream) {
+  VRAG_LOCK(c);
   Store* st;
   TRY(find_store(c, name, &st));
   TRY(set_device(c));
@@ -1466,6 +1488,7 @@ extern "C" int vrag_batch_stage_dev(vrag_corpus_t* c, int stage, const char* nam
 // 1 if a prefiltered stage since the last upload kept too few / too many candidates for some query (the caller then
 // repeats the stages with allow_prefilter = 0). Synchronises `stream`.
 extern "C" int vrag_batch_prefilter_failed(vrag_corpus_t* c, void* stream, int* failed) {
+  VRAG_LOCK(c);
   if (!c || !failed) return fail("NULL argument");
   TRY(set_device(c));
   if (!c->batch.valid) return fail("no uploaded batch");
@@ -1484,6 +1507,7 @@ extern "C" int vrag_batch_prefilter_failed(vrag_corpus_t* c, void* stream, int* 
 // Batched exact top-k merge: scores/ids [nq][n] (device) -> [nq][k], ties -> lower position.
 extern "C" int vrag_topk_batch_dev(vrag_corpus_t* c, const float* scores_dev, const int64_t* ids_dev, int64_t n, int k, int nq,
                                    float* out_scores_dev, int64_t* out_ids_dev, void* stream) {
+  VRAG_LOCK(c);
   if (!c) return fail("corpus is NULL");
   TRY(set_device(c));
   if (!scores_dev || !ids_dev || !out_scores_dev || !out_ids_dev) return fail("NULL device pointer");
@@ -1495,6 +1519,7 @@ extern "C" int vrag_search_multistage_batch(vrag_corpus_t* c, int n_stages, cons
                                             const uint32_t* flags, const int* ks, int n_queries, const float* query_rows,
                                             const int* q_offsets, int per_stage_queries, float* out_scores,
                                             int64_t* out_ids, int* out_counts) {
+  VRAG_LOCK(c);
   return search_multistage_batch_impl(c, n_stages, names, flags, ks, n_queries, query_rows, q_offsets, per_stage_queries,
                                       out_scores, out_ids, out_counts, false);
 }
@@ -1502,6 +1527,7 @@ extern "C" int vrag_search_multistage_batch(vrag_corpus_t* c, int n_stages, cons
 // ------------------------------------------------------------------------------------------------ saliency
 extern "C" int vrag_saliency(vrag_corpus_t* c, const char* name, const float* query, int n_query_rows, int64_t page_id,
                              float* out_scores, int64_t capacity, int64_t* out_rows) {
+  VRAG_LOCK(c);
   Store* s;
   TRY(find_store(c, name, &s));
   TRY(set_device(c));
@@ -1537,6 +1563,7 @@ extern "C" int vrag_saliency(vrag_corpus_t* c, const char* name, const float* qu
 extern "C" int vrag_score_dev(vrag_corpus_t* c, const char* name, const float* query_dev, int n_query_rows,
                               uint32_t flags, const int64_t* cand_ids_dev, int64_t n_cand, float* out_scores_dev,
                               void* stream) {
+  VRAG_LOCK(c);
   Store* s;
   TRY(find_store(c, name, &s));
   TRY(set_device(c));
@@ -1547,6 +1574,7 @@ extern "C" int vrag_score_dev(vrag_corpus_t* c, const char* name, const float* q
 
 extern "C" int vrag_topk_dev(vrag_corpus_t* c, const float* scores_dev, const int64_t* ids_dev, int64_t id_base,
                              int64_t n, int k, float* out_scores_dev, int64_t* out_ids_dev, void* stream) {
+  VRAG_LOCK(c);
   if (!c) return fail("corpus is NULL");
   TRY(set_device(c));
   if (!out_scores_dev || !out_ids_dev) return fail("NULL device pointer");
@@ -1810,6 +1838,7 @@ extern "C" int vrag_pool_page(int device, const vrag_pool_spec_t* spec, const vo
 
 extern "C" int vrag_store_pool(vrag_corpus_t* c, const char* src, int n_specs, const vrag_pool_spec_t* specs,
                                const char* const* dst_names, const int32_t* grid_hw) {
+  VRAG_LOCK(c);
   Store* sp;
   TRY(find_store(c, src, &sp));
   TRY(set_device(c));
@@ -1908,6 +1937,7 @@ extern "C" int vrag_store_pool(vrag_corpus_t* c, const char* src, int n_specs, c
 }
 
 extern "C" int vrag_last_timing(vrag_corpus_t* c, float* out_ms, int n) {
+  VRAG_LOCK(c);
   if (!c || !out_ms) return fail("NULL argument");
   for (int i = 0; i < n && i < 2; ++i) out_ms[i] = c->last_ms[i];
   return 0;

@@ -9,6 +9,8 @@ the mirrors in visual_rag_b200.retrieval — run unchanged on top of the GPU sto
 
 from __future__ import annotations
 
+import functools
+import threading
 from typing import Any, Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -63,6 +65,18 @@ def _match(cond, payload: dict) -> bool:
     return True
 
 
+def _locked(fn):
+    """Client calls and ingest (GpuIndexer.upload_batch) serialise on one lock: a batch upload appends to several named
+    stores and then registers its ids, and a search must not observe the collection in between."""
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with self._lock:
+            return fn(self, *args, **kwargs)
+
+    return wrapper
+
+
 class GpuCorpusClient:
     """In-process, GPU-resident replacement of QdrantClient for the retrieval path.
 
@@ -81,10 +95,12 @@ class GpuCorpusClient:
             {pid: i for i, pid in enumerate(self._ids)} if self._ids is not None else None
         )
         self._payloads = list(payloads) if payloads is not None else None
+        self._lock = threading.RLock()
         self._columns: Dict[str, np.ndarray] = {}       # payload key -> per-page value column (built on first use)
         self._filter_cache: Dict[Any, np.ndarray] = {}  # filter signature -> candidate page ids
 
     # ------------------------------------------------------------------ id mapping
+    @_locked
     def set_points(self, point_ids: Sequence[Any], payloads: Optional[Sequence[Optional[dict]]] = None) -> None:
         self._ids = list(point_ids)
         self._index = {pid: i for i, pid in enumerate(self._ids)}
@@ -92,6 +108,7 @@ class GpuCorpusClient:
         self._columns = {}
         self._filter_cache = {}
 
+    @_locked
     def append_points(self, point_ids: Sequence[Any], payloads: Optional[Sequence[Optional[dict]]] = None) -> None:
         """Register the pages a batch upload appended (incremental: O(batch), not O(collection))."""
         if self._ids is None:
@@ -106,6 +123,7 @@ class GpuCorpusClient:
         self._columns = {}
         self._filter_cache = {}
 
+    @_locked
     def set_payload(self, point_id, payload: Optional[dict]) -> None:
         """Replace the payload of an existing point (upsert of an id that is already in the collection)."""
         page = self._page(point_id)
@@ -233,6 +251,7 @@ class GpuCorpusClient:
         q = np.asarray(query, dtype=np.float32)
         return q[None, :] if q.ndim == 1 else q
 
+    @_locked
     def query_points(self, collection_name=None, query=None, using=None, limit=10, query_filter=None,
                      with_payload=True, with_vectors=False, search_params=None, prefetch=None, timeout=None,
                      **_ignored) -> QueryResponse:
@@ -264,6 +283,7 @@ class GpuCorpusClient:
                 p.vector = {nm: self.corpus.read_page(nm, page).astype(np.float32).tolist() for nm in names}
         return QueryResponse(points)
 
+    @_locked
     def query_three_stage(self, *, stage1_query, stage2_query, stage3_query, stage1_using, stage2_using,
                           stage3_using, stage1_k: int, stage2_k: int, top_k: int, query_filter=None):
         """The three ID-restricted scans of ThreeStageRetriever.search_server_side (three_stage.py:102-159)
@@ -280,6 +300,7 @@ class GpuCorpusClient:
                         for s, i in zip(scores[keep], ids[keep])])
         return out
 
+    @_locked
     def query_multistage_batch(self, *, usings: Sequence[str], limits: Sequence[int],
                                stage_queries: Sequence[Sequence[Any]], with_payload: bool = True):
         """A batch of independent multi-stage searches in ONE native call (BASELINE configs[2]: 256 queries):
@@ -304,6 +325,7 @@ class GpuCorpusClient:
             out.append(stages)
         return out
 
+    @_locked
     def query_multistage_batch_final(self, *, usings: Sequence[str], limits: Sequence[int],
                                      stage_queries: Optional[Sequence[Sequence[Any]]] = None,
                                      queries: Optional[Sequence[Any]] = None,
@@ -364,6 +386,7 @@ class GpuCorpusClient:
             out.append((pids, scores, stages, payloads))
         return out
 
+    @_locked
     def retrieve(self, collection_name=None, ids=(), with_payload=False, with_vectors=None, timeout=None, **_ignored):
         out = []
         names = [] if not with_vectors else (list(with_vectors) if not isinstance(with_vectors, bool) else [])
@@ -377,6 +400,7 @@ class GpuCorpusClient:
             out.append(ScoredPoint(pid, None, self._payload(page) if with_payload else None, vec or None))
         return out
 
+    @_locked
     def get_collection(self, collection_name=None):
         vectors = {}
         count = 0

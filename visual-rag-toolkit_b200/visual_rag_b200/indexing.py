@@ -37,6 +37,9 @@ class GpuIndexer:
         if self.client._ids is None:
             self.client.set_points([], [])
         self._extra_names: List[str] = []
+        # the reference drives upload_batch from uploader threads (run_qdrant_beir.py:720-768) while queries may run: one
+        # batch at a time validates, writes its pages to every named store and registers its ids; searches wait
+        self._lock = self.client._lock      # shared with the client's query methods (re-entrant)
 
     # ------------------------------------------------------------------ collection
     def collection_exists(self) -> bool:
@@ -93,6 +96,10 @@ class GpuIndexer:
             return 0
         if stop_event is not None and getattr(stop_event, "is_set", lambda: False)():
             return 0
+        with self._lock:
+            return self._upload_locked(points)
+
+    def _upload_locked(self, points: List[Dict[str, Any]]) -> int:
         # ---- every point -> its named vectors (fp32 first, 423-441); the last occurrence of an id wins
         per_id: Dict[Any, Dict[str, np.ndarray]] = {}
         payload_of: Dict[Any, Any] = {}
