@@ -891,3 +891,49 @@ def test_indexer_upload_from_threads_and_shared_handle():
             assert got.payload == p["metadata"]
             assert np.array_equal(np.asarray(got.vector["initial"], np.float32), p["visual_embedding"].astype(np.float16).astype(np.float32))
             assert np.array_equal(np.asarray(got.vector["mean_pooling"], np.float32), p["tile_pooled_embedding"].astype(np.float16).astype(np.float32))
+
+
+@pytest.mark.gpu
+def test_sampled_topk_equals_radix_select(corpus, monkeypatch):
+    """Single-query searches over large score arrays take their top-k from a sampled threshold + one compaction pass; the
+    lists must be bit-identical to the radix-select path (VRAG_SAMPLED_TOPK=0, pinned to the oracle by the tests above),
+    including the cases where the estimate must fail and fall back: all scores tied, almost all pages empty."""
+    def both(name, q, k, **kw):
+        a = corpus.search(name, q, k, **kw)
+        monkeypatch.setenv("VRAG_SAMPLED_TOPK", "0")
+        b = corpus.search(name, q, k, **kw)
+        monkeypatch.delenv("VRAG_SAMPLED_TOPK")
+        assert a[1].tolist() == b[1].tolist() and a[0].tolist() == b[0].tolist(), (name, k)
+        return a
+
+    q = CS.query_rows(9100, 12)
+    n = 300_000                                     # strided sample (n > 65536)
+    corpus.add_store("tk", rows16(9101, n * 2), fixed_rows=2)
+    for k in (1, 10, 256, 1000):
+        s, ids = both("tk", q, k)
+        assert len(ids) == k and np.all(np.diff(s) <= 0)
+    both("tk", q, 64, pool_query=True)
+    cand = np.random.default_rng(3).permutation(n)[:40_000]      # candidate list: ids map through the list
+    s, ids = both("tk", q, 100, candidate_ids=cand)
+    assert set(ids.tolist()) <= set(cand.tolist())
+    st = corpus.search_multistage([("tk", False, 500), ("tk", False, 7)], q)
+    monkeypatch.setenv("VRAG_SAMPLED_TOPK", "0")
+    st0 = corpus.search_multistage([("tk", False, 500), ("tk", False, 7)], q)
+    monkeypatch.delenv("VRAG_SAMPLED_TOPK")
+    assert st[0][1].tolist() == st0[0][1].tolist() and st[1][1].tolist() == st0[1][1].tolist()
+    corpus.add_store("tk_small", rows16(9102, 20_000 * 3), fixed_rows=3)    # n <= 65536: every score is "sampled"
+    for k in (10, 300):
+        both("tk_small", q, k)
+    # all pages identical -> every score ties -> the estimate cannot separate k keys -> exact fallback, ties by lower id
+    one = rows16(9103, 4)
+    corpus.add_store("tk_ties", np.tile(one, (30_000, 1)), fixed_rows=4)
+    s, ids = both("tk_ties", q, 50)
+    assert ids.tolist() == list(range(50)) and len(set(s.tolist())) == 1
+    # almost every page empty (-inf): fewer finite scores than k
+    off = np.zeros(20_001, dtype=np.int64)
+    off[-5:] = np.arange(1, 6) * 3
+    corpus.add_store("tk_empty", rows16(9104, 15), page_offsets=off)
+    s, ids = both("tk_empty", q, 10)
+    assert sorted(ids[:5].tolist()) == [19_995, 19_996, 19_997, 19_998, 19_999][:5] or np.isfinite(s[:5]).all()
+    for nm in ("tk", "tk_small", "tk_ties", "tk_empty"):
+        corpus.drop_store(nm)

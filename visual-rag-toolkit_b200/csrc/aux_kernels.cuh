@@ -267,6 +267,8 @@ struct TopkArgs {
   long long out_stride;       // out_scores / out_ids / out_pos
   long long ids_stride;
   const int* n_dyn;           // optional per-query element count (device); overrides n / n_total
+  int* fail_flag;             // optional (with n_dyn): set when a query's count is < need or > n (= the list capacity):
+  int need;                   //   the sampled / prefiltered candidate list is unusable and the caller must redo exactly
 };
 
 template <int CHUNK, int THREADS>
@@ -274,8 +276,12 @@ __global__ void __launch_bounds__(THREADS, 1) topk_kernel(const TopkArgs a) {
   extern __shared__ unsigned long long skeys[];
   constexpr int PER = CHUNK / 2 / THREADS;   // compare-exchanges per thread per full-width stage
   const long long b = blockIdx.y;
-  const long long n_in = a.n_dyn ? a.n_dyn[b] : a.n;
-  const long long n_real = a.n_dyn ? a.n_dyn[b] : a.n_total;
+  long long n_in = a.n_dyn ? a.n_dyn[b] : a.n;
+  if (a.n_dyn && a.fail_flag) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && (n_in < a.need || n_in > a.n)) atomicOr(a.fail_flag, 1);
+    if (n_in > a.n) n_in = a.n;
+  }
+  const long long n_real = a.n_dyn ? n_in : a.n_total;
   const long long base = static_cast<long long>(blockIdx.x) * CHUNK;
   for (int j = threadIdx.x; j < CHUNK; j += THREADS) {
     const long long i = base + j;
@@ -590,8 +596,15 @@ __global__ void prefilter_thr_kernel(const float* __restrict__ sample_top, int m
 // between their min and max, then the lower edge of the bin in which the count from the top reaches m. The
 // threshold only has to let roughly m sample scores through (the survivor count of the full scan is verified
 // afterwards), so no exact selection is needed: two passes over an L2-resident 256 KB row.
+// CACHE (single-query sampled top-k, n_sample <= 32768): the strided sample is gathered once into dynamic shared memory
+// and the histogram pass reads it from there. One block does the whole estimate; every 4-byte sample costs a 32-byte
+// sector from L2, which is what its ~17 us are made of (a compact sample written by the scan epilogue would cut it).
+constexpr int kThrCacheMax = 32768;
+template <bool CACHE>
 __global__ void __launch_bounds__(1024) prefilter_sample_thr_kernel(const float* __restrict__ sample, long long n_sample,
-                                                                    int m, float* __restrict__ thr, int* __restrict__ cnt) {
+                                                                    int m, float* __restrict__ thr, int* __restrict__ cnt,
+                                                                    long long elem_stride = 1) {
+  extern __shared__ float s_cache[];   // CACHE: [n_sample]
   __shared__ unsigned int hist[2048];
   __shared__ float red_lo[32], red_hi[32];
   __shared__ float s_lo, s_w;
@@ -600,9 +613,26 @@ __global__ void __launch_bounds__(1024) prefilter_sample_thr_kernel(const float*
   const float* sc = sample + b * n_sample;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float lo = INFINITY, hi = -INFINITY;
-  for (long long i = threadIdx.x; i < n_sample; i += 1024) {
-    const float x = sc[i];
-    if (x > -INFINITY && x < INFINITY) { lo = fminf(lo, x); hi = fmaxf(hi, x); }
+  if constexpr (CACHE) {
+    for (long long i0 = threadIdx.x; i0 < n_sample; i0 += 4096) {
+      float x[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long i = i0 + j * 1024;
+        x[j] = i < n_sample ? __ldg(sc + i * elem_stride) : __int_as_float(0x7fc00000);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long i = i0 + j * 1024;
+        if (i < n_sample) s_cache[i] = x[j];
+        if (x[j] > -INFINITY && x[j] < INFINITY) { lo = fminf(lo, x[j]); hi = fmaxf(hi, x[j]); }
+      }
+    }
+  } else {
+    for (long long i = threadIdx.x; i < n_sample; i += 1024) {
+      const float x = sc[i * elem_stride];
+      if (x > -INFINITY && x < INFINITY) { lo = fminf(lo, x); hi = fmaxf(hi, x); }
+    }
   }
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
@@ -623,7 +653,7 @@ __global__ void __launch_bounds__(1024) prefilter_sample_thr_kernel(const float*
   if (w > 0.0f) {
     const float inv_w = 1.0f / w;
     for (long long i = threadIdx.x; i < n_sample; i += 1024) {
-      const float x = sc[i];
+      const float x = CACHE ? s_cache[i] : sc[i * elem_stride];
       if (x > -INFINITY && x < INFINITY) atomicAdd(&hist[min(2047, max(0, static_cast<int>((x - base) * inv_w)))], 1u);
     }
   }
@@ -662,6 +692,53 @@ __global__ void prefilter_check_kernel(int* __restrict__ cnt, int batch, int nee
     const int c = cnt[b];
     if (c < need || c > cap) atomicOr(flag, 1);
     if (c > cap) cnt[b] = cap;
+  }
+}
+
+// Sampled top-k, pass 2: append the keys of all scores above the threshold to keys[0, cap) (any order; the sort
+// kernel orders them). One warp-aggregated atomic per warp and 128 scores. thr == -inf lets everything above -inf through.
+__global__ void __launch_bounds__(256) topk_compact_thr_kernel(const float* __restrict__ scores, long long n,
+                                                               const float* __restrict__ thr, int* __restrict__ cnt,
+                                                               unsigned long long* __restrict__ keys, int cap) {
+  const float t = __ldg(thr);
+  const int lane = threadIdx.x & 31;
+  const long long n4 = n >> 2;
+  // warp-uniform trip count (the shuffles below need every lane): vb = first float4 index of the warp's 32
+  for (long long vb = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) - lane; vb < n4 + 1;
+       vb += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long v = vb + lane;
+    float x[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    if (v < n4) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(scores) + v);
+      x[0] = f.x; x[1] = f.y; x[2] = f.z; x[3] = f.w;
+    } else if (v == n4) {
+      for (int j = 0; j < static_cast<int>(n & 3); ++j) x[j] = scores[v * 4 + j];
+    }
+    unsigned hits = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (x[j] > t) hits |= 1u << j;   // NaN and -inf never pass
+    const int mine = __popc(hits);
+    // exclusive prefix of `mine` over the warp + one atomic for the warp's total
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += y;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) continue;   // warp-uniform
+    int base = 0;
+    if (lane == 31) base = atomicAdd(cnt, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((hits >> j) & 1u) {
+        if (base < cap)
+          keys[base] = (static_cast<unsigned long long>(score_to_ord(x[j])) << 32) |
+                       static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<uint32_t>(v * 4 + j));
+        ++base;
+      }
   }
 }
 

@@ -183,6 +183,10 @@ struct vrag_corpus {
   cudaStream_t stream = nullptr;
   std::map<std::string, Store> stores;
   DevBuf<float> d_query, d_scores, d_out_scores;
+  DevBuf<unsigned long long> d_skeys;   // sampled top-k: survivor keys
+  DevBuf<float> d_sthr;           // sampled top-k: threshold [1]
+  DevBuf<int> d_sstate;           // sampled top-k: [0] survivor count, [1] "estimate failed" flag
+  int sampled_runs = 0, sampled_fallbacks = 0;
   DevBuf<float> d_scores_part;    // partial page scores of the later row chunks of a > 128-token query
   DevBuf<uint8_t> d_qimg;
   DevBuf<unsigned long long> d_keys_a, d_keys_b;
@@ -253,12 +257,12 @@ extern "C" int vrag_corpus_create(int device, int64_t page_base, vrag_corpus_t**
   CUDA_OK(cudaEventCreate(&c->evk1));
   CUDA_OK(cudaMallocHost(&c->h_query, kMaxQueryRows * 128 * sizeof(float)));
   c->h_query_cap = kMaxQueryRows;
-  CUDA_OK(cudaMallocHost(&c->h_counts, kMaxStages * sizeof(int)));
+  CUDA_OK(cudaMallocHost(&c->h_counts, (kMaxStages + 1) * sizeof(int)));   // + the sampled top-k flag
   CUDA_OK(cudaMallocHost(&c->h_flag, sizeof(int)));
   *c->h_flag = 0;
   TRY(c->d_query.ensure(kMaxQueryRows * 128));
   TRY(c->d_qimg.ensure(256 * 256));
-  TRY(c->d_counts.ensure(kMaxStages));
+  TRY(c->d_counts.ensure(kMaxStages + 1));
   *out = c;
   return 0;
 }
@@ -272,6 +276,9 @@ extern "C" int vrag_corpus_destroy(vrag_corpus_t* c) {
   c->d_scores.release();
   c->d_out_scores.release();
   c->d_scores_part.release();
+  c->d_skeys.release();
+  c->d_sthr.release();
+  c->d_sstate.release();
   c->d_qimg.release();
   c->d_keys_a.release();
   c->d_keys_b.release();
@@ -996,6 +1003,98 @@ static int launch_topk(vrag_corpus* c, const float* d_scores, const long long* d
   return 0;
 }
 
+// Sorted top-k of per-query key lists keys[batch][cap] holding n_dyn[b] valid keys each (cap <= 8192).
+static int launch_topk_keys(vrag_corpus* c, const unsigned long long* keys, const int* n_dyn, int cap, int k,
+                            int64_t id_base, float* out_scores, long long* out_ids, cudaStream_t st, int batch,
+                            const long long* ids = nullptr, int* out_count = nullptr, int* fail_flag = nullptr, int need = 0) {
+  int k2 = 1;
+  while (k2 < k) k2 <<= 1;
+  TopkArgs a;
+  memset(&a, 0, sizeof(a));
+  a.k = k;
+  a.keys_in = keys;
+  a.in_stride = cap;
+  a.n = cap;
+  a.n_total = cap;
+  a.n_dyn = n_dyn;
+  a.out_scores = out_scores;
+  a.out_ids = out_ids;
+  a.id_base = id_base;
+  a.ids = ids;
+  a.out_count = out_count;
+  a.fail_flag = fail_flag;
+  a.need = need;
+  a.out_stride = k;
+  const int chunk = cap <= 1024 ? 1024 : (cap <= 2048 ? 2048 : 8192);
+  a.k2 = std::min(k2, chunk);
+  if (chunk == 8192) TRY((launch_topk_sort<8192, 1024>(c, a, batch, st)));
+  else if (chunk == 2048) TRY((launch_topk_sort<2048, 1024>(c, a, batch, st)));
+  else TRY((launch_topk_sort<1024, 512>(c, a, batch, st)));
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Sampled top-k of ONE large score array (single-query searches: the radix select costs ~70 us of launches and
+// match_any histograms per call, 9 % of a two-stage query): a threshold from a strided sample of the scores
+// (prefilter_sample_thr_kernel), one compaction pass that keeps the keys above it, and a sort of the ~1k survivors.
+// Exact whenever between k and cap keys survive (checked on the device; otherwise the caller repeats the search with
+// the radix select) — ties at the k-th score are all above the threshold, so the key order still breaks them by index.
+struct SampledPlan {
+  bool on = false;
+  long long stride = 1, n_sample = 0;
+  int m = 0, cap = 0;
+};
+static SampledPlan plan_sampled_topk(int64_t n, int k) {
+  SampledPlan pl;
+  if (env_flag_is("VRAG_SAMPLED_TOPK", '0')) return pl;
+  if (n < 8192 || k > 1024 || k >= n) return pl;
+  const long long want = std::max<long long>(8192, (24ll * n + k - 1) / k);   // >= 24 expected sample hits above the k-th score
+  double bound;
+  if (n <= 65536 || want * 2 > n) {   // small arrays: "sample" everything, the threshold is the k-th score's histogram bin
+    pl.stride = 1;
+    pl.n_sample = n;
+    pl.m = k;
+    bound = k + 64.0 + n / 512.0;
+  } else {
+    const long long take = std::min<long long>(want, kThrCacheMax);   // the estimate kernel caches its sample in shared memory
+    pl.stride = (n + take - 1) / take;
+    pl.n_sample = (n + pl.stride - 1) / pl.stride;
+    const double ratio = static_cast<double>(n) / pl.n_sample, target = k / ratio;
+    // 4-sigma margins on both sides (a miss, ~3e-5 per query, costs one exact redo)
+    int m = static_cast<int>(target) + 1;
+    while (m - 4.0 * sqrt(static_cast<double>(m)) < target) ++m;
+    pl.m = m;
+    bound = m * ratio * (1.0 + 3.0 / sqrt(static_cast<double>(m)));   // list capacity: +3 sigma
+  }
+  pl.cap = bound <= 1024 ? 1024 : bound <= 2048 ? 2048 : bound <= 8192 ? 8192 : 0;
+  pl.on = pl.cap > 0;
+  return pl;
+}
+static int launch_topk_sampled(vrag_corpus* c, const float* d_scores, const long long* d_ids, int64_t id_base, int64_t n, int k,
+                               float* out_scores, long long* out_ids, int* out_count, int* d_fail_flag, cudaStream_t st,
+                               const SampledPlan& pl) {
+  TRY(c->d_skeys.ensure(pl.cap));
+  TRY(c->d_sthr.ensure(1));
+  TRY(c->d_sstate.ensure(2));
+  if (pl.n_sample <= kThrCacheMax) {
+    static PerDeviceOnce once;
+    if (once.first())
+      CUDA_OK(cudaFuncSetAttribute(prefilter_sample_thr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThrCacheMax * 4));
+    prefilter_sample_thr_kernel<true><<<1, 1024, static_cast<size_t>(pl.n_sample) * 4, st>>>(d_scores, pl.n_sample, pl.m, c->d_sthr.p,
+                                                                                             c->d_sstate.p, pl.stride);
+  } else {
+    prefilter_sample_thr_kernel<false><<<1, 1024, 0, st>>>(d_scores, pl.n_sample, pl.m, c->d_sthr.p, c->d_sstate.p, pl.stride);
+  }
+  const long long vecs = n / 4 + 1;
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(c->num_sms * 8ll, (vecs + 255) / 256));
+  topk_compact_thr_kernel<<<grid, 256, 0, st>>>(d_scores, n, c->d_sthr.p, c->d_sstate.p, c->d_skeys.p, pl.cap);
+  c->launches += 2;
+  c->sampled_runs++;
+  // the sort kernel also checks the survivor count (k <= count <= cap) and raises the flag otherwise
+  return launch_topk_keys(c, c->d_skeys.p, c->d_sstate.p, pl.cap, k, id_base, out_scores, out_ids, st, 1, d_ids, out_count,
+                          d_fail_flag, static_cast<int>(std::min<int64_t>(k, n)));
+}
+
 // ------------------------------------------------------------------------------------------------ host-facing search
 static int stage_query(vrag_corpus* c, const float* query, int n_query_rows) {
   if (!query) return fail("query is NULL");
@@ -1032,11 +1131,10 @@ extern "C" int vrag_score(vrag_corpus_t* c, const char* name, const float* query
   return 0;
 }
 
-extern "C" int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char* const* names,
-                                      const uint32_t* flags, const int* ks, const float* query, int n_query_rows,
-                                      const int* q_offsets, const int64_t* cand_ids, int64_t n_cand,
-                                      float* out_scores, int64_t* out_ids, int* out_counts) {
-  VRAG_LOCK(c);
+static int search_multistage_impl(vrag_corpus_t* c, int n_stages, const char* const* names,
+                                  const uint32_t* flags, const int* ks, const float* query, int n_query_rows,
+                                  const int* q_offsets, const int64_t* cand_ids, int64_t n_cand,
+                                  float* out_scores, int64_t* out_ids, int* out_counts, bool allow_sampled) {
   if (!c) return fail("corpus is NULL");
   if (n_stages < 1 || n_stages > kMaxStages) return fail("n_stages %d out of range [1,%d]", n_stages, kMaxStages);
   if (!names || !flags || !ks || !out_scores || !out_ids || !out_counts) return fail("NULL argument");
@@ -1070,7 +1168,8 @@ extern "C" int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char
   size_t off = 0;
   int64_t n_prev = n_first;   // survivors entering the stage
   const long long* d_prev_ids = cand_ids ? c->d_cand.p : nullptr;
-  bool timed = false;
+  bool timed = false, used_sampled = false;
+  int* const d_fail = c->d_counts.p + kMaxStages;   // travels to the host with the per-stage counts
   for (int s = 0; s < n_stages; ++s) {
     const int64_t n_items = n_prev;
     const float* dq = c->d_query.p + (q_offsets ? static_cast<size_t>(q_offsets[s]) * 128 : 0);
@@ -1080,8 +1179,16 @@ extern "C" int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char
       TRY(launch_scan(c, *st[s], dq, qrows, flags[s], d_prev_ids, n_items, c->d_scores.p, c->stream, !timed));
       timed = true;
     }
-    TRY(launch_topk(c, c->d_scores.p, d_prev_ids, c->page_base, n_items, ks[s], c->d_out_scores.p + off,
-                    c->d_out_ids.p + off, nullptr, c->d_counts.p + s, c->stream));
+    const SampledPlan sp = (allow_sampled && n_items > 0) ? plan_sampled_topk(n_items, ks[s]) : SampledPlan();
+    if (sp.on) {
+      if (!used_sampled) CUDA_OK(cudaMemsetAsync(d_fail, 0, sizeof(int), c->stream));
+      used_sampled = true;
+      TRY(launch_topk_sampled(c, c->d_scores.p, d_prev_ids, c->page_base, n_items, ks[s], c->d_out_scores.p + off,
+                              c->d_out_ids.p + off, c->d_counts.p + s, d_fail, c->stream, sp));
+    } else {
+      TRY(launch_topk(c, c->d_scores.p, d_prev_ids, c->page_base, n_items, ks[s], c->d_out_scores.p + off,
+                      c->d_out_ids.p + off, nullptr, c->d_counts.p + s, c->stream));
+    }
     d_prev_ids = c->d_out_ids.p + off;
     n_prev = std::min<int64_t>(ks[s], n_items);
     off += ks[s];
@@ -1089,14 +1196,29 @@ extern "C" int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char
   CUDA_OK(cudaEventRecord(c->ev1, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->h_out_scores, c->d_out_scores.p, total_k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->h_out_ids, c->d_out_ids.p, total_k * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->h_counts, c->d_counts.p, n_stages * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->h_counts, c->d_counts.p, (kMaxStages + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (used_sampled && c->h_counts[kMaxStages]) {
+    // a sampled threshold kept too few / too many keys (heavy ties, mostly -inf scores, ...): exact radix-select path
+    c->sampled_fallbacks++;
+    return search_multistage_impl(c, n_stages, names, flags, ks, query, n_query_rows, q_offsets, cand_ids, n_cand, out_scores,
+                                  out_ids, out_counts, false);
+  }
   memcpy(out_scores, c->h_out_scores, total_k * sizeof(float));
   memcpy(out_ids, c->h_out_ids, total_k * sizeof(long long));
   memcpy(out_counts, c->h_counts, n_stages * sizeof(int));
   cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1);
   if (timed) cudaEventElapsedTime(&c->last_ms[1], c->evk0, c->evk1);
   return 0;
+}
+
+extern "C" int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char* const* names,
+                                      const uint32_t* flags, const int* ks, const float* query, int n_query_rows,
+                                      const int* q_offsets, const int64_t* cand_ids, int64_t n_cand,
+                                      float* out_scores, int64_t* out_ids, int* out_counts) {
+  VRAG_LOCK(c);
+  return search_multistage_impl(c, n_stages, names, flags, ks, query, n_query_rows, q_offsets, cand_ids, n_cand, out_scores,
+                                out_ids, out_counts, true);
 }
 
 extern "C" int vrag_search(vrag_corpus_t* c, const char* name, const float* query, int n_query_rows, uint32_t flags,
@@ -1111,32 +1233,6 @@ extern "C" int vrag_search(vrag_corpus_t* c, const char* name, const float* quer
   return 0;
 }
 
-
-// Sorted top-k of per-query key lists keys[batch][cap] holding n_dyn[b] valid keys each (cap <= 8192).
-static int launch_topk_keys(vrag_corpus* c, const unsigned long long* keys, const int* n_dyn, int cap, int k,
-                            int64_t id_base, float* out_scores, long long* out_ids, cudaStream_t st, int batch) {
-  int k2 = 1;
-  while (k2 < k) k2 <<= 1;
-  TopkArgs a;
-  memset(&a, 0, sizeof(a));
-  a.k = k;
-  a.keys_in = keys;
-  a.in_stride = cap;
-  a.n = cap;
-  a.n_total = cap;
-  a.n_dyn = n_dyn;
-  a.out_scores = out_scores;
-  a.out_ids = out_ids;
-  a.id_base = id_base;
-  a.out_stride = k;
-  const int chunk = cap <= 1024 ? 1024 : (cap <= 2048 ? 2048 : 8192);
-  a.k2 = std::min(k2, chunk);
-  if (chunk == 8192) TRY((launch_topk_sort<8192, 1024>(c, a, batch, st)));
-  else if (chunk == 2048) TRY((launch_topk_sort<2048, 1024>(c, a, batch, st)));
-  else TRY((launch_topk_sort<1024, 512>(c, a, batch, st)));
-  CUDA_OK(cudaGetLastError());
-  return 0;
-}
 
 // Fused top-k prefilter plan for a dense batched stage (top-k of n_pages scores per query, k << n_pages):
 //   1. score a strided sample of S pages, take each query's m-th best sample score as its threshold;
@@ -1263,7 +1359,7 @@ static int batch_stage_chunk(vrag_corpus* c, int s, Store& store, uint32_t flags
       o.n_sample = plan.n_sample;
       TRY(launch_scan_dense_batch(c, store, c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows, flags, c->d_scores.p, stm,
                                   false, o));
-      prefilter_sample_thr_kernel<<<qc, 1024, 0, stm>>>(c->d_scores.p, plan.n_sample, plan.m, c->d_fthr.p, c->d_fcnt.p);
+      prefilter_sample_thr_kernel<false><<<qc, 1024, 0, stm>>>(c->d_scores.p, plan.n_sample, plan.m, c->d_fthr.p, c->d_fcnt.p);
       DenseOpts f;
       f.thr = c->d_fthr.p;
       f.cnt = c->d_fcnt.p;
