@@ -937,3 +937,57 @@ def test_sampled_topk_equals_radix_select(corpus, monkeypatch):
     assert sorted(ids[:5].tolist()) == [19_995, 19_996, 19_997, 19_998, 19_999][:5] or np.isfinite(s[:5]).all()
     for nm in ("tk", "tk_small", "tk_ties", "tk_empty"):
         corpus.drop_store(nm)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_randomized_differential_vs_oracle(corpus, seed):
+    """Seeded random layouts — page sizes from empty to > 1000 rows (or all small, or fixed), 1..150 query rows, random k,
+    optional candidate lists with out-of-shard ids, pooled or token queries, with and without normalisation — scored by the
+    kernels and by the oracle: scores within tolerance, top-k lists identical up to swaps between near-equal scores."""
+    rng = np.random.default_rng(10_000 + seed)
+    kind = seed % 4
+    n = int(rng.integers(5, 400))
+    if kind == 0:
+        lens = rng.integers(0, 1100, size=n)          # LARGE, ragged, some empty
+    elif kind == 1:
+        lens = rng.integers(0, 33, size=n)            # pooled-store sized, ragged
+    elif kind == 2:
+        lens = np.full(n, int(rng.integers(1, 129)))  # fixed rows <= 128
+    else:
+        lens = rng.integers(1, 129, size=n)           # PACKED general path
+    if lens.sum() == 0:
+        lens[0] = 3
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    rows = rows16(20_000 + seed, int(off[-1]), scale=bool(seed % 2))
+    docs = [rows[off[i]:off[i + 1]].astype(np.float32) for i in range(n)]
+    if kind == 2:
+        corpus.add_store("rd", rows, fixed_rows=int(lens[0]))
+    else:
+        corpus.add_store("rd", rows, page_offsets=off)
+    for trial in range(3):
+        qn = int(rng.choice([1, 2, 7, 20, 33, 64, 100, 150]))
+        q = CS.query_rows(30_000 + seed * 10 + trial, qn)
+        pool = bool(rng.integers(0, 2)) and qn > 1
+        normalize = bool(rng.integers(0, 4))          # mostly cosine
+        k = int(rng.integers(1, 2 * n))
+        qq = q.mean(axis=0, keepdims=True) if pool else q
+        want = np.array([MO.maxsim_score(qq, d, normalize=normalize) if len(d) else -np.inf for d in docs])
+        got = corpus.score("rd", q, normalize=normalize, pool_query=pool)
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), fin)
+        close(got[fin], want[fin], rtol=1e-4 if normalize else 3e-4, atol=1e-5 if normalize else 1e-3)
+        cand = None
+        if trial == 1:
+            cand = np.concatenate([rng.permutation(n)[: max(1, n // 3)], [n + 5, -2]]).astype(np.int64)
+            rng.shuffle(cand)
+        s, ids = corpus.search("rd", q, k, normalize=normalize, pool_query=pool, candidate_ids=cand)
+        # rank by the kernel's own scores: an exact-order check of the top-k logic. Empty pages and ids outside the shard
+        # score -inf and sort last, in candidate order (the sharded merge relies on that; the client drops them)
+        pool_idx = np.arange(n) if cand is None else cand
+        inside = (pool_idx >= 0) & (pool_idx < n)
+        ref_scores = np.where(inside, got[np.clip(pool_idx, 0, n - 1)], -np.inf)
+        order = sorted(range(len(pool_idx)), key=lambda j: (-ref_scores[j], j))[:k]
+        assert ids.tolist() == [int(pool_idx[j]) for j in order], (seed, trial, kind)
+        assert s.tolist() == [float(ref_scores[j]) for j in order]
+    corpus.drop_store("rd")
