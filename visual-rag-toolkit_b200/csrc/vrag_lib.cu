@@ -1865,6 +1865,55 @@ static int launch_pool(const PoolInput& in, int n, const vrag_pool_spec_t* specs
   return 0;
 }
 
+// Per-device context of the single-page pooling calls (the drop-in for calling a pooling.py function on one numpy
+// array, ~10 calls per indexed page): one stream, grow-only device buffers and pinned staging, created on first use and
+// kept for the life of the process — a call is two copies, one launch and one synchronisation (no allocation, no stream
+// creation, no device-property query on the call path). Calls on one device serialise on the context's lock.
+struct PoolPageCtx {
+  std::mutex mu;
+  bool ready = false;
+  int num_sms = 0;
+  cudaStream_t st = nullptr;
+  void *d_in = nullptr, *d_out = nullptr, *h_in = nullptr, *h_out = nullptr;
+  long long* d_off = nullptr;    // {0, 0}: the offsets of an empty page
+  size_t in_cap = 0, out_cap = 0;
+};
+static PoolPageCtx g_pool_ctx[64];
+
+static int pool_ctx_ensure(PoolPageCtx& cx, int device, size_t in_b, size_t out_b) {
+  if (!cx.ready) {
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+    cx.num_sms = prop.multiProcessorCount;
+    CUDA_OK(cudaStreamCreateWithFlags(&cx.st, cudaStreamNonBlocking));
+    CUDA_OK(cudaMalloc(&cx.d_off, 2 * sizeof(long long)));
+    CUDA_OK(cudaMemset(cx.d_off, 0, 2 * sizeof(long long)));
+    cx.ready = true;
+  }
+  if (in_b > cx.in_cap) {
+    if (cx.d_in) cudaFree(cx.d_in);
+    if (cx.h_in) cudaFreeHost(cx.h_in);
+    cx.d_in = cx.h_in = nullptr;
+    cx.in_cap = 0;
+    const size_t want = std::max<size_t>(in_b + in_b / 2, size_t(1) << 20);
+    CUDA_OK(cudaMalloc(&cx.d_in, want));
+    CUDA_OK(cudaMallocHost(&cx.h_in, want));
+    cx.in_cap = want;
+  }
+  if (out_b > cx.out_cap) {
+    if (cx.d_out) cudaFree(cx.d_out);
+    if (cx.h_out) cudaFreeHost(cx.h_out);
+    cx.d_out = cx.h_out = nullptr;
+    cx.out_cap = 0;
+    const size_t want = std::max<size_t>(out_b + out_b / 2, size_t(1) << 18);
+    CUDA_OK(cudaMalloc(&cx.d_out, want));
+    CUDA_OK(cudaMallocHost(&cx.h_out, want));
+    cx.out_cap = want;
+  }
+  return 0;
+}
+
 extern "C" int vrag_pool_page(int device, const vrag_pool_spec_t* spec, const void* in, int in_dtype, int64_t in_rows,
                               void* out, int out_dtype, int64_t out_capacity_rows, int64_t* out_rows) {
   if (!spec || !out_rows) return fail("NULL argument");
@@ -1884,52 +1933,38 @@ extern "C" int vrag_pool_page(int device, const vrag_pool_spec_t* spec, const vo
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("no CUDA device available: libvrag_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev || device >= 64) return fail("device %d out of range (have %d)", device, ndev);
   CUDA_OK(cudaSetDevice(device));
   const size_t in_b = static_cast<size_t>(in_rows) * 128 * (in_dtype == VRAG_F32 ? 4 : 2);
   const size_t out_b = static_cast<size_t>(n_out) * 128 * (out_dtype == VRAG_F32 ? 4 : 2);
-  void *d_in = nullptr, *d_out = nullptr;
-  cudaStream_t st;
-  CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  int rc = 0;
-  do {
-    if (cudaMalloc(&d_in, std::max<size_t>(in_b, 256)) != cudaSuccess || cudaMalloc(&d_out, out_b) != cudaSuccess) {
-      rc = fail("cudaMalloc failed in vrag_pool_page");
-      break;
-    }
-    if (in_b && cudaMemcpyAsync(d_in, in, in_b, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = fail("H2D copy failed"); break; }
-    PoolInput pin;
-    memset(&pin, 0, sizeof(pin));
-    pin.in = d_in;
-    pin.in_f32 = in_dtype == VRAG_F32;
-    pin.in_fixed = std::max<int64_t>(in_rows, 1);
-    pin.n_pages = 1;
-    PoolSpecDev dev = to_dev_spec(*spec);
-    dev.out = d_out;
-    dev.out_f32 = out_dtype == VRAG_F32;
-    dev.out_fixed = n_out;
-    long long* d_off = nullptr;
-    if (in_rows == 0) {   // empty page (GLOBAL_MEAN of an empty mean-pool): describe it with offsets {0,0}
-      long long h_off[2] = {0, 0};
-      if (cudaMalloc(&d_off, sizeof(h_off)) != cudaSuccess) { rc = fail("cudaMalloc failed"); break; }
-      cudaMemcpyAsync(d_off, h_off, sizeof(h_off), cudaMemcpyHostToDevice, st);
-      pin.in_off = d_off;
-      pin.in_fixed = 0;
-    }
-    cudaDeviceProp prop;
-    cudaGetDeviceProperties(&prop, device);
-    const int mo = static_cast<int>(n_out);
-    rc = launch_pool(pin, 1, spec, &dev, static_cast<int>(in_rows), gh, &mo, prop.multiProcessorCount, st, nullptr);
-    if (rc == 0 && cudaMemcpyAsync(out, d_out, out_b, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = fail("D2H copy failed");
-    if (rc == 0) {
-      cudaError_t e = cudaStreamSynchronize(st);
-      if (e != cudaSuccess) rc = fail("pooling kernel failed: %s", cudaGetErrorString(e));
-    }
-    if (d_off) cudaFree(d_off);
-  } while (0);
-  if (d_in) cudaFree(d_in);
-  if (d_out) cudaFree(d_out);
-  cudaStreamDestroy(st);
-  return rc;
+  PoolPageCtx& cx = g_pool_ctx[device];
+  std::lock_guard<std::mutex> lock(cx.mu);
+  TRY(pool_ctx_ensure(cx, device, in_b, out_b));
+  if (in_b) {
+    memcpy(cx.h_in, in, in_b);   // pinned staging: the copy below is a real async DMA, not a pageable-memory bounce
+    CUDA_OK(cudaMemcpyAsync(cx.d_in, cx.h_in, in_b, cudaMemcpyHostToDevice, cx.st));
+  }
+  PoolInput pin;
+  memset(&pin, 0, sizeof(pin));
+  pin.in = cx.d_in;
+  pin.in_f32 = in_dtype == VRAG_F32;
+  pin.in_fixed = std::max<int64_t>(in_rows, 1);
+  pin.n_pages = 1;
+  PoolSpecDev dev = to_dev_spec(*spec);
+  dev.out = cx.d_out;
+  dev.out_f32 = out_dtype == VRAG_F32;
+  dev.out_fixed = n_out;
+  if (in_rows == 0) {   // empty page (GLOBAL_MEAN of an empty mean-pool): describe it with offsets {0,0}
+    pin.in_off = cx.d_off;
+    pin.in_fixed = 0;
+  }
+  const int mo = static_cast<int>(n_out);
+  TRY(launch_pool(pin, 1, spec, &dev, static_cast<int>(in_rows), gh, &mo, cx.num_sms, cx.st, nullptr));
+  CUDA_OK(cudaMemcpyAsync(cx.h_out, cx.d_out, out_b, cudaMemcpyDeviceToHost, cx.st));
+  cudaError_t e = cudaStreamSynchronize(cx.st);
+  if (e != cudaSuccess) return fail("pooling kernel failed: %s", cudaGetErrorString(e));
+  memcpy(out, cx.h_out, out_b);
+  return 0;
 }
 
 extern "C" int vrag_store_pool(vrag_corpus_t* c, const char* src, int n_specs, const vrag_pool_spec_t* specs,
