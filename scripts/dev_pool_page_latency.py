@@ -29,3 +29,9 @@ bench("weighted_row_smoothing gaussian k=3 (32 rows)", lambda: GP.weighted_row_s
 bench("colpali_experimental (legacy conv) k=3", lambda: GP.colpali_experimental_pooling_from_rows(rows, window_size=3),
       lambda: PO.colpali_experimental_pooling_from_rows(rows, window_size=3))
 bench("global_mean_pooling 1024", lambda: GP.global_mean_pooling(tok), lambda: PO.global_mean_pooling(tok))
+q = rng.standard_normal((20, 128)).astype(np.float32)
+doc = rng.standard_normal((768, 128)).astype(np.float16).astype(np.float32)
+from oracle import maxsim_oracle as MO
+bench("compute_maxsim_score 20 x 768", lambda: GP.compute_maxsim_score(q, doc), lambda: MO.maxsim_score(q, doc))
+docs = [rng.standard_normal((768, 128)).astype(np.float16).astype(np.float32) for _ in range(256)]
+bench("compute_maxsim_batch 256 docs", lambda: GP.compute_maxsim_batch(q, docs), lambda: [MO.maxsim_score(q, d) for d in docs], n=20)

@@ -187,6 +187,7 @@ struct vrag_corpus {
   DevBuf<float> d_sthr;           // sampled top-k: threshold [1]
   DevBuf<int> d_sstate;           // sampled top-k: [0] survivor count, [1] "estimate failed" flag
   int sampled_runs = 0, sampled_fallbacks = 0;
+  DevBuf<float> d_stage_f32;      // fp32 -> fp16 ingest cast: staging for small uploads
   DevBuf<float> d_scores_part;    // partial page scores of the later row chunks of a > 128-token query
   DevBuf<uint8_t> d_qimg;
   DevBuf<unsigned long long> d_keys_a, d_keys_b;
@@ -276,6 +277,7 @@ extern "C" int vrag_corpus_destroy(vrag_corpus_t* c) {
   c->d_scores.release();
   c->d_out_scores.release();
   c->d_scores_part.release();
+  c->d_stage_f32.release();
   c->d_skeys.release();
   c->d_sthr.release();
   c->d_sstate.release();
@@ -406,6 +408,15 @@ static int alloc_store(vrag_corpus* c, const char* name, int64_t total_rows, Sto
   if (!name || !*name) return fail("store name is empty");
   auto it = c->stores.find(name);
   if (it != c->stores.end()) {
+    if (total_rows > 0 && it->second.cap_rows >= total_rows &&
+        (it->second.cap_rows <= (1ll << 18) || it->second.cap_rows <= 4 * total_rows)) {   // never pin >4x (or >64 MB) of slack
+      // replacing a store by one that fits its buffers (the scratch store of compute_maxsim_score / _batch is rewritten on
+      // every call): keep the row / scale allocations; finish_store rebuilds page tables and tensor maps
+      it->second.total_rows = total_rows;
+      it->second.h_offsets.clear();
+      *out = &it->second;
+      return 0;
+    }
     free_store(it->second);
     c->stores.erase(it);
   }
@@ -439,7 +450,13 @@ static int upload_rows(vrag_corpus* c, __half* dst, float* dst_inv, const void* 
     const size_t chunk = size_t(32) << 20;  // elements per staging chunk
     float* tmp = nullptr;
     const float* src_base = static_cast<const float*>(rows);
-    if (!rows_on_device) CUDA_OK(cudaMalloc(&tmp, std::min(chunk, n_el) * sizeof(float)));
+    const bool small = !rows_on_device && n_el <= (size_t(1) << 22);   // <= 16 MB: the handle's persistent staging buffer
+    if (small) {
+      TRY(c->d_stage_f32.ensure(n_el));
+      tmp = c->d_stage_f32.p;
+    } else if (!rows_on_device) {
+      CUDA_OK(cudaMalloc(&tmp, std::min(chunk, n_el) * sizeof(float)));
+    }
     for (size_t o = 0; o < n_el; o += chunk) {
       const size_t n = std::min(chunk, n_el - o);
       const float* src = src_base + o;
@@ -454,11 +471,11 @@ static int upload_rows(vrag_corpus* c, __half* dst, float* dst_inv, const void* 
         e = cudaStreamSynchronize(c->stream);
       }
       if (e != cudaSuccess) {
-        if (tmp) cudaFree(tmp);
+        if (tmp && !small) cudaFree(tmp);
         return fail("fp32 -> fp16 store cast failed: %s", cudaGetErrorString(e));
       }
     }
-    if (tmp) cudaFree(tmp);
+    if (tmp && !small) cudaFree(tmp);
   }
   const long long threads = n_rows * 16;
   inv_norm_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, c->stream>>>(dst, n_rows, dst_inv);

@@ -14,6 +14,7 @@ instead of an embedder object, since model inference is out of scope).
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Any, Dict, List, Literal, Optional, Sequence, Union
 
 import numpy as np
@@ -274,13 +275,28 @@ def global_mean_pooling(embedding, output_dtype=None) -> np.ndarray:
 
 
 # ------------------------------------------------------------------------------------------------ a1 / a2
-def _page_scores(query_embedding, docs: Sequence[np.ndarray], normalize: bool) -> List[float]:
+_scratch = {}             # device -> GpuCorpus kept for the per-call scoring functions below
+_scratch_lock = threading.Lock()
+
+
+def _scratch_corpus():
+    """One long-lived corpus handle per device for compute_maxsim_score / compute_maxsim_batch: creating a handle
+    (stream, events, pinned staging, device-property query) costs milliseconds, a per-pair score must not."""
     from ..corpus import GpuCorpus
 
-    lens = [int(np.asarray(d).shape[0]) for d in docs]
-    rows = np.concatenate([_to_host_rows(d) for d in docs], axis=0)
+    c = _scratch.get(DEVICE)
+    if c is None:
+        c = _scratch[DEVICE] = GpuCorpus(DEVICE)
+    return c
+
+
+def _page_scores(query_embedding, docs: Sequence[np.ndarray], normalize: bool) -> List[float]:
+    mats = [_to_host_rows(d) for d in docs]
+    lens = [int(m.shape[0]) for m in mats]
+    rows = mats[0] if len(mats) == 1 else np.concatenate(mats, axis=0)
     q = np.asarray(query_embedding, dtype=np.float32)
-    with GpuCorpus(DEVICE) as c:
+    with _scratch_lock:
+        c = _scratch_corpus()
         c.add_store("docs", rows, page_offsets=np.concatenate([[0], np.cumsum(lens)]))
         return [float(s) for s in c.score("docs", q, normalize=normalize)]
 
