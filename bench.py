@@ -455,6 +455,11 @@ def run_extras(corpus, args, peak, kern_ms):
     pages = corpus.n_pages("initial")
     out["exhaustive_batched"] = {"queries_per_pass": 4, "ms_per_pass": ms, "page_scorings_per_s": 4 * pages / (ms * 1e-3),
                                  "speedup_vs_single_query": 4 * kern_ms / ms}
+    corpus.search_multistage_batch([("initial", False, TOP_K)], q4, fp16_query=True)
+    corpus.search_multistage_batch([("initial", False, TOP_K)], q4, fp16_query=True)
+    ms16 = corpus.last_timing_ms()[0]
+    out["exhaustive_batched"]["fp16_query_ms_per_pass"] = ms16     # opt-in VRAG_Q_FP16: half the tensor work (power-limited scan)
+    out["exhaustive_batched"]["fp16_query_page_scorings_per_s"] = 4 * pages / (ms16 * 1e-3)
     for nm in ("initial", "mean_pooling"):
         corpus.drop_store(nm)
     # ---- cfg0: the reference's own CPU-runnable case, in full on both sides (ColSmol-shaped, exact top-10)

@@ -534,6 +534,18 @@ def test_fp16_query_flag_is_inside_the_parity_gate(corpus):
     np.testing.assert_allclose(exact, want, rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(out, want, rtol=5e-4)
     assert np.abs(out - want).max() > 0          # it really is the reduced-precision path
+    # the same opt-in through the Python methods: single, multi-stage and batched calls
+    np.testing.assert_array_equal(corpus.score("fq", q, fp16_query=True), out)
+    s16, i16 = corpus.search("fq", q, 10, fp16_query=True)
+    np.testing.assert_allclose(s16, np.sort(want)[::-1][:10], rtol=5e-4)
+    ms = corpus.search_multistage([("fq", False, 20), ("fq", False, 5)], q, fp16_query=True)
+    np.testing.assert_allclose(ms[1][0], np.sort(want)[::-1][:5], rtol=5e-4)
+    qs = [q, rng.standard_normal((9, 128)).astype(np.float32), rng.standard_normal((31, 128)).astype(np.float32)]
+    b16 = corpus.search_multistage_batch([("fq", False, 8)], qs, fp16_query=True)
+    bex = corpus.search_multistage_batch([("fq", False, 8)], qs)
+    for a, b in zip(b16, bex):
+        np.testing.assert_allclose(a[0][0], b[0][0], rtol=5e-4)
+        assert np.abs(a[0][0] - b[0][0]).max() > 0
     corpus.drop_store("fq")
 
 

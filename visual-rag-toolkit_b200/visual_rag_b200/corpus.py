@@ -283,8 +283,12 @@ class GpuCorpus:
         normalize: bool = True,
         pool_query: bool = False,
         candidate_ids: Optional[Sequence[int]] = None,
+        fp16_query: bool = False,
     ) -> np.ndarray:
-        """MaxSim score of every page (or of the listed global page ids). fp32 [n]."""
+        """MaxSim score of every page (or of the listed global page ids). fp32 [n].
+        fp16_query (all scoring methods): opt-in VRAG_Q_FP16 — contract the query as plain fp16 instead of the exact
+        hi/lo pair: scores move by < 1e-4 relative (inside the 1e-3 parity gate), scans of stores with > 128 rows per
+        page do half the tensor work (+2-3 % single-query, +15-19 % for 4-query dense batches, both power-limited)."""
         q = _as_f32_query(query)
         if candidate_ids is None:
             n = self.n_pages(name)
@@ -297,7 +301,7 @@ class GpuCorpus:
         N.check(
             self._lib.vrag_score(
                 self._h, name.encode(), q.ctypes.data_as(C.POINTER(C.c_float)), q.shape[0],
-                query_flags(normalize, pool_query), cand_p, n_cand, out.ctypes.data_as(C.POINTER(C.c_float)),
+                query_flags(normalize, pool_query, fp16_query), cand_p, n_cand, out.ctypes.data_as(C.POINTER(C.c_float)),
             )
         )
         return out
@@ -310,6 +314,7 @@ class GpuCorpus:
         normalize: bool = True,
         pool_query: bool = False,
         candidate_ids: Optional[Sequence[int]] = None,
+        fp16_query: bool = False,
     ) -> Tuple[np.ndarray, np.ndarray]:
         """Top-k pages by MaxSim: (scores fp32 [m], global page ids int64 [m]), m <= k, sorted by score
         descending, ties by lower id."""
@@ -329,7 +334,7 @@ class GpuCorpus:
         N.check(
             self._lib.vrag_search(
                 self._h, name.encode(), q.ctypes.data_as(C.POINTER(C.c_float)), q.shape[0],
-                query_flags(normalize, pool_query), cand_p, n_cand, k,
+                query_flags(normalize, pool_query, fp16_query), cand_p, n_cand, k,
                 scores.ctypes.data_as(C.POINTER(C.c_float)), ids.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(cnt),
             )
         )
@@ -343,6 +348,7 @@ class GpuCorpus:
         normalize: bool = True,
         stage_queries: Optional[Sequence] = None,
         candidate_ids: Optional[Sequence[int]] = None,
+        fp16_query: bool = False,
     ) -> List[Tuple[np.ndarray, np.ndarray]]:
         """Fused multi-stage search: stages = [(store name, pool_query, k), ...]; stage s is restricted to
         the survivors of stage s-1 (stage 0 to `candidate_ids` if given). One host synchronisation.
@@ -368,7 +374,7 @@ class GpuCorpus:
             n_cand = cand.size
             cand_p = cand.ctypes.data_as(C.POINTER(C.c_int64))
         names = (C.c_char_p * ns)(*[s[0].encode() for s in stages])
-        flags = (C.c_uint32 * ns)(*[query_flags(normalize, bool(s[1])) for s in stages])
+        flags = (C.c_uint32 * ns)(*[query_flags(normalize, bool(s[1]), fp16_query) for s in stages])
         ks = (C.c_int * ns)(*[int(s[2]) for s in stages])
         total = int(sum(int(s[2]) for s in stages))
         scores = np.empty((total,), dtype=np.float32)
@@ -397,6 +403,7 @@ class GpuCorpus:
         stage_queries: Optional[Sequence[Sequence]] = None,
         as_arrays: bool = False,
         final_only: bool = False,
+        fp16_query: bool = False,
     ):
         """`search_multistage` for a batch of independent queries in ONE native call / host synchronisation
         (BASELINE configs[2]: 256 queries). queries: sequence of [Q_b,128] matrices (ragged). stage_queries:
@@ -432,7 +439,7 @@ class GpuCorpus:
             rows = np.ascontiguousarray(np.concatenate(mats, axis=0))
             offs = np.ascontiguousarray(np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])]).astype(np.int32))
         names = (C.c_char_p * ns)(*[s[0].encode() for s in stages])
-        flags = (C.c_uint32 * ns)(*[query_flags(normalize, bool(s[1])) for s in stages])
+        flags = (C.c_uint32 * ns)(*[query_flags(normalize, bool(s[1]), fp16_query) for s in stages])
         ks = [int(s[2]) for s in stages]
         ks_c = (C.c_int * ns)(*ks)
         if final_only:
