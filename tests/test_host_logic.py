@@ -241,3 +241,79 @@ def test_batched_retriever_results_from_columnar_client_lists():
     assert corpus.calls[-1][2] is not None and corpus.calls[-1][2][0][0].shape == (1, 128)
     with pytest.raises(ValueError):
         plain.query_multistage_batch_final(usings=["initial"], limits=[3])
+
+
+class _ListCorpus:
+    """Host-side stand-in for the store methods GpuIndexer drives (append / replace / page ranges)."""
+
+    page_base = 0
+
+    def __init__(self):
+        self.stores = {}
+        self.log = []
+
+    def has_store(self, name):
+        return name in self.stores
+
+    def n_pages(self, name):
+        return len(self.stores[name])
+
+    def page_range(self, name, local_page):
+        rows = [m.shape[0] for m in self.stores[name]]
+        return int(sum(rows[:local_page])), int(rows[local_page])
+
+    def append_store(self, name, rows, page_offsets=None, fixed_rows=0):
+        off = np.asarray(page_offsets)
+        self.stores.setdefault(name, []).extend(rows[off[i]:off[i + 1]] for i in range(len(off) - 1))
+        self.log.append(("append", name, len(off) - 1))
+
+    def replace_pages(self, name, local_pages, rows, page_offsets):
+        off = np.asarray(page_offsets)
+        for j, pg in enumerate(local_pages):
+            assert self.stores[name][pg].shape == rows[off[j]:off[j + 1]].shape
+            self.stores[name][pg] = rows[off[j]:off[j + 1]]
+        self.log.append(("replace", name, list(local_pages)))
+
+    def drop_store(self, name):
+        del self.stores[name]
+
+
+def test_indexer_upsert_host_logic():
+    """GpuIndexer.upload_batch without a GPU: client.upsert semantics (qdrant_indexer.py:459-507) — new ids appended, existing
+    ids replaced in place with their payload, the last occurrence of an id inside a batch wins, and every refusal (shape
+    change, missing named vector) happens before anything is written."""
+    from visual_rag_b200.indexing import GpuIndexer
+
+    def point(i, t, r, ver, with_exp=True):
+        g = np.random.default_rng(100 * ver + i)
+        p = {"id": f"id{i}", "visual_embedding": g.standard_normal((t, 128)).astype(np.float32),
+             "tile_pooled_embedding": g.standard_normal((r, 128)).astype(np.float32), "metadata": {"i": i, "ver": ver}}
+        if with_exp:
+            p["experimental_pooled_embedding"] = {"experimental_pooling": g.standard_normal((r, 128)).astype(np.float32)}
+        return p
+
+    c = _ListCorpus()
+    idx = GpuIndexer(c, "c")
+    assert idx.create_collection() and idx.upload_batch([]) == 0
+    assert idx.upload_batch([point(i, 10 + i, 3, 1) for i in range(4)]) == 4
+    assert c.n_pages("initial") == 4 and set(c.stores) == {"initial", "mean_pooling", "global_pooling", "experimental_pooling"}
+    assert c.stores["initial"][2].dtype == np.float16                       # store dtype cast
+    np.testing.assert_array_equal(c.stores["global_pooling"][1],           # global = mean(tile_pooled) fallback, 417-421
+                                  point(1, 11, 3, 1)["tile_pooled_embedding"].mean(axis=0).reshape(1, -1).astype(np.float16))
+    c.log.clear()
+    batch = [point(2, 12, 3, 2), point(7, 30, 5, 2), point(2, 12, 3, 3), point(0, 10, 3, 2)]
+    assert idx.upload_batch(batch) == 4
+    assert ("replace", "initial", [2, 0]) in c.log and ("append", "initial", 1) in c.log
+    assert idx.client._ids == ["id0", "id1", "id2", "id3", "id7"]
+    assert [p["ver"] for p in idx.client._payloads] == [2, 1, 3, 1, 2]          # last occurrence of id2 (ver 3) won
+    np.testing.assert_array_equal(c.stores["initial"][2], point(2, 12, 3, 3)["visual_embedding"].astype(np.float16))
+    assert idx.check_exists("id7") and not idx.check_exists("id9") and idx.get_existing_ids() == set(idx.client._ids)
+    before = [m.copy() for m in c.stores["initial"]]
+    c.log.clear()
+    with pytest.raises(ValueError, match="equal shapes"):
+        idx.upload_batch([point(8, 9, 2, 4), point(1, 99, 3, 4)])              # id1 changes its token count
+    with pytest.raises(ValueError, match="missing from some points"):
+        idx.upload_batch([point(9, 9, 2, 4), point(10, 9, 2, 4, with_exp=False)])
+    assert c.log == [] and len(idx.client._ids) == 5 and all(np.array_equal(a, b) for a, b in zip(before, c.stores["initial"]))
+    assert idx.create_collection() is False and idx.create_collection(force_recreate=True) and not c.stores
+    assert idx.client._ids == []
