@@ -379,6 +379,11 @@ def test_sharded_searcher_single_rank_matches_corpus_api(corpus):
     sa, ia = s.search("initial", q, 7)
     sb, ib = corpus.search("initial", q, 7)
     assert ia.tolist() == ib.tolist() and np.array_equal(sa, sb)
+    q_long = CS.query_rows(1301, 200)                 # longer than the searcher's initial staging (128 rows): it grows
+    a = s.search_multistage(stages, q_long)
+    b = corpus.search_multistage(stages, q_long)
+    for (sa, ia), (sb, ib) in zip(a, b):
+        assert ia.tolist() == ib.tolist() and np.allclose(sa, sb, rtol=1e-6)
 
 
 # ---------------------------------------------------------------------------------------------------------------
