@@ -44,6 +44,7 @@ class ShardedSearcher:
             self._q_pin = self._q_pin.pin_memory()
         self._scores: Optional[torch.Tensor] = None
         self._bufs = {}
+        self._h_out = None      # pinned (scores, ids) staging of the host-facing search
 
     # ------------------------------------------------------------------ helpers
     def _buf(self, key: str, n: int, dtype) -> torch.Tensor:
@@ -70,7 +71,7 @@ class ShardedSearcher:
         return n
 
     def _stage(self, name: str, n_q: int, flags: int, cand: Optional[torch.Tensor], k: int,
-               tag: str) -> Tuple[torch.Tensor, torch.Tensor]:
+               tag: str, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """One stage on the device: local scan -> local top-k -> all-gather -> merged global top-k.
         Returns (scores[k], global ids[k]) identical on every rank; invalid slots are (-inf, -1)."""
         c = self.corpus
@@ -84,12 +85,14 @@ class ShardedSearcher:
             # candidate stage: every candidate is owned by exactly one shard (-inf elsewhere) -> one max-all-reduce of
             # the score vector, then the same top-k on every rank: ties keep candidate order, exactly like one shard
             self.dist.all_reduce(scores, op=self.dist.ReduceOp.MAX, group=self.group)
-            ms = self._buf(tag + "_ms", k, torch.float32)
-            mi = self._buf(tag + "_mi", k, torch.int64)
+            ms, mi = out if out is not None else (self._buf(tag + "_ms", k, torch.float32), self._buf(tag + "_mi", k, torch.int64))
             c.topk_dev(scores.data_ptr(), cand.data_ptr(), 0, n_items, k, ms.data_ptr(), mi.data_ptr(), stream)
             return ms, mi
-        ls = self._buf(tag + "_ls", k, torch.float32)
-        li = self._buf(tag + "_li", k, torch.int64)
+        if self.world == 1 and out is not None:
+            ls, li = out
+        else:
+            ls = self._buf(tag + "_ls", k, torch.float32)
+            li = self._buf(tag + "_li", k, torch.int64)
         c.topk_dev(scores.data_ptr(), cand.data_ptr() if cand is not None else 0, c.page_base, n_items, k,
                    ls.data_ptr(), li.data_ptr(), stream)
         if self.world == 1:
@@ -98,8 +101,7 @@ class ShardedSearcher:
         gi = self._buf(tag + "_gi", k * self.world, torch.int64)
         self.dist.all_gather_into_tensor(gs, ls, group=self.group)
         self.dist.all_gather_into_tensor(gi, li, group=self.group)
-        ms = self._buf(tag + "_ms", k, torch.float32)
-        mi = self._buf(tag + "_mi", k, torch.int64)
+        ms, mi = out if out is not None else (self._buf(tag + "_ms", k, torch.float32), self._buf(tag + "_mi", k, torch.int64))
         # merge: keys are (score, position in the gathered list); rank-major gather order + per-rank id order
         # make "lower position" == "lower global id" among equal scores of different ranks only if shards are
         # id-ordered by rank, which contiguous page ranges guarantee.
@@ -108,27 +110,49 @@ class ShardedSearcher:
 
     # ------------------------------------------------------------------ public API
     def search_multistage_device(self, stages: Sequence[Tuple[str, bool, int]], n_q: int,
-                                 normalize: bool = True) -> List[Tuple[torch.Tensor, torch.Tensor]]:
-        """All stages on the device, no host synchronisation. The query must already be uploaded."""
+                                 normalize: bool = True, packed_out: bool = False) -> List[Tuple[torch.Tensor, torch.Tensor]]:
+        """All stages on the device, no host synchronisation. The query must already be uploaded.
+        packed_out: the stages' merged lists are views into ONE scores and ONE ids tensor (stage s at
+        [sum(k[:s]), sum(k[:s+1]))), so the host needs two copies for the whole search instead of two per stage."""
         out = []
         cand = None
+        total = sum(int(k) for _, _, k in stages)
+        all_s = self._buf("out_s", total, torch.float32) if packed_out else None
+        all_i = self._buf("out_i", total, torch.int64) if packed_out else None
+        off = 0
         for s, (name, pool, k) in enumerate(stages):
-            sc, ids = self._stage(name, n_q, query_flags(normalize, pool), cand, int(k), f"s{s}")
+            k = int(k)
+            dst = (all_s[off:off + k], all_i[off:off + k]) if packed_out else None
+            sc, ids = self._stage(name, n_q, query_flags(normalize, pool), cand, k, f"s{s}", dst)
             out.append((sc, ids))
             cand = ids
+            off += k
         return out
 
     def search_multistage(self, stages: Sequence[Tuple[str, bool, int]], query,
                           normalize: bool = True) -> List[Tuple[np.ndarray, np.ndarray]]:
         """Host-facing: uploads the query, runs the stages, reads back every stage's merged list."""
         n_q = self.upload_query(query)
-        dev = self.search_multistage_device(stages, n_q, normalize)
-        res = []
-        for sc, ids in dev:
-            s = sc.cpu().numpy()
-            i = ids.cpu().numpy()
+        self.search_multistage_device(stages, n_q, normalize, packed_out=True)
+        total = sum(int(k) for _, _, k in stages)
+        if not self.on_gpu:
+            s_all, i_all = self._bufs["out_s"][:total].numpy().copy(), self._bufs["out_i"][:total].numpy().copy()
+        else:
+            # two async copies into pinned staging and ONE synchronisation for all stages
+            if self._h_out is None or self._h_out[0].numel() < total:
+                self._h_out = (torch.empty((max(total, 1),), dtype=torch.float32).pin_memory(),
+                               torch.empty((max(total, 1),), dtype=torch.int64).pin_memory())
+            hs, hi = self._h_out[0][:total], self._h_out[1][:total]
+            hs.copy_(self._bufs["out_s"][:total], non_blocking=True)
+            hi.copy_(self._bufs["out_i"][:total], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            s_all, i_all = hs.numpy().copy(), hi.numpy().copy()
+        res, off = [], 0
+        for _, _, k in stages:
+            s, i = s_all[off:off + int(k)], i_all[off:off + int(k)]
             keep = (i >= 0) & np.isfinite(s)
             res.append((s[keep], i[keep]))
+            off += int(k)
         return res
 
     def search(self, name: str, query, k: int, normalize: bool = True, pool_query: bool = False):
