@@ -227,6 +227,14 @@ def run_ours(args):
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
 
+    lib = os.path.join(ROOT, "visual-rag-toolkit_b200", "visual_rag_b200", "libvrag_b200.so")
+    if not os.path.exists(lib):   # git-ignored build artefact: a bare checkout builds it once (rank 0), the others wait
+        if local_rank == 0:
+            import __graft_entry__
+
+            __graft_entry__.build()
+        if dist is not None:
+            dist.barrier()
     from visual_rag_b200.corpus import GpuCorpus
     from visual_rag_b200.distributed import ShardedSearcher
 
