@@ -225,6 +225,67 @@ int vrag_pool_page(int device, const vrag_pool_spec_t* spec, const void* in, int
 int vrag_store_pool(vrag_corpus_t* c, const char* src, int n_specs, const vrag_pool_spec_t* specs,
                     const char* const* dst_names, const int32_t* grid_hw);
 
+/* ------------------------------------------------------------------ multi-GPU: page-sharded corpus
+ * One process per GPU. Every rank owns a contiguous page range of every named store: its vrag_corpus_t is created with
+ * page_base = the first global page id of its range. The reference itself is single-process; its scale-out is Qdrant's
+ * server-side sharding behind the SAME query_points call (two_stage.py:162-178, three_stage.py:103-157) — these entry points
+ * give the GPU backend that property.
+ *
+ * After vrag_comm_init the search entry points of the handle — vrag_search, vrag_search_multistage,
+ * vrag_search_multistage_batch(_final), vrag_search_multistage_dev — are COLLECTIVE: all ranks call them with the same
+ * queries and stage arguments and every rank receives the same merged GLOBAL lists (score descending, ties -> lower global
+ * page id, i.e. exactly the single-shard order). The exchange is ONE collective per stage:
+ *   - a stage that scans the store (or a rank-local candidate list, see below): each rank's local top-k travels as packed
+ *     16-byte vrag_hit_t entries, written by the top-k kernel straight into the send buffer, in one all-gather
+ *     (k = 10: 160 B per rank), followed by the same deterministic merge on every rank;
+ *   - a stage restricted to the previous stage's (replicated) survivors: every candidate is owned by exactly one rank
+ *     (-inf elsewhere), so one max-all-reduce of the candidate score vector completes it and ties keep candidate order.
+ * cand_ids of a collective search is RANK-LOCAL: each rank lists (in ascending id order) the pages of its own range that
+ * pass the filter; ids of other ranks are ignored. Reference semantics are kept: the global top-prefetch_k is formed
+ * before the rerank (two_stage.py:161-178).
+ * Transport: NCCL (resolved at run time with dlopen("libnccl.so.2"), so that a process that already loaded a NCCL — e.g.
+ * through torch — shares it; the library has no link-time NCCL dependency).                                          */
+typedef struct vrag_hit {
+  float score;
+  uint32_t aux;   /* bit 0: this rank's list came from a top-k estimate that missed; the search is repeated exactly */
+  int64_t id;     /* global page id; < 0: padding (the rank had fewer than k results) */
+} vrag_hit_t;
+
+#define VRAG_UNIQUE_ID_BYTES 128
+/* Rank 0 creates the communicator id (ncclGetUniqueId); the host distributes the 128 bytes to the other ranks through any
+ * channel it has (MPI, a TCP store, a file) and every rank calls vrag_comm_init. Needs no corpus handle.               */
+int vrag_comm_unique_id(void* out_id128);
+/* Join the communicator (collective: all nranks ranks call it). The handle's device is the rank's GPU.              */
+int vrag_comm_init(vrag_corpus_t* c, int rank, int nranks, const void* unique_id128);
+int vrag_comm_info(vrag_corpus_t* c, int* rank, int* nranks);
+int vrag_comm_destroy(vrag_corpus_t* c);
+
+/* The building blocks of a collective stage, for hosts that drive the stages themselves (device pointers, caller's stream):
+ * local scan + local top-k as packed entries -> all-gather -> merge.
+ * vrag_stage_hits_dev: score store `name` (every page, or cand_ids_dev) with the device query and write this rank's top-k
+ *   as k packed entries. vrag_allgather_topk: gathered_dev[r][list][k] <- rank r's local_dev[list][k], one collective for
+ *   n_lists lists (batched queries). vrag_merge_hits_dev: merge n_src gathered lists of k_src entries per list into the
+ *   global top-k (scores/ids [n_lists][k]); *flag_dev is OR-ed with 1 if any rank flagged a missed estimate.          */
+int vrag_stage_hits_dev(vrag_corpus_t* c, const char* name, const float* query_dev, int n_query_rows, uint32_t flags,
+                        const int64_t* cand_ids_dev, int64_t n_cand, int k, vrag_hit_t* out_hits_dev, void* stream);
+int vrag_allgather_topk(vrag_corpus_t* c, const vrag_hit_t* local_dev, int n_lists, int k, vrag_hit_t* gathered_dev,
+                        void* stream);
+int vrag_merge_hits_dev(vrag_corpus_t* c, const vrag_hit_t* gathered_dev, int n_src, int n_lists, int k_src, int k,
+                        float* out_scores_dev, int64_t* out_ids_dev, int* flag_dev, void* stream);
+/* In-place max-all-reduce of a device fp32 vector (the candidate-stage exchange).                                   */
+int vrag_allreduce_max_dev(vrag_corpus_t* c, float* scores_dev, int64_t n, void* stream);
+
+/* Device-resident multi-stage search: query and outputs are device pointers, everything is enqueued on `stream` and the
+ * call returns without synchronising (collective when the handle has a communicator). Stage s writes ks[s] entries at
+ * [sum(ks[:s]), ...) of out_scores_dev / out_ids_dev; unused slots are (-inf, -1). Exact: no sampled top-k.          */
+int vrag_search_multistage_dev(vrag_corpus_t* c, int n_stages, const char* const* names, const uint32_t* flags,
+                               const int* ks, const float* query_dev, int n_query_rows, const int* q_offsets,
+                               float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+
+/* Device time (microseconds, CUDA events) of each collective of the most recent host-facing search on this handle, in
+ * issue order; *n receives how many there were (<= capacity written).                                               */
+int vrag_last_comm_timing(vrag_corpus_t* c, float* out_us, int capacity, int* n);
+
 /* ------------------------------------------------------------------ measurement helpers */
 /* Device-side time (ms, CUDA events on the library stream) of the most recent vrag_search /
  * vrag_search_multistage on this corpus: [0] whole call, [1] dominant scan kernel only.            */

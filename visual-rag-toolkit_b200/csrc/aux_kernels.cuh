@@ -237,6 +237,16 @@ __global__ void synth_rows_kernel(__half* __restrict__ rows, float* __restrict__
 // writes (score, id) pairs.
 constexpr int kTopkMaxK = 4096;
 
+// Packed top-k entry exchanged between shards (== vrag_hit_t, include/vrag_b200.h): one 16-byte record per result so
+// that a shard's whole local list travels as ONE message. aux bit 0: the list came from a top-k estimate that missed
+// (sampled threshold / prefilter) and the search must be repeated exactly; id < 0 marks padding.
+struct __align__(16) Hit {
+  float score;
+  uint32_t aux;
+  long long id;
+};
+constexpr uint32_t kHitMiss = 1u;
+
 __device__ __forceinline__ uint32_t score_to_ord(float f) {
   if (f != f) return 0u;  // NaN sorts last
   const uint32_t u = __float_as_uint(f);
@@ -269,6 +279,13 @@ struct TopkArgs {
   const int* n_dyn;           // optional per-query element count (device); overrides n / n_total
   int* fail_flag;             // optional (with n_dyn): set when a query's count is < need or > n (= the list capacity):
   int need;                   //   the sampled / prefiltered candidate list is unusable and the caller must redo exactly
+  // ---- sharded search (exchange of per-shard lists)
+  const Hit* hits_in;         // merge input: gathered per-shard lists instead of scores / keys. Element i of query b is
+  int hits_k_src;             //   hits_in[(i / hits_k_src) * hits_rank_stride + b * hits_k_src + i % hits_k_src]
+  long long hits_rank_stride; //   ([rank][query][k_src] as an all-gather leaves them); ties -> lower i = lower rank = lower
+                              //   global id; padding entries (id < 0) are ignored; a set kHitMiss bit raises fail_flag
+  Hit* out_hits;              // final level: also write the results as packed entries [k] (the all-gather send buffer)
+  const int* aux_src;         // optional device flag OR-ed into bit 0 (kHitMiss) of every out_hits entry
 };
 
 template <int CHUNK, int THREADS>
@@ -287,7 +304,14 @@ __global__ void __launch_bounds__(THREADS, 1) topk_kernel(const TopkArgs a) {
     const long long i = base + j;
     unsigned long long key = 0ull;
     if (i < n_in) {
-      if (a.scores) {
+      if (a.hits_in) {
+        const long long r = i / a.hits_k_src;
+        const Hit h = a.hits_in[r * a.hits_rank_stride + b * a.hits_k_src + (i - r * a.hits_k_src)];
+        if (h.id >= 0)
+          key = (static_cast<unsigned long long>(score_to_ord(h.score)) << 32) |
+                static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<uint32_t>(i));
+        if ((h.aux & kHitMiss) && a.fail_flag) atomicOr(a.fail_flag, 1);
+      } else if (a.scores) {
         key = (static_cast<unsigned long long>(score_to_ord(a.scores[b * a.in_stride + i])) << 32) |
               static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<uint32_t>(i));
       } else {
@@ -368,17 +392,37 @@ __global__ void __launch_bounds__(THREADS, 1) topk_kernel(const TopkArgs a) {
   } else {
     const long long nvalid = n_real < a.k ? n_real : a.k;
     const long long ob = b * a.out_stride;
+    uint32_t aux = 0u;
+    if (a.out_hits) {
+      if (a.n_dyn && a.fail_flag && ((a.n_dyn[b] < a.need) || (a.n_dyn[b] > a.n))) aux |= kHitMiss;
+      if (a.aux_src && *a.aux_src) aux |= kHitMiss;
+    }
     for (int j = threadIdx.x; j < a.k; j += THREADS) {
-      if (j < nvalid) {
-        const unsigned long long key = skeys[j];
+      const unsigned long long key = skeys[j];
+      float sc = -INFINITY;
+      long long id = -1;
+      int pos = -1;
+      if (j < nvalid && key != 0ull) {   // key 0: padding of a gathered list
         const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
-        a.out_scores[ob + j] = ord_to_score(static_cast<uint32_t>(key >> 32));
-        a.out_ids[ob + j] = a.ids ? a.ids[b * a.ids_stride + idx] : (a.id_base + idx);
-        if (a.out_pos) a.out_pos[ob + j] = static_cast<int>(idx);
-      } else {
-        a.out_scores[ob + j] = -INFINITY;
-        a.out_ids[ob + j] = -1;
-        if (a.out_pos) a.out_pos[ob + j] = -1;
+        sc = ord_to_score(static_cast<uint32_t>(key >> 32));
+        if (a.hits_in) {
+          const long long r = idx / a.hits_k_src;
+          id = a.hits_in[r * a.hits_rank_stride + b * a.hits_k_src + (idx - r * a.hits_k_src)].id;
+        } else {
+          id = a.ids ? a.ids[b * a.ids_stride + idx] : (a.id_base + idx);
+        }
+        pos = static_cast<int>(idx);
+        if (id < 0) sc = -INFINITY;   // padding that reached the output (fewer than k real entries)
+      }
+      if (a.out_scores) a.out_scores[ob + j] = sc;
+      if (a.out_ids) a.out_ids[ob + j] = id;
+      if (a.out_pos) a.out_pos[ob + j] = pos;
+      if (a.out_hits) {
+        Hit h;
+        h.score = sc;
+        h.aux = aux;
+        h.id = id;
+        a.out_hits[ob + j] = h;
       }
     }
     if (a.out_count && threadIdx.x == 0) a.out_count[b] = static_cast<int>(nvalid);
@@ -768,6 +812,27 @@ __global__ void __launch_bounds__(256) gather_stage_scores_kernel(const long lon
     }
   }
   if (lane == 0) out[w * out_stride + out_col] = found;
+}
+
+// Gathered per-shard lists that are too long for one sort block (n_src * k_src > 8192): unpack them into plain score / id
+// arrays [n_lists][n_src * k_src] for the radix-select path. Padding entries get a NaN score (the lowest key), so that
+// they sort behind every real entry including real -inf ones; a kHitMiss bit raises the flag.
+__global__ void hits_unpack_kernel(const Hit* __restrict__ hits, int n_src, int n_lists, int k_src, float* __restrict__ scores,
+                                   long long* __restrict__ ids, int* __restrict__ fail_flag) {
+  const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long per = static_cast<long long>(n_src) * k_src;
+  if (t >= per * n_lists) return;
+  const long long b = t / per, i = t - b * per;
+  const long long r = i / k_src;
+  const Hit h = hits[(r * n_lists + b) * k_src + (i - r * k_src)];
+  scores[t] = h.id >= 0 ? h.score : __int_as_float(0x7fc00000);
+  ids[t] = h.id;
+  if ((h.aux & kHitMiss) && fail_flag) atomicOr(fail_flag, 1);
+}
+
+__global__ void fill_f32_kernel(float* __restrict__ p, long long n, float v) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) p[i] = v;
 }
 
 __global__ void sel_init_kernel(SelState* st, int k, int batch) {

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <map>
 #include <mutex>
 #include <string>
@@ -13,7 +14,7 @@
 
 #include "../../include/vrag_b200.h"
 #include "aux_kernels.cuh"
-#include "maxsim_scan.cuh"
+#include "scan_launch.h"
 #include "pooling_kernels.cuh"
 
 using namespace vrag;
@@ -45,7 +46,7 @@ static int fail(const char* fmt, ...) {
   } while (0)
 
 extern "C" const char* vrag_last_error(void) { return g_err.c_str(); }
-extern "C" int vrag_abi_version(void) { return 1; }
+extern "C" int vrag_abi_version(void) { return 2; }
 
 // Function attributes (opt-in dynamic shared memory) are per device: every launch site keeps one flag per device of
 // the process. Returns true the first time a site is reached on the current device.
@@ -171,6 +172,35 @@ struct BatchCtx {   // the batch of queries last uploaded to the device
   std::vector<int> max_rows;   // largest query row count per stage
 };
 
+// NCCL, resolved at run time (dlopen): the few entry points the exchange needs, declared here so that the build has no
+// NCCL header / link dependency. ncclUniqueId is a 128-byte struct passed by value; ncclComm_t is an opaque pointer.
+struct NcclId { char internal[VRAG_UNIQUE_ID_BYTES]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static const int kNcclInt8 = 0, kNcclFloat32 = 7, kNcclMax = 2;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+static const int kMaxCommEvents = 24;
+struct CommState {
+  int rank = 0, nranks = 1;
+  void* nccl = nullptr;              // ncclComm_t
+  DevBuf<Hit> send, recv;            // packed local lists / gathered lists
+  DevBuf<float> raw;                 // batched candidate stages: [n_queries][n_cand] scores (max-all-reduced across shards)
+  DevBuf<float> m_scores;            // unpacked gathered lists (very long merges)
+  DevBuf<long long> m_ids;
+  cudaEvent_t ev[2 * kMaxCommEvents] = {nullptr};
+  int n_ev = 0;                      // collectives timed in the current host-facing search
+  bool timing = false;               // record events around collectives (host-facing searches on the library stream)
+  float last_us[kMaxCommEvents] = {0};
+  int last_n = 0;
+};
+
 struct vrag_corpus {
   // One handle = one stream + one set of scratch buffers: entry points serialise on this lock, so a handle may be shared
   // by threads (the reference's ingest runs uploader threads, run_qdrant_beir.py:720-768; ctypes releases the GIL).
@@ -216,6 +246,7 @@ struct vrag_corpus {
   float last_ms[2] = {0, 0};
   int64_t launches = 0;
   bool attrs_set = false;
+  CommState comm;
 };
 
 static const int kOperandRows = 128;    // query rows of one MMA operand image; longer token queries are scored in chunks
@@ -268,6 +299,8 @@ extern "C" int vrag_corpus_create(int device, int64_t page_base, vrag_corpus_t**
   return 0;
 }
 
+static void comm_release(vrag_corpus* c);
+
 extern "C" int vrag_corpus_destroy(vrag_corpus_t* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
@@ -297,6 +330,7 @@ extern "C" int vrag_corpus_destroy(vrag_corpus_t* c) {
   c->d_fcnt.release();
   c->d_stage_sc.release();
   c->d_fkeys.release();
+  comm_release(c);
   if (c->h_flag) cudaFreeHost(c->h_flag);
   if (c->h_qmeta) cudaFreeHost(c->h_qmeta);
   if (c->h_query) cudaFreeHost(c->h_query);
@@ -692,16 +726,24 @@ extern "C" int vrag_store_drop(vrag_corpus_t* c, const char* name) {
 }
 
 // ------------------------------------------------------------------------------------------------ launches
-template <int QP, bool PACKED, bool BSW = false, int QS = QP>
-static int launch_scan_t(vrag_corpus* c, const Store& s, const ScanParams& p, long long n_units, cudaStream_t st) {
-  auto kern = maxsim_scan_kernel<QP, QS, PACKED, BSW>;
-  const size_t smem = ScanCfg<QP>::smem_bytes(PACKED, BSW, QS < QP);
-  static PerDeviceOnce once;
-  if (once.first()) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const unsigned grid = static_cast<unsigned>(std::min<long long>(c->num_sms, n_units));
-  kern<<<grid, ScanCfg<QP>::threads(PACKED, QS < QP), smem, st>>>(p.pad_rows > 0 ? s.tm3d : s.tm128, s.tm32, s.ts128, s.ts32, p);
+// kind: 0 single query (QS == QP), 1 operand switching (BSW), 2 sub-queries (QP == 128, qs in {1, 32})
+static int launch_scan_variant(vrag_corpus* c, const Store& s, const ScanParams& p, long long n_units, cudaStream_t st,
+                               int kind, int qp_or_qs) {
+  ScanLaunch L;
+  L.tm_rows = p.pad_rows > 0 ? &s.tm3d : &s.tm128;
+  L.tm_rows32 = &s.tm32;
+  L.tm_scale128 = &s.ts128;
+  L.tm_scale32 = &s.ts32;
+  L.p = p;
+  L.n_units = n_units;
+  L.num_sms = c->num_sms;
+  L.stream = st;
+  cudaError_t e = kind == 0 ? scan_launch_single(qp_or_qs, s.packed, L)
+                : kind == 1 ? scan_launch_bsw(qp_or_qs, s.packed, L)
+                            : scan_launch_multi(qp_or_qs, s.packed, L);
   c->launches++;
-  CUDA_OK(cudaGetLastError());
+  if (e != cudaSuccess) return fail("scan kernel launch (kind %d, %d, %s) failed: %s", kind, qp_or_qs,
+                                    s.packed ? "packed" : "large", cudaGetErrorString(e));
   return 0;
 }
 
@@ -809,25 +851,7 @@ static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int
     p.hi_only = (((flags & VRAG_Q_FP16) != 0 || knob_hi_only()) && QP >= 16 && !s.packed) ? 1 : 0;
   }
   if (time_kernel) CUDA_OK(cudaEventRecord(c->evk0, st));
-  int r = 0;
-#define VRAG_DISPATCH(QPV)                                                     \
-  case QPV:                                                                    \
-    r = s.packed ? launch_scan_t<QPV, true>(c, s, p, n_units, st)              \
-                 : launch_scan_t<QPV, false>(c, s, p, n_units, st);            \
-    break;
-  switch (QP) {
-    VRAG_DISPATCH(8)
-    VRAG_DISPATCH(16)
-    case 24:
-      r = launch_scan_t<24, false>(c, s, p, n_units, st);
-      break;
-    VRAG_DISPATCH(32)
-    VRAG_DISPATCH(64)
-    VRAG_DISPATCH(128)
-    default:
-      return fail("internal: bad QP %d", QP);
-  }
-#undef VRAG_DISPATCH
+  int r = launch_scan_variant(c, s, p, n_units, st, 0, QP);
   if (r) return r;
   if (time_kernel) CUDA_OK(cudaEventRecord(c->evk1, st));
   return 0;
@@ -861,10 +885,7 @@ static int launch_scan_batch(vrag_corpus* c, const Store& s, const float* d_quer
   p.q_valid_arr = d_qvalid;
   p.n_groups = nq;
   const long long n_units = upg * nq;
-  int r;
-  if (QP == 32) r = s.packed ? launch_scan_t<32, true, true>(c, s, p, n_units, st) : launch_scan_t<32, false, true>(c, s, p, n_units, st);
-  else r = s.packed ? launch_scan_t<64, true, true>(c, s, p, n_units, st) : launch_scan_t<64, false, true>(c, s, p, n_units, st);
-  return r;
+  return launch_scan_variant(c, s, p, n_units, st, 1, QP);
 }
 
 // Dense batched scan: every query scores every page of the store; G = 128/QS queries share each document tile
@@ -935,10 +956,7 @@ static int launch_scan_dense_batch(vrag_corpus* c, const Store& s, const float* 
       p.f_keys = o.keys + static_cast<size_t>(g) * G * o.cap;
       p.f_cap = o.cap;
     }
-    int r;
-    if (QS == 1) r = s.packed ? launch_scan_t<128, true, false, 1>(c, s, p, n_units, st) : launch_scan_t<128, false, false, 1>(c, s, p, n_units, st);
-    else r = s.packed ? launch_scan_t<128, true, false, 32>(c, s, p, n_units, st) : launch_scan_t<128, false, false, 32>(c, s, p, n_units, st);
-    if (r) return r;
+    TRY(launch_scan_variant(c, s, p, n_units, st, 2, QS));
   }
   if (time_kernel) CUDA_OK(cudaEventRecord(c->evk1, st));
   return 0;
@@ -959,7 +977,7 @@ static int launch_topk_sort(vrag_corpus* c, const TopkArgs& a, int batch, cudaSt
 
 static int launch_topk(vrag_corpus* c, const float* d_scores, const long long* d_ids, int64_t id_base, int64_t n,
                        int k, float* out_scores, long long* out_ids, int* out_pos, int* out_count, cudaStream_t st,
-                       int batch = 1, long long ids_stride = 0) {
+                       int batch = 1, long long ids_stride = 0, Hit* out_hits = nullptr, const int* aux_src = nullptr) {
   if (k < 1) return fail("k must be >= 1");
   if (k > kTopkMaxK) return fail("k=%d exceeds the supported maximum %d", k, kTopkMaxK);
   if (n >= (1ll << 32) - 1) return fail("too many items for top-k");
@@ -978,6 +996,8 @@ static int launch_topk(vrag_corpus* c, const float* d_scores, const long long* d
   a.n_total = n;
   a.out_stride = k;
   a.ids_stride = ids_stride;
+  a.out_hits = out_hits;
+  a.aux_src = aux_src;
   long long m = n;   // elements the final sort sees
   if (n > 4096) {
     // ---- radix select: leaves exactly k keys per query in d_keys_a
@@ -1023,7 +1043,8 @@ static int launch_topk(vrag_corpus* c, const float* d_scores, const long long* d
 // Sorted top-k of per-query key lists keys[batch][cap] holding n_dyn[b] valid keys each (cap <= 8192).
 static int launch_topk_keys(vrag_corpus* c, const unsigned long long* keys, const int* n_dyn, int cap, int k,
                             int64_t id_base, float* out_scores, long long* out_ids, cudaStream_t st, int batch,
-                            const long long* ids = nullptr, int* out_count = nullptr, int* fail_flag = nullptr, int need = 0) {
+                            const long long* ids = nullptr, int* out_count = nullptr, int* fail_flag = nullptr, int need = 0,
+                            Hit* out_hits = nullptr, const int* aux_src = nullptr) {
   int k2 = 1;
   while (k2 < k) k2 <<= 1;
   TopkArgs a;
@@ -1042,6 +1063,8 @@ static int launch_topk_keys(vrag_corpus* c, const unsigned long long* keys, cons
   a.fail_flag = fail_flag;
   a.need = need;
   a.out_stride = k;
+  a.out_hits = out_hits;
+  a.aux_src = aux_src;
   const int chunk = cap <= 1024 ? 1024 : (cap <= 2048 ? 2048 : 8192);
   a.k2 = std::min(k2, chunk);
   if (chunk == 8192) TRY((launch_topk_sort<8192, 1024>(c, a, batch, st)));
@@ -1089,7 +1112,7 @@ static SampledPlan plan_sampled_topk(int64_t n, int k) {
 }
 static int launch_topk_sampled(vrag_corpus* c, const float* d_scores, const long long* d_ids, int64_t id_base, int64_t n, int k,
                                float* out_scores, long long* out_ids, int* out_count, int* d_fail_flag, cudaStream_t st,
-                               const SampledPlan& pl) {
+                               const SampledPlan& pl, Hit* out_hits = nullptr) {
   TRY(c->d_skeys.ensure(pl.cap));
   TRY(c->d_sthr.ensure(1));
   TRY(c->d_sstate.ensure(2));
@@ -1109,7 +1132,184 @@ static int launch_topk_sampled(vrag_corpus* c, const float* d_scores, const long
   c->sampled_runs++;
   // the sort kernel also checks the survivor count (k <= count <= cap) and raises the flag otherwise
   return launch_topk_keys(c, c->d_skeys.p, c->d_sstate.p, pl.cap, k, id_base, out_scores, out_ids, st, 1, d_ids, out_count,
-                          d_fail_flag, static_cast<int>(std::min<int64_t>(k, n)));
+                          d_fail_flag, static_cast<int>(std::min<int64_t>(k, n)), out_hits);
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU exchange
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+static int nccl_load() {
+  std::lock_guard<std::mutex> lock(g_nccl_mu);
+  if (g_nccl.lib) return 0;
+  void* h = nullptr;
+  // a bare soname: if the process already loaded a NCCL (torch's bundled one), the dynamic loader hands that one back
+  for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+    h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return fail("NCCL not found (dlopen libnccl.so.2: %s)", dlerror());
+  NcclApi api;
+  api.lib = h;
+#define VRAG_SYM(field, sym)                                                   \
+  *reinterpret_cast<void**>(&api.field) = dlsym(h, sym);                       \
+  if (!api.field) return fail("NCCL symbol %s not found", sym);
+  VRAG_SYM(GetUniqueId, "ncclGetUniqueId")
+  VRAG_SYM(CommInitRank, "ncclCommInitRank")
+  VRAG_SYM(CommDestroy, "ncclCommDestroy")
+  VRAG_SYM(AllGather, "ncclAllGather")
+  VRAG_SYM(AllReduce, "ncclAllReduce")
+  VRAG_SYM(GetErrorString, "ncclGetErrorString")
+#undef VRAG_SYM
+  g_nccl = api;
+  return 0;
+}
+#define NCCL_OK(expr)                                                                                       \
+  do {                                                                                                      \
+    int _r = (expr);                                                                                        \
+    if (_r != 0) return fail("%s failed: %s (%s:%d)", #expr, g_nccl.GetErrorString(_r), __FILE__, __LINE__); \
+  } while (0)
+
+static void comm_release(vrag_corpus* c) {
+  CommState& cm = c->comm;
+  if (cm.nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(cm.nccl);
+  cm.nccl = nullptr;
+  cm.send.release();
+  cm.recv.release();
+  cm.raw.release();
+  cm.m_scores.release();
+  cm.m_ids.release();
+  for (auto& e : cm.ev)
+    if (e) { cudaEventDestroy(e); e = nullptr; }
+  cm.rank = 0;
+  cm.nranks = 1;
+}
+
+extern "C" int vrag_comm_unique_id(void* out_id128) {
+  if (!out_id128) return fail("out_id128 is NULL");
+  TRY(nccl_load());
+  NcclId id;
+  NCCL_OK(g_nccl.GetUniqueId(&id));
+  memcpy(out_id128, &id, sizeof(id));
+  return 0;
+}
+
+extern "C" int vrag_comm_init(vrag_corpus_t* c, int rank, int nranks, const void* unique_id128) {
+  VRAG_LOCK(c);
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail("rank %d / nranks %d out of range", rank, nranks);
+  if (c->comm.nccl) return fail("the handle already has a communicator");
+  TRY(set_device(c));
+  if (nranks > 1) {
+    if (!unique_id128) return fail("unique_id128 is NULL");
+    TRY(nccl_load());
+    NcclId id;
+    memcpy(&id, unique_id128, sizeof(id));
+    NCCL_OK(g_nccl.CommInitRank(&c->comm.nccl, nranks, id, rank));
+    for (auto& e : c->comm.ev) CUDA_OK(cudaEventCreate(&e));
+  }
+  c->comm.rank = rank;
+  c->comm.nranks = nranks;
+  return 0;
+}
+
+extern "C" int vrag_comm_info(vrag_corpus_t* c, int* rank, int* nranks) {
+  VRAG_LOCK(c);
+  if (rank) *rank = c->comm.rank;
+  if (nranks) *nranks = c->comm.nranks;
+  return 0;
+}
+
+extern "C" int vrag_comm_destroy(vrag_corpus_t* c) {
+  VRAG_LOCK(c);
+  TRY(set_device(c));
+  cudaStreamSynchronize(c->stream);
+  comm_release(c);
+  return 0;
+}
+
+extern "C" int vrag_last_comm_timing(vrag_corpus_t* c, float* out_us, int capacity, int* n) {
+  VRAG_LOCK(c);
+  if (!n) return fail("n is NULL");
+  *n = c->comm.last_n;
+  for (int i = 0; i < c->comm.last_n && i < capacity && out_us; ++i) out_us[i] = c->comm.last_us[i];
+  return 0;
+}
+
+static_assert(sizeof(Hit) == sizeof(vrag_hit_t) && sizeof(Hit) == 16, "packed entries are 16 bytes on both sides of the ABI");
+static bool sharded(const vrag_corpus* c) { return c->comm.nranks > 1; }
+// event pair around a collective of a host-facing search (device time of the exchange, reported by vrag_last_comm_timing)
+static void comm_mark(vrag_corpus* c, cudaStream_t st, bool begin) {
+  CommState& cm = c->comm;
+  if (!cm.timing || cm.n_ev >= kMaxCommEvents) return;
+  cudaEventRecord(cm.ev[2 * cm.n_ev + (begin ? 0 : 1)], st);
+  if (!begin) cm.n_ev++;
+}
+static void comm_collect_timing(vrag_corpus* c) {   // after the stream was synchronised
+  CommState& cm = c->comm;
+  cm.last_n = cm.n_ev;
+  for (int i = 0; i < cm.n_ev; ++i) {
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, cm.ev[2 * i], cm.ev[2 * i + 1]);
+    cm.last_us[i] = ms * 1e3f;
+  }
+  cm.n_ev = 0;
+}
+
+// gathered[r][list][k] <- rank r's local[list][k]: ONE collective for all lists of a stage
+static int comm_allgather_hits(vrag_corpus* c, const Hit* local, int n_lists, int k, Hit* gathered, cudaStream_t st) {
+  const size_t bytes = static_cast<size_t>(n_lists) * k * sizeof(Hit);
+  if (!sharded(c)) {
+    if (gathered != local) CUDA_OK(cudaMemcpyAsync(gathered, local, bytes, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  comm_mark(c, st, true);
+  NCCL_OK(g_nccl.AllGather(local, gathered, bytes, kNcclInt8, c->comm.nccl, st));
+  comm_mark(c, st, false);
+  return 0;
+}
+static int comm_allreduce_max(vrag_corpus* c, float* buf, int64_t n, cudaStream_t st) {
+  if (!sharded(c) || n == 0) return 0;
+  comm_mark(c, st, true);
+  NCCL_OK(g_nccl.AllReduce(buf, buf, static_cast<size_t>(n), kNcclFloat32, kNcclMax, c->comm.nccl, st));
+  comm_mark(c, st, false);
+  return 0;
+}
+
+// Merge gathered lists hits[src][list][k_src] -> global top-k per list (ties -> lower source rank = lower global id).
+static int merge_hits(vrag_corpus* c, const Hit* hits, int n_src, int n_lists, int k_src, int k, float* out_scores,
+                      long long* out_ids, int* fail_flag, cudaStream_t st) {
+  if (k < 1 || k > kTopkMaxK) return fail("k=%d out of range [1,%d]", k, kTopkMaxK);
+  const long long n = static_cast<long long>(n_src) * k_src;
+  if (n <= 8192) {
+    int k2 = 1;
+    while (k2 < k) k2 <<= 1;
+    TopkArgs a;
+    memset(&a, 0, sizeof(a));
+    a.k = k;
+    a.hits_in = hits;
+    a.hits_k_src = k_src;
+    a.hits_rank_stride = static_cast<long long>(n_lists) * k_src;
+    a.n = n;
+    a.n_total = n;
+    a.out_scores = out_scores;
+    a.out_ids = out_ids;
+    a.out_stride = k;
+    a.fail_flag = fail_flag;
+    const int chunk = n <= 1024 ? 1024 : (n <= 2048 ? 2048 : 8192);
+    a.k2 = std::min(k2, chunk);
+    if (chunk == 8192) TRY((launch_topk_sort<8192, 1024>(c, a, n_lists, st)));
+    else if (chunk == 2048) TRY((launch_topk_sort<2048, 1024>(c, a, n_lists, st)));
+    else TRY((launch_topk_sort<1024, 512>(c, a, n_lists, st)));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  // very long lists (k > 1024 on 8 ranks): unpack and take the radix-select path
+  const size_t tot = static_cast<size_t>(n) * n_lists;
+  TRY(c->comm.m_scores.ensure(tot));
+  TRY(c->comm.m_ids.ensure(tot));
+  hits_unpack_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, st>>>(hits, n_src, n_lists, k_src, c->comm.m_scores.p,
+                                                                             c->comm.m_ids.p, fail_flag);
+  c->launches++;
+  return launch_topk(c, c->comm.m_scores.p, c->comm.m_ids.p, 0, n, k, out_scores, out_ids, nullptr, nullptr, st, n_lists, n);
 }
 
 // ------------------------------------------------------------------------------------------------ host-facing search
@@ -1148,6 +1348,83 @@ extern "C" int vrag_score(vrag_corpus_t* c, const char* name, const float* query
   return 0;
 }
 
+// Scores of candidates when this shard's store has no rows at all: every candidate is foreign -> -inf.
+static int fill_neg_inf(vrag_corpus* c, float* d, int64_t n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  fill_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(d, n, -INFINITY);
+  c->launches++;
+  return 0;
+}
+
+// All stages of one query on the device, enqueued on `stm`, no synchronisation. d_query: device query rows; d_cand:
+// optional stage-0 candidate ids (rank-local when the handle is sharded). Stage s writes ks[s] entries at
+// [sum(ks[:s]), ...) of d_out_scores / d_out_ids (unused slots (-inf, -1)) and, single shard only, its valid count to
+// d_counts[s]. d_fail (may be null unless allow_sampled): OR-ed with 1 when a sampled top-k estimate missed on any rank.
+// Collective when sharded (see include/vrag_b200.h): one all-gather of packed local lists per scanning stage, one
+// max-all-reduce per stage over replicated candidates.
+static int run_stages(vrag_corpus* c, int n_stages, Store* const* st, const uint32_t* flags, const int* ks,
+                      const float* d_query, int n_query_rows, const int* q_offsets, const long long* d_cand, int64_t n_cand,
+                      float* d_out_scores, long long* d_out_ids, int* d_counts, int* d_fail, bool allow_sampled,
+                      cudaStream_t stm, bool* timed_out, bool* used_sampled_out) {
+  const bool sh = sharded(c);
+  const int64_t n_first = d_cand ? n_cand : st[0]->n_pages;
+  int64_t max_k = 0;
+  for (int s = 0; s < n_stages; ++s) max_k = std::max<int64_t>(max_k, ks[s]);
+  TRY(c->d_scores.ensure(std::max<int64_t>(std::max(n_first, max_k), 1)));
+  if (sh) {
+    TRY(c->comm.send.ensure(max_k));
+    TRY(c->comm.recv.ensure(max_k * c->comm.nranks));
+  }
+  size_t off = 0;
+  int64_t n_prev = n_first;   // items entering the stage
+  const long long* d_prev_ids = d_cand;
+  bool timed = false, used_sampled = false;
+  for (int s = 0; s < n_stages; ++s) {
+    const int64_t n_items = n_prev;
+    const float* dq = d_query + (q_offsets ? static_cast<size_t>(q_offsets[s]) * 128 : 0);
+    const int qrows = q_offsets ? (q_offsets[s + 1] - q_offsets[s]) : n_query_rows;
+    const bool replicated = sh && s > 0;   // candidates = the previous stage's merged list, identical on every rank
+    if (n_items > 0) {
+      if (st[s]->total_rows == 0 && d_prev_ids) {
+        TRY(fill_neg_inf(c, c->d_scores.p, n_items, stm));
+      } else if (st[s]->n_pages > 0 || d_prev_ids) {
+        // the dominant (timed) kernel is the first scan
+        TRY(launch_scan(c, *st[s], dq, qrows, flags[s], d_prev_ids, n_items, c->d_scores.p, stm, !timed && timed_out));
+        timed = true;
+      }
+    }
+    float* o_sc = d_out_scores + off;
+    long long* o_id = d_out_ids + off;
+    if (replicated) {
+      TRY(comm_allreduce_max(c, c->d_scores.p, n_items, stm));
+      TRY(launch_topk(c, c->d_scores.p, d_prev_ids, c->page_base, n_items, ks[s], o_sc, o_id, nullptr, nullptr, stm));
+    } else {
+      const SampledPlan sp = (allow_sampled && n_items > 0) ? plan_sampled_topk(n_items, ks[s]) : SampledPlan();
+      Hit* hits = sh ? c->comm.send.p : nullptr;
+      if (sp.on) {
+        if (!used_sampled) CUDA_OK(cudaMemsetAsync(d_fail, 0, sizeof(int), stm));
+        used_sampled = true;
+        TRY(launch_topk_sampled(c, c->d_scores.p, d_prev_ids, c->page_base, n_items, ks[s], sh ? nullptr : o_sc,
+                                sh ? nullptr : o_id, sh ? nullptr : d_counts + s, d_fail, stm, sp, hits));
+      } else {
+        TRY(launch_topk(c, c->d_scores.p, d_prev_ids, c->page_base, n_items, ks[s], sh ? nullptr : o_sc, sh ? nullptr : o_id,
+                        nullptr, sh ? nullptr : d_counts + s, stm, 1, 0, hits));
+      }
+      if (sh) {
+        TRY(comm_allgather_hits(c, c->comm.send.p, 1, ks[s], c->comm.recv.p, stm));
+        TRY(merge_hits(c, c->comm.recv.p, c->comm.nranks, 1, ks[s], ks[s], o_sc, o_id, d_fail, stm));
+      }
+    }
+    d_prev_ids = o_id;
+    // sharded: the global survivor count is not known on the host; unused slots carry id -1 and score -inf downstream
+    n_prev = sh ? ks[s] : std::min<int64_t>(ks[s], n_items);
+    off += ks[s];
+  }
+  if (timed_out) *timed_out = timed;
+  if (used_sampled_out) *used_sampled_out = used_sampled;
+  return 0;
+}
+
 static int search_multistage_impl(vrag_corpus_t* c, int n_stages, const char* const* names,
                                   const uint32_t* flags, const int* ks, const float* query, int n_query_rows,
                                   const int* q_offsets, const int64_t* cand_ids, int64_t n_cand,
@@ -1174,59 +1451,121 @@ static int search_multistage_impl(vrag_corpus_t* c, int n_stages, const char* co
   TRY(c->d_out_scores.ensure(total_k));
   TRY(c->d_out_ids.ensure(total_k));
   TRY(ensure_host_out(c, total_k));
-  const int64_t n_first = cand_ids ? n_cand : st[0]->n_pages;
-  TRY(c->d_scores.ensure(std::max<int64_t>(n_first, 1)));
   if (cand_ids) {
     TRY(c->d_cand.ensure(std::max<int64_t>(n_cand, 1)));
     if (n_cand > 0)
       CUDA_OK(cudaMemcpyAsync(c->d_cand.p, cand_ids, n_cand * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
   }
   CUDA_OK(cudaEventRecord(c->ev0, c->stream));
-  size_t off = 0;
-  int64_t n_prev = n_first;   // survivors entering the stage
-  const long long* d_prev_ids = cand_ids ? c->d_cand.p : nullptr;
   bool timed = false, used_sampled = false;
   int* const d_fail = c->d_counts.p + kMaxStages;   // travels to the host with the per-stage counts
-  for (int s = 0; s < n_stages; ++s) {
-    const int64_t n_items = n_prev;
-    const float* dq = c->d_query.p + (q_offsets ? static_cast<size_t>(q_offsets[s]) * 128 : 0);
-    const int qrows = q_offsets ? (q_offsets[s + 1] - q_offsets[s]) : n_query_rows;
-    if (n_items > 0) {
-      // the dominant (timed) kernel is the first scan
-      TRY(launch_scan(c, *st[s], dq, qrows, flags[s], d_prev_ids, n_items, c->d_scores.p, c->stream, !timed));
-      timed = true;
-    }
-    const SampledPlan sp = (allow_sampled && n_items > 0) ? plan_sampled_topk(n_items, ks[s]) : SampledPlan();
-    if (sp.on) {
-      if (!used_sampled) CUDA_OK(cudaMemsetAsync(d_fail, 0, sizeof(int), c->stream));
-      used_sampled = true;
-      TRY(launch_topk_sampled(c, c->d_scores.p, d_prev_ids, c->page_base, n_items, ks[s], c->d_out_scores.p + off,
-                              c->d_out_ids.p + off, c->d_counts.p + s, d_fail, c->stream, sp));
-    } else {
-      TRY(launch_topk(c, c->d_scores.p, d_prev_ids, c->page_base, n_items, ks[s], c->d_out_scores.p + off,
-                      c->d_out_ids.p + off, nullptr, c->d_counts.p + s, c->stream));
-    }
-    d_prev_ids = c->d_out_ids.p + off;
-    n_prev = std::min<int64_t>(ks[s], n_items);
-    off += ks[s];
+  const bool sh = sharded(c);
+  if (sh) {
+    CUDA_OK(cudaMemsetAsync(d_fail, 0, sizeof(int), c->stream));
+    c->comm.timing = true;
+    c->comm.n_ev = 0;
   }
+  int rc = run_stages(c, n_stages, st, flags, ks, c->d_query.p, n_query_rows, q_offsets, cand_ids ? c->d_cand.p : nullptr,
+                      n_cand, c->d_out_scores.p, c->d_out_ids.p, c->d_counts.p, d_fail, allow_sampled, c->stream, &timed,
+                      &used_sampled);
+  c->comm.timing = false;
+  if (rc) return rc;
   CUDA_OK(cudaEventRecord(c->ev1, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->h_out_scores, c->d_out_scores.p, total_k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->h_out_ids, c->d_out_ids.p, total_k * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->h_counts, c->d_counts.p, (kMaxStages + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (sh) comm_collect_timing(c);
   if (used_sampled && c->h_counts[kMaxStages]) {
-    // a sampled threshold kept too few / too many keys (heavy ties, mostly -inf scores, ...): exact radix-select path
+    // a sampled threshold kept too few / too many keys (heavy ties, mostly -inf scores, ...) on this or — sharded: the
+    // flag travels in the exchanged entries, so every rank takes this branch together — any rank: exact radix-select path
     c->sampled_fallbacks++;
     return search_multistage_impl(c, n_stages, names, flags, ks, query, n_query_rows, q_offsets, cand_ids, n_cand, out_scores,
                                   out_ids, out_counts, false);
   }
   memcpy(out_scores, c->h_out_scores, total_k * sizeof(float));
   memcpy(out_ids, c->h_out_ids, total_k * sizeof(long long));
-  memcpy(out_counts, c->h_counts, n_stages * sizeof(int));
+  if (sh) {   // valid results of a merged list = the leading entries with a real page id
+    size_t off = 0;
+    for (int s = 0; s < n_stages; ++s) {
+      int n = 0;
+      while (n < ks[s] && c->h_out_ids[off + n] >= 0) ++n;
+      out_counts[s] = n;
+      off += ks[s];
+    }
+  } else {
+    memcpy(out_counts, c->h_counts, n_stages * sizeof(int));
+  }
   cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1);
   if (timed) cudaEventElapsedTime(&c->last_ms[1], c->evk0, c->evk1);
   return 0;
+}
+
+extern "C" int vrag_stage_hits_dev(vrag_corpus_t* c, const char* name, const float* query_dev, int n_query_rows, uint32_t flags,
+                                   const int64_t* cand_ids_dev, int64_t n_cand, int k, vrag_hit_t* out_hits_dev, void* stream) {
+  VRAG_LOCK(c);
+  Store* s;
+  TRY(find_store(c, name, &s));
+  TRY(set_device(c));
+  if (!query_dev || !out_hits_dev) return fail("NULL device pointer");
+  if (k < 1 || k > kTopkMaxK) return fail("k=%d out of range [1,%d]", k, kTopkMaxK);
+  cudaStream_t stm = static_cast<cudaStream_t>(stream);
+  const long long* cand = reinterpret_cast<const long long*>(cand_ids_dev);
+  const int64_t n_items = cand ? n_cand : s->n_pages;
+  TRY(c->d_scores.ensure(std::max<int64_t>(n_items, 1)));
+  if (n_items > 0) {
+    if (s->total_rows == 0 && cand) TRY(fill_neg_inf(c, c->d_scores.p, n_items, stm));
+    else TRY(launch_scan(c, *s, query_dev, n_query_rows, flags, cand, n_items, c->d_scores.p, stm, false));
+  }
+  return launch_topk(c, c->d_scores.p, cand, c->page_base, n_items, k, nullptr, nullptr, nullptr, nullptr, stm, 1, 0,
+                     reinterpret_cast<Hit*>(out_hits_dev));
+}
+
+extern "C" int vrag_allgather_topk(vrag_corpus_t* c, const vrag_hit_t* local_dev, int n_lists, int k, vrag_hit_t* gathered_dev,
+                                   void* stream) {
+  VRAG_LOCK(c);
+  TRY(set_device(c));
+  if (!local_dev || !gathered_dev) return fail("NULL device pointer");
+  if (n_lists < 1 || k < 1) return fail("n_lists and k must be >= 1");
+  return comm_allgather_hits(c, reinterpret_cast<const Hit*>(local_dev), n_lists, k, reinterpret_cast<Hit*>(gathered_dev),
+                             static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vrag_merge_hits_dev(vrag_corpus_t* c, const vrag_hit_t* gathered_dev, int n_src, int n_lists, int k_src, int k,
+                                   float* out_scores_dev, int64_t* out_ids_dev, int* flag_dev, void* stream) {
+  VRAG_LOCK(c);
+  TRY(set_device(c));
+  if (!gathered_dev || !out_scores_dev || !out_ids_dev) return fail("NULL device pointer");
+  if (n_src < 1 || n_lists < 1 || k_src < 1) return fail("n_src, n_lists and k_src must be >= 1");
+  return merge_hits(c, reinterpret_cast<const Hit*>(gathered_dev), n_src, n_lists, k_src, k, out_scores_dev,
+                    reinterpret_cast<long long*>(out_ids_dev), flag_dev, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vrag_allreduce_max_dev(vrag_corpus_t* c, float* scores_dev, int64_t n, void* stream) {
+  VRAG_LOCK(c);
+  TRY(set_device(c));
+  if (!scores_dev && n > 0) return fail("NULL device pointer");
+  return comm_allreduce_max(c, scores_dev, n, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vrag_search_multistage_dev(vrag_corpus_t* c, int n_stages, const char* const* names, const uint32_t* flags,
+                                          const int* ks, const float* query_dev, int n_query_rows, const int* q_offsets,
+                                          float* out_scores_dev, int64_t* out_ids_dev, void* stream) {
+  VRAG_LOCK(c);
+  if (n_stages < 1 || n_stages > kMaxStages) return fail("n_stages %d out of range [1,%d]", n_stages, kMaxStages);
+  if (!names || !flags || !ks || !query_dev || !out_scores_dev || !out_ids_dev) return fail("NULL argument");
+  TRY(set_device(c));
+  Store* st[kMaxStages];
+  for (int s = 0; s < n_stages; ++s) {
+    TRY(find_store(c, names[s], &st[s]));
+    if (ks[s] < 1 || ks[s] > kTopkMaxK) return fail("stage %d: k=%d out of range [1,%d]", s, ks[s], kTopkMaxK);
+    if (st[s]->n_pages != st[0]->n_pages) return fail("stage %d: store '%s' has a different page count", s, names[s]);
+    if (q_offsets && (q_offsets[s] < 0 || q_offsets[s + 1] <= q_offsets[s] || q_offsets[s + 1] > n_query_rows))
+      return fail("stage %d: bad query row range", s);
+  }
+  return run_stages(c, n_stages, st, flags, ks, query_dev, n_query_rows, q_offsets, nullptr, 0, out_scores_dev,
+                    reinterpret_cast<long long*>(out_ids_dev), c->d_counts.p, c->d_counts.p + kMaxStages, false,
+                    static_cast<cudaStream_t>(stream), nullptr, nullptr);
 }
 
 extern "C" int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char* const* names,
@@ -1358,8 +1697,9 @@ static int batch_upload(vrag_corpus* c, int n_stages, const uint32_t* flags, int
 // o_sc / o_id ([qc][k]). d_prev_ids: nullptr (every page) or [qc][n_items] global candidate ids.
 static int batch_stage_chunk(vrag_corpus* c, int s, Store& store, uint32_t flags, int k, const long long* d_prev_ids,
                              int64_t n_items, bool have_items, int b0, int qc, float* o_sc, long long* o_id, cudaStream_t stm,
-                             const PrefilterPlan& plan, bool* timed, float* raw_out = nullptr) {
+                             const PrefilterPlan& plan, bool* timed, float* raw_out = nullptr, Hit* o_hits = nullptr) {
   // raw_out != nullptr (candidate stages only): write the [qc][n_items] score matrix there and skip the top-k
+  // o_hits != nullptr (sharded scanning stage): the local lists go out as packed entries [qc][k] (o_sc / o_id may be null)
   BatchCtx& bc = c->batch;
   float* const d_sc = raw_out ? raw_out : c->d_scores.p;
   const int nq = bc.nq;
@@ -1389,7 +1729,8 @@ static int batch_stage_chunk(vrag_corpus* c, int s, Store& store, uint32_t flags
       prefilter_check_kernel<<<(qc + 127) / 128, 128, 0, stm>>>(c->d_fcnt.p, qc, static_cast<int>(std::min<int64_t>(k, store.n_pages)),
                                                                 plan.cap, c->d_fcnt.p + nq);
       c->launches += 2;
-      TRY(launch_topk_keys(c, c->d_fkeys.p, c->d_fcnt.p, plan.cap, k, c->page_base, o_sc, o_id, stm, qc));
+      TRY(launch_topk_keys(c, c->d_fkeys.p, c->d_fcnt.p, plan.cap, k, c->page_base, o_sc, o_id, stm, qc, nullptr, nullptr, nullptr, 0,
+                           o_hits, o_hits ? c->d_fcnt.p + nq : nullptr));
       return 0;
     }
     if (!d_prev_ids && dense_batch_covers(qc, max_rows, flags)) {
@@ -1397,6 +1738,9 @@ static int batch_stage_chunk(vrag_corpus* c, int s, Store& store, uint32_t flags
                                   timed && !*timed);
       if (r == 1) return r;
       if (r == 0 && timed) *timed = true;
+    } else if (d_prev_ids && store.total_rows == 0) {
+      TRY(fill_neg_inf(c, d_sc, static_cast<int64_t>(qc) * n_items, stm));   // an empty shard owns no candidate
+      r = 0;
     } else if (d_prev_ids) {
       const bool t = timed && !*timed;
       if (t) CUDA_OK(cudaEventRecord(c->evk0, stm));
@@ -1417,7 +1761,7 @@ static int batch_stage_chunk(vrag_corpus* c, int s, Store& store, uint32_t flags
   }
   if (raw_out) return 0;
   return launch_topk(c, c->d_scores.p, d_prev_ids, c->page_base, have_items ? n_items : 0, k, o_sc, o_id, nullptr, nullptr, stm,
-                     qc, d_prev_ids ? n_items : 0);
+                     qc, d_prev_ids ? n_items : 0, o_hits);
 }
 
 // chunk size (queries) that bounds the stage-0 score matrix [chunk][n_pages] to ~1 GiB, and the scratch it needs
@@ -1436,6 +1780,54 @@ static int batch_prepare_stage(vrag_corpus* c, Store& store, int k, int64_t n_it
     c->prefilter_runs++;
   }
   *qchunk_out = qchunk;
+  return 0;
+}
+
+// The uploaded batch over a sharded corpus, stage-major: every stage's local work for ALL queries first (in query
+// chunks that bound the dense score matrix — chunking is a local matter and never changes the number of collectives),
+// then ONE collective for the whole batch — the all-gather of [n_queries][k] packed local lists for a scanning stage,
+// the max-all-reduce of the [n_queries][n_cand] candidate scores for a restricted stage — and the batched merge.
+// Results are stage-major in d_out_scores / d_out_ids like the single-shard path. The prefilter's "estimate missed"
+// flag of any rank reaches every rank inside the exchanged entries (d_fcnt[nq] after the merge).
+static int batch_run_sharded(vrag_corpus* c, int n_stages, Store* const* st, const uint32_t* flags, const int* ks,
+                             bool allow_prefilter, cudaStream_t stm, bool* timed) {
+  BatchCtx& bc = c->batch;
+  const int nq = bc.nq, R = c->comm.nranks;
+  size_t off = 0;
+  const long long* d_prev_ids = nullptr;
+  for (int s = 0; s < n_stages; ++s) {
+    const int k = ks[s];
+    float* o_sc = c->d_out_scores.p + off * nq;
+    long long* o_id = c->d_out_ids.p + off * nq;
+    PrefilterPlan plan;
+    int qchunk = 1;
+    if (s == 0) {
+      const int64_t n_pages = st[0]->n_pages;
+      TRY(batch_prepare_stage(c, *st[0], k, 0, true, allow_prefilter, flags[0], 0, &plan, &qchunk));
+      TRY(c->comm.send.ensure(static_cast<size_t>(nq) * k));
+      TRY(c->comm.recv.ensure(static_cast<size_t>(nq) * k * R));
+      for (int b0 = 0; b0 < nq; b0 += qchunk) {
+        const int qc = std::min(qchunk, nq - b0);
+        TRY(batch_stage_chunk(c, 0, *st[0], flags[0], k, nullptr, n_pages, n_pages > 0, b0, qc, nullptr, nullptr, stm, plan, timed,
+                              nullptr, c->comm.send.p + static_cast<size_t>(b0) * k));
+      }
+      TRY(comm_allgather_hits(c, c->comm.send.p, nq, k, c->comm.recv.p, stm));
+      TRY(merge_hits(c, c->comm.recv.p, R, nq, k, k, o_sc, o_id, c->d_fcnt.p + nq, stm));
+    } else {
+      const int64_t n_cand = ks[s - 1];
+      TRY(batch_prepare_stage(c, *st[s], k, n_cand, false, false, flags[s], s, &plan, &qchunk));
+      TRY(c->comm.raw.ensure(static_cast<size_t>(nq) * n_cand));
+      for (int b0 = 0; b0 < nq; b0 += qchunk) {
+        const int qc = std::min(qchunk, nq - b0);
+        TRY(batch_stage_chunk(c, s, *st[s], flags[s], k, d_prev_ids + static_cast<size_t>(b0) * n_cand, n_cand, true, b0, qc,
+                              nullptr, nullptr, stm, PrefilterPlan(), timed, c->comm.raw.p + static_cast<size_t>(b0) * n_cand));
+      }
+      TRY(comm_allreduce_max(c, c->comm.raw.p, static_cast<int64_t>(nq) * n_cand, stm));
+      TRY(launch_topk(c, c->comm.raw.p, d_prev_ids, 0, n_cand, k, o_sc, o_id, nullptr, nullptr, stm, nq, n_cand));
+    }
+    d_prev_ids = o_id;
+    off += k;
+  }
   return 0;
 }
 
@@ -1473,8 +1865,18 @@ static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const ch
   TRY(ensure_host_out(c, std::max(out_n, stage_sc_n)));
   if (final_only) TRY(c->d_stage_sc.ensure(stage_sc_n));
   const int64_t n_pages = st[0]->n_pages;
+  const bool sh = sharded(c);
   PrefilterPlan plan;
   int qchunk = 1;
+  bool timed = false;
+  if (sh) {
+    CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+    c->comm.timing = true;
+    c->comm.n_ev = 0;
+    const int rc = batch_run_sharded(c, n_stages, st, flags, ks, !no_prefilter, c->stream, &timed);
+    c->comm.timing = false;
+    if (rc) return rc;
+  } else {
   TRY(batch_prepare_stage(c, *st[0], ks[0], 0, true, !no_prefilter, flags[0], 0, &plan, &qchunk));
   {
     int64_t need = static_cast<int64_t>(qchunk) * std::max<int64_t>(n_pages, 1);
@@ -1482,7 +1884,6 @@ static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const ch
     TRY(c->d_scores.ensure(need));
   }
   CUDA_OK(cudaEventRecord(c->ev0, c->stream));
-  bool timed = false;
   for (int b0 = 0; b0 < nq; b0 += qchunk) {
     const int qc = std::min(qchunk, nq - b0);
     size_t off = 0;
@@ -1500,6 +1901,7 @@ static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const ch
       else if (s == n_stages - 1) for (int b = 0; b < qc; ++b) out_counts[b0 + b] = static_cast<int>(n_prev);
       off += ks[s];
     }
+  }
   }
   const size_t off_last = (total_k - k_last) * nq;   // the last stage's [nq][k_last] block
   if (final_only) {
@@ -1524,9 +1926,11 @@ static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const ch
     CUDA_OK(cudaMemcpyAsync(c->h_out_scores, c->d_out_scores.p, out_n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaMemcpyAsync(c->h_out_ids, c->d_out_ids.p, out_n * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
   }
-  if (plan.on) CUDA_OK(cudaMemcpyAsync(c->h_flag, c->d_fcnt.p + nq, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  const bool check_flag = plan.on || (sh && !no_prefilter);
+  if (check_flag) CUDA_OK(cudaMemcpyAsync(c->h_flag, c->d_fcnt.p + nq, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
-  if (plan.on && *c->h_flag) {
+  if (sh) comm_collect_timing(c);
+  if (check_flag && *c->h_flag) {
     // a threshold estimate kept too few / too many candidates for some query: redo the batch with the exact path
     *c->h_flag = 0;
     c->prefilter_fallbacks++;
@@ -1539,6 +1943,23 @@ static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const ch
   } else {
     memcpy(out_scores, c->h_out_scores, out_n * sizeof(float));
     memcpy(out_ids, c->h_out_ids, out_n * sizeof(long long));
+  }
+  if (sh) {   // merged lists: the valid results are the leading entries with a real page id
+    auto count_valid = [](const long long* ids, int k) {
+      int n = 0;
+      while (n < k && ids[n] >= 0) ++n;
+      return n;
+    };
+    if (final_only) {
+      for (int b = 0; b < nq; ++b) out_counts[b] = count_valid(c->h_out_ids + static_cast<size_t>(b) * k_last, k_last);
+    } else {
+      size_t off = 0;
+      for (int s = 0; s < n_stages; ++s) {
+        for (int b = 0; b < nq; ++b)
+          out_counts[static_cast<size_t>(s) * nq + b] = count_valid(c->h_out_ids + off * nq + static_cast<size_t>(b) * ks[s], ks[s]);
+        off += ks[s];
+      }
+    }
   }
   cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1);
   if (timed) cudaEventElapsedTime(&c->last_ms[1], c->evk0, c->evk1);

@@ -86,6 +86,16 @@ SIGNATURES = {
     "vrag_saliency": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int, C.c_int64, _f32p, C.c_int64, _i64p]),
     "vrag_score_dev": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "vrag_topk_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vrag_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "vrag_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "vrag_comm_info": (C.c_int, [C.c_void_p, _i32p, _i32p]),
+    "vrag_comm_destroy": (C.c_int, [C.c_void_p]),
+    "vrag_stage_hits_dev": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "vrag_allgather_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "vrag_merge_hits_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vrag_allreduce_max_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "vrag_search_multistage_dev": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _u32p, _i32p, C.c_void_p, C.c_int, _i32p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vrag_last_comm_timing": (C.c_int, [C.c_void_p, _f32p, C.c_int, _i32p]),
     "vrag_pool_out_rows": (C.c_int, [C.POINTER(PoolSpec), C.c_int64, _i64p]),
     "vrag_pool_page": (C.c_int, [C.c_int, C.POINTER(PoolSpec), C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64, _i64p]),
     "vrag_store_pool": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(PoolSpec), C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]),

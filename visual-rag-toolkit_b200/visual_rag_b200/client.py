@@ -1,17 +1,19 @@
-"""`GpuCorpusClient`: the duck-typed `qdrant_client` of the reference retrievers, backed by a GpuCorpus.
+"""`GpuCorpusClient` / `ShardedCorpusClient`: the duck-typed `qdrant_client` of the reference retrievers, backed by a
+GPU-resident corpus (one GPU, or page-sharded over the GPUs of a box).
 
 The reference retrievers only ever call `query_points`, `retrieve` and `get_collection` on their client
 (two_stage.py:162-178,307-316,349-358,384-390; three_stage.py:103-157;
-single_stage.py:123-132).  This class implements exactly those with Qdrant's COSINE + MAX_SIM semantics
+single_stage.py:123-132).  These classes implement exactly those with Qdrant's COSINE + MAX_SIM semantics
 (qdrant_indexer.py:200-239) computed by the sm_100a kernels, so the reference's own retriever classes — and
 the mirrors in visual_rag_b200.retrieval — run unchanged on top of the GPU store.
 """
 
 from __future__ import annotations
 
+import bisect
 import functools
 import threading
-from typing import Any, Dict, Iterable, List, Optional, Sequence
+from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -52,19 +54,6 @@ class _CollectionInfo:
         self.points_count = points_count
 
 
-def _match(cond, payload: dict) -> bool:
-    """FieldCondition(key, match=MatchValue(value)|MatchAny(any)) on a payload dict (two_stage.py:449-480)."""
-    val = payload.get(getattr(cond, "key", None)) if payload else None
-    m = getattr(cond, "match", None)
-    if m is None:
-        return True
-    if hasattr(m, "any") and getattr(m, "any") is not None:
-        return val in list(m.any)
-    if hasattr(m, "value"):
-        return val == m.value
-    return True
-
-
 def _locked(fn):
     """Client calls and ingest (GpuIndexer.upload_batch) serialise on one lock: a batch upload appends to several named
     stores and then registers its ids, and a search must not observe the collection in between."""
@@ -75,6 +64,42 @@ def _locked(fn):
             return fn(self, *args, **kwargs)
 
     return wrapper
+
+
+# ---------------------------------------------------------------------------------------------------- filters
+def _is_filter(obj) -> bool:
+    return any(getattr(obj, a, None) is not None for a in ("must", "should", "must_not")) and not hasattr(obj, "key") \
+        and not hasattr(obj, "has_id")
+
+
+def _as_list(x) -> list:
+    if x is None:
+        return []
+    return list(x) if isinstance(x, (list, tuple)) else [x]
+
+
+def _cond_signature(cond) -> tuple:
+    """Hashable structural signature of a filter / condition (cache key of its page mask). TypeError for unhashable
+    match values."""
+    if _is_filter(cond):
+        return ("filter",
+                tuple(_cond_signature(c) for c in _as_list(getattr(cond, "must", None))),
+                tuple(_cond_signature(c) for c in _as_list(getattr(cond, "should", None))),
+                tuple(_cond_signature(c) for c in _as_list(getattr(cond, "must_not", None))))
+    if hasattr(cond, "has_id"):
+        return ("has_id", frozenset(cond.has_id))
+    key = str(getattr(cond, "key", None))
+    m = getattr(cond, "match", None)
+    rng = getattr(cond, "range", None)
+    sig: tuple = ("field", key)
+    if m is not None:
+        for attr in ("value", "any", "except_"):
+            v = getattr(m, attr, None)
+            if v is not None:
+                sig += (attr, tuple(sorted(map(repr, v))) if attr != "value" else repr(v))
+    if rng is not None:
+        sig += ("range",) + tuple(repr(getattr(rng, a, None)) for a in ("gt", "gte", "lt", "lte"))
+    return sig
 
 
 class GpuCorpusClient:
@@ -97,16 +122,19 @@ class GpuCorpusClient:
         self._payloads = list(payloads) if payloads is not None else None
         self._lock = threading.RLock()
         self._columns: Dict[str, np.ndarray] = {}       # payload key -> per-page value column (built on first use)
-        self._filter_cache: Dict[Any, np.ndarray] = {}  # filter signature -> candidate page ids
+        self._filter_cache: Dict[Any, Any] = {}         # filter signature -> (page mask, candidate page ids)
 
-    # ------------------------------------------------------------------ id mapping
+    # ------------------------------------------------------------------ id mapping (pages of THIS corpus handle)
+    def _invalidate(self) -> None:
+        self._columns = {}
+        self._filter_cache = {}
+
     @_locked
     def set_points(self, point_ids: Sequence[Any], payloads: Optional[Sequence[Optional[dict]]] = None) -> None:
         self._ids = list(point_ids)
         self._index = {pid: i for i, pid in enumerate(self._ids)}
         self._payloads = list(payloads) if payloads is not None else None
-        self._columns = {}
-        self._filter_cache = {}
+        self._invalidate()
 
     @_locked
     def append_points(self, point_ids: Sequence[Any], payloads: Optional[Sequence[Optional[dict]]] = None) -> None:
@@ -120,8 +148,7 @@ class GpuCorpusClient:
         for i, pid in enumerate(point_ids):
             self._index[pid] = n0 + i
         self._payloads.extend(payloads if payloads is not None else [None] * len(point_ids))
-        self._columns = {}
-        self._filter_cache = {}
+        self._invalidate()
 
     @_locked
     def set_payload(self, point_id, payload: Optional[dict]) -> None:
@@ -132,14 +159,14 @@ class GpuCorpusClient:
         if self._payloads is None:
             self._payloads = [None] * len(self._ids)
         self._payloads[page - self.corpus.page_base] = payload
-        self._columns = {}
-        self._filter_cache = {}
+        self._invalidate()
 
     def _pid(self, page: int):
         local = page - self.corpus.page_base
         return self._ids[local] if self._ids is not None else page
 
     def _page(self, pid) -> int:
+        """external point id -> global page id (-1 if unknown)."""
         if self._index is not None:
             i = self._index.get(pid)
             if i is None and not isinstance(pid, str):
@@ -155,68 +182,94 @@ class GpuCorpusClient:
             return {}
         return self._payloads[page - self.corpus.page_base]
 
+    def _pids_of(self, pages: List[int]) -> list:
+        ext, base = self._ids, self.corpus.page_base
+        return pages if ext is None else [ext[p - base] for p in pages]
+
+    def _payloads_of(self, pages: List[int]) -> list:
+        pls, base = self._payloads, self.corpus.page_base
+        return [{} for _ in pages] if pls is None else [pls[p - base] for p in pages]
+
+    def _read_pages(self, name: str, pages: Sequence[int]) -> Dict[int, np.ndarray]:
+        """fp16 rows of the listed global pages (what `with_vectors=[name]` returns)."""
+        base = self.corpus.page_base
+        return {int(p): self.corpus.read_page(name, int(p) - base) for p in pages}
+
+    def _n_points_total(self, n_local: int) -> int:
+        return n_local
+
     # ------------------------------------------------------------------ filters
     def _candidates(self, query_filter, n_pages: int) -> Optional[np.ndarray]:
-        """Filter -> sorted global page ids, or None for 'all pages'. HasIdCondition is the candidate
-        restriction of three_stage.py:75-81; FieldConditions (build_filter, two_stage.py:436-480) are
-        evaluated on the host payloads."""
+        """Filter -> ascending global page ids of THIS handle's pages that pass it, or None for 'all pages'.
+        `must` is a conjunction, `should` a disjunction (at least one), `must_not` a negated disjunction — Qdrant's
+        filter semantics; conditions: HasIdCondition (the candidate restriction of three_stage.py:75-81 and the rerank
+        list of two_stage.py:380-390), FieldCondition with MatchValue / MatchAny / MatchExcept / Range (build_filter,
+        two_stage.py:436-480; the per_dataset scope filter, run_qdrant_beir.py:1987-1997) and nested Filters. Anything
+        else raises NotImplementedError — a clause is never silently dropped. Payload clauses are evaluated column-wise
+        on the host payloads (one numpy pass per key) and the resulting page mask is cached per filter."""
         if query_filter is None:
             return None
-        allowed: Optional[set] = None
-        field_conds = []
+        base = self.corpus.page_base
+        # split the top-level conjunction into id restrictions (handled as small sorted sets: O(k), never O(n_pages))
+        # and the payload part (a cached page mask)
+        id_sets: List[set] = []
+        rest_must: list = []
 
-        def walk(f):
-            nonlocal allowed
-            for cond in (getattr(f, "must", None) or []):
+        def split(f):
+            for cond in _as_list(getattr(f, "must", None)):
                 if hasattr(cond, "has_id"):
                     s = {self._page(p) for p in cond.has_id}
                     s.discard(-1)
-                    allowed = s if allowed is None else (allowed & s)
-                elif hasattr(cond, "must") or hasattr(cond, "should") or hasattr(cond, "must_not"):
-                    walk(cond)
-                elif hasattr(cond, "key"):
-                    field_conds.append(cond)
+                    id_sets.append(s)
+                elif _is_filter(cond) and getattr(cond, "should", None) is None and getattr(cond, "must_not", None) is None:
+                    split(cond)
+                else:
+                    rest_must.append(cond)
 
-        walk(query_filter)
-        if allowed is None and not field_conds:
-            return None
-        base = self.corpus.page_base
-        # payload conditions are evaluated column-wise (one numpy pass per key) and the resulting page list is cached
-        # per filter, so a benchmark that reuses one filter (run_qdrant_beir.py:1987-1997) pays for it once
+        split(query_filter)
+        should = _as_list(getattr(query_filter, "should", None))
+        must_not = _as_list(getattr(query_filter, "must_not", None))
+        has_rest = bool(rest_must or should or must_not)
+        allowed: Optional[set] = None
+        for s in id_sets:
+            allowed = s if allowed is None else (allowed & s)
+        if not has_rest:
+            if allowed is None:
+                return None
+            return np.asarray(sorted(p for p in allowed if 0 <= p - base < n_pages), dtype=np.int64)
+        mask, pages = self._payload_mask(rest_must, should, must_not, n_pages)
+        if allowed is None:
+            return pages
+        return np.asarray(sorted(p for p in allowed if 0 <= p - base < n_pages and mask[p - base]), dtype=np.int64)
+
+    def _payload_mask(self, must, should, must_not, n_pages: int) -> Tuple[np.ndarray, np.ndarray]:
+        """(bool mask over this handle's pages, ascending global ids of the pages that pass), cached per filter — a
+        benchmark that reuses one filter (run_qdrant_beir.py:1987-1997) pays for it once."""
         sig = None
-        if field_conds:
-            try:
-                sig = (n_pages, tuple(sorted(self._cond_signature(c) for c in field_conds)),
-                       None if allowed is None else frozenset(allowed))
-                hit = self._filter_cache.get(sig)
-                if hit is not None:
-                    return hit
-            except TypeError:   # unhashable match values: evaluate without caching
-                sig = None
-            mask = np.ones((n_pages,), dtype=bool)
-            for cond in field_conds:
-                mask &= self._cond_mask(cond, n_pages)
-            if allowed is not None:
-                sel = np.zeros((n_pages,), dtype=bool)
-                idx = np.fromiter((p - base for p in allowed if 0 <= p - base < n_pages), dtype=np.int64)
-                sel[idx] = True
-                mask &= sel
-            pages_arr = np.nonzero(mask)[0].astype(np.int64) + base
-            if sig is not None:
-                if len(self._filter_cache) > 64:
-                    self._filter_cache.clear()
-                self._filter_cache[sig] = pages_arr
-            return pages_arr
-        return np.asarray(sorted(allowed), dtype=np.int64)
-
-    @staticmethod
-    def _cond_signature(cond):
-        m = getattr(cond, "match", None)
-        if m is None:
-            return (str(getattr(cond, "key", None)), "none", ())
-        if hasattr(m, "any") and getattr(m, "any") is not None:
-            return (str(cond.key), "any", tuple(sorted(map(repr, m.any))))
-        return (str(cond.key), "value", (repr(getattr(m, "value", None)),))
+        try:
+            sig = (n_pages, tuple(_cond_signature(c) for c in must), tuple(_cond_signature(c) for c in should),
+                   tuple(_cond_signature(c) for c in must_not))
+            hit = self._filter_cache.get(sig)
+            if hit is not None:
+                return hit
+        except TypeError:   # unhashable match values: evaluate without caching
+            sig = None
+        mask = np.ones((n_pages,), dtype=bool)
+        for cond in must:
+            mask &= self._cond_mask(cond, n_pages)
+        if should:
+            any_of = np.zeros((n_pages,), dtype=bool)
+            for cond in should:
+                any_of |= self._cond_mask(cond, n_pages)
+            mask &= any_of
+        for cond in must_not:
+            mask &= ~self._cond_mask(cond, n_pages)
+        out = (mask, np.nonzero(mask)[0].astype(np.int64) + self.corpus.page_base)
+        if sig is not None:
+            if len(self._filter_cache) > 64:
+                self._filter_cache.clear()
+            self._filter_cache[sig] = out
+        return out
 
     def _column(self, key: str, n_pages: int) -> np.ndarray:
         col = self._columns.get(key)
@@ -230,26 +283,69 @@ class GpuCorpusClient:
         return col
 
     def _cond_mask(self, cond, n_pages: int) -> np.ndarray:
-        """FieldCondition(key, match=MatchValue|MatchAny) over all pages (two_stage.py:449-480)."""
-        m = getattr(cond, "match", None)
-        if m is None:
-            return np.ones((n_pages,), dtype=bool)
-        col = self._column(getattr(cond, "key", None), n_pages)
-        if hasattr(m, "any") and getattr(m, "any") is not None:
-            vals = list(m.any)
-            out = np.zeros((n_pages,), dtype=bool)
-            for v in vals:
-                out |= (col == v)
-            return out
-        if hasattr(m, "value"):
-            return np.asarray(col == m.value, dtype=bool)
-        return np.ones((n_pages,), dtype=bool)
+        """One condition over all pages of this handle -> bool mask."""
+        if _is_filter(cond):
+            m = np.ones((n_pages,), dtype=bool)
+            for c in _as_list(getattr(cond, "must", None)):
+                m &= self._cond_mask(c, n_pages)
+            sh = _as_list(getattr(cond, "should", None))
+            if sh:
+                any_of = np.zeros((n_pages,), dtype=bool)
+                for c in sh:
+                    any_of |= self._cond_mask(c, n_pages)
+                m &= any_of
+            for c in _as_list(getattr(cond, "must_not", None)):
+                m &= ~self._cond_mask(c, n_pages)
+            return m
+        if hasattr(cond, "has_id"):
+            m = np.zeros((n_pages,), dtype=bool)
+            base = self.corpus.page_base
+            idx = [self._page(p) - base for p in cond.has_id]
+            idx = [i for i in idx if 0 <= i < n_pages]
+            m[idx] = True
+            return m
+        if not hasattr(cond, "key"):
+            raise NotImplementedError(f"unsupported filter condition {type(cond).__name__}")
+        col = self._column(getattr(cond, "key"), n_pages)
+        match, rng = getattr(cond, "match", None), getattr(cond, "range", None)
+        if match is None and rng is None:
+            raise NotImplementedError(f"FieldCondition on '{cond.key}' has neither match nor range "
+                                      "(only MatchValue / MatchAny / MatchExcept / Range are supported)")
+        out = np.ones((n_pages,), dtype=bool)
+        if match is not None:
+            if getattr(match, "any", None) is not None:
+                hit = np.zeros((n_pages,), dtype=bool)
+                for v in list(match.any):
+                    hit |= np.asarray(col == v, dtype=bool)
+                out &= hit
+            elif getattr(match, "except_", None) is not None:
+                for v in list(match.except_):
+                    out &= ~np.asarray(col == v, dtype=bool)
+            elif hasattr(match, "value"):
+                out &= np.asarray(col == match.value, dtype=bool)
+            else:
+                raise NotImplementedError(f"unsupported matcher {type(match).__name__} on '{cond.key}'")
+        if rng is not None:
+            num = np.array([x if isinstance(x, (int, float)) and not isinstance(x, bool) else np.nan for x in col], dtype=np.float64)
+            with np.errstate(invalid="ignore"):
+                for attr, op in (("gt", np.greater), ("gte", np.greater_equal), ("lt", np.less), ("lte", np.less_equal)):
+                    bound = getattr(rng, attr, None)
+                    if bound is not None:
+                        out &= op(num, float(bound))
+        return out
 
     # ------------------------------------------------------------------ the three client methods
     @staticmethod
     def _as_query(query) -> np.ndarray:
         q = np.asarray(query, dtype=np.float32)
         return q[None, :] if q.ndim == 1 else q
+
+    def _points(self, scores, ids, with_payload) -> List[ScoredPoint]:
+        keep = np.isfinite(scores) & (ids >= 0)
+        pages = [int(i) for i in ids[keep]]
+        pids = self._pids_of(pages)
+        pls = self._payloads_of(pages) if with_payload else [None] * len(pages)
+        return [ScoredPoint(pid, float(s), pl) for pid, s, pl in zip(pids, scores[keep], pls)]
 
     @_locked
     def query_points(self, collection_name=None, query=None, using=None, limit=10, query_filter=None,
@@ -271,16 +367,13 @@ class GpuCorpusClient:
             scores, ids = stages[-1]
         else:
             scores, ids = self.corpus.search(using, q, limit, candidate_ids=cand)
-        keep = np.isfinite(scores)
-        points = [
-            ScoredPoint(self._pid(int(i)), float(s), self._payload(int(i)) if with_payload else None)
-            for s, i in zip(scores[keep], ids[keep])
-        ]
+        points = self._points(scores, ids, with_payload)
         if with_vectors:
             names = [using] if with_vectors is True else list(with_vectors)
-            for p in points:
-                page = self._page(p.id) - self.corpus.page_base
-                p.vector = {nm: self.corpus.read_page(nm, page).astype(np.float32).tolist() for nm in names}
+            pages = [self._page(p.id) for p in points]
+            rows = {nm: self._read_pages(nm, pages) for nm in names}
+            for p, page in zip(points, pages):
+                p.vector = {nm: rows[nm][page].astype(np.float32).tolist() for nm in names}
         return QueryResponse(points)
 
     @_locked
@@ -293,12 +386,7 @@ class GpuCorpusClient:
             [(stage1_using, False, int(stage1_k)), (stage2_using, False, int(stage2_k)), (stage3_using, False, int(top_k))],
             None, stage_queries=[self._as_query(stage1_query), self._as_query(stage2_query), self._as_query(stage3_query)],
             candidate_ids=cand)
-        out = []
-        for si, (scores, ids) in enumerate(stages):
-            keep = np.isfinite(scores)
-            out.append([ScoredPoint(self._pid(int(i)), float(s), self._payload(int(i)) if si == 2 else None)
-                        for s, i in zip(scores[keep], ids[keep])])
-        return out
+        return [self._points(scores, ids, si == 2) for si, (scores, ids) in enumerate(stages)]
 
     @_locked
     def query_multistage_batch(self, *, usings: Sequence[str], limits: Sequence[int],
@@ -314,16 +402,8 @@ class GpuCorpusClient:
         sq = [[self._as_query(x) for x in per_query] for per_query in stage_queries]
         res = self.corpus.search_multistage_batch([(usings[s], False, int(limits[s])) for s in range(ns)], None,
                                                   stage_queries=sq)
-        out = []
-        for per_query in res:
-            stages = []
-            for si, (scores, ids) in enumerate(per_query):
-                keep = np.isfinite(scores)
-                last = si == ns - 1
-                stages.append([ScoredPoint(self._pid(int(i)), float(s), self._payload(int(i)) if (last and with_payload) else None)
-                               for s, i in zip(scores[keep], ids[keep])])
-            out.append(stages)
-        return out
+        return [[self._points(scores, ids, with_payload and si == ns - 1) for si, (scores, ids) in enumerate(per_query)]
+                for per_query in res]
 
     @_locked
     def query_multistage_batch_final(self, *, usings: Sequence[str], limits: Sequence[int],
@@ -342,11 +422,15 @@ class GpuCorpusClient:
             raise ValueError("usings and limits must have the same length")
         if stage_queries is not None:
             sq = [[self._as_query(x) for x in per_query] for per_query in stage_queries]
+            if not sq:
+                return []
             sc, ids, st, cnt = self.corpus.search_multistage_batch(
                 [(usings[s], False, int(limits[s])) for s in range(ns)], None, stage_queries=sq, final_only=True)
         else:
             if queries is None:
                 raise ValueError("either stage_queries or queries is required")
+            if len(queries) == 0:
+                return []
             pf = [False] * ns if pool_flags is None else [bool(x) for x in pool_flags]
             if len(pf) != ns:
                 raise ValueError("pool_flags must have one entry per stage")
@@ -367,7 +451,6 @@ class GpuCorpusClient:
             else:
                 st_cols.append(col.tolist())
         sc_l, ids_l = sc.tolist(), ids.tolist()
-        base, ext, pls = self.corpus.page_base, self._ids, self._payloads
         out = []
         for b in range(nq):
             pages, scores, stages = ids_l[b], sc_l[b], [col[b] for col in st_cols]
@@ -376,28 +459,22 @@ class GpuCorpusClient:
                 pages = [pages[j] for j in keep]
                 scores = [scores[j] for j in keep]
                 stages = [[col[j] for j in keep] for col in stages]
-            pids = pages if ext is None else [ext[p - base] for p in pages]
-            if not with_payload:
-                payloads = [None] * len(pages)
-            elif pls is None:
-                payloads = [{} for _ in pages]
-            else:
-                payloads = [pls[p - base] for p in pages]
+            pids = self._pids_of(pages)
+            payloads = self._payloads_of(pages) if with_payload else [None] * len(pages)
             out.append((pids, scores, stages, payloads))
         return out
 
     @_locked
     def retrieve(self, collection_name=None, ids=(), with_payload=False, with_vectors=None, timeout=None, **_ignored):
-        out = []
         names = [] if not with_vectors else (list(with_vectors) if not isinstance(with_vectors, bool) else [])
-        for pid in ids:
-            page = self._page(pid)
-            if page < 0:
-                continue
-            local = page - self.corpus.page_base
-            vec = {nm: self.corpus.read_page(nm, local).astype(np.float32).tolist() for nm in names
-                   if self.corpus.has_store(nm)}
-            out.append(ScoredPoint(pid, None, self._payload(page) if with_payload else None, vec or None))
+        names = [nm for nm in names if self.corpus.has_store(nm)]
+        known = [(pid, self._page(pid)) for pid in ids]
+        known = [(pid, page) for pid, page in known if page >= 0]
+        rows = {nm: self._read_pages(nm, [page for _, page in known]) for nm in names}
+        out = []
+        for pid, page in known:
+            vec = {nm: rows[nm][page].astype(np.float32).tolist() for nm in names}
+            out.append(ScoredPoint(pid, None, self._payloads_of([page])[0] if with_payload else None, vec or None))
         return out
 
     @_locked
@@ -409,4 +486,136 @@ class GpuCorpusClient:
                 info = self.corpus.store_info(nm)
                 vectors[nm] = _VectorInfo(multivector=(nm != "global_pooling"))
                 count = info["n_pages"]
-        return _CollectionInfo(vectors, count)
+        return _CollectionInfo(vectors, self._n_points_total(count))
+
+
+class ShardedCorpusClient(GpuCorpusClient):
+    """The same client over a corpus that is page-sharded across the GPUs of a box: one process per GPU
+    (torchrun), every rank constructs the client over ITS shard (`corpus`, a GpuCorpus whose page_base is the first
+    global page id of the rank's range) and all ranks make the same client calls in the same order (SPMD) — each call
+    is one collective search in the library and every rank receives the same global result, so the retriever classes
+    (`TwoStageRetriever`, `ThreeStageRetriever`, `SingleStageRetriever`, `MultiVectorRetriever`, and the reference's own)
+    run unchanged at N > 1.
+
+    point_ids / payloads describe THIS rank's pages (page order). The id / payload tables of all ranks are exchanged
+    once here (and after every `sync_points`) through the torch.distributed group, so turning result pages into
+    ScoredPoints never communicates; the vectors and the payload COLUMNS used by filters stay sharded with the pages:
+    a filter is evaluated by every rank over its own pages only and enters the collective search as a rank-local
+    candidate list. `with_vectors` / `retrieve(with_vectors=...)` fetch rows from the owning rank (one object
+    all-gather per call: the reference's slow client-side rerank path, kept for completeness)."""
+
+    def __init__(self, corpus, collection_name: str = "gpu", point_ids: Optional[Sequence[Any]] = None,
+                 payloads: Optional[Sequence[Optional[dict]]] = None, group=None):
+        super().__init__(corpus, collection_name, point_ids, payloads)
+        import torch.distributed as dist
+
+        self._dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.group = group
+        if self._dist is not None and getattr(corpus, "world", 1) == 1 and self._dist.get_world_size(group) > 1:
+            corpus.comm_init_torch(group)
+        self.rank = getattr(corpus, "rank", 0)
+        self.world = getattr(corpus, "world", 1)
+        self._shards: List[Tuple[int, int, Optional[list], Optional[list]]] = []   # (base, n_pages, ids, payloads) by rank
+        self._bases: List[int] = []
+        self._gindex: Optional[Dict[Any, int]] = None
+        self._plain = True
+        self.sync_points()
+
+    # ------------------------------------------------------------------ replicated id / payload tables
+    def _gather(self, obj) -> list:
+        if self._dist is None or self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self._dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    @_locked
+    def sync_points(self) -> None:
+        """Collective: exchange (page range, ids, payloads) of every rank. Called by the constructor; call it again after
+        the local tables changed (set_points / append_points on every rank)."""
+        n_local = len(self._ids) if self._ids is not None else (
+            len(self._payloads) if self._payloads is not None else self._local_pages())
+        parts = self._gather((int(self.corpus.page_base), int(n_local), self._ids, self._payloads))
+        parts.sort(key=lambda t: t[0])
+        for (b0, n0, _, _), (b1, _, _, _) in zip(parts, parts[1:]):
+            if b0 + n0 > b1:
+                raise ValueError(f"page ranges of two ranks overlap: [{b0},{b0 + n0}) and [{b1},...)")
+        self._shards = parts
+        self._bases = [p[0] for p in parts]
+        self._plain = all(p[2] is None for p in parts)
+        if self._plain:
+            self._gindex = None
+        else:
+            self._gindex = {}
+            for base, n, ids, _ in parts:
+                for i in range(n):
+                    self._gindex[ids[i] if ids is not None else base + i] = base + i
+
+    def _local_pages(self) -> int:
+        for nm in ("initial", "mean_pooling", "experimental_pooling", "global_pooling"):
+            if self.corpus.has_store(nm):
+                return int(self.corpus.n_pages(nm))
+        return 0
+
+    def _locate(self, page: int) -> Tuple[int, int]:
+        r = bisect.bisect_right(self._bases, page) - 1
+        if r < 0 or page - self._bases[r] >= self._shards[r][1]:
+            raise KeyError(f"page {page} belongs to no shard")
+        return r, page - self._bases[r]
+
+    def _pid(self, page: int):
+        r, loc = self._locate(page)
+        ids = self._shards[r][2]
+        return ids[loc] if ids is not None else page
+
+    def _page(self, pid) -> int:
+        if self._gindex is not None:
+            g = self._gindex.get(pid)
+            if g is None and not isinstance(pid, str):
+                g = self._gindex.get(str(pid))
+            return -1 if g is None else g
+        try:
+            return int(pid)
+        except (TypeError, ValueError):
+            return -1
+
+    def _payload(self, page: int):
+        r, loc = self._locate(page)
+        pls = self._shards[r][3]
+        return {} if pls is None else pls[loc]
+
+    def _pids_of(self, pages: List[int]) -> list:
+        return pages if self._plain else [self._pid(p) for p in pages]
+
+    def _payloads_of(self, pages: List[int]) -> list:
+        return [self._payload(p) for p in pages]
+
+    def _n_points_total(self, n_local: int) -> int:
+        return int(sum(self._gather(int(n_local))))
+
+    def _read_pages(self, name: str, pages: Sequence[int]) -> Dict[int, np.ndarray]:
+        """Collective: every rank reads the listed pages it owns; one object all-gather hands everyone all of them."""
+        base = self.corpus.page_base
+        n = self.corpus.n_pages(name) if self.corpus.has_store(name) else 0
+        mine = {int(p): self.corpus.read_page(name, int(p) - base) for p in pages if 0 <= int(p) - base < n}
+        out: Dict[int, np.ndarray] = {}
+        for part in self._gather(mine):
+            out.update(part)
+        return out
+
+    # local table edits keep working (this rank's pages); they become visible to result building after sync_points()
+    def set_payload(self, point_id, payload: Optional[dict]) -> None:
+        page = self._page(point_id)
+        if page < 0:
+            raise KeyError(point_id)
+        r, loc = self._locate(page)
+        base, n, ids, pls = self._shards[r]
+        if pls is None:
+            pls = [None] * n
+            self._shards[r] = (base, n, ids, pls)
+        pls[loc] = payload
+        if r == self._bases.index(self.corpus.page_base):
+            if self._payloads is None:
+                self._payloads = [None] * n
+            self._payloads[loc] = payload
+            self._invalidate()

@@ -87,6 +87,7 @@ class GpuCorpus:
         self._h = h
         self.device = int(device)
         self.page_base = int(page_base)
+        self.rank, self.world = 0, 1     # set by comm_init: this handle is one shard of a page-sharded corpus
 
     # ------------------------------------------------------------------ lifetime
     def close(self) -> None:
@@ -105,6 +106,45 @@ class GpuCorpus:
 
     def __exit__(self, *exc):
         self.close()
+
+    # ------------------------------------------------------------------ multi-GPU (one process per GPU)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """The 128-byte communicator id rank 0 creates (ncclGetUniqueId) and the host hands to every rank."""
+        buf = C.create_string_buffer(128)
+        N.check(N.load().vrag_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, unique_id: Optional[bytes]) -> None:
+        """Join the communicator of the page-sharded corpus (collective over all `world` ranks). Afterwards `search`,
+        `search_multistage` and `search_multistage_batch` of this handle are collective calls that return the merged
+        GLOBAL lists on every rank (include/vrag_b200.h, multi-GPU section)."""
+        if world > 1 and (unique_id is None or len(unique_id) != 128):
+            raise ValueError("unique_id must be the 128 bytes of GpuCorpus.comm_unique_id() from rank 0")
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        N.check(self._lib.vrag_comm_init(self._h, int(rank), int(world), buf))
+        self.rank, self.world = int(rank), int(world)
+
+    def comm_init_torch(self, group=None) -> None:
+        """comm_init with the id distributed through an initialised torch.distributed process group (any backend)."""
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [self.comm_unique_id() if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self.comm_init(rank, world, box[0])
+
+    def comm_destroy(self) -> None:
+        N.check(self._lib.vrag_comm_destroy(self._h))
+        self.rank, self.world = 0, 1
+
+    def comm_timing_us(self) -> List[float]:
+        """Device time (us) of each collective of the most recent host-facing search on this handle, in issue order."""
+        buf = (C.c_float * 32)()
+        n = C.c_int()
+        N.check(self._lib.vrag_last_comm_timing(self._h, buf, 32, C.byref(n)))
+        return [float(buf[i]) for i in range(min(n.value, 32))]
 
     # ------------------------------------------------------------------ stores
     def add_store(
@@ -276,6 +316,19 @@ class GpuCorpus:
         return self.last_timing_ms()[0]
 
     # ------------------------------------------------------------------ scoring
+    @staticmethod
+    def _cand_arg(candidate_ids):
+        """candidate id list -> (array kept alive by the caller, pointer, count). On a sharded handle the list is
+        rank-local and may be empty: the call is collective and still has to be made, so an empty list travels as a
+        valid pointer with count 0."""
+        if candidate_ids is None:
+            return None, None, 0
+        cand = np.ascontiguousarray(np.asarray(candidate_ids, dtype=np.int64))
+        n = int(cand.size)
+        if n == 0:
+            cand = np.zeros((1,), dtype=np.int64)
+        return cand, cand.ctypes.data_as(C.POINTER(C.c_int64)), n
+
     def score(
         self,
         name: str,
@@ -320,14 +373,9 @@ class GpuCorpus:
         descending, ties by lower id."""
         q = _as_f32_query(query)
         k = int(k)
-        if k < 1 or (candidate_ids is not None and len(candidate_ids) == 0):
+        if k < 1 or (candidate_ids is not None and len(candidate_ids) == 0 and self.world == 1):
             return np.empty((0,), np.float32), np.empty((0,), np.int64)
-        if candidate_ids is None:
-            cand_p, n_cand = None, 0
-        else:
-            cand = np.ascontiguousarray(np.asarray(candidate_ids, dtype=np.int64))
-            n_cand = cand.size
-            cand_p = cand.ctypes.data_as(C.POINTER(C.c_int64))
+        cand, cand_p, n_cand = self._cand_arg(candidate_ids)
         scores = np.empty((k,), dtype=np.float32)
         ids = np.empty((k,), dtype=np.int64)
         cnt = C.c_int()
@@ -365,14 +413,9 @@ class GpuCorpus:
         else:
             q = _as_f32_query(query)
             off_p = None
-        if candidate_ids is None:
-            cand_p, n_cand = None, 0
-        elif len(candidate_ids) == 0:
+        if candidate_ids is not None and len(candidate_ids) == 0 and self.world == 1:
             return [(np.empty((0,), np.float32), np.empty((0,), np.int64)) for _ in stages]
-        else:
-            cand = np.ascontiguousarray(np.asarray(candidate_ids, dtype=np.int64))
-            n_cand = cand.size
-            cand_p = cand.ctypes.data_as(C.POINTER(C.c_int64))
+        cand, cand_p, n_cand = self._cand_arg(candidate_ids)
         names = (C.c_char_p * ns)(*[s[0].encode() for s in stages])
         flags = (C.c_uint32 * ns)(*[query_flags(normalize, bool(s[1]), fp16_query) for s in stages])
         ks = (C.c_int * ns)(*[int(s[2]) for s in stages])
@@ -517,6 +560,18 @@ class GpuCorpus:
                 int(n), int(k), C.c_void_p(out_scores_dev_ptr), C.c_void_p(out_ids_dev_ptr), C.c_void_p(stream),
             )
         )
+
+    def search_multistage_dev(self, stages: Sequence[Tuple[str, bool, int]], query_dev_ptr: int, n_query_rows: int,
+                              out_scores_dev_ptr: int, out_ids_dev_ptr: int, stream: int, normalize: bool = True) -> None:
+        """All stages on the device for a query that is already there; results stay on the device (stage s at
+        [sum(k[:s]), sum(k[:s+1])) of the output arrays), nothing is synchronised. Collective on a sharded handle."""
+        ns = len(stages)
+        names = (C.c_char_p * ns)(*[s[0].encode() for s in stages])
+        flags = (C.c_uint32 * ns)(*[query_flags(normalize, bool(s[1])) for s in stages])
+        ks = (C.c_int * ns)(*[int(s[2]) for s in stages])
+        N.check(self._lib.vrag_search_multistage_dev(self._h, ns, names, flags, ks, C.c_void_p(query_dev_ptr), int(n_query_rows),
+                                                     None, C.c_void_p(out_scores_dev_ptr), C.c_void_p(out_ids_dev_ptr),
+                                                     C.c_void_p(stream)))
 
     # ------------------------------------------------------------------ device-level batched stages (sharded batched search)
     def batch_upload(self, n_stages: int, packed: "PackedQueries", per_stage: bool = False) -> None:

@@ -1,5 +1,5 @@
 """Attribute-compatible stand-ins for the few `qdrant_client.http.models` classes the retrievers build
-(SearchParams, Prefetch, Filter, HasIdCondition, FieldCondition, MatchAny, MatchValue).  The reference
+(SearchParams, Prefetch, Filter, HasIdCondition, FieldCondition, MatchAny, MatchValue, MatchExcept, Range).  The reference
 imports them from qdrant_client (two_stage.py:25-26, three_stage.py:76); the GPU backend only reads their
 attributes, so real qdrant objects work as well."""
 
@@ -39,4 +39,15 @@ class MatchAny(_Kw):
 
 
 class MatchValue(_Kw):
+    pass
+
+
+class MatchExcept(_Kw):
+    def __init__(self, **kw):
+        if "except" in kw:            # qdrant's field is `except_` (alias "except")
+            kw["except_"] = kw.pop("except")
+        super().__init__(**kw)
+
+
+class Range(_Kw):
     pass
