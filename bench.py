@@ -10,9 +10,14 @@ Workload (BASELINE.json configs[3] per-GPU shard; weak scaling): every GPU holds
 device from a counter-based seeded generator. One step = one 20-token query scored against EVERY page
 (exact MaxSim), exact top-10 per shard, NCCL all-gather merge of the per-shard lists.
   value  : pages/s, corpus and query resident in HBM, CUDA-event timed, max over ranks.
-  e2e    : same metric through the public host API (numpy query in, top-10 (score,id) out) — pinned H2D of the
-           query and D2H of the result inside the timed region, wall-clock, max over ranks.
-  extra  : two-stage (tokens_vs_standard_pooling, prefetch_k=256, top-10) QPS / p50 / p95 through the same API.
+  e2e    : same metric through the reference-facing seam — SingleStageRetriever.search(strategy="multi_vector") on the
+           (Sharded)GpuCorpusClient: numpy query in, result dicts out; H2D of the query and D2H of the result inside the
+           timed region, wall-clock, max over ranks.
+  extra  : two-stage (tokens_vs_standard_pooling, prefetch_k=256, top-10) QPS / p50 / p95 through the C ABI and through
+           TwoStageRetriever.search_server_side, with the device time of every collective broken out; at N > 1 the
+           `sharded_parity` block (exhaustive / two-stage / three-stage-batch / filtered lists over a host-generated corpus
+           striped across the ranks == the oracle on the whole corpus, incl. a cross-shard exact tie), the cfg1
+           strong-scaling run (1M pages TOTAL) and cfg4 pooling over all GPUs; at N = 1 the other BASELINE configs.
 """
 from __future__ import annotations
 
@@ -33,6 +38,7 @@ for _p in (ROOT, os.path.join(ROOT, "visual-rag-toolkit_b200")):
         sys.path.insert(0, _p)
 
 TOKENS = 1030          # ColPali-v1.3: 1024 visual + 6 instruction tokens
+VISUAL_TOKENS = 1024
 POOLED_ROWS = 32       # mean_pooling rows per page (colpali_row_mean_pooling)
 Q_TOKENS = 20
 TOP_K = 10
@@ -105,16 +111,51 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_sample_pages_per_s(docs_f32, queries, min_seconds=10.0, max_passes=200):
-    """The oracle's search_exhaustive (= the reference's client-side CPU path, quick_test.py:158-166) timed on
-    a bounded sample: one query after the other over the sampled pages until `min_seconds` of CPU work are done.
-    Returns (pages/s, seconds, blas_threads, passes)."""
+def load_reference():
+    """The UNMODIFIED reference, installed by baseline/install_ref.py into baseline/_ref (git-ignored, shipped to the GPU
+    box): returns its `benchmarks.quick_test` module (search_exhaustive / search_two_stage, quick_test.py:158-206, which
+    call visual_rag.embedding.pooling.compute_maxsim_score) or None when it is not installed."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "benchmarks")):
+        return None
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    try:
+        import logging
+
+        logging.disable(logging.INFO)
+        from benchmarks import quick_test   # the reference's own module, nothing of this repository on that path
+
+        return quick_test
+    except Exception as e:  # noqa: BLE001
+        print(f"bench.py: reference import failed ({e!r}); falling back to the oracle port", file=sys.stderr)
+        return None
+
+
+def cpu_search_fn():
+    """(search_exhaustive(query, docs_f32_list, k) -> [(index, score)], kind) — the reference's own function when
+    baseline/_ref is there (kind "reference"), else the oracle port (kind "port")."""
+    qt = load_reference()
+    if qt is not None:
+        def run(query, docs, k):
+            res = qt.search_exhaustive(query, {i: {"embedding": d} for i, d in enumerate(docs)}, top_k=k)
+            return [(r["id"], r["score"]) for r in res]
+
+        return run, "reference"
     from oracle import maxsim_oracle as MO
 
+    return (lambda query, docs, k: MO.search_exhaustive(query, docs, k)), "port"
+
+
+def cpu_sample_pages_per_s(docs_f32, queries, min_seconds=10.0, max_passes=200):
+    """The reference's client-side CPU path (quick_test.search_exhaustive, quick_test.py:158-166) timed on a bounded
+    sample: one query after the other over the sampled pages until `min_seconds` of CPU work are done.
+    Returns (pages/s, seconds, blas_threads, passes, kind)."""
+    fn, kind = cpu_search_fn()
     t0 = time.perf_counter()
     passes = 0
     while True:
-        MO.search_exhaustive(queries[passes % len(queries)], docs_f32, TOP_K)
+        fn(queries[passes % len(queries)], docs_f32, TOP_K)
         passes += 1
         dt = time.perf_counter() - t0
         if dt >= min_seconds or passes >= max_passes:
@@ -126,7 +167,7 @@ def cpu_sample_pages_per_s(docs_f32, queries, min_seconds=10.0, max_passes=200):
         threads = max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
     except Exception:
         pass
-    return passes * len(docs_f32) / dt, dt, threads, passes
+    return passes * len(docs_f32) / dt, dt, threads, passes, kind
 
 
 def host_sample(n_pages, seed):
@@ -140,6 +181,9 @@ def host_sample(n_pages, seed):
     return docs
 
 
+_REF_FN = None   # set in the parent before the pool forks, so that the workers inherit the imported reference
+
+
 def _ref_worker(args):
     n_pages, seed, qseed, reps = args
     try:
@@ -148,20 +192,18 @@ def _ref_worker(args):
         threadpool_limits(1)
     except Exception:
         pass
-    from oracle import maxsim_oracle as MO
-
     docs = host_sample(n_pages, seed)
     q = np.random.default_rng(qseed).standard_normal((Q_TOKENS, 128)).astype(np.float32)
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        MO.search_exhaustive(q, docs, TOP_K)
+        _REF_FN(q, docs, TOP_K)
         times.append(time.perf_counter() - t0)
     return times
 
 
 def workload_config(pages, world):
-    """`config` of the JSON line — the same dict on both arms (the reference arm adds what it sampled)."""
+    """`config` of the JSON line — the SAME dict on both arms."""
     total_pages = pages * world
     return {
         "workload": f"exhaustive MaxSim top-{TOP_K} over {total_pages} ColPali-shaped pages "
@@ -172,14 +214,18 @@ def workload_config(pages, world):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port of quick_test.search_exhaustive ->
-    compute_maxsim_score) on all host cores: the page sample is split over one process per core, each
-    running the reference's per-page Python loop; a step = one query over the whole sample."""
+    """--impl reference: the reference's own CPU implementation of the path — benchmarks/quick_test.py::search_exhaustive
+    (-> visual_rag.embedding.pooling.compute_maxsim_score), imported unmodified from baseline/_ref — on all host cores: the
+    reference is a single-process per-page Python loop, so the page sample of a step is split over one process per
+    core, each running that function on its slice; a step = one query over the whole sample. Falls back to the oracle
+    port (kind "port") only when baseline/_ref is missing."""
+    global _REF_FN
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import multiprocessing as mp
 
+    _REF_FN, kind = cpu_search_fn()
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     workers = max(1, min(cores, 64))
     pages_per_worker = max(8, args.ref_sample_pages // workers)
@@ -192,17 +238,16 @@ def run_reference(args):
     step_times = [max(r[i] for r in res) for i in range(args.warmup, reps)]
     dt = sum(step_times)
     value = total_pages * args.steps / dt
+    sample = (f"each step scores a bounded sample of {total_pages} pages of this workload, split over {workers} processes "
+              f"(1 BLAS thread each); " + ("benchmarks/quick_test.py::search_exhaustive of the unmodified reference (baseline/_ref)"
+                                           if kind == "reference" else "oracle/maxsim_oracle.py::search_exhaustive (port)"))
     line = {
         "impl": "reference", "metric": "exhaustive_maxsim_pages_per_s", "value": value, "unit": "pages/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args.pages_per_gpu, max(1, args.gpus)),
-                       reference_sample=f"each step scores a bounded sample of {total_pages} pages of this workload on the host cores; "
-                                        "pages/s is the rate over the sample",
-                       pages_per_step=total_pages),
-        "cpu_baseline": {"value": value, "unit": "pages/s", "cores": workers, "kind": "port",
-                         "sample": f"{total_pages} pages/step split over {workers} processes (1 BLAS thread each), "
-                                   "oracle/maxsim_oracle.py::search_exhaustive"},
+        "config": workload_config(args.pages_per_gpu, max(1, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": "pages/s", "cores": workers, "kind": kind, "sample": sample,
+                         "pages_per_step": total_pages},
         "e2e": {"value": value, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -210,6 +255,125 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+def sharded_parity_check(local_rank, rank, world):
+    """N > 1, on hardware: a host-generated corpus (every rank generates the same seeded pages) is striped across the
+    ranks in contiguous page ranges and searched through the reference-facing classes on a ShardedCorpusClient; every
+    rank compares the merged GLOBAL lists with the oracle run over the WHOLE corpus: exhaustive top-10, the two-stage
+    (256 -> 10) lists, a three-stage batch, a payload-filtered search, a full ranking (k = all pages: the long-merge
+    path) and a cross-shard exact tie (two identical pages on the first and the last rank: lower global id first).
+    Returns a dict for the JSON line; never raises (a failure is reported as sharded_parity: false with the reason)."""
+    from oracle import maxsim_oracle as MO
+    from visual_rag_b200.client import ShardedCorpusClient
+    from visual_rag_b200.corpus import GpuCorpus
+    from visual_rag_b200.distributed import shard_page_range
+    from visual_rag_b200.retrieval import SingleStageRetriever, ThreeStageRetriever, TwoStageRetriever
+
+    P = 4096
+    out = {"sharded_parity": False, "pages": P, "checks": []}
+    c2 = None
+    try:
+        rng = np.random.default_rng(SEED + 4242)
+        lens = rng.integers(129, 261, size=P)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        rows = rng.standard_normal((int(off[-1]), 128), dtype=np.float32)
+        rows /= np.linalg.norm(rows, axis=1, keepdims=True)
+        rows = rows.astype(np.float16)
+        tie_a, tie_b = 5, P - 2                      # page P-2 (last rank) := page 5 (rank 0), same row count
+        la, lb = int(lens[tie_a]), int(lens[tie_b])
+        m = min(la, lb)
+        rows[off[tie_b]:off[tie_b] + m] = rows[off[tie_a]:off[tie_a] + m]
+        if lb > m:                                     # longer copy: repeat rows (max over tokens is unchanged)
+            rows[off[tie_b] + m:off[tie_b + 1]] = rows[off[tie_a]:off[tie_a] + (lb - m)]
+        if la > m:
+            rows[off[tie_a] + m:off[tie_a + 1]] = rows[off[tie_a]:off[tie_a] + (la - m)]
+        docs = [rows[off[i]:off[i + 1]].astype(np.float32) for i in range(P)]
+        pooled = [d[:32] for d in docs]
+        glob = [d.mean(axis=0, keepdims=True).astype(np.float16).astype(np.float32) for d in docs]
+        payloads = [{"page": i, "year": 2000 + i % 3} for i in range(P)]
+        b, e = shard_page_range(P, rank, world)
+        c2 = GpuCorpus(local_rank, page_base=b)
+        c2.comm_init_torch()
+        c2.add_store("initial", rows[off[b]:off[e]], page_offsets=off[b:e + 1] - off[b])
+        c2.add_store("mean_pooling", np.concatenate(pooled[b:e]).astype(np.float16), fixed_rows=32)
+        c2.add_store("global_pooling", np.concatenate(glob[b:e]).astype(np.float16), fixed_rows=1)
+        client = ShardedCorpusClient(c2, "parity", payloads=payloads[b:e])
+        single = SingleStageRetriever(client, "parity")
+        two = TwoStageRetriever(client, "parity")
+        three = ThreeStageRetriever(client, "parity", experimental_vector_name="mean_pooling")
+        qs = [rng.standard_normal((int(rng.integers(10, 31)), 128)).astype(np.float32) for _ in range(6)]
+
+        def same(got, want, what):
+            gi, wi = [g["id"] for g in got], [i for i, _ in want]
+            if gi != wi:
+                raise AssertionError(f"{what}: ids differ {gi[:12]} vs {wi[:12]}")
+            gs, ws = np.array([g["score_final"] for g in got]), np.array([x for _, x in want])
+            if not np.allclose(gs, ws, rtol=2e-5, atol=2e-6):
+                raise AssertionError(f"{what}: scores differ by {np.abs(gs - ws).max()}")
+            out["checks"].append(what)
+
+        for j, q in enumerate(qs[:3]):
+            same(single.search(q, top_k=10, strategy="multi_vector"), MO.search_exhaustive(q, docs, 10), f"exhaustive_top10_q{j}")
+            ref = MO.multistage(q, [(pooled, False, PREFETCH_K), (docs, False, TOP_K)])
+            same(two.search_server_side(q, top_k=TOP_K, prefetch_k=PREFETCH_K, stage1_mode="tokens_vs_standard_pooling"), ref[1],
+                 f"two_stage_256_10_q{j}")
+        got = three.search_server_side_batch(query_embeddings=qs, top_k=10, stage1_k=100, stage2_k=30)
+        for j, q in enumerate(qs):
+            ref = MO.multistage(q, [(glob, True, 100), (pooled, False, 30), (docs, False, 10)])
+            same(got[j], ref[2], f"three_stage_batch_q{j}")
+        keep = [i for i in range(P) if payloads[i]["year"] == 2001]
+        ref = MO.search_exhaustive(qs[0], [docs[i] for i in keep], 10)
+        same(single.search(qs[0], top_k=10, strategy="multi_vector", filter_obj=two.build_filter(year=2001)),
+             [(keep[i], x) for i, x in ref], "filtered_top10_year2001")
+        full = single.search(qs[1], top_k=P, strategy="multi_vector")
+        ids = [g["id"] for g in full]
+        want = MO.search_exhaustive(qs[1], docs, P)
+        if sorted(ids) != list(range(P)):
+            raise AssertionError("full ranking is not a permutation of all pages")
+        if ids.index(tie_a) + 1 != ids.index(tie_b):
+            raise AssertionError(f"cross-shard tie: page {tie_a} at {ids.index(tie_a)}, page {tie_b} at {ids.index(tie_b)}")
+        if ids[:200] != [i for i, _ in want[:200]]:
+            raise AssertionError("full ranking: first 200 ids differ from the oracle")
+        out["checks"].append("full_ranking_k4096_cross_shard_tie")
+        # ---- shards of >= 8192 pages: the host-facing search takes the SAMPLED local top-k; its miss flag travels in the
+        # exchanged entries. Store A: random pages (estimate holds). Store B: 90 % identical pages (massive ties: the
+        # estimate misses on every rank and all ranks redo the search exactly, together).
+        n_big, r_big = 12288, 8
+        big = rng.standard_normal((n_big * world * r_big, 128), dtype=np.float32)
+        big /= np.linalg.norm(big, axis=1, keepdims=True)
+        big = big.astype(np.float16).reshape(n_big * world, r_big, 128)
+        tied = big.copy()
+        tied[np.arange(n_big * world) % 10 != 0] = big[1]
+        lo, hi = rank * n_big, (rank + 1) * n_big
+        c3 = GpuCorpus(local_rank, page_base=lo)
+        try:
+            c3.comm_init_torch()
+            c3.add_store("a", big[lo:hi].reshape(-1, 128), fixed_rows=r_big)
+            c3.add_store("b", tied[lo:hi].reshape(-1, 128), fixed_rows=r_big)
+            q_tie = big[1, :4].astype(np.float32)    # the tied pages are this query's best matches: ~90 % of all scores tie at the top
+            for name, arr, qq, what in (("a", big, qs[2], "sampled_topk_through_exchange"),
+                                        ("b", tied, q_tie, "sampled_miss_flag_redo_all_ranks")):
+                sc, ids = c3.search(name, qq, 50)
+                want = MO.search_exhaustive(qq, [x.astype(np.float32) for x in arr], 50)
+                if [int(i) for i in ids] != [i for i, _ in want]:
+                    raise AssertionError(f"{what}: ids differ {ids[:8].tolist()} vs {[i for i, _ in want[:8]]}")
+                if not np.allclose(sc, [x for _, x in want], rtol=2e-5, atol=2e-6):
+                    raise AssertionError(f"{what}: scores differ")
+                out["checks"].append(what)
+        finally:
+            c3.close()
+        out["sharded_parity"] = True
+        out["comm_us_last_search"] = c2.comm_timing_us()
+    except Exception as e:  # noqa: BLE001
+        out["error"] = repr(e)[:400]
+    finally:
+        if c2 is not None:
+            try:
+                c2.close()
+            except Exception:
+                pass
+    return out
+
+
 def run_ours(args):
     import torch
 
@@ -235,27 +399,40 @@ def run_ours(args):
             __graft_entry__.build()
         if dist is not None:
             dist.barrier()
-    from visual_rag_b200.corpus import GpuCorpus
+    from visual_rag_b200.client import GpuCorpusClient, ShardedCorpusClient
+    from visual_rag_b200.corpus import GpuCorpus, query_flags
     from visual_rag_b200.distributed import ShardedSearcher
-
-    pages = args.pages_per_gpu
-    corpus = GpuCorpus(local_rank, page_base=rank * pages)
-    t_gen0 = time.perf_counter()
-    corpus.add_synthetic_store("initial", pages, fixed_rows=TOKENS, seed=SEED, row_seed_base=rank * pages * TOKENS)
-    gen_s = time.perf_counter() - t_gen0
-    # mean_pooling is DERIVED on the device with the pooling kernels: 1030 tokens is not a square grid, so the
-    # reference takes its sequence-chunk path (visual_embedder.py:824-835) -> 32 rows per page.
     from visual_rag_b200.embedding import pooling as GP
-
-    pool_ms = corpus.pool_store("initial", [GP.spec_seq_chunks(POOLED_ROWS)], ["mean_pooling"])
-    searcher = ShardedSearcher(corpus)
-    rng = np.random.default_rng(SEED + 7)
-    queries = [rng.standard_normal((Q_TOKENS, 128)).astype(np.float32) for _ in range(max(8, args.steps + args.warmup))]
+    from visual_rag_b200.retrieval import SingleStageRetriever, TwoStageRetriever
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(values):
+        t = torch.tensor([float(v) for v in values], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.cpu()]
+
+    pages = args.pages_per_gpu
+    corpus = GpuCorpus(local_rank, page_base=rank * pages)
+    if world > 1:
+        corpus.comm_init_torch()          # the library's own communicator (C ABI: vrag_comm_init); the id travels via torch
+    t_gen0 = time.perf_counter()
+    corpus.add_synthetic_store("initial", pages, fixed_rows=TOKENS, seed=SEED, row_seed_base=rank * pages * TOKENS)
+    gen_s = time.perf_counter() - t_gen0
+    # cfg1: mean_pooling = colpali_row_mean_pooling (p2) of the page's 1024 VISUAL tokens (32 x 32 grid -> 32 rows); the
+    # 6 instruction tokens behind them are part of `initial` only. Derived on the device.
+    mean_spec = GP.with_token_window(GP.spec_adaptive_rows(32, 32, POOLED_ROWS), 0, VISUAL_TOKENS)
+    pool_ms = corpus.pool_store("initial", [mean_spec], ["mean_pooling"])
+    searcher = ShardedSearcher(corpus)
+    client = ShardedCorpusClient(corpus, "bench") if world > 1 else GpuCorpusClient(corpus, "bench")
+    single = SingleStageRetriever(client, "bench")
+    two = TwoStageRetriever(client, "bench")
+    rng = np.random.default_rng(SEED + 7)
+    queries = [rng.standard_normal((Q_TOKENS, 128)).astype(np.float32) for _ in range(max(8, args.steps + args.warmup))]
 
     ex_stage = [("initial", False, TOP_K)]
     ts_stages = [("mean_pooling", False, PREFETCH_K), ("initial", False, TOP_K)]
@@ -265,9 +442,9 @@ def run_ours(args):
         from oracle import maxsim_oracle as MO
 
         sc = corpus.score("initial", queries[0], candidate_ids=[corpus.page_base + 3, corpus.page_base + pages - 1])
-        for s, p in zip(sc, (3, pages - 1)):
-            want = MO.maxsim_score(queries[0], corpus.read_page("initial", p).astype(np.float32))
-            assert abs(s - want) <= 1e-3 * abs(want), ("parity spot check failed", s, want)
+        for s_, p_ in zip(sc, (3, pages - 1)):
+            want = MO.maxsim_score(queries[0], corpus.read_page("initial", p_).astype(np.float32))
+            assert abs(s_ - want) <= 1e-3 * abs(want), ("parity spot check failed", s_, want)
 
     # ---------------- device-resident throughput (value) ----------------
     nq = searcher.upload_query(queries[0])
@@ -284,18 +461,17 @@ def run_ours(args):
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        searcher.search_multistage_device(ex_stage, nq)
+        dev_res = searcher.search_multistage_device(ex_stage, nq)
     ev1.record()
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = corpus.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    dev_top = (dev_res[0][0].cpu().numpy(), dev_res[0][1].cpu().numpy())
 
     # ---------------- dominant kernel alone (roofline numerator), same stream, CUDA events ----------------
     scores_buf = torch.empty((pages,), dtype=torch.float32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
-    from visual_rag_b200.corpus import query_flags
-
     for _ in range(2):
         corpus.score_dev("initial", searcher._q_dev.data_ptr(), nq, query_flags(True, False), 0, pages, scores_buf.data_ptr(), stream)
     torch.cuda.synchronize()
@@ -318,57 +494,74 @@ def run_ours(args):
     torch.cuda.synchronize()
     kern16_ms = k0.elapsed_time(k1) / args.steps
 
-    # ---------------- end to end through the host API ----------------
+    # ---------------- end to end through the reference-facing seam ----------------
+    # SingleStageRetriever.search(strategy="multi_vector") -> client.query_points -> C ABI (collective at N > 1):
+    # numpy query in (H2D inside), result dicts out (D2H inside). The host-facing search may use the sampled top-k;
+    # its list must equal the device-resident (exact radix-select) list of the same query.
     for i in range(args.warmup):
-        searcher.search("initial", queries[i % len(queries)], TOP_K)
+        single.search(queries[i % len(queries)], top_k=TOP_K, strategy="multi_vector")
     barrier()
     t0 = time.perf_counter()
     last = None
     for i in range(args.steps):
-        last = searcher.search("initial", queries[i % len(queries)], TOP_K)
+        last = single.search(queries[i % len(queries)], top_k=TOP_K, strategy="multi_vector")
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    first = single.search(queries[0], top_k=TOP_K, strategy="multi_vector")
+    host_equals_device = ([h["id"] for h in first] == [int(i) for i in dev_top[1]]
+                          and np.allclose([h["score"] for h in first], dev_top[0], rtol=1e-6))
 
-    # ---------------- two-stage latency (extra) ----------------
-    n_lat = args.latency_queries
-    for i in range(5):
-        searcher.search_multistage(ts_stages, queries[i % len(queries)])
-    barrier()
-    lat = []
-    t_all0 = time.perf_counter()
-    for i in range(n_lat):
-        t1 = time.perf_counter()
-        searcher.search_multistage(ts_stages, queries[i % len(queries)])
-        lat.append(1e3 * (time.perf_counter() - t1))
-    ts_wall = time.perf_counter() - t_all0
-    barrier()
-
-    # the same two-stage search through the reference-facing class (TwoStageRetriever.search_server_side on the
-    # GpuCorpusClient: result dicts with payloads), single shard only — the sharded path has no per-shard client
-    retr_lat = None
-    if world == 1:
-        from visual_rag_b200.client import GpuCorpusClient
-        from visual_rag_b200.retrieval import TwoStageRetriever
-
-        retr = TwoStageRetriever(GpuCorpusClient(corpus, "bench"), "bench")
+    # ---------------- two-stage latency (extra): C ABI and retriever class ----------------
+    def two_stage_latency(n_lat):
         for i in range(5):
-            retr.search_server_side(queries[i % len(queries)], top_k=TOP_K, prefetch_k=PREFETCH_K, stage1_mode="tokens_vs_standard_pooling")
-        retr_lat = []
+            corpus.search_multistage(ts_stages, queries[i % len(queries)])
+        barrier()
+        lat, comm = [], []
+        t_all0 = time.perf_counter()
         for i in range(n_lat):
             t1 = time.perf_counter()
-            hits = retr.search_server_side(queries[i % len(queries)], top_k=TOP_K, prefetch_k=PREFETCH_K,
-                                           stage1_mode="tokens_vs_standard_pooling")
-            retr_lat.append(1e3 * (time.perf_counter() - t1))
+            corpus.search_multistage(ts_stages, queries[i % len(queries)])
+            lat.append(1e3 * (time.perf_counter() - t1))
+            if world > 1 and i % 16 == 0:
+                comm.append(corpus.comm_timing_us())
+        wall = time.perf_counter() - t_all0
+        dev_total_ms = corpus.last_timing_ms()[0]
+        barrier()
+        for i in range(5):
+            two.search_server_side(queries[i % len(queries)], top_k=TOP_K, prefetch_k=PREFETCH_K, stage1_mode="tokens_vs_standard_pooling")
+        barrier()
+        rlat = []
+        for i in range(n_lat):
+            t1 = time.perf_counter()
+            hits = two.search_server_side(queries[i % len(queries)], top_k=TOP_K, prefetch_k=PREFETCH_K,
+                                          stage1_mode="tokens_vs_standard_pooling")
+            rlat.append(1e3 * (time.perf_counter() - t1))
         assert len(hits) == TOP_K
+        barrier()
+        wall, p50, p95, r50, r95, dev_total_ms = max_over_ranks([wall, np.percentile(lat, 50), np.percentile(lat, 95),
+                                                                np.percentile(rlat, 50), np.percentile(rlat, 95), dev_total_ms])
+        res = {"qps": n_lat / wall, "p50_ms": p50, "p95_ms": p95, "queries": n_lat, "retriever_p50_ms": r50, "retriever_p95_ms": r95,
+               "device_ms_last_query": dev_total_ms}
+        if comm:
+            med = np.median(np.array(comm), axis=0)
+            res["collective_us"] = {"stage1_allgather_topk256": float(med[0]), "stage2_allreduce_max_256": float(med[1]),
+                                    "note": "device time (CUDA events) of each collective, median of sampled queries, rank 0"}
+        return res
+
+    ts = two_stage_latency(args.latency_queries)
 
     # ---------------- max over ranks ----------------
-    vals = torch.tensor([dev_ms, e2e_s, kern_ms, ts_wall, float(np.percentile(lat, 50)), float(np.percentile(lat, 95))],
-                        dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s, kern_ms, ts_wall, p50, p95 = [float(v) for v in vals.cpu()]
+    dev_ms, e2e_s, kern_ms, kern16_ms = max_over_ranks([dev_ms, e2e_s, kern_ms, kern16_ms])
 
+    # ---------------- N > 1: merged lists on hardware vs the oracle on the whole corpus (all ranks take part) --------
+    parity = sharded_parity_check(local_rank, rank, world) if world > 1 else None
+    if parity is not None:
+        ok = max_over_ranks([0.0 if parity["sharded_parity"] else 1.0])[0] == 0.0
+        parity["all_ranks"] = bool(ok)
+        parity["sharded_parity"] = bool(parity["sharded_parity"] and ok)
+
+    line = None
     if rank == 0:
         total_pages = pages * world
         peak, peak_src = measured_peaks()
@@ -377,13 +570,10 @@ def run_ours(args):
         # CPU baseline on a bounded sample of the SAME corpus (pages read back from the device)
         n_cpu = args.cpu_sample_pages
         docs = [corpus.read_page("initial", p).astype(np.float32) for p in range(n_cpu)]
-        # the timed CPU leg runs at N=1 only; at N>1 one pass still checks the GPU top-k against the oracle
-        cpu_pps, cpu_s, blas_threads, cpu_passes = cpu_sample_pages_per_s(docs, queries, args.cpu_seconds if world == 1 else 0.0)
-        gpu_top = corpus.search("initial", queries[0], TOP_K, candidate_ids=list(range(corpus.page_base, corpus.page_base + n_cpu)))
-        from oracle import maxsim_oracle as MO
-
-        cpu_top = MO.search_exhaustive(queries[0], docs, TOP_K)
-        parity_ok = [int(i) for i in gpu_top[1]] == [corpus.page_base + i for i, _ in cpu_top]
+        # the timed CPU leg runs at N=1 only; at N>1 one pass still checks the GPU top-k against the CPU path
+        cpu_pps, cpu_s, blas_threads, cpu_passes, cpu_kind = cpu_sample_pages_per_s(docs, queries, args.cpu_seconds if world == 1 else 0.0)
+        fn, _ = cpu_search_fn()
+        cpu_top = fn(queries[0], docs, TOP_K)
         line = {
             "metric": "exhaustive_maxsim_pages_per_s",
             "value": total_pages * args.steps / (dev_ms * 1e-3),
@@ -394,13 +584,18 @@ def run_ours(args):
             "dtype": "f16",
             "dtype_detail": "fp16 tensor-core operands, fp32 accumulate; the fp32 query is carried as an fp16 hi/lo pair (fp32-exact)",
             "data": "synthetic",
-            "config": dict(workload_config(pages, world),
-                           l2="input (>=26 GB per step) is far larger than the 126 MB L2; no flush needed",
-                           corpus_generation_s=gen_s),
+            "config": workload_config(pages, world),
+            "notes": {"l2": "input (>=26 GB per step) is far larger than the 126 MB L2; no flush needed", "corpus_generation_s": gen_s,
+                      "exchange": "C ABI (vrag_comm_init / one packed all-gather per scanning stage, one max-all-reduce per "
+                                  "candidate stage); NCCL resolved by the library at run time" if world > 1 else "single shard"},
             "hbm_gbs_algorithmic": total_pages * bytes_per_page * args.steps / (dev_ms * 1e-3) / 1e9,
             "e2e": {"value": total_pages * args.steps / e2e_s, "unit": "pages/s",
-                    "h2d_bytes_per_step": Q_TOKENS * 128 * 4, "d2h_bytes_per_step": TOP_K * (4 + 8),
-                    "ms_per_step": 1e3 * e2e_s / args.steps},
+                    "h2d_bytes_per_step": Q_TOKENS * 128 * 4, "d2h_bytes_per_step": TOP_K * (4 + 8) + 36,
+                    "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "call": "SingleStageRetriever.search(q, top_k=10, strategy='multi_vector') on the "
+                            + ("ShardedCorpusClient (collective, every rank)" if world > 1 else "GpuCorpusClient"),
+                    "frac_of_value": (total_pages * args.steps / e2e_s) / (total_pages * args.steps / (dev_ms * 1e-3)),
+                    "host_list_equals_device_list": bool(host_equals_device)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "vrag::maxsim_scan_kernel<QP=24 (MMA N=48), LARGE>", "achieved": achieved,
@@ -411,38 +606,137 @@ def run_ours(args):
                          "traffic_source": "dram__bytes_read+write per launch / algorithmic bytes = 1.0104 in the ncu --set full capture of "
                                            "this same launch shape, 500k pages (profiles/r1e_kernels_ncu_summary.md, column `large_500k`: "
                                            "135.285 GB read + 9.7 MB written vs 133.9 GB algorithmic); scaled by pages for other sizes"},
-            "cpu_baseline": {"value": cpu_pps, "unit": "pages/s", "cores": blas_threads, "kind": "port",
+            "cpu_baseline": {"value": cpu_pps, "unit": "pages/s", "cores": blas_threads, "kind": cpu_kind,
                              "sample": f"first {n_cpu} pages of the same corpus read back from the device, {cpu_passes} queries one after "
-                                       f"the other ({cpu_passes * n_cpu} page scorings, {cpu_s:.1f} s); oracle/maxsim_oracle.py::search_exhaustive "
-                                       f"(single process, numpy BLAS threads={blas_threads})",
-                             "topk_matches_gpu": bool(parity_ok)} if world == 1 else
-                            {"value": None, "note": "timed at N=1 only", "topk_matches_gpu": bool(parity_ok)},
+                                       f"the other ({cpu_passes * n_cpu} page scorings, {cpu_s:.1f} s); "
+                                       + ("benchmarks/quick_test.py::search_exhaustive of the unmodified reference (baseline/_ref)"
+                                          if cpu_kind == "reference" else "oracle/maxsim_oracle.py::search_exhaustive")
+                                       + f" (single process, numpy BLAS threads={blas_threads})"} if world == 1 else
+                            {"value": None, "note": "timed at N=1 only", "kind": cpu_kind},
             "fp16_query_variant": {"flag": "VRAG_Q_FP16 (opt-in; default is the fp32-exact hi/lo query)", "kernel_ms": kern16_ms,
                                    "hbm_gbs": pages * bytes_per_page / (kern16_ms * 1e-3) / 1e9,
                                    "frac": pages * bytes_per_page / (kern16_ms * 1e-3) / 1e9 / peak},
-            "two_stage": {"mode": "tokens_vs_standard_pooling", "prefetch_k": PREFETCH_K, "top_k": TOP_K,
-                          "qps": n_lat / ts_wall, "p50_ms": p50, "p95_ms": p95, "queries": n_lat,
-                          "pooled_rows_per_page": POOLED_ROWS,
-                          "retriever_p50_ms": float(np.percentile(retr_lat, 50)) if retr_lat else None,
-                          "retriever_p95_ms": float(np.percentile(retr_lat, 95)) if retr_lat else None,
-                          "retriever_call": "TwoStageRetriever.search_server_side(q, top_k=10, prefetch_k=256, "
-                                            "stage1_mode='tokens_vs_standard_pooling') -> result dicts (N=1 only)",
-                          "note": "mean_pooling derived on the device from `initial` (sequence-chunk mean pooling, 32 rows/page)"},
-            "pooling": {"kind": "seq_chunks 1030 -> 32 rows/page (visual_embedder.py:824-835), fp16 in / fp16 out",
+            "two_stage": dict({"mode": "tokens_vs_standard_pooling", "prefetch_k": PREFETCH_K, "top_k": TOP_K,
+                               "total_pages": total_pages, "pooled_rows_per_page": POOLED_ROWS,
+                               "retriever_call": "TwoStageRetriever.search_server_side(q, top_k=10, prefetch_k=256, "
+                                                 "stage1_mode='tokens_vs_standard_pooling') -> result dicts",
+                               "note": "mean_pooling = colpali_row_mean_pooling of the 1024 visual tokens (32 rows/page), derived on the device"},
+                              **ts),
+            "pooling": {"kind": "colpali_row_mean_pooling (p2) over the 1024 visual tokens of each 1030-token page -> 32 rows, fp16 in / fp16 out",
                         "pages_per_s_per_gpu": pages / (pool_ms * 1e-3), "ms": pool_ms,
-                        "hbm_gbs": pages * (TOKENS * 256 + POOLED_ROWS * 256) / (pool_ms * 1e-3) / 1e9},
-            "last_top1": [float(last[0][0]), int(last[1][0])] if last is not None and len(last[0]) else None,
+                        "hbm_gbs": pages * (VISUAL_TOKENS * 256 + POOLED_ROWS * 256) / (pool_ms * 1e-3) / 1e9},
+            "last_top1": [float(last[0]["score"]), int(last[0]["id"])] if last else None,
         }
-        if world == 1 and args.extras:
-            try:
-                line.update(run_extras(corpus, args, peak, kern_ms))
-            except Exception as e:  # extras must never cost the headline line
+        # the first n_cpu pages live on rank 0: the GPU's candidate-restricted top-10 over them vs the CPU path
+        gpu_top = corpus.score("initial", queries[0], candidate_ids=list(range(corpus.page_base, corpus.page_base + n_cpu)))
+        order = np.lexsort((np.arange(n_cpu), -gpu_top))[:TOP_K]
+        line["cpu_baseline"]["topk_matches_gpu"] = bool([int(i) for i in order] == [int(i) for i, _ in cpu_top])
+        if parity is not None:
+            line["sharded_parity"] = parity["sharded_parity"]
+            line["sharded_parity_detail"] = parity
+    if args.extras:
+        try:
+            if world == 1:
+                extra = run_extras(corpus, args, measured_peaks()[0], kern_ms)
+            else:
+                extra = run_multi_extras(corpus, client, two, args, rank, world, barrier, max_over_ranks, queries, ts)
+            if line is not None:
+                line.update(extra)
+        except Exception as e:  # extras must never cost the headline line
+            if line is not None:
                 line["extras_error"] = repr(e)
+    if line is not None:
         print(json.dumps(line))
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
     corpus.close()
     return 0
+
+
+def run_multi_extras(corpus, client, two, args, rank, world, barrier, max_over_ranks, queries, ts_weak):
+    """N > 1, after the headline measurements (all ranks take part):
+      two_stage_strong : BASELINE configs[1] as stated — 1M pages TOTAL (1M / N per GPU), tokens_vs_standard_pooling
+                         256 -> 10, single query: p50 / p95 / QPS through the C ABI and the retriever class, the device
+                         time of each collective, and the ideal stage-1 scan time of the shard for scale.
+      pooling_cfg4     : BASELINE configs[4] — 1M ColPali-shaped pages over the N GPUs (no collective), all pooled
+                         stores of the collection in one pass."""
+    import torch
+
+    from visual_rag_b200.embedding import pooling as GP
+
+    out = {}
+    peak = measured_peaks()[0]
+    total = args.total_pages
+    per = total // world
+    pages_main = corpus.n_pages("initial")
+    if per == pages_main:
+        strong = dict(ts_weak)
+    else:
+        for nm in ("initial", "mean_pooling"):
+            corpus.drop_store(nm)
+        corpus.add_synthetic_store("initial", per, fixed_rows=TOKENS, seed=SEED + 21, row_seed_base=rank * per * TOKENS)
+        corpus.pool_store("initial", [GP.with_token_window(GP.spec_adaptive_rows(32, 32, POOLED_ROWS), 0, VISUAL_TOKENS)], ["mean_pooling"])
+        if hasattr(client, "sync_points"):
+            client.sync_points()
+        ts_stages = [("mean_pooling", False, PREFETCH_K), ("initial", False, TOP_K)]
+        for i in range(5):
+            corpus.search_multistage(ts_stages, queries[i % len(queries)])
+        barrier()
+        lat, comm = [], []
+        t0 = time.perf_counter()
+        for i in range(args.latency_queries):
+            t1 = time.perf_counter()
+            corpus.search_multistage(ts_stages, queries[i % len(queries)])
+            lat.append(1e3 * (time.perf_counter() - t1))
+            if i % 16 == 0:
+                comm.append(corpus.comm_timing_us())
+        wall = time.perf_counter() - t0
+        dev_ms = corpus.last_timing_ms()[0]
+        barrier()
+        for i in range(5):
+            two.search_server_side(queries[i % len(queries)], top_k=TOP_K, prefetch_k=PREFETCH_K, stage1_mode="tokens_vs_standard_pooling")
+        barrier()
+        rlat = []
+        for i in range(args.latency_queries):
+            t1 = time.perf_counter()
+            two.search_server_side(queries[i % len(queries)], top_k=TOP_K, prefetch_k=PREFETCH_K, stage1_mode="tokens_vs_standard_pooling")
+            rlat.append(1e3 * (time.perf_counter() - t1))
+        barrier()
+        wall, p50, p95, r50, r95, dev_ms = max_over_ranks([wall, np.percentile(lat, 50), np.percentile(lat, 95),
+                                                          np.percentile(rlat, 50), np.percentile(rlat, 95), dev_ms])
+        med = np.median(np.array(comm), axis=0)
+        strong = {"qps": args.latency_queries / wall, "p50_ms": p50, "p95_ms": p95, "queries": args.latency_queries,
+                  "retriever_p50_ms": r50, "retriever_p95_ms": r95, "device_ms_last_query": dev_ms,
+                  "collective_us": {"stage1_allgather_topk256": float(med[0]), "stage2_allreduce_max_256": float(med[1])}}
+    ideal_ms = per * POOLED_ROWS * (256 + 4) / (peak * 1e9) * 1e3 + PREFETCH_K / world * TOKENS * 260 / (peak * 1e9) * 1e3
+    out["two_stage_strong"] = dict(strong, total_pages=per * world, pages_per_gpu=per, mode="tokens_vs_standard_pooling",
+                                   prefetch_k=PREFETCH_K, top_k=TOP_K,
+                                   ideal_scan_ms_at_measured_hbm_peak=ideal_ms,
+                                   p50_over_ideal=strong["p50_ms"] / ideal_ms,
+                                   workload="BASELINE configs[1]: 1M ColPali pages TOTAL, strong scaling")
+    # ---- cfg4 over all GPUs
+    for nm in ("initial", "mean_pooling"):
+        if corpus.has_store(nm):
+            corpus.drop_store(nm)
+    npg = args.cfg4_total_pages // world
+    corpus.add_synthetic_store("vis", npg, fixed_rows=1024, seed=SEED + 4, row_seed_base=rank * npg * 1024)
+    specs = [GP.spec_adaptive_rows(32, 32, 32)] + [GP.derived_from(x, 0) for x in (
+        GP.spec_legacy_conv(3), GP.spec_smooth(3, "gaussian"), GP.spec_smooth(3, "triangular"), GP.spec_global_mean(True))]
+    names = ["mean_pooling", "experimental_pooling", "experimental_pooling_gaussian", "experimental_pooling_triangular", "global_pooling"]
+    for _ in range(3):
+        barrier()
+        ms = corpus.pool_store("vis", specs, names)
+    ms = max_over_ranks([ms])[0]
+    b = npg * (1024 * 256 + (32 + 34 + 32 + 32 + 1) * 256)
+    out["pooling_cfg4"] = {"colpali": {"total_pages": npg * world, "pages_per_gpu": npg, "ms_max_over_ranks": ms,
+                                       "pages_per_s": npg * world / (ms * 1e-3), "hbm_gbs_algorithmic_per_gpu": b / (ms * 1e-3) / 1e9,
+                                       "frac_of_peak": b / (ms * 1e-3) / 1e9 / peak, "collective": "none (pages are independent)",
+                                       "stores": "row-mean 32 + legacy k=3 (34) + gaussian (32) + triangular (32) + global (1), one pass"}}
+    for nm in names + ["vis"]:
+        corpus.drop_store(nm)
+    torch.cuda.synchronize()
+    return out
 
 
 def run_extras(corpus, args, peak, kern_ms):
@@ -592,12 +886,25 @@ def run_cfg0(corpus, args, rng):
     pooled = [praw[i * 12:(i + 1) * 12] for i in range(n0)]
     n_cpu = max(1, args.cfg0_cpu_queries)
     same_ex = same_ts = True
-    t1 = time.perf_counter()
-    cpu_ex = [MO.search_exhaustive(q, docs, TOP_K) for q in qs[:n_cpu]]
-    cpu_ex_s = (time.perf_counter() - t1) / n_cpu
-    t1 = time.perf_counter()
-    cpu_ts = [MO.search_two_stage_pooled(q, docs, pooled, 256, TOP_K) for q in qs[:n_cpu]]
-    cpu_ts_s = (time.perf_counter() - t1) / n_cpu
+    qt = load_reference()
+    if qt is not None:   # the reference's own functions on its own document dictionary (quick_test.py:158-206)
+        ddict = {i: {"embedding": docs[i], "pooled": pooled[i]} for i in range(n0)}
+        t1 = time.perf_counter()
+        cpu_ex = [[(r["id"], r["score"]) for r in qt.search_exhaustive(q, ddict, top_k=TOP_K)] for q in qs[:n_cpu]]
+        cpu_ex_s = (time.perf_counter() - t1) / n_cpu
+        t1 = time.perf_counter()
+        cpu_ts = [[(r["id"], r["score"], r["stage1_rank"]) for r in qt.search_two_stage(q, ddict, prefetch_k=256, top_k=TOP_K)]
+                  for q in qs[:n_cpu]]
+        cpu_ts_s = (time.perf_counter() - t1) / n_cpu
+        cpu_kind = "reference (benchmarks/quick_test.py::search_exhaustive / search_two_stage, unmodified, baseline/_ref), single process"
+    else:
+        t1 = time.perf_counter()
+        cpu_ex = [MO.search_exhaustive(q, docs, TOP_K) for q in qs[:n_cpu]]
+        cpu_ex_s = (time.perf_counter() - t1) / n_cpu
+        t1 = time.perf_counter()
+        cpu_ts = [MO.search_two_stage_pooled(q, docs, pooled, 256, TOP_K) for q in qs[:n_cpu]]
+        cpu_ts_s = (time.perf_counter() - t1) / n_cpu
+        cpu_kind = "port (oracle/maxsim_oracle.py::search_exhaustive / search_two_stage_pooled = benchmarks/quick_test.py:158-206), single process"
     max_rel = 0.0
     for q, ce, ct in zip(qs, cpu_ex, cpu_ts):
         s, ids = corpus.search("initial", q, TOP_K)
@@ -616,7 +923,7 @@ def run_cfg0(corpus, args, rng):
         "gpu_two_stage_p50_ms": float(np.percentile(lat_ts, 50)), "gpu_two_stage_qps": 1e3 / float(np.mean(lat_ts)),
         "cpu_exhaustive_s_per_query": cpu_ex_s, "cpu_exhaustive_pages_per_s": n0 / cpu_ex_s,
         "cpu_two_stage_s_per_query": cpu_ts_s, "cpu_queries": n_cpu,
-        "cpu_kind": "port (oracle/maxsim_oracle.py::search_exhaustive / search_two_stage_pooled = benchmarks/quick_test.py:158-206), single process",
+        "cpu_kind": cpu_kind,
         "top10_ids_identical_exhaustive": bool(same_ex), "top10_ids_identical_two_stage": bool(same_ts),
         "max_rel_score_diff": max_rel,
     }
@@ -638,6 +945,8 @@ def main():
     ap.add_argument("--cfg0-cpu-queries", type=int, default=2)
     ap.add_argument("--cfg2-pages", type=int, default=1_000_000)
     ap.add_argument("--cfg4-pages", type=int, default=400_000)
+    ap.add_argument("--total-pages", type=int, default=1_000_000, help="N>1: corpus size of the cfg1 strong-scaling two-stage run")
+    ap.add_argument("--cfg4-total-pages", type=int, default=1_000_000, help="N>1: pages pooled over all GPUs (cfg4)")
     ap.add_argument("--ncu-traffic-ratio", type=float, default=1.0104,
                     help="DRAM bytes / algorithmic bytes of the scan kernel in the committed ncu capture (profiles/)")
     args = ap.parse_args()

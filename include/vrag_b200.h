@@ -205,6 +205,10 @@ typedef struct vrag_pool_spec {
                              call (a token-level spec): the pipeline's "experimental / global pooling of the mean-pooled
                              rows" (pipeline.py:452-507), computed inside that spec's pass from shared memory — the pooled
                              rows are used as stored (rounded to the store dtype), never re-read from HBM.            */
+  int in_row_skip;        /* token-level kinds of vrag_store_pool (input_spec == 0): pool only rows [in_row_skip, in_row_skip +  */
+  int in_row_count;       /* in_row_count) of every source page (count <= 0: to the page end) — the pipeline pools the VISUAL
+                             tokens of a page (visual_token_indices, pipeline.py:400-430) while `initial` also keeps the
+                             instruction tokens: ColPali-v1.3 pages are 1024 visual + 6 text tokens.   */
 } vrag_pool_spec_t;
 
 /* Rows this spec produces for a page of in_rows rows (host arithmetic only; validates the arguments with the

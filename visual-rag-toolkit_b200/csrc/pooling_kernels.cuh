@@ -65,6 +65,7 @@ struct PoolInput {
   long long in_fixed;
   long long n_pages;
   const int* grid_hw;         // [n_pages][2] device (ADAPTIVE_ROWS / TILE_4N per-page grids) or nullptr
+  int row_skip, row_count;    // token-level pass: pool rows [row_skip, row_skip + row_count) of every page (count <= 0: rest)
 };
 
 __device__ __forceinline__ float4 pool_load4(const void* base, int f32, long long row, int lane) {
@@ -279,6 +280,12 @@ __global__ void __launch_bounds__(256, 4) pool_tokens_kernel(const PoolInput in,
     long long r0, o0;
     int t, n_out;
     pool_page_rows(in.in_off, in.in_fixed, page, r0, t);
+    {   // token window (the page's visual tokens)
+      const int skip = min(max(in.row_skip, 0), t);
+      r0 += skip;
+      t -= skip;
+      if (in.row_count > 0) t = min(t, in.row_count);
+    }
     pool_page_rows(s.out_off, s.out_fixed, page, o0, n_out);
     if (s.kind == kPoolAdaptiveRows) {
       int gh = s.grid_h, gw = s.grid_w;

@@ -2258,7 +2258,8 @@ static int launch_pool(const PoolInput& in, int n, const vrag_pool_spec_t* specs
     if (specs[i].kind != VRAG_POOL_TILE_MEAN || specs[i].input_spec != 0) continue;
     for (int j = 0; j < n; ++j) {
       if (specs[j].kind == VRAG_POOL_COLSMOL_EXPERIMENTAL && specs[j].input_spec == 0 && specs[j].num_tiles <= 0 &&
-          specs[j].patches_per_tile == specs[i].patches_per_tile && dev[j].out_f32 == dev[i].out_f32) {
+          specs[j].patches_per_tile == specs[i].patches_per_tile && dev[j].out_f32 == dev[i].out_f32 &&
+          specs[j].in_row_skip == specs[i].in_row_skip && specs[j].in_row_count == specs[i].in_row_count) {
         dev[i].out2 = dev[j].out;
         dev[i].out2_off = dev[j].out_off;
         dev[i].out2_fixed = dev[j].out_fixed;
@@ -2271,7 +2272,7 @@ static int launch_pool(const PoolInput& in, int n, const vrag_pool_spec_t* specs
     const int k = specs[i].kind;
     if (specs[i].input_spec != 0 || pool_is_row_level(k) || i == fused_exp) continue;
     if (ra.n_specs > 0 && small_pages && (k == VRAG_POOL_LEGACY_CONV || k == VRAG_POOL_GLOBAL_MEAN) &&
-        ra.n_specs < kPoolMaxSpecs) {
+        ra.n_specs < kPoolMaxSpecs && specs[i].in_row_skip == 0 && specs[i].in_row_count <= 0) {
       ra.specs[ra.n_specs++] = dev[i];
       continue;
     }
@@ -2286,8 +2287,11 @@ static int launch_pool(const PoolInput& in, int n, const vrag_pool_spec_t* specs
     if (grid_rows + keep_rows > 384) return fail("pooling: %d staged rows per page exceed shared memory", grid_rows + keep_rows);
     const size_t smem = static_cast<size_t>(grid_rows + keep_rows) * 512;
     const unsigned grid = static_cast<unsigned>(std::min<long long>(in.n_pages, static_cast<long long>(num_sms) * 8));
-    if (d.n_specs > 0) pool_tokens_kernel<true><<<grid, 256, smem, st>>>(in, dev[i], d, grid_rows * 128);
-    else pool_tokens_kernel<false><<<grid, 256, smem, st>>>(in, dev[i], d, grid_rows * 128);
+    PoolInput win = in;
+    win.row_skip = specs[i].in_row_skip;
+    win.row_count = specs[i].in_row_count;
+    if (d.n_specs > 0) pool_tokens_kernel<true><<<grid, 256, smem, st>>>(win, dev[i], d, grid_rows * 128);
+    else pool_tokens_kernel<false><<<grid, 256, smem, st>>>(win, dev[i], d, grid_rows * 128);
     if (launches) ++*launches;
   }
   if (ra.n_specs > 0) {
@@ -2356,6 +2360,7 @@ extern "C" int vrag_pool_page(int device, const vrag_pool_spec_t* spec, const vo
                               void* out, int out_dtype, int64_t out_capacity_rows, int64_t* out_rows) {
   if (!spec || !out_rows) return fail("NULL argument");
   if (spec->input_spec != 0) return fail("input_spec must be 0 for a single pooling call");
+  if (spec->in_row_skip != 0 || spec->in_row_count != 0) return fail("token windows apply to vrag_store_pool only");
   if ((in_dtype != VRAG_F16 && in_dtype != VRAG_F32) || (out_dtype != VRAG_F16 && out_dtype != VRAG_F32))
     return fail("unknown dtype");
   if (in_rows < 0) return fail("in_rows < 0");
@@ -2436,8 +2441,13 @@ extern "C" int vrag_store_pool(vrag_corpus_t* c, const char* src, int n_specs, c
     offs[i][0] = 0;
     bool all_same = true;
     for (int64_t p = 0; p < n_pages; ++p) {
-      const int64_t t = par >= 0 ? (offs[par][p + 1] - offs[par][p])
-                                 : (sp->fixed_rows > 0 ? sp->fixed_rows : (sp->h_offsets[p + 1] - sp->h_offsets[p]));
+      int64_t t = par >= 0 ? (offs[par][p + 1] - offs[par][p])
+                           : (sp->fixed_rows > 0 ? sp->fixed_rows : (sp->h_offsets[p + 1] - sp->h_offsets[p]));
+      if (par < 0 && !pool_is_row_level(specs[i].kind)) {   // token window of a token-level spec
+        const int64_t skip = std::min<int64_t>(std::max(specs[i].in_row_skip, 0), t);
+        t -= skip;
+        if (specs[i].in_row_count > 0) t = std::min<int64_t>(t, specs[i].in_row_count);
+      }
       int gh, gw;
       pool_grid_of(specs[i], grid_hw, p, &gh, &gw);
       int64_t r = 0;

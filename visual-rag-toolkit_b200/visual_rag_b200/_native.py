@@ -52,6 +52,8 @@ class PoolSpec(C.Structure):
         ("via_f16", C.c_int),
         ("derive_from_f32", C.c_int),
         ("input_spec", C.c_int),
+        ("in_row_skip", C.c_int),
+        ("in_row_count", C.c_int),
     ]
 
 

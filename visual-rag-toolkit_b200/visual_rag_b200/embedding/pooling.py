@@ -157,6 +157,15 @@ def spec_seq_chunks(target_rows: int) -> N.PoolSpec:
     return N.PoolSpec(kind=N.POOL_SEQ_CHUNKS, target_rows=int(target_rows))
 
 
+def with_token_window(spec: N.PoolSpec, skip: int, count: int) -> N.PoolSpec:
+    """Bulk pooling only (GpuCorpus.pool_store): pool rows [skip, skip+count) of every source page — the page's visual
+    tokens (pipeline.py:400-430 pools `visual_embedding = embedding[visual_token_indices]`) when the `initial` store
+    also holds the instruction tokens (ColPali-v1.3: 1024 visual + 6 text tokens)."""
+    spec.in_row_skip = int(skip)
+    spec.in_row_count = int(count)
+    return spec
+
+
 def derived_from(spec: N.PoolSpec, index: int) -> N.PoolSpec:
     """Chain `spec` to the OUTPUT of spec number `index` of the same GpuCorpus.pool_store call (the pipeline's
     experimental / global pooling of the mean-pooled rows, pipeline.py:452-507): computed in that spec's pass."""
