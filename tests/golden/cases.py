@@ -152,3 +152,38 @@ def saliency_cases():
     return [{"key": f"sal{i}", "seed": 9100 + i, "qseed": 9200 + i, "n": n, "q": q, "token_info": ti}
             for i, (n, q, ti) in enumerate([(832, 20, {"n_rows": 4, "n_cols": 3}), (1030, 13, None), (300, 1, None),
                                             (768, 32, {"n_rows": 3, "n_cols": 4}), (70, 25, {"n_rows": 1, "n_cols": 1})])]
+
+
+# ------------------------------------------------------------------ true-fp32 inputs (NOT fp16-representable)
+def raw_rows(seed: int, n: int, d: int = 128, scale: bool = True) -> np.ndarray:
+    """Seeded gaussian rows, L2-normalised in fp32 and optionally rescaled — full fp32 mantissas, i.e. values that do
+    NOT survive an fp16 round trip (what an embedder emits in fp32; the reference's compute_maxsim_score callers,
+    two_stage.py:398-400, see such arrays). Pins (a) the pooling arithmetic on inputs whose partial sums are inexact
+    in fp32 and (b) the deviation the fp16 store dtype introduces against the reference's fp32 arithmetic."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    if scale:
+        x *= rng.uniform(0.5, 2.0, size=(n, 1)).astype(np.float32)
+    return x
+
+
+def fp32_pooling_cases():
+    """Every pooling call of pooling_case_specs() once more, on true-fp32 inputs."""
+    return [{"key": f"p_raw_{i:03d}", "fn": fn, "n": n, "seed": 11000 + i, "kwargs": kwargs, "args": args}
+            for i, (fn, n, kwargs, args) in enumerate(pooling_case_specs())]
+
+
+FP32_MAXSIM_SPECS = [(20, 768), (20, 1030), (1, 32), (13, 100), (33, 13), (64, 300), (20, 2048)]
+
+
+def fp32_maxsim_cases():
+    return [{"key": f"m_raw_{i:02d}", "q": q, "t": t, "seed": 12000 + i} for i, (q, t) in enumerate(FP32_MAXSIM_SPECS)]
+
+
+def fp32_corpus(seed: int = 13000, n_docs: int = 200):
+    """Variable-length true-fp32 pages + query for the exhaustive / two-stage searches on fp32 inputs."""
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(60, 400, size=n_docs)
+    docs = [raw_rows(seed + 1 + i, int(lens[i])) for i in range(n_docs)]
+    return query_rows(seed + 5000, 20), docs

@@ -1008,3 +1008,149 @@ def test_randomized_differential_vs_oracle(corpus, seed):
         assert ids.tolist() == [int(pool_idx[j]) for j in order], (seed, trial, kind)
         assert s.tolist() == [float(ref_scores[j]) for j in order]
     corpus.drop_store("rd")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the exchange building blocks of the C ABI on ONE GPU: two handles on device 0 act as the two shards of a corpus; their
+# packed local lists are laid out as an all-gather would leave them ([rank][list][k]) and merged with vrag_merge_hits_dev;
+# a candidate stage is completed with the element-wise max the all-reduce computes. (The collectives themselves run at
+# N > 1 in bench.py's `sharded_parity`; vrag_allgather_topk / vrag_allreduce_max_dev are the identity on one rank.)
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [10, 256, 3000])
+def test_packed_hit_exchange_blocks_emulate_two_shards(corpus, k):
+    import torch
+
+    from visual_rag_b200.corpus import GpuCorpus, query_flags
+
+    n, t, split = 9000, 40, 3700
+    rows = rows16(4100, n * t)
+    rows[(n - 2) * t:(n - 1) * t] = rows[5 * t:6 * t]                 # exact tie across the two shards
+    pooled = rows16(4101, n * 8)
+    q = CS.query_rows(4102, 17)
+    corpus.add_store("ex_i", rows, fixed_rows=t)
+    corpus.add_store("ex_p", pooled, fixed_rows=8)
+    want = corpus.search_multistage([("ex_p", False, k), ("ex_i", False, min(k, 50))], q)
+    shards = [GpuCorpus(0, page_base=0), GpuCorpus(0, page_base=split)]
+    try:
+        shards[0].add_store("ex_i", rows[:split * t], fixed_rows=t)
+        shards[0].add_store("ex_p", pooled[:split * 8], fixed_rows=8)
+        shards[1].add_store("ex_i", rows[split * t:], fixed_rows=t)
+        shards[1].add_store("ex_p", pooled[split * 8:], fixed_rows=8)
+        dev = torch.device("cuda", 0)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        qd = torch.from_numpy(q).to(dev)
+        fl = query_flags(True, False)
+        # ---- stage 1 (scan): local lists as packed entries -> "gathered" [rank][1][k] -> merge
+        gathered = torch.zeros((2, k, 16), dtype=torch.uint8, device=dev)
+        for r, sh in enumerate(shards):
+            local = torch.zeros((k, 16), dtype=torch.uint8, device=dev)
+            sh.stage_hits_dev("ex_p", qd.data_ptr(), q.shape[0], fl, 0, 0, k, local.data_ptr(), st)
+            sh.allgather_topk(local.data_ptr(), 1, k, gathered[r].data_ptr(), st)      # one rank: a device copy
+        ms = torch.empty((k,), dtype=torch.float32, device=dev)
+        mi = torch.empty((k,), dtype=torch.int64, device=dev)
+        flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+        shards[0].merge_hits_dev(gathered.data_ptr(), 2, 1, k, k, ms.data_ptr(), mi.data_ptr(), flag.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert int(flag.item()) == 0
+        assert mi.cpu().numpy().tolist() == want[0][1].tolist()
+        assert np.array_equal(ms.cpu().numpy(), want[0][0])
+        hits = np.frombuffer(gathered.cpu().numpy().tobytes(), dtype=GpuCorpus.HIT_DTYPE).reshape(2, k)
+        assert (hits["id"][0] < split).all() and (hits["id"][1][hits["id"][1] >= 0] >= split).all()
+        # ---- stage 2 (restricted to the merged list): -inf for foreign pages, max across shards, top-k in candidate order
+        k2 = min(k, 50)
+        sc = [torch.empty((k,), dtype=torch.float32, device=dev) for _ in shards]
+        for sh, buf in zip(shards, sc):
+            sh.score_dev("ex_i", qd.data_ptr(), q.shape[0], fl, mi.data_ptr(), k, buf.data_ptr(), st)
+            sh.allreduce_max_dev(buf.data_ptr(), k, st)                                  # one rank: no-op
+        torch.cuda.synchronize()
+        assert torch.isinf(sc[0]).sum() + torch.isinf(sc[1]).sum() == k                 # every candidate has exactly one owner
+        red = torch.maximum(sc[0], sc[1])
+        o_s = torch.empty((k2,), dtype=torch.float32, device=dev)
+        o_i = torch.empty((k2,), dtype=torch.int64, device=dev)
+        shards[0].topk_dev(red.data_ptr(), mi.data_ptr(), 0, k, k2, o_s.data_ptr(), o_i.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert o_i.cpu().numpy().tolist() == want[1][1].tolist()
+        assert np.array_equal(o_s.cpu().numpy(), want[1][0])
+    finally:
+        for sh in shards:
+            sh.close()
+        corpus.drop_store("ex_i")
+        corpus.drop_store("ex_p")
+
+
+@pytest.mark.gpu
+def test_merge_flags_a_missed_estimate_and_ignores_padding(corpus):
+    """A kHitMiss bit in any gathered entry raises the flag on the merging rank; padding entries (id < 0) never reach the
+    output ahead of real ones, even real -inf ones."""
+    import torch
+
+    from visual_rag_b200.corpus import GpuCorpus
+
+    dev = torch.device("cuda", 0)
+    h = np.zeros((3, 4), dtype=GpuCorpus.HIT_DTYPE)
+    h["id"], h["score"] = -1, -np.inf
+    h[0][:2] = [(0.5, 0, 7), (-np.inf, 0, 9)]            # a real page with score -inf (empty page) ...
+    h[1][:1] = [(0.5, 0, 1000)]                          # ... a tie with rank 0's best: lower rank (= lower id) first
+    h[2][:3] = [(0.9, 1, 2000), (0.1, 1, 2001), (0.0, 1, 2002)]   # rank 2's list came from a missed estimate
+    g = torch.from_numpy(np.frombuffer(h.tobytes(), dtype=np.uint8).copy()).to(dev)
+    ms = torch.empty((6,), dtype=torch.float32, device=dev)
+    mi = torch.empty((6,), dtype=torch.int64, device=dev)
+    flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+    corpus.merge_hits_dev(g.data_ptr(), 3, 1, 4, 6, ms.data_ptr(), mi.data_ptr(), flag.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    torch.cuda.synchronize()
+    assert int(flag.item()) == 1
+    assert mi.cpu().tolist() == [2000, 7, 1000, 2001, 2002, 9]
+    assert ms.cpu().tolist()[:5] == [np.float32(0.9), 0.5, 0.5, np.float32(0.1), 0.0] and np.isinf(ms.cpu().numpy()[5])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# payload filters: the RANKING of a filtered search equals the oracle restricted to the pages that pass (8f-3)
+@pytest.mark.gpu
+def test_filtered_searches_rank_like_the_oracle_on_the_filtered_set(retrieval_golden):
+    from visual_rag_b200.client import GpuCorpusClient
+    from visual_rag_b200.corpus import GpuCorpus
+    from visual_rag_b200.retrieval import SingleStageRetriever, ThreeStageRetriever, TwoStageRetriever
+    from visual_rag_b200.retrieval import models as M
+
+    q, initial = CS.retrieval_corpus()
+    n = len(initial)
+    off = retrieval_golden["offsets_pooled"]
+    own = GpuCorpus(0)       # its own handle: other tests of this module overwrite the shared corpus' stores
+    own.add_store("initial", np.concatenate(initial).astype(np.float16),
+                  page_offsets=np.concatenate([[0], np.cumsum([d.shape[0] for d in initial])]))
+    own.add_store("mean_pooling", retrieval_golden["mean_pooling"], page_offsets=off)
+    own.add_store("experimental_pooling", retrieval_golden["experimental_pooling"], page_offsets=off)
+    own.add_store("global_pooling", retrieval_golden["global_pooling"], fixed_rows=1)
+    client = GpuCorpusClient(own, "c", payloads=[{"page": i, "year": 2000 + i % 3} for i in range(n)])
+    split = lambda rows: [rows[off[i]:off[i + 1]].astype(np.float32) for i in range(n)]  # noqa: E731
+    pooled, exper = split(retrieval_golden["mean_pooling"]), split(retrieval_golden["experimental_pooling"])
+    glob = [g.astype(np.float32)[None, :] for g in retrieval_golden["global_pooling"]]
+    docs = [d.astype(np.float16).astype(np.float32) for d in initial]
+    payload = lambda i: {"page": i, "year": 2000 + i % 3}   # noqa: E731  (the gpu_client fixture's payloads)
+
+    def restricted(pred, stages):
+        keep = [i for i in range(n) if pred(payload(i))]
+        res = MO.multistage(q, [([st[i] for i in keep], pool, k) for st, pool, k in stages])[-1]
+        return [(keep[i], s) for i, s in res]
+
+    def same(got, want):
+        assert [g["id"] for g in got] == [i for i, _ in want]
+        close([g["score_final"] for g in got], [s for _, s in want])
+
+    single, two, three = SingleStageRetriever(client, "c"), TwoStageRetriever(client, "c"), ThreeStageRetriever(client, "c")
+    f = two.build_filter(year=2001)
+    is01 = lambda p: p["year"] == 2001   # noqa: E731
+    same(single.search(q, top_k=10, strategy="multi_vector", filter_obj=f), restricted(is01, [(docs, False, 10)]))
+    same(two.search_server_side(q, top_k=10, prefetch_k=25, filter_obj=f, stage1_mode="tokens_vs_standard_pooling"),
+         restricted(is01, [(pooled, False, 25), (docs, False, 10)]))
+    same(three.search_server_side(query_embedding=q, top_k=5, stage1_k=30, stage2_k=12, filter_obj=f),
+         restricted(is01, [(glob, True, 30), (exper, False, 12), (docs, False, 5)]))
+    mix = M.Filter(must=[M.FieldCondition(key="year", match=M.MatchAny(any=[2000, 2002]))],
+                   must_not=[M.FieldCondition(key="page", range=M.Range(lt=20))],
+                   should=[M.FieldCondition(key="page", match=M.MatchExcept(**{"except": list(range(0, n, 2))})),
+                           M.FieldCondition(key="page", range=M.Range(gte=100, lte=110))])
+    pred = lambda p: p["year"] in (2000, 2002) and not p["page"] < 20 and (p["page"] % 2 == 1 or 100 <= p["page"] <= 110)  # noqa: E731
+    same(single.search(q, top_k=12, strategy="multi_vector", filter_obj=mix), restricted(pred, [(docs, False, 12)]))
+    with pytest.raises(NotImplementedError):
+        single.search(q, top_k=3, filter_obj=M.Filter(must=[M.FieldCondition(key="year")]))
+    own.close()

@@ -1,8 +1,9 @@
 """The reference's OWN retriever classes, unmodified, on top of `GpuCorpusClient` (the drop-in seam).
 
-Runs only where the reference tree is present (this container; `/root/reference` does not exist on the GPU box, where the
-GPU parity tests cover the arithmetic). The corpus behind the client is a numpy double of `GpuCorpus` that scores with the
-oracle, so what is exercised here is the client's side of the seam: the exact `query_points` / `retrieve` call shapes of
+The reference is imported from `/root/reference` where that exists (this container) and otherwise from `baseline/_ref`
+— the verbatim install made by baseline/install_ref.py, which travels to the GPU box. Two variants: on the CPU the corpus
+behind the client is a numpy double of `GpuCorpus` that scores with the oracle; the `gpu`-marked variant puts the same
+corpus into a real `GpuCorpus` on cuda:0, so the reference's classes drive the CUDA kernels. What is exercised is the seam: the exact `query_points` / `retrieve` call shapes of
 visual_rag/retrieval/{two_stage,three_stage,single_stage}.py — `prefetch=[Prefetch(...)]`, `Filter(must=[HasIdCondition])`,
 `with_vectors=[name]`, list-typed queries — and the result objects the reference reads back (`.points[*].id/.score/
 .payload`, `.vector[name]`). Results must equal the goldens the same classes produced on the in-memory Qdrant double."""
@@ -16,8 +17,10 @@ import cases as CS
 from fake_qdrant import install_qdrant_stub
 from oracle import maxsim_oracle as MO
 
-REF = "/root/reference"
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "visual_rag")), reason="reference tree not present")
+from conftest import ROOT
+
+REF = next((p for p in ("/root/reference", os.path.join(ROOT, "baseline", "_ref")) if os.path.isdir(os.path.join(p, "visual_rag"))), None)
+pytestmark = pytest.mark.skipif(REF is None, reason="reference not present (neither /root/reference nor baseline/_ref)")
 
 
 class OracleCorpus:
@@ -57,8 +60,7 @@ class OracleCorpus:
         return out
 
 
-@pytest.fixture(scope="module")
-def ref_setup(retrieval_golden, golden_index):
+def _reference_classes():
     install_qdrant_stub()
     if REF not in sys.path:
         sys.path.insert(0, REF)
@@ -66,17 +68,41 @@ def ref_setup(retrieval_golden, golden_index):
     from visual_rag.retrieval.three_stage import ThreeStageRetriever
     from visual_rag.retrieval.two_stage import TwoStageRetriever
 
-    from visual_rag_b200.client import GpuCorpusClient
+    return TwoStageRetriever, ThreeStageRetriever, SingleStageRetriever
 
+
+def _stores(retrieval_golden):
     q, initial = CS.retrieval_corpus()
     off = retrieval_golden["offsets_pooled"]
     split = lambda rows: [rows[off[i]:off[i + 1]].astype(np.float32) for i in range(len(off) - 1)]  # noqa: E731
     stores = {"initial": initial, "mean_pooling": split(retrieval_golden["mean_pooling"]),
               "experimental_pooling": split(retrieval_golden["experimental_pooling"]),
               "global_pooling": [g.astype(np.float32)[None, :] for g in retrieval_golden["global_pooling"]]}
-    payloads = [{"page": i, "year": 2000 + i % 3} for i in range(len(initial))]
+    return q, stores, [{"page": i, "year": 2000 + i % 3} for i in range(len(initial))]
+
+
+@pytest.fixture(scope="module")
+def ref_setup_gpu(retrieval_golden, golden_index):
+    """The same corpus in a real GpuCorpus on cuda:0 behind the product's GpuCorpusClient."""
+    from visual_rag_b200.client import GpuCorpusClient
+    from visual_rag_b200.corpus import GpuCorpus
+
+    q, stores, payloads = _stores(retrieval_golden)
+    corpus = GpuCorpus(0)
+    for name, pages in stores.items():
+        off = np.concatenate([[0], np.cumsum([len(p) for p in pages])])
+        corpus.add_store(name, np.concatenate(pages).astype(np.float16), page_offsets=off)
+    yield q, GpuCorpusClient(corpus, "c", payloads=payloads), golden_index["retrieval"], _reference_classes()
+    corpus.close()
+
+
+@pytest.fixture(scope="module")
+def ref_setup(retrieval_golden, golden_index):
+    from visual_rag_b200.client import GpuCorpusClient
+
+    q, stores, payloads = _stores(retrieval_golden)
     client = GpuCorpusClient(OracleCorpus(stores), "c", payloads=payloads)
-    return q, client, golden_index["retrieval"], (TwoStageRetriever, ThreeStageRetriever, SingleStageRetriever)
+    return q, client, golden_index["retrieval"], _reference_classes()
 
 
 def _ids(res):
@@ -120,3 +146,19 @@ def test_reference_three_and_single_stage_classes_run_on_the_client(ref_setup):
     for strat in ("multi_vector", "tiles_maxsim", "pooled_tile", "pooled_global", "experimental_maxsim", "pooled_experimental"):
         res = single.search(q, top_k=10, strategy=strat)
         assert _ids(res) == [x["id"] for x in gold[f"single::{strat}"]], strat
+
+
+# ------------------------------------------------------------------ the same, on a real GpuCorpus (cuda:0)
+@pytest.mark.gpu
+def test_reference_two_stage_classes_drive_the_cuda_kernels(ref_setup_gpu):
+    test_reference_two_stage_classes_run_on_the_client(ref_setup_gpu)
+    q, client, gold, (Two, _, _) = ref_setup_gpu
+    assert client.corpus.launch_count() > 0
+    # the reference's client-side rerank with embeddings pulled through retrieve(with_vectors=[...])
+    res = Two(client, "c").search(q, top_k=5, prefetch_k=20, stage1_mode="tokens_vs_tiles", return_embeddings=True)
+    assert all(np.asarray(r["embedding"]).shape[1] == 128 for r in res)
+
+
+@pytest.mark.gpu
+def test_reference_three_and_single_stage_classes_drive_the_cuda_kernels(ref_setup_gpu):
+    test_reference_three_and_single_stage_classes_run_on_the_client(ref_setup_gpu)

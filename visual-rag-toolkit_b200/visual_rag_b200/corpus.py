@@ -573,6 +573,30 @@ class GpuCorpus:
                                                      None, C.c_void_p(out_scores_dev_ptr), C.c_void_p(out_ids_dev_ptr),
                                                      C.c_void_p(stream)))
 
+    # ------------------------------------------------------------------ building blocks of a collective stage
+    HIT_DTYPE = np.dtype([("score", np.float32), ("aux", np.uint32), ("id", np.int64)])   # vrag_hit_t, 16 bytes
+
+    def stage_hits_dev(self, name: str, query_dev_ptr: int, n_query_rows: int, flags: int, cand_dev_ptr: int, n_cand: int,
+                       k: int, out_hits_dev_ptr: int, stream: int) -> None:
+        """Local scan + local top-k of this shard as k packed entries (the all-gather send buffer)."""
+        N.check(self._lib.vrag_stage_hits_dev(self._h, name.encode(), C.c_void_p(query_dev_ptr), int(n_query_rows), int(flags),
+                                              C.c_void_p(cand_dev_ptr) if cand_dev_ptr else None, int(n_cand), int(k),
+                                              C.c_void_p(out_hits_dev_ptr), C.c_void_p(stream)))
+
+    def allgather_topk(self, local_dev_ptr: int, n_lists: int, k: int, gathered_dev_ptr: int, stream: int) -> None:
+        N.check(self._lib.vrag_allgather_topk(self._h, C.c_void_p(local_dev_ptr), int(n_lists), int(k),
+                                              C.c_void_p(gathered_dev_ptr), C.c_void_p(stream)))
+
+    def merge_hits_dev(self, gathered_dev_ptr: int, n_src: int, n_lists: int, k_src: int, k: int, out_scores_dev_ptr: int,
+                       out_ids_dev_ptr: int, flag_dev_ptr: int, stream: int) -> None:
+        """Merge n_src gathered lists ([src][list][k_src] packed entries) into the global top-k of every list."""
+        N.check(self._lib.vrag_merge_hits_dev(self._h, C.c_void_p(gathered_dev_ptr), int(n_src), int(n_lists), int(k_src), int(k),
+                                              C.c_void_p(out_scores_dev_ptr), C.c_void_p(out_ids_dev_ptr),
+                                              C.c_void_p(flag_dev_ptr) if flag_dev_ptr else None, C.c_void_p(stream)))
+
+    def allreduce_max_dev(self, scores_dev_ptr: int, n: int, stream: int) -> None:
+        N.check(self._lib.vrag_allreduce_max_dev(self._h, C.c_void_p(scores_dev_ptr), int(n), C.c_void_p(stream)))
+
     # ------------------------------------------------------------------ device-level batched stages (sharded batched search)
     def batch_upload(self, n_stages: int, packed: "PackedQueries", per_stage: bool = False) -> None:
         N.check(self._lib.vrag_batch_upload(self._h, int(n_stages), len(packed) // (n_stages if per_stage else 1),
