@@ -64,13 +64,30 @@ int vrag_store_add(vrag_corpus_t* c, const char* name, const void* rows, int dty
 int vrag_store_append(vrag_corpus_t* c, const char* name, const void* rows, int dtype, int rows_on_device,
                       const int64_t* page_offsets, int64_t n_pages, int64_t fixed_rows);
 
-/* Overwrite existing pages in place — the "upsert of a point that already exists" half of QdrantIndexer.upload_batch
+/* Overwrite existing pages — the "upsert of a point that already exists" half of QdrantIndexer.upload_batch
  * (client.upsert, visual_rag/indexing/qdrant_indexer.py:459-507; ids are deterministic, 602-613, so re-indexing a document
  * re-sends the same ids). local_pages[n_pages]: shard-local page indices; rows / page_offsets describe the new pages
- * back to back as in vrag_store_append. Every new page must have exactly the row count of the page it replaces (the shard
- * layout is dense; a page whose shape changed needs a rebuilt store) — otherwise nothing is written and the call fails. */
+ * back to back as in vrag_store_append. Pages that keep their row count are overwritten in place and the store stays on
+ * the dense layout. A page whose row count changed switches the store to a PAGE TABLE (page -> row range anywhere in the
+ * row buffer): a page that shrank is overwritten in place, a page that grew moves behind the last row and its old rows
+ * become garbage until vrag_store_compact. Scans of a store with a page table fetch every page on its own (the gather
+ * path); everything is validated before anything is written.                                                          */
 int vrag_store_replace_pages(vrag_corpus_t* c, const char* name, const int64_t* local_pages, int64_t n_pages,
                              const void* rows, int dtype, int rows_on_device, const int64_t* page_offsets, int64_t fixed_rows);
+
+/* Delete pages (qdrant `client.delete(points_selector=ids)`; the reference itself only drops whole collections,
+ * qdrant_indexer.py:175). A deleted page keeps its index — the host's id tables stay valid — but owns no rows: it scores
+ * -inf in every scan and is never returned. Switches the store to the page table.                                     */
+int vrag_store_delete_pages(vrag_corpus_t* c, const char* name, const int64_t* local_pages, int64_t n_pages);
+
+/* Drop the LAST pages of a store, keeping n_pages: the rollback of a batch upload that appended to several named stores
+ * and failed on a later one (client.upsert is atomic per batch).                                                       */
+int vrag_store_truncate(vrag_corpus_t* c, const char* name, int64_t n_pages);
+
+/* Rewrite a store with a page table contiguously in page order (one device pass): garbage rows are reclaimed and the
+ * dense fast paths apply again. Page indices do not change (deleted pages stay as zero-row pages). No-op on a dense
+ * store. vrag_store_pool compacts its source automatically.                                                           */
+int vrag_store_compact(vrag_corpus_t* c, const char* name);
 
 /* Fill a named store with the seeded synthetic corpus of SURVEY.md 8(d) directly on the device
  * (gaussian rows, L2-normalised, rounded to fp16).  Row r of the store depends only on (seed, row_seed_base + r). */

@@ -791,8 +791,7 @@ def test_long_queries_in_batches_and_saliency(corpus):
 @pytest.mark.gpu
 def test_indexer_upsert_replaces_pages_in_place():
     """client.upsert semantics of QdrantIndexer.upload_batch (qdrant_indexer.py:459-507): a batch mixing ids that exist
-    (same shapes, new vectors and payload) with new ids == a bulk store of the final state; a point whose shape changed is
-    refused before anything is written."""
+    (same shapes, new vectors and payload) with new ids == a bulk store of the final state."""
     from visual_rag_b200.client import GpuCorpusClient
     from visual_rag_b200.corpus import GpuCorpus
     from visual_rag_b200.indexing import GpuIndexer
@@ -841,18 +840,97 @@ def test_indexer_upsert_replaces_pages_in_place():
             b = TwoStageRetriever(client2, "c").search_server_side(q, top_k=8, prefetch_k=15, stage1_mode=mode)
             assert [(r["id"], r["score_final"], r["payload"]) for r in a] == [(r["id"], r["score_final"], r["payload"]) for r in b]
         assert {r["payload"]["version"] for r in two.search_server_side(q, top_k=30, prefetch_k=30)} == {1, 2}
-        # a point whose token count changed cannot be replaced in place: refused, collection untouched
-        before = c1.read_rows("initial", 0, 50).copy()
-        bad = [point(31, 150, 9, 4), point(3, shapes[3][0] + 1, shapes[3][1], 4)]
-        with pytest.raises(ValueError, match="equal shapes"):
-            idx.upload_batch(bad)
-        assert not idx.check_exists(bad[0]["id"]) and c1.n_pages("initial") == 30
-        assert np.array_equal(c1.read_rows("initial", 0, 50), before)
         from visual_rag_b200._native import VragError
-        with pytest.raises(VragError, match="equal shapes"):
-            c1.replace_pages("initial", [0], np.zeros((3, 128), np.float16), [0, 3])
         with pytest.raises(VragError, match="out of range"):
             c1.replace_pages("initial", [99], np.zeros((3, 128), np.float16), [0, 3])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["large", "pooled32", "fixed13", "mixed"])
+def test_shape_changing_upserts_deletes_and_compaction_match_the_oracle(layout):
+    """Page-table indirection (vrag_store_replace_pages with new shapes, vrag_store_delete_pages, vrag_store_compact):
+    after every step the scans — exhaustive, candidate-restricted, batched, pooled-query — equal the oracle over the
+    store's CURRENT pages; compaction changes no result and returns the store to the dense layout."""
+    from visual_rag_b200.corpus import GpuCorpus
+
+    rng = np.random.default_rng({"large": 1, "pooled32": 2, "fixed13": 3, "mixed": 4}[layout])
+    n = 300
+    if layout == "large":
+        lens = rng.integers(129, 400, size=n)
+    elif layout == "pooled32":
+        lens = rng.integers(5, 33, size=n)
+    elif layout == "fixed13":
+        lens = np.full((n,), 13)
+    else:
+        lens = rng.integers(1, 260, size=n)
+    pages = [rows16(int(rng.integers(1 << 30)), int(t)) for t in lens]
+    q = CS.query_rows(77, 19)
+    qs = [CS.query_rows(80 + j, 6 + 5 * j) for j in range(3)]
+
+    def check(c, what):
+        want = np.array([MO.maxsim_score(q, p.astype(np.float32)) if len(p) else -np.inf for p in pages], dtype=np.float64)
+        got = c.score("s", q)
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), fin), what
+        close(got[fin], want[fin])
+        k = 25
+        s_, ids = c.search("s", q, k)
+        order = np.lexsort((np.arange(len(want)), -want))[:k]
+        _same_ranking(ids, s_, [(int(i), float(want[i])) for i in order])
+        cand = rng.permutation(len(pages))[:40]
+        gc = c.score("s", q, candidate_ids=cand)
+        assert np.array_equal(np.isfinite(gc), fin[cand]) and np.allclose(gc[fin[cand]], want[cand][fin[cand]], rtol=RTOL, atol=ATOL), what
+        wantp = np.array([MO.pooled_query_score(q, p.astype(np.float32)) if len(p) else -np.inf for p in pages])
+        gp = c.score("s", q, pool_query=True)
+        assert np.allclose(gp[fin], wantp[fin], rtol=RTOL, atol=ATOL), what
+        res = c.search_multistage_batch([("s", False, 10)], qs)
+        for qq, r in zip(qs, res):
+            w = np.array([MO.maxsim_score(qq, p.astype(np.float32)) if len(p) else -np.inf for p in pages])
+            _same_ranking(r[0][1], r[0][0], [(int(i), float(w[i])) for i in np.lexsort((np.arange(len(w)), -w))[:10]])
+
+    with GpuCorpus(0) as c:
+        off = np.concatenate([[0], np.cumsum([len(p) for p in pages])])
+        if layout == "fixed13":
+            c.add_store("s", np.concatenate(pages), fixed_rows=13)
+        else:
+            c.add_store("s", np.concatenate(pages), page_offsets=off)
+        check(c, "initial")
+        # ---- upsert with new shapes: some pages grow, some shrink, some keep their size
+        hi = 400 if layout in ("large", "mixed") else (32 if layout == "pooled32" else 40)
+        lo = 129 if layout == "large" else 1
+        changed = rng.permutation(n)[:60].tolist()
+        new_pages = [rows16(int(rng.integers(1 << 30)), int(rng.integers(lo, hi + 1))) for _ in changed]
+        new_pages[0] = rows16(5, len(pages[changed[0]]))                      # same size: stays in place
+        c.replace_pages("s", changed, np.concatenate(new_pages), np.concatenate([[0], np.cumsum([len(p) for p in new_pages])]))
+        for pg, p in zip(changed, new_pages):
+            pages[pg] = p
+        assert c.store_info("s")["fixed_rows"] == 0
+        check(c, "after shape-changing upsert")
+        for pg in (changed[1], 0, n - 1):
+            assert np.array_equal(c.read_page("s", pg).view(np.uint16), pages[pg].view(np.uint16))
+        # ---- deletes
+        gone = rng.permutation(n)[:25].tolist()
+        c.delete_pages("s", gone)
+        for pg in gone:
+            pages[pg] = pages[pg][:0]
+        check(c, "after deletes")
+        # ---- appends behind a page table
+        extra = [rows16(int(rng.integers(1 << 30)), int(rng.integers(lo, hi + 1))) for _ in range(17)]
+        c.append_store("s", np.concatenate(extra), page_offsets=np.concatenate([[0], np.cumsum([len(p) for p in extra])]))
+        pages.extend(extra)
+        check(c, "after append")
+        before = c.score("s", q)
+        rows_before = c.store_info("s")["total_rows"]
+        c.compact_store("s")
+        info = c.store_info("s")
+        assert info["total_rows"] == sum(len(p) for p in pages) <= rows_before and info["n_pages"] == len(pages)
+        after = c.score("s", q)
+        assert np.array_equal(np.isfinite(before), np.isfinite(after))
+        assert np.allclose(before[np.isfinite(before)], after[np.isfinite(after)], rtol=1e-6)
+        check(c, "after compaction")
+        c.truncate_store("s", n)
+        del pages[n:]
+        check(c, "after truncate")
 
 
 @pytest.mark.gpu

@@ -157,6 +157,17 @@ def test_retry_and_torch_queries(setup):
     with pytest.raises(RuntimeError, match="transient"):
         r.search_server_side(q)
 
+    class Bad:
+        calls = 0
+
+        def query_points(self, **kw):
+            Bad.calls += 1
+            raise ValueError("k=5000 exceeds the supported maximum 4096 results per search stage")
+
+    with pytest.raises(ValueError, match="exceeds"):          # deterministic errors are not retried (no back-off sleeps)
+        TwoStageRetriever(Bad(), "c", retry_sleep=10.0).search_server_side(q)
+    assert Bad.calls == 1
+
 
 def test_build_filter_and_stage1_table():
     r = TwoStageRetriever(None, "c")
@@ -251,6 +262,7 @@ class _ListCorpus:
     def __init__(self):
         self.stores = {}
         self.log = []
+        self.fail_on = None
 
     def has_store(self, name):
         return name in self.stores
@@ -263,16 +275,31 @@ class _ListCorpus:
         return int(sum(rows[:local_page])), int(rows[local_page])
 
     def append_store(self, name, rows, page_offsets=None, fixed_rows=0):
+        if self.fail_on == ("append", name):
+            raise RuntimeError("device error (injected)")
         off = np.asarray(page_offsets)
         self.stores.setdefault(name, []).extend(rows[off[i]:off[i + 1]] for i in range(len(off) - 1))
         self.log.append(("append", name, len(off) - 1))
 
     def replace_pages(self, name, local_pages, rows, page_offsets):
+        if self.fail_on == ("replace", name):
+            raise RuntimeError("device error (injected)")
         off = np.asarray(page_offsets)
         for j, pg in enumerate(local_pages):
-            assert self.stores[name][pg].shape == rows[off[j]:off[j + 1]].shape
-            self.stores[name][pg] = rows[off[j]:off[j + 1]]
+            self.stores[name][pg] = rows[off[j]:off[j + 1]]        # any shape: the store keeps a page table
         self.log.append(("replace", name, list(local_pages)))
+
+    def delete_pages(self, name, local_pages):
+        for pg in local_pages:
+            self.stores[name][pg] = self.stores[name][pg][:0]
+        self.log.append(("delete", name, list(local_pages)))
+
+    def truncate_store(self, name, n_pages):
+        del self.stores[name][n_pages:]
+        self.log.append(("truncate", name, n_pages))
+
+    def compact_store(self, name):
+        self.log.append(("compact", name))
 
     def drop_store(self, name):
         del self.stores[name]
@@ -280,8 +307,8 @@ class _ListCorpus:
 
 def test_indexer_upsert_host_logic():
     """GpuIndexer.upload_batch without a GPU: client.upsert semantics (qdrant_indexer.py:459-507) — new ids appended, existing
-    ids replaced in place with their payload, the last occurrence of an id inside a batch wins, and every refusal (shape
-    change, missing named vector) happens before anything is written."""
+    ids replaced with their payload (whatever their new shape), the last occurrence of an id inside a batch wins, named vectors
+    are optional per point, a failed batch is rolled back and reports 0, deletes keep page indices stable."""
     from visual_rag_b200.indexing import GpuIndexer
 
     def point(i, t, r, ver, with_exp=True):
@@ -308,12 +335,35 @@ def test_indexer_upsert_host_logic():
     assert [p["ver"] for p in idx.client._payloads] == [2, 1, 3, 1, 2]          # last occurrence of id2 (ver 3) won
     np.testing.assert_array_equal(c.stores["initial"][2], point(2, 12, 3, 3)["visual_embedding"].astype(np.float16))
     assert idx.check_exists("id7") and not idx.check_exists("id9") and idx.get_existing_ids() == set(idx.client._ids)
-    before = [m.copy() for m in c.stores["initial"]]
+    # ---- an upsert may change a point's shape (client.upsert has no shape constraint): id1 grows from 11 to 99 tokens
     c.log.clear()
-    with pytest.raises(ValueError, match="equal shapes"):
-        idx.upload_batch([point(8, 9, 2, 4), point(1, 99, 3, 4)])              # id1 changes its token count
-    with pytest.raises(ValueError, match="missing from some points"):
-        idx.upload_batch([point(9, 9, 2, 4), point(10, 9, 2, 4, with_exp=False)])
-    assert c.log == [] and len(idx.client._ids) == 5 and all(np.array_equal(a, b) for a, b in zip(before, c.stores["initial"]))
+    assert idx.upload_batch([point(8, 9, 2, 4), point(1, 99, 3, 4)]) == 2
+    assert c.stores["initial"][1].shape == (99, 128) and ("replace", "initial", [1]) in c.log
+    assert idx.client._ids == ["id0", "id1", "id2", "id3", "id7", "id8"]
+    # ---- named vectors are optional per point (pipeline.py:485-503): id10 has no experimental vector -> an empty page there;
+    # a named vector that appears late (experimental_pooling_2d) gives the earlier points empty pages
+    p11 = point(11, 9, 2, 4)
+    p11["experimental_pooled_embedding"]["experimental_pooling_2d"] = np.ones((13, 128), np.float32)
+    assert idx.upload_batch([point(9, 9, 2, 4), point(10, 9, 2, 4, with_exp=False), p11]) == 3
+    n = len(idx.client._ids)
+    assert n == 9 and all(c.n_pages(nm) == n for nm in c.stores)
+    assert c.stores["experimental_pooling"][7].shape == (0, 128) and c.stores["experimental_pooling"][6].shape == (2, 128)
+    assert [m.shape[0] for m in c.stores["experimental_pooling_2d"]] == [0] * 8 + [13]
+    # ---- a failed batch leaves nothing behind and reports 0 (the reference logs and returns 0, qdrant_indexer.py:497-507)
+    before = {nm: [m.copy() for m in v] for nm, v in c.stores.items()}
+    c.fail_on = ("append", "mean_pooling")                              # the second store of the batch fails on the device
+    assert idx.upload_batch([point(20, 5, 2, 5), point(21, 6, 2, 5)]) == 0
+    c.fail_on = None
+    assert len(idx.client._ids) == n and not idx.check_exists("id20")
+    assert all(len(c.stores[nm]) == n and all(np.array_equal(a, b) for a, b in zip(before[nm], c.stores[nm])) for nm in before)
+    assert idx.upload_batch([{"id": "bad", "visual_embedding": np.zeros((3, 64)), "tile_pooled_embedding": np.zeros((2, 64))}]) == 0
+    assert idx.upload_batch([{"id": "bad2", "metadata": {}}]) == 0        # malformed point: logged, 0 uploaded, nothing written
+    assert len(idx.client._ids) == n
+    # ---- deletes: the pages stay (empty), the ids leave the collection
+    assert idx.delete_points(["id2", "nope"]) == 1
+    assert not idx.check_exists("id2") and c.stores["initial"][2].shape == (0, 128) and idx.client._ids[2] is None
+    assert idx.upload_batch([point(2, 7, 2, 6)]) == 1 and idx.client._page("id2") == n    # re-inserted as a new page
+    idx.compact()
+    assert ("compact", "initial") in c.log
     assert idx.create_collection() is False and idx.create_collection(force_recreate=True) and not c.stores
     assert idx.client._ids == []

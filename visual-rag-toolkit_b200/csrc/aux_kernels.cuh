@@ -398,11 +398,11 @@ __global__ void __launch_bounds__(THREADS, 1) topk_kernel(const TopkArgs a) {
       if (a.aux_src && *a.aux_src) aux |= kHitMiss;
     }
     for (int j = threadIdx.x; j < a.k; j += THREADS) {
-      const unsigned long long key = skeys[j];
+      const unsigned long long key = j < nvalid ? skeys[j] : 0ull;   // k may exceed the sort buffer: never read past nvalid
       float sc = -INFINITY;
       long long id = -1;
       int pos = -1;
-      if (j < nvalid && key != 0ull) {   // key 0: padding of a gathered list
+      if (key != 0ull) {   // key 0: padding of a gathered list / beyond the valid results
         const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
         sc = ord_to_score(static_cast<uint32_t>(key >> 32));
         if (a.hits_in) {
@@ -828,6 +828,22 @@ __global__ void hits_unpack_kernel(const Hit* __restrict__ hits, int n_src, int 
   scores[t] = h.id >= 0 ? h.score : __int_as_float(0x7fc00000);
   ids[t] = h.id;
   if ((h.aux & kHitMiss) && fail_flag) atomicOr(fail_flag, 1);
+}
+
+// Store compaction: page p's rows [begin[p], begin[p] + n) -> rows [new_off[p], new_off[p+1]) of the new buffers (and the
+// matching inverse norms). One block walks pages; a warp moves one 256-byte row per step (16-byte lanes x 16).
+__global__ void __launch_bounds__(256) compact_rows_kernel(const __half* __restrict__ rows, const float* __restrict__ inv,
+                                                           const long long* __restrict__ begin, const long long* __restrict__ new_off,
+                                                           long long n_pages, __half* __restrict__ out_rows, float* __restrict__ out_inv) {
+  const int sub = threadIdx.x & 15, rl = threadIdx.x >> 4;   // 16 rows in flight per block step
+  for (long long p = blockIdx.x; p < n_pages; p += gridDim.x) {
+    const long long src = begin[p], dst = new_off[p], n = new_off[p + 1] - dst;
+    for (long long r = rl; r < n; r += 16) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(rows + (src + r) * 128) + sub);
+      *(reinterpret_cast<uint4*>(out_rows + (dst + r) * 128) + sub) = v;
+      if (sub == 0) out_inv[dst + r] = inv[src + r];
+    }
+  }
 }
 
 __global__ void fill_f32_kernel(float* __restrict__ p, long long n, float v) {

@@ -75,7 +75,7 @@ __device__ __forceinline__ bool resolve_page(const ScanParams& p, long long page
     row0 = page * p.fixed_rows;
     nrows = static_cast<int>(p.fixed_rows);
   } else {
-    const long long a = __ldg(p.offsets + page), b = __ldg(p.offsets + page + 1);
+    const long long a = __ldg(p.offsets + page), b = p.page_end ? __ldg(p.page_end + page) : __ldg(p.offsets + page + 1);
     row0 = a;
     nrows = static_cast<int>(b - a);
   }

@@ -24,6 +24,7 @@ constexpr float kLoScale = 2048.0f;  // lo half of the query is stored scaled by
 
 struct ScanParams {
   const long long* offsets;   // [n_pages+1] row offsets of the store (used when fixed_rows == 0)
+  const long long* page_end;  // != nullptr: the store has a page table: page p owns rows [offsets[p], page_end[p])
   long long fixed_rows;       // > 0: page p owns rows [p*fixed_rows, (p+1)*fixed_rows)
   long long n_pages;          // pages in this store (this shard)
   const long long* cand;      // nullptr: item i is page i. else: item i is page cand[i] - cand_base

@@ -141,7 +141,45 @@ struct Store {
   CUtensorMap tm128, tm32, ts128, ts32;
   CUtensorMap tm3d;              // fixed_rows <= 32, not a power of two: {128, fixed_rows, n_pages} view with a padded box
   int pad_slot = 0;              // its slot height (next power of two), 0 when the view does not exist
+  // Page-table indirection (upserts that change a page's row count, deletes): page p owns rows [h_begin[p], h_end[p])
+  // anywhere in the row buffer. A replaced page that grew lives behind the last row, its old rows are garbage until
+  // vrag_store_compact; a deleted page has end == begin and keeps its index. Dense stores (indirect == false) stay on
+  // the contiguous fast paths.
+  bool indirect = false;
+  std::vector<int64_t> h_begin, h_end;
+  long long* d_begin = nullptr;
+  long long* d_end = nullptr;
+  int64_t garbage_rows = 0;
 };
+
+// rows [r0, r0 + n) of page p (host-side page table)
+static void page_rows_h(const Store& s, int64_t p, int64_t* r0, int64_t* n) {
+  if (s.indirect) {
+    *r0 = s.h_begin[p];
+    *n = s.h_end[p] - s.h_begin[p];
+  } else if (s.fixed_rows > 0) {
+    *r0 = p * s.fixed_rows;
+    *n = s.fixed_rows;
+  } else {
+    *r0 = s.h_offsets[p];
+    *n = s.h_offsets[p + 1] - s.h_offsets[p];
+  }
+}
+static void make_indirect(Store& s) {
+  if (s.indirect) return;
+  s.h_begin.resize(s.n_pages);
+  s.h_end.resize(s.n_pages);
+  for (int64_t p = 0; p < s.n_pages; ++p) {
+    int64_t r0, n;
+    page_rows_h(s, p, &r0, &n);
+    s.h_begin[p] = r0;
+    s.h_end[p] = r0 + n;
+  }
+  s.indirect = true;
+  s.fixed_rows = 0;
+  s.h_offsets.clear();
+  s.dirty = true;
+}
 
 template <typename T>
 struct DevBuf {
@@ -264,6 +302,8 @@ static void free_store(Store& s) {
   if (s.offsets) cudaFree(s.offsets);
   if (s.tile_page0) cudaFree(s.tile_page0);
   if (s.tile_row0) cudaFree(s.tile_row0);
+  if (s.d_begin) cudaFree(s.d_begin);
+  if (s.d_end) cudaFree(s.d_end);
   s = Store();
 }
 
@@ -370,7 +410,21 @@ static int finish_store(vrag_corpus* c, Store& s, const int64_t* page_offsets, i
   s.dirty = false;
   s.n_pages = n_pages;
   s.fixed_rows = fixed_rows;
-  if (fixed_rows > 0) {
+  if (s.d_begin) cudaFree(s.d_begin);
+  if (s.d_end) cudaFree(s.d_end);
+  s.d_begin = s.d_end = nullptr;
+  if (s.indirect) {
+    int64_t mx = 0;
+    for (int64_t i = 0; i < n_pages; ++i) mx = std::max(mx, s.h_end[i] - s.h_begin[i]);
+    s.max_rows = mx;
+    if (n_pages > 0) {
+      CUDA_OK(cudaMalloc(&s.d_begin, n_pages * sizeof(long long)));
+      CUDA_OK(cudaMalloc(&s.d_end, n_pages * sizeof(long long)));
+      CUDA_OK(cudaMemcpyAsync(s.d_begin, s.h_begin.data(), n_pages * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+      CUDA_OK(cudaMemcpyAsync(s.d_end, s.h_end.data(), n_pages * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+      CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+  } else if (fixed_rows > 0) {
     s.max_rows = fixed_rows;
   } else {
     if (page_offsets != s.h_offsets.data()) s.h_offsets.assign(page_offsets, page_offsets + n_pages + 1);
@@ -382,7 +436,7 @@ static int finish_store(vrag_corpus* c, Store& s, const int64_t* page_offsets, i
     CUDA_OK(cudaStreamSynchronize(c->stream));
   }
   s.packed = s.max_rows <= kTileRows;
-  if (s.packed && fixed_rows == 0 && n_pages > 0) {
+  if (s.packed && fixed_rows == 0 && n_pages > 0 && !s.indirect) {
     // greedy packing of consecutive pages into 128-row tiles
     std::vector<int> t0;
     int64_t pg = 0;
@@ -448,6 +502,10 @@ static int alloc_store(vrag_corpus* c, const char* name, int64_t total_rows, Sto
       // every call): keep the row / scale allocations; finish_store rebuilds page tables and tensor maps
       it->second.total_rows = total_rows;
       it->second.h_offsets.clear();
+      it->second.indirect = false;
+      it->second.h_begin.clear();
+      it->second.h_end.clear();
+      it->second.garbage_rows = 0;
       *out = &it->second;
       return 0;
     }
@@ -533,6 +591,37 @@ extern "C" int vrag_store_add(vrag_corpus_t* c, const char* name, const void* ro
   return finish_store(c, *s, page_offsets, n_pages, fixed_rows);
 }
 
+// Grow the row / scale buffers of a store to at least `need` rows (contents preserved).
+static int grow_store(vrag_corpus* c, Store& s, const char* name, int64_t need) {
+  if (need <= s.cap_rows) return 0;
+  if (need >= (1ll << 31)) return fail("a store holds at most 2^31-1 rows per shard (TMA coordinates are int32)");
+  const int64_t cap = std::min<int64_t>((1ll << 31) - 1, std::max<int64_t>(need, s.cap_rows + s.cap_rows / 2 + 1024));
+  __half* nr = nullptr;
+  float* ni = nullptr;
+  CUDA_OK(cudaMalloc(&nr, static_cast<size_t>(cap) * 128 * sizeof(__half)));
+  if (cudaMalloc(&ni, static_cast<size_t>(cap) * sizeof(float)) != cudaSuccess) {
+    cudaFree(nr);
+    return fail("cudaMalloc(inv) failed while growing store '%s'", name);
+  }
+  if (s.total_rows > 0) {
+    cudaError_t e = cudaMemcpyAsync(nr, s.rows, static_cast<size_t>(s.total_rows) * 256, cudaMemcpyDeviceToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ni, s.inv, static_cast<size_t>(s.total_rows) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+      cudaFree(nr);
+      cudaFree(ni);
+      return fail("copy into the grown store '%s' failed: %s", name, cudaGetErrorString(e));
+    }
+  }
+  if (s.rows) cudaFree(s.rows);
+  if (s.inv) cudaFree(s.inv);
+  s.rows = nr;
+  s.inv = ni;
+  s.cap_rows = cap;
+  s.dirty = true;   // tensor maps point at the old buffers
+  return 0;
+}
+
 // Append pages to a named store (created on first use): the ingest path of QdrantIndexer.upload_batch
 // (qdrant_indexer.py:341-507) — every batch of points adds its pages behind the existing ones; page index = upload
 // order. Device buffers grow geometrically; page tables and tensor maps are rebuilt lazily on the next use.
@@ -553,46 +642,45 @@ extern "C" int vrag_store_append(vrag_corpus_t* c, const char* name, const void*
   const int64_t total = s.total_rows + new_rows;
   if (total >= (1ll << 31)) return fail("a store holds at most 2^31-1 rows per shard (TMA coordinates are int32)");
   if (s.n_pages + n_pages >= (1ll << 31)) return fail("a shard holds at most 2^31-1 pages");
-  // ---- page layout: stay fixed-rows only if every new page has the same row count
+  // ---- page layout: stay fixed-rows only if every new page has the same row count. The new layout is built on the side
+  // and committed only after the allocation and the upload have succeeded: a failed append leaves the store untouched.
   bool stay_fixed = s.fixed_rows > 0;
   if (stay_fixed) {
     if (fixed_rows > 0) stay_fixed = fixed_rows == s.fixed_rows;
     else
       for (int64_t i = 0; i < n_pages && stay_fixed; ++i) stay_fixed = (page_offsets[i + 1] - page_offsets[i]) == s.fixed_rows;
   }
+  std::vector<int64_t> new_tail;     // row offsets of the appended pages (absolute), when the store is / becomes variable
+  bool materialise = false;          // the existing pages' offsets have to be written out first (fixed -> variable)
+  if (s.indirect) stay_fixed = false;
   if (!stay_fixed) {
-    if (s.fixed_rows > 0 || s.h_offsets.empty()) {   // materialise the offsets of the existing pages
+    materialise = !s.indirect && (s.fixed_rows > 0 || s.h_offsets.empty());
+    int64_t at = s.total_rows;
+    new_tail.reserve(n_pages);
+    for (int64_t i = 0; i < n_pages; ++i) {
+      at += fixed_rows > 0 ? fixed_rows : (page_offsets[i + 1] - page_offsets[i]);
+      new_tail.push_back(at);
+    }
+  }
+  // ---- grow (same rows, larger buffers: the store is still consistent if the upload below fails)
+  TRY(grow_store(c, s, name, total));
+  if (new_rows > 0) TRY(upload_rows(c, s.rows + static_cast<size_t>(s.total_rows) * 128, s.inv + s.total_rows, rows, dtype, rows_on_device, new_rows));
+  // ---- commit
+  if (s.indirect) {
+    int64_t at = s.total_rows;
+    for (int64_t i = 0; i < n_pages; ++i) {
+      s.h_begin.push_back(at);
+      s.h_end.push_back(new_tail[i]);
+      at = new_tail[i];
+    }
+  } else if (!stay_fixed) {
+    if (materialise) {
       s.h_offsets.resize(s.n_pages + 1);
       for (int64_t i = 0; i <= s.n_pages; ++i) s.h_offsets[i] = i * s.fixed_rows;
     }
-    for (int64_t i = 0; i < n_pages; ++i) {
-      const int64_t r = fixed_rows > 0 ? fixed_rows : (page_offsets[i + 1] - page_offsets[i]);
-      s.h_offsets.push_back(s.h_offsets.back() + r);
-    }
+    s.h_offsets.insert(s.h_offsets.end(), new_tail.begin(), new_tail.end());
     s.fixed_rows = 0;
   }
-  // ---- grow
-  if (total > s.cap_rows) {
-    const int64_t cap = std::min<int64_t>((1ll << 31) - 1, std::max<int64_t>(total, s.cap_rows + s.cap_rows / 2 + 1024));
-    __half* nr = nullptr;
-    float* ni = nullptr;
-    CUDA_OK(cudaMalloc(&nr, static_cast<size_t>(cap) * 128 * sizeof(__half)));
-    if (cudaMalloc(&ni, static_cast<size_t>(cap) * sizeof(float)) != cudaSuccess) {
-      cudaFree(nr);
-      return fail("cudaMalloc(inv) failed while growing store '%s'", name);
-    }
-    if (s.total_rows > 0) {
-      CUDA_OK(cudaMemcpyAsync(nr, s.rows, static_cast<size_t>(s.total_rows) * 256, cudaMemcpyDeviceToDevice, c->stream));
-      CUDA_OK(cudaMemcpyAsync(ni, s.inv, static_cast<size_t>(s.total_rows) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
-      CUDA_OK(cudaStreamSynchronize(c->stream));
-    }
-    if (s.rows) cudaFree(s.rows);
-    if (s.inv) cudaFree(s.inv);
-    s.rows = nr;
-    s.inv = ni;
-    s.cap_rows = cap;
-  }
-  if (new_rows > 0) TRY(upload_rows(c, s.rows + static_cast<size_t>(s.total_rows) * 128, s.inv + s.total_rows, rows, dtype, rows_on_device, new_rows));
   s.total_rows = total;
   s.n_pages += n_pages;
   s.dirty = true;
@@ -616,26 +704,161 @@ extern "C" int vrag_store_replace_pages(vrag_corpus_t* c, const char* name, cons
   if (new_rows > 0 && !rows) return fail("rows is NULL");
   Store& s = it->second;
   // validate everything first: either all pages are replaced or none
+  bool same_shapes = true;
+  int64_t extra_rows = 0;   // rows that have to go behind the last row (pages that grew)
   for (int64_t i = 0; i < n_pages; ++i) {
     const int64_t pg = local_pages[i];
     if (pg < 0 || pg >= s.n_pages) return fail("page %lld out of range (store '%s' has %lld pages)", (long long)pg, name, (long long)s.n_pages);
-    const int64_t have = s.fixed_rows > 0 ? s.fixed_rows : (s.h_offsets[pg + 1] - s.h_offsets[pg]);
+    int64_t r0, have;
+    page_rows_h(s, pg, &r0, &have);
     const int64_t got = fixed_rows > 0 ? fixed_rows : (page_offsets[i + 1] - page_offsets[i]);
-    if (have != got)
-      return fail("page %lld of store '%s' has %lld rows, its replacement has %lld: in-place replacement needs equal shapes",
-                  (long long)pg, name, (long long)have, (long long)got);
+    if (have != got) same_shapes = false;
+    if (got > have) extra_rows += got;
   }
   const size_t el = dtype == VRAG_F16 ? sizeof(__half) : sizeof(float);
+  if (!same_shapes) {
+    // a page changed its row count: the store gets a page table. A page that shrank is overwritten in place, a page
+    // that grew moves behind the last row (its old rows become garbage until vrag_store_compact).
+    if (s.total_rows + extra_rows >= (1ll << 31)) return fail("a store holds at most 2^31-1 rows per shard (TMA coordinates are int32)");
+    TRY(grow_store(c, s, name, s.total_rows + extra_rows));
+    make_indirect(s);
+  }
   for (int64_t i = 0; i < n_pages; ++i) {
     const int64_t pg = local_pages[i];
-    const int64_t r0 = s.fixed_rows > 0 ? pg * s.fixed_rows : s.h_offsets[pg];
+    int64_t r0, have;
+    page_rows_h(s, pg, &r0, &have);
     const int64_t src0 = fixed_rows > 0 ? i * fixed_rows : page_offsets[i];
     const int64_t nr = fixed_rows > 0 ? fixed_rows : (page_offsets[i + 1] - page_offsets[i]);
+    if (nr > have) {          // moves to the end of the row buffer
+      s.garbage_rows += have;
+      r0 = s.total_rows;
+      s.total_rows += nr;
+    } else if (nr < have) {
+      s.garbage_rows += have - nr;
+    }
+    if (nr != have) {
+      s.h_begin[pg] = r0;
+      s.h_end[pg] = r0 + nr;
+      s.dirty = true;
+    }
     if (nr == 0) continue;
     TRY(upload_rows(c, s.rows + static_cast<size_t>(r0) * 128, s.inv + r0,
                     static_cast<const char*>(rows) + static_cast<size_t>(src0) * 128 * el, dtype, rows_on_device, nr));
   }
-  return 0;   // row counts are unchanged: page tables, tile packing and tensor maps stay valid
+  return 0;   // equal shapes: page tables, tile packing and tensor maps stay valid; otherwise rebuilt on next use (dirty)
+}
+
+// Delete pages: a deleted page keeps its index (the id tables of the host stay valid) and owns no rows, so it scores
+// -inf in every scan and is never returned. Its rows are reclaimed by vrag_store_compact.
+extern "C" int vrag_store_delete_pages(vrag_corpus_t* c, const char* name, const int64_t* local_pages, int64_t n_pages) {
+  VRAG_LOCK(c);
+  if (!c) return fail("corpus is NULL");
+  if (!name || !*name) return fail("store name is empty");
+  auto it = c->stores.find(name);
+  if (it == c->stores.end()) return fail("unknown vector store '%s'", name);
+  if (n_pages == 0) return 0;
+  if (!local_pages) return fail("local_pages is NULL");
+  Store& s = it->second;
+  for (int64_t i = 0; i < n_pages; ++i)
+    if (local_pages[i] < 0 || local_pages[i] >= s.n_pages)
+      return fail("page %lld out of range (store '%s' has %lld pages)", (long long)local_pages[i], name, (long long)s.n_pages);
+  make_indirect(s);
+  for (int64_t i = 0; i < n_pages; ++i) {
+    const int64_t pg = local_pages[i];
+    s.garbage_rows += s.h_end[pg] - s.h_begin[pg];
+    s.h_end[pg] = s.h_begin[pg];
+  }
+  s.dirty = true;
+  return 0;
+}
+
+// Drop the last pages of a store (the rollback of a multi-store batch upload whose later store failed).
+extern "C" int vrag_store_truncate(vrag_corpus_t* c, const char* name, int64_t n_pages) {
+  VRAG_LOCK(c);
+  if (!c) return fail("corpus is NULL");
+  if (!name || !*name) return fail("store name is empty");
+  auto it = c->stores.find(name);
+  if (it == c->stores.end()) return fail("unknown vector store '%s'", name);
+  Store& s = it->second;
+  if (n_pages < 0 || n_pages > s.n_pages) return fail("cannot truncate store '%s' (%lld pages) to %lld", name, (long long)s.n_pages, (long long)n_pages);
+  if (n_pages == s.n_pages) return 0;
+  if (s.indirect) {
+    s.h_begin.resize(n_pages);
+    s.h_end.resize(n_pages);
+    int64_t top = 0;
+    for (int64_t p = 0; p < n_pages; ++p) top = std::max(top, s.h_end[p]);
+    s.total_rows = top;
+  } else if (s.fixed_rows > 0) {
+    s.total_rows = n_pages * s.fixed_rows;
+  } else {
+    s.h_offsets.resize(n_pages + 1);
+    s.total_rows = s.h_offsets[n_pages];
+  }
+  s.n_pages = n_pages;
+  s.dirty = true;
+  return 0;
+}
+
+// Rewrite the rows of a store contiguously in page order (one device pass) and return it to the dense layout: garbage
+// left by replaced / deleted pages is reclaimed and the contiguous fast paths apply again. Deleted pages stay as
+// zero-row pages, so page indices do not change.
+static int compact_store(vrag_corpus* c, Store& s, const char* name) {
+  if (!s.indirect) return 0;
+  std::vector<int64_t> off(s.n_pages + 1, 0);
+  for (int64_t p = 0; p < s.n_pages; ++p) off[p + 1] = off[p] + (s.h_end[p] - s.h_begin[p]);
+  const int64_t total = off[s.n_pages];
+  __half* nr = nullptr;
+  float* ni = nullptr;
+  long long *d_b = nullptr, *d_o = nullptr;
+  if (total > 0) {
+    CUDA_OK(cudaMalloc(&nr, static_cast<size_t>(total) * 256));
+    if (cudaMalloc(&ni, static_cast<size_t>(total) * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&d_b, s.n_pages * sizeof(long long)) != cudaSuccess ||
+        cudaMalloc(&d_o, (s.n_pages + 1) * sizeof(long long)) != cudaSuccess) {
+      cudaFree(nr);
+      if (ni) cudaFree(ni);
+      if (d_b) cudaFree(d_b);
+      return fail("cudaMalloc failed while compacting store '%s'", name);
+    }
+    cudaMemcpyAsync(d_b, s.h_begin.data(), s.n_pages * sizeof(long long), cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(d_o, off.data(), (s.n_pages + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream);
+    const unsigned grid = static_cast<unsigned>(std::min<int64_t>(s.n_pages, static_cast<int64_t>(c->num_sms) * 16));
+    compact_rows_kernel<<<grid, 256, 0, c->stream>>>(s.rows, s.inv, d_b, d_o, s.n_pages, nr, ni);
+    c->launches++;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_b);
+    cudaFree(d_o);
+    if (e != cudaSuccess) {
+      cudaFree(nr);
+      cudaFree(ni);
+      return fail("compaction of store '%s' failed: %s", name, cudaGetErrorString(e));
+    }
+  }
+  if (s.rows) cudaFree(s.rows);
+  if (s.inv) cudaFree(s.inv);
+  s.rows = nr;
+  s.inv = ni;
+  s.cap_rows = total;
+  s.total_rows = total;
+  s.indirect = false;
+  s.h_begin.clear();
+  s.h_end.clear();
+  s.garbage_rows = 0;
+  bool same = s.n_pages > 0;
+  for (int64_t p = 1; p < s.n_pages && same; ++p) same = (off[p + 1] - off[p]) == off[1];
+  const int64_t fixed = (same && off[1] > 0) ? off[1] : 0;
+  s.h_offsets = off;
+  return finish_store(c, s, fixed > 0 ? nullptr : s.h_offsets.data(), s.n_pages, fixed);
+}
+
+extern "C" int vrag_store_compact(vrag_corpus_t* c, const char* name) {
+  VRAG_LOCK(c);
+  if (!c) return fail("corpus is NULL");
+  if (!name || !*name) return fail("store name is empty");
+  auto it = c->stores.find(name);
+  if (it == c->stores.end()) return fail("unknown vector store '%s'", name);
+  TRY(set_device(c));
+  return compact_store(c, it->second, name);
 }
 
 extern "C" int vrag_store_add_synthetic(vrag_corpus_t* c, const char* name, const int64_t* page_offsets,
@@ -668,7 +891,7 @@ static int find_store(vrag_corpus* c, const char* name, Store** out) {
   if (it->second.dirty) {   // appended to: rebuild page tables, tile packing and tensor maps once, on first use
     Store& s = it->second;
     TRY(set_device(c));
-    TRY(finish_store(c, s, s.fixed_rows > 0 ? nullptr : s.h_offsets.data(), s.n_pages, s.fixed_rows));
+    TRY(finish_store(c, s, (s.fixed_rows > 0 || s.indirect) ? nullptr : s.h_offsets.data(), s.n_pages, s.fixed_rows));
   }
   return 0;
 }
@@ -691,13 +914,7 @@ extern "C" int vrag_store_page_range(vrag_corpus_t* c, const char* name, int64_t
   Store* s;
   TRY(find_store(c, name, &s));
   if (local_page < 0 || local_page >= s->n_pages) return fail("page %lld out of range", (long long)local_page);
-  if (s->fixed_rows > 0) {
-    *row0 = local_page * s->fixed_rows;
-    *n_rows = s->fixed_rows;
-  } else {
-    *row0 = s->h_offsets[local_page];
-    *n_rows = s->h_offsets[local_page + 1] - s->h_offsets[local_page];
-  }
+  page_rows_h(*s, local_page, row0, n_rows);
   return 0;
 }
 
@@ -753,7 +970,8 @@ static void fill_scan_params(vrag_corpus* c, const Store& s, const long long* d_
                              bool multi = false) {
   ScanParams& p = *out;
   memset(&p, 0, sizeof(p));
-  p.offsets = s.offsets;
+  p.offsets = s.indirect ? s.d_begin : s.offsets;
+  p.page_end = s.indirect ? s.d_end : nullptr;
   p.fixed_rows = s.fixed_rows;
   p.n_pages = s.n_pages;
   p.cand = d_cand;
@@ -767,13 +985,14 @@ static void fill_scan_params(vrag_corpus* c, const Store& s, const long long* d_
   long long n_units = n_items;
   if (s.packed) {
     const bool small_rows = s.max_rows <= 32;
-    if (d_cand) {
-      // slot mode (candidate lists): one slot per page -> segmented-butterfly epilogue when slots are 32 rows
+    if (d_cand || s.indirect) {
+      // slot mode (candidate lists; stores with a page table): one slot per page, fetched on its own -> segmented-butterfly
+      // epilogue when slots are 32 rows
       p.slot_mode = 1;
       p.slot_rows = small_rows ? 32 : (s.max_rows <= 64 ? 64 : 128);
       const int per_tile = kTileRows / p.slot_rows;
       p.n_tiles = (n_items + per_tile - 1) / per_tile;
-      if (p.slot_rows == 32 && QP <= 32) p.shfl_rows = 32;
+      if (p.slot_rows == 32 && (QP <= 32 || (multi && !d_cand))) p.shfl_rows = 32;
     } else if (s.fixed_rows > 0 && s.pad_slot > 0 && (QP <= 32 || multi) && !knob_no_pad()) {
       // odd page sizes (ColSmol's 12/13 tiles, 3, 5, ...): TMA pads every page to a power-of-two slot for free
       p.pad_rows = static_cast<int>(s.fixed_rows);
@@ -801,6 +1020,8 @@ static void fill_scan_params(vrag_corpus* c, const Store& s, const long long* d_
   }
   *n_units_out = n_units;
 }
+
+static int fill_neg_inf(vrag_corpus* c, float* d, int64_t n, cudaStream_t st);
 
 // Score a store (or a candidate list) into d_scores[n_items]. All pointers are device pointers.
 static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int n_query_rows, uint32_t flags,
@@ -836,7 +1057,7 @@ static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int
   const int QP = q_eff <= 8 ? 8 : q_eff <= 16 ? 16 : (q_eff <= 24 && !s.packed) ? 24 : q_eff <= 32 ? 32 : q_eff <= 64 ? 64 : 128;
   const int64_t n_items = d_cand ? n_cand : s.n_pages;
   if (n_items == 0) return 0;
-  if (s.total_rows == 0) return fail("store is empty");
+  if (s.total_rows == 0) return fill_neg_inf(c, d_scores, n_items, st);   // pages without rows (a named vector no point has yet)
 
   query_prep_kernel<<<QP, 128, 0, st>>>(d_query, n_query_rows, pool ? 1 : 0, normalize ? 1 : 0, QP, c->d_qimg.p);
   c->launches++;
@@ -870,7 +1091,7 @@ static int launch_scan_batch(vrag_corpus* c, const Store& s, const float* d_quer
   const int q_eff = pool ? 1 : max_q_eff;
   if (q_eff > 64 || !d_cand) return 2;
   if (n_items == 0 || nq == 0) return 0;
-  if (s.total_rows == 0) return fail("store is empty");
+  if (s.total_rows == 0) return fill_neg_inf(c, d_scores, n_items * nq, st);
   const int QP = q_eff <= 32 ? 32 : 64;
   const size_t img = static_cast<size_t>(2 * QP) * 256;
   TRY(c->d_qimg_batch.ensure(img * nq));
@@ -912,7 +1133,7 @@ static int launch_scan_dense_batch(vrag_corpus* c, const Store& s, const float* 
   const int q_eff = pool ? 1 : max_q_eff;
   if (q_eff > 32 || nq < 1) return 2;
   if (s.n_pages == 0) return 0;
-  if (s.total_rows == 0) return fail("store is empty");
+  if (s.total_rows == 0) return 2;   // pages without rows: the per-query path fills -inf
   const int QP = 128;
   const int QS = q_eff == 1 ? 1 : 32;
   const int G = QP / QS;
@@ -2069,8 +2290,8 @@ extern "C" int vrag_saliency(vrag_corpus_t* c, const char* name, const float* qu
   const int64_t local = page_id - c->page_base;
   if (local < 0 || local >= s->n_pages) return fail("page id %lld is not in this shard", (long long)page_id);
   if (n_query_rows < 1 || n_query_rows > kMaxQueryRows) return fail("query rows %d out of range [1,%d]", n_query_rows, kMaxQueryRows);
-  const int64_t r0 = s->fixed_rows > 0 ? local * s->fixed_rows : s->h_offsets[local];
-  const int64_t n = s->fixed_rows > 0 ? s->fixed_rows : (s->h_offsets[local + 1] - s->h_offsets[local]);
+  int64_t r0, n;
+  page_rows_h(*s, local, &r0, &n);
   *out_rows = n;
   if (n > capacity) return fail("output buffer too small: need %lld scores", (long long)n);
   if (n == 0) return 0;
@@ -2416,6 +2637,7 @@ extern "C" int vrag_store_pool(vrag_corpus_t* c, const char* src, int n_specs, c
   Store* sp;
   TRY(find_store(c, src, &sp));
   TRY(set_device(c));
+  if (sp->indirect) TRY(compact_store(c, *sp, src));   // the pooling kernels read pages as contiguous row ranges
   if (n_specs < 1 || n_specs > kPoolMaxSpecs) return fail("n_specs %d out of range [1,%d]", n_specs, kPoolMaxSpecs);
   if (!specs || !dst_names) return fail("NULL argument");
   const int64_t n_pages = sp->n_pages;
@@ -2427,6 +2649,8 @@ extern "C" int vrag_store_pool(vrag_corpus_t* c, const char* src, int n_specs, c
   for (int i = 0; i < n_specs; ++i) {
     if (!dst_names[i] || !*dst_names[i]) return fail("dst name %d is empty", i);
     if (std::string(dst_names[i]) == src) return fail("dst store must differ from src");
+    for (int j = 0; j < i; ++j)
+      if (std::string(dst_names[i]) == dst_names[j]) return fail("dst store '%s' is named twice", dst_names[i]);
     const int par = specs[i].input_spec - 1;   // -1: the source store
     if (par >= i) return fail("spec %d: input_spec must name an earlier spec", i);
     if (par >= 0) {
@@ -2459,15 +2683,25 @@ extern "C" int vrag_store_pool(vrag_corpus_t* c, const char* src, int n_specs, c
     }
     if (all_same && n_pages > 0 && offs[i][1] > 0) fixed[i] = offs[i][1];
   }
-  // 2. allocate destination stores, device offsets, per-page grids
-  int* d_grid = nullptr;
+  // 2. allocate destination stores, device offsets, per-page grids (the temporaries are freed on every return path)
+  struct Temps {
+    int* grid = nullptr;
+    std::vector<long long*> offs;
+    ~Temps() {
+      if (grid) cudaFree(grid);
+      for (auto p : offs)
+        if (p) cudaFree(p);
+    }
+  } tmp;
+  tmp.offs.assign(n_specs, nullptr);
+  int*& d_grid = tmp.grid;
+  std::vector<long long*>& d_offs = tmp.offs;
   if (grid_hw && n_pages > 0) {
     CUDA_OK(cudaMalloc(&d_grid, n_pages * 2 * sizeof(int)));
     CUDA_OK(cudaMemcpyAsync(d_grid, grid_hw, n_pages * 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   }
   std::vector<PoolSpecDev> dev(n_specs);
   std::vector<Store*> dst(n_specs);
-  std::vector<long long*> d_offs(n_specs, nullptr);
   // NOTE: alloc_store may rehash the map; std::map keeps element addresses stable, and `sp` stays valid.
   for (int i = 0; i < n_specs; ++i) {
     TRY(alloc_store(c, dst_names[i], offs[i][n_pages], &dst[i]));
@@ -2504,8 +2738,6 @@ extern "C" int vrag_store_pool(vrag_corpus_t* c, const char* src, int n_specs, c
     }
   }
   cudaError_t e = cudaStreamSynchronize(c->stream);
-  for (auto p : d_offs) if (p) cudaFree(p);
-  if (d_grid) cudaFree(d_grid);
   if (rc) return rc;
   if (e != cudaSuccess) return fail("pooling kernels failed: %s", cudaGetErrorString(e));
   cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1);

@@ -71,6 +71,9 @@ SIGNATURES = {
     "vrag_store_add": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, _i64p, C.c_int64, C.c_int64]),
     "vrag_store_append": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, _i64p, C.c_int64, C.c_int64]),
     "vrag_store_replace_pages": (C.c_int, [C.c_void_p, C.c_char_p, _i64p, C.c_int64, C.c_void_p, C.c_int, C.c_int, _i64p, C.c_int64]),
+    "vrag_store_delete_pages": (C.c_int, [C.c_void_p, C.c_char_p, _i64p, C.c_int64]),
+    "vrag_store_truncate": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "vrag_store_compact": (C.c_int, [C.c_void_p, C.c_char_p]),
     "vrag_store_add_synthetic": (C.c_int, [C.c_void_p, C.c_char_p, _i64p, C.c_int64, C.c_int64, C.c_uint64, C.c_int64]),
     "vrag_store_info": (C.c_int, [C.c_void_p, C.c_char_p, _i64p, _i64p, _i64p, _i64p]),
     "vrag_store_read_rows": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64, C.c_void_p]),

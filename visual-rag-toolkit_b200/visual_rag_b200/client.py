@@ -161,6 +161,21 @@ class GpuCorpusClient:
         self._payloads[page - self.corpus.page_base] = payload
         self._invalidate()
 
+    @_locked
+    def remove_points(self, point_ids: Sequence[Any]) -> None:
+        """Forget deleted points: their pages stay (empty) in the stores, their ids leave the index."""
+        if self._ids is None:       # implicit ids (page index): make them explicit first
+            n = max([self.corpus.n_pages(nm) for nm in ("initial", "mean_pooling", "global_pooling") if self.corpus.has_store(nm)] or [0])
+            self._ids = list(range(self.corpus.page_base, self.corpus.page_base + n))
+            self._index = {pid: i for i, pid in enumerate(self._ids)}
+        for pid in point_ids:
+            i = self._index.pop(pid, None)
+            if i is not None:
+                self._ids[i] = None
+                if self._payloads is not None:
+                    self._payloads[i] = None
+        self._invalidate()
+
     def _pid(self, page: int):
         local = page - self.corpus.page_base
         return self._ids[local] if self._ids is not None else page

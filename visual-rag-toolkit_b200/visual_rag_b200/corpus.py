@@ -17,6 +17,16 @@ import numpy as np
 from . import _native as N
 
 DIM = 128
+MAX_K = 4096   # kTopkMaxK of the library: the largest `limit` / `prefetch_k` / stage size one search stage can keep
+
+
+def _check_k(k: int, what: str = "k") -> int:
+    """Stage sizes are validated here so that an oversized request is a plain ValueError (never retried by the
+    retrievers' back-off loop) instead of a library error."""
+    k = int(k)
+    if k > MAX_K:
+        raise ValueError(f"{what}={k} exceeds the supported maximum {MAX_K} results per search stage")
+    return k
 
 
 def _as_f32_query(query) -> np.ndarray:
@@ -227,9 +237,9 @@ class GpuCorpus:
                                             int(n_pages), int(fixed_rows)))
 
     def replace_pages(self, name: str, local_pages: Sequence[int], rows, page_offsets: Sequence[int]) -> None:
-        """Overwrite existing pages of `name` in place (the upsert of points that already exist,
-        qdrant_indexer.py:459-507). Every replacement must have the row count of the page it replaces; otherwise the
-        library refuses and nothing is written."""
+        """Overwrite existing pages of `name` (the upsert of points that already exist, qdrant_indexer.py:459-507).
+        Pages that keep their row count are rewritten in place; a page whose row count changed puts the store on a page
+        table (see include/vrag_b200.h) until `compact_store`."""
         arr = np.asarray(rows)
         if arr.dtype not in (np.float16, np.float32):
             arr = arr.astype(np.float32)
@@ -242,6 +252,19 @@ class GpuCorpus:
         N.check(self._lib.vrag_store_replace_pages(self._h, name.encode(), pages.ctypes.data_as(C.POINTER(C.c_int64)),
                                                    int(pages.size), arr.ctypes.data_as(C.c_void_p), dtype, 0,
                                                    off.ctypes.data_as(C.POINTER(C.c_int64)), 0))
+
+    def delete_pages(self, name: str, local_pages: Sequence[int]) -> None:
+        """Deleted pages keep their index but own no rows: they score -inf and are never returned."""
+        pages = np.ascontiguousarray(np.asarray(local_pages, dtype=np.int64))
+        N.check(self._lib.vrag_store_delete_pages(self._h, name.encode(), pages.ctypes.data_as(C.POINTER(C.c_int64)), int(pages.size)))
+
+    def truncate_store(self, name: str, n_pages: int) -> None:
+        """Drop the last pages of `name`, keeping n_pages (rollback of a failed multi-store batch upload)."""
+        N.check(self._lib.vrag_store_truncate(self._h, name.encode(), int(n_pages)))
+
+    def compact_store(self, name: str) -> None:
+        """Return a store with a page table to the dense layout (reclaims the rows of replaced / deleted pages)."""
+        N.check(self._lib.vrag_store_compact(self._h, name.encode()))
 
     def add_synthetic_store(
         self,
@@ -372,7 +395,7 @@ class GpuCorpus:
         """Top-k pages by MaxSim: (scores fp32 [m], global page ids int64 [m]), m <= k, sorted by score
         descending, ties by lower id."""
         q = _as_f32_query(query)
-        k = int(k)
+        k = _check_k(k)
         if k < 1 or (candidate_ids is not None and len(candidate_ids) == 0 and self.world == 1):
             return np.empty((0,), np.float32), np.empty((0,), np.int64)
         cand, cand_p, n_cand = self._cand_arg(candidate_ids)
@@ -403,6 +426,8 @@ class GpuCorpus:
         stage_queries: optional per-stage query matrices (else every stage uses `query`).
         Returns per-stage (scores, ids)."""
         ns = len(stages)
+        for st in stages:
+            _check_k(st[2], f"stage '{st[0]}': k")
         if stage_queries is not None:
             qs = [_as_f32_query(x) for x in stage_queries]
             if len(qs) != ns:
@@ -458,6 +483,8 @@ class GpuCorpus:
         for every final result, the score its page had in each earlier stage (NaN if absent) — what the retrievers' result
         dictionaries carry — so the long intermediate lists never leave the device."""
         ns = len(stages)
+        for st in stages:
+            _check_k(st[2], f"stage '{st[0]}': k")
         if stage_queries is not None:
             mats = []
             for sq in stage_queries:
@@ -475,6 +502,12 @@ class GpuCorpus:
             nq = len(mats)
             per_stage = 0
         if nq == 0:
+            if final_only:
+                kl = int(stages[-1][2])
+                return (np.empty((0, kl), np.float32), np.empty((0, kl), np.int64), np.empty((0, kl, max(ns - 1, 0)), np.float32),
+                        np.empty((0,), np.int32))
+            if as_arrays:
+                return [(np.empty((0, int(k)), np.float32), np.empty((0, int(k)), np.int64), np.empty((0,), np.int32)) for _, _, k in stages]
             return []
         if mats is None:
             rows, offs = queries.rows, queries.offsets

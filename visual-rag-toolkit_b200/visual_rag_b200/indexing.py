@@ -7,7 +7,8 @@ visual_rag/indexing/qdrant_indexer.py::QdrantIndexer that the processing pipelin
 (optional) and `metadata`; this class appends them to the named stores of a GpuCorpus with the same store-dtype
 cast (every array -> fp32 -> fp16, 423-441) and the same fallback global = mean(tile_pooled) (417-421), and
 registers id / payload with the GpuCorpusClient so the retrievers can serve the pages immediately. Ids that already
-exist are overwritten in place (upsert), as long as the point keeps its shape.
+exist are overwritten (upsert) whatever their new shape; named vectors are optional per point; a failed batch leaves
+nothing behind (appends are rolled back) and reports 0 uploaded points, like the reference.
 """
 
 from __future__ import annotations
@@ -37,6 +38,7 @@ class GpuIndexer:
         if self.client._ids is None:
             self.client.set_points([], [])
         self._extra_names: List[str] = []
+        self._seen_names: List[str] = []      # every named vector an upload has written so far
         # the reference drives upload_batch from uploader threads (run_qdrant_beir.py:720-768) while queries may run: one
         # batch at a time validates, writes its pages to every named store and registers its ids; searches wait
         self._lock = self.client._lock      # shared with the client's query methods (re-entrant)
@@ -55,9 +57,10 @@ class GpuIndexer:
         if self.collection_exists():
             if not force_recreate:
                 return False
-            for nm in names:
+            for nm in list(dict.fromkeys(names + self._seen_names)):
                 if self.corpus.has_store(nm):
                     self.corpus.drop_store(nm)
+            self._seen_names = []
             self.client.set_points([], [])
         return True
 
@@ -87,17 +90,30 @@ class GpuIndexer:
 
     def upload_batch(self, points: List[Dict[str, Any]], max_retries: int = 3, delay_between_batches: float = 0.0,
                      wait: bool = True, stop_event=None) -> int:
-        """qdrant_indexer.py:341-507 (client.upsert semantics). Returns the number of uploaded points. New ids are
-        appended behind the existing pages; an id that is already in the collection is overwritten IN PLACE (vectors of
-        every named store + payload), which needs every vector of the point to keep its row count — the dense shard
-        layout cannot grow a page in the middle, so a point whose shape changed raises ValueError (nothing is written;
-        rebuild with create_collection(force_recreate=True)). Within one batch the last occurrence of an id wins."""
+        """qdrant_indexer.py:341-507 (client.upsert semantics). Returns the number of uploaded points — and, like the
+        reference, 0 after logging when the batch cannot be written (malformed points, device errors): nothing of a
+        failed batch stays in the collection.
+
+        New ids are appended behind the existing pages; an id that is already in the collection is overwritten (vectors
+        of every named store + payload) whatever its new shape — a page whose row count changed moves the store onto a
+        page table until `compact()`. Named vectors are optional per point, as in Qdrant: the pipeline emits
+        `experimental_pooling_2d` only for pages with a tile grid (pipeline.py:485-503); a point without a named vector
+        owns an empty page in that store (it scores -inf there and is never returned from it), so page indices stay
+        aligned across stores. Within one batch the last occurrence of an id wins."""
         if not points:
             return 0
         if stop_event is not None and getattr(stop_event, "is_set", lambda: False)():
             return 0
         with self._lock:
-            return self._upload_locked(points)
+            try:
+                return self._upload_locked(points)
+            except Exception as e:  # noqa: BLE001 - the reference's contract: log and report 0 uploaded points
+                logger.error(f"Upload failed: {e}")
+                return 0
+
+    def _known_names(self) -> List[str]:
+        names = ["initial", "mean_pooling", "global_pooling", "experimental_pooling"] + list(self._extra_names) + list(self._seen_names)
+        return [n for n in dict.fromkeys(names) if self.corpus.has_store(n)]
 
     def _upload_locked(self, points: List[Dict[str, Any]]) -> int:
         # ---- every point -> its named vectors (fp32 first, 423-441); the last occurrence of an id wins
@@ -117,43 +133,85 @@ class GpuIndexer:
                         per_point[str(k)] = self._rows(v)
             elif exp is not None:
                 per_point["experimental_pooling"] = self._rows(exp)
+            for k, v in per_point.items():
+                if v.ndim != 2 or v.shape[1] != 128:
+                    raise ValueError(f"point {p['id']!r}: named vector '{k}' has shape {v.shape}, expected [rows, 128]")
             per_id.pop(p["id"], None)            # re-insert so that dict order = order of the last occurrences
             per_id[p["id"]] = per_point
             payload_of[p["id"]] = p.get("metadata")
         new_ids = [i for i in per_id if not self.check_exists(i)]
         old_ids = [i for i in per_id if self.check_exists(i)]
         n_before = len(self.client._ids)
-        names = sorted({k for v in per_id.values() for k in v})
-        # ---- validate before anything is written
-        for name in names:
-            missing = [i for i in per_id if name not in per_id[i]]
-            if missing:
-                raise ValueError(f"named vector '{name}' is missing from some points of the batch")
-            have = self.corpus.n_pages(name) if self.corpus.has_store(name) else 0
+        existing = self._known_names()
+        names = list(dict.fromkeys(existing + sorted({k for v in per_id.values() for k in v})))
+        # ---- validate before anything is written: every store of the collection holds one page per point
+        for name in existing:
+            have = self.corpus.n_pages(name)
             if have != n_before:
                 raise ValueError(f"named vector '{name}' holds {have} pages but the collection has {n_before} points")
         base = self.corpus.page_base
         old_pages = [self.client._page(i) - base for i in old_ids]
-        for name in names:
-            for i, pg in zip(old_ids, old_pages):
-                have_rows = self.corpus.page_range(name, pg)[1]
-                got_rows = per_id[i][name].shape[0]
-                if have_rows != got_rows:
-                    raise ValueError(f"point id {i!r}: named vector '{name}' has {have_rows} rows in the collection, the "
-                                     f"upserted point has {got_rows}; in-place replacement needs equal shapes")
-        # ---- write: replacements in place, new points appended
-        for name in names:
-            if old_ids:
-                mats = [per_id[i][name] for i in old_ids]
-                off = np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])]).astype(np.int64)
-                self.corpus.replace_pages(name, old_pages, np.concatenate(mats, axis=0).astype(np.float16), off)
+        empty = np.zeros((0, 128), dtype=np.float32)
+
+        def pack(ids, name):
+            mats = [per_id[i].get(name, empty) for i in ids]       # a point without this named vector: an empty page
+            off = np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])]).astype(np.int64)
+            rows = np.concatenate(mats, axis=0).astype(np.float16) if mats else np.zeros((0, 128), np.float16)   # store dtype cast
+            return rows, off
+
+        # ---- write. Appends first (they can be rolled back by truncating), then the in-place part of the upsert.
+        appended: List[str] = []
+        created: List[str] = []
+        try:
             if new_ids:
-                mats = [per_id[i][name] for i in new_ids]
-                off = np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])]).astype(np.int64)
-                rows = np.concatenate(mats, axis=0).astype(np.float16)           # store dtype cast
-                self.corpus.append_store(name, rows, page_offsets=off)
+                for name in names:
+                    if not self.corpus.has_store(name):
+                        created.append(name)
+                        if n_before > 0:        # a named vector that appears late: the earlier points own empty pages in it
+                            self.corpus.append_store(name, np.zeros((0, 128), np.float16), page_offsets=np.zeros((n_before + 1,), np.int64))
+                    rows, off = pack(new_ids, name)
+                    self.corpus.append_store(name, rows, page_offsets=off)
+                    appended.append(name)
+            if old_ids:
+                for name in names:
+                    if not self.corpus.has_store(name):
+                        created.append(name)
+                        self.corpus.append_store(name, np.zeros((0, 128), np.float16), page_offsets=np.zeros((n_before + 1,), np.int64))
+                    rows, off = pack(old_ids, name)
+                    self.corpus.replace_pages(name, old_pages, rows, off)
+        except Exception:
+            for name in created:
+                if self.corpus.has_store(name):
+                    self.corpus.drop_store(name)
+            for name in appended:
+                if name not in created and self.corpus.has_store(name):
+                    self.corpus.truncate_store(name, n_before)
+            raise
+        for name in names:
+            if name not in self._seen_names:
+                self._seen_names.append(name)
         for i in old_ids:
             self.client.set_payload(i, payload_of[i])
         if new_ids:
             self.client.append_points(new_ids, [payload_of[i] for i in new_ids])
         return len(points)
+
+    # ------------------------------------------------------------------ deletes / maintenance
+    def delete_points(self, point_ids: Sequence[Any]) -> int:
+        """qdrant `client.delete(points_selector=ids)`: the points disappear from every search and from check_exists; their
+        pages keep their index (and are reclaimed by `compact`). Returns the number of deleted points."""
+        with self._lock:
+            base = self.corpus.page_base
+            pages = [self.client._page(i) - base for i in point_ids if self.check_exists(i)]
+            if not pages:
+                return 0
+            for name in self._known_names():
+                self.corpus.delete_pages(name, pages)
+            self.client.remove_points([i for i in point_ids if self.check_exists(i)])
+            return len(pages)
+
+    def compact(self) -> None:
+        """Return every named store to the dense layout (after shape-changing upserts / deletes)."""
+        with self._lock:
+            for name in self._known_names():
+                self.corpus.compact_store(name)

@@ -75,7 +75,12 @@ def retry_call(fn, max_retries: int, retry_sleep: float):
     for attempt in range(max_retries):
         try:
             return fn()
+        except (ValueError, TypeError, NotImplementedError, KeyError):
+            raise       # deterministic: a bad argument does not get better with a back-off (the reference's loop guards
+                        # network hiccups of a remote Qdrant)
         except Exception as e:  # noqa: BLE001 - mirror of the reference
+            if type(e).__name__ == "VragError":   # an error reported by the library is deterministic too
+                raise
             last_err = e
             if attempt >= max_retries - 1:
                 break
