@@ -14,36 +14,44 @@ import numpy as np
 from . import pooling as GP
 
 
+def _divisor_pairs(n: int):
+    """(h, w) with h * w == n, in the order the grid search visits them: for every divisor d <= sqrt(n) ascending,
+    first (d, n/d), then its transpose."""
+    for d in range(1, math.isqrt(n) + 1):
+        if n % d == 0:
+            yield d, n // d
+            yield n // d, d
+
+
 def infer_grid(num_tokens: int, *, width: Optional[int] = None, height: Optional[int] = None) -> Tuple[int, int]:
-    """scripts/qdrant_recompute_colqwen_pooling_from_initial.py:64-105 (host logic, same enumeration order)."""
+    """Patch grid (rows, cols) of a page from its token count and image size — the rule of
+    scripts/qdrant_recompute_colqwen_pooling_from_initial.py:64-105: among all factorisations rows * cols == num_tokens
+    take the one whose cols/rows ratio is closest (in log space) to the image's width/height; unknown sizes mean a
+    square target; the first factorisation in search order wins a tie. Host logic (a few dozen divisors per distinct
+    token count; results are cached per (tokens, width, height) by the caller)."""
     n = int(num_tokens)
     if n <= 0:
         raise ValueError("num_tokens must be > 0")
-    if width and height and int(width) > 0 and int(height) > 0:
-        aspect = float(width) / float(height)
-    else:
-        aspect = 1.0
-    best = None
-    best_score = float("inf")
-    for h in range(1, int(math.isqrt(n)) + 1):
-        if n % h != 0:
-            continue
-        w = n // h
-        for hh, ww in ((h, w), (w, h)):
-            score = abs(math.log(max(float(ww) / float(hh), 1e-9) / max(aspect, 1e-9)))
-            if score < best_score:
-                best_score = score
-                best = (int(hh), int(ww))
-    return best
+    have_size = bool(width) and bool(height) and int(width) > 0 and int(height) > 0
+    target = max(float(width) / float(height), 1e-9) if have_size else 1.0
+
+    def mismatch(hw: Tuple[int, int]) -> float:
+        rows, cols = hw
+        return abs(math.log(max(float(cols) / float(rows), 1e-9) / target))
+
+    rows, cols = min(_divisor_pairs(n), key=mismatch)     # min() keeps the first of equally good candidates
+    return int(rows), int(cols)
 
 
 def _payload_size(payload: Optional[Dict[str, Any]]):
+    """(width, height) of the image the page's tokens were computed from: the resized size if recorded, else the cropped,
+    else the original one (qdrant_recompute_colqwen_pooling_from_initial.py:292-300); (None, None) when unusable."""
     payload = payload or {}
-    w = payload.get("resized_width") or payload.get("cropped_width") or payload.get("original_width")
-    h = payload.get("resized_height") or payload.get("cropped_height") or payload.get("original_height")
+    dims = [next((payload[f"{stage}_{axis}"] for stage in ("resized", "cropped", "original") if payload.get(f"{stage}_{axis}")), None)
+            for axis in ("width", "height")]
     try:
-        return (int(w) if w is not None else None), (int(h) if h is not None else None)
-    except Exception:
+        return tuple(int(v) if v is not None else None for v in dims)
+    except (TypeError, ValueError):
         return None, None
 
 
