@@ -52,15 +52,23 @@ struct ScanCfg {
   static constexpr int sc_bytes(bool packed, bool multi = false) {
     return packed ? (multi ? 4 * 32 : EPI_GROUPS_PACKED * QP) * SC_PITCH * 4 : 0;
   }
+  // PACKED kernels keep the per-tile side data (inverse norms, slot metadata) in a ring of kMetaRing entries indexed by the
+  // tile's sequence number instead of inside the row stage: the 32 KB row stage is handed back to the producer as soon as
+  // the tile's MMAs retire, not when its epilogue gets round to it (gathers are bound by tiles in flight x latency). The
+  // ring is deeper than stages + accumulator stages, the furthest the producer can run ahead of the epilogue.
+  static constexpr int kMetaRing = 16;
+  static constexpr int meta_entries(bool packed, int n_stages) { return packed ? kMetaRing : n_stages; }
+  static constexpr int stage_bytes(bool packed) { return kTileBytes + (packed ? 0 : kScaleStride * 4); }
   // bsw: the query operand is double-buffered so that a CTA can switch between query groups mid-kernel
   static constexpr int stages(bool packed, bool bsw = false, bool multi = false) {
-    const int budget = 227 * 1024 - 1024 /*align slack*/ - (bsw ? 2 : 1) * B_BYTES - MISC_BYTES - sc_bytes(packed, multi);
-    const int s = budget / (kTileBytes + kScaleStride * 4);
+    const int budget = 227 * 1024 - 1024 /*align slack*/ - (bsw ? 2 : 1) * B_BYTES - MISC_BYTES - sc_bytes(packed, multi) -
+                       (packed ? kMetaRing * kScaleStride * 4 : 0);
+    const int s = budget / stage_bytes(packed);
     return s > 6 ? 6 : s;
   }
   static constexpr size_t smem_bytes(bool packed, bool bsw = false, bool multi = false) {
-    return 1024 + size_t(stages(packed, bsw, multi)) * (kTileBytes + kScaleStride * 4) + (bsw ? 2 : 1) * B_BYTES +
-           MISC_BYTES + sc_bytes(packed, multi);
+    return 1024 + size_t(stages(packed, bsw, multi)) * stage_bytes(packed) + (packed ? kMetaRing * kScaleStride * 4 : 0) +
+           (bsw ? 2 : 1) * B_BYTES + MISC_BYTES + sc_bytes(packed, multi);
   }
 };
 
@@ -190,7 +198,7 @@ __device__ __forceinline__ void packed_segment(const ScanParams& p, int g, long 
 // of stage buffer `a` (+ their inv_norm scales at sc[(row & 3) ...]). dst_row is a multiple of 32.
 // Returns the bytes the mbarrier must expect.
 __device__ __forceinline__ uint32_t issue_rows(uint8_t* a, float* sc, uint64_t* bar, const CUtensorMap* tm128,
-                                               const CUtensorMap* tm32, const CUtensorMap* ts128,
+                                               const RowMaps* small, const CUtensorMap* ts128,
                                                const CUtensorMap* ts32, long long row, int nrows, int dst_row,
                                                bool use_scale) {
   const int32_t r32 = static_cast<int32_t>(row);
@@ -200,16 +208,23 @@ __device__ __forceinline__ uint32_t issue_rows(uint8_t* a, float* sc, uint64_t* 
     if (use_scale) tma_load_1d(sc, ts128, bar, r32 & ~3);
     return kTileBytes + (use_scale ? kScaleBoxBig * 4 : 0);
   }
+  // boxes of at most 32 rows; the last one is sized to the rows that are left (rounded up to 4): the rows of the tile
+  // beyond it keep stale shared memory, which the epilogue never reads (it masks by the page's row count)
   const int nb = (nrows + kBoxRowsSmall - 1) / kBoxRowsSmall;
+  uint32_t bytes = 0;
   for (int j = 0; j < nb; ++j) {
     const int32_t r = r32 + j * kBoxRowsSmall;
     const int d = dst_row + j * kBoxRowsSmall;
-    tma_load_2d(a + d * 128, tm32, bar, 0, r);
-    tma_load_2d(a + kHalfBytes + d * 128, tm32, bar, 64, r);
+    const int left = nrows - j * kBoxRowsSmall;
+    const int mi = (min(left, kBoxRowsSmall) + kBoxStep - 1) / kBoxStep - 1;
+    const CUtensorMap* tm = &small->m[mi];
+    tma_load_2d(a + d * 128, tm, bar, 0, r);
+    tma_load_2d(a + kHalfBytes + d * 128, tm, bar, 64, r);
+    bytes += (mi + 1) * kBoxStep * kDim * 2;
     // consecutive scale boxes of one slot overlap by 4 floats in smem; both write identical values there
     if (use_scale) tma_load_1d(sc + j * kBoxRowsSmall, ts32, bar, r & ~3);
   }
-  return nb * (kBoxRowsSmall * kDim * 2 + (use_scale ? kScaleBoxSmall * 4 : 0));
+  return bytes + nb * (use_scale ? kScaleBoxSmall * 4 : 0);
 }
 
 // In-place butterfly max over the 32 lanes of a warp for CNT (power of two <= 32) values per lane.
@@ -283,7 +298,7 @@ __device__ __forceinline__ float slot_maxsim(float* v, int lane, int q_valid) {
 // candidate scans). QS < QP (dense batched scans): QP/QS queries share every document tile.
 template <int QP, int QS, bool PACKED, bool BSW>
 __global__ void __launch_bounds__(ScanCfg<QP>::threads(PACKED, QS < QP), 1)
-maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_constant__ CUtensorMap tm_rows32,
+maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_constant__ RowMaps tm_small,
                    const __grid_constant__ CUtensorMap tm_scale128, const __grid_constant__ CUtensorMap tm_scale32,
                    const ScanParams p) {
   using Cfg = ScanCfg<QP>;
@@ -309,7 +324,9 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * kTileBytes;
   float* sScale = reinterpret_cast<float*>(sB + NB * Cfg::B_BYTES);
-  float* sSc = sScale + STAGES * kScaleStride;                       // PACKED: [EPI_GROUPS][QP][SC_PITCH]
+  constexpr int META = Cfg::meta_entries(PACKED, STAGES);             // side-data entries: ring (PACKED) / one per stage
+  static_assert(!PACKED || META >= 6 + ACC + 1, "side-data ring shorter than the producer's lead over the epilogue");
+  float* sSc = sScale + META * kScaleStride;                         // PACKED: [EPI_GROUPS][QP][SC_PITCH]
   uint8_t* misc = reinterpret_cast<uint8_t*>(sSc) + Cfg::sc_bytes(PACKED, MULTI);
   uint64_t* full = reinterpret_cast<uint64_t*>(misc);
   uint64_t* empty = full + STAGES;
@@ -318,7 +335,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   uint64_t* bfull = tempty + ACC;            // BSW: operand buffer filled (bulk copy) / drained (MMAs retired)
   uint64_t* bempty = bfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty + 2);
-  int* sMis = reinterpret_cast<int*>(misc + 256);                 // [STAGES][4] scale misalignment per slot
+  int* sMis = reinterpret_cast<int*>(misc + 256);                 // [META][4] scale misalignment (+ slot rows) per slot
   float* sRed = reinterpret_cast<float*>(misc + 512);             // LARGE: [2][4][QP]
   int* sSeg = reinterpret_cast<int*>(misc + 512);                 // PACKED: [EPI_GROUPS][3][128] ints (item, begin, end)
   float* sThr = reinterpret_cast<float*>(misc + 7168);            // QS < QP: [128] prefilter thresholds
@@ -336,15 +353,19 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_rows128);
-    tma_prefetch_desc(&tm_rows32);
+    for (int i = 0; i < kNumSmallMaps; ++i) tma_prefetch_desc(&tm_small.m[i]);
     tma_prefetch_desc(&tm_scale128);
     tma_prefetch_desc(&tm_scale32);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1 + EPI_ARRIVALS);   // tcgen05.commit + one arrive per consuming epilogue warp (scale rows)
+      // LARGE: tcgen05.commit + one arrive per consuming epilogue warp (it reads the stage's scale rows).
+      // PACKED: the commit alone — the epilogue reads its side data from the ring, never from the stage.
+      mbar_init(&empty[s], PACKED ? 1 : 1 + EPI_ARRIVALS);
     }
     for (int a = 0; a < ACC; ++a) {
-      mbar_init(&tfull[a], 1);
+      // PACKED: + a plain arrive of the MMA thread after it observed full[stage]: the epilogue acquires the TMA-written
+      // side data through tfull (it must not wait on full[stage] itself: the stage may already be in its next round)
+      mbar_init(&tfull[a], PACKED ? 2 : 1);
       mbar_init(&tempty[a], EPI_ARRIVALS);
     }
     for (int b = 0; b < 2; ++b) {
@@ -454,12 +475,13 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             uint32_t bytes = 0;
             if (lane < 4) {
               uint8_t* a = sA + stage * kTileBytes;
-              float* sc = sScale + stage * kScaleStride;
+              const int me = static_cast<int>((i0 + t) % META);          // side-data ring entry of this tile
+              float* sc = sScale + me * kScaleStride;
               if (my_nr > 0)
-                bytes = issue_rows(a, sc + lane * (p.slot_rows + 32), &full[stage], &tm_rows128, &tm_rows32, &tm_scale128,
+                bytes = issue_rows(a, sc + lane * (p.slot_rows + 32), &full[stage], &tm_rows128, &tm_small, &tm_scale128,
                                    &tm_scale32, my_r0, my_nr, lane * p.slot_rows, use_scale);
               // low 2 bits: scale misalignment; rest: rows of the slot (0 for unused / empty slots)
-              sMis[stage * 4 + lane] = static_cast<int>(my_r0 & 3) | (my_nr << 2);
+              sMis[me * 4 + lane] = static_cast<int>(my_r0 & 3) | (my_nr << 2);
             }
             bytes += __shfl_xor_sync(0xffffffffu, bytes, 1);
             bytes += __shfl_xor_sync(0xffffffffu, bytes, 2);
@@ -497,7 +519,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             float* sc = sScale + stage * kScaleStride;
             // copies first, then one arrive.expect_tx with the exact byte count: the phase cannot complete
             // before the arrive, and the tx-count may go transiently negative.
-            const uint32_t bytes = issue_rows(a, sc, &full[stage], &tm_rows128, &tm_rows32, &tm_scale128,
+            const uint32_t bytes = issue_rows(a, sc, &full[stage], &tm_rows128, &tm_small, &tm_scale128,
                                               &tm_scale32, row0 + t0, rows, 0, use_scale);
             sMis[stage * 4] = static_cast<int>((row0 + t0) & 3);
             mbar_arrive_expect_tx(&full[stage], bytes);
@@ -516,7 +538,8 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           }
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* a = sA + stage * kTileBytes;
-          float* sc = sScale + stage * kScaleStride;
+          const int me = static_cast<int>(i % META);                     // side-data ring entry of this tile
+          float* sc = sScale + me * kScaleStride;
           uint32_t bytes = 0;
           if (p.pad_rows > 0) {
             // padded slots: the first map is the store's 3-D {cols, rows-in-page, pages} view; one box per K-half
@@ -529,9 +552,9 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
               bytes += kScaleBoxBig * 4;
             }
           } else if (cur.nr[0] > 0)
-            bytes = issue_rows(a, sc, &full[stage], &tm_rows128, &tm_rows32, &tm_scale128, &tm_scale32, cur.r0[0],
+            bytes = issue_rows(a, sc, &full[stage], &tm_rows128, &tm_small, &tm_scale128, &tm_scale32, cur.r0[0],
                                cur.nr[0], 0, use_scale);
-          sMis[stage * 4] = static_cast<int>(cur.r0[0] & 3);
+          sMis[me * 4] = static_cast<int>(cur.r0[0] & 3);
           mbar_arrive_expect_tx(&full[stage], bytes);
           cur = nxt;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -569,6 +592,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         for (int t = 0; t < ntiles; ++t) {
           mbar_wait(&tempty[acc], accphase ^ 1);
           mbar_wait(&full[stage], phase);
+          if constexpr (PACKED) mbar_arrive(&tfull[acc]);   // releases what this thread acquired: the tile's side data
           tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(sA + stage * kTileBytes);
           const uint32_t d_addr = tmem_base + acc * N;
@@ -730,7 +754,9 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           qv_g = g;
         }
         float* const scores_g = p.scores + g * p.n_items;
-        const uint32_t stage = static_cast<uint32_t>(seq % STAGES), phase = static_cast<uint32_t>((seq / STAGES) & 1);
+        // side data of this tile: ring entry `me` (written by the producer / TMA, acquired through tfull); the row stage
+        // itself is never touched here
+        const int me = static_cast<int>(seq % META);
         const uint32_t acc = static_cast<uint32_t>(seq % ACC), accphase = static_cast<uint32_t>((seq / ACC) & 1);
         const uint32_t ta = lane_addr + acc * N + col0;
         if constexpr (MULTI && QS == 1) {
@@ -744,10 +770,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             mbar_wait(&tfull[acc], accphase);
             tc_fence_after_sync();
             float scale = 1.0f;
-            if (use_scale) {
-              mbar_wait(&full[stage], phase);
-              scale = sScale[stage * kScaleStride + trow + (sMis[stage * 4] & 3)];
-            }
+            if (use_scale) scale = sScale[me * kScaleStride + trow + (sMis[me * 4] & 3)];
             float v[32];
             uint32_t pass = 0u;
             const float4* thr4 = reinterpret_cast<const float4*>(sThr + col0);   // +inf for absent queries
@@ -771,10 +794,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             }
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) {
-              mbar_arrive(&tempty[acc]);
-              mbar_arrive(&empty[stage]);
-            }
+            if (lane == 0) mbar_arrive(&tempty[acc]);
             if (page >= p.n_pages) pass = 0u;
             unsigned any = __reduce_or_sync(0xffffffffu, pass);
             while (any) {   // warp-uniform
@@ -807,17 +827,16 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             }
             mbar_wait(&tfull[acc], accphase);
             tc_fence_after_sync();
-            mbar_wait(&full[stage], phase);   // acquire the producer's per-slot metadata and the scale rows
-            if (p.slot_mode) nr = item_ok ? (sMis[stage * 4 + slot] >> 2) : 0;   // slot == 32-row slot here (SR == 32)
+            if (p.slot_mode) nr = item_ok ? (sMis[me * 4 + slot] >> 2) : 0;   // slot == 32-row slot here (SR == 32)
             float scale = 1.0f;
             if (use_scale) {
               if (p.pad_rows > 0) {
                 // padded slots: the scale rows are the tile's real rows back to back (slot j starts at j * fixed_rows)
-                scale = rin < nr ? sScale[stage * kScaleStride + slot * p.pad_rows + rin + (sMis[stage * 4] & 3)] : 0.0f;
+                scale = rin < nr ? sScale[me * kScaleStride + slot * p.pad_rows + rin + (sMis[me * 4] & 3)] : 0.0f;
               } else {
                 const int sslot = trow / p.slot_rows;
-                scale = sScale[stage * kScaleStride + sslot * (p.slot_rows + 32) + (trow - sslot * p.slot_rows) +
-                               (sMis[stage * 4 + sslot] & 3)];
+                scale = sScale[me * kScaleStride + sslot * (p.slot_rows + 32) + (trow - sslot * p.slot_rows) +
+                               (sMis[me * 4 + sslot] & 3)];
               }
             }
             float v[QE];
@@ -855,10 +874,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             }
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) {
-              mbar_arrive(&tempty[acc]);
-              mbar_arrive(&empty[stage]);
-            }
+            if (lane == 0) mbar_arrive(&tempty[acc]);
             if constexpr (MULTI && QS == 1) {
               // 32 single-column queries: after the segmented butterfly lane rin of a slot holds the column maxima
               // of columns col0 + rin*cf .. +cf (cf = 32 / SR)
@@ -948,10 +964,9 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         tc_fence_after_sync();
         float scale = 1.0f;
         if (use_scale) {
-          mbar_wait(&full[stage], phase);
           const int slot = trow / p.slot_rows;
-          scale = sScale[stage * kScaleStride + slot * (p.slot_rows + 32) + (trow - slot * p.slot_rows) +
-                         (sMis[stage * 4 + slot] & 3)];
+          scale = sScale[me * kScaleStride + slot * (p.slot_rows + 32) + (trow - slot * p.slot_rows) +
+                         (sMis[me * 4 + slot] & 3)];
         }
 #pragma unroll
         for (int c = 0; c < QE; c += 8) {
@@ -966,10 +981,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         }
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&tempty[acc]);
-          mbar_arrive(&empty[stage]);
-        }
+        if (lane == 0) mbar_arrive(&tempty[acc]);
         named_bar_sync(bar_id, 128);
         // 3. segmented max: a group of QW lanes handles one segment; lane -> q (+32 per extra query group);
         //    rows are read 4 at a time (16-byte aligned, conflict-free at pitch 132)

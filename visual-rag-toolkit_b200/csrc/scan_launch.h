@@ -7,7 +7,7 @@ namespace vrag {
 
 struct ScanLaunch {
   const CUtensorMap* tm_rows;     // 128-row boxes (or the padded 3-D view when p.pad_rows > 0)
-  const CUtensorMap* tm_rows32;
+  const RowMaps* tm_small;        // boxes of 4, 8, ..., 32 rows
   const CUtensorMap* tm_scale128;
   const CUtensorMap* tm_scale32;
   ScanParams p;

@@ -11,7 +11,13 @@ constexpr int kDim = 128;            // embedding dim (qdrant_indexer.py:133)
 constexpr int kTileRows = 128;       // UMMA M
 constexpr int kTileBytes = kTileRows * kDim * 2;  // 32 KB of fp16 per stage
 constexpr int kHalfBytes = kTileBytes / 2;        // one K-half (64 fp16 = 128 B per row)
-constexpr int kBoxRowsSmall = 32;    // partial tiles are fetched in 32-row boxes
+constexpr int kBoxRowsSmall = 32;    // partial tiles are fetched in boxes of at most 32 rows
+constexpr int kBoxStep = 4;          // ... sized to the rows that are really needed, in steps of 4 rows: a gathered page of
+constexpr int kNumSmallMaps = kBoxRowsSmall / kBoxStep;   // 24 rows is fetched as ONE 24-row box, not as a 32-row box
+// Tensor maps {64 cols, 4*(i+1) rows} over the same rows, i = 0..7 (box size is a property of the map).
+struct RowMaps {
+  CUtensorMap m[kNumSmallMaps];
+};
 // threads: warp0 TMA, warp1 MMA, then 4 epilogue warps per epilogue group (ScanCfg::threads)
 // inv_norm rows travel by 1-D TMA whose global start must be 16-byte aligned: fetch from (row & ~3) with a
 // box 4 floats longer and let the epilogue index with the misalignment (row & 3).

@@ -138,7 +138,8 @@ struct Store {
   int64_t cap_rows = 0;          // allocated rows (>= total_rows; vrag_store_append grows geometrically)
   bool dirty = false;            // appended to since the page tables / tensor maps were last built
   bool packed = false;
-  CUtensorMap tm128, tm32, ts128, ts32;
+  CUtensorMap tm128, ts128, ts32;
+  RowMaps tm_small;              // row boxes of 4, 8, ..., 32 rows
   CUtensorMap tm3d;              // fixed_rows <= 32, not a power of two: {128, fixed_rows, n_pages} view with a padded box
   int pad_slot = 0;              // its slot height (next power of two), 0 when the view does not exist
   // Page-table indirection (upserts that change a page's row count, deletes): page p owns rows [h_begin[p], h_end[p])
@@ -469,7 +470,7 @@ static int finish_store(vrag_corpus* c, Store& s, const int64_t* page_offsets, i
   }
   if (s.total_rows > 0) {
     TRY(make_rows_map(&s.tm128, s.rows, s.total_rows, kTileRows));
-    TRY(make_rows_map(&s.tm32, s.rows, s.total_rows, kBoxRowsSmall));
+    for (int i = 0; i < kNumSmallMaps; ++i) TRY(make_rows_map(&s.tm_small.m[i], s.rows, s.total_rows, kBoxStep * (i + 1)));
     TRY(make_scale_map(&s.ts128, s.inv, s.total_rows, kScaleBoxBig));
     TRY(make_scale_map(&s.ts32, s.inv, s.total_rows, kScaleBoxSmall));
   }
@@ -948,7 +949,7 @@ static int launch_scan_variant(vrag_corpus* c, const Store& s, const ScanParams&
                                int kind, int qp_or_qs) {
   ScanLaunch L;
   L.tm_rows = p.pad_rows > 0 ? &s.tm3d : &s.tm128;
-  L.tm_rows32 = &s.tm32;
+  L.tm_small = &s.tm_small;
   L.tm_scale128 = &s.ts128;
   L.tm_scale32 = &s.ts32;
   L.p = p;
