@@ -48,7 +48,13 @@ struct ScanCfg {
   static constexpr int MISC_BYTES = 8192;                  // barriers, reduce scratch, segment tables
   // multi (sub-query kernels, QP == 128): four epilogue groups, each owning 32 accumulator columns
   static constexpr int epi_groups(bool packed, bool multi = false) { return multi ? 4 : (packed ? EPI_GROUPS_PACKED : 1); }
-  static constexpr int threads(bool packed, bool multi = false) { return 64 + 128 * epi_groups(packed, multi); }
+  // PACKED operand-switching kernels (every query of a batch gathers its own candidate pages): a second producer warp
+  // (the two alternate tiles: ~300 instructions per tile in ONE warp were the bound of the small-page gather, not HBM)
+  // and a warp whose only job is to stream the query operand images (it needs no tile bookkeeping at all)
+  static constexpr int extra_warps(bool packed, bool bsw) { return (packed && bsw) ? 2 : 0; }
+  static constexpr int threads(bool packed, bool multi = false, bool bsw = false) {
+    return 64 + 128 * epi_groups(packed, multi) + 32 * extra_warps(packed, bsw);
+  }
   static constexpr int sc_bytes(bool packed, bool multi = false) {
     return packed ? (multi ? 4 * 32 : EPI_GROUPS_PACKED * QP) * SC_PITCH * 4 : 0;
   }
@@ -121,6 +127,25 @@ __device__ __forceinline__ UnitRange unit_range(const ScanParams& p, long long u
   }
   return r;
 }
+
+// Walks the units of a UnitRange without a 64-bit division per unit (the per-tile instruction streams of the producer,
+// the MMA thread and the epilogue warps are what bounds gathers of small pages): seek() divides once, advance() adds.
+struct UnitIter {
+  int g;
+  long long u;
+  __device__ __forceinline__ void seek(const UnitRange& r, long long i) { r.decode(i, g, u); }
+  __device__ __forceinline__ void advance(const UnitRange& r, long long n) {
+    if (r.per_group == 0) {
+      u += n * r.step;
+    } else {
+      u += n;   // step == 1 in the multi-group layout
+      while (u >= r.per_group) {
+        u -= r.per_group;
+        ++g;
+      }
+    }
+  }
+};
 
 // Row ranges one PACKED tile fetches: dense layouts -> one contiguous range; slot mode -> up to 4 items.
 struct PackedTileMeta {
@@ -297,7 +322,7 @@ __device__ __forceinline__ float slot_maxsim(float* v, int lane, int q_valid) {
 // QS: columns per query inside the operand image. QS == QP: one query per image (single-query scans and BSW
 // candidate scans). QS < QP (dense batched scans): QP/QS queries share every document tile.
 template <int QP, int QS, bool PACKED, bool BSW>
-__global__ void __launch_bounds__(ScanCfg<QP>::threads(PACKED, QS < QP), 1)
+__global__ void __launch_bounds__(ScanCfg<QP>::threads(PACKED, QS < QP, BSW), 1)
 maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_constant__ RowMaps tm_small,
                    const __grid_constant__ CUtensorMap tm_scale128, const __grid_constant__ CUtensorMap tm_scale32,
                    const ScanParams p) {
@@ -307,7 +332,10 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   constexpr bool MULTI = QS < QP;
   constexpr int STAGES = Cfg::stages(PACKED, BSW, MULTI);
   constexpr int NB = BSW ? 2 : 1;              // query operand buffers
-  constexpr int NTHREADS = Cfg::threads(PACKED, MULTI);
+  constexpr int NTHREADS = Cfg::threads(PACKED, MULTI, BSW);
+  constexpr int PRODUCERS = Cfg::extra_warps(PACKED, BSW) ? 2 : 1;   // producer warps (slot-mode tiles alternate between them)
+  constexpr int WARP_PROD_B = 2 + 4 * Cfg::epi_groups(PACKED, MULTI);  // second producer warp / operand loader warp
+  constexpr int WARP_OPERANDS = WARP_PROD_B + 1;                       //   (exist only when PRODUCERS == 2)
   constexpr int EPI_GROUPS = Cfg::epi_groups(PACKED, MULTI);
   constexpr int QE = MULTI ? 32 : QP;          // accumulator columns one epilogue group handles
   constexpr int QR = QE <= 8 ? 8 : QE <= 16 ? 16 : QE <= 32 ? 32 : QE;   // QE padded to a power of two (reductions)
@@ -413,13 +441,36 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   // Work units of this CTA (LARGE: items, PACKED: tiles)
   const UnitRange ur = unit_range(p, PACKED ? p.n_tiles : p.n_items);
 
-  if (warp == 0) {
-    // ===================================================================== TMA producer
+  const bool is_prod_b = PRODUCERS == 2 && warp == WARP_PROD_B;
+  if (PRODUCERS == 2 && warp == WARP_OPERANDS) {
+    // ===================================================================== operand loader (PACKED + BSW)
+    // The CTA's units are a contiguous range of the group-major unit space, so it visits query groups g_first..g_last in
+    // order: stream their operand images into the two buffers, each as soon as the MMAs of the group that used the buffer
+    // before have retired. No tile bookkeeping, and the tile producers never wait for an operand switch.
+    if constexpr (BSW) {
+      if (lane == 0 && ur.count > 0) {
+        int g_first, g_last;
+        long long u;
+        ur.decode(0, g_first, u);
+        ur.decode(ur.count - 1, g_last, u);
+        int n_sw = -1;
+        for (int g = g_first; g <= g_last; ++g) {
+          ++n_sw;
+          const int slot = n_sw & 1;
+          if (n_sw >= 2) mbar_wait(&bempty[slot], ((n_sw >> 1) - 1) & 1);
+          bulk_load(sB + slot * Cfg::B_BYTES, p.qimg + g * p.qimg_stride, Cfg::B_BYTES, &bfull[slot]);
+          mbar_arrive_expect_tx(&bfull[slot], Cfg::B_BYTES);
+        }
+      }
+    }
+  } else if (warp == 0 || is_prod_b) {
+    // ===================================================================== TMA producer(s)
     uint32_t stage = 0, phase = 0;
     int cur_g = -1, n_sw = -1;
-    // BSW: entering query group g -> fill the other operand buffer once its previous MMAs retired (lane 0 only)
+    // BSW with a single producer (LARGE pages): entering query group g -> fill the other operand buffer once its previous
+    // MMAs retired (lane 0 only). With two producers the operand loader warp above does this.
     auto switch_group = [&](int g) {
-      if constexpr (BSW) {
+      if constexpr (BSW && PRODUCERS == 1) {
         if (g != cur_g) {
           ++n_sw;
           const int slot = n_sw & 1;
@@ -430,6 +481,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         }
       }
     };
+    (void)cur_g; (void)n_sw;
     bool slot_path = false;
     if constexpr (PACKED) slot_path = p.slot_mode != 0;
     if (slot_path) {
@@ -439,8 +491,12 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         // ahead of the tiles being issued, so the chain is off the TMA issue path.
         const int per_tile = kTileRows / p.slot_rows;          // 4, 2 or 1 items per tile
         const int tiles_per_batch = 32 / per_tile;
-        auto resolve_batch = [&](long long i0, long long& r0, int& nr) {
-          const long long i = i0 + lane / per_tile;
+        // Producer warp pw takes the tiles pw, pw + PRODUCERS, ... of the CTA's range ("own" tiles, counted by k); tile i
+        // uses stage i % STAGES whoever issues it, so the MMA thread still consumes the stages in order.
+        const int pw = is_prod_b ? 1 : 0;
+        const long long n_own = ur.count > pw ? (ur.count - pw + PRODUCERS - 1) / PRODUCERS : 0;
+        auto resolve_batch = [&](long long k0, long long& r0, int& nr) {
+          const long long i = pw + PRODUCERS * (k0 + lane / per_tile);
           r0 = 0;
           nr = 0;
           if (i < ur.count) {
@@ -453,11 +509,16 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         };
         long long cur_r0, nxt_r0;
         int cur_nr, nxt_nr;
+        UnitIter it;                       // lane 0: (group, unit) of the tile being issued (single producer + BSW only)
+        it.seek(ur, pw);
         resolve_batch(0, cur_r0, cur_nr);
-        for (long long i0 = 0; i0 < ur.count; i0 += tiles_per_batch) {
-          resolve_batch(i0 + tiles_per_batch, nxt_r0, nxt_nr);
+        for (long long k0 = 0; k0 < n_own; k0 += tiles_per_batch) {
+          resolve_batch(k0 + tiles_per_batch, nxt_r0, nxt_nr);
           for (int t = 0; t < tiles_per_batch; ++t) {
-            if (i0 + t >= ur.count) break;   // warp-uniform
+            if (k0 + t >= n_own) break;   // warp-uniform
+            const long long i = pw + PRODUCERS * (k0 + t);        // tile index in the CTA's range
+            stage = static_cast<uint32_t>(i % STAGES);
+            phase = static_cast<uint32_t>((i / STAGES) & 1);
             // lane j (< per_tile) owns item j of this tile and issues its TMA boxes itself: the copies of the (up to 4)
             // items are issued in parallel instead of one thread serialising 12 bulk-tensor instructions per tile
             const int src = (t * per_tile + lane) & 31;
@@ -465,17 +526,17 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             int my_nr = __shfl_sync(0xffffffffu, cur_nr, src);
             if (lane >= per_tile) my_nr = 0, my_r0 = 0;
             if (lane == 0) {
-              int g;
-              long long u;
-              ur.decode(i0 + t, g, u);
-              switch_group(g);
+              if constexpr (BSW && PRODUCERS == 1) {
+                switch_group(it.g);
+                it.advance(ur, 1);
+              }
               mbar_wait(&empty[stage], phase ^ 1);
             }
             __syncwarp();
             uint32_t bytes = 0;
             if (lane < 4) {
               uint8_t* a = sA + stage * kTileBytes;
-              const int me = static_cast<int>((i0 + t) % META);          // side-data ring entry of this tile
+              const int me = static_cast<int>(i % META);          // side-data ring entry of this tile
               float* sc = sScale + me * kScaleStride;
               if (my_nr > 0)
                 bytes = issue_rows(a, sc + lane * (p.slot_rows + 32), &full[stage], &tm_rows128, &tm_small, &tm_scale128,
@@ -487,13 +548,12 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             bytes += __shfl_xor_sync(0xffffffffu, bytes, 2);
             __syncwarp();   // the other lanes' sMis stores are ordered before lane 0's (releasing) arrive
             if (lane == 0) mbar_arrive_expect_tx(&full[stage], bytes);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           cur_r0 = nxt_r0;
           cur_nr = nxt_nr;
         }
       }
-    } else if (lane == 0) {
+    } else if (lane == 0 && !is_prod_b) {
       PackedTileMeta cur, nxt;
       cur.cnt = nxt.cnt = 0;
       long long row0 = 0, row0_n = 0;
@@ -568,10 +628,11 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
       uint32_t b_addr = smem_u32(sB);
       uint32_t stage = 0, phase = 0, acc = 0, accphase = 0;
       int cur_g = -1, n_sw = -1;
-      for (long long i = 0; i < ur.count; ++i) {
-        int g;
-        long long u;
-        ur.decode(i, g, u);
+      UnitIter it;
+      it.seek(ur, 0);
+      for (long long i = 0; i < ur.count; ++i, it.advance(ur, 1)) {
+        const int g = it.g;
+        const long long u = it.u;
         if constexpr (BSW) {
           if (g != cur_g) {
             if (n_sw >= 0) umma_commit(&bempty[n_sw & 1]);   // previous group's operand buffer is free once its MMAs retire
@@ -596,12 +657,14 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(sA + stage * kTileBytes);
           const uint32_t d_addr = tmem_base + acc * N;
+          // one descriptor per operand and tile; the eight K-steps only move the start-address field (16-byte units)
+          const uint64_t ad0 = umma_desc_k_sw128(a_addr), bd0 = umma_desc_k_sw128(b_addr);
 #pragma unroll
           for (int kh = 0; kh < 2; ++kh) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t ad = umma_desc_k_sw128(a_addr + kh * kHalfBytes + kk * 32);
-              const uint64_t bd = umma_desc_k_sw128(b_addr + kh * (N * 128) + kk * 32);
+              const uint64_t ad = ad0 + static_cast<uint64_t>((kh * kHalfBytes + kk * 32) >> 4);
+              const uint64_t bd = bd0 + static_cast<uint64_t>((kh * (N * 128) + kk * 32) >> 4);
               umma_f16_ss(d_addr, ad, bd, idesc, (kh | kk) != 0);
             }
           }
@@ -633,10 +696,11 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
     if constexpr (!PACKED) {
       uint32_t stage = 0, phase = 0, acc = 0, accphase = 0, par = 0;
       int q_valid = 0, qv_g = -1;
-      for (long long i = 0; i < ur.count; ++i) {
-        int g;
-        long long u;
-        ur.decode(i, g, u);
+      UnitIter it;
+      it.seek(ur, 0);
+      for (long long i = 0; i < ur.count; ++i, it.advance(ur, 1)) {
+        const int g = it.g;
+        const long long u = it.u;
         // per-group query width: a global load, so it is refreshed only when the group changes (never on the tile path)
         if (g != qv_g) {
           if constexpr (MULTI) q_valid = (QS == 32 && grp < p.n_sub) ? __ldg(p.q_valid_arr + grp) : 0;
@@ -743,10 +807,11 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
       const bool row_fast = MULTI && QS == 1 && p.f_thr != nullptr && p.shfl_rows == 1 && !p.slot_mode && p.pad_rows == 0 &&
                             p.tile_stride == 1 && p.fixed_rows == 1;
       (void)row_fast;
-      for (long long seq = seq0; seq < ur.count; seq += seq_step) {
-        int g;
-        long long u;
-        ur.decode(seq, g, u);
+      UnitIter it;
+      it.seek(ur, seq0);
+      for (long long seq = seq0; seq < ur.count; seq += seq_step, it.advance(ur, seq_step)) {
+        const int g = it.g;
+        const long long u = it.u;
         // per-group query width: a global load, so it is refreshed only when the group changes (never on the tile path)
         if (g != qv_g) {
           if constexpr (MULTI) q_valid = (QS == 32 && grp < p.n_sub) ? __ldg(p.q_valid_arr + grp) : 0;

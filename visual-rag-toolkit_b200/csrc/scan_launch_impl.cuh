@@ -29,7 +29,7 @@ static cudaError_t scan_launch_t(const ScanLaunch& L) {
     if (e != cudaSuccess) return e;
   }
   const unsigned grid = static_cast<unsigned>(std::min<long long>(L.num_sms, L.n_units));
-  kern<<<grid, ScanCfg<QP>::threads(PACKED, QS < QP), smem, L.stream>>>(*L.tm_rows, *L.tm_small, *L.tm_scale128,
+  kern<<<grid, ScanCfg<QP>::threads(PACKED, QS < QP, BSW), smem, L.stream>>>(*L.tm_rows, *L.tm_small, *L.tm_scale128,
                                                                        *L.tm_scale32, L.p);
   return cudaGetLastError();
 }
