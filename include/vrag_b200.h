@@ -136,6 +136,21 @@ int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char* const* na
                            const int64_t* cand_ids, int64_t n_cand, float* out_scores, int64_t* out_ids,
                            int* out_counts);
 
+/* ------------------------------------------------------------------ payload filters in the scan
+ * A filter is a bitmask over the shard's pages (bit p of word p/32 set = page p passes), built by the host from the payload
+ * conditions of TwoStageRetriever.build_filter (two_stage.py:436-480) or the per_dataset scope filter of the benchmark
+ * (run_qdrant_beir.py:1987-1997), uploaded once and reused by every query that carries the same filter. A page that does not
+ * pass is treated as an empty page INSIDE the scan: over full-token stores none of its tiles is fetched or multiplied (a
+ * 50 %-selective filter halves the scan), over pooled stores its score is masked in the epilogue; either way it scores
+ * -inf and is never returned. vrag_search_multistage_filtered is vrag_search_multistage with the mask on stage 0 (later
+ * stages only see stage 0's survivors); collective on a sharded handle (every rank passes the mask of its own pages).
+ * For very selective filters (a few thousand pages) the candidate-list form (cand_ids) reads less.                       */
+int vrag_filter_create(vrag_corpus_t* c, const uint32_t* bits, int64_t n_pages, int* out_filter);
+int vrag_filter_destroy(vrag_corpus_t* c, int filter);
+int vrag_search_multistage_filtered(vrag_corpus_t* c, int filter, int n_stages, const char* const* names,
+                                    const uint32_t* flags, const int* ks, const float* query, int n_query_rows,
+                                    const int* q_offsets, float* out_scores, int64_t* out_ids, int* out_counts);
+
 /* ------------------------------------------------------------------ scoring: batched queries
  * n_queries independent multi-stage searches in one call and one host synchronisation (the evaluation loop of
  * benchmarks/vidore_beir_qdrant/run_qdrant_beir.py:378-402 issues them one by one; BASELINE configs[2] batches 256).

@@ -1232,3 +1232,103 @@ def test_filtered_searches_rank_like_the_oracle_on_the_filtered_set(retrieval_go
     with pytest.raises(NotImplementedError):
         single.search(q, top_k=3, filter_obj=M.Filter(must=[M.FieldCondition(key="year")]))
     own.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["large", "large_var", "pooled32", "fixed13", "ragged_small", "global1"])
+def test_page_bitmask_filter_in_the_scan_equals_candidate_list_and_oracle(corpus, layout):
+    """vrag_filter_create + vrag_search_multistage_filtered: the in-scan page bitmask gives exactly the lists of the
+    candidate-list form of the same filter (and of the oracle restricted to the pages that pass), for every store layout;
+    multi-stage: filtered-out pages never re-enter through a later stage, even when fewer pages pass than a stage keeps."""
+    rng = np.random.default_rng({"large": 1, "large_var": 2, "pooled32": 3, "fixed13": 4, "ragged_small": 5, "global1": 6}[layout])
+    n = 3000
+    if layout == "large":
+        lens = np.full((n,), 200)
+    elif layout == "large_var":
+        lens = rng.integers(129, 300, size=n)
+    elif layout == "pooled32":
+        lens = np.full((n,), 32)
+    elif layout == "fixed13":
+        lens = np.full((n,), 13)
+    elif layout == "ragged_small":
+        lens = rng.integers(1, 33, size=n)
+    else:
+        lens = np.full((n,), 1)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    rows = rows16(900 + len(layout), int(off[-1]))
+    fixed = int(lens[0]) if len(set(lens.tolist())) == 1 else 0
+    if fixed:
+        corpus.add_store("fm", rows, fixed_rows=fixed)
+    else:
+        corpus.add_store("fm", rows, page_offsets=off)
+    corpus.add_synthetic_store("fm_pool", n, fixed_rows=8, seed=77)
+    q = CS.query_rows(901, 18)
+    for frac in (0.5, 0.05, 0.9):
+        allowed = rng.random(n) < frac
+        allowed[:3] = [True, False, True]
+        fid = corpus.create_filter(allowed)
+        ids_allowed = np.nonzero(allowed)[0]
+        for pool in (False, True):
+            s_m, i_m = corpus.search("fm", q, 40, pool_query=pool, filter_id=fid)
+            s_c, i_c = corpus.search("fm", q, 40, pool_query=pool, candidate_ids=ids_allowed)
+            keep = np.isfinite(s_m)
+            assert i_m[keep].tolist() == i_c.tolist()[:int(keep.sum())] and np.array_equal(s_m[keep], s_c[:int(keep.sum())])
+            assert allowed[i_m[keep]].all() and keep.sum() == min(40, len(ids_allowed))
+        sub = [rows[off[i]:off[i + 1]].astype(np.float32) for i in ids_allowed]
+        want = MO.search_exhaustive(q, sub, 10)
+        s_m, i_m = corpus.search("fm", q, 10, filter_id=fid)
+        _same_ranking(i_m, s_m, [(int(ids_allowed[i]), x) for i, x in want])
+        # two-stage under the mask == two-stage over the candidate list
+        st_m = corpus.search_multistage([("fm_pool", False, 64), ("fm", False, 10)], q, filter_id=fid)
+        st_c = corpus.search_multistage([("fm_pool", False, 64), ("fm", False, 10)], q, candidate_ids=ids_allowed)
+        assert st_m[1][1].tolist() == st_c[1][1].tolist() and np.array_equal(st_m[1][0], st_c[1][0])
+        corpus.destroy_filter(fid)
+    # fewer pages pass than the stages keep: the padded (filtered-out) pages stay out of the later stage
+    few = np.zeros(n, dtype=bool)
+    few[[5, 17, 1234]] = True
+    fid = corpus.create_filter(few)
+    st = corpus.search_multistage([("fm_pool", False, 64), ("fm", False, 10)], q, filter_id=fid)
+    fin = np.isfinite(st[1][0])
+    assert sorted(st[1][1][fin].tolist()) == [5, 17, 1234]
+    corpus.destroy_filter(fid)
+    from visual_rag_b200._native import VragError
+    with pytest.raises(VragError, match="unknown filter"):
+        corpus.search("fm", q, 5, filter_id=fid)
+    corpus.drop_store("fm")
+    corpus.drop_store("fm_pool")
+
+
+@pytest.mark.gpu
+def test_client_picks_bitmask_or_candidate_list_by_selectivity():
+    """GpuCorpusClient: a payload filter that lets many pages through runs as a device bitmask (created once, reused), a
+    selective one as a candidate list; rankings equal the oracle on the filtered set either way."""
+    from visual_rag_b200.client import GpuCorpusClient
+    from visual_rag_b200.corpus import GpuCorpus
+    from visual_rag_b200.retrieval import SingleStageRetriever, TwoStageRetriever
+
+    n, t = 20000, 12
+    rows = rows16(31337, n * t)
+    q = CS.query_rows(31338, 9)
+    with GpuCorpus(0) as c:
+        c.add_store("initial", rows, fixed_rows=t)
+        client = GpuCorpusClient(c, "c", payloads=[{"year": 2000 + i % 2, "bucket": i % 100} for i in range(n)])
+        single, two = SingleStageRetriever(client, "c"), TwoStageRetriever(client, "c")
+        docs = rows.astype(np.float32).reshape(n, t, 128)
+        for f, pred, expect_mask in ((two.build_filter(year=2001), lambda i: i % 2 == 1, True),
+                                     (Filter_bucket(7), lambda i: i % 100 == 7, False)):
+            keep = [i for i in range(n) if pred(i)]
+            want = MO.search_exhaustive(q, [docs[i] for i in keep], 10)
+            calls = []
+            orig = c.create_filter
+            c.create_filter = lambda m: (calls.append(1), orig(m))[1]
+            for _ in range(3):
+                got = single.search(q, top_k=10, strategy="multi_vector", filter_obj=f)
+                _same_ranking([g["id"] for g in got], [g["score"] for g in got], [(keep[i], x) for i, x in want])
+            c.create_filter = orig
+            assert len(calls) == (1 if expect_mask else 0)      # one upload for three queries / none for the selective filter
+
+
+def Filter_bucket(b):
+    from visual_rag_b200.retrieval import models as M
+
+    return M.Filter(must=[M.FieldCondition(key="bucket", match=M.MatchValue(value=b))])

@@ -79,8 +79,11 @@ struct ScanCfg {
 };
 
 // Resolve work item -> (first row, row count). Returns false when the item is not a page of this shard.
+__device__ __forceinline__ bool page_allowed(const ScanParams& p, long long page) {
+  return p.mask == nullptr || ((__ldg(p.mask + (page >> 5)) >> (page & 31)) & 1u) != 0u;
+}
 __device__ __forceinline__ bool resolve_page(const ScanParams& p, long long page, long long& row0, int& nrows) {
-  if (page < 0 || page >= p.n_pages) {
+  if (page < 0 || page >= p.n_pages || !page_allowed(p, page)) {   // outside the shard, or filtered out: an empty page
     row0 = 0;
     nrows = 0;
     return false;
@@ -199,9 +202,9 @@ __device__ __forceinline__ void packed_segment(const ScanParams& p, int g, long 
       if (p.fixed_rows > 0) rbase = pg0 * p.fixed_rows;
       else rbase = __ldg(p.tile_row0 + u);
       (void)tmp;
-      resolve_page(p, pg0 + et, r0, nr);
+      const bool live = resolve_page(p, pg0 + et, r0, nr);
       item = static_cast<int>(pg0 + et);   // dense: item == page (n_items == n_pages < 2^31 per shard)
-      rb = static_cast<int>(r0 - rbase);
+      rb = live ? static_cast<int>(r0 - rbase) : 0;   // filtered-out page: an empty segment (-inf)
       re = rb + nr;
     }
   } else {
@@ -493,9 +496,11 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         const int tiles_per_batch = 32 / per_tile;
         // Producer warp pw takes the tiles pw, pw + PRODUCERS, ... of the CTA's range ("own" tiles, counted by k); tile i
         // uses stage i % STAGES whoever issues it, so the MMA thread still consumes the stages in order.
+        // (a CTA's share of the tiles fits 32 bits: the per-tile index arithmetic below is on the single-warp critical path)
         const int pw = is_prod_b ? 1 : 0;
-        const long long n_own = ur.count > pw ? (ur.count - pw + PRODUCERS - 1) / PRODUCERS : 0;
-        auto resolve_batch = [&](long long k0, long long& r0, int& nr) {
+        const uint32_t n_tiles_cta = static_cast<uint32_t>(ur.count);
+        const uint32_t n_own = n_tiles_cta > static_cast<uint32_t>(pw) ? (n_tiles_cta - pw + PRODUCERS - 1) / PRODUCERS : 0u;
+        auto resolve_batch = [&](uint32_t k0, long long& r0, int& nr) {
           const long long i = pw + PRODUCERS * (k0 + lane / per_tile);
           r0 = 0;
           nr = 0;
@@ -512,13 +517,13 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         UnitIter it;                       // lane 0: (group, unit) of the tile being issued (single producer + BSW only)
         it.seek(ur, pw);
         resolve_batch(0, cur_r0, cur_nr);
-        for (long long k0 = 0; k0 < n_own; k0 += tiles_per_batch) {
+        for (uint32_t k0 = 0; k0 < n_own; k0 += tiles_per_batch) {
           resolve_batch(k0 + tiles_per_batch, nxt_r0, nxt_nr);
           for (int t = 0; t < tiles_per_batch; ++t) {
             if (k0 + t >= n_own) break;   // warp-uniform
-            const long long i = pw + PRODUCERS * (k0 + t);        // tile index in the CTA's range
-            stage = static_cast<uint32_t>(i % STAGES);
-            phase = static_cast<uint32_t>((i / STAGES) & 1);
+            const uint32_t i = pw + PRODUCERS * (k0 + t);          // tile index in the CTA's range
+            stage = i % STAGES;
+            phase = (i / STAGES) & 1u;
             // lane j (< per_tile) owns item j of this tile and issues its TMA boxes itself: the copies of the (up to 4)
             // items are issued in parallel instead of one thread serialising 12 bulk-tensor instructions per tile
             const int src = (t * per_tile + lane) & 31;
@@ -538,9 +543,25 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
               uint8_t* a = sA + stage * kTileBytes;
               const int me = static_cast<int>(i % META);          // side-data ring entry of this tile
               float* sc = sScale + me * kScaleStride;
-              if (my_nr > 0)
-                bytes = issue_rows(a, sc + lane * (p.slot_rows + 32), &full[stage], &tm_rows128, &tm_small, &tm_scale128,
-                                   &tm_scale32, my_r0, my_nr, lane * p.slot_rows, use_scale);
+              if (my_nr > 0) {
+                if (p.slot_rows == kBoxRowsSmall) {
+                  // one page per 32-row slot: exactly one row box (sized to the page) per K-half + its scale rows
+                  const int mi = (my_nr + kBoxStep - 1) / kBoxStep - 1;
+                  const CUtensorMap* tm = &tm_small.m[mi];
+                  const int32_t r = static_cast<int32_t>(my_r0);
+                  uint8_t* dst = a + lane * (kBoxRowsSmall * 128);
+                  tma_load_2d(dst, tm, &full[stage], 0, r);
+                  tma_load_2d(dst + kHalfBytes, tm, &full[stage], 64, r);
+                  bytes = (mi + 1) * (kBoxStep * kDim * 2);
+                  if (use_scale) {
+                    tma_load_1d(sc + lane * (kBoxRowsSmall + 32), &tm_scale32, &full[stage], r & ~3);
+                    bytes += kScaleBoxSmall * 4;
+                  }
+                } else {
+                  bytes = issue_rows(a, sc + lane * (p.slot_rows + 32), &full[stage], &tm_rows128, &tm_small, &tm_scale128,
+                                     &tm_scale32, my_r0, my_nr, lane * p.slot_rows, use_scale);
+                }
+              }
               // low 2 bits: scale misalignment; rest: rows of the slot (0 for unused / empty slots)
               sMis[me * 4 + lane] = static_cast<int>(my_r0 & 3) | (my_nr << 2);
             }
@@ -821,8 +842,9 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         float* const scores_g = p.scores + g * p.n_items;
         // side data of this tile: ring entry `me` (written by the producer / TMA, acquired through tfull); the row stage
         // itself is never touched here
-        const int me = static_cast<int>(seq % META);
-        const uint32_t acc = static_cast<uint32_t>(seq % ACC), accphase = static_cast<uint32_t>((seq / ACC) & 1);
+        const uint32_t seq32 = static_cast<uint32_t>(seq);
+        const int me = static_cast<int>(seq32 % META);
+        const uint32_t acc = seq32 % ACC, accphase = (seq32 / ACC) & 1u;
         const uint32_t ta = lane_addr + acc * N + col0;
         if constexpr (MULTI && QS == 1) {
           // ---- one page per tile row (global_pooling) under the top-k prefilter: the dense stage-1 scan of a batch of
@@ -886,7 +908,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             bool item_ok;
             if (!p.slot_mode) {
               item_ok = page < p.n_pages;
-              nr = item_ok ? (p.pad_rows > 0 ? p.pad_rows : SR) : 0;
+              nr = (item_ok && page_allowed(p, page)) ? (p.pad_rows > 0 ? p.pad_rows : SR) : 0;
             } else {
               item_ok = item < p.n_items;
             }

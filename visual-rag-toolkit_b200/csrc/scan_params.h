@@ -31,6 +31,9 @@ constexpr float kLoScale = 2048.0f;  // lo half of the query is stored scaled by
 struct ScanParams {
   const long long* offsets;   // [n_pages+1] row offsets of the store (used when fixed_rows == 0)
   const long long* page_end;  // != nullptr: the store has a page table: page p owns rows [offsets[p], page_end[p])
+  const uint32_t* mask;       // != nullptr: payload-filter bitmask over the shard's pages (bit p set = page p passes the
+                              //   filter): a page that does not pass is treated as an EMPTY page — no tile of it is
+                              //   fetched or multiplied (LARGE pages) and its score is -inf (single-query kernels)
   long long fixed_rows;       // > 0: page p owns rows [p*fixed_rows, (p+1)*fixed_rows)
   long long n_pages;          // pages in this store (this shard)
   const long long* cand;      // nullptr: item i is page i. else: item i is page cand[i] - cand_base

@@ -286,6 +286,9 @@ struct vrag_corpus {
   int64_t launches = 0;
   bool attrs_set = false;
   CommState comm;
+  std::map<int, DevBuf<uint32_t>> filters;   // payload-filter page bitmasks (vrag_filter_create)
+  std::map<int, int64_t> filter_pages;       // pages each mask covers
+  int next_filter = 1;
 };
 
 static const int kOperandRows = 128;    // query rows of one MMA operand image; longer token queries are scored in chunks
@@ -372,6 +375,7 @@ extern "C" int vrag_corpus_destroy(vrag_corpus_t* c) {
   c->d_stage_sc.release();
   c->d_fkeys.release();
   comm_release(c);
+  for (auto& kv : c->filters) kv.second.release();
   if (c->h_flag) cudaFreeHost(c->h_flag);
   if (c->h_qmeta) cudaFreeHost(c->h_qmeta);
   if (c->h_query) cudaFreeHost(c->h_query);
@@ -1026,7 +1030,8 @@ static int fill_neg_inf(vrag_corpus* c, float* d, int64_t n, cudaStream_t st);
 
 // Score a store (or a candidate list) into d_scores[n_items]. All pointers are device pointers.
 static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int n_query_rows, uint32_t flags,
-                       const long long* d_cand, int64_t n_cand, float* d_scores, cudaStream_t st, bool time_kernel) {
+                       const long long* d_cand, int64_t n_cand, float* d_scores, cudaStream_t st, bool time_kernel,
+                       const uint32_t* d_mask = nullptr) {
   const bool pool = (flags & VRAG_Q_POOL) != 0;
   const bool normalize = (flags & VRAG_Q_NORMALIZE) != 0;
   if (n_query_rows < 1) return fail("query has no rows");
@@ -1043,7 +1048,8 @@ static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int
     for (int i = 0; i < n_chunks; ++i) {
       const int rows = (q_eff - r0 + (n_chunks - i) - 1) / (n_chunks - i);
       float* dst = i == 0 ? d_scores : c->d_scores_part.p;
-      TRY(launch_scan(c, s, d_query + static_cast<size_t>(r0) * 128, rows, flags, d_cand, n_cand, dst, st, time_kernel && i == 0));
+      TRY(launch_scan(c, s, d_query + static_cast<size_t>(r0) * 128, rows, flags, d_cand, n_cand, dst, st, time_kernel && i == 0,
+                      d_mask));
       if (i > 0) {
         add_scores_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(d_scores, c->d_scores_part.p, n);
         c->launches++;
@@ -1068,6 +1074,7 @@ static int launch_scan(vrag_corpus* c, const Store& s, const float* d_query, int
   fill_scan_params(c, s, d_cand, n_items, QP, normalize, d_scores, &p, &n_units);
   p.qimg = c->d_qimg.p;
   p.q_valid = q_eff;
+  p.mask = d_mask;
   {  // VRAG_Q_FP16 (or the experiment knob VRAG_QUERY_SPLIT=0): contract only the fp16 hi half of the query
     // (half the tensor work; LARGE pages only — that is where the scan is power/bandwidth bound)
     p.hi_only = (((flags & VRAG_Q_FP16) != 0 || knob_hi_only()) && QP >= 16 && !s.packed) ? 1 : 0;
@@ -1587,7 +1594,7 @@ static int fill_neg_inf(vrag_corpus* c, float* d, int64_t n, cudaStream_t st) {
 static int run_stages(vrag_corpus* c, int n_stages, Store* const* st, const uint32_t* flags, const int* ks,
                       const float* d_query, int n_query_rows, const int* q_offsets, const long long* d_cand, int64_t n_cand,
                       float* d_out_scores, long long* d_out_ids, int* d_counts, int* d_fail, bool allow_sampled,
-                      cudaStream_t stm, bool* timed_out, bool* used_sampled_out) {
+                      cudaStream_t stm, bool* timed_out, bool* used_sampled_out, const uint32_t* d_mask = nullptr) {
   const bool sh = sharded(c);
   const int64_t n_first = d_cand ? n_cand : st[0]->n_pages;
   int64_t max_k = 0;
@@ -1611,7 +1618,9 @@ static int run_stages(vrag_corpus* c, int n_stages, Store* const* st, const uint
         TRY(fill_neg_inf(c, c->d_scores.p, n_items, stm));
       } else if (st[s]->n_pages > 0 || d_prev_ids) {
         // the dominant (timed) kernel is the first scan
-        TRY(launch_scan(c, *st[s], dq, qrows, flags[s], d_prev_ids, n_items, c->d_scores.p, stm, !timed && timed_out));
+        // a payload-filter bitmask applies to every stage: when fewer pages pass than a stage keeps, its list is padded with
+        // filtered-out pages (score -inf), which must stay -inf in the stages behind it
+        TRY(launch_scan(c, *st[s], dq, qrows, flags[s], d_prev_ids, n_items, c->d_scores.p, stm, !timed && timed_out, d_mask));
         timed = true;
       }
     }
@@ -1650,11 +1659,17 @@ static int run_stages(vrag_corpus* c, int n_stages, Store* const* st, const uint
 static int search_multistage_impl(vrag_corpus_t* c, int n_stages, const char* const* names,
                                   const uint32_t* flags, const int* ks, const float* query, int n_query_rows,
                                   const int* q_offsets, const int64_t* cand_ids, int64_t n_cand,
-                                  float* out_scores, int64_t* out_ids, int* out_counts, bool allow_sampled) {
+                                  float* out_scores, int64_t* out_ids, int* out_counts, bool allow_sampled, int filter_id = 0) {
   if (!c) return fail("corpus is NULL");
   if (n_stages < 1 || n_stages > kMaxStages) return fail("n_stages %d out of range [1,%d]", n_stages, kMaxStages);
   if (!names || !flags || !ks || !out_scores || !out_ids || !out_counts) return fail("NULL argument");
   TRY(set_device(c));
+  const uint32_t* d_mask = nullptr;
+  if (filter_id != 0) {
+    auto f = c->filters.find(filter_id);
+    if (f == c->filters.end()) return fail("unknown filter %d", filter_id);
+    d_mask = f->second.p;
+  }
   Store* st[kMaxStages];
   size_t total_k = 0;
   for (int s = 0; s < n_stages; ++s) {
@@ -1669,6 +1684,9 @@ static int search_multistage_impl(vrag_corpus_t* c, int n_stages, const char* co
     }
   }
   if (cand_ids && n_cand < 0) return fail("n_cand < 0");
+  if (d_mask && c->filter_pages[filter_id] != st[0]->n_pages)
+    return fail("filter %d covers %lld pages, store '%s' has %lld", filter_id, (long long)c->filter_pages[filter_id], names[0],
+                (long long)st[0]->n_pages);
   TRY(stage_query(c, query, n_query_rows));
   TRY(c->d_out_scores.ensure(total_k));
   TRY(c->d_out_ids.ensure(total_k));
@@ -1689,7 +1707,7 @@ static int search_multistage_impl(vrag_corpus_t* c, int n_stages, const char* co
   }
   int rc = run_stages(c, n_stages, st, flags, ks, c->d_query.p, n_query_rows, q_offsets, cand_ids ? c->d_cand.p : nullptr,
                       n_cand, c->d_out_scores.p, c->d_out_ids.p, c->d_counts.p, d_fail, allow_sampled, c->stream, &timed,
-                      &used_sampled);
+                      &used_sampled, d_mask);
   c->comm.timing = false;
   if (rc) return rc;
   CUDA_OK(cudaEventRecord(c->ev1, c->stream));
@@ -1703,7 +1721,7 @@ static int search_multistage_impl(vrag_corpus_t* c, int n_stages, const char* co
     // flag travels in the exchanged entries, so every rank takes this branch together — any rank: exact radix-select path
     c->sampled_fallbacks++;
     return search_multistage_impl(c, n_stages, names, flags, ks, query, n_query_rows, q_offsets, cand_ids, n_cand, out_scores,
-                                  out_ids, out_counts, false);
+                                  out_ids, out_counts, false, filter_id);
   }
   memcpy(out_scores, c->h_out_scores, total_k * sizeof(float));
   memcpy(out_ids, c->h_out_ids, total_k * sizeof(long long));
@@ -1797,6 +1815,51 @@ extern "C" int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char
   VRAG_LOCK(c);
   return search_multistage_impl(c, n_stages, names, flags, ks, query, n_query_rows, q_offsets, cand_ids, n_cand, out_scores,
                                 out_ids, out_counts, true);
+}
+
+// ------------------------------------------------------------------------------------------------ payload filters
+extern "C" int vrag_filter_create(vrag_corpus_t* c, const uint32_t* bits, int64_t n_pages, int* out_filter) {
+  VRAG_LOCK(c);
+  if (!out_filter) return fail("out_filter is NULL");
+  if (n_pages < 0 || (n_pages > 0 && !bits)) return fail("bad filter arguments");
+  TRY(set_device(c));
+  const size_t words = static_cast<size_t>((n_pages + 31) / 32);
+  const int id = c->next_filter++;
+  DevBuf<uint32_t>& buf = c->filters[id];
+  int rc = buf.ensure(std::max<size_t>(words, 1));
+  if (rc == 0 && words > 0) {
+    cudaError_t e = cudaMemcpyAsync(buf.p, bits, words * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = fail("filter upload failed: %s", cudaGetErrorString(e));
+  }
+  if (rc) {
+    buf.release();
+    c->filters.erase(id);
+    return rc;
+  }
+  c->filter_pages[id] = n_pages;
+  *out_filter = id;
+  return 0;
+}
+
+extern "C" int vrag_filter_destroy(vrag_corpus_t* c, int filter) {
+  VRAG_LOCK(c);
+  auto f = c->filters.find(filter);
+  if (f == c->filters.end()) return fail("unknown filter %d", filter);
+  TRY(set_device(c));
+  cudaStreamSynchronize(c->stream);
+  f->second.release();
+  c->filters.erase(f);
+  c->filter_pages.erase(filter);
+  return 0;
+}
+
+extern "C" int vrag_search_multistage_filtered(vrag_corpus_t* c, int filter, int n_stages, const char* const* names,
+                                               const uint32_t* flags, const int* ks, const float* query, int n_query_rows,
+                                               const int* q_offsets, float* out_scores, int64_t* out_ids, int* out_counts) {
+  VRAG_LOCK(c);
+  return search_multistage_impl(c, n_stages, names, flags, ks, query, n_query_rows, q_offsets, nullptr, 0, out_scores, out_ids,
+                                out_counts, true, filter);
 }
 
 extern "C" int vrag_search(vrag_corpus_t* c, const char* name, const float* query, int n_query_rows, uint32_t flags,

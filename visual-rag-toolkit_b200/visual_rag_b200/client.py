@@ -122,12 +122,26 @@ class GpuCorpusClient:
         self._payloads = list(payloads) if payloads is not None else None
         self._lock = threading.RLock()
         self._columns: Dict[str, np.ndarray] = {}       # payload key -> per-page value column (built on first use)
-        self._filter_cache: Dict[Any, Any] = {}         # filter signature -> (page mask, candidate page ids)
+        self._filter_cache: Dict[Any, Any] = {}         # filter signature -> {mask, pages, fid (device bitmask, or None)}
+        self._device_masks: List[dict] = []             # cache entries that currently own a device bitmask
+        self._last_mask = None
+        self._mask_entry = None
 
     # ------------------------------------------------------------------ id mapping (pages of THIS corpus handle)
     def _invalidate(self) -> None:
         self._columns = {}
+        self._drop_device_masks()
         self._filter_cache = {}
+
+    def _drop_device_masks(self) -> None:
+        for entry in getattr(self, "_device_masks", []):
+            if entry.get("fid") is not None:
+                try:
+                    self.corpus.destroy_filter(entry["fid"])
+                except Exception:  # noqa: BLE001 - the handle may already be closed
+                    pass
+                entry["fid"] = None
+        self._device_masks = []
 
     @_locked
     def set_points(self, point_ids: Sequence[Any], payloads: Optional[Sequence[Optional[dict]]] = None) -> None:
@@ -214,6 +228,33 @@ class GpuCorpusClient:
         return n_local
 
     # ------------------------------------------------------------------ filters
+    # A payload filter that lets more than this many pages through (and more than 1/64 of the store) runs as a page bitmask
+    # inside the scan (uploaded once per filter); below it the candidate-list gather reads less.
+    MASK_MIN_PAGES = 4096
+
+    def _restriction(self, query_filter, n_pages: int) -> dict:
+        """Filter -> keyword arguments for the corpus search: {} (no restriction), {"candidate_ids": ids} or
+        {"filter_id": id of a device-resident page bitmask}."""
+        if query_filter is None:
+            return {}
+        self._last_mask = None
+        cand = self._candidates(query_filter, n_pages)
+        if cand is None:
+            return {}
+        hit = self._last_mask     # set by _candidates when the result is exactly a cached payload mask (no id restriction)
+        if hit is not None and len(cand) > max(self.MASK_MIN_PAGES, n_pages // 64) and hasattr(self.corpus, "create_filter"):
+            entry = hit
+            if entry.get("fid") is None:
+                if len(self._device_masks) >= 8:           # keep a handful of device masks alive
+                    old = self._device_masks.pop(0)
+                    if old.get("fid") is not None:
+                        self.corpus.destroy_filter(old["fid"])
+                        old["fid"] = None
+                entry["fid"] = self.corpus.create_filter(entry["mask"])
+                self._device_masks.append(entry)
+            return {"filter_id": entry["fid"]}
+        return {"candidate_ids": cand}
+
     def _candidates(self, query_filter, n_pages: int) -> Optional[np.ndarray]:
         """Filter -> ascending global page ids of THIS handle's pages that pass it, or None for 'all pages'.
         `must` is a conjunction, `should` a disjunction (at least one), `must_not` a negated disjunction — Qdrant's
@@ -254,6 +295,7 @@ class GpuCorpusClient:
             return np.asarray(sorted(p for p in allowed if 0 <= p - base < n_pages), dtype=np.int64)
         mask, pages = self._payload_mask(rest_must, should, must_not, n_pages)
         if allowed is None:
+            self._last_mask = self._mask_entry     # the cache entry of this payload mask (may carry a device filter id)
             return pages
         return np.asarray(sorted(p for p in allowed if 0 <= p - base < n_pages and mask[p - base]), dtype=np.int64)
 
@@ -266,7 +308,8 @@ class GpuCorpusClient:
                    tuple(_cond_signature(c) for c in must_not))
             hit = self._filter_cache.get(sig)
             if hit is not None:
-                return hit
+                self._mask_entry = hit
+                return hit["mask"], hit["pages"]
         except TypeError:   # unhashable match values: evaluate without caching
             sig = None
         mask = np.ones((n_pages,), dtype=bool)
@@ -279,12 +322,14 @@ class GpuCorpusClient:
             mask &= any_of
         for cond in must_not:
             mask &= ~self._cond_mask(cond, n_pages)
-        out = (mask, np.nonzero(mask)[0].astype(np.int64) + self.corpus.page_base)
+        entry = {"mask": mask, "pages": np.nonzero(mask)[0].astype(np.int64) + self.corpus.page_base, "fid": None}
+        self._mask_entry = entry
         if sig is not None:
             if len(self._filter_cache) > 64:
+                self._drop_device_masks()
                 self._filter_cache.clear()
-            self._filter_cache[sig] = out
-        return out
+            self._filter_cache[sig] = entry
+        return entry["mask"], entry["pages"]
 
     def _column(self, key: str, n_pages: int) -> np.ndarray:
         col = self._columns.get(key)
@@ -370,7 +415,7 @@ class GpuCorpusClient:
             raise ValueError("`using` (named vector) is required")
         limit = int(limit)
         n_pages = self.corpus.n_pages(using)
-        cand = self._candidates(query_filter, n_pages)
+        restrict = self._restriction(query_filter, n_pages)
         q = self._as_query(query)
         if prefetch:
             # Qdrant prefetch= (two_stage.py:170-176): stage-1 query and rerank query travel separately;
@@ -378,10 +423,10 @@ class GpuCorpusClient:
             pf = prefetch[0] if isinstance(prefetch, (list, tuple)) else prefetch
             stages = self.corpus.search_multistage(
                 [(pf.using, False, int(pf.limit)), (using, False, limit)], None,
-                stage_queries=[self._as_query(pf.query), q], candidate_ids=cand)
+                stage_queries=[self._as_query(pf.query), q], **restrict)
             scores, ids = stages[-1]
         else:
-            scores, ids = self.corpus.search(using, q, limit, candidate_ids=cand)
+            scores, ids = self.corpus.search(using, q, limit, **restrict)
         points = self._points(scores, ids, with_payload)
         if with_vectors:
             names = [using] if with_vectors is True else list(with_vectors)
@@ -396,11 +441,11 @@ class GpuCorpusClient:
                           stage3_using, stage1_k: int, stage2_k: int, top_k: int, query_filter=None):
         """The three ID-restricted scans of ThreeStageRetriever.search_server_side (three_stage.py:102-159)
         fused on the device: returns the three point lists (stage 3 with payloads)."""
-        cand = self._candidates(query_filter, self.corpus.n_pages(stage1_using))
+        restrict = self._restriction(query_filter, self.corpus.n_pages(stage1_using))
         stages = self.corpus.search_multistage(
             [(stage1_using, False, int(stage1_k)), (stage2_using, False, int(stage2_k)), (stage3_using, False, int(top_k))],
             None, stage_queries=[self._as_query(stage1_query), self._as_query(stage2_query), self._as_query(stage3_query)],
-            candidate_ids=cand)
+            **restrict)
         return [self._points(scores, ids, si == 2) for si, (scores, ids) in enumerate(stages)]
 
     @_locked

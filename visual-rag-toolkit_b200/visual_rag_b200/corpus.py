@@ -338,6 +338,24 @@ class GpuCorpus:
         N.check(self._lib.vrag_store_pool(self._h, src.encode(), n, arr, names, g))
         return self.last_timing_ms()[0]
 
+    # ------------------------------------------------------------------ payload filters (page bitmasks)
+    def create_filter(self, allowed) -> int:
+        """Upload a payload filter as a bitmask over this handle's pages: allowed[p] truthy = page p passes. Returns a
+        filter id for `search(..., filter_id=)` / `search_multistage(..., filter_id=)`; the mask stays on the device until
+        destroy_filter (one upload per distinct filter, none per query)."""
+        a = np.asarray(allowed, dtype=bool)
+        n = int(a.shape[0])
+        bits = np.packbits(a, bitorder="little")
+        words = np.zeros(((n + 31) // 32) * 4, dtype=np.uint8)
+        words[: bits.shape[0]] = bits
+        w32 = np.ascontiguousarray(words.view(np.uint32)) if words.size else np.zeros((1,), np.uint32)
+        fid = C.c_int()
+        N.check(self._lib.vrag_filter_create(self._h, w32.ctypes.data_as(C.POINTER(C.c_uint32)), n, C.byref(fid)))
+        return int(fid.value)
+
+    def destroy_filter(self, filter_id: int) -> None:
+        N.check(self._lib.vrag_filter_destroy(self._h, int(filter_id)))
+
     # ------------------------------------------------------------------ scoring
     @staticmethod
     def _cand_arg(candidate_ids):
@@ -391,9 +409,12 @@ class GpuCorpus:
         pool_query: bool = False,
         candidate_ids: Optional[Sequence[int]] = None,
         fp16_query: bool = False,
+        filter_id: Optional[int] = None,
     ) -> Tuple[np.ndarray, np.ndarray]:
         """Top-k pages by MaxSim: (scores fp32 [m], global page ids int64 [m]), m <= k, sorted by score
-        descending, ties by lower id."""
+        descending, ties by lower id. filter_id: restrict the scan to the pages of a `create_filter` bitmask."""
+        if filter_id is not None:
+            return self.search_multistage([(name, pool_query, k)], query, normalize, fp16_query=fp16_query, filter_id=filter_id)[0]
         q = _as_f32_query(query)
         k = _check_k(k)
         if k < 1 or (candidate_ids is not None and len(candidate_ids) == 0 and self.world == 1):
@@ -420,9 +441,12 @@ class GpuCorpus:
         stage_queries: Optional[Sequence] = None,
         candidate_ids: Optional[Sequence[int]] = None,
         fp16_query: bool = False,
+        filter_id: Optional[int] = None,
     ) -> List[Tuple[np.ndarray, np.ndarray]]:
         """Fused multi-stage search: stages = [(store name, pool_query, k), ...]; stage s is restricted to
-        the survivors of stage s-1 (stage 0 to `candidate_ids` if given). One host synchronisation.
+        the survivors of stage s-1 (stage 0 to `candidate_ids` if given, or to the pages of the `create_filter`
+        bitmask `filter_id` — filtered-out pages are skipped inside the scan and come back with score -inf, i.e. after
+        every page that passes). One host synchronisation.
         stage_queries: optional per-stage query matrices (else every stage uses `query`).
         Returns per-stage (scores, ids)."""
         ns = len(stages)
@@ -448,13 +472,23 @@ class GpuCorpus:
         scores = np.empty((total,), dtype=np.float32)
         ids = np.empty((total,), dtype=np.int64)
         counts = (C.c_int * ns)()
-        N.check(
-            self._lib.vrag_search_multistage(
-                self._h, ns, names, flags, ks, q.ctypes.data_as(C.POINTER(C.c_float)), q.shape[0], off_p,
-                cand_p, n_cand,
-                scores.ctypes.data_as(C.POINTER(C.c_float)), ids.ctypes.data_as(C.POINTER(C.c_int64)), counts,
+        if filter_id is not None:
+            if candidate_ids is not None:
+                raise ValueError("pass either candidate_ids or filter_id, not both")
+            N.check(
+                self._lib.vrag_search_multistage_filtered(
+                    self._h, int(filter_id), ns, names, flags, ks, q.ctypes.data_as(C.POINTER(C.c_float)), q.shape[0], off_p,
+                    scores.ctypes.data_as(C.POINTER(C.c_float)), ids.ctypes.data_as(C.POINTER(C.c_int64)), counts,
+                )
             )
-        )
+        else:
+            N.check(
+                self._lib.vrag_search_multistage(
+                    self._h, ns, names, flags, ks, q.ctypes.data_as(C.POINTER(C.c_float)), q.shape[0], off_p,
+                    cand_p, n_cand,
+                    scores.ctypes.data_as(C.POINTER(C.c_float)), ids.ctypes.data_as(C.POINTER(C.c_int64)), counts,
+                )
+            )
         out = []
         off = 0
         for s in range(ns):
