@@ -1272,7 +1272,9 @@ def test_page_bitmask_filter_in_the_scan_equals_candidate_list_and_oracle(corpus
             s_m, i_m = corpus.search("fm", q, 40, pool_query=pool, filter_id=fid)
             s_c, i_c = corpus.search("fm", q, 40, pool_query=pool, candidate_ids=ids_allowed)
             keep = np.isfinite(s_m)
-            assert i_m[keep].tolist() == i_c.tolist()[:int(keep.sum())] and np.array_equal(s_m[keep], s_c[:int(keep.sum())])
+            # the masked scan and the gather sum a page's token maxima in different orders: ids equal, scores to the last ulps
+            assert i_m[keep].tolist() == i_c.tolist()[:int(keep.sum())]
+            np.testing.assert_allclose(s_m[keep], s_c[:int(keep.sum())], rtol=2e-6)
             assert allowed[i_m[keep]].all() and keep.sum() == min(40, len(ids_allowed))
         sub = [rows[off[i]:off[i + 1]].astype(np.float32) for i in ids_allowed]
         want = MO.search_exhaustive(q, sub, 10)
@@ -1281,7 +1283,8 @@ def test_page_bitmask_filter_in_the_scan_equals_candidate_list_and_oracle(corpus
         # two-stage under the mask == two-stage over the candidate list
         st_m = corpus.search_multistage([("fm_pool", False, 64), ("fm", False, 10)], q, filter_id=fid)
         st_c = corpus.search_multistage([("fm_pool", False, 64), ("fm", False, 10)], q, candidate_ids=ids_allowed)
-        assert st_m[1][1].tolist() == st_c[1][1].tolist() and np.array_equal(st_m[1][0], st_c[1][0])
+        assert st_m[1][1].tolist() == st_c[1][1].tolist()
+        np.testing.assert_allclose(st_m[1][0], st_c[1][0], rtol=2e-6)
         corpus.destroy_filter(fid)
     # fewer pages pass than the stages keep: the padded (filtered-out) pages stay out of the later stage
     few = np.zeros(n, dtype=bool)
