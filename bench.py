@@ -57,6 +57,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["bf16_tflops_sustained"])
+    except Exception:
+        return 1400.0
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -766,6 +775,24 @@ def run_extras(corpus, args, peak, kern_ms):
     ms16 = corpus.last_timing_ms()[0]
     out["exhaustive_batched"]["fp16_query_ms_per_pass"] = ms16     # opt-in VRAG_Q_FP16: half the tensor work (power-limited scan)
     out["exhaustive_batched"]["fp16_query_page_scorings_per_s"] = 4 * pages / (ms16 * 1e-3)
+    # 8 and 32 queries per call: approximate first pass (8 plain-fp16 queries share every document tile) + exact re-score of
+    # 128 candidates per query; the lists must equal the single-query (fp32-exact) searches
+    flops_per_page_query = 2 * Q_TOKENS * TOKENS * 128
+    for nqb in (8, 32):
+        qb = [rng.standard_normal((Q_TOKENS, 128)).astype(np.float32) for _ in range(nqb)]
+        for _ in range(2):
+            res = corpus.search_multistage_batch([("initial", False, TOP_K)], qb)
+        ms_b, kern_b = corpus.last_timing_ms()
+        same = all(res[b][0][1].tolist() == corpus.search("initial", qb[b], TOP_K)[1].tolist() for b in range(0, nqb, 5))
+        issued = (nqb + 7) // 8 * pages * 2 * 256 * TOKENS * 128            # MMA flops issued: N = 256 columns per tile row
+        out["exhaustive_batched"][f"queries_{nqb}"] = {
+            "ms_per_call": ms_b, "first_pass_kernel_ms": kern_b, "page_scorings_per_s": nqb * pages / (ms_b * 1e-3),
+            "speedup_vs_single_query": nqb * kern_ms / ms_b, "lists_equal_single_query_path": bool(same),
+            "useful_tflops": nqb * pages * flops_per_page_query / (ms_b * 1e-3) / 1e12,
+            "roofline": {"bound": "tensor", "achieved": issued / (ms_b * 1e-3) / 1e12, "peak": measured_tensor_peak(),
+                         "unit": "TFLOP/s", "frac": issued / (ms_b * 1e-3) / 1e12 / measured_tensor_peak(),
+                         "note": "issued fp16 MMA flops (128 x 256 x 128 per tile and 8 queries) over bf16_tflops_sustained of "
+                                 "MEASURED_PEAKS.json; useful flops are 20/32 of the issued ones (20-token queries in 32-column slots)"}}
     # ---- payload-filter bitmask inside the scan (8(f)-3): the headline scan restricted to the pages that pass
     out["filtered_scan"] = {}
     for frac in (0.5, 0.05):

@@ -1335,3 +1335,55 @@ def Filter_bucket(b):
     from visual_rag_b200.retrieval import models as M
 
     return M.Filter(must=[M.FieldCondition(key="bucket", match=M.MatchValue(value=b))])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# batched exhaustive scans of full-token stores: approximate first pass (8 plain-fp16 queries per document tile) + exact
+# re-score of the candidates; a device-side guard keeps the result exact
+@pytest.mark.gpu
+@pytest.mark.parametrize("nq,k", [(8, 10), (13, 10), (5, 100), (32, 3)])
+def test_approximate_first_pass_batches_are_exact(corpus, nq, k, monkeypatch):
+    rng = np.random.default_rng(100 + nq)
+    n = 6000
+    lens = rng.integers(129, 420, size=n)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    corpus.add_synthetic_store("ap", 0, page_offsets=off, seed=4242)
+    qs = [rng.standard_normal((int(rng.integers(3, 33)), 128)).astype(np.float32) for _ in range(nq)]
+    got = corpus.search_multistage_batch([("ap", False, k)], qs)                     # approximate pass + re-score (default)
+    monkeypatch.setenv("VRAG_APPROX_PASS", "0")
+    exact = corpus.search_multistage_batch([("ap", False, k)], qs)                   # 4 fp32-exact queries per tile
+    monkeypatch.delenv("VRAG_APPROX_PASS")
+    for b, q in enumerate(qs):
+        assert got[b][0][1].tolist() == exact[b][0][1].tolist(), b
+        np.testing.assert_allclose(got[b][0][0], exact[b][0][0], rtol=1e-6)
+        s1, i1 = corpus.search("ap", q, k)                                           # single-query path
+        assert got[b][0][1].tolist() == i1.tolist()
+        np.testing.assert_allclose(got[b][0][0], s1, rtol=1e-6)
+    # as stage 0 of a two-stage batch (the candidate hand-off sees the re-scored, exactly ordered list)
+    corpus.add_synthetic_store("ap2", n, fixed_rows=140, seed=4243)
+    st_a = corpus.search_multistage_batch([("ap", False, 40), ("ap2", False, 5)], qs, as_arrays=True)
+    monkeypatch.setenv("VRAG_APPROX_PASS", "0")
+    st_e = corpus.search_multistage_batch([("ap", False, 40), ("ap2", False, 5)], qs, as_arrays=True)
+    monkeypatch.delenv("VRAG_APPROX_PASS")
+    for (sa, ia, _), (se, ie, _) in zip(st_a, st_e):
+        assert np.array_equal(ia, ie)
+        np.testing.assert_allclose(sa, se, rtol=1e-6)
+    corpus.drop_store("ap")
+    corpus.drop_store("ap2")
+
+
+@pytest.mark.gpu
+def test_approximate_first_pass_guard_falls_back_on_near_ties(corpus):
+    """Hundreds of identical pages tie at the top: the candidates of the fp16 pass cannot be proven to contain the top-k
+    (no candidate beats the bound of the pages left out), the guard raises the flag and the batch is redone exactly —
+    ties still resolve to the lower page id."""
+    rng = np.random.default_rng(7)
+    n, t = 5000, 150
+    rows = rows16(5151, n * t).reshape(n, t, 128)
+    rows[100:700] = rows[100]                                   # 600 identical pages
+    qs = [rows[100, :20].astype(np.float32) + 0.01 * rng.standard_normal((20, 128)).astype(np.float32) for _ in range(8)]
+    corpus.add_store("tie", rows.reshape(-1, 128), fixed_rows=t)
+    got = corpus.search_multistage_batch([("tie", False, 10)], qs)
+    for b in range(8):
+        assert got[b][0][1].tolist() == list(range(100, 110)), got[b][0][1]
+    corpus.drop_store("tie")

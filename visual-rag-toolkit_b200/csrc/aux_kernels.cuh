@@ -89,13 +89,18 @@ __global__ void query_prep_batch_kernel(const float* __restrict__ q, const int* 
 
 // Dense batched scans: G = QP/QS queries share one operand image (blockIdx.y = image); image row r holds row
 // r % QS of query (image*G + r / QS), hi half at row r and lo half at row QP + r; absent rows/queries are zero.
+// two_block (QS == 32): the image holds 2 * QP / QS queries as PLAIN fp16 — blockIdx.z = 0 fills rows [0, QP) with queries
+// 0..3, blockIdx.z = 1 rows [QP, 2QP) with queries 4..7 — and eps_out[b] accumulates the bound the host's exactness guard
+// needs for query b: sum over its rows of ||qhat - fp16(qhat)||_2 (the most a unit-norm document row can move that
+// row's cosine) + 2^-12 (the fp16 rounding of the row's running maximum in the first-pass epilogue).
 __global__ void query_prep_group_kernel(const float* __restrict__ q, const int* __restrict__ q_begin,
                                         const int* __restrict__ q_end, int nq, int pool, int normalize, int QP, int QS,
                                         uint8_t* __restrict__ qimg, long long qimg_stride,
-                                        int* __restrict__ q_valid_out) {
+                                        int* __restrict__ q_valid_out, int two_block = 0, float* __restrict__ eps_out = nullptr) {
   const int r = blockIdx.x;
   const int d = threadIdx.x;
-  const int b = blockIdx.y * (QP / QS) + r / QS;
+  const int G = (two_block ? 2 : 1) * (QP / QS);
+  const int b = blockIdx.y * G + blockIdx.z * (QP / QS) + r / QS;
   const int t = r % QS;
   __shared__ float wsum[4];
   float x = 0.0f;
@@ -130,6 +135,19 @@ __global__ void query_prep_group_kernel(const float* __restrict__ q, const int* 
   const __half lo = __float2half_rn((x - __half2float(hi)) * 2048.0f);
   const uint32_t rows = 2u * QP;
   uint8_t* img = qimg + blockIdx.y * qimg_stride;
+  if (two_block) {
+    *reinterpret_cast<__half*>(img + sw128_offset(rows, blockIdx.z * QP + r, d)) = live ? hi : __float2half_rn(0.0f);
+    // rounding error of this row, for the guard
+    float e = live ? (x - __half2float(hi)) : 0.0f;
+    e *= e;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+    __syncthreads();   // wsum was read above by every thread
+    if ((d & 31) == 0) wsum[d >> 5] = e;
+    __syncthreads();
+    if (d == 0 && live && eps_out) atomicAdd(eps_out + b, sqrtf((wsum[0] + wsum[1]) + (wsum[2] + wsum[3])) + 2.44140625e-4f);
+    return;
+  }
   *reinterpret_cast<__half*>(img + sw128_offset(rows, r, d)) = live ? hi : __float2half_rn(0.0f);
   *reinterpret_cast<__half*>(img + sw128_offset(rows, QP + r, d)) = live ? lo : __float2half_rn(0.0f);
 }
@@ -812,6 +830,44 @@ __global__ void __launch_bounds__(256) gather_stage_scores_kernel(const long lon
     }
   }
   if (lane == 0) out[w * out_stride + out_col] = found;
+}
+
+// Second half of the approximate-first-pass scheme (batched exhaustive scans): per query, the candidates of the fp16 first
+// pass with their EXACT scores -> sort keys (score, lower page first), and the guard: at least `need` candidates must beat
+// (strictly) the best score any page outside the candidate list can have, h_min + eps (h_min = the first-pass score of the
+// last candidate; a missing candidate, id < 0, means every page of the store is in the list). One block per query.
+__global__ void __launch_bounds__(256) approx_finalize_kernel(const float* __restrict__ exact, const float* __restrict__ approx,
+                                                              const long long* __restrict__ ids, int kc, int cap, long long id_base,
+                                                              const float* __restrict__ eps, int need,
+                                                              unsigned long long* __restrict__ keys, int* __restrict__ n_keys,
+                                                              int* __restrict__ fail_flag) {
+  const long long b = blockIdx.x;
+  __shared__ int s_better, s_valid;
+  if (threadIdx.x == 0) s_better = s_valid = 0;
+  __syncthreads();
+  const long long last_id = ids[b * kc + kc - 1];
+  const float bound = last_id >= 0 ? approx[b * kc + kc - 1] + eps[b] : -INFINITY;
+  int better = 0, valid = 0;
+  for (int j = threadIdx.x; j < kc; j += 256) {
+    const long long id = ids[b * kc + j];
+    const float e = exact[b * kc + j];
+    unsigned long long key = 0ull;
+    if (id >= 0) {
+      key = (static_cast<unsigned long long>(score_to_ord(e)) << 32) |
+            static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<uint32_t>(id - id_base));
+      ++valid;
+      if (e > bound) ++better;
+    }
+    keys[b * cap + j] = key;
+  }
+  for (int j = kc + threadIdx.x; j < cap; j += 256) keys[b * cap + j] = 0ull;
+  atomicAdd(&s_better, better);
+  atomicAdd(&s_valid, valid);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    n_keys[b] = kc;
+    if (s_better < min(need, s_valid)) atomicOr(fail_flag, 1);
+  }
 }
 
 // Gathered per-shard lists that are too long for one sort block (n_src * k_src > 8192): unpack them into plain score / id

@@ -324,7 +324,10 @@ __device__ __forceinline__ float slot_maxsim(float* v, int lane, int q_valid) {
 
 // QS: columns per query inside the operand image. QS == QP: one query per image (single-query scans and BSW
 // candidate scans). QS < QP (dense batched scans): QP/QS queries share every document tile.
-template <int QP, int QS, bool PACKED, bool BSW>
+// NBLK == 2 (LARGE pages, QS == 32): the operand image holds EIGHT queries as plain fp16 (rows [0,128) = queries 0-3,
+// rows [128,256) = queries 4-7; no lo halves): the first pass of a batched exhaustive scan — twice the queries per
+// document tile for the same tensor work; the host re-scores the top candidates exactly (hi|lo) afterwards.
+template <int QP, int QS, bool PACKED, bool BSW, int NBLK = 1>
 __global__ void __launch_bounds__(ScanCfg<QP>::threads(PACKED, QS < QP, BSW), 1)
 maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_constant__ RowMaps tm_small,
                    const __grid_constant__ CUtensorMap tm_scale128, const __grid_constant__ CUtensorMap tm_scale32,
@@ -349,6 +352,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   constexpr int EPI_ARRIVALS = MULTI ? 16 : 4; // epilogue warps that consume every tile
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
   static_assert(QS == QP || ((QS == 1 || QS == 32) && QP == 128 && !BSW), "sub-query layouts: 128x1 or 4x32 columns");
+  static_assert(NBLK == 1 || (NBLK == 2 && QS == 32 && QP == 128 && !PACKED && !BSW), "two query blocks: LARGE 8x32 only");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -645,7 +649,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (one thread)
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(kTileRows, p.hi_only ? ((QP + 15) / 16) * 16 : N);
+      const uint32_t idesc = umma_idesc_f16(kTileRows, (p.hi_only && NBLK == 1) ? ((QP + 15) / 16) * 16 : N);
       uint32_t b_addr = smem_u32(sB);
       uint32_t stage = 0, phase = 0, acc = 0, accphase = 0;
       int cur_g = -1, n_sw = -1;
@@ -716,7 +720,8 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
 
     if constexpr (!PACKED) {
       uint32_t stage = 0, phase = 0, acc = 0, accphase = 0, par = 0;
-      int q_valid = 0, qv_g = -1;
+      int q_valid = 0, q_valid2 = 0, qv_g = -1;
+      (void)q_valid2;
       UnitIter it;
       it.seek(ur, 0);
       for (long long i = 0; i < ur.count; ++i, it.advance(ur, 1)) {
@@ -726,15 +731,23 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         if (g != qv_g) {
           if constexpr (MULTI) q_valid = (QS == 32 && grp < p.n_sub) ? __ldg(p.q_valid_arr + grp) : 0;
           else q_valid = p.q_valid_arr ? __ldg(p.q_valid_arr + g) : p.q_valid;
+          if constexpr (NBLK == 2) q_valid2 = (grp + 4 < p.n_sub) ? __ldg(p.q_valid_arr + grp + 4) : 0;
           qv_g = g;
         }
         long long row0;
         int nrows;
         const bool ok = resolve_page(p, item_page(p, u, g), row0, nrows);
-        float run[QR];
+        float run[NBLK == 2 ? 1 : QR];
+        // NBLK == 2: 64 running maxima per thread (two query blocks) would not fit the register file of an 18-warp CTA, so
+        // this first, approximate pass keeps them as packed fp16 pairs: max commutes with the (monotone) rounding, i.e. each
+        // per-token maximum carries one fp16 rounding (<= 2^-12 for |cos| <= 1), which the host's exactness guard accounts for
+        __half2 runA[NBLK == 2 ? QR / 2 : 1], runB[NBLK == 2 ? QR / 2 : 1];
 #pragma unroll
-        for (int q = 0; q < QR; ++q) run[q] = -INFINITY;
+        for (int q = 0; q < (NBLK == 2 ? 1 : QR); ++q) run[q] = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < (NBLK == 2 ? QR / 2 : 1); ++q) runA[q] = runB[q] = __float2half2_rn(-INFINITY);
         const int ncol = !MULTI ? QE : (QS == 32 ? ((q_valid + 7) & ~7) : ((min(32, max(0, p.n_sub - col0)) + 7) & ~7));
+        const int ncol2 = (q_valid2 + 7) & ~7;
         for (int t0 = 0; t0 < nrows; t0 += kTileRows) {
           const int valid = min(kTileRows, nrows - t0);
           mbar_wait(&tfull[acc], accphase);
@@ -749,6 +762,31 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           // kernels are bound by the TMEM read port (64 B/clk: a 128x256 fp32 accumulator takes 2048 clk to drain), so
           // they read only the columns that hold real query rows (ncol, a multiple of 8).
           constexpr int LW = (QE % 16 == 0 && !MULTI) ? 16 : 8;
+          if constexpr (NBLK == 2) {
+            // two independent query blocks, both plain fp16: block A at columns [col0, col0+32), block B at QP + the same
+#pragma unroll
+            for (int c = 0; c < QE; c += 8) {
+              if (c >= ncol && c >= ncol2) break;
+              uint32_t a8[8], b8[8];
+              if (c < ncol) tmem_ld_x8(ta + c, a8);
+              if (c < ncol2) tmem_ld_x8(ta + QP + c, b8);
+              tmem_ld_wait();
+              if (trow < valid) {
+                if (c < ncol) {
+#pragma unroll
+                  for (int j = 0; j < 8; j += 2)
+                    runA[(c + j) / 2] = __hmax2(runA[(c + j) / 2], __floats2half2_rn(__uint_as_float(a8[j]) * scale,
+                                                                                   __uint_as_float(a8[j + 1]) * scale));
+                }
+                if (c < ncol2) {
+#pragma unroll
+                  for (int j = 0; j < 8; j += 2)
+                    runB[(c + j) / 2] = __hmax2(runB[(c + j) / 2], __floats2half2_rn(__uint_as_float(b8[j]) * scale,
+                                                                                   __uint_as_float(b8[j + 1]) * scale));
+                }
+              }
+            }
+          } else {
 #pragma unroll
           for (int c = 0; c < QE; c += LW) {
             if (MULTI && c >= ncol) break;
@@ -771,6 +809,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
               }
             }
           }
+          }
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) {
@@ -782,11 +821,23 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         }
         // page done: max across the 128 rows owned by the group's threads, then sum over q
         float* red = sRed + par * 4 * RS + col0;
+        if constexpr (NBLK == 2) {
+          float v[32];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float2 f = __half22float2(runA[q]);
+            v[2 * q] = f.x;
+            v[2 * q + 1] = f.y;
+          }
+          warp_transpose_max<32>(v, lane);
+          red[ew * RS + lane] = v[0];
+        } else {
 #pragma unroll
         for (int gq = 0; gq < QG; ++gq) {
           warp_transpose_max<QW>(run + gq * 32, lane);
           constexpr int rep = 32 / QW;  // lanes holding the same q
           if ((lane & (rep - 1)) == 0) red[ew * RS + gq * 32 + (lane / rep)] = run[gq * 32];
+        }
         }
         named_bar_sync(bar_id, 128);
         if (ew == 0) {
@@ -817,6 +868,29 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           }
         }
         par ^= 1;
+        if constexpr (NBLK == 2) {
+          // second query block: same reduction through the other scratch buffer (the barrier above separates its writes
+          // from the reads of the previous page that used it)
+          float* red2 = sRed + par * 4 * RS + col0;
+          float v[32];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float2 f = __half22float2(runB[q]);
+            v[2 * q] = f.x;
+            v[2 * q + 1] = f.y;
+          }
+          warp_transpose_max<32>(v, lane);
+          red2[ew * RS + lane] = v[0];
+          named_bar_sync(bar_id, 128);
+          if (ew == 0) {
+            const float m = fmaxf(fmaxf(red2[lane], red2[RS + lane]), fmaxf(red2[2 * RS + lane], red2[3 * RS + lane]));
+            float sum = lane < q_valid2 ? m : 0.0f;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            if (lane == 0 && grp + 4 < p.n_sub) emit(grp + 4, u, u * p.tile_stride, sum + ((ok && nrows > 0) ? 0.0f : -INFINITY));
+          }
+          par ^= 1;
+        }
       }
     } else {
       // ---------------- PACKED: several pages per tile

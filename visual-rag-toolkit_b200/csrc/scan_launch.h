@@ -20,6 +20,7 @@ struct ScanLaunch {
 // not built. Sets the opt-in shared-memory attribute once per device and variant.
 cudaError_t scan_launch_single(int QP, bool packed, const ScanLaunch& L);          // QS == QP, one query
 cudaError_t scan_launch_bsw(int QP, bool packed, const ScanLaunch& L);             // operand switching (QP 32 / 64)
-cudaError_t scan_launch_multi(int QS, bool packed, const ScanLaunch& L);           // QP == 128, QS in {1, 32}
+cudaError_t scan_launch_multi(int QS, bool packed, const ScanLaunch& L);           // QP == 128, QS in {1, 32}; kMultiQs8x32 (LARGE):
+constexpr int kMultiQs8x32 = 3208;                                                 //   eight plain-fp16 queries per image (first pass)
 
 }  // namespace vrag

@@ -19,9 +19,9 @@ struct PerDeviceOnceK {
   }
 };
 
-template <int QP, bool PACKED, bool BSW = false, int QS = QP>
+template <int QP, bool PACKED, bool BSW = false, int QS = QP, int NBLK = 1>
 static cudaError_t scan_launch_t(const ScanLaunch& L) {
-  auto kern = maxsim_scan_kernel<QP, QS, PACKED, BSW>;
+  auto kern = maxsim_scan_kernel<QP, QS, PACKED, BSW, NBLK>;
   const size_t smem = ScanCfg<QP>::smem_bytes(PACKED, BSW, QS < QP);
   static PerDeviceOnceK once;
   if (once.first()) {

@@ -271,6 +271,11 @@ struct vrag_corpus {
   DevBuf<float> d_stage_sc;       // final-only batch results: earlier-stage scores of the final ids
   DevBuf<int> d_fcnt;             // prefilter: candidate counts [nq] + flag [1]
   DevBuf<unsigned long long> d_fkeys;   // prefilter: candidate keys [nq][cap]
+  DevBuf<float> d_ap_sc, d_ap_exact, d_ap_eps;   // approximate first pass: candidate scores (fp16 pass / exact) [nq][kc], bounds [nq]
+  DevBuf<long long> d_ap_id;                     //   candidate ids [nq][kc]
+  DevBuf<unsigned long long> d_ap_keys;          //   sort keys of the exact scores [nq][key_cap]
+  DevBuf<int> d_ap_cnt;                          //   key counts [nq]
+  int64_t approx_runs = 0;
   int* h_flag = nullptr;          // pinned
   int64_t prefilter_runs = 0, prefilter_fallbacks = 0;
   int* h_qmeta = nullptr;         // pinned staging of d_qmeta
@@ -374,6 +379,12 @@ extern "C" int vrag_corpus_destroy(vrag_corpus_t* c) {
   c->d_fcnt.release();
   c->d_stage_sc.release();
   c->d_fkeys.release();
+  c->d_ap_sc.release();
+  c->d_ap_exact.release();
+  c->d_ap_eps.release();
+  c->d_ap_id.release();
+  c->d_ap_keys.release();
+  c->d_ap_cnt.release();
   comm_release(c);
   for (auto& kv : c->filters) kv.second.release();
   if (c->h_flag) cudaFreeHost(c->h_flag);
@@ -1128,6 +1139,8 @@ struct DenseOpts {
   unsigned long long* keys = nullptr;
   int cap = 0;
   bool skip_prep = false;         // operand images are already in d_qimg_batch (second pass of the same queries)
+  bool two_block = false;         // approximate first pass: 8 plain-fp16 token queries per image (LARGE stores)
+  float* eps = nullptr;           //   its per-query error bounds [nq] (zeroed and filled by the operand preparation)
 };
 static bool dense_batch_covers(int nq, int max_q_eff, uint32_t flags) {
   const int q_eff = (flags & VRAG_Q_POOL) ? 1 : max_q_eff;
@@ -1144,13 +1157,17 @@ static int launch_scan_dense_batch(vrag_corpus* c, const Store& s, const float* 
   if (s.total_rows == 0) return 2;   // pages without rows: the per-query path fills -inf
   const int QP = 128;
   const int QS = q_eff == 1 ? 1 : 32;
-  const int G = QP / QS;
+  const bool two = o.two_block && QS == 32 && !s.packed;
+  const int G = (two ? 2 : 1) * (QP / QS);
   const int n_img = (nq + G - 1) / G;
   const size_t img = static_cast<size_t>(2 * QP) * 256;
   if (!o.skip_prep) {
     TRY(c->d_qimg_batch.ensure(img * n_img));
-    query_prep_group_kernel<<<dim3(QP, n_img), 128, 0, st>>>(d_queries, d_qbegin, d_qend, nq, pool ? 1 : 0, normalize ? 1 : 0,
-                                                             QP, QS, c->d_qimg_batch.p, static_cast<long long>(img), d_qvalid);
+    if (two && o.eps) CUDA_OK(cudaMemsetAsync(o.eps, 0, static_cast<size_t>(nq) * sizeof(float), st));
+    query_prep_group_kernel<<<dim3(QP, n_img, two ? 2 : 1), 128, 0, st>>>(d_queries, d_qbegin, d_qend, nq, pool ? 1 : 0,
+                                                                          normalize ? 1 : 0, QP, QS, c->d_qimg_batch.p,
+                                                                          static_cast<long long>(img), d_qvalid, two ? 1 : 0,
+                                                                          two ? o.eps : nullptr);
     c->launches++;
   }
   if (time_kernel) CUDA_OK(cudaEventRecord(c->evk0, st));
@@ -1166,7 +1183,7 @@ static int launch_scan_dense_batch(vrag_corpus* c, const Store& s, const float* 
     p.score_stride = stride_cols;
     p.n_sub = std::min(G, nq - g * G);
     {
-      p.hi_only = (((flags & VRAG_Q_FP16) != 0 || knob_hi_only()) && !s.packed) ? 1 : 0;
+      p.hi_only = (two || (((flags & VRAG_Q_FP16) != 0 || knob_hi_only()) && !s.packed)) ? 1 : 0;
     }
     if (o.tile_stride > 1) {   // sample pass: every tile_stride-th page (LARGE) / full tile (PACKED fixed rows)
       p.tile_stride = o.tile_stride;
@@ -1185,7 +1202,7 @@ static int launch_scan_dense_batch(vrag_corpus* c, const Store& s, const float* 
       p.f_keys = o.keys + static_cast<size_t>(g) * G * o.cap;
       p.f_cap = o.cap;
     }
-    TRY(launch_scan_variant(c, s, p, n_units, st, 2, QS));
+    TRY(launch_scan_variant(c, s, p, n_units, st, 2, two ? kMultiQs8x32 : QS));
   }
   if (time_kernel) CUDA_OK(cudaEventRecord(c->evk1, st));
   return 0;
@@ -1887,7 +1904,15 @@ struct PrefilterPlan {
   int64_t n_sample = 0;
   int m = 0;
   int cap = 8192;
+  // Approximate first pass + exact re-score (dense batched token scans of LARGE stores, >= 5 queries): the scan runs with 8
+  // plain-fp16 queries per document tile (twice the queries for the same tensor work), keeps kc > k candidates per query,
+  // re-scores them exactly (fp32 query as hi|lo pair, the operand-switching gather) and takes the top-k of those. A
+  // device-side guard proves that no page outside the candidates can reach the top-k (else the batch is redone exactly).
+  bool approx = false;
+  int kc = 0;         // candidates kept by the first pass
+  int key_cap = 0;    // key-list capacity of the final sort (power of two >= kc)
 };
+static bool knob_no_approx() { return env_flag_is("VRAG_APPROX_PASS", '0'); }
 static PrefilterPlan plan_prefilter(const Store& s, int k, int nq, int max_q_eff, uint32_t flags) {
   PrefilterPlan pl;
   if (knob_no_prefilter()) return pl;
@@ -1902,6 +1927,8 @@ static PrefilterPlan plan_prefilter(const Store& s, int k, int nq, int max_q_eff
   }
   const int64_t want = std::max<int64_t>(65536, (32 * n + k - 1) / k);   // sample size: >= 32 expected hits above the k-th score
   if (want * 4 > n) return pl;
+  if (!s.packed && want * 20 > n) return pl;   // full-token stores: the sample pass re-reads corpus bytes, the score matrix it
+                                               // saves is tiny next to them — only worth it when the sample is < 5 % of the scan
   const int64_t stride = n_units / ((want + unit_pages - 1) / unit_pages);
   if (stride < 2) return pl;
   const int64_t sampled_units = (n_units + stride - 1) / stride;
@@ -1994,11 +2021,30 @@ static int batch_stage_chunk(vrag_corpus* c, int s, Store& store, uint32_t flags
   const int max_rows = bc.max_rows[s];
   if (have_items) {
     int r = 2;
+    // first-pass outputs: the stage's own lists, or — approximate first pass — the candidate lists that get re-scored
+    const bool approx = plan.approx && !d_prev_ids;
+    const int k1 = approx ? plan.kc : k;
+    float* const l_sc = approx ? c->d_ap_sc.p : o_sc;
+    long long* const l_id = approx ? c->d_ap_id.p : o_id;
+    Hit* const l_hits = approx ? nullptr : o_hits;
+    auto finish_approx = [&]() -> int {
+      // exact scores of every query's candidates (operand-switching gather, fp32-exact query), then the final order
+      int rr = launch_scan_batch(c, store, c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows, flags, c->d_ap_id.p, plan.kc,
+                                 c->d_ap_exact.p, stm);
+      if (rr) return rr == 2 ? fail("internal: candidate re-score not covered") : rr;
+      approx_finalize_kernel<<<qc, 256, 0, stm>>>(c->d_ap_exact.p, c->d_ap_sc.p, c->d_ap_id.p, plan.kc, plan.key_cap, c->page_base,
+                                                  c->d_ap_eps.p, k, c->d_ap_keys.p, c->d_ap_cnt.p, c->d_fcnt.p + nq);
+      c->launches++;
+      return launch_topk_keys(c, c->d_ap_keys.p, c->d_ap_cnt.p, plan.key_cap, k, c->page_base, o_sc, o_id, stm, qc, nullptr, nullptr,
+                              nullptr, 0, o_hits, o_hits ? c->d_fcnt.p + nq : nullptr);
+    };
     if (!d_prev_ids && plan.on) {
       // fused top-k prefilter: sample -> thresholds -> filtered scan -> sort the survivors
       DenseOpts o;
       o.tile_stride = plan.tile_stride;
       o.n_sample = plan.n_sample;
+      o.two_block = approx;
+      o.eps = c->d_ap_eps.p;
       TRY(launch_scan_dense_batch(c, store, c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows, flags, c->d_scores.p, stm,
                                   false, o));
       prefilter_sample_thr_kernel<false><<<qc, 1024, 0, stm>>>(c->d_scores.p, plan.n_sample, plan.m, c->d_fthr.p, c->d_fcnt.p);
@@ -2008,15 +2054,26 @@ static int batch_stage_chunk(vrag_corpus* c, int s, Store& store, uint32_t flags
       f.keys = c->d_fkeys.p;
       f.cap = plan.cap;
       f.skip_prep = true;
+      f.two_block = approx;
       TRY(launch_scan_dense_batch(c, store, c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows, flags, nullptr, stm,
                                   timed && !*timed, f));
       if (timed) *timed = true;
-      prefilter_check_kernel<<<(qc + 127) / 128, 128, 0, stm>>>(c->d_fcnt.p, qc, static_cast<int>(std::min<int64_t>(k, store.n_pages)),
+      prefilter_check_kernel<<<(qc + 127) / 128, 128, 0, stm>>>(c->d_fcnt.p, qc, static_cast<int>(std::min<int64_t>(k1, store.n_pages)),
                                                                 plan.cap, c->d_fcnt.p + nq);
       c->launches += 2;
-      TRY(launch_topk_keys(c, c->d_fkeys.p, c->d_fcnt.p, plan.cap, k, c->page_base, o_sc, o_id, stm, qc, nullptr, nullptr, nullptr, 0,
-                           o_hits, o_hits ? c->d_fcnt.p + nq : nullptr));
-      return 0;
+      TRY(launch_topk_keys(c, c->d_fkeys.p, c->d_fcnt.p, plan.cap, k1, c->page_base, l_sc, l_id, stm, qc, nullptr, nullptr, nullptr, 0,
+                           l_hits, l_hits ? c->d_fcnt.p + nq : nullptr));
+      return approx ? finish_approx() : 0;
+    }
+    if (approx) {
+      DenseOpts o;
+      o.two_block = true;
+      o.eps = c->d_ap_eps.p;
+      TRY(launch_scan_dense_batch(c, store, c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows, flags, c->d_scores.p, stm,
+                                  timed && !*timed, o));
+      if (timed) *timed = true;
+      TRY(launch_topk(c, c->d_scores.p, nullptr, c->page_base, n_items, k1, l_sc, l_id, nullptr, nullptr, stm, qc, 0));
+      return finish_approx();
     }
     if (!d_prev_ids && dense_batch_covers(qc, max_rows, flags)) {
       r = launch_scan_dense_batch(c, store, c->d_query.p, d_qb, d_qe, d_qvalid + b0, qc, max_rows, flags, c->d_scores.p, stm,
@@ -2058,11 +2115,32 @@ static int batch_prepare_stage(vrag_corpus* c, Store& store, int k, int64_t n_it
   const int qchunk = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(bc.nq, max_scores / per_query)));
   TRY(c->d_scores.ensure(static_cast<int64_t>(qchunk) * per_query));
   *plan = PrefilterPlan();
-  if (dense && allow_prefilter && !knob_no_prefilter()) *plan = plan_prefilter(store, k, qchunk, bc.max_rows[s], flags);
+  // approximate first pass + exact re-score: token queries (<= 32 rows), cosine scores, a full-token store, enough queries
+  // to fill more than one 4-query image, and a candidate list that stays a small part of the store
+  bool approx = false;
+  int kc = 0;
+  if (dense && allow_prefilter && !knob_no_approx() && !store.packed && (flags & VRAG_Q_NORMALIZE) &&
+      !(flags & (VRAG_Q_POOL | VRAG_Q_FP16)) && bc.max_rows[s] > 1 && bc.max_rows[s] <= 32 && qchunk >= 5 && k >= 1) {
+    kc = std::max(k + 118, 2 * k);
+    approx = kc <= 2048 && static_cast<int64_t>(kc) * 8 <= store.n_pages;
+  }
+  if (dense && allow_prefilter && !knob_no_prefilter()) *plan = plan_prefilter(store, approx ? kc : k, qchunk, bc.max_rows[s], flags);
   if (plan->on) {
     TRY(c->d_fthr.ensure(qchunk));
     TRY(c->d_fkeys.ensure(static_cast<size_t>(qchunk) * plan->cap));
     c->prefilter_runs++;
+  }
+  if (approx) {
+    plan->approx = true;
+    plan->kc = kc;
+    plan->key_cap = kc <= 1024 ? 1024 : 2048;
+    TRY(c->d_ap_sc.ensure(static_cast<size_t>(qchunk) * kc));
+    TRY(c->d_ap_exact.ensure(static_cast<size_t>(qchunk) * kc));
+    TRY(c->d_ap_id.ensure(static_cast<size_t>(qchunk) * kc));
+    TRY(c->d_ap_eps.ensure(qchunk));
+    TRY(c->d_ap_keys.ensure(static_cast<size_t>(qchunk) * plan->key_cap));
+    TRY(c->d_ap_cnt.ensure(qchunk));
+    c->approx_runs++;
   }
   *qchunk_out = qchunk;
   return 0;
@@ -2211,7 +2289,7 @@ static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const ch
     CUDA_OK(cudaMemcpyAsync(c->h_out_scores, c->d_out_scores.p, out_n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaMemcpyAsync(c->h_out_ids, c->d_out_ids.p, out_n * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
   }
-  const bool check_flag = plan.on || (sh && !no_prefilter);
+  const bool check_flag = plan.on || plan.approx || (sh && !no_prefilter);
   if (check_flag) CUDA_OK(cudaMemcpyAsync(c->h_flag, c->d_fcnt.p + nq, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
   if (sh) comm_collect_timing(c);
