@@ -49,6 +49,14 @@ elif what == "large_batch":
     for _ in range(reps):
         c.search_multistage_batch([("initial", False, 10)], qs)
     print("large_batch", n, c.last_timing_ms())
+elif what == "large_batch8":
+    # batched exhaustive scan, approximate first pass: 8 plain-fp16 queries share every document tile (kernel <128,32,0,0,2>)
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 100_000
+    c.add_synthetic_store("initial", n, fixed_rows=1030, seed=1)
+    qs = [rng.standard_normal((20, 128)).astype(np.float32) for _ in range(8)]
+    for _ in range(reps):
+        c.search_multistage_batch([("initial", False, 10)], qs)
+    print("large_batch8", n, c.last_timing_ms())
 elif what == "packed_batch":
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 500_000
     c.add_synthetic_store("mean_pooling", n, fixed_rows=32, seed=2)
