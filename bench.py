@@ -370,6 +370,47 @@ def sharded_parity_check(local_rank, rank, world):
                 out["checks"].append(what)
         finally:
             c3.close()
+        # ---- sharded ingest: every rank uploads the points routed to it (stable hash of the id), upserts one of them with
+        # a new shape, then all ranks sync the id / payload tables; searches see the union, with external ids and payloads
+        from visual_rag_b200.client import owner_rank_of_id
+        from visual_rag_b200.indexing import GpuIndexer
+
+        c4 = GpuCorpus(local_rank, page_base=rank << 32)       # ingest shards own disjoint, sparse id ranges
+        try:
+            c4.comm_init_torch()
+            cl4 = ShardedCorpusClient(c4, "ingest", point_ids=[], payloads=[])
+            idx = GpuIndexer(c4, "ingest", client=cl4)
+            n_pts = 600
+
+            def point(i, ver):
+                g = np.random.default_rng(7000 + 10 * i + ver)
+                t = int(g.integers(130, 200)) + 7 * ver
+                v = g.standard_normal((t, 128)).astype(np.float32)
+                v /= np.linalg.norm(v, axis=1, keepdims=True)
+                return {"id": f"doc-{i:05d}", "visual_embedding": v.astype(np.float16).astype(np.float32),
+                        "tile_pooled_embedding": v[:8].astype(np.float16).astype(np.float32), "metadata": {"i": i, "ver": ver}}
+
+            mine = [i for i in range(n_pts) if owner_rank_of_id(f"doc-{i:05d}", world) == rank]
+            for lo in range(0, len(mine), 64):
+                assert idx.upload_batch([point(i, 0) for i in mine[lo:lo + 64]]) == len(mine[lo:lo + 64])
+            changed = [i for i in mine if i % 50 == 0]
+            if changed:
+                assert idx.upload_batch([point(i, 1) for i in changed]) == len(changed)     # upsert with a new token count
+            cl4.sync_points()
+            final = [point(i, 1 if i % 50 == 0 else 0) for i in range(n_pts)]
+            got = SingleStageRetriever(cl4, "ingest").search(qs[3], top_k=10, strategy="multi_vector")
+            want = MO.search_exhaustive(qs[3], [p_["visual_embedding"] for p_ in final], 10)
+            if [g["id"] for g in got] != [final[i]["id"] for i, _ in want]:
+                raise AssertionError(f"sharded ingest: ids differ {[g['id'] for g in got][:5]} vs {[final[i]['id'] for i, _ in want][:5]}")
+            if not np.allclose([g["score"] for g in got], [x for _, x in want], rtol=2e-5):
+                raise AssertionError("sharded ingest: scores differ")
+            if [g["payload"] for g in got] != [final[i]["metadata"] for i, _ in want]:
+                raise AssertionError("sharded ingest: payloads differ")
+            if cl4.get_collection("ingest").points_count != n_pts:
+                raise AssertionError("sharded ingest: points_count")
+            out["checks"].append("sharded_ingest_upsert_sync_search")
+        finally:
+            c4.close()
         out["sharded_parity"] = True
         out["comm_us_last_search"] = c2.comm_timing_us()
     except Exception as e:  # noqa: BLE001

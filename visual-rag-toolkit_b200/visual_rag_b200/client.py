@@ -166,13 +166,13 @@ class GpuCorpusClient:
 
     @_locked
     def set_payload(self, point_id, payload: Optional[dict]) -> None:
-        """Replace the payload of an existing point (upsert of an id that is already in the collection)."""
-        page = self._page(point_id)
-        if page < 0:
+        """Replace the payload of an existing point of this handle (upsert of an id that is already in the collection)."""
+        local = self.local_page(point_id)
+        if local < 0:
             raise KeyError(point_id)
         if self._payloads is None:
             self._payloads = [None] * len(self._ids)
-        self._payloads[page - self.corpus.page_base] = payload
+        self._payloads[local] = payload
         self._invalidate()
 
     @_locked
@@ -210,6 +210,21 @@ class GpuCorpusClient:
         if self._payloads is None:
             return {}
         return self._payloads[page - self.corpus.page_base]
+
+    def local_page(self, pid) -> int:
+        """external point id -> index of its page in THIS corpus handle (-1 if this handle does not hold it). What the
+        ingest path (GpuIndexer) uses: on a sharded client it never sees the points of other ranks."""
+        if self._index is not None:
+            i = self._index.get(pid)
+            if i is None and not isinstance(pid, str):
+                i = self._index.get(str(pid))
+            return -1 if i is None else int(i)
+        try:
+            i = int(pid) - self.corpus.page_base
+        except (TypeError, ValueError):
+            return -1
+        n = max([self.corpus.n_pages(nm) for nm in ("initial", "mean_pooling", "global_pooling") if self.corpus.has_store(nm)] or [0])
+        return i if 0 <= i < n else -1
 
     def _pids_of(self, pages: List[int]) -> list:
         ext, base = self._ids, self.corpus.page_base
@@ -663,19 +678,15 @@ class ShardedCorpusClient(GpuCorpusClient):
             out.update(part)
         return out
 
-    # local table edits keep working (this rank's pages); they become visible to result building after sync_points()
-    def set_payload(self, point_id, payload: Optional[dict]) -> None:
-        page = self._page(point_id)
-        if page < 0:
-            raise KeyError(point_id)
-        r, loc = self._locate(page)
-        base, n, ids, pls = self._shards[r]
-        if pls is None:
-            pls = [None] * n
-            self._shards[r] = (base, n, ids, pls)
-        pls[loc] = payload
-        if r == self._bases.index(self.corpus.page_base):
-            if self._payloads is None:
-                self._payloads = [None] * n
-            self._payloads[loc] = payload
-            self._invalidate()
+    # Ingest at N > 1: every rank ingests ITS OWN points (GpuIndexer(corpus, client=this client).upload_batch(points of
+    # this rank) — route ids to ranks with `owner_rank_of_id`, so that an upsert of an id lands on the rank that holds it),
+    # then all ranks call sync_points() together: the local table edits (append_points / set_payload / remove_points)
+    # become visible to result building on every rank.
+
+
+def owner_rank_of_id(point_id, world: int) -> int:
+    """Stable rank assignment of a point id for sharded ingest (the same id always lands on the same rank)."""
+    import hashlib
+
+    h = hashlib.sha256(str(point_id).encode()).digest()
+    return int.from_bytes(h[:8], "little") % max(int(world), 1)

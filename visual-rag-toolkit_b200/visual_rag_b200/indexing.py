@@ -37,6 +37,8 @@ class GpuIndexer:
         self.client = client if client is not None else GpuCorpusClient(corpus, collection_name, point_ids=[], payloads=[])
         if self.client._ids is None:
             self.client.set_points([], [])
+        # At N > 1 (client = ShardedCorpusClient) every rank runs its own indexer over its own points; see the note at the
+        # end of client.py (owner_rank_of_id, sync_points).
         self._extra_names: List[str] = []
         self._seen_names: List[str] = []      # every named vector an upload has written so far
         # the reference drives upload_batch from uploader threads (run_qdrant_beir.py:720-768) while queries may run: one
@@ -73,7 +75,7 @@ class GpuIndexer:
         return f"{hex_str[:8]}-{hex_str[8:12]}-{hex_str[12:16]}-{hex_str[16:20]}-{hex_str[20:32]}"
 
     def check_exists(self, chunk_id: str) -> bool:
-        return self.client._page(chunk_id) >= 0
+        return self.client.local_page(chunk_id) >= 0
 
     def get_existing_ids(self, filename: Optional[str] = None) -> set:
         ids = self.client._ids or []
@@ -149,8 +151,7 @@ class GpuIndexer:
             have = self.corpus.n_pages(name)
             if have != n_before:
                 raise ValueError(f"named vector '{name}' holds {have} pages but the collection has {n_before} points")
-        base = self.corpus.page_base
-        old_pages = [self.client._page(i) - base for i in old_ids]
+        old_pages = [self.client.local_page(i) for i in old_ids]
         empty = np.zeros((0, 128), dtype=np.float32)
 
         def pack(ids, name):
@@ -201,8 +202,7 @@ class GpuIndexer:
         """qdrant `client.delete(points_selector=ids)`: the points disappear from every search and from check_exists; their
         pages keep their index (and are reclaimed by `compact`). Returns the number of deleted points."""
         with self._lock:
-            base = self.corpus.page_base
-            pages = [self.client._page(i) - base for i in point_ids if self.check_exists(i)]
+            pages = [self.client.local_page(i) for i in point_ids if self.check_exists(i)]
             if not pages:
                 return 0
             for name in self._known_names():
