@@ -255,6 +255,16 @@ __device__ __forceinline__ uint32_t issue_rows(uint8_t* a, float* sc, uint64_t* 
   return bytes + nb * (use_scale ? kScaleBoxSmall * 4 : 0);
 }
 
+// Bytes issue_rows() makes the mbarrier expect for the same arguments (pure arithmetic: lets a converged warp know the
+// count while only one elected lane issues the copies).
+__device__ __forceinline__ uint32_t issue_rows_bytes(int nrows, int dst_row, bool use_scale) {
+  if (dst_row == 0 && nrows > 96) return kTileBytes + (use_scale ? kScaleBoxBig * 4 : 0);
+  const int nb = (nrows + kBoxRowsSmall - 1) / kBoxRowsSmall;
+  const int last = nrows - (nb - 1) * kBoxRowsSmall;
+  const int last_rows = ((last + kBoxStep - 1) / kBoxStep) * kBoxStep;
+  return ((nb - 1) * kBoxRowsSmall + last_rows) * (kDim * 2) + nb * (use_scale ? kScaleBoxSmall * 4 : 0);
+}
+
 // In-place butterfly max over the 32 lanes of a warp for CNT (power of two <= 32) values per lane.
 // On return v[0] of lane L holds the max over all lanes of value index (L >> (5 - log2 CNT)).
 template <int CNT>
@@ -476,14 +486,18 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
     int cur_g = -1, n_sw = -1;
     // BSW with a single producer (LARGE pages): entering query group g -> fill the other operand buffer once its previous
     // MMAs retired (lane 0 only). With two producers the operand loader warp above does this.
+    // (called by the whole, converged warp: the wait is uniform, the copy is issued by one elected lane)
     auto switch_group = [&](int g) {
       if constexpr (BSW && PRODUCERS == 1) {
         if (g != cur_g) {
           ++n_sw;
           const int slot = n_sw & 1;
           if (n_sw >= 2) mbar_wait(&bempty[slot], ((n_sw >> 1) - 1) & 1);
-          bulk_load(sB + slot * Cfg::B_BYTES, p.qimg + g * p.qimg_stride, Cfg::B_BYTES, &bfull[slot]);
-          mbar_arrive_expect_tx(&bfull[slot], Cfg::B_BYTES);
+          if (elect_one_sync()) {
+            bulk_load(sB + slot * Cfg::B_BYTES, p.qimg + g * p.qimg_stride, Cfg::B_BYTES, &bfull[slot]);
+            mbar_arrive_expect_tx(&bfull[slot], Cfg::B_BYTES);
+          }
+          __syncwarp();
           cur_g = g;
         }
       }
@@ -528,57 +542,58 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             const uint32_t i = pw + PRODUCERS * (k0 + t);          // tile index in the CTA's range
             stage = i % STAGES;
             phase = (i / STAGES) & 1u;
-            // lane j (< per_tile) owns item j of this tile and issues its TMA boxes itself: the copies of the (up to 4)
-            // items are issued in parallel instead of one thread serialising 12 bulk-tensor instructions per tile
-            const int src = (t * per_tile + lane) & 31;
-            long long my_r0 = __shfl_sync(0xffffffffu, cur_r0, src);
-            int my_nr = __shfl_sync(0xffffffffu, cur_nr, src);
-            if (lane >= per_tile) my_nr = 0, my_r0 = 0;
-            if (lane == 0) {
-              if constexpr (BSW && PRODUCERS == 1) {
-                switch_group(it.g);
-                it.advance(ur, 1);
+            if constexpr (BSW && PRODUCERS == 1) {
+              switch_group(it.g);
+              it.advance(ur, 1);
+            }
+            mbar_wait(&empty[stage], phase ^ 1);   // the whole warp (uniform)
+            uint8_t* a = sA + stage * kTileBytes;
+            const int me = static_cast<int>(i % META);          // side-data ring entry of this tile
+            float* sc = sScale + me * kScaleStride;
+            // The tile's (up to 4) items are issued one after the other from warp-uniform values (their row ranges are
+            // broadcast from the lanes that resolved them): uniform operands keep every copy at a handful of instructions;
+            // per-lane operands cost a register -> uniform-register waterfall per copy.
+            uint32_t bytes = 0;
+            for (int j = 0; j < per_tile; ++j) {
+              const int src = (t * per_tile + j) & 31;
+              const long long r0 = __shfl_sync(0xffffffffu, cur_r0, src);
+              const int nr = __shfl_sync(0xffffffffu, cur_nr, src);
+              const int mi = (nr + kBoxStep - 1) / kBoxStep - 1;   // slot_rows == 32: one box of 4 * (mi + 1) rows per K-half
+              const bool one_box = p.slot_rows == kBoxRowsSmall;
+              if (nr > 0)
+                bytes += one_box ? (mi + 1) * (kBoxStep * kDim * 2) + (use_scale ? kScaleBoxSmall * 4 : 0)
+                                 : issue_rows_bytes(nr, j * p.slot_rows, use_scale);
+              if (elect_one_sync()) {
+                if (nr > 0) {
+                  if (one_box) {
+                    const CUtensorMap* tm = &tm_small.m[mi];
+                    const int32_t r = static_cast<int32_t>(r0);
+                    uint8_t* dst = a + j * (kBoxRowsSmall * 128);
+                    tma_load_2d(dst, tm, &full[stage], 0, r);
+                    tma_load_2d(dst + kHalfBytes, tm, &full[stage], 64, r);
+                    if (use_scale) tma_load_1d(sc + j * (kBoxRowsSmall + 32), &tm_scale32, &full[stage], r & ~3);
+                  } else {
+                    issue_rows(a, sc + j * (p.slot_rows + 32), &full[stage], &tm_rows128, &tm_small, &tm_scale128, &tm_scale32, r0, nr,
+                               j * p.slot_rows, use_scale);
+                  }
+                }
+                // low 2 bits: scale misalignment; rest: rows of the slot (0 for unused / empty slots)
+                sMis[me * 4 + j] = static_cast<int>(r0 & 3) | (nr << 2);
               }
-              mbar_wait(&empty[stage], phase ^ 1);
+              __syncwarp();
+            }
+            if (elect_one_sync()) {
+              for (int j = per_tile; j < 4; ++j) sMis[me * 4 + j] = 0;
+              mbar_arrive_expect_tx(&full[stage], bytes);   // same lane as the copies and the sMis stores
             }
             __syncwarp();
-            uint32_t bytes = 0;
-            if (lane < 4) {
-              uint8_t* a = sA + stage * kTileBytes;
-              const int me = static_cast<int>(i % META);          // side-data ring entry of this tile
-              float* sc = sScale + me * kScaleStride;
-              if (my_nr > 0) {
-                if (p.slot_rows == kBoxRowsSmall) {
-                  // one page per 32-row slot: exactly one row box (sized to the page) per K-half + its scale rows
-                  const int mi = (my_nr + kBoxStep - 1) / kBoxStep - 1;
-                  const CUtensorMap* tm = &tm_small.m[mi];
-                  const int32_t r = static_cast<int32_t>(my_r0);
-                  uint8_t* dst = a + lane * (kBoxRowsSmall * 128);
-                  tma_load_2d(dst, tm, &full[stage], 0, r);
-                  tma_load_2d(dst + kHalfBytes, tm, &full[stage], 64, r);
-                  bytes = (mi + 1) * (kBoxStep * kDim * 2);
-                  if (use_scale) {
-                    tma_load_1d(sc + lane * (kBoxRowsSmall + 32), &tm_scale32, &full[stage], r & ~3);
-                    bytes += kScaleBoxSmall * 4;
-                  }
-                } else {
-                  bytes = issue_rows(a, sc + lane * (p.slot_rows + 32), &full[stage], &tm_rows128, &tm_small, &tm_scale128,
-                                     &tm_scale32, my_r0, my_nr, lane * p.slot_rows, use_scale);
-                }
-              }
-              // low 2 bits: scale misalignment; rest: rows of the slot (0 for unused / empty slots)
-              sMis[me * 4 + lane] = static_cast<int>(my_r0 & 3) | (my_nr << 2);
-            }
-            bytes += __shfl_xor_sync(0xffffffffu, bytes, 1);
-            bytes += __shfl_xor_sync(0xffffffffu, bytes, 2);
-            __syncwarp();   // the other lanes' sMis stores are ordered before lane 0's (releasing) arrive
-            if (lane == 0) mbar_arrive_expect_tx(&full[stage], bytes);
           }
           cur_r0 = nxt_r0;
           cur_nr = nxt_nr;
         }
       }
-    } else if (lane == 0 && !is_prod_b) {
+    } else if (!is_prod_b) {
+      // streaming layouts (LARGE pages, dense PACKED tiles): the warp runs converged, one elected lane issues the copies
       PackedTileMeta cur, nxt;
       cur.cnt = nxt.cnt = 0;
       long long row0 = 0, row0_n = 0;
@@ -602,12 +617,15 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* a = sA + stage * kTileBytes;
             float* sc = sScale + stage * kScaleStride;
-            // copies first, then one arrive.expect_tx with the exact byte count: the phase cannot complete
-            // before the arrive, and the tx-count may go transiently negative.
-            const uint32_t bytes = issue_rows(a, sc, &full[stage], &tm_rows128, &tm_small, &tm_scale128,
-                                              &tm_scale32, row0 + t0, rows, 0, use_scale);
-            sMis[stage * 4] = static_cast<int>((row0 + t0) & 3);
-            mbar_arrive_expect_tx(&full[stage], bytes);
+            if (elect_one_sync()) {
+              // copies first, then one arrive.expect_tx with the exact byte count: the phase cannot complete
+              // before the arrive, and the tx-count may go transiently negative.
+              const uint32_t bytes = issue_rows(a, sc, &full[stage], &tm_rows128, &tm_small, &tm_scale128,
+                                                &tm_scale32, row0 + t0, rows, 0, use_scale);
+              sMis[stage * 4] = static_cast<int>((row0 + t0) & 3);
+              mbar_arrive_expect_tx(&full[stage], bytes);
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           row0 = row0_n;
@@ -626,6 +644,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           const int me = static_cast<int>(i % META);                     // side-data ring entry of this tile
           float* sc = sScale + me * kScaleStride;
           uint32_t bytes = 0;
+          if (elect_one_sync()) {
           if (p.pad_rows > 0) {
             // padded slots: the first map is the store's 3-D {cols, rows-in-page, pages} view; one box per K-half
             const int32_t pg0 = static_cast<int32_t>(cur.r0[0] / p.pad_rows);
@@ -641,15 +660,23 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
                                cur.nr[0], 0, use_scale);
           sMis[me * 4] = static_cast<int>(cur.r0[0] & 3);
           mbar_arrive_expect_tx(&full[stage], bytes);
+          }
+          __syncwarp();
           cur = nxt;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer (one thread)
-    if (lane == 0) {
+    // ===================================================================== MMA issuer
+    // The whole warp runs this loop converged (waits included) and ONE elected lane issues the tcgen05 instructions: with
+    // uniform control flow the operand descriptors and the loop state live in the uniform datapath. (With `if (lane == 0)`
+    // around the loop every UTCHMMA needed ~19 instructions of per-thread descriptor arithmetic and register -> uniform
+    // register waterfalls; that single instruction stream, ~200 per tile, was what the scan ran at once the SM clock dropped
+    // under the power cap.)
+    {
       const uint32_t idesc = umma_idesc_f16(kTileRows, (p.hi_only && NBLK == 1) ? ((QP + 15) / 16) * 16 : N);
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t b_addr = smem_u32(sB);
       uint32_t stage = 0, phase = 0, acc = 0, accphase = 0;
       int cur_g = -1, n_sw = -1;
@@ -660,10 +687,10 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         const long long u = it.u;
         if constexpr (BSW) {
           if (g != cur_g) {
-            if (n_sw >= 0) umma_commit(&bempty[n_sw & 1]);   // previous group's operand buffer is free once its MMAs retire
+            if (n_sw >= 0 && elect_one_sync()) umma_commit(&bempty[n_sw & 1]);   // previous group's operand buffer is free once its MMAs retire
+            __syncwarp();
             ++n_sw;
             mbar_wait(&bfull[n_sw & 1], (n_sw >> 1) & 1);
-            tc_fence_after_sync();
             b_addr = smem_u32(sB + (n_sw & 1) * Cfg::B_BYTES);
             cur_g = g;
           }
@@ -678,23 +705,26 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         for (int t = 0; t < ntiles; ++t) {
           mbar_wait(&tempty[acc], accphase ^ 1);
           mbar_wait(&full[stage], phase);
-          if constexpr (PACKED) mbar_arrive(&tfull[acc]);   // releases what this thread acquired: the tile's side data
-          tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(sA + stage * kTileBytes);
-          const uint32_t d_addr = tmem_base + acc * N;
+          const uint32_t d_addr = tbase + acc * N;
           // one descriptor per operand and tile; the eight K-steps only move the start-address field (16-byte units)
           const uint64_t ad0 = umma_desc_k_sw128(a_addr), bd0 = umma_desc_k_sw128(b_addr);
+          if (elect_one_sync()) {
+            if constexpr (PACKED) mbar_arrive(&tfull[acc]);   // releases what this thread acquired: the tile's side data
+            tc_fence_after_sync();
 #pragma unroll
-          for (int kh = 0; kh < 2; ++kh) {
+            for (int kh = 0; kh < 2; ++kh) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t ad = ad0 + static_cast<uint64_t>((kh * kHalfBytes + kk * 32) >> 4);
-              const uint64_t bd = bd0 + static_cast<uint64_t>((kh * (N * 128) + kk * 32) >> 4);
-              umma_f16_ss(d_addr, ad, bd, idesc, (kh | kk) != 0);
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t ad = ad0 + static_cast<uint64_t>((kh * kHalfBytes + kk * 32) >> 4);
+                const uint64_t bd = bd0 + static_cast<uint64_t>((kh * (N * 128) + kk * 32) >> 4);
+                umma_f16_ss(d_addr, ad, bd, idesc, (kh | kk) != 0);
+              }
             }
+            umma_commit(&empty[stage]);   // smem stage may be refilled once these MMAs retire
+            umma_commit(&tfull[acc]);     // accumulator ready for the epilogue
           }
-          umma_commit(&empty[stage]);   // smem stage may be refilled once these MMAs retire
-          umma_commit(&tfull[acc]);     // accumulator ready for the epilogue
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           if (++acc == ACC) { acc = 0; accphase ^= 1; }
         }
