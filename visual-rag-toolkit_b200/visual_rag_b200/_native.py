@@ -12,7 +12,8 @@ import os
 from typing import Optional
 
 _LIB_NAME = "libvrag_b200.so"
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+# VRAG_LIB: A/B experiments with another build of the same library (developer knob; the default is the in-tree build)
+_LIB_PATH = os.environ.get("VRAG_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 VRAG_F16 = 0
 VRAG_F32 = 1
