@@ -510,14 +510,86 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         // Slot mode (gathered pages, one slot per item): item -> candidate id -> page offsets is a chain of dependent
         // global loads (~2 us). The whole warp resolves 32 items at a time (lane l: item l of the batch), one batch
         // ahead of the tiles being issued, so the chain is off the TMA issue path.
-        const int per_tile = kTileRows / p.slot_rows;          // 4, 2 or 1 items per tile
-        const int tiles_per_batch = 32 / per_tile;
         // Producer warp pw takes the tiles pw, pw + PRODUCERS, ... of the CTA's range ("own" tiles, counted by k); tile i
         // uses stage i % STAGES whoever issues it, so the MMA thread still consumes the stages in order.
         // (a CTA's share of the tiles fits 32 bits: the per-tile index arithmetic below is on the single-warp critical path)
         const int pw = is_prod_b ? 1 : 0;
         const uint32_t n_tiles_cta = static_cast<uint32_t>(ur.count);
         const uint32_t n_own = n_tiles_cta > static_cast<uint32_t>(pw) ? (n_tiles_cta - pw + PRODUCERS - 1) / PRODUCERS : 0u;
+        if (p.slot_rows == kBoxRowsSmall) {
+          // ---- one page per 32-row slot, 4 slots per tile: the gather of small (pooled) pages. What bounds it is the
+          // producers' instruction stream, so the per-item work is split in two: all 32 lanes resolve and pre-compute one
+          // batch of 32 items (8 tiles) at a time — row, box map, byte count, side data — and publish the batch in shared
+          // memory; the tile loop then runs converged and ONE elected lane issues the tile's copies from four 16-byte reads.
+          // The dependent global loads (item -> candidate id -> page rows) are software-pipelined over the batches: ids two
+          // batches ahead, row ranges one batch ahead, so the in-order warp never waits for either.
+          int4* pbuf = reinterpret_cast<int4*>(misc + (MULTI ? 6656 : 4096)) + pw * 32;   // (free space between the segment tables and sThr)
+          auto batch_pages = [&](uint32_t k0) -> long long {
+            const long long i = pw + PRODUCERS * static_cast<long long>(k0 + (lane >> 2));
+            long long page = -1;
+            if (i < ur.count) {
+              int g;
+              long long u;
+              ur.decode(i, g, u);
+              const long long it = u * 4 + (lane & 3);
+              if (it < p.n_items) page = item_page(p, it, g);
+            }
+            return page;
+          };
+          long long r0_c, pg_n;
+          int nr_c;
+          resolve_page(p, batch_pages(0), r0_c, nr_c);
+          pg_n = batch_pages(8);
+          stage = static_cast<uint32_t>(pw) % STAGES;
+          phase = 0;
+          uint32_t me = static_cast<uint32_t>(pw);
+          for (uint32_t k0 = 0; k0 < n_own; k0 += 8) {
+            {
+              const int mi = (nr_c + kBoxStep - 1) / kBoxStep - 1;
+              int4 e;
+              e.x = static_cast<int32_t>(r0_c);                                   // first row (TMA coordinate)
+              e.y = nr_c > 0 ? (static_cast<int>(r0_c & 3) | (nr_c << 2)) : 0;    // side data: scale misalignment | rows << 2
+              e.z = mi * static_cast<int>(sizeof(CUtensorMap));                   // which box map
+              e.w = nr_c > 0 ? (mi + 1) * (kBoxStep * kDim * 2) + (use_scale ? kScaleBoxSmall * 4 : 0) : 0;   // bytes
+              pbuf[lane] = e;
+            }
+            __syncwarp();
+            resolve_page(p, pg_n, r0_c, nr_c);   // batch k0 + 8 (its ids were loaded one batch ago)
+            pg_n = batch_pages(k0 + 16);
+            const uint32_t nt = min(8u, n_own - k0);
+            for (uint32_t t = 0; t < nt; ++t) {
+              mbar_wait(&empty[stage], phase ^ 1);   // the whole warp (uniform)
+              if (elect_one_sync()) {
+                uint8_t* a = sA + stage * kTileBytes;
+                float* sc = sScale + me * kScaleStride;
+                uint32_t bytes = 0;
+                int misv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int4 e = pbuf[t * 4 + j];
+                  if (e.w > 0) {
+                    const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const char*>(&tm_small) + e.z);
+                    uint8_t* dst = a + j * (kBoxRowsSmall * 128);
+                    tma_load_2d(dst, tm, &full[stage], 0, e.x);
+                    tma_load_2d(dst + kHalfBytes, tm, &full[stage], 64, e.x);
+                    if (use_scale) tma_load_1d(sc + j * (kBoxRowsSmall + 32), &tm_scale32, &full[stage], e.x & ~3);
+                  }
+                  bytes += static_cast<uint32_t>(e.w);
+                  misv[j] = e.y;
+                }
+                *reinterpret_cast<int4*>(sMis + me * 4) = make_int4(misv[0], misv[1], misv[2], misv[3]);
+                mbar_arrive_expect_tx(&full[stage], bytes);   // same lane as the copies and the side-data store
+              }
+              __syncwarp();
+              stage += PRODUCERS;
+              if (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
+              me = (me + PRODUCERS) % META;
+            }
+          }
+        } else {
+        // ---- 64- / 128-row slots (2 or 1 items per tile): several boxes per item (issue_rows)
+        const int per_tile = kTileRows / p.slot_rows;
+        const int tiles_per_batch = 32 / per_tile;
         auto resolve_batch = [&](uint32_t k0, long long& r0, int& nr) {
           const long long i = pw + PRODUCERS * (k0 + lane / per_tile);
           r0 = 0;
@@ -532,8 +604,6 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         };
         long long cur_r0, nxt_r0;
         int cur_nr, nxt_nr;
-        UnitIter it;                       // lane 0: (group, unit) of the tile being issued (single producer + BSW only)
-        it.seek(ur, pw);
         resolve_batch(0, cur_r0, cur_nr);
         for (uint32_t k0 = 0; k0 < n_own; k0 += tiles_per_batch) {
           resolve_batch(k0 + tiles_per_batch, nxt_r0, nxt_nr);
@@ -542,41 +612,23 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
             const uint32_t i = pw + PRODUCERS * (k0 + t);          // tile index in the CTA's range
             stage = i % STAGES;
             phase = (i / STAGES) & 1u;
-            if constexpr (BSW && PRODUCERS == 1) {
-              switch_group(it.g);
-              it.advance(ur, 1);
-            }
             mbar_wait(&empty[stage], phase ^ 1);   // the whole warp (uniform)
             uint8_t* a = sA + stage * kTileBytes;
             const int me = static_cast<int>(i % META);          // side-data ring entry of this tile
             float* sc = sScale + me * kScaleStride;
-            // The tile's (up to 4) items are issued one after the other from warp-uniform values (their row ranges are
-            // broadcast from the lanes that resolved them): uniform operands keep every copy at a handful of instructions;
+            // The tile's items are issued one after the other from warp-uniform values (their row ranges are broadcast
+            // from the lanes that resolved them): uniform operands keep every copy at a handful of instructions;
             // per-lane operands cost a register -> uniform-register waterfall per copy.
             uint32_t bytes = 0;
             for (int j = 0; j < per_tile; ++j) {
               const int src = (t * per_tile + j) & 31;
               const long long r0 = __shfl_sync(0xffffffffu, cur_r0, src);
               const int nr = __shfl_sync(0xffffffffu, cur_nr, src);
-              const int mi = (nr + kBoxStep - 1) / kBoxStep - 1;   // slot_rows == 32: one box of 4 * (mi + 1) rows per K-half
-              const bool one_box = p.slot_rows == kBoxRowsSmall;
-              if (nr > 0)
-                bytes += one_box ? (mi + 1) * (kBoxStep * kDim * 2) + (use_scale ? kScaleBoxSmall * 4 : 0)
-                                 : issue_rows_bytes(nr, j * p.slot_rows, use_scale);
+              if (nr > 0) bytes += issue_rows_bytes(nr, j * p.slot_rows, use_scale);
               if (elect_one_sync()) {
-                if (nr > 0) {
-                  if (one_box) {
-                    const CUtensorMap* tm = &tm_small.m[mi];
-                    const int32_t r = static_cast<int32_t>(r0);
-                    uint8_t* dst = a + j * (kBoxRowsSmall * 128);
-                    tma_load_2d(dst, tm, &full[stage], 0, r);
-                    tma_load_2d(dst + kHalfBytes, tm, &full[stage], 64, r);
-                    if (use_scale) tma_load_1d(sc + j * (kBoxRowsSmall + 32), &tm_scale32, &full[stage], r & ~3);
-                  } else {
-                    issue_rows(a, sc + j * (p.slot_rows + 32), &full[stage], &tm_rows128, &tm_small, &tm_scale128, &tm_scale32, r0, nr,
-                               j * p.slot_rows, use_scale);
-                  }
-                }
+                if (nr > 0)
+                  issue_rows(a, sc + j * (p.slot_rows + 32), &full[stage], &tm_rows128, &tm_small, &tm_scale128, &tm_scale32, r0, nr,
+                             j * p.slot_rows, use_scale);
                 // low 2 bits: scale misalignment; rest: rows of the slot (0 for unused / empty slots)
                 sMis[me * 4 + j] = static_cast<int>(r0 & 3) | (nr << 2);
               }
@@ -590,6 +642,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           }
           cur_r0 = nxt_r0;
           cur_nr = nxt_nr;
+        }
         }
       }
     } else if (!is_prod_b) {
