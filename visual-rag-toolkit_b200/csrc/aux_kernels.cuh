@@ -89,8 +89,8 @@ __global__ void query_prep_batch_kernel(const float* __restrict__ q, const int* 
 
 // Dense batched scans: G = QP/QS queries share one operand image (blockIdx.y = image); image row r holds row
 // r % QS of query (image*G + r / QS), hi half at row r and lo half at row QP + r; absent rows/queries are zero.
-// two_block (QS == 32): the image holds 2 * QP / QS queries as PLAIN fp16 — blockIdx.z = 0 fills rows [0, QP) with queries
-// 0..3, blockIdx.z = 1 rows [QP, 2QP) with queries 4..7 — and eps_out[b] accumulates the bound the host's exactness guard
+// two_block (QS == 32): the image holds 2 * QP / QS queries as PLAIN fp16 — blockIdx.z = 0 writes queries 0..3, blockIdx.z = 1
+// queries 4..7; queries g and g + 4 share the 64 rows [64g, 64g + 64), interleaved in quads of token rows — and eps_out[b] accumulates the bound the host's exactness guard
 // needs for query b: sum over its rows of ||qhat - fp16(qhat)||_2 (the most a unit-norm document row can move that
 // row's cosine) + 2^-12 (the fp16 rounding of the row's running maximum in the first-pass epilogue).
 __global__ void query_prep_group_kernel(const float* __restrict__ q, const int* __restrict__ q_begin,
@@ -136,7 +136,10 @@ __global__ void query_prep_group_kernel(const float* __restrict__ q, const int* 
   const uint32_t rows = 2u * QP;
   uint8_t* img = qimg + blockIdx.y * qimg_stride;
   if (two_block) {
-    *reinterpret_cast<__half*>(img + sw128_offset(rows, blockIdx.z * QP + r, d)) = live ? hi : __float2half_rn(0.0f);
+    // the two query blocks of an epilogue group (queries g and g + 4: blockIdx.z = 0 / 1) are interleaved in quads of token
+    // columns inside the group's 64 accumulator columns: A[0:4] B[0:4] A[4:8] B[4:8] ... (maxsim_scan.cuh, first_pass_cols)
+    const uint32_t row2 = (r / QS) * 64u + (t / 4) * 8u + blockIdx.z * 4u + (t % 4);
+    *reinterpret_cast<__half*>(img + sw128_offset(rows, row2, d)) = live ? hi : __float2half_rn(0.0f);
     // rounding error of this row, for the guard
     float e = live ? (x - __half2float(hi)) : 0.0f;
     e *= e;

@@ -291,6 +291,66 @@ __device__ __forceinline__ void warp_transpose_max(float* v, int lane) {
   }
 }
 
+// Packed fp16 pairs are carried as plain 32-bit registers (arrays of them stay in registers under full unrolling).
+__device__ __forceinline__ uint32_t h2_max(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t h2_pack(float lo, float hi) {   // round-to-nearest-even, {lo -> bits 0-15, hi -> bits 16-31}
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+constexpr uint32_t kH2NegInf = 0xFC00FC00u;
+// The same butterfly over packed fp16 pairs: 16 pairs (32 columns) per lane. On return lane L holds, in v[0], the maxima
+// over all lanes of the column pair (L >> 1); half the shuffles and selects of the fp32 version.
+__device__ __forceinline__ void warp_transpose_max_h2x16(uint32_t (&v)[16], int lane) {
+  int cnt = 16;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    if (cnt > 1) {
+      const int half = cnt >> 1;
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < half) {
+          const uint32_t keep = upper ? v[j + half] : v[j];
+          const uint32_t send = upper ? v[j] : v[j + half];
+          v[j] = h2_max(keep, __shfl_xor_sync(0xffffffffu, send, off));
+        }
+      }
+      cnt = half;
+    } else {
+      v[0] = h2_max(v[0], __shfl_xor_sync(0xffffffffu, v[0], off));
+    }
+  }
+}
+__device__ __forceinline__ float h2_column_max(uint32_t v0, int lane) {
+  return __half2float(__ushort_as_half(static_cast<unsigned short>((lane & 1) ? (v0 >> 16) : (v0 & 0xFFFFu))));
+}
+
+// First (approximate) pass of a batched exhaustive scan. The operand image interleaves the two query blocks of an epilogue
+// group in quads of token columns — A[0:4] B[0:4] A[4:8] B[4:8] ... (query_prep_group_kernel, two_block) — so ONE TMEM load
+// of W columns starting at column 2*C of the group brings tokens [C, C + W/2) of both queries, and a pair of queries of 20
+// tokens reads exactly 40 columns. Values are scaled, rounded to fp16 pairs and folded into the running maxima.
+template <int C, int W>
+__device__ __forceinline__ void first_pass_cols(uint32_t tg, bool live, float scale, uint32_t (&runA)[16], uint32_t (&runB)[16]) {
+  uint32_t v[W];
+  tmem_ld<W>(tg + 2 * C, v);
+  tmem_ld_wait();
+  if (live) {
+#pragma unroll
+    for (int j = 0; j < W; j += 8) {   // one quad of each block
+      const int t = C + j / 2;
+      runA[t / 2] = h2_max(runA[t / 2], h2_pack(__uint_as_float(v[j]) * scale, __uint_as_float(v[j + 1]) * scale));
+      runA[t / 2 + 1] = h2_max(runA[t / 2 + 1], h2_pack(__uint_as_float(v[j + 2]) * scale, __uint_as_float(v[j + 3]) * scale));
+      runB[t / 2] = h2_max(runB[t / 2], h2_pack(__uint_as_float(v[j + 4]) * scale, __uint_as_float(v[j + 5]) * scale));
+      runB[t / 2 + 1] = h2_max(runB[t / 2 + 1], h2_pack(__uint_as_float(v[j + 6]) * scale, __uint_as_float(v[j + 7]) * scale));
+    }
+  }
+}
+
 // PACKED fast path: the SR (power of two <= 32) lanes of a slot hold QP values each (one tile row per lane).
 // Segmented transpose-max over the slot's lanes, then sum over q. Returns the slot's score in all of its lanes.
 template <int QP, int SR>
@@ -824,13 +884,15 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         // NBLK == 2: 64 running maxima per thread (two query blocks) would not fit the register file of an 18-warp CTA, so
         // this first, approximate pass keeps them as packed fp16 pairs: max commutes with the (monotone) rounding, i.e. each
         // per-token maximum carries one fp16 rounding (<= 2^-12 for |cos| <= 1), which the host's exactness guard accounts for
-        __half2 runA[NBLK == 2 ? QR / 2 : 1], runB[NBLK == 2 ? QR / 2 : 1];
+        uint32_t runA[16], runB[16];   // (dead, and removed by the compiler, in the other kernels)
 #pragma unroll
         for (int q = 0; q < (NBLK == 2 ? 1 : QR); ++q) run[q] = -INFINITY;
 #pragma unroll
-        for (int q = 0; q < (NBLK == 2 ? QR / 2 : 1); ++q) runA[q] = runB[q] = __float2half2_rn(-INFINITY);
+        for (int q = 0; q < 16; ++q) runA[q] = runB[q] = kH2NegInf;
         const int ncol = !MULTI ? QE : (QS == 32 ? ((q_valid + 7) & ~7) : ((min(32, max(0, p.n_sub - col0)) + 7) & ~7));
-        const int ncol2 = (q_valid2 + 7) & ~7;
+        const int ncol2 = (q_valid2 + 3) & ~3;
+        const int nmax = NBLK == 2 ? max((q_valid + 3) & ~3, ncol2) : 0;   // first pass: columns read per block (steps of 4)
+        (void)nmax;
         for (int t0 = 0; t0 < nrows; t0 += kTileRows) {
           const int valid = min(kTileRows, nrows - t0);
           mbar_wait(&tfull[acc], accphase);
@@ -845,31 +907,27 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           // kernels are bound by the TMEM read port (64 B/clk: a 128x256 fp32 accumulator takes 2048 clk to drain), so
           // they read only the columns that hold real query rows (ncol, a multiple of 8).
           constexpr int LW = (QE % 16 == 0 && !MULTI) ? 16 : 8;
+          // (a warp whose 32 rows all lie beyond the page's last row — three of four on the 6-row tail tile of a 1030-row
+          // page — skips the tile: the batched kernels are bound by the TMEM read port and the epilogue's instruction issue)
+          const bool warp_live = lg * 32 < valid;
           if constexpr (NBLK == 2) {
-            // two independent query blocks, both plain fp16: block A at columns [col0, col0+32), block B at QP + the same
-#pragma unroll
-            for (int c = 0; c < QE; c += 8) {
-              if (c >= ncol && c >= ncol2) break;
-              uint32_t a8[8], b8[8];
-              if (c < ncol) tmem_ld_x8(ta + c, a8);
-              if (c < ncol2) tmem_ld_x8(ta + QP + c, b8);
-              tmem_ld_wait();
-              if (trow < valid) {
-                if (c < ncol) {
-#pragma unroll
-                  for (int j = 0; j < 8; j += 2)
-                    runA[(c + j) / 2] = __hmax2(runA[(c + j) / 2], __floats2half2_rn(__uint_as_float(a8[j]) * scale,
-                                                                                   __uint_as_float(a8[j + 1]) * scale));
-                }
-                if (c < ncol2) {
-#pragma unroll
-                  for (int j = 0; j < 8; j += 2)
-                    runB[(c + j) / 2] = __hmax2(runB[(c + j) / 2], __floats2half2_rn(__uint_as_float(b8[j]) * scale,
-                                                                                   __uint_as_float(b8[j + 1]) * scale));
-                }
-              }
+            // two independent query blocks, both plain fp16: block A at columns [col0, col0+32), block B at QP + the same.
+            // Only the columns that hold query rows are read (in steps of 4); both blocks read the wider of the two widths —
+            // the operand rows beyond a query's length are zero and its sum ignores them.
+            if (warp_live && nmax > 0) {
+              const bool live = trow < valid;
+              const uint32_t tg = lane_addr + acc * N + grp * 64;   // the group's 64 interleaved columns
+              // tokens [8k, 8k+8) of both queries per round trip; the first four when the queries end there
+              if (nmax >= 8) first_pass_cols<0, 16>(tg, live, scale, runA, runB);
+              else first_pass_cols<0, 8>(tg, live, scale, runA, runB);
+              if (nmax >= 16) first_pass_cols<8, 16>(tg, live, scale, runA, runB);
+              else if (nmax > 8) first_pass_cols<8, 8>(tg, live, scale, runA, runB);
+              if (nmax >= 24) first_pass_cols<16, 16>(tg, live, scale, runA, runB);
+              else if (nmax > 16) first_pass_cols<16, 8>(tg, live, scale, runA, runB);
+              if (nmax >= 32) first_pass_cols<24, 16>(tg, live, scale, runA, runB);
+              else if (nmax > 24) first_pass_cols<24, 8>(tg, live, scale, runA, runB);
             }
-          } else {
+          } else if (warp_live) {
 #pragma unroll
           for (int c = 0; c < QE; c += LW) {
             if (MULTI && c >= ncol) break;
@@ -905,15 +963,8 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
         // page done: max across the 128 rows owned by the group's threads, then sum over q
         float* red = sRed + par * 4 * RS + col0;
         if constexpr (NBLK == 2) {
-          float v[32];
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float2 f = __half22float2(runA[q]);
-            v[2 * q] = f.x;
-            v[2 * q + 1] = f.y;
-          }
-          warp_transpose_max<32>(v, lane);
-          red[ew * RS + lane] = v[0];
+          warp_transpose_max_h2x16(runA, lane);
+          red[ew * RS + lane] = h2_column_max(runA[0], lane);
         } else {
 #pragma unroll
         for (int gq = 0; gq < QG; ++gq) {
@@ -955,15 +1006,8 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tm_rows128, const __grid_
           // second query block: same reduction through the other scratch buffer (the barrier above separates its writes
           // from the reads of the previous page that used it)
           float* red2 = sRed + par * 4 * RS + col0;
-          float v[32];
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float2 f = __half22float2(runB[q]);
-            v[2 * q] = f.x;
-            v[2 * q + 1] = f.y;
-          }
-          warp_transpose_max<32>(v, lane);
-          red2[ew * RS + lane] = v[0];
+          warp_transpose_max_h2x16(runB, lane);
+          red2[ew * RS + lane] = h2_column_max(runB[0], lane);
           named_bar_sync(bar_id, 128);
           if (ew == 0) {
             const float m = fmaxf(fmaxf(red2[lane], red2[RS + lane]), fmaxf(red2[2 * RS + lane], red2[3 * RS + lane]));

@@ -162,6 +162,18 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr));
+}
+template <int W>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[W]) {
+  static_assert(W == 4 || W == 8 || W == 16, "tcgen05.ld widths wrapped here: x4, x8, x16");
+  if constexpr (W == 4) tmem_ld_x4(taddr, v);
+  else if constexpr (W == 8) tmem_ld_x8(taddr, v);
+  else tmem_ld_x16(taddr, v);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // One lane of a converged warp (elect.sync): lets a warp run its control flow uniformly — so that the compiler keeps
