@@ -856,6 +856,7 @@ def run_extras(corpus, args, peak, kern_ms):
         corpus.drop_store(nm)
     # ---- cfg0: the reference's own CPU-runnable case, in full on both sides (ColSmol-shaped, exact top-10)
     out["cfg0_colsmol"] = run_cfg0(corpus, args, rng)
+    out["per_call_twins"] = run_per_call_twins(rng)
     # ---- cfg2
     n = args.cfg2_pages
     h = rng.integers(16, 33, size=n)
@@ -942,6 +943,40 @@ def run_extras(corpus, args, peak, kern_ms):
                                       "hbm_gbs_algorithmic": b / (ms * 1e-3) / 1e9, "frac_of_peak": b / (ms * 1e-3) / 1e9 / peak,
                                       "stores": "tile mean 13 + experimental 76 + 4-neighbour 13 + global 1, one pass"}
     return out
+
+
+def run_per_call_twins(rng):
+    """compute_maxsim_score / compute_maxsim_batch called per document (list) with HOST arrays, as the reference's client-side
+    callers do (two_stage.py:398-426): this build (pipelined host cast + upload + one scan) against the reference's own
+    numpy functions on the same inputs and host."""
+    from oracle import maxsim_oracle as MO
+    from visual_rag_b200.embedding import pooling as GP
+
+    q = rng.standard_normal((Q_TOKENS, 128)).astype(np.float32)
+    docs = [rng.standard_normal((768, 128)).astype(np.float32) for _ in range(256)]
+    ref_fn_b, ref_fn_s, kind = MO.maxsim_batch, MO.maxsim_score, "port (oracle/maxsim_oracle.py)"
+    if load_reference() is not None:
+        from visual_rag.embedding import pooling as RP   # baseline/_ref, unmodified
+
+        ref_fn_b, ref_fn_s, kind = RP.compute_maxsim_batch, RP.compute_maxsim_score, "reference (visual_rag/embedding/pooling.py, baseline/_ref)"
+
+    def best(fn, n):
+        ts = []
+        for _ in range(n):
+            t1 = time.perf_counter()
+            r = fn()
+            ts.append(time.perf_counter() - t1)
+        return float(np.median(ts)), r
+
+    GP.compute_maxsim_batch(q, docs[:8])   # scratch handle, pinned staging, worker pool
+    g_b, got = best(lambda: GP.compute_maxsim_batch(q, docs), 7)
+    c_b, want = best(lambda: ref_fn_b(q, docs), 3)
+    g_s, _ = best(lambda: GP.compute_maxsim_score(q, docs[0]), 200)
+    c_s, _ = best(lambda: ref_fn_s(q, docs[0]), 200)
+    rel = max(abs(a - b) / abs(b) for a, b in zip(got, want))
+    return {"workload": "compute_maxsim_batch(q, 256 fp32 documents x 768 tokens = 100.7 MB of host memory) and compute_maxsim_score(q, one of them); 20-token query",
+            "batch_ms": 1e3 * g_b, "batch_cpu_ms": 1e3 * c_b, "single_us": 1e6 * g_s, "single_cpu_us": 1e6 * c_s, "cpu_kind": kind,
+            "max_rel_score_diff_vs_cpu": rel, "note": "the documents are true fp32 (not fp16-representable): the deviation is the fp16 store cast"}
 
 
 def run_cfg0(corpus, args, rng):

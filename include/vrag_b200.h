@@ -120,6 +120,21 @@ int vrag_search(vrag_corpus_t* c, const char* name, const float* query, int n_qu
 int vrag_score(vrag_corpus_t* c, const char* name, const float* query, int n_query_rows, uint32_t flags,
                const int64_t* cand_ids, int64_t n_cand, float* out_scores);
 
+/* The per-call twins themselves — compute_maxsim_score(query, doc) (pooling.py:468-514) and
+ * compute_maxsim_batch(query, [docs]) (pooling.py:517-552) — over documents in ordinary HOST memory, one pointer per
+ * document (pages[i]: page_rows[i] x 128 values of `dtype`, contiguous; no concatenation needed): the host worker pool
+ * casts fp32 documents to the fp16 store dtype (numpy astype(float16), qdrant_indexer.py:423-441) into pinned staging
+ * chunks while the previous chunk is in flight, one scan scores them all. out_scores[i] = score of pages[i]; an empty
+ * page scores -inf (the reference raises on one). Uses a scratch store of the handle.                                   */
+int vrag_score_pages(vrag_corpus_t* c, const float* query, int n_query_rows, uint32_t flags, const void* const* pages,
+                     const int64_t* page_rows, int64_t n_pages, int dtype, float* out_scores);
+
+/* The ingest cast on the host (what vrag_store_add / vrag_store_append / vrag_score_pages apply to fp32 rows that
+ * arrive in host memory): dst[i] = fp16(src[i]), round to nearest even, bit-identical to numpy's astype(float16)
+ * (qdrant_indexer.py:423-441). threads <= 1: the calling thread; otherwise the library's worker pool. force_scalar != 0
+ * selects the portable conversion instead of F16C (both give the same bits). Needs no GPU.                            */
+int vrag_host_f32_to_f16(const float* src, uint16_t* dst, int64_t n, int threads, int force_scalar);
+
 /* ------------------------------------------------------------------ scoring: fused multi-stage
  * n_stages stages executed back to back on the device with ONE host synchronisation: stage s scores
  * store names[s] with flags[s], restricted to the survivors of stage s-1, and keeps ks[s] pages.

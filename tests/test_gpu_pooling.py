@@ -69,6 +69,36 @@ def test_maxsim_function_mirrors(maxsim_golden):
     assert GP.compute_maxsim_batch(q, []) == []
 
 
+def test_score_pages_pipelined_host_upload_matches_oracle_and_store_path():
+    """vrag_score_pages (the engine of compute_maxsim_score / _batch): documents handed over one pointer each, cast and
+    copied by the host worker pool through pinned staging chunks. Sized to span several chunks with ragged page lengths,
+    an empty page in the middle, true-fp32 and fp16 documents; scores must equal (bit for bit) those of a store built
+    from the concatenated rows, and the oracle on the fp16-cast documents within the score tolerance."""
+    from oracle import maxsim_oracle as MO
+    from visual_rag_b200.corpus import GpuCorpus
+
+    rng = np.random.default_rng(11)
+    lens = [int(v) for v in rng.integers(1, 1400, size=60)]
+    lens[17] = 0
+    lens += [20000, 3, 128, 129]                       # one page larger than a 2M-value staging chunk
+    q = rng.standard_normal((23, 128)).astype(np.float32)
+    for dt in (np.float32, np.float16):
+        docs = [(rng.standard_normal((n, 128)) * 0.7).astype(dt) for n in lens]
+        with GpuCorpus(0) as c:
+            got = c.score_pages(q, docs)
+            rows = np.concatenate(docs, axis=0)
+            c.add_store("cat", rows, page_offsets=np.concatenate([[0], np.cumsum(lens)]))
+            via_store = c.score("cat", q)
+            # the rows the device holds are numpy's astype(float16) of the inputs
+            back = c.read_rows("cat", 0, rows.shape[0])
+            assert np.array_equal(back.view(np.uint16), rows.astype(np.float16).view(np.uint16))
+        assert np.array_equal(got.view(np.uint32), via_store.view(np.uint32))
+        assert got[17] == -np.inf
+        for i in (0, 5, 33, 60, 63):
+            want = MO.maxsim_score(q, docs[i].astype(np.float16).astype(np.float32))
+            assert abs(got[i] - want) <= 2e-5 * abs(want), (i, got[i], want)
+
+
 def test_error_behaviour_matches_reference():
     from visual_rag_b200.embedding import pooling as GP
 

@@ -367,3 +367,52 @@ def test_indexer_upsert_host_logic():
     assert ("compact", "initial") in c.log
     assert idx.create_collection() is False and idx.create_collection(force_recreate=True) and not c.stores
     assert idx.client._ids == []
+
+
+# ------------------------------------------------------------------ host-side ingest cast (qdrant_indexer.py:423-441)
+def _cast_with_library(x: np.ndarray, threads: int, force_scalar: bool) -> np.ndarray:
+    import ctypes as C
+
+    from visual_rag_b200 import _native
+
+    lib = _native.load()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty(x.shape, dtype=np.uint16)
+    rc = lib.vrag_host_f32_to_f16(x.ctypes.data_as(C.POINTER(C.c_float)), out.ctypes.data_as(C.POINTER(C.c_uint16)), x.size,
+                                  threads, int(force_scalar))
+    assert rc == 0
+    return out
+
+
+@pytest.mark.parametrize("force_scalar", [False, True], ids=["f16c", "scalar"])
+@pytest.mark.parametrize("threads", [1, 4])
+def test_host_ingest_cast_is_numpy_astype_float16_bit_for_bit(force_scalar, threads):
+    """The cast the library applies to fp32 rows arriving in host memory equals numpy's astype(float16) — what
+    QdrantIndexer._build_qdrant_points stores — on every class of value: random bit patterns (all exponents), exact ties,
+    fp16 denormals, the overflow boundary, signed zeros and infinities."""
+    rng = np.random.default_rng(7)
+    bits = rng.integers(0, 2**32, size=1 << 19, dtype=np.uint64).astype(np.uint32)
+    vals = bits.view(np.float32)
+    vals = vals[~np.isnan(vals)]
+    # every fp16 value, the midpoints between neighbours (ties) and their fp32 neighbours
+    h = np.arange(0, 0x7C00, dtype=np.uint16).view(np.float16).astype(np.float32)
+    mid = (h[:-1] + h[1:]) * 0.5
+    ties = np.concatenate([mid, np.nextafter(mid, np.float32(np.inf)), np.nextafter(mid, np.float32(-np.inf))])
+    edge = np.array([0.0, -0.0, np.inf, -np.inf, 65504.0, 65519.99, 65520.0, 65536.0, 1e30, 2.0**-24, 2.0**-25,
+                     np.nextafter(np.float32(2.0**-25), np.float32(1)), 2.0**-26, 6.1e-5, 5.96e-8, 1e-45], dtype=np.float32)
+    x = np.concatenate([vals, h, -h, ties, -ties, edge, -edge,
+                        rng.standard_normal(300_000).astype(np.float32)]).astype(np.float32)
+    got = _cast_with_library(x, threads, force_scalar)
+    with np.errstate(over="ignore"):
+        want = x.astype(np.float16).view(np.uint16)
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, (x[bad[:5]], got[bad[:5]], want[bad[:5]])
+
+
+def test_host_ingest_cast_handles_odd_lengths_and_empty():
+    rng = np.random.default_rng(1)
+    for n in (0, 1, 7, 8, 9, 15, 17, 1000003):
+        x = rng.standard_normal(n).astype(np.float32) * 3
+        for threads in (1, 8):
+            got = _cast_with_library(x, threads, False)
+            assert np.array_equal(got, x.astype(np.float16).view(np.uint16))

@@ -14,6 +14,7 @@
 
 #include "../../include/vrag_b200.h"
 #include "aux_kernels.cuh"
+#include "host_convert.h"
 #include "scan_launch.h"
 #include "pooling_kernels.cuh"
 
@@ -256,7 +257,6 @@ struct vrag_corpus {
   DevBuf<float> d_sthr;           // sampled top-k: threshold [1]
   DevBuf<int> d_sstate;           // sampled top-k: [0] survivor count, [1] "estimate failed" flag
   int sampled_runs = 0, sampled_fallbacks = 0;
-  DevBuf<float> d_stage_f32;      // fp32 -> fp16 ingest cast: staging for small uploads
   DevBuf<float> d_scores_part;    // partial page scores of the later row chunks of a > 128-token query
   DevBuf<uint8_t> d_qimg;
   DevBuf<unsigned long long> d_keys_a, d_keys_b;
@@ -287,6 +287,8 @@ struct vrag_corpus {
   int* h_counts = nullptr;
   size_t h_out_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+  uint16_t* h_up = nullptr;       // pinned staging of host uploads: two chunks of kUploadChunk fp16 values, filled by the
+  cudaEvent_t ev_up[2] = {nullptr, nullptr};   //   host worker pool while the other one is on its way (upload_host_pages)
   float last_ms[2] = {0, 0};
   int64_t launches = 0;
   bool attrs_set = false;
@@ -359,7 +361,6 @@ extern "C" int vrag_corpus_destroy(vrag_corpus_t* c) {
   c->d_scores.release();
   c->d_out_scores.release();
   c->d_scores_part.release();
-  c->d_stage_f32.release();
   c->d_skeys.release();
   c->d_sthr.release();
   c->d_sstate.release();
@@ -393,6 +394,9 @@ extern "C" int vrag_corpus_destroy(vrag_corpus_t* c) {
   if (c->h_out_scores) cudaFreeHost(c->h_out_scores);
   if (c->h_out_ids) cudaFreeHost(c->h_out_ids);
   if (c->h_counts) cudaFreeHost(c->h_counts);
+  if (c->h_up) cudaFreeHost(c->h_up);
+  for (int i = 0; i < 2; ++i)
+    if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   cudaEventDestroy(c->evk0);
@@ -544,46 +548,78 @@ static int alloc_store(vrag_corpus* c, const char* name, int64_t total_rows, Sto
   return 0;
 }
 
+// Host rows -> fp16 rows on the device, pipelined: the pages (each a contiguous [rows][128] block of fp32 or fp16 in
+// ordinary host memory) are treated as one stream of values, cut into chunks of kUploadChunk; the host worker pool casts
+// (numpy's astype(float16): round to nearest even) or copies a chunk into one of two pinned staging buffers while the DMA
+// engine still moves the previous one. Half the PCIe bytes of an fp32 upload, no device staging buffer, no cast kernel,
+// and the caller need not concatenate its documents. Enqueues on c->stream; does not synchronise at the end.
+static const size_t kUploadChunk = size_t(2) << 20;   // values per staging buffer (4 MB of fp16)
+static int upload_host_pages(vrag_corpus* c, __half* dst, const void* const* pages, const int64_t* page_rows, int64_t n_pages,
+                             int dtype) {
+  std::vector<size_t> pre(static_cast<size_t>(n_pages) + 1, 0);   // value offset of every page in the stream
+  for (int64_t i = 0; i < n_pages; ++i) pre[i + 1] = pre[i] + static_cast<size_t>(page_rows[i]) * 128;
+  const size_t n_el = pre[n_pages];
+  if (n_el == 0) return 0;
+  if (!c->h_up) {
+    CUDA_OK(cudaMallocHost(&c->h_up, 2 * kUploadChunk * sizeof(uint16_t)));
+    for (int i = 0; i < 2; ++i) CUDA_OK(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
+  }
+  const size_t esz = dtype == VRAG_F32 ? 4 : 2;
+  // values [e0, e1) of the stream -> out
+  auto fill = [&](size_t e0, size_t e1, uint16_t* out) {
+    size_t pg = static_cast<size_t>(std::upper_bound(pre.begin(), pre.end(), e0) - pre.begin()) - 1;
+    while (e0 < e1) {
+      const size_t n = std::min(e1, pre[pg + 1]) - e0;
+      if (n > 0) {
+        const char* src = static_cast<const char*>(pages[pg]) + (e0 - pre[pg]) * esz;
+        if (dtype == VRAG_F32) vrag::host_f32_to_f16(reinterpret_cast<const float*>(src), out, n);
+        else memcpy(out, src, n * 2);
+        out += n;
+        e0 += n;
+      }
+      ++pg;
+    }
+  };
+  const int threads = vrag::host_pool_threads();
+  int k = 0;
+  for (size_t e0 = 0; e0 < n_el; e0 += kUploadChunk, ++k) {
+    const size_t e1 = std::min(n_el, e0 + kUploadChunk);
+    const int b = k & 1;
+    uint16_t* buf = c->h_up + b * kUploadChunk;
+    CUDA_OK(cudaEventSynchronize(c->ev_up[b]));   // the copy that last read this buffer (this call or an earlier one)
+    const size_t n = e1 - e0;
+    const int tasks = static_cast<int>(std::min<size_t>(threads, (n + 65535) / 65536));   // >= 64k values per task
+    if (tasks <= 1) {
+      fill(e0, e1, buf);
+    } else {
+      const size_t per = ((n + tasks - 1) / tasks + 15) & ~size_t(15);
+      vrag::host_parallel_for(tasks, [&](int t) {
+        const size_t a = e0 + std::min(n, per * t), z = e0 + std::min(n, per * (t + 1));
+        if (a < z) fill(a, z, buf + (a - e0));
+      });
+    }
+    CUDA_OK(cudaMemcpyAsync(dst + e0, buf, n * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaEventRecord(c->ev_up[b], c->stream));
+  }
+  return 0;
+}
+
 // rows (host or device, fp16 or fp32) -> fp16 rows at dst + their inverse norms. fp32 is cast exactly like
 // QdrantIndexer._build_qdrant_points (qdrant_indexer.py:423-441).
 static int upload_rows(vrag_corpus* c, __half* dst, float* dst_inv, const void* rows, int dtype, int rows_on_device,
                        int64_t n_rows) {
   const size_t n_el = static_cast<size_t>(n_rows) * 128;
-  const cudaMemcpyKind kind = rows_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  if (dtype == VRAG_F16) {
+  if (!rows_on_device) {
+    const void* pages[1] = {rows};
+    const int64_t prow[1] = {n_rows};
+    TRY(upload_host_pages(c, dst, pages, prow, 1, dtype));
+  } else if (dtype == VRAG_F16) {
     // all copies go through the library stream: the kernels below run on it (a non-blocking stream does not
     // order against the legacy default stream a plain cudaMemcpy uses)
-    CUDA_OK(cudaMemcpyAsync(dst, rows, n_el * sizeof(__half), kind, c->stream));
+    CUDA_OK(cudaMemcpyAsync(dst, rows, n_el * sizeof(__half), cudaMemcpyDeviceToDevice, c->stream));
   } else {
-    const size_t chunk = size_t(32) << 20;  // elements per staging chunk
-    float* tmp = nullptr;
-    const float* src_base = static_cast<const float*>(rows);
-    const bool small = !rows_on_device && n_el <= (size_t(1) << 22);   // <= 16 MB: the handle's persistent staging buffer
-    if (small) {
-      TRY(c->d_stage_f32.ensure(n_el));
-      tmp = c->d_stage_f32.p;
-    } else if (!rows_on_device) {
-      CUDA_OK(cudaMalloc(&tmp, std::min(chunk, n_el) * sizeof(float)));
-    }
-    for (size_t o = 0; o < n_el; o += chunk) {
-      const size_t n = std::min(chunk, n_el - o);
-      const float* src = src_base + o;
-      cudaError_t e = cudaSuccess;
-      if (!rows_on_device) {
-        e = cudaMemcpyAsync(tmp, src, n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
-        src = tmp;
-      }
-      if (e == cudaSuccess) {
-        f32_to_f16_kernel<<<static_cast<unsigned>((n / 4 + 256) / 256), 256, 0, c->stream>>>(src, n, dst + o);
-        c->launches++;
-        e = cudaStreamSynchronize(c->stream);
-      }
-      if (e != cudaSuccess) {
-        if (tmp && !small) cudaFree(tmp);
-        return fail("fp32 -> fp16 store cast failed: %s", cudaGetErrorString(e));
-      }
-    }
-    if (tmp && !small) cudaFree(tmp);
+    f32_to_f16_kernel<<<static_cast<unsigned>((n_el / 4 + 256) / 256), 256, 0, c->stream>>>(static_cast<const float*>(rows), n_el, dst);
+    c->launches++;
   }
   const long long threads = n_rows * 16;
   inv_norm_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, c->stream>>>(dst, n_rows, dst_inv);
@@ -1592,6 +1628,59 @@ extern "C" int vrag_score(vrag_corpus_t* c, const char* name, const float* query
   cudaEventElapsedTime(&c->last_ms[0], c->ev0, c->ev1);
   cudaEventElapsedTime(&c->last_ms[1], c->evk0, c->evk1);
   return 0;
+}
+
+extern "C" int vrag_host_f32_to_f16(const float* src, uint16_t* dst, int64_t n, int threads, int force_scalar) {
+  if (n < 0 || (n > 0 && (!src || !dst))) return fail("bad arguments");
+  if (threads <= 1 || n < (1 << 17)) {
+    vrag::host_f32_to_f16(src, dst, static_cast<size_t>(n), force_scalar != 0);
+    return 0;
+  }
+  const int tasks = std::min<int64_t>(threads, (n + 65535) / 65536);
+  const int64_t per = ((n + tasks - 1) / tasks + 15) & ~int64_t(15);
+  vrag::host_parallel_for(tasks, [&](int t) {
+    const int64_t a = std::min<int64_t>(n, per * t), z = std::min<int64_t>(n, per * (t + 1));
+    if (a < z) vrag::host_f32_to_f16(src + a, dst + a, static_cast<size_t>(z - a), force_scalar != 0);
+  });
+  return 0;
+}
+
+// MaxSim of one query against documents that live in ordinary host memory, one pointer per document: the per-call twins
+// of the reference (compute_maxsim_score / compute_maxsim_batch, pooling.py:468-552). The documents go through the
+// pipelined host upload into a scratch store of the handle (buffers kept between calls) and are scored by one scan.
+extern "C" int vrag_score_pages(vrag_corpus_t* c, const float* query, int n_query_rows, uint32_t flags,
+                                const void* const* pages, const int64_t* page_rows, int64_t n_pages, int dtype,
+                                float* out_scores) {
+  VRAG_LOCK(c);
+  if (!c) return fail("corpus is NULL");
+  TRY(set_device(c));
+  if (dtype != VRAG_F16 && dtype != VRAG_F32) return fail("unknown dtype %d", dtype);
+  if (n_pages < 0) return fail("n_pages < 0");
+  if (n_pages == 0) return 0;
+  if (!pages || !page_rows || !out_scores) return fail("NULL argument");
+  std::vector<int64_t> offs(static_cast<size_t>(n_pages) + 1, 0);
+  for (int64_t i = 0; i < n_pages; ++i) {
+    if (page_rows[i] < 0) return fail("page %lld has a negative row count", (long long)i);
+    if (page_rows[i] > 0 && !pages[i]) return fail("page %lld is NULL", (long long)i);
+    offs[i + 1] = offs[i] + page_rows[i];
+  }
+  int64_t total_rows = 0;
+  TRY(check_layout(offs.data(), n_pages, 0, &total_rows));
+  static const char* kScratch = "__score_pages__";
+  Store* s = nullptr;
+  TRY(alloc_store(c, kScratch, total_rows, &s));
+  if (total_rows > 0) {
+    TRY(upload_host_pages(c, s->rows, pages, page_rows, n_pages, dtype));
+    const long long threads = total_rows * 16;
+    inv_norm_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, c->stream>>>(s->rows, total_rows, s->inv);
+    c->launches++;
+  }
+  // equal row counts (always so for a single document): the fixed-rows layout needs no offset table on the device
+  bool uniform = page_rows[0] > 0;
+  for (int64_t i = 1; i < n_pages && uniform; ++i) uniform = page_rows[i] == page_rows[0];
+  if (uniform) TRY(finish_store(c, *s, nullptr, n_pages, page_rows[0]));
+  else TRY(finish_store(c, *s, offs.data(), n_pages, 0));
+  return vrag_score(c, kScratch, query, n_query_rows, flags, nullptr, 0, out_scores);
 }
 
 // Scores of candidates when this shard's store has no rows at all: every candidate is foreign -> -inf.

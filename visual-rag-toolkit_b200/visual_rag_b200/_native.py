@@ -82,6 +82,8 @@ SIGNATURES = {
     "vrag_store_drop": (C.c_int, [C.c_void_p, C.c_char_p]),
     "vrag_search": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int, C.c_uint32, _i64p, C.c_int64, C.c_int, _f32p, _i64p, _i32p]),
     "vrag_score": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int, C.c_uint32, _i64p, C.c_int64, _f32p]),
+    "vrag_score_pages": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_uint32, C.POINTER(C.c_void_p), _i64p, C.c_int64, C.c_int, _f32p]),
+    "vrag_host_f32_to_f16": (C.c_int, [_f32p, C.POINTER(C.c_uint16), C.c_int64, C.c_int, C.c_int]),
     "vrag_search_multistage": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _u32p, _i32p, _f32p, C.c_int, _i32p, _i64p, C.c_int64, _f32p, _i64p, _i32p]),
     "vrag_filter_create": (C.c_int, [C.c_void_p, _u32p, C.c_int64, _i32p]),
     "vrag_filter_destroy": (C.c_int, [C.c_void_p, C.c_int]),

@@ -609,6 +609,32 @@ class GpuCorpus:
         return out[: got.value]
 
     # ------------------------------------------------------------------ device-pointer variants (multi-GPU path)
+    def score_pages(self, query, pages: Sequence[np.ndarray], normalize: bool = True) -> np.ndarray:
+        """MaxSim of one query against documents in host memory (compute_maxsim_score / compute_maxsim_batch,
+        pooling.py:468-552): one [rows, 128] fp16 or fp32 array per document, handed over by pointer — no concatenation;
+        the library casts / copies them into pinned staging with its worker pool while the previous chunk is in flight.
+        fp32 [len(pages)]; an empty document scores -inf."""
+        q = _as_f32_query(query)
+        mats = [np.ascontiguousarray(m) for m in pages]
+        n = len(mats)
+        out = np.empty((n,), dtype=np.float32)
+        if n == 0:
+            return out
+        dt = np.float16 if all(m.dtype == np.float16 for m in mats) else np.float32
+        mats = [m if m.dtype == dt else m.astype(dt) for m in mats]
+        for m in mats:
+            if m.ndim != 2 or m.shape[1] != 128:
+                raise ValueError(f"documents must be [rows, 128] arrays, got {m.shape}")
+        ptrs = (C.c_void_p * n)(*[m.ctypes.data for m in mats])
+        rows = (C.c_int64 * n)(*[int(m.shape[0]) for m in mats])
+        N.check(
+            self._lib.vrag_score_pages(
+                self._h, q.ctypes.data_as(C.POINTER(C.c_float)), q.shape[0], query_flags(normalize, False, False), ptrs, rows, n,
+                N.VRAG_F16 if dt == np.float16 else N.VRAG_F32, out.ctypes.data_as(C.POINTER(C.c_float)),
+            )
+        )
+        return out
+
     def score_dev(self, name: str, query_dev_ptr: int, n_query_rows: int, flags: int, cand_dev_ptr: int,
                   n_cand: int, out_scores_dev_ptr: int, stream: int) -> None:
         N.check(

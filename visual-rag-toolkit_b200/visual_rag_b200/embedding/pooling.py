@@ -301,13 +301,9 @@ def _scratch_corpus():
 
 def _page_scores(query_embedding, docs: Sequence[np.ndarray], normalize: bool) -> List[float]:
     mats = [_to_host_rows(d) for d in docs]
-    lens = [int(m.shape[0]) for m in mats]
-    rows = mats[0] if len(mats) == 1 else np.concatenate(mats, axis=0)
     q = np.asarray(query_embedding, dtype=np.float32)
     with _scratch_lock:
-        c = _scratch_corpus()
-        c.add_store("docs", rows, page_offsets=np.concatenate([[0], np.cumsum(lens)]))
-        return [float(s) for s in c.score("docs", q, normalize=normalize)]
+        return _scratch_corpus().score_pages(q, mats, normalize=normalize).tolist()
 
 
 def compute_maxsim_score(query_embedding: np.ndarray, doc_embedding: np.ndarray, normalize: bool = True) -> float:
