@@ -20,6 +20,7 @@ large large maxsim_scan 2
 packed packed maxsim_scan 2
 global global maxsim_scan 2
 large_batch large_batch maxsim_scan 2
+large_batch8 large_batch8 maxsim_scan 2
 packed_batch packed_batch maxsim_scan 5
 global_batch global_batch maxsim_scan 5
 cfg2_gather cfg2 maxsim_scan 10
