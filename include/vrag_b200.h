@@ -100,6 +100,9 @@ int vrag_store_info(vrag_corpus_t* c, const char* name, int64_t* n_pages, int64_
  * two_stage.py:383-390) */
 int vrag_store_read_rows(vrag_corpus_t* c, const char* name, int64_t row0, int64_t n_rows, void* out_f16_host);
 int vrag_store_page_range(vrag_corpus_t* c, const char* name, int64_t local_page, int64_t* row0, int64_t* n_rows);
+/* Row counts of pages [first_page, first_page + n) in one call (the token counts the bulk re-pooling script reads point by
+ * point to infer each page's patch grid, scripts/qdrant_recompute_colqwen_pooling_from_initial.py:292-300). */
+int vrag_store_page_rows(vrag_corpus_t* c, const char* name, int64_t first_page, int64_t n, int64_t* out_rows);
 int vrag_store_drop(vrag_corpus_t* c, const char* name);
 
 /* ------------------------------------------------------------------ scoring: one stage

@@ -99,6 +99,23 @@ def test_score_pages_pipelined_host_upload_matches_oracle_and_store_path():
             assert abs(got[i] - want) <= 2e-5 * abs(want), (i, got[i], want)
 
 
+def test_page_rows_in_one_call_for_every_layout():
+    from visual_rag_b200.corpus import GpuCorpus
+
+    rng = np.random.default_rng(5)
+    lens = [int(v) for v in rng.integers(0, 300, size=40)]
+    rows = rng.standard_normal((sum(lens), 128)).astype(np.float16)
+    with GpuCorpus(0) as c:
+        c.add_store("var", rows, page_offsets=np.concatenate([[0], np.cumsum(lens)]))
+        assert c.page_rows("var").tolist() == lens
+        c.add_store("fix", rows[: 13 * 20], fixed_rows=13)
+        assert c.page_rows("fix").tolist() == [13] * 20
+        c.delete_pages("var", [3, 7])               # page table
+        want = list(lens)
+        want[3] = want[7] = 0
+        assert c.page_rows("var").tolist() == want
+
+
 def test_error_behaviour_matches_reference():
     from visual_rag_b200.embedding import pooling as GP
 

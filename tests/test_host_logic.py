@@ -416,3 +416,32 @@ def test_host_ingest_cast_handles_odd_lengths_and_empty():
         for threads in (1, 8):
             got = _cast_with_library(x, threads, False)
             assert np.array_equal(got, x.astype(np.float16).view(np.uint16))
+
+
+def test_infer_grids_vectorised_equals_per_page_inference():
+    """repool.infer_grids (one infer_grid per distinct (tokens, width, height), scattered back) == infer_grid per page,
+    with and without payload sizes, including pages whose payload lacks a usable size."""
+    from visual_rag_b200.embedding.repool import _payload_size, infer_grid, infer_grids
+
+    rng = np.random.default_rng(3)
+    tokens = rng.integers(1, 769, size=500)
+    payloads = []
+    for i in range(500):
+        kind = i % 4
+        if kind == 0:
+            payloads.append({"resized_width": int(rng.integers(200, 1200)), "resized_height": int(rng.integers(200, 1200))})
+        elif kind == 1:
+            payloads.append({"original_width": 800, "original_height": 600, "cropped_width": 640, "cropped_height": 640})
+        elif kind == 2:
+            payloads.append(None)
+        else:
+            payloads.append({"resized_width": "bad"})
+    got = infer_grids(tokens, payloads)
+    assert got.shape == (500, 2) and got.dtype == np.int32
+    for p in range(500):
+        w, h = _payload_size(payloads[p])
+        assert tuple(got[p]) == infer_grid(int(tokens[p]), width=w, height=h)
+        assert int(got[p, 0]) * int(got[p, 1]) == int(tokens[p])
+    no_payload = infer_grids(tokens)
+    for p in range(0, 500, 17):
+        assert tuple(no_payload[p]) == infer_grid(int(tokens[p]))

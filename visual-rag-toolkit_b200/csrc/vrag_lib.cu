@@ -970,6 +970,19 @@ extern "C" int vrag_store_page_range(vrag_corpus_t* c, const char* name, int64_t
   return 0;
 }
 
+extern "C" int vrag_store_page_rows(vrag_corpus_t* c, const char* name, int64_t first_page, int64_t n, int64_t* out_rows) {
+  VRAG_LOCK(c);
+  Store* s;
+  TRY(find_store(c, name, &s));
+  if (first_page < 0 || n < 0 || first_page + n > s->n_pages) return fail("pages [%lld, %lld) out of range", (long long)first_page, (long long)(first_page + n));
+  if (n > 0 && !out_rows) return fail("out_rows is NULL");
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t r0;
+    page_rows_h(*s, first_page + i, &r0, out_rows + i);
+  }
+  return 0;
+}
+
 extern "C" int vrag_store_read_rows(vrag_corpus_t* c, const char* name, int64_t row0, int64_t n_rows,
                                     void* out_f16_host) {
   VRAG_LOCK(c);

@@ -79,6 +79,7 @@ SIGNATURES = {
     "vrag_store_info": (C.c_int, [C.c_void_p, C.c_char_p, _i64p, _i64p, _i64p, _i64p]),
     "vrag_store_read_rows": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64, C.c_void_p]),
     "vrag_store_page_range": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, _i64p, _i64p]),
+    "vrag_store_page_rows": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64, _i64p]),
     "vrag_store_drop": (C.c_int, [C.c_void_p, C.c_char_p]),
     "vrag_search": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int, C.c_uint32, _i64p, C.c_int64, C.c_int, _f32p, _i64p, _i32p]),
     "vrag_score": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int, C.c_uint32, _i64p, C.c_int64, _f32p]),

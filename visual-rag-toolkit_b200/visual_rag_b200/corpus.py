@@ -315,6 +315,13 @@ class GpuCorpus:
         N.check(self._lib.vrag_store_page_range(self._h, name.encode(), int(local_page), C.byref(r0), C.byref(n)))
         return r0.value, n.value
 
+    def page_rows(self, name: str) -> np.ndarray:
+        """Row (token) count of every page of the store, int64 [n_pages] — one call."""
+        n = self.n_pages(name)
+        out = np.empty((n,), dtype=np.int64)
+        N.check(self._lib.vrag_store_page_rows(self._h, name.encode(), 0, n, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
     def read_page(self, name: str, local_page: int) -> np.ndarray:
         """fp16 rows of one page ([rows,128]) — what qdrant `retrieve(with_vectors=[name])` returns
         (two_stage.py:383-400)."""

@@ -55,22 +55,37 @@ def _payload_size(payload: Optional[Dict[str, Any]]):
         return None, None
 
 
+def infer_grids(tokens: np.ndarray, payloads: Optional[Sequence[Optional[dict]]] = None) -> np.ndarray:
+    """Per-page patch grids [n, 2] (rows, cols) for a whole collection: `infer_grid` evaluated once per DISTINCT
+    (token count, width, height) — a collection has a few hundred of them — and scattered back."""
+    tokens = np.asarray(tokens, dtype=np.int64)
+    n = tokens.shape[0]
+    sizes = np.zeros((n, 2), dtype=np.int64)          # 0 = unknown
+    if payloads is not None:
+        for p in range(n):
+            w, h = _payload_size(payloads[p])
+            if w and h:
+                sizes[p] = (w, h)
+    keys = np.concatenate([tokens[:, None], sizes], axis=1)
+    uniq, inverse = np.unique(keys, axis=0, return_inverse=True)
+    table = np.array([infer_grid(int(t), width=int(w) or None, height=int(h) or None) for t, w, h in uniq], dtype=np.int32)
+    return table.reshape(-1, 2)[np.asarray(inverse).reshape(-1)]
+
+
 def recompute_pooling_from_initial(corpus, payloads: Optional[Sequence[Optional[dict]]] = None, *,
-                                   max_mean_pool_vectors: int = 32, src: str = "initial") -> Dict[str, float]:
+                                   max_mean_pool_vectors: int = 32, src: str = "initial",
+                                   grids: Optional[np.ndarray] = None) -> Dict[str, float]:
     """Rebuild mean_pooling / experimental_pooling(_gaussian,_triangular) / global_pooling of every page of `corpus`
-    from store `src`. payloads: per-page payload dicts (image sizes) or None. Returns {"ms": device time,
-    "pages": n}. Raises ValueError for empty pages (the script skips points without vectors)."""
+    from store `src`. payloads: per-page payload dicts (image sizes) or None; grids: per-page (rows, cols) when the caller
+    already knows them (skips the inference). Returns {"ms": device time, "pages": n}. Raises ValueError for empty pages
+    (the script skips points without vectors)."""
     n = corpus.n_pages(src)
-    grids = np.empty((n, 2), dtype=np.int32)
-    cache: Dict[Tuple[int, Optional[int], Optional[int]], Tuple[int, int]] = {}
-    for p in range(n):
-        _, t = corpus.page_range(src, p)
-        w, h = _payload_size(payloads[p] if payloads is not None else None)
-        key = (t, w, h)
-        g = cache.get(key)
-        if g is None:
-            g = cache[key] = infer_grid(t, width=w, height=h)
-        grids[p] = g
+    if grids is None:
+        tokens = corpus.page_rows(src)
+        if n and int(tokens.min()) <= 0:
+            raise ValueError("num_tokens must be > 0")
+        grids = infer_grids(tokens, payloads)
+    grids = np.ascontiguousarray(np.asarray(grids, dtype=np.int32).reshape(-1, 2))
     cap = int(max_mean_pool_vectors)
     parent = GP.spec_adaptive_rows(0, 0, cap if cap > 0 else 0, clamp_to_h=True)
     parent.derive_from_f32 = 1
