@@ -103,6 +103,18 @@ elif what == "pool_fused":
     for _ in range(reps):
         ms = c.pool_store("vis", specs, ["mean_pooling", "e1", "e2", "e3", "g"])
     print("pool_fused", ms)
+elif what == "pool_qwen":
+    # cfg4 ColQwen2.5: bulk re-pooling of variable-grid pages from `initial` (adaptive rows + gaussian x2 + triangular + global)
+    from visual_rag_b200.embedding.repool import recompute_pooling_from_initial
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 400_000
+    h = rng.integers(16, 33, size=n)
+    w = np.minimum(rng.integers(16, 33, size=n), 768 // h)
+    off = np.concatenate([[0], np.cumsum(h * w)]).astype(np.int64)
+    c.add_synthetic_store("initial", 0, page_offsets=off, seed=1)
+    for _ in range(reps):
+        info = recompute_pooling_from_initial(c, grids=np.stack([h, w], axis=1))
+    b = int(off[-1]) * 256 + (4 * int(np.minimum(h, 32).sum()) + n) * 256
+    print("pool_qwen", n, info, "GB/s", b / (info["ms"] * 1e-3) / 1e9)
 elif what == "pool_rows":
     c.add_synthetic_store("mean_pooling", 1_000_000, fixed_rows=32, seed=6)
     for _ in range(reps):

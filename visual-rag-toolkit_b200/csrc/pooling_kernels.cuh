@@ -115,25 +115,26 @@ __device__ __forceinline__ float4 pool_raw_to_f4(const PoolRaw& r, int f32) {
   const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.w.y));
   return make_float4(a.x, a.y, b.x, b.y);
 }
+// acc += rows [r, r + N) of `base`, in row order; the N loads are in flight together
+template <int N>
+__device__ __forceinline__ void pool_add_rows(float4& acc, const void* base, int f32, long long r, int lane) {
+  PoolRaw v[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) v[j] = pool_load_raw(base, f32, r + j, lane);
+#pragma unroll
+  for (int j = 0; j < N; ++j) acc = f4_add(acc, pool_raw_to_f4(v[j], f32));
+}
 __device__ __forceinline__ float4 range_mean_global(const void* base, int f32, long long lo, long long hi, int lane) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   long long r = lo;
-  for (; r + 16 <= hi; r += 16) {
-    PoolRaw v[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = pool_load_raw(base, f32, r + j, lane);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc = f4_add(acc, pool_raw_to_f4(v[j], f32));
-  }
-  if (r + 8 <= hi) {
-    PoolRaw v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = pool_load_raw(base, f32, r + j, lane);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc = f4_add(acc, pool_raw_to_f4(v[j], f32));
-    r += 8;
-  }
-  for (; r < hi; ++r) acc = f4_add(acc, pool_load4(base, f32, r, lane));
+  for (; r + 16 <= hi; r += 16) pool_add_rows<16>(acc, base, f32, r, lane);
+  // the remaining 1..15 rows in at most four batches (8, 4, 2, 1) instead of one HBM latency per row: ColQwen2.5 grids
+  // have 17..31 tokens per grid row. No predicated work: the token pass is as much issue- as latency-bound.
+  const int left = static_cast<int>(hi - r);
+  if (left & 8) { pool_add_rows<8>(acc, base, f32, r, lane); r += 8; }
+  if (left & 4) { pool_add_rows<4>(acc, base, f32, r, lane); r += 4; }
+  if (left & 2) { pool_add_rows<2>(acc, base, f32, r, lane); r += 2; }
+  if (left & 1) pool_add_rows<1>(acc, base, f32, r, lane);
   return f4_div(acc, static_cast<float>(hi - lo));
 }
 __device__ __forceinline__ float4 range_mean_smem(const float* rows, int lo, int hi, int lane) {
@@ -263,10 +264,14 @@ __global__ void __launch_bounds__(128) pool_rows_kernel(const PoolRowsArgs a) {
 // store dtype exactly as a reader of the stored rows would see them (the reference's dtype chain), are
 // kept in smem (at float offset d_off) and the derived stores are written in the same pass — the pooled store is
 // never re-read from HBM.
-template <bool DERIVE>
+// IN_F32: the input dtype at compile time (a run-time flag leaves both conversion paths in the instruction stream as
+// predicated-off instructions, and ncu shows the pass issue-bound as much as latency-bound: 10.7 G -> 8.5 G instructions
+// for 400k ColQwen2.5 pages).
+template <bool DERIVE, bool IN_F32>
 __global__ void __launch_bounds__(256, 4) pool_tokens_kernel(const PoolInput in, const PoolSpecDev s, const PoolRowsArgs d,
                                                              const int d_off) {
   extern __shared__ float pool_smem[];
+  constexpr int kInF32 = IN_F32 ? 1 : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kWarps = 8;
   float* drows = pool_smem + d_off;
@@ -295,7 +300,7 @@ __global__ void __launch_bounds__(256, 4) pool_tokens_kernel(const PoolInput in,
       }
       // 1) row means of the gh x gw grid -> smem (pooling.py:162-163)
       for (int h = warp; h < gh; h += kWarps) {
-        const float4 m = range_mean_global(in.in, in.in_f32, r0 + static_cast<long long>(h) * gw,
+        const float4 m = range_mean_global(in.in, kInF32, r0 + static_cast<long long>(h) * gw,
                                            r0 + static_cast<long long>(h + 1) * gw, lane);
         reinterpret_cast<float4*>(pool_smem + h * 128)[lane] = m;
       }
@@ -373,9 +378,9 @@ __global__ void __launch_bounds__(256, 4) pool_tokens_kernel(const PoolInput in,
       }
       float4 v;
       if (hi - lo == 1) {
-        v = pool_load4(in.in, in.in_f32, r0 + lo, lane);   // x/1 == x: raw rows pass through exactly
+        v = pool_load4(in.in, kInF32, r0 + lo, lane);   // x/1 == x: raw rows pass through exactly
       } else {
-        v = range_mean_global(in.in, in.in_f32, r0 + lo, r0 + hi, lane);
+        v = range_mean_global(in.in, kInF32, r0 + lo, r0 + hi, lane);
       }
       pool_store4(s.out, s.out_f32, o0 + o, lane, v, s.via_f16);
       keep(o, v);
@@ -394,7 +399,7 @@ __global__ void __launch_bounds__(256, 4) pool_tokens_kernel(const PoolInput in,
       const int head = n_out - 1;
       for (int o = head + warp; o < e_n; o += kWarps)
         pool_store4(s.out2, s.out_f32, e0 + o, lane,
-                    pool_load4(in.in, in.in_f32, r0 + static_cast<long long>(head) * s.ppt + (o - head), lane), 0);
+                    pool_load4(in.in, kInF32, r0 + static_cast<long long>(head) * s.ppt + (o - head), lane), 0);
     }
     if constexpr (DERIVE) {
       __syncthreads();

@@ -2701,8 +2701,10 @@ static int launch_pool(const PoolInput& in, int n, const vrag_pool_spec_t* specs
                        int max_grid_h, const int* max_out, int num_sms, cudaStream_t st, int64_t* launches) {
   static PerDeviceOnce once;
   if (once.first()) {
-    CUDA_OK(cudaFuncSetAttribute(pool_tokens_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 384 * 512));
-    CUDA_OK(cudaFuncSetAttribute(pool_tokens_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 384 * 512));
+    CUDA_OK(cudaFuncSetAttribute(pool_tokens_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 384 * 512));
+    CUDA_OK(cudaFuncSetAttribute(pool_tokens_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 384 * 512));
+    CUDA_OK(cudaFuncSetAttribute(pool_tokens_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 384 * 512));
+    CUDA_OK(cudaFuncSetAttribute(pool_tokens_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 384 * 512));
     CUDA_OK(cudaFuncSetAttribute(pool_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 512));
   }
   if (in.n_pages == 0) return 0;
@@ -2755,8 +2757,10 @@ static int launch_pool(const PoolInput& in, int n, const vrag_pool_spec_t* specs
     PoolInput win = in;
     win.row_skip = specs[i].in_row_skip;
     win.row_count = specs[i].in_row_count;
-    if (d.n_specs > 0) pool_tokens_kernel<true><<<grid, 256, smem, st>>>(win, dev[i], d, grid_rows * 128);
-    else pool_tokens_kernel<false><<<grid, 256, smem, st>>>(win, dev[i], d, grid_rows * 128);
+#define VRAG_TOKENS(D, F) pool_tokens_kernel<D, F><<<grid, 256, smem, st>>>(win, dev[i], d, grid_rows * 128)
+    if (d.n_specs > 0) { if (in.in_f32) VRAG_TOKENS(true, true); else VRAG_TOKENS(true, false); }
+    else { if (in.in_f32) VRAG_TOKENS(false, true); else VRAG_TOKENS(false, false); }
+#undef VRAG_TOKENS
     if (launches) ++*launches;
   }
   if (ra.n_specs > 0) {
