@@ -445,3 +445,24 @@ def test_infer_grids_vectorised_equals_per_page_inference():
     no_payload = infer_grids(tokens)
     for p in range(0, 500, 17):
         assert tuple(no_payload[p]) == infer_grid(int(tokens[p]))
+
+
+def test_host_worker_pool_survives_fork():
+    """A process that forks after the library's worker pool exists (multiprocessing's default start method) gets a fresh
+    pool in the child instead of waiting for threads that were not copied."""
+    import multiprocessing as mp
+
+    x = np.random.default_rng(0).standard_normal(1 << 20).astype(np.float32)
+    want = x.astype(np.float16).view(np.uint16)
+    assert np.array_equal(_cast_with_library(x, 8, False), want)      # the parent's pool exists now
+
+    def child(q):
+        q.put(bool(np.array_equal(_cast_with_library(x, 8, False), want)))
+
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    p = ctx.Process(target=child, args=(q,))
+    p.start()
+    p.join(60)
+    assert not p.is_alive(), "child hung in the worker pool"
+    assert q.get(timeout=5) is True

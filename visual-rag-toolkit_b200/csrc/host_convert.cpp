@@ -5,7 +5,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <pthread.h>
+
 #include <algorithm>
+#include <atomic>
+#include <new>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -133,8 +137,26 @@ struct Pool {
     n_tasks = next = 0;
   }
 };
+// The pool is created on first use and never destroyed (its detached workers may outlive static destruction). A forked
+// child has none of the parent's threads: it starts over with a fresh pool on its first use (the old object is leaked; its
+// mutexes may have been held by threads that no longer exist).
+std::atomic<Pool*> g_pool{nullptr};
+std::once_flag g_atfork_once;
+std::mutex g_pool_mu;
+void forget_pool_in_child() {
+  g_pool.store(nullptr, std::memory_order_relaxed);
+  new (&g_pool_mu) std::mutex();
+}
 Pool& pool() {
-  static Pool* p = new Pool();   // never destroyed: its detached workers may outlive static destruction
+  Pool* p = g_pool.load(std::memory_order_acquire);
+  if (p) return *p;
+  std::call_once(g_atfork_once, [] { pthread_atfork(nullptr, nullptr, forget_pool_in_child); });
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  p = g_pool.load(std::memory_order_acquire);
+  if (!p) {
+    p = new Pool();
+    g_pool.store(p, std::memory_order_release);
+  }
   return *p;
 }
 }  // namespace
