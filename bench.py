@@ -639,8 +639,10 @@ def run_ours(args):
             "data": "synthetic",
             "config": workload_config(pages, world),
             "notes": {"l2": "input (>=26 GB per step) is far larger than the 126 MB L2; no flush needed", "corpus_generation_s": gen_s,
-                      "exchange": "C ABI (vrag_comm_init / one packed all-gather per scanning stage, one max-all-reduce per "
-                                  "candidate stage); NCCL resolved by the library at run time" if world > 1 else "single shard"},
+                      "exchange": ("C ABI (vrag_comm_init / one packed all-gather per scanning stage, one max-all-reduce per "
+                                   "candidate stage); transport: " + ("NVLink peer memory (CUDA IPC windows; one kernel per collective: "
+                                   "stores into every peer's window -> flag -> wait -> consume)" if corpus.comm_peer_memory() else
+                                   "NCCL (resolved by the library at run time)")) if world > 1 else "single shard"},
             "hbm_gbs_algorithmic": total_pages * bytes_per_page * args.steps / (dev_ms * 1e-3) / 1e9,
             "e2e": {"value": total_pages * args.steps / e2e_s, "unit": "pages/s",
                     "h2d_bytes_per_step": Q_TOKENS * 128 * 4, "d2h_bytes_per_step": TOP_K * (4 + 8) + 36,

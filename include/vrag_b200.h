@@ -312,6 +312,12 @@ int vrag_comm_unique_id(void* out_id128);
 /* Join the communicator (collective: all nranks ranks call it). The handle's device is the rank's GPU.              */
 int vrag_comm_init(vrag_corpus_t* c, int rank, int nranks, const void* unique_id128);
 int vrag_comm_info(vrag_corpus_t* c, int* rank, int* nranks);
+/* Which transport the handle's collectives use: *peer_memory = 1 when every rank could map every other rank's exchange
+ * window (CUDA IPC over NVLink / NVSwitch peer memory): messages up to 4 MB per rank then travel as direct stores into the
+ * peers' windows followed by a flag, in ONE kernel per collective (store to all peers -> publish -> wait -> consume);
+ * 0: NCCL (also for larger messages, and when VRAG_P2P=0 or the mapping failed on any rank — agreed by all ranks at
+ * vrag_comm_init).                                                                                                */
+int vrag_comm_transport(vrag_corpus_t* c, int* peer_memory);
 int vrag_comm_destroy(vrag_corpus_t* c);
 
 /* The building blocks of a collective stage, for hosts that drive the stages themselves (device pointers, caller's stream):

@@ -921,4 +921,103 @@ __global__ void sel_init_kernel(SelState* st, int k, int batch) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ peer-memory exchange
+// One-shot collectives of the sharded search over NVLink / NVSwitch peer memory (the messages are 4 KB .. a few MB and
+// latency-bound: a NCCL all-gather of 256 packed hits costs 25-58 us on 8 GPUs, mostly protocol). Every rank owns a
+// WINDOW that all peers have mapped (CUDA IPC): data[2 slots][R sources][cap bytes] + flags[2][R]. A collective with
+// sequence number `epoch` uses slot epoch & 1: each rank stores its message into region [slot][me] of EVERY rank's window
+// (plain stores through the peer mapping), fences system-wide, and the last block to finish publishes `epoch` in
+// flags[slot][me] of every window; then it waits until its own flags[slot][*] all show `epoch` and consumes the R regions
+// from local memory. Two slots suffice: a rank can be at most one collective ahead of the slowest peer (completing
+// collective e needs every peer's flag for e, which a peer only sends after it finished e - 1 in stream order).
+constexpr int kP2PMaxRanks = 16;
+struct P2PWindow {
+  uint8_t* win[kP2PMaxRanks];   // window base of every rank as mapped into THIS process (win[me] = the local one)
+  unsigned long long cap;       // bytes per (slot, source) region
+  int me, R;
+  unsigned epoch;
+  unsigned* ctr;                // local: blocks that finished their stores (last one publishes the flags)
+};
+__device__ __forceinline__ unsigned* p2p_flag(const P2PWindow& w, int rank, int slot, int src) {
+  return reinterpret_cast<unsigned*>(w.win[rank] + 2ull * w.R * w.cap) + slot * kP2PMaxRanks + src;
+}
+__device__ __forceinline__ unsigned p2p_ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void p2p_st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// message of this rank (n16 16-byte words) -> every rank's window; publish; wait for all sources. All blocks of the grid
+// must be co-resident (they spin): launched with <= 32 blocks.
+__device__ __forceinline__ void p2p_exchange(const P2PWindow& w, const uint4* __restrict__ msg, long long n16, long long n_tail = 0) {
+  const int slot = w.epoch & 1;
+  const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long gsz = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (int r = 0; r < w.R; ++r) {
+    uint4* dst = reinterpret_cast<uint4*>(w.win[r] + (static_cast<unsigned long long>(slot) * w.R + w.me) * w.cap);
+    for (long long i = gtid; i < n16; i += gsz) dst[i] = msg[i];
+    for (long long i = gtid; i < n_tail; i += gsz)   // trailing 4-byte words (a message that is not a multiple of 16 bytes;
+      reinterpret_cast<unsigned*>(dst + n16)[i] = reinterpret_cast<const unsigned*>(msg + n16)[i];   // all of it when unaligned)
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(w.ctr, 1u);
+    if (prev == gridDim.x - 1) {
+      *w.ctr = 0u;               // next collective (same stream) starts from zero
+      __threadfence_system();    // cumulative: every block's stores (observed through the counter) before the flags
+      for (int r = 0; r < w.R; ++r) p2p_st_release_sys(p2p_flag(w, r, slot, w.me), w.epoch);
+    }
+  }
+  if (threadIdx.x < w.R) {
+    const unsigned* f = p2p_flag(w, w.me, slot, threadIdx.x);
+    const long long t0 = clock64();
+    while (static_cast<int>(p2p_ld_acquire_sys(f) - w.epoch) < 0) {
+      if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer died or the ranks' collective calls diverged
+        printf("vrag: peer exchange watchdog rank=%d waits for rank=%d epoch=%u\n", w.me, static_cast<int>(threadIdx.x), w.epoch);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
+// all-gather: gathered[src][0..n16) for src = 0..R-1 (the layout ncclAllGather produces)
+__global__ void __launch_bounds__(256) p2p_allgather_kernel(const P2PWindow w, const uint4* __restrict__ msg, long long n16,
+                                                            uint4* __restrict__ gathered) {
+  p2p_exchange(w, msg, n16);
+  const int slot = w.epoch & 1;
+  const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long gsz = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (int s = 0; s < w.R; ++s) {
+    const uint4* src = reinterpret_cast<const uint4*>(w.win[w.me] + (static_cast<unsigned long long>(slot) * w.R + s) * w.cap);
+    for (long long i = gtid; i < n16; i += gsz) gathered[s * n16 + i] = __ldcg(src + i);   // written by a peer: not through L1
+  }
+}
+// max-all-reduce of n floats in place. A buffer that is not 16-byte aligned goes through the 4-byte path entirely (the
+// choice must not change which collective path a rank takes: the ranks' sequence numbers have to stay in step).
+__global__ void __launch_bounds__(256) p2p_allreduce_max_kernel(const P2PWindow w, float* __restrict__ buf, long long n) {
+  const long long n4 = (reinterpret_cast<unsigned long long>(buf) & 15ull) == 0 ? (n >> 2) : 0;
+  const long long n_tail = n - 4 * n4;
+  p2p_exchange(w, reinterpret_cast<const uint4*>(buf), n4, n_tail);
+  const int slot = w.epoch & 1;
+  const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long gsz = static_cast<long long>(gridDim.x) * blockDim.x;
+  const uint8_t* base = w.win[w.me] + static_cast<unsigned long long>(slot) * w.R * w.cap;
+  for (long long i = gtid; i < n4; i += gsz) {
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int s = 0; s < w.R; ++s) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(base + s * w.cap) + i);   // written by a peer: not through L1
+      m = make_float4(fmaxf(m.x, v.x), fmaxf(m.y, v.y), fmaxf(m.z, v.z), fmaxf(m.w, v.w));
+    }
+    reinterpret_cast<float4*>(buf)[i] = m;
+  }
+  for (long long i = gtid; i < n_tail; i += gsz) {
+    float m = -INFINITY;
+    for (int s = 0; s < w.R; ++s) m = fmaxf(m, __ldcg(reinterpret_cast<const float*>(base + s * w.cap) + n4 * 4 + i));
+    buf[n4 * 4 + i] = m;
+  }
+}
+
 }  // namespace vrag

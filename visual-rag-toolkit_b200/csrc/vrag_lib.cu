@@ -224,7 +224,7 @@ struct NcclApi {
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
-static const int kNcclInt8 = 0, kNcclFloat32 = 7, kNcclMax = 2;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+static const int kNcclInt8 = 0, kNcclFloat32 = 7, kNcclMax = 2, kNcclMin = 3;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
 
 static const int kMaxCommEvents = 24;
 struct CommState {
@@ -239,6 +239,13 @@ struct CommState {
   bool timing = false;               // record events around collectives (host-facing searches on the library stream)
   float last_us[kMaxCommEvents] = {0};
   int last_n = 0;
+  // peer-memory exchange (aux_kernels.cuh): this rank's window, the peers' windows as mapped here, the collective counter
+  bool p2p = false;
+  uint8_t* win = nullptr;
+  uint8_t* peer_win[kP2PMaxRanks] = {nullptr};
+  size_t p2p_cap = 0;                // bytes per (slot, source) region
+  unsigned p2p_epoch = 0;
+  unsigned* p2p_ctr = nullptr;
 };
 
 struct vrag_corpus {
@@ -1475,9 +1482,96 @@ static void comm_release(vrag_corpus* c) {
   cm.m_ids.release();
   for (auto& e : cm.ev)
     if (e) { cudaEventDestroy(e); e = nullptr; }
+  for (int r = 0; r < kP2PMaxRanks; ++r) {
+    if (cm.peer_win[r] && cm.peer_win[r] != cm.win) cudaIpcCloseMemHandle(cm.peer_win[r]);
+    cm.peer_win[r] = nullptr;
+  }
+  if (cm.win) cudaFree(cm.win);
+  if (cm.p2p_ctr) cudaFree(cm.p2p_ctr);
+  cm.win = nullptr;
+  cm.p2p_ctr = nullptr;
+  cm.p2p = false;
+  cm.p2p_epoch = 0;
   cm.rank = 0;
   cm.nranks = 1;
 }
+
+// Map every rank's exchange window into this process (CUDA IPC; handles travel through one NCCL all-gather). Any failure
+// on any rank (no peer access, IPC not permitted in this container, VRAG_P2P=0) leaves ALL ranks on the NCCL collectives:
+// the decision is agreed with a min-all-reduce.
+static const size_t kP2PRegionBytes = size_t(4) << 20;
+static int comm_setup_p2p(vrag_corpus* c) {
+  CommState& cm = c->comm;
+  const int R = cm.nranks;
+  int ok = (R <= kP2PMaxRanks && !env_flag_is("VRAG_P2P", '0')) ? 1 : 0;
+  const size_t win_bytes = 2 * static_cast<size_t>(R) * kP2PRegionBytes + 2 * kP2PMaxRanks * sizeof(unsigned);
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok && (cudaMalloc(&cm.win, win_bytes) != cudaSuccess || cudaMalloc(&cm.p2p_ctr, sizeof(unsigned)) != cudaSuccess)) ok = 0;
+  if (ok && (cudaMemset(cm.win, 0, win_bytes) != cudaSuccess || cudaMemset(cm.p2p_ctr, 0, sizeof(unsigned)) != cudaSuccess)) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine, cm.win) != cudaSuccess) ok = 0;
+  cudaGetLastError();
+  // exchange handles (+ this rank's verdict so far) through NCCL
+  struct Msg { cudaIpcMemHandle_t h; int ok; int pad[3]; };
+  static_assert(sizeof(Msg) % 16 == 0, "message size");
+  Msg* d_msgs = nullptr;
+  CUDA_OK(cudaMalloc(&d_msgs, sizeof(Msg) * (R + 1)));
+  Msg m;
+  memset(&m, 0, sizeof(m));
+  m.h = mine;
+  m.ok = ok;
+  CUDA_OK(cudaMemcpyAsync(d_msgs + R, &m, sizeof(Msg), cudaMemcpyHostToDevice, c->stream));
+  NCCL_OK(g_nccl.AllGather(d_msgs + R, d_msgs, sizeof(Msg), kNcclInt8, cm.nccl, c->stream));
+  std::vector<Msg> all(R);
+  CUDA_OK(cudaMemcpyAsync(all.data(), d_msgs, sizeof(Msg) * R, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < R; ++r) ok &= all[r].ok;
+  if (ok) {
+    for (int r = 0; r < R && ok; ++r) {
+      if (r == cm.rank) { cm.peer_win[r] = cm.win; continue; }
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0;
+      cm.peer_win[r] = static_cast<uint8_t*>(p);
+    }
+    cudaGetLastError();
+  }
+  // second agreement: every rank could map every window
+  float* d_flag = reinterpret_cast<float*>(d_msgs);
+  const float mine_ok = ok ? 1.0f : 0.0f;
+  CUDA_OK(cudaMemcpyAsync(d_flag, &mine_ok, sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  NCCL_OK(g_nccl.AllReduce(d_flag, d_flag, 1, kNcclFloat32, kNcclMin, cm.nccl, c->stream));
+  float all_ok = 0.0f;
+  CUDA_OK(cudaMemcpyAsync(&all_ok, d_flag, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_msgs);
+  cm.p2p = all_ok == 1.0f;
+  cm.p2p_cap = kP2PRegionBytes;
+  cm.p2p_epoch = 0;
+  if (!cm.p2p) {
+    for (int r = 0; r < kP2PMaxRanks; ++r) {
+      if (cm.peer_win[r] && cm.peer_win[r] != cm.win) cudaIpcCloseMemHandle(cm.peer_win[r]);
+      cm.peer_win[r] = nullptr;
+    }
+    if (cm.win) cudaFree(cm.win);
+    if (cm.p2p_ctr) cudaFree(cm.p2p_ctr);
+    cm.win = nullptr;
+    cm.p2p_ctr = nullptr;
+    cudaGetLastError();
+  }
+  return 0;
+}
+static P2PWindow p2p_window(vrag_corpus* c) {
+  CommState& cm = c->comm;
+  P2PWindow w;
+  for (int r = 0; r < kP2PMaxRanks; ++r) w.win[r] = cm.peer_win[r];
+  w.cap = cm.p2p_cap;
+  w.me = cm.rank;
+  w.R = cm.nranks;
+  w.epoch = ++cm.p2p_epoch;
+  w.ctr = cm.p2p_ctr;
+  return w;
+}
+static unsigned p2p_blocks(long long n16) { return static_cast<unsigned>(std::max<long long>(1, std::min<long long>(32, (n16 + 255) / 256))); }
 
 extern "C" int vrag_comm_unique_id(void* out_id128) {
   if (!out_id128) return fail("out_id128 is NULL");
@@ -1503,6 +1597,7 @@ extern "C" int vrag_comm_init(vrag_corpus_t* c, int rank, int nranks, const void
   }
   c->comm.rank = rank;
   c->comm.nranks = nranks;
+  if (nranks > 1) TRY(comm_setup_p2p(c));
   return 0;
 }
 
@@ -1510,6 +1605,12 @@ extern "C" int vrag_comm_info(vrag_corpus_t* c, int* rank, int* nranks) {
   VRAG_LOCK(c);
   if (rank) *rank = c->comm.rank;
   if (nranks) *nranks = c->comm.nranks;
+  return 0;
+}
+
+extern "C" int vrag_comm_transport(vrag_corpus_t* c, int* peer_memory) {
+  VRAG_LOCK(c);
+  if (peer_memory) *peer_memory = c->comm.p2p ? 1 : 0;
   return 0;
 }
 
@@ -1557,14 +1658,29 @@ static int comm_allgather_hits(vrag_corpus* c, const Hit* local, int n_lists, in
     return 0;
   }
   comm_mark(c, st, true);
-  NCCL_OK(g_nccl.AllGather(local, gathered, bytes, kNcclInt8, c->comm.nccl, st));
+  if (c->comm.p2p && bytes <= c->comm.p2p_cap && bytes > 0) {
+    // one kernel: this rank's lists -> every rank's window over NVLink, publish, wait for the others, copy out
+    const long long n16 = static_cast<long long>(bytes / sizeof(uint4));
+    p2p_allgather_kernel<<<p2p_blocks(n16), 256, 0, st>>>(p2p_window(c), reinterpret_cast<const uint4*>(local), n16,
+                                                         reinterpret_cast<uint4*>(gathered));
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+  } else {
+    NCCL_OK(g_nccl.AllGather(local, gathered, bytes, kNcclInt8, c->comm.nccl, st));
+  }
   comm_mark(c, st, false);
   return 0;
 }
 static int comm_allreduce_max(vrag_corpus* c, float* buf, int64_t n, cudaStream_t st) {
   if (!sharded(c) || n == 0) return 0;
   comm_mark(c, st, true);
-  NCCL_OK(g_nccl.AllReduce(buf, buf, static_cast<size_t>(n), kNcclFloat32, kNcclMax, c->comm.nccl, st));
+  if (c->comm.p2p && static_cast<size_t>(n) * sizeof(float) <= c->comm.p2p_cap) {
+    p2p_allreduce_max_kernel<<<p2p_blocks(n >> 2), 256, 0, st>>>(p2p_window(c), buf, n);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+  } else {
+    NCCL_OK(g_nccl.AllReduce(buf, buf, static_cast<size_t>(n), kNcclFloat32, kNcclMax, c->comm.nccl, st));
+  }
   comm_mark(c, st, false);
   return 0;
 }

@@ -101,6 +101,7 @@ SIGNATURES = {
     "vrag_comm_unique_id": (C.c_int, [C.c_void_p]),
     "vrag_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "vrag_comm_info": (C.c_int, [C.c_void_p, _i32p, _i32p]),
+    "vrag_comm_transport": (C.c_int, [C.c_void_p, _i32p]),
     "vrag_comm_destroy": (C.c_int, [C.c_void_p]),
     "vrag_stage_hits_dev": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "vrag_allgather_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

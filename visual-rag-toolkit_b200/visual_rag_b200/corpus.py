@@ -135,6 +135,13 @@ class GpuCorpus:
         N.check(self._lib.vrag_comm_init(self._h, int(rank), int(world), buf))
         self.rank, self.world = int(rank), int(world)
 
+    def comm_peer_memory(self) -> bool:
+        """True when the handle's collectives (messages up to 4 MB per rank) run over mapped peer memory (NVLink / NVSwitch,
+        one kernel per collective) rather than NCCL — agreed by all ranks at comm_init."""
+        v = C.c_int(0)
+        N.check(self._lib.vrag_comm_transport(self._h, C.byref(v)))
+        return bool(v.value)
+
     def comm_init_torch(self, group=None) -> None:
         """comm_init with the id distributed through an initialised torch.distributed process group (any backend)."""
         import torch.distributed as dist
