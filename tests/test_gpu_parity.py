@@ -180,6 +180,55 @@ def test_topk_radix_select_with_massive_ties(corpus):
     assert ids.tolist() == list(range(300))
 
 
+def test_topk_beyond_the_shared_memory_sort(corpus):
+    """k > 4096 (the reference accepts any prefetch_k / limit): radix select + global bitonic sort + emit. Exact order
+    incl. ties, k between powers of two, k >= n, candidate lists, a multi-stage search whose prefetch is > 4096, and the
+    batched call (which runs such a batch query by query)."""
+    n = 300_000
+    corpus.add_synthetic_store("gb", n, fixed_rows=1, seed=3)
+    q = CS.query_rows(901, 1)
+    sc = corpus.score("gb", q)
+    full = np.lexsort((np.arange(n), -sc))
+    for k in (4097, 5000, 8192, 8193, 20000, 70000):
+        s, ids = corpus.search("gb", q, k)
+        assert len(ids) == k and ids.tolist() == full[:k].tolist() and np.array_equal(s, sc[full[:k]])
+    # massive ties at the threshold + k >= n
+    base = rows16(952, 50, scale=False)
+    pick = np.random.default_rng(2).integers(0, 50, size=20000)
+    corpus.add_store("dupb", base[pick], fixed_rows=1)
+    q3 = CS.query_rows(953, 3)
+    sd = corpus.score("dupb", q3)
+    order = np.lexsort((np.arange(len(sd)), -sd))
+    for k in (4100, 9000, 19999, 20000, 25000, 40000):
+        s, ids = corpus.search("dupb", q3, k)
+        m = min(k, len(sd))
+        assert len(ids) == m and ids.tolist() == order[:m].tolist() and np.array_equal(s, sd[order[:m]])
+    # candidate list (ids in arbitrary order; ties -> lower POSITION in the list, as the reference's stable sort over the list)
+    cand = np.random.default_rng(3).permutation(len(sd))[:12000]
+    s, ids = corpus.search("dupb", q3, 6000, candidate_ids=cand)
+    o = np.lexsort((np.arange(len(cand)), -sd[cand]))[:6000]
+    assert ids.tolist() == cand[o].tolist() and np.array_equal(s, sd[cand][o])
+    # two-stage with a 6000-page prefetch == the oracle order on the same scores
+    rows = rows16(954, 9000 * 6)
+    corpus.add_store("bp", rows.reshape(9000, 6, 128).mean(axis=1).astype(np.float16), fixed_rows=1)
+    corpus.add_store("bi", rows, fixed_rows=6)
+    qq = CS.query_rows(955, 7)
+    s1 = corpus.score("bp", qq)
+    pre = np.lexsort((np.arange(9000), -s1))[:6000]
+    s2 = corpus.score("bi", qq)
+    fin = pre[np.lexsort((np.arange(6000), -s2[pre]))[:10]]
+    res = corpus.search_multistage([("bp", False, 6000), ("bi", False, 10)], qq)
+    assert res[0][1].tolist() == pre.tolist() and res[1][1].tolist() == fin.tolist()
+    assert np.array_equal(res[1][0], s2[fin])
+    b = corpus.search_multistage_batch([("bp", False, 6000), ("bi", False, 10)], [qq, q3], as_arrays=True)
+    assert b[0][1].shape == (2, 6000) and b[1][1][0].tolist() == fin.tolist() and b[0][2].tolist() == [6000, 6000]
+    f_sc, f_id, f_st, f_cnt = corpus.search_multistage_batch([("bp", False, 6000), ("bi", False, 10)], [qq, q3], final_only=True)
+    assert f_id[0].tolist() == fin.tolist() and f_cnt.tolist() == [10, 10]
+    assert np.array_equal(f_st[0, :, 0], s1[fin])
+    for name in ("gb", "dupb", "bp", "bi"):
+        corpus.drop_store(name)
+
+
 # ------------------------------------------------------------------ edge cases
 def test_edge_cases(corpus):
     from visual_rag_b200._native import VragError

@@ -309,6 +309,41 @@ struct TopkArgs {
   const int* aux_src;         // optional device flag OR-ed into bit 0 (kHitMiss) of every out_hits entry
 };
 
+// Result j of query b from its sorted key (0: padding of a gathered list / beyond the valid results).
+__device__ __forceinline__ void topk_emit(const TopkArgs& a, long long b, long long j, unsigned long long key) {
+  const long long ob = b * a.out_stride;
+  uint32_t aux = 0u;
+  if (a.out_hits) {
+    if (a.n_dyn && a.fail_flag && ((a.n_dyn[b] < a.need) || (a.n_dyn[b] > a.n))) aux |= kHitMiss;
+    if (a.aux_src && *a.aux_src) aux |= kHitMiss;
+  }
+  float sc = -INFINITY;
+  long long id = -1;
+  int pos = -1;
+  if (key != 0ull) {
+    const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
+    sc = ord_to_score(static_cast<uint32_t>(key >> 32));
+    if (a.hits_in) {
+      const long long r = idx / a.hits_k_src;
+      id = a.hits_in[r * a.hits_rank_stride + b * a.hits_k_src + (idx - r * a.hits_k_src)].id;
+    } else {
+      id = a.ids ? a.ids[b * a.ids_stride + idx] : (a.id_base + idx);
+    }
+    pos = static_cast<int>(idx);
+    if (id < 0) sc = -INFINITY;   // padding that reached the output (fewer than k real entries)
+  }
+  if (a.out_scores) a.out_scores[ob + j] = sc;
+  if (a.out_ids) a.out_ids[ob + j] = id;
+  if (a.out_pos) a.out_pos[ob + j] = pos;
+  if (a.out_hits) {
+    Hit h;
+    h.score = sc;
+    h.aux = aux;
+    h.id = id;
+    a.out_hits[ob + j] = h;
+  }
+}
+
 template <int CHUNK, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) topk_kernel(const TopkArgs a) {
   extern __shared__ unsigned long long skeys[];
@@ -412,40 +447,7 @@ __global__ void __launch_bounds__(THREADS, 1) topk_kernel(const TopkArgs a) {
       a.keys_out[b * a.keys_out_stride + static_cast<long long>(blockIdx.x) * a.k + j] = skeys[j];
   } else {
     const long long nvalid = n_real < a.k ? n_real : a.k;
-    const long long ob = b * a.out_stride;
-    uint32_t aux = 0u;
-    if (a.out_hits) {
-      if (a.n_dyn && a.fail_flag && ((a.n_dyn[b] < a.need) || (a.n_dyn[b] > a.n))) aux |= kHitMiss;
-      if (a.aux_src && *a.aux_src) aux |= kHitMiss;
-    }
-    for (int j = threadIdx.x; j < a.k; j += THREADS) {
-      const unsigned long long key = j < nvalid ? skeys[j] : 0ull;   // k may exceed the sort buffer: never read past nvalid
-      float sc = -INFINITY;
-      long long id = -1;
-      int pos = -1;
-      if (key != 0ull) {   // key 0: padding of a gathered list / beyond the valid results
-        const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
-        sc = ord_to_score(static_cast<uint32_t>(key >> 32));
-        if (a.hits_in) {
-          const long long r = idx / a.hits_k_src;
-          id = a.hits_in[r * a.hits_rank_stride + b * a.hits_k_src + (idx - r * a.hits_k_src)].id;
-        } else {
-          id = a.ids ? a.ids[b * a.ids_stride + idx] : (a.id_base + idx);
-        }
-        pos = static_cast<int>(idx);
-        if (id < 0) sc = -INFINITY;   // padding that reached the output (fewer than k real entries)
-      }
-      if (a.out_scores) a.out_scores[ob + j] = sc;
-      if (a.out_ids) a.out_ids[ob + j] = id;
-      if (a.out_pos) a.out_pos[ob + j] = pos;
-      if (a.out_hits) {
-        Hit h;
-        h.score = sc;
-        h.aux = aux;
-        h.id = id;
-        a.out_hits[ob + j] = h;
-      }
-    }
+    for (int j = threadIdx.x; j < a.k; j += THREADS) topk_emit(a, b, j, j < nvalid ? skeys[j] : 0ull);   // k may exceed the sort buffer: never read past nvalid
     if (a.out_count && threadIdx.x == 0) a.out_count[b] = static_cast<int>(nvalid);
   }
 }
@@ -471,7 +473,8 @@ struct SelArgs {
   int k;
   SelState* state;         // [batch]
   unsigned int* hist;      // [batch][3][kSelBins]
-  unsigned long long* keys_out;   // [batch][k]
+  unsigned long long* keys_out;   // [batch][keys_stride], k keys written per query
+  long long keys_stride;   // elements between the key lists of consecutive queries (>= k)
 };
 
 __device__ __forceinline__ int sel_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
@@ -551,7 +554,7 @@ __global__ void __launch_bounds__(256) sel_compact_kernel(const SelArgs a) {
   const unsigned int T = st->prefix;
   const bool take_eq = st->eq_count == st->k_rem;
   const float* sc = a.scores + b * a.n;
-  unsigned long long* out = a.keys_out + b * a.k;
+  unsigned long long* out = a.keys_out + b * a.keys_stride;
   const long long base = static_cast<long long>(blockIdx.x) * kSelItemsPerBlock;
   for (int j = 0; j < kSelItemsPerBlock / 256; ++j) {
     const long long i = base + j * 256 + threadIdx.x;
@@ -576,7 +579,7 @@ __global__ void __launch_bounds__(1024) sel_ties_kernel(const SelArgs a) {
   const unsigned int T = st->prefix;
   const int need = st->k_rem, start = st->count_gt;
   const float* sc = a.scores + b * a.n;
-  unsigned long long* out = a.keys_out + b * a.k;
+  unsigned long long* out = a.keys_out + b * a.keys_stride;
   if (threadIdx.x == 0) running = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -601,6 +604,74 @@ __global__ void __launch_bounds__(1024) sel_ties_kernel(const SelArgs a) {
     __syncthreads();
     if (running >= need) break;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k > kTopkMaxK (the reference accepts any prefetch_k / limit): the k selected keys of a query (radix select above, or
+// every score when k >= n) are sorted by a bitonic network over GLOBAL memory — P = pow2ceil(k) keys per query, zero-padded,
+// descending; compare-exchange distances below kBigChunk run inside shared memory (one launch per merge size), the few
+// longer ones one launch each — and topk_emit_kernel writes the results. Rare path: a few launches, a few MB.
+constexpr int kBigChunk = 4096;
+__global__ void __launch_bounds__(256) keys_from_scores_kernel(const float* __restrict__ scores, long long n, long long in_stride,
+                                                               unsigned long long* __restrict__ keys, long long P) {
+  const long long b = blockIdx.y;
+  const long long i = blockIdx.x * 256ll + threadIdx.x;
+  if (i >= P) return;
+  keys[b * P + i] = i < n ? ((static_cast<unsigned long long>(score_to_ord(scores[b * in_stride + i])) << 32) |
+                             static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<uint32_t>(i)))
+                          : 0ull;
+}
+__global__ void __launch_bounds__(256) keys_zero_tail_kernel(unsigned long long* __restrict__ keys, long long from, long long P) {
+  const long long i = from + blockIdx.x * 256ll + threadIdx.x;
+  if (i < P) keys[blockIdx.y * P + i] = 0ull;
+}
+// all compare-exchange steps with distance < kBigChunk of the merge sizes [size_lo, size_hi] (size_lo == size_hi > kBigChunk:
+// the in-chunk tail of one global merge; size_lo = 2: the initial sort of every chunk)
+__global__ void __launch_bounds__(512) bitonic_chunk_kernel(unsigned long long* __restrict__ keys, long long P, long long size_lo,
+                                                            long long size_hi) {
+  __shared__ unsigned long long sk[kBigChunk];
+  unsigned long long* g = keys + blockIdx.y * P + static_cast<long long>(blockIdx.x) * kBigChunk;
+  const long long gbase = static_cast<long long>(blockIdx.x) * kBigChunk;
+  for (int j = threadIdx.x; j < kBigChunk; j += 512) sk[j] = g[j];
+  for (long long size = size_lo; size <= size_hi; size <<= 1) {
+    const int s0 = static_cast<int>(size >> 1 < kBigChunk / 2 ? size >> 1 : kBigChunk / 2);
+    for (int stride = s0; stride > 0; stride >>= 1) {
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < kBigChunk / 2 / 512; ++t) {
+        const int e = threadIdx.x + t * 512;
+        const int pos = 2 * e - (e & (stride - 1));
+        const unsigned long long x = sk[pos], y = sk[pos + stride];
+        const bool desc = ((gbase + pos) & size) == 0;   // size == P: always descending
+        if ((x < y) == desc) {
+          sk[pos] = y;
+          sk[pos + stride] = x;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < kBigChunk; j += 512) g[j] = sk[j];
+}
+__global__ void __launch_bounds__(256) bitonic_global_kernel(unsigned long long* __restrict__ keys, long long P, long long size,
+                                                             long long stride) {
+  const long long e = blockIdx.x * 256ll + threadIdx.x;
+  if (e >= (P >> 1)) return;
+  unsigned long long* g = keys + blockIdx.y * P;
+  const long long pos = 2 * e - (e & (stride - 1));
+  const unsigned long long x = g[pos], y = g[pos + stride];
+  const bool desc = (pos & size) == 0;
+  if ((x < y) == desc) {
+    g[pos] = y;
+    g[pos + stride] = x;
+  }
+}
+__global__ void __launch_bounds__(256) topk_emit_kernel(const TopkArgs a, const unsigned long long* __restrict__ keys, long long P) {
+  const long long b = blockIdx.y;
+  const long long j = blockIdx.x * 256ll + threadIdx.x;
+  const long long nvalid = a.n_total < a.k ? a.n_total : a.k;
+  if (j < a.k) topk_emit(a, b, j, j < nvalid ? keys[b * P + j] : 0ull);
+  if (a.out_count && j == 0) a.out_count[b] = static_cast<int>(nvalid);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -937,7 +1008,13 @@ struct P2PWindow {
   int me, R;
   unsigned epoch;
   unsigned* ctr;                // local: blocks that finished their stores (last one publishes the flags)
+  unsigned long long timeout_ns;   // watchdog of the flag wait (VRAG_P2P_TIMEOUT_S, default 120 s)
 };
+__device__ __forceinline__ unsigned long long p2p_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ unsigned* p2p_flag(const P2PWindow& w, int rank, int slot, int src) {
   return reinterpret_cast<unsigned*>(w.win[rank] + 2ull * w.R * w.cap) + slot * kP2PMaxRanks + src;
 }
@@ -973,9 +1050,12 @@ __device__ __forceinline__ void p2p_exchange(const P2PWindow& w, const uint4* __
   }
   if (threadIdx.x < w.R) {
     const unsigned* f = p2p_flag(w, w.me, slot, threadIdx.x);
-    const long long t0 = clock64();
+    const unsigned long long t0 = p2p_now_ns();
+    unsigned spins = 0;
     while (static_cast<int>(p2p_ld_acquire_sys(f) - w.epoch) < 0) {
-      if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer died or the ranks' collective calls diverged
+      // a peer that is merely late (host-side skew between the ranks) is waited for; only a peer that died or ranks whose
+      // collective calls diverged end in the watchdog, which fails the call instead of hanging the GPU
+      if ((++spins & 1023u) == 0 && p2p_now_ns() - t0 > w.timeout_ns) {
         printf("vrag: peer exchange watchdog rank=%d waits for rank=%d epoch=%u\n", w.me, static_cast<int>(threadIdx.x), w.epoch);
         __trap();
       }

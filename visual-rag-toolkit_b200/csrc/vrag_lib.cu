@@ -246,6 +246,7 @@ struct CommState {
   size_t p2p_cap = 0;                // bytes per (slot, source) region
   unsigned p2p_epoch = 0;
   unsigned* p2p_ctr = nullptr;
+  unsigned long long p2p_timeout_ns = 120ull * 1000000000ull;
 };
 
 struct vrag_corpus {
@@ -1277,13 +1278,88 @@ static int launch_topk_sort(vrag_corpus* c, const TopkArgs& a, int batch, cudaSt
   return 0;
 }
 
+// k > kTopkMaxK (a prefetch_k / limit beyond what the shared-memory sort holds; the reference accepts any value): radix
+// select of the k best keys (or every key when k >= n) into a zero-padded power-of-two list, global bitonic sort, emit.
+static const int kTopkHardMaxK = 1 << 20;
+static int launch_topk_big(vrag_corpus* c, const float* d_scores, const long long* d_ids, int64_t id_base, int64_t n, int k,
+                           float* out_scores, long long* out_ids, int* out_pos, int* out_count, cudaStream_t st, int batch,
+                           long long ids_stride, Hit* out_hits, const int* aux_src) {
+  const long long k_sel = std::min<long long>(k, n);
+  long long P = kBigChunk;
+  while (P < k_sel) P <<= 1;
+  TRY(c->d_keys_a.ensure(static_cast<size_t>(batch) * P));
+  unsigned long long* keys = c->d_keys_a.p;
+  const unsigned ub = static_cast<unsigned>(batch);
+  if (k_sel >= n) {
+    keys_from_scores_kernel<<<dim3(static_cast<unsigned>((P + 255) / 256), ub), 256, 0, st>>>(d_scores, n, n, keys, P);
+    c->launches++;
+  } else {
+    TRY(c->d_sel_state.ensure(static_cast<size_t>(batch) * sizeof(SelState)));
+    TRY(c->d_sel_hist.ensure(static_cast<size_t>(batch) * 3 * kSelBins));
+    SelArgs sa;
+    sa.scores = d_scores;
+    sa.n = n;
+    sa.k = k;
+    sa.state = reinterpret_cast<SelState*>(c->d_sel_state.p);
+    sa.hist = c->d_sel_hist.p;
+    sa.keys_out = keys;
+    sa.keys_stride = P;
+    CUDA_OK(cudaMemsetAsync(sa.hist, 0, static_cast<size_t>(batch) * 3 * kSelBins * sizeof(unsigned int), st));
+    sel_init_kernel<<<(batch + 127) / 128, 128, 0, st>>>(sa.state, k, batch);
+    const dim3 grid(static_cast<unsigned>((n + kSelItemsPerBlock - 1) / kSelItemsPerBlock), ub);
+    for (int pass = 0; pass < 3; ++pass) {
+      sel_hist_kernel<<<grid, 256, 0, st>>>(sa, pass);
+      sel_scan_kernel<<<batch, 256, 0, st>>>(sa, pass);
+    }
+    sel_compact_kernel<<<grid, 256, 0, st>>>(sa);
+    sel_ties_kernel<<<batch, 1024, 0, st>>>(sa);
+    c->launches += 9;
+    if (P > k_sel) {
+      keys_zero_tail_kernel<<<dim3(static_cast<unsigned>((P - k_sel + 255) / 256), ub), 256, 0, st>>>(keys, k_sel, P);
+      c->launches++;
+    }
+  }
+  const dim3 cgrid(static_cast<unsigned>(P / kBigChunk), ub);
+  bitonic_chunk_kernel<<<cgrid, 512, 0, st>>>(keys, P, 2, kBigChunk);
+  c->launches++;
+  for (long long size = 2ll * kBigChunk; size <= P; size <<= 1) {
+    for (long long stride = size >> 1; stride >= kBigChunk; stride >>= 1) {
+      bitonic_global_kernel<<<dim3(static_cast<unsigned>((P / 2 + 255) / 256), ub), 256, 0, st>>>(keys, P, size, stride);
+      c->launches++;
+    }
+    bitonic_chunk_kernel<<<cgrid, 512, 0, st>>>(keys, P, size, size);
+    c->launches++;
+  }
+  TopkArgs a;
+  memset(&a, 0, sizeof(a));
+  a.k = k;
+  a.out_scores = out_scores;
+  a.out_ids = out_ids;
+  a.out_pos = out_pos;
+  a.out_count = out_count;
+  a.ids = d_ids;
+  a.id_base = id_base;
+  a.n = n;
+  a.n_total = n;
+  a.out_stride = k;
+  a.ids_stride = ids_stride;
+  a.out_hits = out_hits;
+  a.aux_src = aux_src;
+  topk_emit_kernel<<<dim3(static_cast<unsigned>((k + 255) / 256), ub), 256, 0, st>>>(a, keys, P);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 static int launch_topk(vrag_corpus* c, const float* d_scores, const long long* d_ids, int64_t id_base, int64_t n,
                        int k, float* out_scores, long long* out_ids, int* out_pos, int* out_count, cudaStream_t st,
                        int batch = 1, long long ids_stride = 0, Hit* out_hits = nullptr, const int* aux_src = nullptr) {
   if (k < 1) return fail("k must be >= 1");
-  if (k > kTopkMaxK) return fail("k=%d exceeds the supported maximum %d", k, kTopkMaxK);
+  if (k > kTopkHardMaxK) return fail("k=%d exceeds the supported maximum %d", k, kTopkHardMaxK);
   if (n >= (1ll << 32) - 1) return fail("too many items for top-k");
   if (batch < 1) return fail("batch must be >= 1");
+  if (k > kTopkMaxK) return launch_topk_big(c, d_scores, d_ids, id_base, n, k, out_scores, out_ids, out_pos, out_count, st, batch,
+                                            ids_stride, out_hits, aux_src);
   int k2 = 1;
   while (k2 < k) k2 <<= 1;
   TopkArgs a;
@@ -1313,6 +1389,7 @@ static int launch_topk(vrag_corpus* c, const float* d_scores, const long long* d
     sa.state = reinterpret_cast<SelState*>(c->d_sel_state.p);
     sa.hist = c->d_sel_hist.p;
     sa.keys_out = c->d_keys_a.p;
+    sa.keys_stride = k;
     CUDA_OK(cudaMemsetAsync(sa.hist, 0, static_cast<size_t>(batch) * 3 * kSelBins * sizeof(unsigned int), st));
     sel_init_kernel<<<(batch + 127) / 128, 128, 0, st>>>(sa.state, k, batch);
     const dim3 grid(static_cast<unsigned>((n + kSelItemsPerBlock - 1) / kSelItemsPerBlock), static_cast<unsigned>(batch));
@@ -1547,6 +1624,10 @@ static int comm_setup_p2p(vrag_corpus* c) {
   cm.p2p = all_ok == 1.0f;
   cm.p2p_cap = kP2PRegionBytes;
   cm.p2p_epoch = 0;
+  if (const char* e = getenv("VRAG_P2P_TIMEOUT_S")) {
+    const double sec = atof(e);
+    if (sec > 0.0) cm.p2p_timeout_ns = static_cast<unsigned long long>(sec * 1e9);
+  }
   if (!cm.p2p) {
     for (int r = 0; r < kP2PMaxRanks; ++r) {
       if (cm.peer_win[r] && cm.peer_win[r] != cm.win) cudaIpcCloseMemHandle(cm.peer_win[r]);
@@ -1569,6 +1650,7 @@ static P2PWindow p2p_window(vrag_corpus* c) {
   w.R = cm.nranks;
   w.epoch = ++cm.p2p_epoch;
   w.ctr = cm.p2p_ctr;
+  w.timeout_ns = cm.p2p_timeout_ns;
   return w;
 }
 static unsigned p2p_blocks(long long n16) { return static_cast<unsigned>(std::max<long long>(1, std::min<long long>(32, (n16 + 255) / 256))); }
@@ -1688,7 +1770,7 @@ static int comm_allreduce_max(vrag_corpus* c, float* buf, int64_t n, cudaStream_
 // Merge gathered lists hits[src][list][k_src] -> global top-k per list (ties -> lower source rank = lower global id).
 static int merge_hits(vrag_corpus* c, const Hit* hits, int n_src, int n_lists, int k_src, int k, float* out_scores,
                       long long* out_ids, int* fail_flag, cudaStream_t st) {
-  if (k < 1 || k > kTopkMaxK) return fail("k=%d out of range [1,%d]", k, kTopkMaxK);
+  if (k < 1 || k > kTopkHardMaxK) return fail("k=%d out of range [1,%d]", k, kTopkHardMaxK);
   const long long n = static_cast<long long>(n_src) * k_src;
   if (n <= 8192) {
     int k2 = 1;
@@ -1910,7 +1992,7 @@ static int search_multistage_impl(vrag_corpus_t* c, int n_stages, const char* co
   for (int s = 0; s < n_stages; ++s) {
     TRY(find_store(c, names[s], &st[s]));
     if (ks[s] < 1) return fail("stage %d: k must be >= 1", s);
-    if (ks[s] > kTopkMaxK) return fail("stage %d: k=%d exceeds the supported maximum %d", s, ks[s], kTopkMaxK);
+    if (ks[s] > kTopkHardMaxK) return fail("stage %d: k=%d exceeds the supported maximum %d", s, ks[s], kTopkHardMaxK);
     if (st[s]->n_pages != st[0]->n_pages) return fail("stage %d: store '%s' has a different page count", s, names[s]);
     total_k += ks[s];
     if (q_offsets) {
@@ -1983,7 +2065,7 @@ extern "C" int vrag_stage_hits_dev(vrag_corpus_t* c, const char* name, const flo
   TRY(find_store(c, name, &s));
   TRY(set_device(c));
   if (!query_dev || !out_hits_dev) return fail("NULL device pointer");
-  if (k < 1 || k > kTopkMaxK) return fail("k=%d out of range [1,%d]", k, kTopkMaxK);
+  if (k < 1 || k > kTopkHardMaxK) return fail("k=%d out of range [1,%d]", k, kTopkHardMaxK);
   cudaStream_t stm = static_cast<cudaStream_t>(stream);
   const long long* cand = reinterpret_cast<const long long*>(cand_ids_dev);
   const int64_t n_items = cand ? n_cand : s->n_pages;
@@ -2033,7 +2115,7 @@ extern "C" int vrag_search_multistage_dev(vrag_corpus_t* c, int n_stages, const 
   Store* st[kMaxStages];
   for (int s = 0; s < n_stages; ++s) {
     TRY(find_store(c, names[s], &st[s]));
-    if (ks[s] < 1 || ks[s] > kTopkMaxK) return fail("stage %d: k=%d out of range [1,%d]", s, ks[s], kTopkMaxK);
+    if (ks[s] < 1 || ks[s] > kTopkHardMaxK) return fail("stage %d: k=%d out of range [1,%d]", s, ks[s], kTopkHardMaxK);
     if (st[s]->n_pages != st[0]->n_pages) return fail("stage %d: store '%s' has a different page count", s, names[s]);
     if (q_offsets && (q_offsets[s] < 0 || q_offsets[s + 1] <= q_offsets[s] || q_offsets[s + 1] > n_query_rows))
       return fail("stage %d: bad query row range", s);
@@ -2431,7 +2513,7 @@ static int search_multistage_batch_impl(vrag_corpus_t* c, int n_stages, const ch
   for (int s = 0; s < n_stages; ++s) {
     TRY(find_store(c, names[s], &st[s]));
     if (ks[s] < 1) return fail("stage %d: k must be >= 1", s);
-    if (ks[s] > kTopkMaxK) return fail("stage %d: k=%d exceeds the supported maximum %d", s, ks[s], kTopkMaxK);
+    if (ks[s] > kTopkMaxK) return fail("stage %d: k=%d exceeds the maximum of a BATCHED stage (%d); use the single-query call", s, ks[s], kTopkMaxK);
     if (st[s]->n_pages != st[0]->n_pages) return fail("stage %d: store '%s' has a different page count", s, names[s]);
     total_k += ks[s];
   }

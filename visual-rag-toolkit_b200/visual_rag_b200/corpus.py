@@ -17,7 +17,8 @@ import numpy as np
 from . import _native as N
 
 DIM = 128
-MAX_K = 4096   # kTopkMaxK of the library: the largest `limit` / `prefetch_k` / stage size one search stage can keep
+MAX_K = 1 << 20      # kTopkHardMaxK of the library: the largest `limit` / `prefetch_k` / stage size of one search stage
+MAX_K_BATCH = 4096   # kTopkMaxK: the largest stage size of the BATCHED native call (beyond it a batch runs query by query)
 
 
 def _check_k(k: int, what: str = "k") -> int:
@@ -549,6 +550,8 @@ class GpuCorpus:
             mats = [_as_f32_query(x) for x in queries]
             nq = len(mats)
             per_stage = 0
+        if nq > 0 and any(int(st[2]) > MAX_K_BATCH for st in stages):
+            return self._batch_query_by_query(stages, queries, mats, nq, normalize, stage_queries, as_arrays, final_only, fp16_query)
         if nq == 0:
             if final_only:
                 kl = int(stages[-1][2])
@@ -610,6 +613,44 @@ class GpuCorpus:
                 out[b].append((sc[b, :m], ii[b, :m]))   # views into this call's own result arrays
             off += nq * ks[s]
         return out
+
+    def _batch_query_by_query(self, stages, queries, mats, nq, normalize, stage_queries, as_arrays, final_only, fp16_query):
+        """A batch with a stage size beyond MAX_K_BATCH (the batched kernels keep at most 4096 results per query and stage in
+        shared memory): the same result formats from one `search_multistage` call per query."""
+        ns = len(stages)
+        ks = [int(st[2]) for st in stages]
+        if stage_queries is not None:
+            per = [self.search_multistage(stages, None, normalize, stage_queries=sq, fp16_query=fp16_query) for sq in stage_queries]
+        else:
+            if mats is None:   # PackedQueries
+                o = queries.offsets
+                mats = [queries.rows[int(o[b]) : int(o[b + 1])] for b in range(nq)]
+            per = [self.search_multistage(stages, q, normalize, fp16_query=fp16_query) for q in mats]
+        if not as_arrays and not final_only:
+            return per
+        arr = []
+        for s in range(ns):
+            sc = np.full((nq, ks[s]), -np.inf, dtype=np.float32)
+            ii = np.full((nq, ks[s]), -1, dtype=np.int64)
+            cnt = np.zeros((nq,), dtype=np.int32)
+            for b in range(nq):
+                m = len(per[b][s][1])
+                sc[b, :m], ii[b, :m], cnt[b] = per[b][s][0], per[b][s][1], m
+            arr.append((sc, ii, cnt))
+        if not final_only:
+            return arr
+        f_sc, f_id, f_cnt = arr[-1]
+        f_st = np.full((nq, ks[-1], max(ns - 1, 0)), np.nan, dtype=np.float32)
+        for b in range(nq):
+            for s in range(ns - 1):
+                sc_s, id_s = per[b][s]
+                order = np.argsort(id_s, kind="stable")
+                pos = np.searchsorted(id_s[order], f_id[b, : f_cnt[b]])
+                pos = np.minimum(pos, max(len(order) - 1, 0))
+                if len(order):
+                    hit = id_s[order][pos] == f_id[b, : f_cnt[b]]
+                    f_st[b, : f_cnt[b], s] = np.where(hit, sc_s[order][pos], np.nan)
+        return f_sc, f_id, f_st, f_cnt
 
     def saliency(self, name: str, query, page_id: int) -> np.ndarray:
         """patch_scores of generate_saliency_map (visualization/saliency.py:69-79) for one page (global page id):
