@@ -148,7 +148,9 @@ int vrag_host_f32_to_f16(const float* src, uint16_t* dst, int64_t n, int threads
  * mean-pooled prefetch vector and the token matrix as two separate queries (two_stage.py:142,159).
  * cand_ids != NULL restricts stage 0 to the listed global page ids (a payload / HasId filter).
  * Outputs are per stage, concatenated: stage s occupies [sum(ks[:s]), sum(ks[:s+1])) of out_scores/out_ids;
- * out_counts[s] valid entries each.                                                                */
+ * out_counts[s] valid entries each. Any stage size 1 <= ks[s] <= 2^20 (the reference accepts any prefetch_k / limit): up
+ * to 4096 results are sorted in shared memory, longer lists by a global bitonic sort of the selected keys; the BATCHED
+ * calls below keep at most 4096 results per query and stage.                                       */
 int vrag_search_multistage(vrag_corpus_t* c, int n_stages, const char* const* names, const uint32_t* flags,
                            const int* ks, const float* query, int n_query_rows, const int* q_offsets,
                            const int64_t* cand_ids, int64_t n_cand, float* out_scores, int64_t* out_ids,
@@ -297,8 +299,12 @@ int vrag_store_pool(vrag_corpus_t* c, const char* src, int n_specs, const vrag_p
  * cand_ids of a collective search is RANK-LOCAL: each rank lists (in ascending id order) the pages of its own range that
  * pass the filter; ids of other ranks are ignored. Reference semantics are kept: the global top-prefetch_k is formed
  * before the rerank (two_stage.py:161-178).
- * Transport: NCCL (resolved at run time with dlopen("libnccl.so.2"), so that a process that already loaded a NCCL — e.g.
- * through torch — shares it; the library has no link-time NCCL dependency).                                          */
+ * Transport: NVLink / NVSwitch peer memory where every rank can map every other rank's exchange window (CUDA IPC; see
+ * vrag_comm_transport) — one kernel per collective — else NCCL; NCCL also bootstraps the windows and carries messages above
+ * 4 MB per rank. NCCL is resolved at run time with dlopen("libnccl.so.2"), so that a process that already loaded a NCCL —
+ * e.g. through torch — shares it; the library has no link-time NCCL dependency. The collectives of one handle must be issued
+ * from one thread at a time and, for the *_dev entry points, on ONE stream (they are numbered in issue order).
+ * A host with no Python in it that does all of this: tests/c_host/vrag_host.c (`vrag_host sharded N`).                 */
 typedef struct vrag_hit {
   float score;
   uint32_t aux;   /* bit 0: this rank's list came from a top-k estimate that missed; the search is repeated exactly */

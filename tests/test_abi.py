@@ -51,3 +51,33 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("the oracle", "").replace("oracle will see", ""), f"{f} mentions oracle/"
+
+
+# ------------------------------------------------------------------ a host with no Python in it (tests/c_host/vrag_host.c)
+def _c_host():
+    import subprocess
+
+    d = os.path.join(ROOT, "tests", "c_host")
+    subprocess.run(["make", "-C", d], check=True, capture_output=True)   # -std=c99 -pedantic -Werror: the header is plain C
+    return os.path.join(d, "vrag_host")
+
+
+def test_plain_c_host_builds_against_the_header_and_loads_the_library():
+    import subprocess
+
+    out = subprocess.run([_c_host(), "abi"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and out.stdout.startswith("abi "), out.stderr
+    if not gpu_available():   # no fallback from C either
+        bad = subprocess.run([_c_host(), "single", "100", "64"], capture_output=True, text=True, timeout=60)
+        assert bad.returncode != 0 and "no CUDA device" in bad.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_host_two_stage_search():
+    """The C program builds a corpus on the device, pools it, runs two-stage and exhaustive searches through the C ABI and
+    checks the lists against vrag_score + a stable host sort (exit code 0 = all equal)."""
+    import subprocess
+
+    out = subprocess.run([_c_host(), "single", "20000", "256"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "equal score + stable sort" in out.stdout
