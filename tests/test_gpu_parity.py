@@ -206,8 +206,9 @@ def test_topk_beyond_the_shared_memory_sort(corpus):
     # candidate list (ids in arbitrary order; ties -> lower POSITION in the list, as the reference's stable sort over the list)
     cand = np.random.default_rng(3).permutation(len(sd))[:12000]
     s, ids = corpus.search("dupb", q3, 6000, candidate_ids=cand)
-    o = np.lexsort((np.arange(len(cand)), -sd[cand]))[:6000]
-    assert ids.tolist() == cand[o].tolist() and np.array_equal(s, sd[cand][o])
+    sdc = corpus.score("dupb", q3, candidate_ids=cand)     # the gather path's own scores (last-ulp differences to the dense scan)
+    o = np.lexsort((np.arange(len(cand)), -sdc))[:6000]
+    assert ids.tolist() == cand[o].tolist() and np.array_equal(s, sdc[o])
     # two-stage with a 6000-page prefetch == the oracle order on the same scores
     rows = rows16(954, 9000 * 6)
     corpus.add_store("bp", rows.reshape(9000, 6, 128).mean(axis=1).astype(np.float16), fixed_rows=1)
