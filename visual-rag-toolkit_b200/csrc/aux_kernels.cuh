@@ -242,6 +242,72 @@ __global__ void synth_rows_kernel(__half* __restrict__ rows, float* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------------ peer-memory windows
+// (the collectives that use them are at the end of this file; the top-k kernels below send / receive through them too)
+constexpr int kP2PMaxRanks = 16;
+struct P2PWindow {
+  uint8_t* win[kP2PMaxRanks];   // window base of every rank as mapped into THIS process (win[me] = the local one)
+  unsigned long long cap;       // bytes per (slot, source) region
+  int me, R;
+  unsigned epoch;
+  unsigned* ctr;                // local: blocks that finished their stores (last one publishes the flags)
+  unsigned long long timeout_ns;   // watchdog of the flag wait (VRAG_P2P_TIMEOUT_S, default 120 s)
+  unsigned long long ll_off;    // byte offset of the LL area inside a window: ll[2 slots][R sources][ll_cap bytes]
+  unsigned long long ll_cap;    // bytes per (slot, source) LL region = 2 x the largest LL payload
+};
+__device__ __forceinline__ unsigned long long p2p_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned* p2p_flag(const P2PWindow& w, int rank, int slot, int src) {
+  return reinterpret_cast<unsigned*>(w.win[rank] + 2ull * w.R * w.cap) + slot * kP2PMaxRanks + src;
+}
+__device__ __forceinline__ unsigned p2p_ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void p2p_st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- LL lines (flag-in-data, the idea of NCCL's low-latency protocol): small messages travel as 16-byte lines
+// (w0, epoch, w1, epoch) written with ONE vector store each — an 8-byte half is delivered atomically, so a reader that sees
+// `epoch` in both halves has the payload; no fence, no separate flag, no counter: the latency of an exchange is one NVLink
+// store plus the poll. The lines of collective `epoch` live in slot epoch & 1 of a window area of their own (a payload word
+// of a bulk message must never be mistaken for a flag); stale lines carry older epochs.
+__device__ __forceinline__ uint8_t* ll_region(const P2PWindow& w, int rank, int src) {
+  return w.win[rank] + w.ll_off + (static_cast<unsigned long long>(w.epoch & 1u) * w.R + src) * w.ll_cap;
+}
+__device__ __forceinline__ void ll_store(uint8_t* line, uint32_t w0, uint32_t w1, uint32_t e) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"(w0), "r"(e), "r"(w1), "r"(e) : "memory");
+}
+__device__ __forceinline__ bool ll_try_load(const uint8_t* line, uint32_t e, uint32_t& w0, uint32_t& w1) {
+  uint32_t f0, f1;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(f0), "=r"(w1), "=r"(f1) : "l"(line) : "memory");
+  return f0 == e && f1 == e;
+}
+// pair p (8 payload bytes) of this rank's message -> region [me] of EVERY rank's window (the local one included)
+__device__ __forceinline__ void ll_send_pair(const P2PWindow& w, long long p, uint32_t w0, uint32_t w1) {
+  for (int r = 0; r < w.R; ++r) ll_store(ll_region(w, r, w.me) + p * 16, w0, w1, w.epoch);
+}
+// pair p of rank src's message, from the local window; spins until it has arrived
+__device__ __forceinline__ void ll_recv_pair(const P2PWindow& w, int src, long long p, uint32_t& w0, uint32_t& w1) {
+  const uint8_t* line = ll_region(w, w.me, src) + p * 16;
+  if (ll_try_load(line, w.epoch, w0, w1)) return;
+  const unsigned long long t0 = p2p_now_ns();
+  unsigned spins = 0;
+  while (!ll_try_load(line, w.epoch, w0, w1)) {
+    // a peer that is merely late (host-side skew between the ranks) is waited for; only a peer that died or ranks whose
+    // collective calls diverged end in the watchdog, which fails the call instead of hanging the GPU
+    if ((++spins & 1023u) == 0 && p2p_now_ns() - t0 > w.timeout_ns) {
+      printf("vrag: peer exchange watchdog (LL) rank=%d waits for rank=%d epoch=%u\n", w.me, src, w.epoch);
+      __trap();
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Exact top-k.  Keys are 64-bit: (order-preserving bits of the fp32 score) << 32 | (0xFFFFFFFF - item
 // index), so "largest key first" = "highest score first, ties -> lower item index", which is what
@@ -267,6 +333,22 @@ struct __align__(16) Hit {
   long long id;
 };
 constexpr uint32_t kHitMiss = 1u;
+// entry idx of a packed list as two LL lines
+__device__ __forceinline__ void ll_send_hit(const P2PWindow& w, long long idx, const Hit& h) {
+  ll_send_pair(w, 2 * idx, __float_as_uint(h.score), h.aux);
+  ll_send_pair(w, 2 * idx + 1, static_cast<uint32_t>(static_cast<unsigned long long>(h.id) & 0xFFFFFFFFull),
+               static_cast<uint32_t>(static_cast<unsigned long long>(h.id) >> 32));
+}
+__device__ __forceinline__ Hit ll_recv_hit(const P2PWindow& w, int src, long long idx) {
+  uint32_t a, b, lo, hi;
+  ll_recv_pair(w, src, 2 * idx, a, b);
+  ll_recv_pair(w, src, 2 * idx + 1, lo, hi);
+  Hit h;
+  h.score = __uint_as_float(a);
+  h.aux = b;
+  h.id = static_cast<long long>((static_cast<unsigned long long>(hi) << 32) | lo);
+  return h;
+}
 
 __device__ __forceinline__ uint32_t score_to_ord(float f) {
   if (f != f) return 0u;  // NaN sorts last
@@ -307,13 +389,25 @@ struct TopkArgs {
                               //   global id; padding entries (id < 0) are ignored; a set kHitMiss bit raises fail_flag
   Hit* out_hits;              // final level: also write the results as packed entries [k] (the all-gather send buffer)
   const int* aux_src;         // optional device flag OR-ed into bit 0 (kHitMiss) of every out_hits entry
+  // ---- exchange fused into the two top-k kernels of a sharded scanning stage (peer-memory transport, lists that fit the LL
+  // area): the final level of the LOCAL top-k sends its packed entries as LL lines straight into every rank's window
+  // (ll_send), the merge level polls the R lists from the local window while it loads its keys (ll_recv, instead of
+  // hits_in): no exchange kernel, no fence, no staging copy between them.
+  int ll_send, ll_recv;
+  P2PWindow ll;
 };
+// element i of query b of the gathered lists ([rank][query][k_src]), from the all-gather buffer or the LL window
+__device__ __forceinline__ Hit topk_gathered_hit(const TopkArgs& a, long long b, long long i) {
+  const long long r = i / a.hits_k_src, j = i - r * a.hits_k_src;
+  if (a.ll_recv) return ll_recv_hit(a.ll, static_cast<int>(r), b * a.hits_k_src + j);
+  return a.hits_in[r * a.hits_rank_stride + b * a.hits_k_src + j];
+}
 
 // Result j of query b from its sorted key (0: padding of a gathered list / beyond the valid results).
 __device__ __forceinline__ void topk_emit(const TopkArgs& a, long long b, long long j, unsigned long long key) {
   const long long ob = b * a.out_stride;
   uint32_t aux = 0u;
-  if (a.out_hits) {
+  if (a.out_hits || a.ll_send) {
     if (a.n_dyn && a.fail_flag && ((a.n_dyn[b] < a.need) || (a.n_dyn[b] > a.n))) aux |= kHitMiss;
     if (a.aux_src && *a.aux_src) aux |= kHitMiss;
   }
@@ -323,9 +417,8 @@ __device__ __forceinline__ void topk_emit(const TopkArgs& a, long long b, long l
   if (key != 0ull) {
     const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
     sc = ord_to_score(static_cast<uint32_t>(key >> 32));
-    if (a.hits_in) {
-      const long long r = idx / a.hits_k_src;
-      id = a.hits_in[r * a.hits_rank_stride + b * a.hits_k_src + (idx - r * a.hits_k_src)].id;
+    if (a.hits_in || a.ll_recv) {
+      id = topk_gathered_hit(a, b, idx).id;   // (LL: the line has arrived, this is a plain re-read)
     } else {
       id = a.ids ? a.ids[b * a.ids_stride + idx] : (a.id_base + idx);
     }
@@ -335,12 +428,13 @@ __device__ __forceinline__ void topk_emit(const TopkArgs& a, long long b, long l
   if (a.out_scores) a.out_scores[ob + j] = sc;
   if (a.out_ids) a.out_ids[ob + j] = id;
   if (a.out_pos) a.out_pos[ob + j] = pos;
-  if (a.out_hits) {
+  if (a.out_hits || a.ll_send) {
     Hit h;
     h.score = sc;
     h.aux = aux;
     h.id = id;
-    a.out_hits[ob + j] = h;
+    if (a.out_hits) a.out_hits[ob + j] = h;
+    if (a.ll_send) ll_send_hit(a.ll, ob + j, h);
   }
 }
 
@@ -360,9 +454,8 @@ __global__ void __launch_bounds__(THREADS, 1) topk_kernel(const TopkArgs a) {
     const long long i = base + j;
     unsigned long long key = 0ull;
     if (i < n_in) {
-      if (a.hits_in) {
-        const long long r = i / a.hits_k_src;
-        const Hit h = a.hits_in[r * a.hits_rank_stride + b * a.hits_k_src + (i - r * a.hits_k_src)];
+      if (a.hits_in || a.ll_recv) {
+        const Hit h = topk_gathered_hit(a, b, i);
         if (h.id >= 0)
           key = (static_cast<unsigned long long>(score_to_ord(h.score)) << 32) |
                 static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<uint32_t>(i));
@@ -995,37 +1088,12 @@ __global__ void sel_init_kernel(SelState* st, int k, int batch) {
 // ------------------------------------------------------------------------------------------------ peer-memory exchange
 // One-shot collectives of the sharded search over NVLink / NVSwitch peer memory (the messages are 4 KB .. a few MB and
 // latency-bound: a NCCL all-gather of 256 packed hits costs 25-58 us on 8 GPUs, mostly protocol). Every rank owns a
-// WINDOW that all peers have mapped (CUDA IPC): data[2 slots][R sources][cap bytes] + flags[2][R]. A collective with
+// WINDOW that all peers have mapped (CUDA IPC): data[2 slots][R sources][cap bytes] + flags[2][R] (+ the LL area, above). A collective with
 // sequence number `epoch` uses slot epoch & 1: each rank stores its message into region [slot][me] of EVERY rank's window
 // (plain stores through the peer mapping), fences system-wide, and the last block to finish publishes `epoch` in
 // flags[slot][me] of every window; then it waits until its own flags[slot][*] all show `epoch` and consumes the R regions
 // from local memory. Two slots suffice: a rank can be at most one collective ahead of the slowest peer (completing
 // collective e needs every peer's flag for e, which a peer only sends after it finished e - 1 in stream order).
-constexpr int kP2PMaxRanks = 16;
-struct P2PWindow {
-  uint8_t* win[kP2PMaxRanks];   // window base of every rank as mapped into THIS process (win[me] = the local one)
-  unsigned long long cap;       // bytes per (slot, source) region
-  int me, R;
-  unsigned epoch;
-  unsigned* ctr;                // local: blocks that finished their stores (last one publishes the flags)
-  unsigned long long timeout_ns;   // watchdog of the flag wait (VRAG_P2P_TIMEOUT_S, default 120 s)
-};
-__device__ __forceinline__ unsigned long long p2p_now_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ unsigned* p2p_flag(const P2PWindow& w, int rank, int slot, int src) {
-  return reinterpret_cast<unsigned*>(w.win[rank] + 2ull * w.R * w.cap) + slot * kP2PMaxRanks + src;
-}
-__device__ __forceinline__ unsigned p2p_ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void p2p_st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // message of this rank (n16 16-byte words) -> every rank's window; publish; wait for all sources. All blocks of the grid
 // must be co-resident (they spin): launched with <= 32 blocks.
 __device__ __forceinline__ void p2p_exchange(const P2PWindow& w, const uint4* __restrict__ msg, long long n16, long long n_tail = 0) {
@@ -1097,6 +1165,46 @@ __global__ void __launch_bounds__(256) p2p_allreduce_max_kernel(const P2PWindow 
     float m = -INFINITY;
     for (int s = 0; s < w.R; ++s) m = fmaxf(m, __ldcg(reinterpret_cast<const float*>(base + s * w.cap) + n4 * 4 + i));
     buf[n4 * 4 + i] = m;
+  }
+}
+
+// The same two collectives for small messages (<= ll_cap / 2 bytes per rank) as LL lines: send, then poll — no fence, flag or
+// counter. <= 32 blocks: every block both sends and waits, so all of them have to be resident.
+__global__ void __launch_bounds__(256) p2p_ll_allgather_kernel(const P2PWindow w, const uint4* __restrict__ msg, long long n16,
+                                                               uint4* __restrict__ gathered) {
+  const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long gsz = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = gtid; i < n16; i += gsz) {
+    const uint4 v = msg[i];
+    ll_send_pair(w, 2 * i, v.x, v.y);
+    ll_send_pair(w, 2 * i + 1, v.z, v.w);
+  }
+  for (int s = 0; s < w.R; ++s)
+    for (long long i = gtid; i < n16; i += gsz) {
+      uint4 v;
+      ll_recv_pair(w, s, 2 * i, v.x, v.y);
+      ll_recv_pair(w, s, 2 * i + 1, v.z, v.w);
+      gathered[s * n16 + i] = v;
+    }
+}
+__global__ void __launch_bounds__(256) p2p_ll_allreduce_max_kernel(const P2PWindow w, float* __restrict__ buf, long long n) {
+  const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long gsz = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long np = (n + 1) >> 1;
+  for (long long p = gtid; p < np; p += gsz) {
+    const float x = buf[2 * p], y = 2 * p + 1 < n ? buf[2 * p + 1] : -INFINITY;
+    ll_send_pair(w, p, __float_as_uint(x), __float_as_uint(y));
+  }
+  for (long long p = gtid; p < np; p += gsz) {   // the same thread that sent pair p overwrites it
+    float m0 = -INFINITY, m1 = -INFINITY;
+    for (int s = 0; s < w.R; ++s) {
+      uint32_t a, b;
+      ll_recv_pair(w, s, p, a, b);
+      m0 = fmaxf(m0, __uint_as_float(a));
+      m1 = fmaxf(m1, __uint_as_float(b));
+    }
+    buf[2 * p] = m0;
+    if (2 * p + 1 < n) buf[2 * p + 1] = m1;
   }
 }
 

@@ -1283,7 +1283,7 @@ static int launch_topk_sort(vrag_corpus* c, const TopkArgs& a, int batch, cudaSt
 static const int kTopkHardMaxK = 1 << 20;
 static int launch_topk_big(vrag_corpus* c, const float* d_scores, const long long* d_ids, int64_t id_base, int64_t n, int k,
                            float* out_scores, long long* out_ids, int* out_pos, int* out_count, cudaStream_t st, int batch,
-                           long long ids_stride, Hit* out_hits, const int* aux_src) {
+                           long long ids_stride, Hit* out_hits, const int* aux_src, const P2PWindow* ll_send) {
   const long long k_sel = std::min<long long>(k, n);
   long long P = kBigChunk;
   while (P < k_sel) P <<= 1;
@@ -1345,6 +1345,10 @@ static int launch_topk_big(vrag_corpus* c, const float* d_scores, const long lon
   a.ids_stride = ids_stride;
   a.out_hits = out_hits;
   a.aux_src = aux_src;
+  if (ll_send) {
+    a.ll_send = 1;
+    a.ll = *ll_send;
+  }
   topk_emit_kernel<<<dim3(static_cast<unsigned>((k + 255) / 256), ub), 256, 0, st>>>(a, keys, P);
   c->launches++;
   CUDA_OK(cudaGetLastError());
@@ -1353,13 +1357,14 @@ static int launch_topk_big(vrag_corpus* c, const float* d_scores, const long lon
 
 static int launch_topk(vrag_corpus* c, const float* d_scores, const long long* d_ids, int64_t id_base, int64_t n,
                        int k, float* out_scores, long long* out_ids, int* out_pos, int* out_count, cudaStream_t st,
-                       int batch = 1, long long ids_stride = 0, Hit* out_hits = nullptr, const int* aux_src = nullptr) {
+                       int batch = 1, long long ids_stride = 0, Hit* out_hits = nullptr, const int* aux_src = nullptr,
+                       const P2PWindow* ll_send = nullptr) {
   if (k < 1) return fail("k must be >= 1");
   if (k > kTopkHardMaxK) return fail("k=%d exceeds the supported maximum %d", k, kTopkHardMaxK);
   if (n >= (1ll << 32) - 1) return fail("too many items for top-k");
   if (batch < 1) return fail("batch must be >= 1");
   if (k > kTopkMaxK) return launch_topk_big(c, d_scores, d_ids, id_base, n, k, out_scores, out_ids, out_pos, out_count, st, batch,
-                                            ids_stride, out_hits, aux_src);
+                                            ids_stride, out_hits, aux_src, ll_send);
   int k2 = 1;
   while (k2 < k) k2 <<= 1;
   TopkArgs a;
@@ -1376,6 +1381,10 @@ static int launch_topk(vrag_corpus* c, const float* d_scores, const long long* d
   a.ids_stride = ids_stride;
   a.out_hits = out_hits;
   a.aux_src = aux_src;
+  if (ll_send) {
+    a.ll_send = 1;
+    a.ll = *ll_send;
+  }
   long long m = n;   // elements the final sort sees
   if (n > 4096) {
     // ---- radix select: leaves exactly k keys per query in d_keys_a
@@ -1423,11 +1432,15 @@ static int launch_topk(vrag_corpus* c, const float* d_scores, const long long* d
 static int launch_topk_keys(vrag_corpus* c, const unsigned long long* keys, const int* n_dyn, int cap, int k,
                             int64_t id_base, float* out_scores, long long* out_ids, cudaStream_t st, int batch,
                             const long long* ids = nullptr, int* out_count = nullptr, int* fail_flag = nullptr, int need = 0,
-                            Hit* out_hits = nullptr, const int* aux_src = nullptr) {
+                            Hit* out_hits = nullptr, const int* aux_src = nullptr, const P2PWindow* ll_send = nullptr) {
   int k2 = 1;
   while (k2 < k) k2 <<= 1;
   TopkArgs a;
   memset(&a, 0, sizeof(a));
+  if (ll_send) {
+    a.ll_send = 1;
+    a.ll = *ll_send;
+  }
   a.k = k;
   a.keys_in = keys;
   a.in_stride = cap;
@@ -1491,7 +1504,7 @@ static SampledPlan plan_sampled_topk(int64_t n, int k) {
 }
 static int launch_topk_sampled(vrag_corpus* c, const float* d_scores, const long long* d_ids, int64_t id_base, int64_t n, int k,
                                float* out_scores, long long* out_ids, int* out_count, int* d_fail_flag, cudaStream_t st,
-                               const SampledPlan& pl, Hit* out_hits = nullptr) {
+                               const SampledPlan& pl, Hit* out_hits = nullptr, const P2PWindow* ll_send = nullptr) {
   TRY(c->d_skeys.ensure(pl.cap));
   TRY(c->d_sthr.ensure(1));
   TRY(c->d_sstate.ensure(2));
@@ -1511,7 +1524,7 @@ static int launch_topk_sampled(vrag_corpus* c, const float* d_scores, const long
   c->sampled_runs++;
   // the sort kernel also checks the survivor count (k <= count <= cap) and raises the flag otherwise
   return launch_topk_keys(c, c->d_skeys.p, c->d_sstate.p, pl.cap, k, id_base, out_scores, out_ids, st, 1, d_ids, out_count,
-                          d_fail_flag, static_cast<int>(std::min<int64_t>(k, n)), out_hits);
+                          d_fail_flag, static_cast<int>(std::min<int64_t>(k, n)), out_hits, nullptr, ll_send);
 }
 
 // ------------------------------------------------------------------------------------------------ multi-GPU exchange
@@ -1577,11 +1590,13 @@ static void comm_release(vrag_corpus* c) {
 // on any rank (no peer access, IPC not permitted in this container, VRAG_P2P=0) leaves ALL ranks on the NCCL collectives:
 // the decision is agreed with a min-all-reduce.
 static const size_t kP2PRegionBytes = size_t(4) << 20;
+static const size_t kLLMaxPayload = size_t(256) << 10;   // messages up to this size travel as LL lines (2 x the bytes on the wire)
+static size_t p2p_ll_offset(int R) { return (2 * static_cast<size_t>(R) * kP2PRegionBytes + 2 * kP2PMaxRanks * sizeof(unsigned) + 255) & ~size_t(255); }
 static int comm_setup_p2p(vrag_corpus* c) {
   CommState& cm = c->comm;
   const int R = cm.nranks;
   int ok = (R <= kP2PMaxRanks && !env_flag_is("VRAG_P2P", '0')) ? 1 : 0;
-  const size_t win_bytes = 2 * static_cast<size_t>(R) * kP2PRegionBytes + 2 * kP2PMaxRanks * sizeof(unsigned);
+  const size_t win_bytes = p2p_ll_offset(R) + 2 * static_cast<size_t>(R) * (2 * kLLMaxPayload);
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof(mine));
   if (ok && (cudaMalloc(&cm.win, win_bytes) != cudaSuccess || cudaMalloc(&cm.p2p_ctr, sizeof(unsigned)) != cudaSuccess)) ok = 0;
@@ -1651,6 +1666,8 @@ static P2PWindow p2p_window(vrag_corpus* c) {
   w.epoch = ++cm.p2p_epoch;
   w.ctr = cm.p2p_ctr;
   w.timeout_ns = cm.p2p_timeout_ns;
+  w.ll_off = p2p_ll_offset(cm.nranks);
+  w.ll_cap = 2 * kLLMaxPayload;
   return w;
 }
 static unsigned p2p_blocks(long long n16) { return static_cast<unsigned>(std::max<long long>(1, std::min<long long>(32, (n16 + 255) / 256))); }
@@ -1741,10 +1758,15 @@ static int comm_allgather_hits(vrag_corpus* c, const Hit* local, int n_lists, in
   }
   comm_mark(c, st, true);
   if (c->comm.p2p && bytes <= c->comm.p2p_cap && bytes > 0) {
-    // one kernel: this rank's lists -> every rank's window over NVLink, publish, wait for the others, copy out
+    // one kernel: this rank's lists -> every rank's window over NVLink, wait for the others, copy out. Small messages as
+    // LL lines (flag in the data: no fence), larger ones as plain stores + system fence + flag
     const long long n16 = static_cast<long long>(bytes / sizeof(uint4));
-    p2p_allgather_kernel<<<p2p_blocks(n16), 256, 0, st>>>(p2p_window(c), reinterpret_cast<const uint4*>(local), n16,
-                                                         reinterpret_cast<uint4*>(gathered));
+    if (bytes <= kLLMaxPayload)
+      p2p_ll_allgather_kernel<<<p2p_blocks(n16), 256, 0, st>>>(p2p_window(c), reinterpret_cast<const uint4*>(local), n16,
+                                                              reinterpret_cast<uint4*>(gathered));
+    else
+      p2p_allgather_kernel<<<p2p_blocks(n16), 256, 0, st>>>(p2p_window(c), reinterpret_cast<const uint4*>(local), n16,
+                                                           reinterpret_cast<uint4*>(gathered));
     c->launches++;
     CUDA_OK(cudaGetLastError());
   } else {
@@ -1757,7 +1779,10 @@ static int comm_allreduce_max(vrag_corpus* c, float* buf, int64_t n, cudaStream_
   if (!sharded(c) || n == 0) return 0;
   comm_mark(c, st, true);
   if (c->comm.p2p && static_cast<size_t>(n) * sizeof(float) <= c->comm.p2p_cap) {
-    p2p_allreduce_max_kernel<<<p2p_blocks(n >> 2), 256, 0, st>>>(p2p_window(c), buf, n);
+    if (static_cast<size_t>(n) * sizeof(float) <= kLLMaxPayload)
+      p2p_ll_allreduce_max_kernel<<<p2p_blocks((n + 1) >> 1), 256, 0, st>>>(p2p_window(c), buf, n);
+    else
+      p2p_allreduce_max_kernel<<<p2p_blocks(n >> 2), 256, 0, st>>>(p2p_window(c), buf, n);
     c->launches++;
     CUDA_OK(cudaGetLastError());
   } else {
@@ -1769,9 +1794,10 @@ static int comm_allreduce_max(vrag_corpus* c, float* buf, int64_t n, cudaStream_
 
 // Merge gathered lists hits[src][list][k_src] -> global top-k per list (ties -> lower source rank = lower global id).
 static int merge_hits(vrag_corpus* c, const Hit* hits, int n_src, int n_lists, int k_src, int k, float* out_scores,
-                      long long* out_ids, int* fail_flag, cudaStream_t st) {
+                      long long* out_ids, int* fail_flag, cudaStream_t st, const P2PWindow* ll_recv = nullptr) {
   if (k < 1 || k > kTopkHardMaxK) return fail("k=%d out of range [1,%d]", k, kTopkHardMaxK);
   const long long n = static_cast<long long>(n_src) * k_src;
+  if (ll_recv && n > 8192) return fail("internal: fused exchange needs lists that fit one merge block");
   if (n <= 8192) {
     int k2 = 1;
     while (k2 < k) k2 <<= 1;
@@ -1779,6 +1805,11 @@ static int merge_hits(vrag_corpus* c, const Hit* hits, int n_src, int n_lists, i
     memset(&a, 0, sizeof(a));
     a.k = k;
     a.hits_in = hits;
+    if (ll_recv) {
+      a.hits_in = nullptr;
+      a.ll_recv = 1;
+      a.ll = *ll_recv;
+    }
     a.hits_k_src = k_src;
     a.hits_rank_stride = static_cast<long long>(n_lists) * k_src;
     a.n = n;
@@ -1948,17 +1979,30 @@ static int run_stages(vrag_corpus* c, int n_stages, Store* const* st, const uint
       TRY(launch_topk(c, c->d_scores.p, d_prev_ids, c->page_base, n_items, ks[s], o_sc, o_id, nullptr, nullptr, stm));
     } else {
       const SampledPlan sp = (allow_sampled && n_items > 0) ? plan_sampled_topk(n_items, ks[s]) : SampledPlan();
-      Hit* hits = sh ? c->comm.send.p : nullptr;
+      // peer-memory transport and lists that fit one merge block: the exchange is fused into the two top-k kernels — the
+      // local top-k's last kernel stores its packed entries as LL lines into every rank's window, the merge kernel polls
+      // them while it loads its keys (the exchange costs no launch of its own)
+      const bool fused = sh && c->comm.p2p && !env_flag_is("VRAG_P2P_FUSED", '0') &&
+                         static_cast<long long>(c->comm.nranks) * ks[s] <= 8192 &&
+                         static_cast<size_t>(ks[s]) * sizeof(Hit) <= kLLMaxPayload;
+      P2PWindow win;
+      if (fused) win = p2p_window(c);
+      const P2PWindow* llw = fused ? &win : nullptr;
+      Hit* hits = (sh && !fused) ? c->comm.send.p : nullptr;
       if (sp.on) {
         if (!used_sampled) CUDA_OK(cudaMemsetAsync(d_fail, 0, sizeof(int), stm));
         used_sampled = true;
         TRY(launch_topk_sampled(c, c->d_scores.p, d_prev_ids, c->page_base, n_items, ks[s], sh ? nullptr : o_sc,
-                                sh ? nullptr : o_id, sh ? nullptr : d_counts + s, d_fail, stm, sp, hits));
+                                sh ? nullptr : o_id, sh ? nullptr : d_counts + s, d_fail, stm, sp, hits, llw));
       } else {
         TRY(launch_topk(c, c->d_scores.p, d_prev_ids, c->page_base, n_items, ks[s], sh ? nullptr : o_sc, sh ? nullptr : o_id,
-                        nullptr, sh ? nullptr : d_counts + s, stm, 1, 0, hits));
+                        nullptr, sh ? nullptr : d_counts + s, stm, 1, 0, hits, nullptr, llw));
       }
-      if (sh) {
+      if (fused) {
+        comm_mark(c, stm, true);    // reported as this stage's collective: the merge kernel = wait for the peers' lines + sort
+        TRY(merge_hits(c, nullptr, c->comm.nranks, 1, ks[s], ks[s], o_sc, o_id, d_fail, stm, llw));
+        comm_mark(c, stm, false);
+      } else if (sh) {
         TRY(comm_allgather_hits(c, c->comm.send.p, 1, ks[s], c->comm.recv.p, stm));
         TRY(merge_hits(c, c->comm.recv.p, c->comm.nranks, 1, ks[s], ks[s], o_sc, o_id, d_fail, stm));
       }
