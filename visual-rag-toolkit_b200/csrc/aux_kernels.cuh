@@ -395,6 +395,10 @@ struct TopkArgs {
   // hits_in): no exchange kernel, no fence, no staging copy between them.
   int ll_send, ll_recv;
   P2PWindow ll;
+  // gathered lists that are each sorted descending (what every rank's local top-k emits): run r of the sort buffer IS list r
+  // (padded to k2 with the smallest key, odd runs loaded back to front = ascending), so the run-sorting stages are skipped
+  // and the kernel goes straight to the merge-and-prune rounds. Number of lists, 0 = off; needs hits_k_src <= k2.
+  int presorted_src;
 };
 // element i of query b of the gathered lists ([rank][query][k_src]), from the all-gather buffer or the LL window
 __device__ __forceinline__ Hit topk_gathered_hit(const TopkArgs& a, long long b, long long i) {
@@ -451,9 +455,16 @@ __global__ void __launch_bounds__(THREADS, 1) topk_kernel(const TopkArgs a) {
   const long long n_real = a.n_dyn ? n_in : a.n_total;
   const long long base = static_cast<long long>(blockIdx.x) * CHUNK;
   for (int j = threadIdx.x; j < CHUNK; j += THREADS) {
-    const long long i = base + j;
+    long long i = base + j;
     unsigned long long key = 0ull;
-    if (i < n_in) {
+    bool have = i < n_in;
+    if (a.presorted_src > 0) {
+      const int run = j / a.k2, pos = j - run * a.k2;
+      const int e = (run & 1) ? a.k2 - 1 - pos : pos;
+      have = run < a.presorted_src && e < a.hits_k_src;
+      i = static_cast<long long>(run) * a.hits_k_src + e;
+    }
+    if (have) {
       if (a.hits_in || a.ll_recv) {
         const Hit h = topk_gathered_hit(a, b, i);
         if (h.id >= 0)
@@ -475,11 +486,11 @@ __global__ void __launch_bounds__(THREADS, 1) topk_kernel(const TopkArgs a) {
   // prefiltered candidate list of ~2k keys in an 8192-key buffer sorts 4x less.
   int eff = CHUNK;
   {
-    const long long here = n_in - base;   // keys of this block
+    const long long here = a.presorted_src > 0 ? static_cast<long long>(a.presorted_src) * K2 : n_in - base;   // keys of this block
     while ((eff >> 1) >= K2 && (eff >> 1) >= here) eff >>= 1;
   }
-  // 1. sorted runs of K2, run r descending iff r is even
-  for (int size = 2; size <= K2; size <<= 1) {
+  // 1. sorted runs of K2, run r descending iff r is even (already so when the input lists were sorted)
+  for (int size = 2; size <= (a.presorted_src > 0 ? 1 : K2); size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       __syncthreads();
 #pragma unroll

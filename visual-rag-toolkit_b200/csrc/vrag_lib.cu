@@ -1794,13 +1794,17 @@ static int comm_allreduce_max(vrag_corpus* c, float* buf, int64_t n, cudaStream_
 
 // Merge gathered lists hits[src][list][k_src] -> global top-k per list (ties -> lower source rank = lower global id).
 static int merge_hits(vrag_corpus* c, const Hit* hits, int n_src, int n_lists, int k_src, int k, float* out_scores,
-                      long long* out_ids, int* fail_flag, cudaStream_t st, const P2PWindow* ll_recv = nullptr) {
+                      long long* out_ids, int* fail_flag, cudaStream_t st, const P2PWindow* ll_recv = nullptr,
+                      bool lists_sorted = false) {
   if (k < 1 || k > kTopkHardMaxK) return fail("k=%d out of range [1,%d]", k, kTopkHardMaxK);
-  const long long n = static_cast<long long>(n_src) * k_src;
+  long long n = static_cast<long long>(n_src) * k_src;
   if (ll_recv && n > 8192) return fail("internal: fused exchange needs lists that fit one merge block");
   if (n <= 8192) {
     int k2 = 1;
     while (k2 < k) k2 <<= 1;
+    // lists that are sorted already (a rank's local top-k): one run per list, no run-sorting stages
+    const bool presorted = lists_sorted && k_src <= k2 && static_cast<long long>(n_src) * k2 <= 8192 &&
+                           !env_flag_is("VRAG_MERGE_PRESORTED", '0');
     TopkArgs a;
     memset(&a, 0, sizeof(a));
     a.k = k;
@@ -1818,6 +1822,10 @@ static int merge_hits(vrag_corpus* c, const Hit* hits, int n_src, int n_lists, i
     a.out_ids = out_ids;
     a.out_stride = k;
     a.fail_flag = fail_flag;
+    if (presorted) {
+      a.presorted_src = n_src;
+      n = static_cast<long long>(n_src) * k2;   // slots of the sort buffer in use
+    }
     const int chunk = n <= 1024 ? 1024 : (n <= 2048 ? 2048 : 8192);
     a.k2 = std::min(k2, chunk);
     if (chunk == 8192) TRY((launch_topk_sort<8192, 1024>(c, a, n_lists, st)));
@@ -2000,11 +2008,11 @@ static int run_stages(vrag_corpus* c, int n_stages, Store* const* st, const uint
       }
       if (fused) {
         comm_mark(c, stm, true);    // reported as this stage's collective: the merge kernel = wait for the peers' lines + sort
-        TRY(merge_hits(c, nullptr, c->comm.nranks, 1, ks[s], ks[s], o_sc, o_id, d_fail, stm, llw));
+        TRY(merge_hits(c, nullptr, c->comm.nranks, 1, ks[s], ks[s], o_sc, o_id, d_fail, stm, llw, true));
         comm_mark(c, stm, false);
       } else if (sh) {
         TRY(comm_allgather_hits(c, c->comm.send.p, 1, ks[s], c->comm.recv.p, stm));
-        TRY(merge_hits(c, c->comm.recv.p, c->comm.nranks, 1, ks[s], ks[s], o_sc, o_id, d_fail, stm));
+        TRY(merge_hits(c, c->comm.recv.p, c->comm.nranks, 1, ks[s], ks[s], o_sc, o_id, d_fail, stm, nullptr, true));
       }
     }
     d_prev_ids = o_id;
@@ -2519,7 +2527,7 @@ static int batch_run_sharded(vrag_corpus* c, int n_stages, Store* const* st, con
                               nullptr, c->comm.send.p + static_cast<size_t>(b0) * k));
       }
       TRY(comm_allgather_hits(c, c->comm.send.p, nq, k, c->comm.recv.p, stm));
-      TRY(merge_hits(c, c->comm.recv.p, R, nq, k, k, o_sc, o_id, c->d_fcnt.p + nq, stm));
+      TRY(merge_hits(c, c->comm.recv.p, R, nq, k, k, o_sc, o_id, c->d_fcnt.p + nq, stm, nullptr, true));
     } else {
       const int64_t n_cand = ks[s - 1];
       TRY(batch_prepare_stage(c, *st[s], k, n_cand, false, false, flags[s], s, &plan, &qchunk));
