@@ -640,8 +640,9 @@ def run_ours(args):
             "config": workload_config(pages, world),
             "notes": {"l2": "input (>=26 GB per step) is far larger than the 126 MB L2; no flush needed", "corpus_generation_s": gen_s,
                       "exchange": ("C ABI (vrag_comm_init / one packed all-gather per scanning stage, one max-all-reduce per "
-                                   "candidate stage); transport: " + ("NVLink peer memory (CUDA IPC windows; one kernel per collective: "
-                                   "stores into every peer's window -> flag -> wait -> consume)" if corpus.comm_peer_memory() else
+                                   "candidate stage); transport: " + ("NVLink peer memory (CUDA IPC windows; small messages as LL lines — flag in the data, no fence — "
+                                   "with a single-query stage's exchange fused into its two top-k kernels; larger ones one kernel per "
+                                   "collective: stores into every peer's window -> flag -> wait -> consume)" if corpus.comm_peer_memory() else
                                    "NCCL (resolved by the library at run time)")) if world > 1 else "single shard"},
             "hbm_gbs_algorithmic": total_pages * bytes_per_page * args.steps / (dev_ms * 1e-3) / 1e9,
             "e2e": {"value": total_pages * args.steps / e2e_s, "unit": "pages/s",
