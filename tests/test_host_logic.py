@@ -466,3 +466,65 @@ def test_host_worker_pool_survives_fork():
     p.join(60)
     assert not p.is_alive(), "child hung in the worker pool"
     assert q.get(timeout=5) is True
+
+
+def test_batch_with_a_stage_beyond_the_batched_limit_runs_query_by_query():
+    """GpuCorpus.search_multistage_batch with a stage size > MAX_K_BATCH: the per-query fallback must reproduce the three
+    result formats of the native batched call (lists, as_arrays, final_only with earlier-stage scores; NaN if absent).
+    Host logic only: search_multistage is replaced by the oracle over small host stores."""
+    from visual_rag_b200 import corpus as GC
+
+    n = 40
+    pooled = [CS.unit_rows(4000 + i, 3) for i in range(n)]
+    full = [CS.unit_rows(5000 + i, 9) for i in range(n)]
+    stores = {"p": pooled, "f": full}
+    calls = []
+
+    class Fake(GC.GpuCorpus):
+        def __init__(self):   # no device
+            pass
+
+        def search_multistage(self, stages, query, normalize=True, stage_queries=None, candidate_ids=None, fp16_query=False,
+                              filter_id=None):
+            calls.append(1)
+            qs = stage_queries if stage_queries is not None else [query] * len(stages)
+            out, cand = [], None
+            for (name, pool, k), q in zip(stages, qs):
+                q = np.asarray(q, np.float32)
+                if pool:
+                    q = q.mean(axis=0, keepdims=True)
+                ids = list(range(n)) if cand is None else cand
+                sc = np.array([MO.maxsim_score(q, stores[name][i].astype(np.float32)) for i in ids], np.float32)
+                order = np.lexsort((np.arange(len(ids)), -sc))[: min(k, len(ids))]
+                out.append((sc[order], np.asarray(ids, np.int64)[order]))
+                cand = [ids[j] for j in order]
+            return out
+
+    c = Fake()
+    big = GC.MAX_K_BATCH + 1
+    stages = [("p", False, big), ("f", False, 5)]
+    queries = [CS.query_rows(6000 + b, 4 + b) for b in range(3)]
+    lists = c.search_multistage_batch(stages, queries)
+    assert len(calls) == 3 and len(lists) == 3
+    for b, q in enumerate(queries):
+        want = c.search_multistage(stages, q)
+        assert lists[b][0][1].tolist() == want[0][1].tolist() and lists[b][1][1].tolist() == want[1][1].tolist()
+    arr = c.search_multistage_batch(stages, GC.pack_queries(queries), as_arrays=True)
+    assert arr[0][0].shape == (3, big) and arr[1][1].shape == (3, 5)
+    assert arr[0][2].tolist() == [n, n, n] and arr[1][2].tolist() == [5, 5, 5]
+    assert np.isneginf(arr[0][0][:, n:]).all() and (arr[0][1][:, n:] == -1).all()
+    for b in range(3):
+        assert arr[1][1][b].tolist() == lists[b][1][1].tolist()
+        np.testing.assert_array_equal(arr[0][0][b, :n], lists[b][0][0])
+    f_sc, f_id, f_st, f_cnt = c.search_multistage_batch(stages, queries, final_only=True)
+    assert f_id.shape == (3, 5) and f_st.shape == (3, 5, 1) and f_cnt.tolist() == [5, 5, 5]
+    for b in range(3):
+        s1 = dict(zip(lists[b][0][1].tolist(), lists[b][0][0].tolist()))
+        assert f_id[b].tolist() == lists[b][1][1].tolist()
+        np.testing.assert_array_equal(f_st[b, :, 0], np.array([s1[i] for i in f_id[b]], np.float32))
+    # a final page that is absent from an earlier list reports NaN for that stage (cannot happen in a chained search: forced)
+    per_stage = [[q, q] for q in queries]
+    f2 = c.search_multistage_batch(stages, None, stage_queries=per_stage, final_only=True)
+    assert f2[1].tolist() == f_id.tolist()
+    with pytest.raises(ValueError, match="exceeds"):
+        c.search_multistage_batch([("p", False, GC.MAX_K + 1)], queries)
