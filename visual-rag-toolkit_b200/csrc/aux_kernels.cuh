@@ -1106,7 +1106,7 @@ __global__ void sel_init_kernel(SelState* st, int k, int batch) {
 // from local memory. Two slots suffice: a rank can be at most one collective ahead of the slowest peer (completing
 // collective e needs every peer's flag for e, which a peer only sends after it finished e - 1 in stream order).
 // message of this rank (n16 16-byte words) -> every rank's window; publish; wait for all sources. All blocks of the grid
-// must be co-resident (they spin): launched with <= 32 blocks.
+// must be co-resident (they spin): launched with at most 128 blocks of 256 threads (see p2p_blocks).
 __device__ __forceinline__ void p2p_exchange(const P2PWindow& w, const uint4* __restrict__ msg, long long n16, long long n_tail = 0) {
   const int slot = w.epoch & 1;
   const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -1180,7 +1180,7 @@ __global__ void __launch_bounds__(256) p2p_allreduce_max_kernel(const P2PWindow 
 }
 
 // The same two collectives for small messages (<= ll_cap / 2 bytes per rank) as LL lines: send, then poll — no fence, flag or
-// counter. <= 32 blocks: every block both sends and waits, so all of them have to be resident.
+// counter. At most 128 blocks: every block both sends and waits, so all of them have to be resident.
 __global__ void __launch_bounds__(256) p2p_ll_allgather_kernel(const P2PWindow w, const uint4* __restrict__ msg, long long n16,
                                                                uint4* __restrict__ gathered) {
   const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;

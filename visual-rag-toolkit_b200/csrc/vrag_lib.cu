@@ -1670,7 +1670,10 @@ static P2PWindow p2p_window(vrag_corpus* c) {
   w.ll_cap = 2 * kLLMaxPayload;
   return w;
 }
-static unsigned p2p_blocks(long long n16) { return static_cast<unsigned>(std::max<long long>(1, std::min<long long>(32, (n16 + 255) / 256))); }
+// Blocks of an exchange kernel: every block sends AND waits, so all of them must be resident at once — the kernel runs alone
+// on its stream's turn (256 threads, no shared memory: one block per SM always fits), so up to 128 of the 148 SMs; small
+// messages take one block per 256 16-byte words.
+static unsigned p2p_blocks(long long n16) { return static_cast<unsigned>(std::max<long long>(1, std::min<long long>(128, (n16 + 255) / 256))); }
 
 extern "C" int vrag_comm_unique_id(void* out_id128) {
   if (!out_id128) return fail("out_id128 is NULL");
