@@ -329,6 +329,11 @@ def sharded_parity_check(local_rank, rank, world):
         for j, q in enumerate(qs):
             ref = MO.multistage(q, [(glob, True, 100), (pooled, False, 30), (docs, False, 10)])
             same(got[j], ref[2], f"three_stage_batch_q{j}")
+        # longer candidate lists: both candidate stages take the owned-candidates path (count -> compact -> scan -> scatter)
+        got = three.search_server_side_batch(query_embeddings=qs[:3], top_k=20, stage1_k=512, stage2_k=256)
+        for j, q in enumerate(qs[:3]):
+            ref = MO.multistage(q, [(glob, True, 512), (pooled, False, 256), (docs, False, 20)])
+            same(got[j], ref[2], f"three_stage_batch_long_lists_q{j}")
         keep = [i for i in range(P) if payloads[i]["year"] == 2001]
         ref = MO.search_exhaustive(qs[0], [docs[i] for i in keep], 10)
         same(single.search(qs[0], top_k=10, strategy="multi_vector", filter_obj=two.build_filter(year=2001)),

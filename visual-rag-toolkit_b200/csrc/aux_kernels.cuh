@@ -1179,6 +1179,79 @@ __global__ void __launch_bounds__(256) p2p_allreduce_max_kernel(const P2PWindow 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ owned candidates
+// A candidate stage of a BATCH over the sharded corpus receives replicated lists [n_queries][n_cand] of global page ids, of
+// which a rank owns ~1/R. A foreign candidate fetches nothing, but it still costs its slot in the gather's tile pipeline and a
+// chain of dependent id -> page -> row-range loads in the rerank, so the stage stopped getting cheaper with more ranks. These
+// kernels restrict the scan to the rank's own candidates: count per query (+ the maximum over the batch, which the host
+// reads to size the lists), order-preserving compaction to [n_queries][stride] (ids padded with -1, original positions
+// kept), and the scatter of the compact scores back into the -inf-filled [n_queries][n_cand] matrix the exchange expects.
+__global__ void __launch_bounds__(256) own_count_kernel(const long long* __restrict__ ids, int n_cand, long long base, long long n_pages,
+                                                        int* __restrict__ cnt, int* __restrict__ max_cnt) {
+  const long long* row = ids + static_cast<long long>(blockIdx.x) * n_cand;
+  int mine = 0;
+  for (int i = threadIdx.x; i < n_cand; i += 256) {
+    const long long id = row[i];
+    mine += (id >= base && id < base + n_pages) ? 1 : 0;
+  }
+  __shared__ int acc;
+  if (threadIdx.x == 0) acc = 0;
+  __syncthreads();
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&acc, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cnt[blockIdx.x] = acc;
+    atomicMax(max_cnt, acc);
+  }
+}
+__global__ void __launch_bounds__(256) own_compact_kernel(const long long* __restrict__ ids, int n_cand, long long base, long long n_pages,
+                                                          int stride, long long* __restrict__ out_ids, int* __restrict__ out_pos) {
+  __shared__ int wsum[8];
+  __shared__ int running;
+  const long long* row = ids + static_cast<long long>(blockIdx.x) * n_cand;
+  long long* oid = out_ids + static_cast<long long>(blockIdx.x) * stride;
+  int* opos = out_pos + static_cast<long long>(blockIdx.x) * stride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < n_cand; i0 += 256) {
+    const int i = i0 + threadIdx.x;
+    const long long id = i < n_cand ? row[i] : -1;
+    const bool own = id >= base && id < base + n_pages;
+    const unsigned bal = __ballot_sync(0xffffffffu, own);
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    int before = running;
+    for (int w = 0; w < warp; ++w) before += wsum[w];
+    const int pos = before + __popc(bal & ((1u << lane) - 1u));
+    if (own && pos < stride) {
+      oid[pos] = id;
+      opos[pos] = i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += wsum[w];
+      running += tot;
+    }
+    __syncthreads();
+  }
+  for (int j = running + threadIdx.x; j < stride; j += 256) {   // padding: a foreign id scores -inf and is never scattered
+    oid[j] = -1;
+    opos[j] = -1;
+  }
+}
+__global__ void __launch_bounds__(256) own_scatter_kernel(const float* __restrict__ sc_c, const int* __restrict__ pos, int stride, int n_cand,
+                                                          int n_queries, float* __restrict__ raw) {
+  const long long t = blockIdx.x * 256ll + threadIdx.x;
+  if (t >= static_cast<long long>(n_queries) * stride) return;
+  const long long b = t / stride;
+  const int p = pos[t];
+  if (p >= 0) raw[b * n_cand + p] = sc_c[t];
+}
+
 // The same two collectives for small messages (<= ll_cap / 2 bytes per rank) as LL lines: send, then poll — no fence, flag or
 // counter. At most 128 blocks: every block both sends and waits, so all of them have to be resident.
 __global__ void __launch_bounds__(256) p2p_ll_allgather_kernel(const P2PWindow w, const uint4* __restrict__ msg, long long n16,

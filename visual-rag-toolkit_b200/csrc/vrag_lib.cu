@@ -232,6 +232,10 @@ struct CommState {
   void* nccl = nullptr;              // ncclComm_t
   DevBuf<Hit> send, recv;            // packed local lists / gathered lists
   DevBuf<float> raw;                 // batched candidate stages: [n_queries][n_cand] scores (max-all-reduced across shards)
+  DevBuf<float> raw_c;               // the same for the rank's OWN candidates only: [n_queries][max own count]
+  DevBuf<long long> own_ids;         // [n_queries][max own count] compacted candidate ids (-1 padded)
+  DevBuf<int> own_pos;               // their positions in the replicated lists
+  DevBuf<int> own_cnt;               // [n_queries] own counts, [n_queries] = the maximum
   DevBuf<float> m_scores;            // unpacked gathered lists (very long merges)
   DevBuf<long long> m_ids;
   cudaEvent_t ev[2 * kMaxCommEvents] = {nullptr};
@@ -1570,6 +1574,10 @@ static void comm_release(vrag_corpus* c) {
   cm.raw.release();
   cm.m_scores.release();
   cm.m_ids.release();
+  cm.raw_c.release();
+  cm.own_ids.release();
+  cm.own_pos.release();
+  cm.own_cnt.release();
   for (auto& e : cm.ev)
     if (e) { cudaEventDestroy(e); e = nullptr; }
   for (int r = 0; r < kP2PMaxRanks; ++r) {
@@ -2533,12 +2541,55 @@ static int batch_run_sharded(vrag_corpus* c, int n_stages, Store* const* st, con
       TRY(merge_hits(c, c->comm.recv.p, R, nq, k, k, o_sc, o_id, c->d_fcnt.p + nq, stm, nullptr, true));
     } else {
       const int64_t n_cand = ks[s - 1];
-      TRY(batch_prepare_stage(c, *st[s], k, n_cand, false, false, flags[s], s, &plan, &qchunk));
       TRY(c->comm.raw.ensure(static_cast<size_t>(nq) * n_cand));
-      for (int b0 = 0; b0 < nq; b0 += qchunk) {
-        const int qc = std::min(qchunk, nq - b0);
-        TRY(batch_stage_chunk(c, s, *st[s], flags[s], k, d_prev_ids + static_cast<size_t>(b0) * n_cand, n_cand, true, b0, qc,
-                              nullptr, nullptr, stm, PrefilterPlan(), timed, c->comm.raw.p + static_cast<size_t>(b0) * n_cand));
+      // the rank scores only the candidates it OWNS (~1/R of the replicated lists): count them per query, read the largest
+      // count back (one small synchronisation per candidate stage), compact to [nq][m], scan, scatter into the -inf matrix
+      bool compacted = false;
+      if (!env_flag_is("VRAG_OWN_COMPACT", '0') && n_cand >= 64 && n_cand <= (1 << 24)) {
+        TRY(c->comm.own_cnt.ensure(static_cast<size_t>(nq) + 1));
+        CUDA_OK(cudaMemsetAsync(c->comm.own_cnt.p + nq, 0, sizeof(int), stm));
+        own_count_kernel<<<nq, 256, 0, stm>>>(d_prev_ids, static_cast<int>(n_cand), c->page_base, st[s]->n_pages, c->comm.own_cnt.p,
+                                             c->comm.own_cnt.p + nq);
+        c->launches++;
+        CUDA_OK(cudaMemcpyAsync(c->h_flag, c->comm.own_cnt.p + nq, sizeof(int), cudaMemcpyDeviceToHost, stm));
+        CUDA_OK(cudaStreamSynchronize(stm));
+        const int m_max = *c->h_flag;
+        *c->h_flag = 0;
+        const int64_t m = std::min<int64_t>(n_cand, (static_cast<int64_t>(std::max(m_max, 1)) + 31) & ~int64_t(31));
+        if (m * 4 <= n_cand * 3) {   // worth it: at most 3/4 of the list left
+          compacted = true;
+          const long long tot = static_cast<long long>(nq) * n_cand;
+          fill_f32_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, stm>>>(c->comm.raw.p, tot, -INFINITY);
+          c->launches++;
+          if (m_max > 0 && st[s]->total_rows > 0) {
+            TRY(c->comm.own_ids.ensure(static_cast<size_t>(nq) * m));
+            TRY(c->comm.own_pos.ensure(static_cast<size_t>(nq) * m));
+            TRY(c->comm.raw_c.ensure(static_cast<size_t>(nq) * m));
+            own_compact_kernel<<<nq, 256, 0, stm>>>(d_prev_ids, static_cast<int>(n_cand), c->page_base, st[s]->n_pages,
+                                                   static_cast<int>(m), c->comm.own_ids.p, c->comm.own_pos.p);
+            c->launches++;
+            TRY(batch_prepare_stage(c, *st[s], k, m, false, false, flags[s], s, &plan, &qchunk));
+            for (int b0 = 0; b0 < nq; b0 += qchunk) {
+              const int qc = std::min(qchunk, nq - b0);
+              TRY(batch_stage_chunk(c, s, *st[s], flags[s], k, c->comm.own_ids.p + static_cast<size_t>(b0) * m, m, true, b0, qc,
+                                    nullptr, nullptr, stm, PrefilterPlan(), timed, c->comm.raw_c.p + static_cast<size_t>(b0) * m));
+            }
+            const long long tc = static_cast<long long>(nq) * m;
+            own_scatter_kernel<<<static_cast<unsigned>((tc + 255) / 256), 256, 0, stm>>>(c->comm.raw_c.p, c->comm.own_pos.p,
+                                                                                        static_cast<int>(m), static_cast<int>(n_cand), nq,
+                                                                                        c->comm.raw.p);
+            c->launches++;
+          }
+          CUDA_OK(cudaGetLastError());
+        }
+      }
+      if (!compacted) {
+        TRY(batch_prepare_stage(c, *st[s], k, n_cand, false, false, flags[s], s, &plan, &qchunk));
+        for (int b0 = 0; b0 < nq; b0 += qchunk) {
+          const int qc = std::min(qchunk, nq - b0);
+          TRY(batch_stage_chunk(c, s, *st[s], flags[s], k, d_prev_ids + static_cast<size_t>(b0) * n_cand, n_cand, true, b0, qc,
+                                nullptr, nullptr, stm, PrefilterPlan(), timed, c->comm.raw.p + static_cast<size_t>(b0) * n_cand));
+        }
       }
       TRY(comm_allreduce_max(c, c->comm.raw.p, static_cast<int64_t>(nq) * n_cand, stm));
       TRY(launch_topk(c, c->comm.raw.p, d_prev_ids, 0, n_cand, k, o_sc, o_id, nullptr, nullptr, stm, nq, n_cand));
