@@ -818,7 +818,7 @@ def run_multi_extras(corpus, client, two, args, rank, world, barrier, max_over_r
         stages = [("global_pooling", True, 1000), ("experimental_pooling", False, 300), ("initial", False, 100)]
         for _ in range(2):
             corpus.search_multistage_batch(stages, qs, final_only=True)
-        walls, devs, comms = [], [], []
+        walls, devs, comms, begins = [], [], [], []
         for _ in range(5):
             barrier()
             t0 = time.perf_counter()
@@ -826,6 +826,7 @@ def run_multi_extras(corpus, client, two, args, rank, world, barrier, max_over_r
             walls.append(time.perf_counter() - t0)
             devs.append(corpus.last_timing_ms()[0])
             comms.append(corpus.comm_timing_us())
+            begins.append(corpus.comm_offsets_us())
         # every rank must hold the same merged lists
         import torch.distributed as dist
 
@@ -842,6 +843,16 @@ def run_multi_extras(corpus, client, two, args, rank, world, barrier, max_over_r
             "collective_us": {"stage1_allgather_256x1000_hits_4MB": float(med[0]), "stage2_allreduce_max_256x1000": float(med[1]),
                               "stage3_allreduce_max_256x300": float(med[2])},
             "lists_identical_on_all_ranks": same, "transport_peer_memory": bool(corpus.comm_peer_memory())}
+        try:   # device timeline of a batch on rank 0 (us): local work before each collective, the collectives, the tail
+            bg = np.median(np.array(begins), axis=0)
+            tl = {"stage1_local_us": float(bg[0]), "stage1_exchange_us": float(med[0]),
+                  "stage2_merge_and_local_us": float(bg[1] - bg[0] - med[0]), "stage2_exchange_us": float(med[1]),
+                  "stage3_topk_and_local_us": float(bg[2] - bg[1] - med[1]), "stage3_exchange_us": float(med[2]),
+                  "tail_topk_and_result_copy_us": float(1e3 * np.median(devs) - bg[2] - med[2]),
+                  "note": "rank 0, median of 5 batches; exchange times include the wait for the slowest rank"}
+            out["three_stage_batched_sharded"]["device_timeline"] = tl
+        except Exception as e:
+            out["three_stage_batched_sharded"]["device_timeline"] = {"error": repr(e)[:200]}
         for nm in ("initial", "experimental_pooling", "global_pooling"):
             corpus.drop_store(nm)
     except Exception as e:  # an extra must not take the headline line down with it

@@ -351,6 +351,9 @@ int vrag_search_multistage_dev(vrag_corpus_t* c, int n_stages, const char* const
 /* Device time (microseconds, CUDA events) of each collective of the most recent host-facing search on this handle, in
  * issue order; *n receives how many there were (<= capacity written).                                               */
 int vrag_last_comm_timing(vrag_corpus_t* c, float* out_us, int capacity, int* n);
+/* Start of each of those collectives, in microseconds after the start of the search (same events): together with the
+ * durations this is the device timeline of a collective search — local stage work | exchange | local stage work | ...  */
+int vrag_last_comm_offsets(vrag_corpus_t* c, float* out_begin_us, int capacity, int* n);
 
 /* ------------------------------------------------------------------ measurement helpers */
 /* Device-side time (ms, CUDA events on the library stream) of the most recent vrag_search /

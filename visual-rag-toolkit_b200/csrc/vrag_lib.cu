@@ -242,6 +242,7 @@ struct CommState {
   int n_ev = 0;                      // collectives timed in the current host-facing search
   bool timing = false;               // record events around collectives (host-facing searches on the library stream)
   float last_us[kMaxCommEvents] = {0};
+  float last_begin_us[kMaxCommEvents] = {0};   // start of each collective relative to the start of the search (ev0)
   int last_n = 0;
   // peer-memory exchange (aux_kernels.cuh): this rank's window, the peers' windows as mapped here, the collective counter
   bool p2p = false;
@@ -1740,6 +1741,14 @@ extern "C" int vrag_last_comm_timing(vrag_corpus_t* c, float* out_us, int capaci
   return 0;
 }
 
+extern "C" int vrag_last_comm_offsets(vrag_corpus_t* c, float* out_begin_us, int capacity, int* n) {
+  VRAG_LOCK(c);
+  if (!n) return fail("n is NULL");
+  *n = c->comm.last_n;
+  for (int i = 0; i < c->comm.last_n && i < capacity && out_begin_us; ++i) out_begin_us[i] = c->comm.last_begin_us[i];
+  return 0;
+}
+
 static_assert(sizeof(Hit) == sizeof(vrag_hit_t) && sizeof(Hit) == 16, "packed entries are 16 bytes on both sides of the ABI");
 static bool sharded(const vrag_corpus* c) { return c->comm.nranks > 1; }
 // event pair around a collective of a host-facing search (device time of the exchange, reported by vrag_last_comm_timing)
@@ -1756,6 +1765,12 @@ static void comm_collect_timing(vrag_corpus* c) {   // after the stream was sync
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, cm.ev[2 * i], cm.ev[2 * i + 1]);
     cm.last_us[i] = ms * 1e3f;
+    float off = 0.0f;
+    if (cudaEventElapsedTime(&off, c->ev0, cm.ev[2 * i]) != cudaSuccess) {
+      off = 0.0f;
+      cudaGetLastError();
+    }
+    cm.last_begin_us[i] = off * 1e3f;
   }
   cm.n_ev = 0;
 }

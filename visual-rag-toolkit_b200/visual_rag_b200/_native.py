@@ -109,6 +109,7 @@ SIGNATURES = {
     "vrag_allreduce_max_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "vrag_search_multistage_dev": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _u32p, _i32p, C.c_void_p, C.c_int, _i32p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vrag_last_comm_timing": (C.c_int, [C.c_void_p, _f32p, C.c_int, _i32p]),
+    "vrag_last_comm_offsets": (C.c_int, [C.c_void_p, _f32p, C.c_int, _i32p]),
     "vrag_pool_out_rows": (C.c_int, [C.POINTER(PoolSpec), C.c_int64, _i64p]),
     "vrag_pool_page": (C.c_int, [C.c_int, C.POINTER(PoolSpec), C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64, _i64p]),
     "vrag_store_pool": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(PoolSpec), C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]),

@@ -164,6 +164,14 @@ class GpuCorpus:
         N.check(self._lib.vrag_last_comm_timing(self._h, buf, 32, C.byref(n)))
         return [float(buf[i]) for i in range(min(n.value, 32))]
 
+    def comm_offsets_us(self) -> List[float]:
+        """Start of each of those collectives in microseconds after the start of the search: with `comm_timing_us` the device
+        timeline of a collective search (local stage work | exchange | local stage work | ...)."""
+        buf = (C.c_float * 32)()
+        n = C.c_int()
+        N.check(self._lib.vrag_last_comm_offsets(self._h, buf, 32, C.byref(n)))
+        return [float(buf[i]) for i in range(min(n.value, 32))]
+
     # ------------------------------------------------------------------ stores
     def add_store(
         self,
