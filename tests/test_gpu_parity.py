@@ -543,13 +543,14 @@ def test_dense_batched_scan_equals_single_query_scan(corpus, layout, pool):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("layout,pool,k", [("fixed1", True, 1000), ("fixed32", False, 256), ("fixed32", True, 300),
-                                           ("fixed300", False, 500)])
+                                           ("fixed300", False, 500), ("fixed1small", True, 1000), ("fixed32small", False, 256)])
 def test_fused_topk_prefilter_is_exact(corpus, layout, pool, k, monkeypatch):
     """Large dense batched stage: the sample-threshold prefilter (scores never written to HBM) must return exactly
     the lists of the unfiltered path (VRAG_PREFILTER=0), which the tests above pin to the oracle."""
     rng = np.random.default_rng(5)
-    r = int(layout[5:])
-    n = 300_000 if r <= 32 else 270_000
+    small = layout.endswith("small")     # the shard of a strongly scaled corpus (1M pages over 8 GPUs): sample = n / 8
+    r = int(layout[5:].replace("small", ""))
+    n = 130_000 if small else (300_000 if r <= 32 else 270_000)
     corpus.add_synthetic_store("pf", n, fixed_rows=r, seed=11)
     queries = [rng.standard_normal((int(rng.integers(8, 33)), 128)).astype(np.float32) for _ in range(9)]
     stages = [("pf", pool, k)]

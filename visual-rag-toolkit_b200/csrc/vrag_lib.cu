@@ -2295,7 +2295,7 @@ static PrefilterPlan plan_prefilter(const Store& s, int k, int nq, int max_q_eff
   PrefilterPlan pl;
   if (knob_no_prefilter()) return pl;
   const int64_t n = s.n_pages;
-  if (n < (1 << 18) || !dense_batch_covers(nq, max_q_eff, flags)) return pl;
+  if (n < (1 << 16) || !dense_batch_covers(nq, max_q_eff, flags)) return pl;
   int64_t unit_pages = 1, n_units = n;   // sampling granularity
   if (s.packed) {
     const bool pow2 = s.fixed_rows > 0 && (s.fixed_rows & (s.fixed_rows - 1)) == 0 && s.fixed_rows <= 32;
@@ -2303,7 +2303,11 @@ static PrefilterPlan plan_prefilter(const Store& s, int k, int nq, int max_q_eff
     unit_pages = kTileRows / s.fixed_rows;
     n_units = n / unit_pages;
   }
-  const int64_t want = std::max<int64_t>(65536, (32 * n + k - 1) / k);   // sample size: >= 32 expected hits above the k-th score
+  // sample size: >= 32 expected hits above the k-th score, and at least 65536 pages — or an eighth of a small store (the
+  // shards of a strongly scaled corpus: 1M pages over 8 GPUs are 125k per rank; without the filter their stage costs a
+  // [queries][pages] score matrix and a batched radix select)
+  const int64_t floor_s = std::min<int64_t>(65536, std::max<int64_t>(8192, n / 8));
+  const int64_t want = std::max<int64_t>(floor_s, (32 * n + k - 1) / k);
   if (want * 4 > n) return pl;
   if (!s.packed && want * 20 > n) return pl;   // full-token stores: the sample pass re-reads corpus bytes, the score matrix it
                                                // saves is tiny next to them — only worth it when the sample is < 5 % of the scan
