@@ -46,11 +46,13 @@ def infer_grid(num_tokens: int, *, width: Optional[int] = None, height: Optional
 def _payload_size(payload: Optional[Dict[str, Any]]):
     """(width, height) of the image the page's tokens were computed from: the resized size if recorded, else the cropped,
     else the original one (qdrant_recompute_colqwen_pooling_from_initial.py:292-300); (None, None) when unusable."""
-    payload = payload or {}
-    dims = [next((payload[f"{stage}_{axis}"] for stage in ("resized", "cropped", "original") if payload.get(f"{stage}_{axis}")), None)
-            for axis in ("width", "height")]
+    if not payload:
+        return None, None
+    get = payload.get
+    w = get("resized_width") or get("cropped_width") or get("original_width") or None
+    h = get("resized_height") or get("cropped_height") or get("original_height") or None
     try:
-        return tuple(int(v) if v is not None else None for v in dims)
+        return (int(w) if w is not None else None), (int(h) if h is not None else None)
     except (TypeError, ValueError):
         return None, None
 
@@ -62,12 +64,23 @@ def infer_grids(tokens: np.ndarray, payloads: Optional[Sequence[Optional[dict]]]
     n = tokens.shape[0]
     sizes = np.zeros((n, 2), dtype=np.int64)          # 0 = unknown
     if payloads is not None:
+        ws, hs = [0] * n, [0] * n                     # plain lists: a per-row numpy store costs more than the lookup itself
         for p in range(n):
             w, h = _payload_size(payloads[p])
-            if w and h:
-                sizes[p] = (w, h)
-    keys = np.concatenate([tokens[:, None], sizes], axis=1)
-    uniq, inverse = np.unique(keys, axis=0, return_inverse=True)
+            if w and h and w > 0 and h > 0:
+                ws[p], hs[p] = w, h
+        sizes[:, 0], sizes[:, 1] = ws, hs
+    if n == 0:
+        return np.zeros((0, 2), dtype=np.int32)
+    if int(tokens.max()) < (1 << 21) and int(sizes.max()) < (1 << 21) and int(tokens.min()) >= 0 and int(sizes.min()) >= 0:
+        # one 63-bit key per page: a 1-D unique is ~20x faster than the row-wise one (1M pages: 0.1 s instead of 1.9 s —
+        # the device pass this feeds takes 34 ms)
+        packed = (tokens << 42) | (sizes[:, 0] << 21) | sizes[:, 1]
+        uk, inverse = np.unique(packed, return_inverse=True)
+        uniq = np.stack([uk >> 42, (uk >> 21) & ((1 << 21) - 1), uk & ((1 << 21) - 1)], axis=1)
+    else:
+        keys = np.concatenate([tokens[:, None], sizes], axis=1)
+        uniq, inverse = np.unique(keys, axis=0, return_inverse=True)
     table = np.array([infer_grid(int(t), width=int(w) or None, height=int(h) or None) for t, w, h in uniq], dtype=np.int32)
     return table.reshape(-1, 2)[np.asarray(inverse).reshape(-1)]
 
