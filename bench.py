@@ -418,6 +418,33 @@ def sharded_parity_check(local_rank, rank, world):
             c4.close()
         out["sharded_parity"] = True
         out["comm_us_last_search"] = c2.comm_timing_us()
+        # ---- (informational, does not gate sharded_parity) shards of >= 65536 pages: the dense batched stage takes the fused
+        # top-k prefilter on every rank and sends its lists as packed hits; the merged lists must equal those of the score-matrix
+        # path (VRAG_PREFILTER=0), bit for bit
+        try:
+            n5 = 70_000
+            c5 = GpuCorpus(local_rank, page_base=rank * n5)
+            try:
+                c5.comm_init_torch()
+                c5.add_synthetic_store("g", n5, fixed_rows=1, seed=SEED + 31, row_seed_base=rank * n5)
+                qrng = np.random.default_rng(SEED + 32)
+                qb = [qrng.standard_normal((int(qrng.integers(10, 31)), 128)).astype(np.float32) for _ in range(16)]
+                got5 = c5.search_multistage_batch([("g", True, 500)], qb, as_arrays=True)
+                old_env = os.environ.get("VRAG_PREFILTER")
+                os.environ["VRAG_PREFILTER"] = "0"
+                try:
+                    want5 = c5.search_multistage_batch([("g", True, 500)], qb, as_arrays=True)
+                finally:
+                    if old_env is None:
+                        os.environ.pop("VRAG_PREFILTER", None)
+                    else:
+                        os.environ["VRAG_PREFILTER"] = old_env
+                out["sharded_prefilter_equals_matrix_path"] = bool(np.array_equal(got5[0][1], want5[0][1])
+                                                                   and np.array_equal(got5[0][0], want5[0][0]))
+            finally:
+                c5.close()
+        except Exception as e5:  # noqa: BLE001
+            out["sharded_prefilter_equals_matrix_path"] = "error: " + repr(e5)[:200]
     except Exception as e:  # noqa: BLE001
         out["error"] = repr(e)[:400]
     finally:
